@@ -1,0 +1,815 @@
+/*
+ * lr_oracle.c -- fp64 CPU restatement of the LIA_RAL hot path (see lr_oracle.h).
+ * TEST INFRASTRUCTURE ONLY: the checker and the timed CPU baseline, never the product.
+ *
+ * Built twice by oracle/Makefile:
+ *   _build/liblr_oracle.so       -O2, no fast-math      -> the parity oracle
+ *   _build/liblr_oracle_fast.so  -O3 -ffast-math (configure.ac:23) + pthreads
+ *                                (configure.ac:38-47)   -> the timed "--enable-MT" baseline
+ */
+#include "lr_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ------------------------------------------------------------------ helpers */
+typedef void (*range_fn)(size_t begin, size_t end, int tid, void *arg);
+typedef struct {
+  range_fn fn;
+  size_t begin, end;
+  int tid;
+  void *arg;
+} range_job;
+
+static void *range_tramp(void *p) {
+  range_job *j = (range_job *)p;
+  j->fn(j->begin, j->end, j->tid, j->arg);
+  return NULL;
+}
+
+/* Contiguous ranges per thread: the split the reference uses for NDX lines
+ * (AccumulateTVStat.cpp:498-507), speakers (:1989-2023) and components (:881-907). */
+static void parallel_ranges(size_t n, int threads, range_fn fn, void *arg) {
+  if (threads <= 1 || n < 2) {
+    fn(0, n, 0, arg);
+    return;
+  }
+  if ((size_t)threads > n) threads = (int)n;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+  range_job *jobs = (range_job *)malloc(sizeof(range_job) * threads);
+  size_t per = n / threads, rem = n % threads, pos = 0;
+  for (int t = 0; t < threads; t++) {
+    size_t len = per + ((size_t)t < rem ? 1 : 0);
+    jobs[t].fn = fn;
+    jobs[t].begin = pos;
+    jobs[t].end = pos + len;
+    jobs[t].tid = t;
+    jobs[t].arg = arg;
+    pos += len;
+    pthread_create(&th[t], NULL, range_tramp, &jobs[t]);
+  }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
+}
+
+/* ------------------------------------------------------------------ A.1 */
+void orc_gmm_compute_all(int C, int D, const double *cov, double *covinv, double *det,
+                         double *cst) {
+  for (int c = 0; c < C; c++) {
+    double dt = 1.0;
+    for (int i = 0; i < D; i++) {
+      double v = cov[(size_t)c * D + i];
+      dt *= v;
+      covinv[(size_t)c * D + i] = 1.0 / v;
+    }
+    det[c] = dt;
+    cst[c] = 1.0 / (pow(2.0 * M_PI, 0.5 * D) * sqrt(dt));
+  }
+}
+
+/* ------------------------------------------------------------------ A.2 */
+double orc_distrib_lk(int D, const double *x, const double *mean, const double *covinv,
+                      double cst) {
+  double q = 0.0;
+  for (int i = 0; i < D; i++) {
+    double d = x[i] - mean[i];
+    q += d * d * covinv[i];
+  }
+  double lk = cst * exp(-0.5 * q);
+  if (isnan(lk)) lk = ORC_EPS_LK;
+  return lk;
+}
+
+/* ------------------------------------------------------------------ A.3 */
+static double frame_lk_d(int C, int D, const double *w, const double *mean, const double *covinv,
+                         const double *cst, const double *xd, double *p) {
+  double s = 0.0;
+  for (int c = 0; c < C; c++) {
+    double v = w[c] * orc_distrib_lk(D, xd, mean + (size_t)c * D, covinv + (size_t)c * D, cst[c]);
+    p[c] = v;
+    s += v;
+  }
+  return s;
+}
+
+double orc_frame_likelihoods(int C, int D, const double *w, const double *mean,
+                             const double *covinv, const double *cst, const float *x,
+                             double *p) {
+  double xd[1024];
+  for (int i = 0; i < D; i++) xd[i] = (double)x[i];
+  return frame_lk_d(C, D, w, mean, covinv, cst, xd, p);
+}
+
+/* ------------------------------------------------------------------ A.4 */
+typedef struct {
+  int C, D;
+  const double *w, *mean, *covinv, *cst;
+  const float *X;
+  size_t T, ldx, U;
+  const int32_t *frame2row;
+  double *N, *F;
+} bw_args;
+
+/* rows [begin,end): every thread scans all frames and keeps those of its own rows, so
+ * rows of N/F are disjoint between threads exactly like StatTVthread (:376-475). */
+static void bw_range(size_t begin, size_t end, int tid, void *argp) {
+  (void)tid;
+  bw_args *a = (bw_args *)argp;
+  int C = a->C, D = a->D;
+  double *p = (double *)malloc(sizeof(double) * C);
+  double xd[1024];
+  for (size_t t = 0; t < a->T; t++) {
+    int32_t row = a->frame2row ? a->frame2row[t] : 0;
+    if (row < 0 || (size_t)row < begin || (size_t)row >= end) continue;
+    const float *x = a->X + t * a->ldx;
+    for (int i = 0; i < D; i++) xd[i] = (double)x[i];
+    double s = frame_lk_d(C, D, a->w, a->mean, a->covinv, a->cst, xd, p);
+    double *n = a->N + (size_t)row * C;
+    double *f = a->F + (size_t)row * C * D;
+    for (int k = 0; k < C; k++) {
+      double g = p[k] / s; /* getOccVect: normalised occupation */
+      n[k] += g;
+      for (int i = 0; i < D; i++) f[(size_t)k * D + i] += g * xd[i];
+    }
+  }
+  free(p);
+}
+
+void orc_bwstats(int C, int D, const double *w, const double *mean, const double *covinv,
+                 const double *cst, const float *X, size_t T, size_t ldx,
+                 const int32_t *frame2row, size_t U, double *N, double *F, int threads) {
+  bw_args a = {C, D, w, mean, covinv, cst, X, T, ldx, U, frame2row, N, F};
+  parallel_ranges(U, threads, bw_range, &a);
+}
+
+/* ------------------------------------------------------------------ A.5 */
+typedef struct {
+  int C, D;
+  const double *w, *mean, *covinv, *cst;
+  const float *X;
+  size_t ldx;
+  double fw;
+  double *occ, *m1, *m2; /* per-thread accumulators: [threads][...] */
+  double *llk;           /* [threads] */
+  size_t acc_stride;
+} em_args;
+
+static void em_range(size_t begin, size_t end, int tid, void *argp) {
+  em_args *a = (em_args *)argp;
+  int C = a->C, D = a->D;
+  double *occ = a->occ + (size_t)tid * C;
+  double *m1 = a->m1 + (size_t)tid * a->acc_stride;
+  double *m2 = a->m2 + (size_t)tid * a->acc_stride;
+  double *p = (double *)malloc(sizeof(double) * C);
+  double xd[1024], x2[1024];
+  double llk = 0.0;
+  for (size_t t = begin; t < end; t++) {
+    const float *x = a->X + t * a->ldx;
+    for (int i = 0; i < D; i++) {
+      xd[i] = (double)x[i];
+      x2[i] = xd[i] * xd[i];
+    }
+    double s = frame_lk_d(C, D, a->w, a->mean, a->covinv, a->cst, xd, p);
+    llk += log(s);
+    for (int k = 0; k < C; k++) {
+      double g = p[k] / s * a->fw;
+      occ[k] += g;
+      double *a1 = m1 + (size_t)k * D, *a2 = m2 + (size_t)k * D;
+      for (int i = 0; i < D; i++) {
+        a1[i] += g * xd[i];
+        a2[i] += g * x2[i];
+      }
+    }
+  }
+  a->llk[tid] = llk;
+  free(p);
+}
+
+double orc_em_accumulate(int C, int D, const double *w, const double *mean,
+                         const double *covinv, const double *cst, const float *X, size_t T,
+                         size_t ldx, double frame_weight, double *occ, double *m1, double *m2,
+                         double *nframes, int threads) {
+  if (threads < 1) threads = 1;
+  size_t cd = (size_t)C * D;
+  /* per-thread MixtureStat merged at the end with addAccEM (AccumulateStat.cpp:286-292) */
+  double *tocc = (double *)calloc((size_t)threads * C, sizeof(double));
+  double *tm1 = (double *)calloc((size_t)threads * cd, sizeof(double));
+  double *tm2 = (double *)calloc((size_t)threads * cd, sizeof(double));
+  double *tllk = (double *)calloc(threads, sizeof(double));
+  em_args a = {C, D, w, mean, covinv, cst, X, ldx, frame_weight, tocc, tm1, tm2, tllk, cd};
+  parallel_ranges(T, threads, em_range, &a);
+  double llk = 0.0;
+  for (int t = 0; t < threads; t++) {
+    llk += tllk[t];
+    for (int k = 0; k < C; k++) occ[k] += tocc[(size_t)t * C + k];
+    for (size_t i = 0; i < cd; i++) {
+      m1[i] += tm1[(size_t)t * cd + i];
+      m2[i] += tm2[(size_t)t * cd + i];
+    }
+  }
+  if (nframes) *nframes += (double)T * frame_weight;
+  free(tocc);
+  free(tm1);
+  free(tm2);
+  free(tllk);
+  return llk;
+}
+
+void orc_em_get(int C, int D, const double *occ, const double *m1, const double *m2, double *w,
+                double *mean, double *cov) {
+  double tot = 0.0;
+  for (int c = 0; c < C; c++) tot += occ[c];
+  for (int c = 0; c < C; c++) {
+    w[c] = occ[c] / tot;
+    if (occ[c] > 0.0) {
+      for (int i = 0; i < D; i++) {
+        double mu = m1[(size_t)c * D + i] / occ[c];
+        mean[(size_t)c * D + i] = mu;
+        cov[(size_t)c * D + i] = m2[(size_t)c * D + i] / occ[c] - mu * mu;
+      }
+    }
+  }
+}
+
+void orc_variance_control(int C, int D, double *cov, double flooring, double ceiling,
+                          const double *cov_signal, long *n_floor, long *n_ceil) {
+  long nf = 0, nc = 0;
+  for (int c = 0; c < C; c++)
+    for (int v = 0; v < D; v++) {
+      double x = cov[(size_t)c * D + v];
+      if (x <= flooring * cov_signal[v]) {
+        x = flooring * cov_signal[v];
+        nf++;
+      }
+      if (x >= ceiling * cov_signal[v]) {
+        x = ceiling * cov_signal[v];
+        nc++;
+      }
+      cov[(size_t)c * D + v] = x;
+    }
+  if (n_floor) *n_floor = nf;
+  if (n_ceil) *n_ceil = nc;
+}
+
+double orc_set_it_parameter(double begin, double end, int nb_it, int it) {
+  if (nb_it < 2) return begin;
+  double step = (begin - end) / ((double)nb_it - 1.0);
+  return begin - step * it;
+}
+
+void orc_mean_cov(int D, const float *X, size_t T, size_t ldx, double *mean, double *cov) {
+  /* FrameAccGD: sum x, sum x^2, count; mean = sx/n ; cov = sxx/n - mean^2 */
+  for (int i = 0; i < D; i++) mean[i] = cov[i] = 0.0;
+  for (size_t t = 0; t < T; t++)
+    for (int i = 0; i < D; i++) {
+      double v = (double)X[t * ldx + i];
+      mean[i] += v;
+      cov[i] += v * v;
+    }
+  for (int i = 0; i < D; i++) {
+    mean[i] /= (double)T;
+    cov[i] = cov[i] / (double)T - mean[i] * mean[i];
+  }
+}
+
+/* ------------------------------------------------------------------ A.6 */
+static double clamp_llk(double lk, double min_llk, double max_llk) {
+  /* restated in TopGauss.cpp:255-260 */
+  double l = log(lk);
+  if (isnan(l)) return min_llk;
+  if (l <= min_llk) return min_llk;
+  if (l >= max_llk) return max_llk;
+  return l;
+}
+
+void orc_llk_determine_top(int C, int D, const double *w, const double *mean,
+                           const double *covinv, const double *cst, const float *X, size_t T,
+                           size_t ldx, int K, int complete, double min_llk, double max_llk,
+                           double *llk, uint32_t *idx, double *top_lk, double *rest_lk,
+                           double *rest_w) {
+  double *p = (double *)malloc(sizeof(double) * C);
+  char *used = (char *)malloc(C);
+  if (K > C) K = C;
+  for (size_t t = 0; t < T; t++) {
+    double s = orc_frame_likelihoods(C, D, w, mean, covinv, cst, X + t * ldx, p);
+    memset(used, 0, C);
+    double top_sum = 0.0, top_w = 0.0;
+    /* descending sort, ties -> lowest index (selection keeps it O(C*K)) */
+    for (int k = 0; k < K; k++) {
+      int best = -1;
+      for (int c = 0; c < C; c++)
+        if (!used[c] && (best < 0 || p[c] > p[best])) best = c;
+      used[best] = 1;
+      idx[t * K + k] = (uint32_t)best;
+      if (top_lk) top_lk[t * K + k] = p[best];
+      top_sum += p[best];
+      top_w += w[best];
+    }
+    double rest = 0.0;
+    for (int c = 0; c < C; c++)
+      if (!used[c]) rest += p[c];
+    if (rest_lk) rest_lk[t] = rest;
+    if (rest_w) rest_w[t] = 1.0 - top_w;
+    (void)s;
+    double lk = complete ? top_sum + rest : top_sum;
+    if (llk) llk[t] = clamp_llk(lk, min_llk, max_llk);
+  }
+  free(p);
+  free(used);
+}
+
+void orc_llk_use_top(int C, int D, const double *w, const double *mean, const double *covinv,
+                     const double *cst, const float *X, size_t T, size_t ldx, int K,
+                     const uint32_t *idx, const double *rest_lk, int complete, double min_llk,
+                     double max_llk, double *llk) {
+  (void)C;
+  double xd[1024];
+  for (size_t t = 0; t < T; t++) {
+    const float *x = X + t * ldx;
+    for (int i = 0; i < D; i++) xd[i] = (double)x[i];
+    double lk = 0.0;
+    for (int k = 0; k < K; k++) {
+      uint32_t c = idx[t * K + k];
+      lk += w[c] * orc_distrib_lk(D, xd, mean + (size_t)c * D, covinv + (size_t)c * D, cst[c]);
+    }
+    if (complete && rest_lk) lk += rest_lk[t];
+    llk[t] = clamp_llk(lk, min_llk, max_llk);
+  }
+}
+
+void orc_llk_all(int C, int D, const double *w, const double *mean, const double *covinv,
+                 const double *cst, const float *X, size_t T, size_t ldx, double min_llk,
+                 double max_llk, double *llk) {
+  double *p = (double *)malloc(sizeof(double) * C);
+  for (size_t t = 0; t < T; t++) {
+    double s = orc_frame_likelihoods(C, D, w, mean, covinv, cst, X + t * ldx, p);
+    llk[t] = clamp_llk(s, min_llk, max_llk);
+  }
+  free(p);
+}
+
+/* ------------------------------------------------------------------ dense helpers */
+int orc_invert(int n, const double *a, double *inv) {
+  /* exact dense inverse (Gauss-Jordan, partial pivoting); DoubleSquareMatrix::invert [ALIZE] */
+  double *m = (double *)malloc(sizeof(double) * n * n);
+  memcpy(m, a, sizeof(double) * n * n);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) inv[(size_t)i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int col = 0; col < n; col++) {
+    int piv = col;
+    double best = fabs(m[(size_t)col * n + col]);
+    for (int r = col + 1; r < n; r++) {
+      double v = fabs(m[(size_t)r * n + col]);
+      if (v > best) {
+        best = v;
+        piv = r;
+      }
+    }
+    if (best == 0.0) {
+      free(m);
+      return -1;
+    }
+    if (piv != col)
+      for (int j = 0; j < n; j++) {
+        double t = m[(size_t)col * n + j];
+        m[(size_t)col * n + j] = m[(size_t)piv * n + j];
+        m[(size_t)piv * n + j] = t;
+        t = inv[(size_t)col * n + j];
+        inv[(size_t)col * n + j] = inv[(size_t)piv * n + j];
+        inv[(size_t)piv * n + j] = t;
+      }
+    double d = 1.0 / m[(size_t)col * n + col];
+    for (int j = 0; j < n; j++) {
+      m[(size_t)col * n + j] *= d;
+      inv[(size_t)col * n + j] *= d;
+    }
+    for (int r = 0; r < n; r++) {
+      if (r == col) continue;
+      double f = m[(size_t)r * n + col];
+      if (f == 0.0) continue;
+      double *mr = m + (size_t)r * n, *mc = m + (size_t)col * n;
+      double *ir = inv + (size_t)r * n, *ic = inv + (size_t)col * n;
+      for (int j = 0; j < n; j++) {
+        mr[j] -= f * mc[j];
+        ir[j] -= f * ic[j];
+      }
+    }
+  }
+  free(m);
+  return 0;
+}
+
+int orc_upper_cholesky(int n, const double *a, double *u) {
+  /* a = u^T u with u upper triangular; DoubleSquareMatrix::upperCholesky [ALIZE] */
+  memset(u, 0, sizeof(double) * n * n);
+  for (int i = 0; i < n; i++) {
+    for (int j = i; j < n; j++) {
+      double s = a[(size_t)i * n + j];
+      for (int k = 0; k < i; k++) s -= u[(size_t)k * n + i] * u[(size_t)k * n + j];
+      if (i == j) {
+        if (s <= 0.0) return -1;
+        u[(size_t)i * n + i] = sqrt(s);
+      } else {
+        u[(size_t)i * n + j] = s / u[(size_t)i * n + i];
+      }
+    }
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ A.7 */
+void orc_tv_subtract_m(size_t U, int C, int D, const double *N, const double *ubm_mean,
+                       double *F) {
+  size_t sv = (size_t)C * D;
+  for (size_t s = 0; s < U; s++)
+    for (int i = 0; i < C; i++)
+      for (int j = 0; j < D; j++)
+        F[s * sv + (size_t)i * D + j] -= ubm_mean[(size_t)i * D + j] * N[s * C + i];
+}
+
+typedef struct {
+  int C, D, R;
+  const double *T, *invvar;
+  double *tett;
+} tett_args;
+
+static void tett_range(size_t begin, size_t end, int tid, void *argp) {
+  (void)tid;
+  tett_args *a = (tett_args *)argp;
+  int D = a->D, R = a->R;
+  size_t sv = (size_t)a->C * D;
+  for (size_t d = begin; d < end; d++) {
+    double *o = a->tett + d * (size_t)R * R;
+    for (int i = 0; i < R; i++)
+      for (int j = 0; j <= i; j++) {
+        double s = 0.0;
+        const double *ti = a->T + (size_t)i * sv + d * D;
+        const double *tj = a->T + (size_t)j * sv + d * D;
+        const double *e = a->invvar + d * D;
+        for (int k = 0; k < D; k++) s += ti[k] * e[k] * tj[k];
+        o[(size_t)i * R + j] = s;
+      }
+    for (int i = 0; i < R; i++)
+      for (int j = i + 1; j < R; j++) o[(size_t)i * R + j] = o[(size_t)j * R + i];
+  }
+}
+
+void orc_tv_tett(int C, int D, int R, const double *T, const double *invvar, double *tett,
+                 int threads) {
+  tett_args a = {C, D, R, T, invvar, tett};
+  parallel_ranges((size_t)C, threads, tett_range, &a);
+}
+
+typedef struct {
+  size_t U;
+  int C, D, R, threads;
+  const double *N, *F, *T, *invvar, *tett;
+  double *W;
+  /* E-step extras (NULL for plain i-vector extraction); per-thread copies */
+  double *A, *Cmx, *Rm, *r, *meanW;
+} iv_args;
+
+/* Posterior of one utterance: L = I + sum_c N_c TETt_c, Linv = L^-1, aux, y = Linv aux */
+static void iv_one(const iv_args *a, size_t spk, double *L, double *Linv, double *aux,
+                   double *y) {
+  int C = a->C, D = a->D, R = a->R;
+  size_t sv = (size_t)C * D;
+  memset(L, 0, sizeof(double) * R * R);
+  for (int i = 0; i < R; i++) L[(size_t)i * R + i] = 1.0;
+  for (int dis = 0; dis < C; dis++) {
+    const double *te = a->tett + (size_t)dis * R * R;
+    double n = a->N[spk * C + dis];
+    for (int i = 0; i < R; i++)
+      for (int j = 0; j <= i; j++) L[(size_t)i * R + j] += te[(size_t)i * R + j] * n;
+  }
+  for (int i = 0; i < R; i++)
+    for (int j = i + 1; j < R; j++) L[(size_t)i * R + j] = L[(size_t)j * R + i];
+  orc_invert(R, L, Linv);
+  const double *f = a->F + spk * sv;
+  for (int i = 0; i < R; i++) {
+    double s = 0.0;
+    const double *ti = a->T + (size_t)i * sv;
+    for (size_t k = 0; k < sv; k++) s += f[k] * a->invvar[k] * ti[k];
+    aux[i] = s;
+  }
+  for (int i = 0; i < R; i++) {
+    double s = 0.0;
+    for (int k = 0; k < R; k++) s += aux[k] * Linv[(size_t)i * R + k];
+    y[i] = s;
+  }
+}
+
+static void iv_range(size_t begin, size_t end, int tid, void *argp) {
+  iv_args *a = (iv_args *)argp;
+  int C = a->C, D = a->D, R = a->R;
+  size_t sv = (size_t)C * D, rr = (size_t)R * R;
+  double *L = (double *)malloc(sizeof(double) * rr);
+  double *Linv = (double *)malloc(sizeof(double) * rr);
+  double *aux = (double *)malloc(sizeof(double) * R);
+  double *A = a->A ? a->A + (size_t)tid * C * rr : NULL;
+  double *Cmx = a->A ? a->Cmx + (size_t)tid * R * sv : NULL;
+  double *Rm = a->A ? a->Rm + (size_t)tid * rr : NULL;
+  double *r = a->A ? a->r + (size_t)tid * R : NULL;
+  double *meanW = a->A ? a->meanW + (size_t)tid * R : NULL;
+  for (size_t spk = begin; spk < end; spk++) {
+    double *y = a->W + spk * R;
+    iv_one(a, spk, L, Linv, aux, y);
+    if (!A) continue;
+    /* E-step accumulators, AccumulateTVStat.cpp:1762-1788 */
+    for (int k = 0; k < R; k++) meanW[k] += y[k];
+    for (int i = 0; i < R; i++) {
+      for (int j = 0; j < R; j++) {
+        Linv[(size_t)i * R + j] += y[i] * y[j];
+        Rm[(size_t)i * R + j] += Linv[(size_t)i * R + j];
+      }
+      r[i] += y[i];
+    }
+    for (int dis = 0; dis < C; dis++) {
+      double n = a->N[spk * C + dis];
+      double *Ad = A + (size_t)dis * rr;
+      for (size_t e = 0; e < rr; e++) Ad[e] += Linv[e] * n;
+    }
+    const double *f = a->F + spk * sv;
+    for (int i = 0; i < R; i++) {
+      double yi = y[i];
+      double *ci = Cmx + (size_t)i * sv;
+      for (size_t j = 0; j < sv; j++) ci[j] += yi * f[j];
+    }
+  }
+  free(L);
+  free(Linv);
+  free(aux);
+}
+
+void orc_tv_ivectors(size_t U, int C, int D, int R, const double *N, const double *F,
+                     const double *T, const double *invvar, const double *tett, double *W,
+                     int threads) {
+  iv_args a = {U, C, D, R, threads, N, F, T, invvar, tett, W, NULL, NULL, NULL, NULL, NULL};
+  memset(W, 0, sizeof(double) * U * R);
+  parallel_ranges(U, threads, iv_range, &a);
+}
+
+void orc_tv_estep(size_t U, int C, int D, int R, const double *N, const double *F,
+                  const double *T, const double *invvar, const double *tett, double *W,
+                  double *A, double *Cmx, double *Rm, double *r, double *meanW, int threads) {
+  if (threads < 1) threads = 1;
+  if ((size_t)threads > U) threads = (int)(U ? U : 1);
+  size_t sv = (size_t)C * D, rr = (size_t)R * R;
+  /* the reference serialises the A / C updates behind two mutexes (:1920-1937); per-thread
+   * partials summed at the end are arithmetically the same reduction */
+  double *tA = (double *)calloc((size_t)threads * C * rr, sizeof(double));
+  double *tC = (double *)calloc((size_t)threads * R * sv, sizeof(double));
+  double *tR = (double *)calloc((size_t)threads * rr, sizeof(double));
+  double *tr = (double *)calloc((size_t)threads * R, sizeof(double));
+  double *tm = (double *)calloc((size_t)threads * R, sizeof(double));
+  iv_args a = {U, C, D, R, threads, N, F, T, invvar, tett, W, tA, tC, tR, tr, tm};
+  memset(W, 0, sizeof(double) * U * R);
+  memset(A, 0, sizeof(double) * C * rr); /* _A.setAllValues(0.0) :1719 */
+  memset(Rm, 0, sizeof(double) * rr);
+  memset(r, 0, sizeof(double) * R);
+  memset(meanW, 0, sizeof(double) * R);
+  parallel_ranges(U, threads, iv_range, &a);
+  for (int t = 0; t < threads; t++) {
+    for (size_t e = 0; e < (size_t)C * rr; e++) A[e] += tA[(size_t)t * C * rr + e];
+    for (size_t e = 0; e < (size_t)R * sv; e++) Cmx[e] += tC[(size_t)t * R * sv + e];
+    for (size_t e = 0; e < rr; e++) Rm[e] += tR[(size_t)t * rr + e];
+    for (int e = 0; e < R; e++) {
+      r[e] += tr[(size_t)t * R + e];
+      meanW[e] += tm[(size_t)t * R + e];
+    }
+  }
+  for (int k = 0; k < R; k++) meanW[k] /= (double)U; /* :1792-1794, _n_speakers */
+  free(tA);
+  free(tC);
+  free(tR);
+  free(tr);
+  free(tm);
+}
+
+void orc_tv_mstep(int C, int D, int R, const double *A, const double *Cmx, double *T) {
+  size_t sv = (size_t)C * D, rr = (size_t)R * R;
+  double *invA = (double *)malloc(sizeof(double) * rr);
+  for (int d = 0; d < C; d++) {
+    orc_invert(R, A + (size_t)d * rr, invA);
+    for (int i = 0; i < R; i++)
+      for (int j = 0; j < D; j++) {
+        double s = 0.0;
+        for (int k = 0; k < R; k++)
+          s += invA[(size_t)i * R + k] * Cmx[(size_t)k * sv + (size_t)d * D + j];
+        T[(size_t)i * sv + (size_t)d * D + j] = s;
+      }
+  }
+  free(invA);
+}
+
+int orc_tv_mindiv(int C, int D, int R, double n_sessions, double *Rm, double *r,
+                  const double *meanW, double *ubm_mean, double *T) {
+  size_t sv = (size_t)C * D;
+  for (int i = 0; i < R; i++) r[i] /= n_sessions;
+  for (int i = 0; i < R; i++)
+    for (int j = 0; j < R; j++)
+      Rm[(size_t)i * R + j] = Rm[(size_t)i * R + j] / n_sessions - r[i] * r[j];
+  double *Ch = (double *)malloc(sizeof(double) * R * R);
+  if (orc_upper_cholesky(R, Rm, Ch) != 0) {
+    free(Ch);
+    return -1;
+  }
+  for (size_t j = 0; j < sv; j++) {
+    double s = ubm_mean[j];
+    for (int k = 0; k < R; k++) s += meanW[k] * T[(size_t)k * sv + j];
+    ubm_mean[j] = s;
+  }
+  double *tmp = (double *)calloc((size_t)R * sv, sizeof(double));
+  for (int i = 0; i < R; i++)
+    for (int k = 0; k < R; k++) {
+      double c = Ch[(size_t)i * R + k];
+      if (c == 0.0) continue;
+      const double *tk = T + (size_t)k * sv;
+      double *o = tmp + (size_t)i * sv;
+      for (size_t j = 0; j < sv; j++) o[j] += c * tk[j];
+    }
+  memcpy(T, tmp, sizeof(double) * R * sv);
+  free(tmp);
+  free(Ch);
+  return 0;
+}
+
+void orc_tv_orthonormalize(int R, size_t sv, double *T) {
+  /* classical Gram-Schmidt over rows, projections taken against the ORIGINAL row */
+  double *Q = (double *)calloc((size_t)R * sv, sizeof(double));
+  double *v = (double *)malloc(sizeof(double) * sv);
+  for (int j = 0; j < R; j++) {
+    const double *tj = T + (size_t)j * sv;
+    memcpy(v, tj, sizeof(double) * sv);
+    for (int i = 0; i < j; i++) {
+      const double *qi = Q + (size_t)i * sv;
+      double rij = 0.0;
+      for (size_t k = 0; k < sv; k++) rij += qi[k] * tj[k];
+      for (size_t k = 0; k < sv; k++) v[k] -= rij * qi[k];
+    }
+    double nv = 0.0;
+    for (size_t k = 0; k < sv; k++) nv += v[k] * v[k];
+    nv = sqrt(nv);
+    double *qj = Q + (size_t)j * sv;
+    if (nv == 0.0)
+      for (size_t k = 0; k < sv; k++) qj[k] = 0.0;
+    else
+      for (size_t k = 0; k < sv; k++) qj[k] = v[k] / nv;
+  }
+  memcpy(T, Q, sizeof(double) * R * sv);
+  free(Q);
+  free(v);
+}
+
+/* ------------------------------------------------------------------ A.9 */
+static void matmul(int m, int k, int n, const double *a, const double *b, double *c) {
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) c[(size_t)i * n + j] = 0.0;
+  for (int i = 0; i < m; i++)
+    for (int l = 0; l < k; l++) {
+      double v = a[(size_t)i * k + l];
+      for (int j = 0; j < n; j++) c[(size_t)i * n + j] += v * b[(size_t)l * n + j];
+    }
+}
+
+static double logdet_via_chol(int n, const double *k) {
+  /* alpha = 2 * sum log diag(chol(K)) (PldaTools.cpp:4511-4516) */
+  double *u = (double *)malloc(sizeof(double) * n * n);
+  double s = 0.0;
+  if (orc_upper_cholesky(n, k, u) == 0)
+    for (int i = 0; i < n; i++) s += log(u[(size_t)i * n + i]);
+  else
+    s = NAN;
+  free(u);
+  return 2.0 * s;
+}
+
+static void k_of(int r, double n, const double *phi, double *K) {
+  double *tmp = (double *)malloc(sizeof(double) * r * r);
+  for (int i = 0; i < r; i++)
+    for (int j = 0; j < r; j++) tmp[(size_t)i * r + j] = n * phi[(size_t)i * r + j] + (i == j);
+  orc_invert(r, tmp, K);
+  free(tmp);
+}
+
+static double quad_form(int r, const double *K, const double *v) {
+  double s = 0.0;
+  for (int i = 0; i < r; i++) {
+    double t = 0.0;
+    for (int j = 0; j < r; j++) t += K[(size_t)i * r + j] * v[j];
+    s += v[i] * t;
+  }
+  return s;
+}
+
+int orc_plda_native_scoring(int d, int rF, int rG, const double *F, const double *G,
+                            const double *Sigma, const double *models, size_t n_enrol,
+                            const int32_t *model_of, size_t n_models, const double *segments,
+                            size_t n_test, double *scores) {
+  /* preComputation (PldaTools.cpp:2950-2972) */
+  double *iS = (double *)malloc(sizeof(double) * d * d);
+  if (orc_invert(d, Sigma, iS) != 0) {
+    free(iS);
+    return -1;
+  }
+  double *Ft = (double *)malloc(sizeof(double) * rF * d); /* F^T */
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < rF; j++) Ft[(size_t)j * d + i] = F[(size_t)i * rF + j];
+  double *Ftw = (double *)malloc(sizeof(double) * rF * d);
+  matmul(rF, d, d, Ft, iS, Ftw);
+  double *FTJ = (double *)malloc(sizeof(double) * rF * d);
+  memcpy(FTJ, Ftw, sizeof(double) * rF * d);
+  if (rG > 0) {
+    double *Gt = (double *)malloc(sizeof(double) * rG * d);
+    for (int i = 0; i < d; i++)
+      for (int j = 0; j < rG; j++) Gt[(size_t)j * d + i] = G[(size_t)i * rG + j];
+    double *Gtw = (double *)malloc(sizeof(double) * rG * d);
+    matmul(rG, d, d, Gt, iS, Gtw);
+    double *GtwG = (double *)malloc(sizeof(double) * rG * rG);
+    matmul(rG, d, rG, Gtw, G, GtwG);
+    for (int i = 0; i < rG; i++) GtwG[(size_t)i * rG + i] += 1.0;
+    double *iGG = (double *)malloc(sizeof(double) * rG * rG);
+    orc_invert(rG, GtwG, iGG);
+    double *FtwG = (double *)malloc(sizeof(double) * rF * rG);
+    matmul(rF, d, rG, Ftw, G, FtwG);
+    double *t1 = (double *)malloc(sizeof(double) * rF * rG);
+    matmul(rF, rG, rG, FtwG, iGG, t1);
+    double *t2 = (double *)malloc(sizeof(double) * rF * d);
+    matmul(rF, rG, d, t1, Gtw, t2);
+    for (size_t e = 0; e < (size_t)rF * d; e++) FTJ[e] -= t2[e];
+    free(Gt);
+    free(Gtw);
+    free(GtwG);
+    free(iGG);
+    free(FtwG);
+    free(t1);
+    free(t2);
+  }
+  double *phi = (double *)malloc(sizeof(double) * rF * rF); /* FTJF */
+  matmul(rF, d, rF, FTJ, F, phi);
+  /* rotateLeft (:3770-3790): project models and segments, rF x n */
+  double *pm = (double *)malloc(sizeof(double) * rF * n_enrol);
+  double *ps = (double *)malloc(sizeof(double) * rF * n_test);
+  matmul(rF, d, (int)n_enrol, FTJ, models, pm);
+  matmul(rF, d, (int)n_test, FTJ, segments, ps);
+  double *K1 = (double *)malloc(sizeof(double) * rF * rF);
+  k_of(rF, 1.0, phi, K1);
+  double alpha1 = logdet_via_chol(rF, K1);
+  /* pldaScoringUnThreaded (:4186-4271) */
+  double *KL = (double *)malloc(sizeof(double) * rF * rF);
+  double *KL1 = (double *)malloc(sizeof(double) * rF * rF);
+  double *m = (double *)malloc(sizeof(double) * rF);
+  double *v = (double *)malloc(sizeof(double) * rF);
+  double *s1 = (double *)malloc(sizeof(double) * n_test);
+  for (size_t i = 0; i < n_test; i++) {
+    for (int k = 0; k < rF; k++) v[k] = ps[(size_t)k * n_test + i];
+    s1[i] = quad_form(rF, K1, v);
+  }
+  size_t sess = 0;
+  long cur_nb = 0;
+  double constant = 0.0;
+  for (size_t mod = 0; mod < n_models; mod++) {
+    for (int k = 0; k < rF; k++) m[k] = 0.0;
+    long nb = 0;
+    int32_t id = model_of[sess];
+    while (sess < n_enrol && model_of[sess] == id) {
+      for (int k = 0; k < rF; k++) m[k] += pm[(size_t)k * n_enrol + sess];
+      nb++;
+      sess++;
+    }
+    if (nb != cur_nb) {
+      cur_nb = nb;
+      k_of(rF, (double)nb, phi, KL);
+      k_of(rF, (double)nb + 1.0, phi, KL1);
+      double aL = logdet_via_chol(rF, KL), aL1 = logdet_via_chol(rF, KL1);
+      constant = (aL1 - aL - alpha1) / 2.0;
+    }
+    double s2 = quad_form(rF, KL, m);
+    for (size_t i = 0; i < n_test; i++) {
+      for (int k = 0; k < rF; k++) v[k] = ps[(size_t)k * n_test + i] + m[k];
+      double s3 = quad_form(rF, KL1, v);
+      scores[mod * n_test + i] = (s3 - s2 - s1[i]) / 2.0 + constant;
+    }
+  }
+  free(iS);
+  free(Ft);
+  free(Ftw);
+  free(FTJ);
+  free(phi);
+  free(pm);
+  free(ps);
+  free(K1);
+  free(KL);
+  free(KL1);
+  free(m);
+  free(v);
+  free(s1);
+  return 0;
+}

@@ -1,0 +1,69 @@
+"""Pins the CPU oracle against the reference's own intact fixtures."""
+import os
+
+import numpy as np
+
+from oracle import np_oracle
+
+
+def _load_tok(golden_dir):
+    return np.load(os.path.join(golden_dir, "gmmtokenizer.npz"))
+
+
+def test_gmmtokenizer_argmax_stream(oracle, golden_dir):
+    """LIA_Utils/GmmTokenizer/test/test1.sym.ref: best Gaussian per selected frame
+    (GmmTokenizer.cpp:99-104 -> DETERMINE_TOP_DISTRIBS, v[0].idx)."""
+    z = _load_tok(golden_dir)
+    g = oracle.gmm(z["w"], z["mean"], 1.0 / z["covinv"])
+    # the RAW file carries its own cst/det; the reference scores with the stored cst
+    g.cst[:] = z["cst"]
+    X = np.ascontiguousarray(z["frames"][z["selected"]], dtype=np.float32)
+    _, idx, _, _, _ = oracle.llk_determine_top(g, X, K=6)
+    best = idx[:, 0].astype(np.int64)
+    collapsed = [best[0]] + [b for a, b in zip(best[:-1], best[1:]) if a != b]
+    assert collapsed == list(z["sym_ref"])
+
+
+def test_gmmtokenizer_top20_confusion(oracle, golden_dir):
+    """mce_matrix.mat.ref: mce(best, v[i].idx)++ for i<20 (GmmTokenizer.cpp:69-76): pins the
+    top-20 index SET of every frame."""
+    z = _load_tok(golden_dir)
+    g = oracle.gmm(z["w"], z["mean"], 1.0 / z["covinv"])
+    X = np.ascontiguousarray(z["frames"][z["selected"]], dtype=np.float32)
+    K = int(z["mce_topk"])
+    _, idx, _, _, _ = oracle.llk_determine_top(g, X, K=K)
+    mce = np.zeros_like(z["mce_ref"])
+    for t in range(idx.shape[0]):
+        for i in range(K):
+            mce[idx[t, 0], idx[t, i]] += 1
+    assert (mce == z["mce_ref"]).all()
+
+
+def test_compute_all_identity_xml(oracle, golden_dir):
+    """TrainWorld/test/wld.validate: det = prod(1/covInv), cst = 1/((2pi)^(D/2) sqrt(det))."""
+    z = np.load(os.path.join(golden_dir, "wld_validate.npz"))
+    g = oracle.gmm(z["w"], z["mean"], 1.0 / z["covinv"])
+    assert np.allclose(g.det, z["det"], rtol=1e-12)
+    assert np.allclose(g.cst, z["cst"], rtol=1e-12)
+    assert np.allclose(g.covinv, z["covinv"], rtol=1e-14)
+
+
+def test_client_equals_world_llr_zero(oracle, golden_dir):
+    """ComputeTest/test/test1.validate.res: model test2 is a byte copy of wld and scores
+    -5.5e-16 / 1.3e-15 under top-10 COMPLETE => client == world must give |LLR| < 1e-14."""
+    z = _load_tok(golden_dir)
+    g = oracle.gmm(z["w"], z["mean"], 1.0 / z["covinv"])
+    X = np.ascontiguousarray(z["frames"][z["selected"]], dtype=np.float32)
+    llkw, idx, _, rest, _ = oracle.llk_determine_top(g, X, K=10, complete=True)
+    llkc = oracle.llk_use_top(g, X, idx, rest, complete=True)
+    assert abs(llkc.mean() - llkw.mean()) < 1e-14
+
+
+def test_numpy_twin_agrees_on_fixture(oracle, golden_dir):
+    z = _load_tok(golden_dir)
+    cov = 1.0 / z["covinv"]
+    g = oracle.gmm(z["w"], z["mean"], cov)
+    X = np.ascontiguousarray(z["frames"], dtype=np.float32)
+    llk = oracle.llk_all(g, X)
+    _, llk_np = np_oracle.posteriors(z["w"], z["mean"], cov, X)
+    assert np.allclose(llk, llk_np, rtol=1e-12, atol=1e-10)
