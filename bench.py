@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GMM-LLK + statistics hot path (BASELINE.json).
+
+Workload (configs[1]): TrainWorld EM on a 2048-component / 60-dim diagonal UBM, 10 M synthetic
+frames per GPU.  One "step" = one EM iteration over all resident frames: per-frame log-likelihood
++ posteriors + occ / sum g x / sum g x^2 accumulation (accumulateStatEM), the statistics
+all-reduce when N > 1 (emAcc.addAccEM), then getEM + varianceControl on the device.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames T] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+C, D = 2048, 60
+METRIC = "frames/sec GMM-LLK+BW-stats (2048c/60d)"
+UNIT = "frames/s"
+FLOP_PER_FRAME_EM = 8 * C * D   # 4CD Mahalanobis + 2CD (g x) + 2CD (g x^2)
+FLOP_PER_FRAME_BW = 6 * C * D
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(bf16=float(j["bf16_tflops_sustained"]), hbm=float(j["hbm_gbs"]), src="measured")
+    return dict(bf16=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def synth_model():
+    from lia_ral_b200 import synth
+    w, mean, cov = synth.make_ubm(C, D, seed=1)
+    start = synth.perturb_ubm(w, mean, cov, seed=3, frac=1.0, scale=0.3)
+    return (w, mean, cov), start
+
+
+def make_frames_gpu(torch, w, mean, cov, T, seed, device):
+    """component ~ weights, x = mu_c + sigma_c N(0,1), float32 [T, 60] generated on the device."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    wt = torch.tensor(w, device=device, dtype=torch.float32)
+    mu = torch.tensor(mean, device=device, dtype=torch.float32)
+    sd = torch.tensor(np.sqrt(cov), device=device, dtype=torch.float32)
+    X = torch.empty((T, D), device=device, dtype=torch.float32)
+    step = 1 << 20
+    for s in range(0, T, step):
+        n = min(step, T - s)
+        comp = torch.multinomial(wt, n, replacement=True, generator=g)
+        X[s:s + n] = mu[comp] + sd[comp] * torch.randn((n, D), device=device, generator=g)
+    return X
+
+
+def cpu_baseline(sample_frames=None, budget_s=15.0):
+    """The oracle's -O3 -ffast-math + pthreads build (the reference's --enable-MT path restated:
+    the reference itself cannot be compiled, alize-core is absent) on the host cores."""
+    from lia_ral_b200 import synth
+    from oracle.ffi import Oracle
+    orc = Oracle(fast=True)
+    cores = os.cpu_count() or 1
+    _, (w, mean, cov) = synth_model()
+    g = orc.gmm(w, mean, cov)
+    probe = 512 * cores
+    X = synth.make_frames(w, mean, cov, probe, seed=2)
+    t0 = time.perf_counter()
+    orc.em_accumulate(g, X, threads=cores)
+    dt = time.perf_counter() - t0
+    n = sample_frames or int(max(probe, min(2_000_000, probe * budget_s / max(dt, 1e-3))))
+    X = synth.make_frames(w, mean, cov, n, seed=2)
+    t0 = time.perf_counter()
+    orc.em_accumulate(g, X, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} frames of the same 2048c/60d EM workload, {cores} pthreads, -O3 -ffast-math fp64"}, n, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    base, n, _ = cpu_baseline(budget_s=8.0)
+    from lia_ral_b200 import synth
+    from oracle.ffi import Oracle
+    orc = Oracle(fast=True)
+    _, (w, mean, cov) = synth_model()
+    g = orc.gmm(w, mean, cov)
+    X = synth.make_frames(w, mean, cov, n, seed=2)
+    cores = base["cores"]
+    for _ in range(min(warm, 1)):
+        orc.em_accumulate(g, X[: max(1024, n // 8)], threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.em_accumulate(g, X, threads=cores)
+    dt = time.perf_counter() - t0
+    val = n * steps / dt
+    base["value"] = val
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "TrainWorld EM iteration, 2048c/60d diagonal UBM (configs[1]), bounded sample",
+                   "frames_per_step": n},
+        "cpu_baseline": base,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=10_000_000, help="frames per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from lia_ral_b200 import capi
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi.init(local)
+    capi.set_gmm_kernel(args.kernel)
+    lr_stream = torch.cuda.ExternalStream(capi.stream_handle(), device=dev)
+
+    (w, mean, cov), start = synth_model()
+    T = args.frames
+    X = make_frames_gpu(torch, w, mean, cov, T, seed=2 + 1000 * rank, device=dev)
+    torch.cuda.synchronize()
+    feats = capi.Feats(device_ptr=X.data_ptr(), T=T, ldx=D, D=D)
+    g = capi.GMM(*start)
+    nstat = g.em_stats_len()
+    stats = torch.zeros(nstat, dtype=torch.float64, device=dev)
+    cov_signal = torch.tensor(X[: min(T, 1 << 20)].double().var(0, unbiased=False).cpu().numpy(), device=dev)
+    floor_, ceil_ = 0.5, 10.0   # floors 0.5 -> 0.5, ceilings 10 -> 10
+    ev_stats = torch.cuda.Event()
+
+    def step():
+        with torch.cuda.stream(lr_stream):
+            stats.zero_()
+        g.em_accumulate_dev(feats, 0, T, 1.0, stats.data_ptr())
+        if world > 1:
+            # one all-reduce of {occ, m1, m2, llk, n} per iteration (emAcc.addAccEM analogue)
+            with torch.cuda.stream(lr_stream):
+                dist.all_reduce(stats)
+        g.em_update_dev(stats.data_ptr(), floor_, ceil_, cov_signal.data_ptr())
+
+    def sync_all():
+        capi.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    capi.profile(True)
+    capi.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(lr_stream):
+        e0.record()
+    for _ in range(args.steps):
+        step()
+    with torch.cuda.stream(lr_stream):
+        e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = capi.launch_count()
+    lse_ms, lse_n = capi.profile_read(0)
+    acc_ms, acc_n = capi.profile_read(1)
+    capi.profile(False)
+    clocks = sampler.summary() if sampler else None
+    llk_per_frame = float(stats[-2].item() / max(stats[-1].item(), 1.0))
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * T * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the same EM iteration through the host-buffer C ABI (pinned host frames in,
+    # host statistics out, host-side getEM call) -- H2D / D2H inside the timed region
+    Te = T
+    Xh = torch.empty((Te, D), dtype=torch.float32, pin_memory=True)
+    Xh.copy_(X[:Te])
+    torch.cuda.synchronize()
+    Xh_np = Xh.numpy()
+    g2 = capi.GMM(*start)
+    gc = cov_signal.cpu().numpy()
+
+    def e2e_step():
+        llk, n, occ, m1, m2 = g2.em_accumulate(Xh_np)
+        g2.em_update(occ, m1, m2, floor_, ceil_, gc)
+        return llk / n
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_llk = e2e_step()
+    capi.synchronize()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * Te * args.e2e_steps / float(te.item())
+    stat_bytes = nstat * 8
+
+    if rank == 0:
+        pk = peaks()
+        dom_ms, dom_n = (acc_ms, acc_n) if acc_ms >= lse_ms else (lse_ms, lse_n)
+        frames_per_launch = T * args.steps / max(dom_n, 1)
+        flop = FLOP_PER_FRAME_EM * frames_per_launch
+        achieved = flop / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TrainWorld EM iteration, 2048c/60d diagonal UBM, 10M frames/GPU (configs[1])",
+                       "frames_per_gpu": T, "components": C, "dim": D,
+                       "l2": "inputs (2.4 GB/GPU) exceed L2, no flush needed",
+                       "kernel": {0: "auto", 1: "simt-fp32", 2: "tcgen05"}[args.kernel],
+                       "mean_llk_per_frame": llk_per_frame},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": Te * D * 4 + 2 * C * D * 8 * 2,
+                    "d2h_bytes_per_step": stat_bytes, "steps": args.e2e_steps,
+                    "mean_llk_per_frame": e2e_llk},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16"], "traffic": None,
+                         "kernel": "statistics pass (LLK recompute + g x / g x^2 accumulation)",
+                         "flop_per_frame": FLOP_PER_FRAME_EM, "launches": dom_n,
+                         "avg_launch_ms": dom_ms / max(dom_n, 1), "peak_source": pk["src"],
+                         "llk_pass_ms_per_step": lse_ms / args.steps, "stat_pass_ms_per_step": acc_ms / args.steps},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"], _, _ = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+/*
+ * lia_ral_b200.h -- C ABI of the B200-native engine for LIA_RAL's GMM / i-vector hot path.
+ *
+ * Drop-in boundary: the reference has no FFI; its hot path is ordinary C++
+ * calls from libliatools (LIA_SpkTools) into alize-core, ONE FRAME AT A TIME.  This ABI is
+ * inserted at the per-BATCH seam instead -- the LIA_SpkTools functions that own the frame /
+ * utterance loops -- and every entry point cites the loop it replaces.
+ *
+ * Conventions
+ *   - plain C types only; all host matrices row-major double exactly as the reference's
+ *     Matrix<double>::getArray() / DoubleVector::getArray() hand them over; frames are the
+ *     on-disk float32 (Feature::getDataVector() widens them, AccumulateTVStat.cpp:336).
+ *   - statistics are ACCUMULATED INTO (+=) the caller's buffers like the reference
+ *     (resetEM / resetAcc stay the caller's job: TrainTools.cpp:1057, AccumulateTVStat.cpp:613).
+ *   - every function returns lr_status (0 = LR_OK) or a handle (NULL on failure);
+ *     lr_last_error() returns the thread-local message.  The C++ host mirror rethrows it as
+ *     an alize::Exception-compatible exception (reference convention: AccumulateTVStat.cpp:481).
+ *   - NO CPU FALLBACK: without a CUDA device every compute entry point fails with LR_ERR_CUDA.
+ *   - "_dev" variants take DEVICE pointers (e.g. torch tensors' data_ptr()) and enqueue on the
+ *     engine stream without synchronising; host variants copy H2D/D2H inside the call.
+ *   - handles are not thread-safe; one host thread per device (the reference's numThread is
+ *     parsed by the host mirror and ignored by this backend).
+ */
+#ifndef LIA_RAL_B200_H
+#define LIA_RAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int lr_status;
+enum {
+  LR_OK = 0,
+  LR_ERR_ARG = 1,   /* bad argument (reference: Exception thrown by the caller-side checks) */
+  LR_ERR_CUDA = 2,  /* CUDA / cuBLAS failure, or no device */
+  LR_ERR_NUMERIC = 3 /* singular / non-SPD matrix (reference: invert()/upperCholesky() failing) */
+};
+
+const char *lr_last_error(void);
+const char *lr_version(void);
+
+/* Bind the calling process to one GPU (one process per GPU; rank r -> device r). */
+lr_status lr_init(int device);
+lr_status lr_shutdown(void);
+lr_status lr_synchronize(void);
+/* cudaStream_t of the engine as an integer, so torch can order against it. */
+uint64_t lr_stream_handle(void);
+int lr_sm_count(void);
+/* Number of kernels this library has launched since the last reset (bench.py gpu_launches). */
+uint64_t lr_launch_count(void);
+void lr_reset_launch_count(void);
+/* Per-kernel device timing for bench.py's roofline line: while enabled, every launch of the
+ * two frames x components kernels is bracketed by CUDA events on the engine stream.
+ * kind 0 = log-likelihood pass, 1 = statistics pass.  lr_profile_read synchronises. */
+lr_status lr_profile(int enable);
+lr_status lr_profile_read(int kind, double *total_ms, uint64_t *n_launches);
+/* Kernel selection for the frames x components pass: 0 = auto, 1 = fp32 SIMT, 2 = tcgen05. */
+lr_status lr_set_gmm_kernel(int which);
+int lr_get_gmm_kernel(void);
+
+/* ------------------------------------------------------------------ GMM (MixtureGD) ------
+ * Replaces MixtureGD + DistribGD::computeAll (alize-core; constants probed on
+ * LIA_SpkDet/TrainWorld/test/wld.validate): covInv = 1/cov, det = prod cov,
+ * cst = 1/((2pi)^(D/2) sqrt(det)).  w[C], mean[C*D], cov[C*D]. */
+typedef struct lr_gmm lr_gmm;
+lr_gmm *lr_gmm_create(int C, int D, const double *w, const double *mean, const double *cov);
+lr_status lr_gmm_set(lr_gmm *g, const double *w, const double *mean, const double *cov);
+/* any output may be NULL */
+lr_status lr_gmm_get(lr_gmm *g, double *w, double *mean, double *cov, double *covinv,
+                     double *cst, double *det);
+/* override the stored cst (RAW model files carry their own cst/det records) */
+lr_status lr_gmm_set_cst(lr_gmm *g, const double *cst);
+void lr_gmm_destroy(lr_gmm *g);
+
+/* ------------------------------------------------------------------ frames in HBM ---------
+ * Replaces the FeatureServer buffer (featureServerBufferSize ALL_FEATURES): a [T x D] float32
+ * block resident on the device so EM iterations do not re-cross PCIe. */
+typedef struct lr_feats lr_feats;
+lr_feats *lr_feats_upload(const float *X, size_t T, size_t ldx, int D);
+lr_feats *lr_feats_wrap_device(const float *dX, size_t T, size_t ldx, int D);
+void lr_feats_destroy(lr_feats *f);
+
+/* A run of selected frames and the statistics row it feeds: the reference's Seg
+ * (sourceName/begin/length after fs.getFirstFeatureIndexOfASource) + the NDX line from
+ * TVTranslate::locIndices (AccumulateTVStat.cpp:313-346).  A file listed on several NDX
+ * lines is passed as several segments over the same frames. */
+typedef struct {
+  int64_t begin;  /* first frame (index into X) */
+  int64_t length; /* number of frames */
+  int32_t row;    /* statistics row (NDX line); ignored by the EM entry points */
+  int32_t pad_;
+} lr_seg;
+
+/* ---- a4/a5: accumulateStatEM (AccumulateStat.cpp:103-140, threaded :170-299) over
+ * MixtureGDStat::computeAndAccumulateEM.  occ[C] += g, m1[C*D] += g x, m2[C*D] += g x^2
+ * (g = frame_weight * posterior), *sum_log_lk += sum_t log(sum_c w_c lk_c(x_t)),
+ * *n_frames += frame_weight * #frames.  segs == NULL -> all T frames. */
+lr_status lr_gmm_em_accumulate(lr_gmm *g, const float *X, size_t T, size_t ldx,
+                               const lr_seg *segs, size_t n_segs, double frame_weight,
+                               double *occ, double *m1, double *m2, double *sum_log_lk,
+                               double *n_frames);
+/* device-resident variant: d_stats = [occ C | m1 C*D | m2 C*D | sum_log_lk | n_frames] doubles
+ * in device memory, accumulated into; frames [t0, t0+T) of f. */
+lr_status lr_gmm_em_accumulate_dev(lr_gmm *g, const lr_feats *f, size_t t0, size_t T,
+                                   double frame_weight, double *d_stats);
+size_t lr_gmm_em_stats_len(const lr_gmm *g); /* C + 2*C*D + 2 */
+/* MixtureGDStat::getEM + varianceControl (TrainTools.cpp:567-587,1076-1077) on the device:
+ * w = occ/sum occ, mean = m1/occ, cov = m2/occ - mean^2, then clamp cov to
+ * [flooring*cov_signal, ceiling*cov_signal] (floor first), then computeAll.  d_cov_signal may
+ * be NULL (no variance control).  Runs without a host sync; g is updated in place. */
+lr_status lr_gmm_em_update_dev(lr_gmm *g, const double *d_stats, double flooring, double ceiling,
+                               const double *d_cov_signal);
+/* host convenience: getEM + varianceControl from host statistics */
+lr_status lr_gmm_em_update(lr_gmm *g, const double *occ, const double *m1, const double *m2,
+                           double flooring, double ceiling, const double *cov_signal);
+/* FrameAccGD via computeMeanCov (TrainTools.cpp:593-602): global mean / cov of the frames */
+lr_status lr_frames_mean_cov(const float *X, size_t T, size_t ldx, int D, double *mean,
+                             double *cov);
+
+/* ---- a2/a3: TVAcc::computeAndAccumulateTVStat (AccumulateTVStat.cpp:268-351, threaded
+ * :376-548): N[U x C] += posterior, F[U x C*D] += posterior * x for the frames of each
+ * segment, into row seg.row. */
+lr_status lr_gmm_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const lr_seg *segs,
+                         size_t n_segs, size_t U, double *N, double *F);
+/* device-resident variant: d_N / d_F device doubles, d_segs host array (small) */
+lr_status lr_gmm_bwstats_dev(lr_gmm *g, const lr_feats *f, const lr_seg *segs, size_t n_segs,
+                             size_t U, double *d_N, double *d_F);
+
+/* ---- a7: MixtureGDStat::computeAndAccumulateLLK (call sites ComputeTest.cpp:162-167,
+ * TopGauss.cpp:166-192, AccumulateStat.cpp:77).
+ * DETERMINE_TOP_DISTRIBS: idx[T*K] = the K most likely components in descending p_c order
+ * (ties: lowest index), top_lk[T*K] their p_c (may be NULL), rest_lk[T] / rest_w[T] = sum of
+ * p_c / weights outside the top K (TopGauss.cpp:181-192 snsl/snsw; may be NULL),
+ * llk[T] = log(lk) clamped to [min_llk, max_llk] with lk = all components (complete != 0,
+ * "COMPLETE") or the top K only ("PARTIAL").  Index selection is exact w.r.t. the fp64
+ * likelihoods: fp32 candidates are re-evaluated in fp64 on the device. */
+lr_status lr_gmm_llk_topk(lr_gmm *world, const float *X, size_t T, size_t ldx, int K,
+                          int complete, double min_llk, double max_llk, double *llk,
+                          uint32_t *idx, double *top_lk, double *rest_lk, double *rest_w);
+/* USE_TOP_DISTRIBS on a client model: lk = sum_k w'_{idx} lk'_{idx}(x) (+ rest_lk if complete) */
+lr_status lr_gmm_llk_use_topk(lr_gmm *client, const float *X, size_t T, size_t ldx, int K,
+                              const uint32_t *idx, const double *rest_lk, int complete,
+                              double min_llk, double max_llk, double *llk);
+/* TOP_DISTRIBS_NO_ACTION: llk over all components (accumulateStatLLK) */
+lr_status lr_gmm_llk(lr_gmm *g, const float *X, size_t T, size_t ldx, double min_llk,
+                     double max_llk, double *llk);
+/* The frame loop of ComputeTest() (ComputeTest.cpp:154-199) for one test file: world top-K
+ * every frame (worldDecime 1), n_clients client models through USE_TOP_DISTRIBS;
+ * mean_llk_world[n_segs_out], mean_llk_client[n_clients * n_segs_out]; per_segment != 0 =
+ * segmentalMode (one mean per segment) else one mean over all segments (n_segs_out = 1). */
+lr_status lr_compute_test(lr_gmm *world, lr_gmm *const *clients, int n_clients, const float *X,
+                          size_t T, size_t ldx, const lr_seg *segs, size_t n_segs, int K,
+                          int complete, double min_llk, double max_llk, int per_segment,
+                          double *mean_llk_world, double *mean_llk_client);
+
+/* ------------------------------------------------------------------ Total Variability -----
+ * Device twin of the TVAcc object (AccumulateTVStat.h): owns _statN [U x C], _statF
+ * [U x C*D], _T [R x C*D], _W [U x R], _TETt, _A [C x R*R], _Cmx [R x C*D], _R, _r, _meanW,
+ * _ubm_means, _ubm_invvar in HBM (fp64). */
+typedef struct lr_tv lr_tv;
+lr_tv *lr_tv_create(int C, int D, int R, size_t U, const double *ubm_mean,
+                    const double *ubm_invvar);
+void lr_tv_destroy(lr_tv *tv);
+lr_status lr_tv_set_stats(lr_tv *tv, const double *N, const double *F); /* loadN / loadF_X */
+lr_status lr_tv_get_stats(lr_tv *tv, double *N, double *F);
+/* device pointers to the statistics so lr_gmm_bwstats_dev can fill them in place */
+double *lr_tv_dev_N(lr_tv *tv);
+double *lr_tv_dev_F(lr_tv *tv);
+lr_status lr_tv_set_T(lr_tv *tv, const double *T); /* loadT / initT result */
+lr_status lr_tv_get_T(lr_tv *tv, double *T);
+lr_status lr_tv_get_mean(lr_tv *tv, double *ubm_mean);
+lr_status lr_tv_get_W(lr_tv *tv, double *W);
+/* any output may be NULL; A[C x R*R], Cmx[R x C*D], Rm[R*R], r[R], meanW[R] */
+lr_status lr_tv_get_acc(lr_tv *tv, double *A, double *Cmx, double *Rm, double *r, double *meanW);
+lr_status lr_tv_reset_tmp_acc(lr_tv *tv);  /* resetTmpAcc: zero Cmx (A, R, r are zeroed by estep) */
+lr_status lr_tv_subtract_m(lr_tv *tv);     /* substractM :1088-1105 */
+lr_status lr_tv_estimate_tett(lr_tv *tv);  /* estimateTETt :766-805 */
+lr_status lr_tv_estimate_w(lr_tv *tv);     /* estimateW :2103-2169 */
+lr_status lr_tv_estimate_a_and_c(lr_tv *tv); /* estimateAandC :1691-1795 */
+lr_status lr_tv_update_t(lr_tv *tv);       /* updateTestimate :974-1005 */
+lr_status lr_tv_min_divergence(lr_tv *tv, double n_sessions); /* minDivergence :2056-2099 */
+lr_status lr_tv_orthonormalize_t(lr_tv *tv); /* orthonormalizeT :1548-1596 */
+/* multi-GPU: device pointer + length (doubles) of the contiguous E-step accumulator block
+ * [A | Cmx | Rm | r | sumW] that one NCCL all-reduce per EM iteration exchanges */
+double *lr_tv_dev_acc(lr_tv *tv);
+size_t lr_tv_acc_len(const lr_tv *tv);
+/* after the all-reduce: meanW = sumW / n_speakers_total */
+lr_status lr_tv_finish_estep(lr_tv *tv, double n_speakers_total);
+
+/* ------------------------------------------------------------------ PLDA scoring ----------
+ * PldaTest::pldaNativeScoring + pldaScoring (PldaTools.cpp:4489-4519, 4175-4271) with
+ * PldaModel::preComputation (:2950-2972) and rotateLeft (:3770-3790).  F[d x rF], G[d x rG]
+ * (rG may be 0, G NULL), Sigma[d x d]; models[d x n_enrol], segments[d x n_test]: one
+ * i-vector per COLUMN like the reference's _models/_segments; model_of[n_enrol] = model
+ * number of each enrolment column (non-decreasing).  scores[n_models x n_test]. */
+lr_status lr_plda_native_scoring(int d, int rF, int rG, const double *F, const double *G,
+                                 const double *Sigma, const double *models, size_t n_enrol,
+                                 const int32_t *model_of, size_t n_models,
+                                 const double *segments, size_t n_test, double *scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

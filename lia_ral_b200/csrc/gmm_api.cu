@@ -1,0 +1,452 @@
+// gmm_api.cu -- extern "C" entry points of the frames x components path: they own the frame
+// and segment loops that LIA_SpkTools runs one frame at a time (accumulateStatEM,
+// computeAndAccumulateTVStat, the ComputeTest frame loop), staging host frames through two
+// device buffers so the PCIe copy of block k+1 overlaps the kernels of block k.
+#include <algorithm>
+
+#include "gmm_topk.cuh"
+
+namespace lr {
+
+namespace {
+
+constexpr long kBlockFrames = 1L << 18;  // frames per staged block (63 MB at D = 60)
+
+struct Plan {
+  std::vector<unsigned> index;  // empty -> identity
+  std::vector<LrChunk> chunks;
+  long P = 0;
+};
+
+struct Clip {
+  int row;
+  long begin;  // relative to the block base
+  long len;
+};
+
+// Frame list + chunk list of the frames [b0, b1) (absolute), positions relative to `base`.
+// segs == nullptr selects every frame, row 0.  Chunks never straddle rows.
+void build_plan(const lr_seg *segs, size_t n_segs, long b0, long b1, long base, bool use_rows,
+                Plan &plan) {
+  plan.index.clear();
+  plan.chunks.clear();
+  plan.P = 0;
+  if (!segs) {
+    plan.P = b1 - b0;
+    if (b0 != base) {
+      plan.index.resize(plan.P);
+      for (long p = 0; p < plan.P; p++) plan.index[p] = (unsigned)(b0 - base + p);
+    }
+    for (long p = 0; p < plan.P; p += kChunkFrames)
+      plan.chunks.push_back({p, (int)std::min<long>(kChunkFrames, plan.P - p), 0});
+    return;
+  }
+  std::vector<Clip> clips;
+  for (size_t s = 0; s < n_segs; s++) {
+    long sb = std::max<long>(segs[s].begin, b0), se = std::min<long>(segs[s].begin + segs[s].length, b1);
+    if (se > sb) clips.push_back({use_rows ? segs[s].row : 0, sb - base, se - sb});
+  }
+  std::stable_sort(clips.begin(), clips.end(),
+                   [](const Clip &a, const Clip &b) { return a.row < b.row; });
+  size_t total = 0;
+  for (auto &c : clips) total += (size_t)c.len;
+  plan.index.resize(total);
+  long pos = 0;
+  size_t i = 0;
+  while (i < clips.size()) {
+    int row = clips[i].row;
+    long row_start = pos;
+    while (i < clips.size() && clips[i].row == row) {
+      for (long k = 0; k < clips[i].len; k++) plan.index[pos + k] = (unsigned)(clips[i].begin + k);
+      pos += clips[i].len;
+      i++;
+    }
+    for (long p = row_start; p < pos; p += kChunkFrames)
+      plan.chunks.push_back({p, (int)std::min<long>(kChunkFrames, pos - p), row});
+  }
+  plan.P = pos;
+}
+
+lr_status check_segs(const lr_seg *segs, size_t n_segs, size_t T, size_t U, bool use_rows) {
+  for (size_t s = 0; s < n_segs; s++) {
+    LR_REQUIRE(segs[s].begin >= 0 && segs[s].length >= 0 &&
+                   (size_t)(segs[s].begin + segs[s].length) <= T,
+               "segment %zu [%lld, +%lld) outside the %zu frames", s, (long long)segs[s].begin,
+               (long long)segs[s].length, T);
+    LR_REQUIRE(!use_rows || (segs[s].row >= 0 && (size_t)segs[s].row < U),
+               "segment %zu: row %d outside [0, %zu)", s, segs[s].row, U);
+  }
+  return LR_OK;
+}
+
+// Upload the plan and run pass 1 (+ pass 2 when any output is requested) over it.
+lr_status run_plan(lr_gmm *g, const float *dX, size_t ldx, const Plan &plan, double fw,
+                   double *dN, double *dF, double *dS2, double *d_llk_sum) {
+  if (plan.P == 0) return LR_OK;
+  Engine &e = engine();
+  float *d_lse = (float *)scratch_get(kSlotLse, plan.P * sizeof(float));
+  if (!d_lse) return LR_ERR_CUDA;
+  unsigned *d_index = nullptr;
+  if (!plan.index.empty()) {
+    d_index = (unsigned *)scratch_get(kSlotIndex, plan.index.size() * sizeof(unsigned));
+    if (!d_index) return LR_ERR_CUDA;
+    LR_CUDA(cudaMemcpyAsync(d_index, plan.index.data(), plan.index.size() * sizeof(unsigned),
+                            cudaMemcpyHostToDevice, e.stream));
+  }
+  FrameList fl{dX, ldx, d_index, plan.P};
+  lr_status st = gmm_pass_lse(g, fl, d_lse, nullptr, d_llk_sum);
+  if (st != LR_OK) return st;
+  if (dN || dF || dS2) {
+    LrChunk *d_chunks = (LrChunk *)scratch_get(kSlotChunks, plan.chunks.size() * sizeof(LrChunk));
+    if (!d_chunks) return LR_ERR_CUDA;
+    LR_CUDA(cudaMemcpyAsync(d_chunks, plan.chunks.data(), plan.chunks.size() * sizeof(LrChunk),
+                            cudaMemcpyHostToDevice, e.stream));
+    st = gmm_pass_acc(g, fl, d_lse, d_chunks, (int)plan.chunks.size(), fw, dN, dF, dS2);
+  }
+  return st;
+}
+
+// Frame range touched by the segments (or [0, T) without segments).
+void seg_range(const lr_seg *segs, size_t n_segs, size_t T, long &lo, long &hi) {
+  if (!segs) {
+    lo = 0;
+    hi = (long)T;
+    return;
+  }
+  lo = (long)T;
+  hi = 0;
+  for (size_t s = 0; s < n_segs; s++) {
+    if (segs[s].length <= 0) continue;
+    lo = std::min<long>(lo, segs[s].begin);
+    hi = std::max<long>(hi, segs[s].begin + segs[s].length);
+  }
+  if (hi < lo) lo = hi = 0;
+}
+
+// Host frames -> staged blocks -> fn(dX_block, b0, b1).  Copies run on the copy stream and
+// alternate between two device buffers guarded by events.
+template <typename Fn>
+lr_status for_each_host_block(const float *X, size_t ldx, long lo, long hi, Fn fn) {
+  Engine &e = engine();
+  int k = 0;
+  for (long b0 = lo; b0 < hi; b0 += kBlockFrames, k++) {
+    long b1 = std::min(hi, b0 + kBlockFrames);
+    int s = k & 1;
+    size_t bytes = (size_t)(b1 - b0) * ldx * sizeof(float);
+    float *buf = (float *)scratch_get(s ? kSlotX1 : kSlotX0,
+                                      (size_t)std::min<long>(kBlockFrames, hi - lo) * ldx *
+                                          sizeof(float));
+    if (!buf) return LR_ERR_CUDA;
+    if (k >= 2) LR_CUDA(cudaStreamWaitEvent(e.copy_stream, e.ev_consumed[s], 0));
+    LR_CUDA(cudaMemcpyAsync(buf, X + (size_t)b0 * ldx, bytes, cudaMemcpyHostToDevice,
+                            e.copy_stream));
+    LR_CUDA(cudaEventRecord(e.ev_copied[s], e.copy_stream));
+    LR_CUDA(cudaStreamWaitEvent(e.stream, e.ev_copied[s], 0));
+    lr_status st = fn(buf, b0, b1);
+    if (st != LR_OK) return st;
+    LR_CUDA(cudaEventRecord(e.ev_consumed[s], e.stream));
+  }
+  return LR_OK;
+}
+
+__global__ void k_add_scalar(double *dst, double v) { *dst += v; }
+
+}  // namespace
+}  // namespace lr
+
+using namespace lr;
+
+extern "C" {
+
+lr_status lr_gmm_em_accumulate(lr_gmm *g, const float *X, size_t T, size_t ldx,
+                               const lr_seg *segs, size_t n_segs, double frame_weight,
+                               double *occ, double *m1, double *m2, double *sum_log_lk,
+                               double *n_frames) {
+  LR_READY();
+  LR_REQUIRE(g && X && occ && m1 && m2, "lr_gmm_em_accumulate: null argument");
+  LR_REQUIRE(ldx >= (size_t)g->D && T < (1ull << 32), "lr_gmm_em_accumulate: bad T / ldx");
+  if (segs) {
+    lr_status st = check_segs(segs, n_segs, T, 1, false);
+    if (st != LR_OK) return st;
+  }
+  Engine &e = engine();
+  size_t C = g->C, cd = (size_t)g->C * g->D, n = lr_gmm_em_stats_len(g);
+  double *d_stats = (double *)scratch_get(kSlotStats, n * sizeof(double));
+  if (!d_stats) return LR_ERR_CUDA;
+  LR_CUDA(cudaMemsetAsync(d_stats, 0, n * sizeof(double), e.stream));
+  long lo, hi;
+  seg_range(segs, n_segs, T, lo, hi);
+  Plan plan;
+  double total_pos = 0.0;
+  lr_status st = for_each_host_block(X, ldx, lo, hi, [&](const float *dX, long b0, long b1) {
+    build_plan(segs, n_segs, b0, b1, b0, false, plan);
+    total_pos += (double)plan.P;
+    return run_plan(g, dX, ldx, plan, frame_weight, d_stats, d_stats + C, d_stats + C + cd,
+                    d_stats + C + 2 * cd);
+  });
+  if (st != LR_OK) return st;
+  std::vector<double> h(n);
+  LR_CUDA(cudaMemcpyAsync(h.data(), d_stats, n * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  for (size_t i = 0; i < C; i++) occ[i] += h[i];
+  for (size_t i = 0; i < cd; i++) {
+    m1[i] += h[C + i];
+    m2[i] += h[C + cd + i];
+  }
+  if (sum_log_lk) *sum_log_lk += h[C + 2 * cd];
+  if (n_frames) *n_frames += frame_weight * total_pos;
+  return LR_OK;
+}
+
+lr_status lr_gmm_em_accumulate_dev(lr_gmm *g, const lr_feats *f, size_t t0, size_t T,
+                                   double frame_weight, double *d_stats) {
+  LR_READY();
+  LR_REQUIRE(g && f && d_stats, "lr_gmm_em_accumulate_dev: null argument");
+  LR_REQUIRE(f->D == g->D && t0 + T <= f->T, "lr_gmm_em_accumulate_dev: frame range / vectSize");
+  size_t C = g->C, cd = (size_t)g->C * g->D;
+  Plan plan;
+  const long step = 1L << 21;
+  for (long b0 = (long)t0; b0 < (long)(t0 + T); b0 += step) {
+    long b1 = std::min<long>((long)(t0 + T), b0 + step);
+    build_plan(nullptr, 0, b0, b1, b0, false, plan);
+    lr_status st = run_plan(g, f->d_x + (size_t)b0 * f->ldx, f->ldx, plan, frame_weight, d_stats,
+                            d_stats + C, d_stats + C + cd, d_stats + C + 2 * cd);
+    if (st != LR_OK) return st;
+  }
+  // n_frames accumulates on the device too (no host sync in this variant)
+  k_add_scalar<<<1, 1, 0, engine().stream>>>(d_stats + C + 2 * cd + 1, frame_weight * (double)T);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+lr_status lr_gmm_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const lr_seg *segs,
+                         size_t n_segs, size_t U, double *N, double *F) {
+  LR_READY();
+  LR_REQUIRE(g && X && N && F && U > 0, "lr_gmm_bwstats: null argument");
+  LR_REQUIRE(ldx >= (size_t)g->D && T < (1ull << 32), "lr_gmm_bwstats: bad T / ldx");
+  if (segs) {
+    lr_status st = check_segs(segs, n_segs, T, U, true);
+    if (st != LR_OK) return st;
+  }
+  Engine &e = engine();
+  size_t nN = U * (size_t)g->C, nF = nN * g->D;
+  DevBuf<double> dN, dF;
+  LR_CUDA(dN.alloc(nN));
+  LR_CUDA(dF.alloc(nF));
+  LR_CUDA(cudaMemcpyAsync(dN.p, N, nN * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  LR_CUDA(cudaMemcpyAsync(dF.p, F, nF * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  long lo, hi;
+  seg_range(segs, n_segs, T, lo, hi);
+  Plan plan;
+  lr_status st = for_each_host_block(X, ldx, lo, hi, [&](const float *dX, long b0, long b1) {
+    build_plan(segs, n_segs, b0, b1, b0, true, plan);
+    return run_plan(g, dX, ldx, plan, 1.0, dN.p, dF.p, nullptr, nullptr);
+  });
+  if (st != LR_OK) return st;
+  LR_CUDA(cudaMemcpyAsync(N, dN.p, nN * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaMemcpyAsync(F, dF.p, nF * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  return LR_OK;
+}
+
+lr_status lr_gmm_bwstats_dev(lr_gmm *g, const lr_feats *f, const lr_seg *segs, size_t n_segs,
+                             size_t U, double *d_N, double *d_F) {
+  LR_READY();
+  LR_REQUIRE(g && f && d_N && d_F && U > 0, "lr_gmm_bwstats_dev: null argument");
+  LR_REQUIRE(f->D == g->D && f->T < (1ull << 32), "lr_gmm_bwstats_dev: vectSize / frame count");
+  if (segs) {
+    lr_status st = check_segs(segs, n_segs, f->T, U, true);
+    if (st != LR_OK) return st;
+  }
+  long lo, hi;
+  seg_range(segs, n_segs, f->T, lo, hi);
+  Plan plan;
+  const long step = 1L << 21;
+  for (long b0 = lo; b0 < hi; b0 += step) {
+    long b1 = std::min(hi, b0 + step);
+    build_plan(segs, n_segs, b0, b1, 0, true, plan);
+    // plan uploads reuse the scratch slots: the previous block's kernels must have consumed them
+    lr_status st = run_plan(g, f->d_x, f->ldx, plan, 1.0, d_N, d_F, nullptr, nullptr);
+    if (st != LR_OK) return st;
+  }
+  return LR_OK;
+}
+
+// -------------------------------------------------------------------------- LLK / top-K
+lr_status lr_gmm_llk(lr_gmm *g, const float *X, size_t T, size_t ldx, double min_llk,
+                     double max_llk, double *llk) {
+  LR_READY();
+  LR_REQUIRE(g && X && llk && ldx >= (size_t)g->D, "lr_gmm_llk: bad argument");
+  Engine &e = engine();
+  return for_each_host_block(X, ldx, 0, (long)T, [&](const float *dX, long b0, long b1) {
+    long P = b1 - b0;
+    float *d_lse = (float *)scratch_get(kSlotLse, P * sizeof(float));
+    double *d_llk = (double *)scratch_get(kSlotLlk, P * sizeof(double));
+    if (!d_lse || !d_llk) return (lr_status)LR_ERR_CUDA;
+    FrameList fl{dX, ldx, nullptr, P};
+    lr_status st = gmm_pass_lse(g, fl, d_lse, nullptr, nullptr);
+    if (st != LR_OK) return st;
+    st = gmm_llk_from_lse(P, d_lse, min_llk, max_llk, d_llk);
+    if (st != LR_OK) return st;
+    LR_CUDA(cudaMemcpyAsync(llk + b0, d_llk, P * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    LR_CUDA(cudaStreamSynchronize(e.stream));
+    return (lr_status)LR_OK;
+  });
+}
+
+// world top-K over a device block; outputs stay on the device in scratch slots
+static lr_status topk_block(lr_gmm *world, const float *dX, size_t ldx, long P, int K, int complete,
+                            double min_llk, double max_llk, double **d_llk, unsigned **d_idx,
+                            double **d_top, double **d_rest, double **d_restw) {
+  float *d_lse = (float *)scratch_get(kSlotLse, P * sizeof(float));
+  float *d_S = (float *)scratch_get(kSlotS, (size_t)P * world->Cp * sizeof(float));
+  *d_llk = (double *)scratch_get(kSlotLlk, P * sizeof(double));
+  *d_idx = (unsigned *)scratch_get(kSlotIdx, (size_t)P * K * sizeof(unsigned));
+  *d_top = (double *)scratch_get(kSlotTmpA, (size_t)P * K * sizeof(double));
+  double *rest = (double *)scratch_get(kSlotRest, (size_t)P * 2 * sizeof(double));
+  if (!d_lse || !d_S || !*d_llk || !*d_idx || !*d_top || !rest) return LR_ERR_CUDA;
+  *d_rest = rest;
+  *d_restw = rest + P;
+  FrameList fl{dX, ldx, nullptr, P};
+  // the top-K path always uses the fp32 SIMT scores (it needs the full S matrix)
+  lr_status st = gmm_pass_lse(world, fl, d_lse, d_S, nullptr);
+  if (st != LR_OK) return st;
+  return gmm_topk(world, fl, d_S, K, complete, min_llk, max_llk, *d_llk, *d_idx, *d_top, *d_rest,
+                  *d_restw);
+}
+
+constexpr long kTopkBlock = 1L << 15;  // frames per block on the top-K path (S is P x Cp floats)
+
+lr_status lr_gmm_llk_topk(lr_gmm *world, const float *X, size_t T, size_t ldx, int K,
+                          int complete, double min_llk, double max_llk, double *llk,
+                          uint32_t *idx, double *top_lk, double *rest_lk, double *rest_w) {
+  LR_READY();
+  LR_REQUIRE(world && X && idx && ldx >= (size_t)world->D, "lr_gmm_llk_topk: bad argument");
+  LR_REQUIRE(K >= 1 && K <= kMaxTopK && K <= world->C, "lr_gmm_llk_topk: K=%d outside [1, min(%d, C)]",
+             K, kMaxTopK);
+  Engine &e = engine();
+  for (long b0 = 0; b0 < (long)T; b0 += kTopkBlock) {
+    long b1 = std::min<long>((long)T, b0 + kTopkBlock), P = b1 - b0;
+    float *dX = (float *)scratch_get(kSlotX0, (size_t)std::min<long>(kTopkBlock, (long)T) * ldx * sizeof(float));
+    if (!dX) return LR_ERR_CUDA;
+    LR_CUDA(cudaMemcpyAsync(dX, X + (size_t)b0 * ldx, (size_t)P * ldx * sizeof(float),
+                            cudaMemcpyHostToDevice, e.stream));
+    double *d_llk, *d_top, *d_rest, *d_restw;
+    unsigned *d_idx;
+    lr_status st = topk_block(world, dX, ldx, P, K, complete, min_llk, max_llk, &d_llk, &d_idx,
+                              &d_top, &d_rest, &d_restw);
+    if (st != LR_OK) return st;
+    if (llk) LR_CUDA(cudaMemcpyAsync(llk + b0, d_llk, P * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    LR_CUDA(cudaMemcpyAsync(idx + (size_t)b0 * K, d_idx, (size_t)P * K * sizeof(unsigned),
+                            cudaMemcpyDeviceToHost, e.stream));
+    if (top_lk)
+      LR_CUDA(cudaMemcpyAsync(top_lk + (size_t)b0 * K, d_top, (size_t)P * K * sizeof(double),
+                              cudaMemcpyDeviceToHost, e.stream));
+    if (rest_lk) LR_CUDA(cudaMemcpyAsync(rest_lk + b0, d_rest, P * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    if (rest_w) LR_CUDA(cudaMemcpyAsync(rest_w + b0, d_restw, P * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    LR_CUDA(cudaStreamSynchronize(e.stream));
+  }
+  return LR_OK;
+}
+
+lr_status lr_gmm_llk_use_topk(lr_gmm *client, const float *X, size_t T, size_t ldx, int K,
+                              const uint32_t *idx, const double *rest_lk, int complete,
+                              double min_llk, double max_llk, double *llk) {
+  LR_READY();
+  LR_REQUIRE(client && X && idx && llk && ldx >= (size_t)client->D, "lr_gmm_llk_use_topk: bad argument");
+  LR_REQUIRE(K >= 1 && K <= client->C, "lr_gmm_llk_use_topk: bad K");
+  for (size_t i = 0; i < T * (size_t)K; i++)
+    LR_REQUIRE(idx[i] < (uint32_t)client->C, "lr_gmm_llk_use_topk: index %u out of range", idx[i]);
+  Engine &e = engine();
+  for (long b0 = 0; b0 < (long)T; b0 += kBlockFrames) {
+    long b1 = std::min<long>((long)T, b0 + kBlockFrames), P = b1 - b0;
+    float *dX = (float *)scratch_get(kSlotX0, (size_t)std::min<long>(kBlockFrames, (long)T) * ldx * sizeof(float));
+    unsigned *d_idx = (unsigned *)scratch_get(kSlotIdx, (size_t)P * K * sizeof(unsigned));
+    double *d_rest = (double *)scratch_get(kSlotRest, P * sizeof(double));
+    double *d_llk = (double *)scratch_get(kSlotLlk, P * sizeof(double));
+    if (!dX || !d_idx || !d_rest || !d_llk) return LR_ERR_CUDA;
+    LR_CUDA(cudaMemcpyAsync(dX, X + (size_t)b0 * ldx, (size_t)P * ldx * sizeof(float),
+                            cudaMemcpyHostToDevice, e.stream));
+    LR_CUDA(cudaMemcpyAsync(d_idx, idx + (size_t)b0 * K, (size_t)P * K * sizeof(unsigned),
+                            cudaMemcpyHostToDevice, e.stream));
+    if (rest_lk)
+      LR_CUDA(cudaMemcpyAsync(d_rest, rest_lk + b0, P * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+    FrameList fl{dX, ldx, nullptr, P};
+    lr_status st = gmm_use_topk(client, fl, K, d_idx, rest_lk ? d_rest : nullptr, complete,
+                                min_llk, max_llk, d_llk);
+    if (st != LR_OK) return st;
+    LR_CUDA(cudaMemcpyAsync(llk + b0, d_llk, P * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    LR_CUDA(cudaStreamSynchronize(e.stream));
+  }
+  return LR_OK;
+}
+
+lr_status lr_compute_test(lr_gmm *world, lr_gmm *const *clients, int n_clients, const float *X,
+                          size_t T, size_t ldx, const lr_seg *segs, size_t n_segs, int K,
+                          int complete, double min_llk, double max_llk, int per_segment,
+                          double *mean_llk_world, double *mean_llk_client) {
+  LR_READY();
+  LR_REQUIRE(world && X && mean_llk_world && (n_clients == 0 || (clients && mean_llk_client)),
+             "lr_compute_test: null argument");
+  LR_REQUIRE(ldx >= (size_t)world->D && T > 0, "lr_compute_test: bad T / ldx");
+  LR_REQUIRE(K >= 1 && K <= kMaxTopK && K <= world->C, "lr_compute_test: K=%d outside [1, min(%d, C)]",
+             K, kMaxTopK);
+  for (int i = 0; i < n_clients; i++)
+    LR_REQUIRE(clients[i] && clients[i]->C == world->C && clients[i]->D == world->D,
+               "lr_compute_test: client %d does not share the world's shape", i);
+  lr_seg all = {0, (int64_t)T, 0, 0};
+  if (!segs) {
+    segs = &all;
+    n_segs = 1;
+  }
+  lr_status st0 = check_segs(segs, n_segs, T, 1, false);
+  if (st0 != LR_OK) return st0;
+  Engine &e = engine();
+  size_t n_out = per_segment ? n_segs : 1;
+  std::vector<double> sum_w(n_out, 0.0), sum_c((size_t)n_clients * n_out, 0.0), cnt(n_out, 0.0);
+  std::vector<double> h_w, h_c;
+  // frames are scored segment by segment in blocks (frames outside the segments are never read)
+  for (size_t s = 0; s < n_segs; s++) {
+    size_t o = per_segment ? s : 0;
+    for (long b0 = segs[s].begin; b0 < segs[s].begin + segs[s].length; b0 += kTopkBlock) {
+      long b1 = std::min<long>(segs[s].begin + segs[s].length, b0 + kTopkBlock), P = b1 - b0;
+      float *dX = (float *)scratch_get(kSlotX0, (size_t)kTopkBlock * ldx * sizeof(float));
+      if (!dX) return LR_ERR_CUDA;
+      LR_CUDA(cudaMemcpyAsync(dX, X + (size_t)b0 * ldx, (size_t)P * ldx * sizeof(float),
+                              cudaMemcpyHostToDevice, e.stream));
+      double *d_llk, *d_top, *d_rest, *d_restw;
+      unsigned *d_idx;
+      lr_status st = topk_block(world, dX, ldx, P, K, complete, min_llk, max_llk, &d_llk, &d_idx,
+                                &d_top, &d_rest, &d_restw);
+      if (st != LR_OK) return st;
+      h_w.resize(P);
+      LR_CUDA(cudaMemcpyAsync(h_w.data(), d_llk, P * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+      double *d_cl = (double *)scratch_get(kSlotTmpB, (size_t)P * std::max(1, n_clients) * sizeof(double));
+      if (!d_cl) return LR_ERR_CUDA;
+      FrameList fl{dX, ldx, nullptr, P};
+      for (int i = 0; i < n_clients; i++) {
+        st = gmm_use_topk(clients[i], fl, K, d_idx, d_rest, complete, min_llk, max_llk,
+                          d_cl + (size_t)i * P);
+        if (st != LR_OK) return st;
+      }
+      h_c.resize((size_t)P * n_clients);
+      if (n_clients)
+        LR_CUDA(cudaMemcpyAsync(h_c.data(), d_cl, (size_t)P * n_clients * sizeof(double),
+                                cudaMemcpyDeviceToHost, e.stream));
+      LR_CUDA(cudaStreamSynchronize(e.stream));
+      // getMeanLLK: accumulated llk / accumulated weight (weight 1 per frame)
+      for (long t = 0; t < P; t++) sum_w[o] += h_w[t];
+      for (int i = 0; i < n_clients; i++)
+        for (long t = 0; t < P; t++) sum_c[(size_t)i * n_out + o] += h_c[(size_t)i * P + t];
+      cnt[o] += (double)P;
+    }
+  }
+  for (size_t o = 0; o < n_out; o++) {
+    mean_llk_world[o] = cnt[o] > 0 ? sum_w[o] / cnt[o] : 0.0;
+    for (int i = 0; i < n_clients; i++)
+      mean_llk_client[(size_t)i * n_out + o] = cnt[o] > 0 ? sum_c[(size_t)i * n_out + o] / cnt[o] : 0.0;
+  }
+  return LR_OK;
+}
+
+}  // extern "C"

@@ -49,10 +49,13 @@ def perturb_ubm(w, mean, cov, seed=3, frac=0.1, scale=0.3):
     return w.copy(), m, cov.copy()
 
 
-def make_T(R, C, D, invvar, seed=4):
-    """T ~ N(0,1) * (sum invvar) * 1e-3, the scale TVAcc::initT uses (AccumulateTVStat.cpp:733-746)."""
+def make_T(R, C, D, invvar, seed=4, scale=None):
+    """T ~ N(0,1) * (sum invvar) * 1e-3, the scale TVAcc::initT uses (AccumulateTVStat.cpp:733-746);
+    `scale` replaces that factor (a trained T has entries of a few 1e-2 sigma)."""
     g = _rng(seed)
-    return g.standard_normal((R, C * D)) * float(np.sum(invvar)) * 1e-3
+    if scale is None:
+        scale = float(np.sum(invvar)) * 1e-3
+    return g.standard_normal((R, C * D)) * scale
 
 
 def make_bw_stats(U, w, mean, cov, R=None, frames_per_utt=3000, active=64, seed=5):

@@ -1,0 +1,281 @@
+"""Parity of the CUDA frames x components path (through the C ABI) against the fp64 oracle.
+
+Tolerances (BASELINE.json north_star): top-Gaussian indices bit-exact; log-likelihoods within
+1e-4 relative; statistics within 1e-4 relative (we hold them to much tighter bounds below so a
+precision regression shows up long before the contract is at risk).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from lia_ral_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from lia_ral_b200 import capi
+    capi.init(0)
+    return capi
+
+
+def _relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _close(a, b, rtol, atol_rel):
+    """elementwise |a-b| <= rtol |b| + atol_rel * max|b|"""
+    return bool((np.abs(a - b) <= rtol * np.abs(b) + atol_rel * np.abs(b).max()).all())
+
+
+@pytest.fixture(scope="module", params=[(2048, 60, 2500), (64, 60, 1500), (100, 13, 777)],
+                ids=["2048c60d", "64c60d", "100c13d"])
+def case(request):
+    C, D, T = request.param
+    w, mean, cov = synth.make_ubm(C=C, D=D, seed=1)
+    X = synth.make_frames(w, mean, cov, T, seed=2)
+    # a test model that is NOT the generator: posteriors spread over several components
+    w2, m2, c2 = synth.perturb_ubm(w, mean, cov * 4.0, seed=3, frac=0.5, scale=1.0)
+    return dict(C=C, D=D, T=T, w=w2, mean=m2, cov=c2, X=X)
+
+
+def test_compute_all(capi, oracle, case):
+    g = capi.GMM(case["w"], case["mean"], case["cov"])
+    o = oracle.gmm(case["w"], case["mean"], case["cov"])
+    got = g.get()
+    assert np.allclose(got["covinv"], o.covinv, rtol=1e-15)
+    assert np.allclose(got["det"], o.det, rtol=1e-12)
+    assert np.allclose(got["cst"], o.cst, rtol=1e-12)
+
+
+def test_llk_all(capi, oracle, case):
+    g = capi.GMM(case["w"], case["mean"], case["cov"])
+    o = oracle.gmm(case["w"], case["mean"], case["cov"])
+    ref = oracle.llk_all(o, case["X"], -1e9, 1e9)
+    got = g.llk(case["X"], -1e9, 1e9)
+    assert np.abs(got - ref).max() < 1e-4 * np.abs(ref).max()  # contract
+    assert np.abs(got - ref).max() < 2e-4                       # what fp32 log2 domain delivers
+    # clamp (minLLK / maxLLK of the shipped configs)
+    lo, hi = np.percentile(ref, 30), np.percentile(ref, 70)
+    got = g.llk(case["X"], lo, hi)
+    assert np.allclose(got, np.clip(ref, lo, hi), atol=2e-4)
+
+
+def _segments(T, U, rng):
+    """ragged segments; some frames unselected, one file listed on two NDX lines"""
+    cuts = np.sort(rng.choice(np.arange(1, T), size=3 * U, replace=False))
+    segs, f2r = [], np.full(T, -1, dtype=np.int32)
+    prev = 0
+    for i, c in enumerate(cuts):
+        if i % 5 != 4:  # every fifth run of frames is not selected by any label
+            row = i % U
+            segs.append((prev, c - prev, row))
+            f2r[prev:c] = row
+        prev = c
+    return segs, f2r
+
+
+def test_bwstats(capi, oracle, case):
+    C, D, T = case["C"], case["D"], case["T"]
+    g = capi.GMM(case["w"], case["mean"], case["cov"])
+    o = oracle.gmm(case["w"], case["mean"], case["cov"])
+    U = 7
+    segs, f2r = _segments(T, U, np.random.default_rng(5))
+    N_ref, F_ref = oracle.bwstats(o, case["X"], f2r, U)
+    N, F = g.bwstats(case["X"], segs, U)
+    assert _close(N, N_ref, 1e-4, 1e-7), _relmax(N, N_ref)
+    assert _close(F, F_ref, 1e-4, 1e-7), _relmax(F, F_ref)
+    assert abs(N.sum() - (f2r >= 0).sum()) < 1e-3
+    # centred statistics F - mu N (substractM) are what the i-vector solve consumes
+    Fc = F.reshape(U, C, D) - N[:, :, None] * case["mean"][None]
+    Fc_ref = F_ref.reshape(U, C, D) - N_ref[:, :, None] * case["mean"][None]
+    assert _relmax(Fc, Fc_ref) < 1e-4
+    # accumulate-into semantics + a file listed on two NDX lines (AccumulateTVStat.cpp:339-346)
+    extra = [(0, 200, 0), (0, 200, 3)]
+    N2, F2 = g.bwstats(case["X"], extra, U, N=N.copy(), F=F.copy())
+    f2 = np.full(T, -1, dtype=np.int32)
+    f2[:200] = 0
+    Na, Fa = oracle.bwstats(o, case["X"], f2, U)
+    f2[:200] = 3
+    Nb, Fb = oracle.bwstats(o, case["X"], f2, U)
+    assert _close(N2, N_ref + Na + Nb, 1e-4, 1e-7)
+    assert _close(F2, F_ref + Fa + Fb, 1e-4, 1e-7)
+
+
+def test_bwstats_strided_and_empty(capi, oracle, case):
+    D, T = case["D"], case["T"]
+    g = capi.GMM(case["w"], case["mean"], case["cov"])
+    o = oracle.gmm(case["w"], case["mean"], case["cov"])
+    wide = np.zeros((T, D + 3), dtype=np.float32)  # featureServerMask-style view: ldx > D
+    wide[:, :D] = case["X"]
+    Xv = wide[:, :D]
+    f2r = np.zeros(T, dtype=np.int32)
+    f2r[400:] = -1
+    N_ref, F_ref = oracle.bwstats(o, Xv, f2r, 2)
+    N, F = g.bwstats(Xv, [(0, 400, 0), (500, 0, 1)], 2)
+    assert _close(N, N_ref, 1e-4, 1e-7) and _close(F, F_ref, 1e-4, 1e-7)
+    assert not N[1].any() and not F[1].any()
+    N, F = g.bwstats(Xv, [], 2)
+    assert not N.any() and not F.any()
+
+
+def test_em_accumulate_and_update(capi, oracle, case):
+    C, D = case["C"], case["D"]
+    g = capi.GMM(case["w"], case["mean"], case["cov"])
+    o = oracle.gmm(case["w"], case["mean"], case["cov"])
+    X = case["X"]
+    llk_ref, n_ref, occ_ref, m1_ref, m2_ref = oracle.em_accumulate(o, X, weight=0.5)
+    llk, n, occ, m1, m2 = g.em_accumulate(X, weight=0.5)
+    assert n == n_ref
+    assert abs(llk - llk_ref) < 1e-5 * abs(llk_ref)
+    assert _close(occ, occ_ref, 1e-4, 1e-7)
+    assert _close(m1, m1_ref, 1e-4, 1e-7)
+    assert _close(m2, m2_ref, 1e-4, 1e-7)
+    # getEM + varianceControl on the device vs the oracle on the ORACLE's statistics
+    gm, gc = oracle.mean_cov(X)
+    fl, ce = 0.3, 3.0
+    w_r, mu_r, cv_r = oracle.em_get(o, occ_ref, m1_ref, m2_ref)
+    cv_r, nf, nc = oracle.variance_control(cv_r, fl, ce, gc)
+    g.em_update(occ_ref, m1_ref, m2_ref, fl, ce, gc)
+    got = g.get()
+    assert np.allclose(got["w"], w_r, rtol=1e-12)
+    assert np.allclose(got["mean"], mu_r, rtol=1e-12, atol=1e-13)
+    assert np.allclose(got["cov"], cv_r, rtol=1e-10, atol=1e-12)
+    o2 = oracle.gmm(w_r, mu_r, cv_r)
+    assert np.allclose(got["cst"], o2.cst, rtol=1e-10)
+    # variances re-estimated from the DEVICE statistics (m2/occ - mu^2 cancels digits)
+    w_d, mu_d, cv_d = oracle.em_get(o, occ, m1, m2)
+    w_o, mu_o, cv_o = oracle.em_get(o, occ_ref, m1_ref, m2_ref)
+    heavy = occ_ref > 1.0
+    if heavy.any():
+        assert _relmax(cv_d[heavy], cv_o[heavy]) < 1e-4
+        assert _relmax(mu_d[heavy], mu_o[heavy]) < 1e-5
+    # segments: only the listed frames, each once
+    segs = [(10, 300), (700, 55)]
+    sel = np.r_[10:310, 700:755]
+    llk_ref, n_ref, occ_ref, m1_ref, m2_ref = oracle.em_accumulate(o, np.ascontiguousarray(X[sel]))
+    llk, n, occ, m1, m2 = g.em_accumulate(X, segs=segs)
+    assert n == len(sel) and abs(llk - llk_ref) < 1e-5 * abs(llk_ref)
+    assert _close(m2, m2_ref, 1e-4, 1e-7)
+
+
+def test_mean_cov(capi, oracle, case):
+    m_ref, c_ref = oracle.mean_cov(case["X"])
+    m, c = capi.frames_mean_cov(case["X"])
+    assert np.allclose(m, m_ref, rtol=1e-12, atol=1e-13) and np.allclose(c, c_ref, rtol=1e-11)
+
+
+def test_topk_indices_bit_exact(capi, oracle, case):
+    g = capi.GMM(case["w"], case["mean"], case["cov"])
+    o = oracle.gmm(case["w"], case["mean"], case["cov"])
+    X = case["X"]
+    for K, complete in ((10, True), (1, False), (min(20, case["C"]), True)):
+        llk_r, idx_r, top_r, rest_r, restw_r = oracle.llk_determine_top(o, X, K, complete)
+        llk, idx, top, rest, restw = g.llk_topk(X, K, complete)
+        assert np.array_equal(idx, idx_r)                     # bit-exact index selection
+        assert np.allclose(top, top_r, rtol=1e-12, atol=0)    # fp64 re-evaluation
+        assert np.allclose(restw, restw_r, rtol=0, atol=1e-14)
+        assert np.allclose(llk, llk_r, rtol=0, atol=1e-4 * np.abs(llk_r).max())
+        tot_r = top_r.sum(1) + rest_r
+        assert np.allclose(top.sum(1) + rest, tot_r, rtol=1e-4)
+        big = rest_r > 1e-6 * tot_r
+        assert np.allclose(rest[big], rest_r[big], rtol=1e-4)
+
+
+def test_use_topk_and_compute_test(capi, oracle, case):
+    C, D, T = case["C"], case["D"], case["T"]
+    X = case["X"]
+    world = capi.GMM(case["w"], case["mean"], case["cov"])
+    o_w = oracle.gmm(case["w"], case["mean"], case["cov"])
+    K = 10
+    cl_params = [synth.perturb_ubm(case["w"], case["mean"], case["cov"], seed=30 + i, frac=0.3,
+                                   scale=0.3) for i in range(3)]
+    clients = [capi.GMM(*p) for p in cl_params]
+    o_cl = [oracle.gmm(*p) for p in cl_params]
+    llk_w, idx, _, rest, _ = oracle.llk_determine_top(o_w, X, K, True)
+    for complete in (True, False):
+        ref = oracle.llk_use_top(o_cl[0], X, idx, rest, complete)
+        got = clients[0].llk_use_topk(X, idx, rest, complete)
+        assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)
+    a, b, c = T // 4, T // 2, T // 5
+    segs = [(0, a), (b, c)]
+    for per_segment in (False, True):
+        mw, mc = capi.compute_test(world, clients, X, segs=segs, K=K, complete=True,
+                                   per_segment=per_segment)
+        groups = [np.r_[0:a], np.r_[b:b + c]] if per_segment else [np.r_[0:a, b:b + c]]
+        for o_i, sel in enumerate(groups):
+            assert abs(mw[o_i] - llk_w[sel].mean()) < 1e-4 * abs(llk_w[sel].mean())
+            for i, oc in enumerate(o_cl):
+                ref = oracle.llk_use_top(oc, X, idx, rest, True)[sel].mean()
+                # LLR = client - world (ComputeTest.cpp:196-199)
+                assert abs((mc[i, o_i] - mw[o_i]) - (ref - llk_w[sel].mean())) < 2e-4
+    # reference fixture property (ComputeTest/test/test1.validate.res): client == world => LLR 0
+    mw, mc = capi.compute_test(world, [world], X, K=K, complete=True)
+    assert abs(mc[0, 0] - mw[0]) < 1e-12
+
+
+def test_gmmtokenizer_golden_on_gpu(capi, golden_dir):
+    """The reference's own KAT (LIA_Utils/GmmTokenizer/test) through the CUDA path."""
+    z = np.load(os.path.join(golden_dir, "gmmtokenizer.npz"))
+    g = capi.GMM(z["w"], z["mean"], 1.0 / z["covinv"])
+    g.set_cst(z["cst"])  # RAW files carry their own cst records
+    X = np.ascontiguousarray(z["frames"][z["selected"]], dtype=np.float32)
+    _, idx, _, _, _ = g.llk_topk(X, 6)
+    best = idx[:, 0].astype(np.int64)
+    collapsed = [best[0]] + [b for a, b in zip(best[:-1], best[1:]) if a != b]
+    assert collapsed == list(z["sym_ref"])
+    K = int(z["mce_topk"])
+    g2 = capi.GMM(z["w"], z["mean"], 1.0 / z["covinv"])
+    _, idx, _, _, _ = g2.llk_topk(X, K)
+    mce = np.zeros_like(z["mce_ref"])
+    for t in range(idx.shape[0]):
+        for i in range(K):
+            mce[idx[t, 0], idx[t, i]] += 1
+    assert (mce == z["mce_ref"]).all()
+
+
+def test_errors_are_loud(capi, case):
+    g = capi.GMM(case["w"], case["mean"], case["cov"])
+    with pytest.raises(capi.LrError):
+        g.bwstats(case["X"], [(0, case["T"] + 1, 0)], 1)      # segment past the end
+    with pytest.raises(capi.LrError):
+        g.bwstats(case["X"], [(0, 10, 5)], 2)                 # row outside U
+    with pytest.raises(capi.LrError):
+        g.llk_topk(case["X"], case["C"] + 1)
+    with pytest.raises(capi.LrError):
+        capi.GMM(np.ones(4) / 4, np.zeros((4, 100)), np.ones((4, 100)))  # D > 63
+
+
+def test_full_size_properties(capi):
+    """BASELINE config sizes (2048c/60d) where the oracle would take minutes: size-independent
+    properties -- occupancies sum to the frame count, statistics are additive over a split of
+    the frames, and the device-resident path equals the host path."""
+    import torch
+    w, mean, cov = synth.make_ubm(2048, 60, seed=1)
+    T = 300_000
+    X = synth.make_frames(w, mean, cov, T, seed=9)
+    g = capi.GMM(w, mean, cov)
+    llk, n, occ, m1, m2 = g.em_accumulate(X)
+    assert n == T and abs(occ.sum() - T) < 1e-6 * T
+    la, _, oa, m1a, m2a = g.em_accumulate(X[:123_457])
+    lb, _, ob, m1b, m2b = g.em_accumulate(X[123_457:])
+    assert abs((la + lb) - llk) < 1e-9 * abs(llk)
+    assert np.allclose(oa + ob, occ, rtol=1e-9, atol=1e-9)
+    assert np.allclose(m2a + m2b, m2, rtol=1e-9, atol=1e-7)
+    # device-resident frames + device statistics
+    xd = torch.from_numpy(X).cuda()
+    feats = capi.Feats(device_ptr=xd.data_ptr(), T=T, ldx=60, D=60)
+    stats = torch.zeros(g.em_stats_len(), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    g.em_accumulate_dev(feats, 0, T, 1.0, stats.data_ptr())
+    capi.synchronize()
+    s = stats.cpu().numpy()
+    assert np.allclose(s[:2048], occ, rtol=1e-9, atol=1e-9)
+    assert np.allclose(s[2048:2048 + 2048 * 60], m1.reshape(-1), rtol=1e-9, atol=1e-7)
+    assert abs(s[-2] - llk) < 1e-9 * abs(llk) and s[-1] == T
+    # BW statistics: N row sums = frames per row, and F / N recovers the data mean per component
+    segs = [(i * 3000, 3000, i) for i in range(100)]
+    N, F = g.bwstats(X, segs, 100)
+    assert np.allclose(N.sum(1), 3000.0, rtol=1e-6)
