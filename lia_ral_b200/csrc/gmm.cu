@@ -58,8 +58,7 @@ lr_status gmm_derive(lr_gmm *g) {
       g->C, g->D, g->Cp, g->d_w, g->d_mean, g->d_cov, g->d_covinv, g->d_det, g->d_cst,
       g->cst_override ? 1 : 0, g->d_sa, g->d_nm, g->d_const2, g->d_mean_f);
   LR_CHECK_LAUNCH();
-  if (tc_supported(g)) return tc_derive(g);
-  return LR_OK;
+  return tc_derive(g);  // no-op for shapes the tensor-core path does not take
 }
 
 // ---- MixtureGDStat::getEM [alize-core] + varianceControl (TrainTools.cpp:567-587):
@@ -142,7 +141,7 @@ static void gmm_free(lr_gmm *g) {
   cudaFree(g->d_nm);
   cudaFree(g->d_const2);
   cudaFree(g->d_mean_f);
-  cudaFree(g->d_tc_w);
+  tc_free(g);
   cudaFree(g->d_g);
   cudaFree(g->d_s);
   cudaFree(g->d_gf);

@@ -74,5 +74,14 @@ lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_l
 lr_status tc_pass_acc(lr_gmm *g, const FrameList &fl, const float *d_lse2,
                       const LrChunk *d_chunks, int n_chunks, double fw, double *out_N,
                       double *out_F, double *out_S2);
+// likelihood + statistics over a tile-padded frame list (chunks tile aligned, host copy)
+lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk> &chunks,
+                       double fw, double *out_N, double *out_F, double *out_S2,
+                       double *d_llk_sum);
+void tc_free(lr_gmm *g);
+// true when the tensor-core path serves this model under the current lr_set_gmm_kernel choice;
+// sets *err when the choice is "tcgen05" but the model cannot be served
+bool tc_selected(const lr_gmm *g, lr_status *err);
+constexpr unsigned kPadFrame = 0xFFFFFFFFu;  // padding entry of a tile-padded frame list
 
 }  // namespace lr

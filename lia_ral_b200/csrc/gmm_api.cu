@@ -26,8 +26,10 @@ struct Clip {
 
 // Frame list + chunk list of the frames [b0, b1) (absolute), positions relative to `base`.
 // segs == nullptr selects every frame, row 0.  Chunks never straddle rows.
+// pad = true (tensor-core path): every row's run of positions is padded with kPadFrame entries
+// to a whole number of 128-frame tiles, so chunks are tile aligned.
 void build_plan(const lr_seg *segs, size_t n_segs, long b0, long b1, long base, bool use_rows,
-                Plan &plan) {
+                bool pad, Plan &plan) {
   plan.index.clear();
   plan.chunks.clear();
   plan.P = 0;
@@ -50,19 +52,24 @@ void build_plan(const lr_seg *segs, size_t n_segs, long b0, long b1, long base, 
                    [](const Clip &a, const Clip &b) { return a.row < b.row; });
   size_t total = 0;
   for (auto &c : clips) total += (size_t)c.len;
-  plan.index.resize(total);
+  plan.index.reserve(total + (pad ? 128 * (clips.size() + 1) : 0));
   long pos = 0;
   size_t i = 0;
   while (i < clips.size()) {
     int row = clips[i].row;
     long row_start = pos;
     while (i < clips.size() && clips[i].row == row) {
-      for (long k = 0; k < clips[i].len; k++) plan.index[pos + k] = (unsigned)(clips[i].begin + k);
+      for (long k = 0; k < clips[i].len; k++) plan.index.push_back((unsigned)(clips[i].begin + k));
       pos += clips[i].len;
       i++;
     }
     for (long p = row_start; p < pos; p += kChunkFrames)
       plan.chunks.push_back({p, (int)std::min<long>(kChunkFrames, pos - p), row});
+    if (pad)
+      while (pos % 128) {
+        plan.index.push_back(kPadFrame);
+        pos++;
+      }
   }
   plan.P = pos;
 }
@@ -80,11 +87,22 @@ lr_status check_segs(const lr_seg *segs, size_t n_segs, size_t T, size_t U, bool
 }
 
 // Upload the plan and run pass 1 (+ pass 2 when any output is requested) over it.
-lr_status run_plan(lr_gmm *g, const float *dX, size_t ldx, const Plan &plan, double fw,
+lr_status run_plan(lr_gmm *g, const float *dX, size_t ldx, const Plan &plan, bool tc, double fw,
                    double *dN, double *dF, double *dS2, double *d_llk_sum) {
   if (plan.P == 0) return LR_OK;
   Engine &e = engine();
-  float *d_lse = (float *)scratch_get(kSlotLse, plan.P * sizeof(float));
+  if (tc) {
+    unsigned *d_index = nullptr;
+    if (!plan.index.empty()) {
+      d_index = (unsigned *)scratch_get(kSlotIndex, plan.index.size() * sizeof(unsigned));
+      if (!d_index) return LR_ERR_CUDA;
+      LR_CUDA(cudaMemcpyAsync(d_index, plan.index.data(), plan.index.size() * sizeof(unsigned),
+                              cudaMemcpyHostToDevice, e.stream));
+    }
+    FrameList fl{dX, ldx, d_index, plan.P};
+    return tc_run_stats(g, fl, plan.chunks, fw, dN, dF, dS2, d_llk_sum);
+  }
+  float *d_lse = (float *)scratch_get(kSlotLse, (plan.P + 128) * sizeof(float));
   if (!d_lse) return LR_ERR_CUDA;
   unsigned *d_index = nullptr;
   if (!plan.index.empty()) {
@@ -178,10 +196,13 @@ lr_status lr_gmm_em_accumulate(lr_gmm *g, const float *X, size_t T, size_t ldx,
   seg_range(segs, n_segs, T, lo, hi);
   Plan plan;
   double total_pos = 0.0;
+  lr_status sel = LR_OK;
+  const bool tc = tc_selected(g, &sel);
+  if (sel != LR_OK) return sel;
   lr_status st = for_each_host_block(X, ldx, lo, hi, [&](const float *dX, long b0, long b1) {
-    build_plan(segs, n_segs, b0, b1, b0, false, plan);
-    total_pos += (double)plan.P;
-    return run_plan(g, dX, ldx, plan, frame_weight, d_stats, d_stats + C, d_stats + C + cd,
+    build_plan(segs, n_segs, b0, b1, b0, false, tc, plan);
+    for (auto &c : plan.chunks) total_pos += (double)c.len;
+    return run_plan(g, dX, ldx, plan, tc, frame_weight, d_stats, d_stats + C, d_stats + C + cd,
                     d_stats + C + 2 * cd);
   });
   if (st != LR_OK) return st;
@@ -205,11 +226,14 @@ lr_status lr_gmm_em_accumulate_dev(lr_gmm *g, const lr_feats *f, size_t t0, size
   LR_REQUIRE(f->D == g->D && t0 + T <= f->T, "lr_gmm_em_accumulate_dev: frame range / vectSize");
   size_t C = g->C, cd = (size_t)g->C * g->D;
   Plan plan;
+  lr_status sel = LR_OK;
+  const bool tc = tc_selected(g, &sel);
+  if (sel != LR_OK) return sel;
   const long step = 1L << 21;
   for (long b0 = (long)t0; b0 < (long)(t0 + T); b0 += step) {
     long b1 = std::min<long>((long)(t0 + T), b0 + step);
-    build_plan(nullptr, 0, b0, b1, b0, false, plan);
-    lr_status st = run_plan(g, f->d_x + (size_t)b0 * f->ldx, f->ldx, plan, frame_weight, d_stats,
+    build_plan(nullptr, 0, b0, b1, b0, false, tc, plan);
+    lr_status st = run_plan(g, f->d_x + (size_t)b0 * f->ldx, f->ldx, plan, tc, frame_weight, d_stats,
                             d_stats + C, d_stats + C + cd, d_stats + C + 2 * cd);
     if (st != LR_OK) return st;
   }
@@ -238,9 +262,12 @@ lr_status lr_gmm_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const 
   long lo, hi;
   seg_range(segs, n_segs, T, lo, hi);
   Plan plan;
+  lr_status sel = LR_OK;
+  const bool tc = tc_selected(g, &sel);
+  if (sel != LR_OK) return sel;
   lr_status st = for_each_host_block(X, ldx, lo, hi, [&](const float *dX, long b0, long b1) {
-    build_plan(segs, n_segs, b0, b1, b0, true, plan);
-    return run_plan(g, dX, ldx, plan, 1.0, dN.p, dF.p, nullptr, nullptr);
+    build_plan(segs, n_segs, b0, b1, b0, true, tc, plan);
+    return run_plan(g, dX, ldx, plan, tc, 1.0, dN.p, dF.p, nullptr, nullptr);
   });
   if (st != LR_OK) return st;
   LR_CUDA(cudaMemcpyAsync(N, dN.p, nN * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
@@ -261,12 +288,14 @@ lr_status lr_gmm_bwstats_dev(lr_gmm *g, const lr_feats *f, const lr_seg *segs, s
   long lo, hi;
   seg_range(segs, n_segs, f->T, lo, hi);
   Plan plan;
+  lr_status sel = LR_OK;
+  const bool tc = tc_selected(g, &sel);
+  if (sel != LR_OK) return sel;
   const long step = 1L << 21;
   for (long b0 = lo; b0 < hi; b0 += step) {
     long b1 = std::min(hi, b0 + step);
-    build_plan(segs, n_segs, b0, b1, 0, true, plan);
-    // plan uploads reuse the scratch slots: the previous block's kernels must have consumed them
-    lr_status st = run_plan(g, f->d_x, f->ldx, plan, 1.0, d_N, d_F, nullptr, nullptr);
+    build_plan(segs, n_segs, b0, b1, 0, true, tc, plan);
+    lr_status st = run_plan(g, f->d_x, f->ldx, plan, tc, 1.0, d_N, d_F, nullptr, nullptr);
     if (st != LR_OK) return st;
   }
   return LR_OK;
@@ -278,13 +307,16 @@ lr_status lr_gmm_llk(lr_gmm *g, const float *X, size_t T, size_t ldx, double min
   LR_READY();
   LR_REQUIRE(g && X && llk && ldx >= (size_t)g->D, "lr_gmm_llk: bad argument");
   Engine &e = engine();
+  lr_status sel = LR_OK;
+  const bool tc = tc_selected(g, &sel);
+  if (sel != LR_OK) return sel;
   return for_each_host_block(X, ldx, 0, (long)T, [&](const float *dX, long b0, long b1) {
     long P = b1 - b0;
-    float *d_lse = (float *)scratch_get(kSlotLse, P * sizeof(float));
+    float *d_lse = (float *)scratch_get(kSlotLse, (P + 128) * sizeof(float));
     double *d_llk = (double *)scratch_get(kSlotLlk, P * sizeof(double));
     if (!d_lse || !d_llk) return (lr_status)LR_ERR_CUDA;
     FrameList fl{dX, ldx, nullptr, P};
-    lr_status st = gmm_pass_lse(g, fl, d_lse, nullptr, nullptr);
+    lr_status st = tc ? tc_pass_lse(g, fl, d_lse, nullptr) : gmm_pass_lse(g, fl, d_lse, nullptr, nullptr);
     if (st != LR_OK) return st;
     st = gmm_llk_from_lse(P, d_lse, min_llk, max_llk, d_llk);
     if (st != LR_OK) return st;
@@ -298,7 +330,7 @@ lr_status lr_gmm_llk(lr_gmm *g, const float *X, size_t T, size_t ldx, double min
 static lr_status topk_block(lr_gmm *world, const float *dX, size_t ldx, long P, int K, int complete,
                             double min_llk, double max_llk, double **d_llk, unsigned **d_idx,
                             double **d_top, double **d_rest, double **d_restw) {
-  float *d_lse = (float *)scratch_get(kSlotLse, P * sizeof(float));
+  float *d_lse = (float *)scratch_get(kSlotLse, (P + 128) * sizeof(float));
   float *d_S = (float *)scratch_get(kSlotS, (size_t)P * world->Cp * sizeof(float));
   *d_llk = (double *)scratch_get(kSlotLlk, P * sizeof(double));
   *d_idx = (unsigned *)scratch_get(kSlotIdx, (size_t)P * K * sizeof(unsigned));

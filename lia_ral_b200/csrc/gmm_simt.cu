@@ -321,13 +321,6 @@ lr_status gmm_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, float *d_S
                        double *d_llk_sum) {
   if (fl.P <= 0) return LR_OK;
   Engine &e = engine();
-  if (e.gmm_kernel == 2 && !d_S) {
-    if (!tc_supported(g))
-      return fail(LR_ERR_ARG, "tcgen05 GMM kernel forced but shape C=%d D=%d is unsupported",
-                  g->C, g->D);
-    return tc_pass_lse(g, fl, d_lse2, d_llk_sum);
-  }
-  if (e.gmm_kernel == 0 && !d_S && tc_supported(g)) return tc_pass_lse(g, fl, d_lse2, d_llk_sum);
   size_t sm = lse_smem(g->D);
   static bool attr_set = false;
   if (!attr_set) {
@@ -348,14 +341,6 @@ lr_status gmm_pass_acc(lr_gmm *g, const FrameList &fl, const float *d_lse2,
                        double *out_F, double *out_S2) {
   if (n_chunks <= 0) return LR_OK;
   Engine &e = engine();
-  if (e.gmm_kernel == 2) {
-    if (!tc_supported(g))
-      return fail(LR_ERR_ARG, "tcgen05 GMM kernel forced but shape C=%d D=%d is unsupported",
-                  g->C, g->D);
-    return tc_pass_acc(g, fl, d_lse2, d_chunks, n_chunks, fw, out_N, out_F, out_S2);
-  }
-  if (e.gmm_kernel == 0 && tc_supported(g))
-    return tc_pass_acc(g, fl, d_lse2, d_chunks, n_chunks, fw, out_N, out_F, out_S2);
   size_t sm = acc_smem(g->D);
   static bool attr_set = false;
   if (!attr_set) {

@@ -1,22 +1,991 @@
 // gmm_tc.cu -- tcgen05 / TMEM implementation of the frames x components passes (sm_100a).
+//
+// Formulation.  In the globally normalised space xh = (x - g) / s (g, s = mixture mean / std per
+// dimension) the log2 joint likelihood is an inner product over K = 128 columns
+//     S2[t,c] = sum_k A[t,k] W[c,k],   A[t,:] = [xh (60) | 1 1 1 | 0 || xh^2 (60) | 0000]
+//     W[c,:] = [-2 alpha beta | K_c split in 3 | 0 || -alpha^2 | 0],  alpha = s sa, beta = g sa + nm
+// Both operands are split hi + lo into two fp16 values (22 significand bits) and the contraction
+// is three fp16 UMMAs with fp32 accumulation in TMEM:  A_hi W_hi + A_lo W_hi + A_hi W_lo.
+//
+// Data layout.  k_tc_convert writes the frame operand once per call as 64 KB tiles of 128
+// frames: four 16 KB panels [xh_hi,1 | xh^2_hi | xh_lo | xh^2_lo], each 128 rows x 64 fp16 in the
+// canonical 128-byte-swizzle layout, so one cp.async.bulk per panel lands it ready for UMMA --
+// as the K-major operand of the likelihood GEMM and, read MN-major, as the B operand of the
+// statistics GEMM.  Each CTA owns a slice of 128 components whose weights (64 KB) stay resident
+// in shared memory for the whole kernel; the grid is (slices x groups), every group streaming a
+// contiguous range of frame tiles through a two-stage mbarrier ring.
+//
+// Pass 1 (k_tc_lse):   D[t, c] = A W^T  (frames on TMEM lanes), per-frame online (max, sum) over
+//                      the slice's 128 columns -> partial log-sum-exp per (slice, frame).
+// Pass 2 (k_tc_acc):   D[c, t] = W A^T  (components on lanes), g' = 2^(S - lse + 14) packed to
+//                      fp16 back into TMEM, then the TS-UMMA  F[c, d] += g'[c, t] A[t, d]  with the
+//                      frame tile as MN-major B operand: N, sum g xh (hi, lo), sum g xh^2 (hi, lo)
+//                      accumulate in TMEM across the tiles of a run and are flushed in fp64.
+#include <cuda_fp16.h>
+
 #include "gmm.cuh"
 
 namespace lr {
 
-bool tc_supported(const lr_gmm *g) {
-  (void)g;
-  return false;
+namespace {
+
+constexpr int kTile = 128;                     // frames per tile
+constexpr int kSlice = 128;                    // components per CTA
+constexpr int kPanelBytes = 128 * 128;         // 128 rows x 64 fp16
+constexpr int kTileBytes = 4 * kPanelBytes;    // 64 KB
+constexpr int kStages = 2;
+constexpr unsigned kPadIndex = 0xFFFFFFFFu;
+constexpr int kOneCol = 60;                    // columns 60..62 of panel a carry 1.0
+constexpr float kGammaShift = 14.f;            // posteriors are stored as fp16(2^14 g)
+constexpr float kXClamp = 240.f;               // |xh| clamp (xh^2 must stay below fp16 max)
+constexpr int kMaxRunTiles = 32;               // fp32 TMEM partial sums are flushed at least this often
+constexpr int kTcThreads = 256;
+constexpr size_t kTcSmem = 1024 + 64 * 1024 + kStages * (size_t)kTileBytes + 1024;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ----------------------------
+// shared-memory matrix descriptor, 128-byte swizzle, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: fp16 x fp16 -> fp32, M x N, operand majors (0 = K, 1 = MN)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+struct TileInfo {
+  int row;    // output row: statistics row, or slab row when bit 2 is set
+  int flags;  // bit 0: first tile of a run (accumulator starts from zero); bit 1: flush after;
+              // bit 2: the run belongs to a row shared between groups -> flush into the slab
+};
+
+// split v into fp16 hi + lo
+__device__ __forceinline__ void split2(float v, __half &hi, __half &lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// ------------------------------------------------------------------ operand preparation
+// g, s per dimension: mixture mean / standard deviation (fp64)
+__global__ void k_tc_norm(int C, int D, const double *__restrict__ w,
+                          const double *__restrict__ mean, const double *__restrict__ cov,
+                          double *__restrict__ g, double *__restrict__ s, float *__restrict__ gf,
+                          float *__restrict__ rsf) {
+  int i = blockIdx.x;
+  if (i >= D) return;
+  __shared__ double sh[3][256];
+  double a = 0.0, b = 0.0, ws = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double m = mean[(size_t)c * D + i];
+    a += w[c] * m;
+    b += w[c] * (cov[(size_t)c * D + i] + m * m);
+    ws += w[c];
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  sh[2][threadIdx.x] = ws;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      for (int k = 0; k < 3; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double wsum = sh[2][0] > 0.0 ? sh[2][0] : 1.0;
+    double gi = sh[0][0] / wsum;
+    double var = sh[1][0] / wsum - gi * gi;
+    double si = var > 1e-300 ? sqrt(var) : 1.0;
+    // the converter normalises with the fp32 values; the weights and the flush use exactly those
+    float gfl = (float)gi, rsfl = (float)(1.0 / si);
+    gf[i] = gfl;
+    rsf[i] = rsfl;
+    g[i] = (double)gfl;
+    s[i] = 1.0 / (double)rsfl;
+  }
+}
+
+// swizzled byte offset of element (row, col) inside a 128 x 64 fp16 panel
+__host__ __device__ __forceinline__ uint32_t panel_off(int row, int col) {
+  return (uint32_t)row * 128u + (uint32_t)((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
+}
+
+// weights of one component -> [slice][hi a | hi b | lo a | lo b] panels.  One thread per comp.
+__global__ void k_tc_weights(int C, int D, int Cp, const double *__restrict__ w,
+                             const double *__restrict__ mean, const double *__restrict__ covinv,
+                             const double *__restrict__ cst, const double *__restrict__ g,
+                             const double *__restrict__ s, unsigned char *__restrict__ Wp,
+                             int *__restrict__ flag) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  unsigned char *base = Wp + (size_t)(c / kSlice) * (4 * kPanelBytes);
+  const int row = c % kSlice;
+  auto put = [&](int panel, int col, __half v) {
+    *reinterpret_cast<__half *>(base + (size_t)panel * kPanelBytes + panel_off(row, col)) = v;
+  };
+  const __half z = __float2half_rn(0.f);
+  for (int p = 0; p < 4; p++)
+    for (int col = 0; col < 64; col++) put(p, col, z);
+  if (c >= C) {
+    put(0, kOneCol, __float2half_rn(-60000.f));  // padding component: S2 = -60000 -> 2^S2 = 0
+    return;
+  }
+  const double kHalfLog2e = 0.72134752044448170368;
+  double kc = log2(w[c]) + log2(cst[c]);
+  bool bad = !(w[c] > 0.0) || !isfinite(kc);
+  double maxabs = 0.0;
+  for (int i = 0; i < D; i++) {
+    double sa = sqrt(kHalfLog2e * covinv[(size_t)c * D + i]);
+    double alpha = s[i] * sa;
+    double beta = (g[i] - mean[(size_t)c * D + i]) * sa;
+    double w1 = -2.0 * alpha * beta, w2 = -alpha * alpha;
+    kc -= beta * beta;
+    maxabs = fmax(maxabs, fmax(fabs(w1), fabs(w2)));
+    __half h, l;
+    split2((float)w1, h, l);
+    // second-order correction of the float cast: lo also absorbs (w1 - float(w1))
+    l = __float2half_rn((float)(w1 - (double)__half2float(h)));
+    put(0, i, h);
+    put(2, i, l);
+    h = __float2half_rn((float)w2);
+    l = __float2half_rn((float)(w2 - (double)__half2float(h)));
+    put(1, i, h);
+    put(3, i, l);
+  }
+  if (bad) {
+    put(0, kOneCol, __float2half_rn(-60000.f));
+    return;
+  }
+  if (fabs(kc) > 30000.0 || maxabs > 30000.0) atomicExch(flag, 1);  // outside the fp16 range
+  __half k0 = __float2half_rn((float)kc);
+  double r1 = kc - (double)__half2float(k0);
+  __half k1 = __float2half_rn((float)r1);
+  double r2 = r1 - (double)__half2float(k1);
+  __half k2 = __float2half_rn((float)r2);
+  put(0, kOneCol, k0);
+  put(0, kOneCol + 1, k1);
+  put(0, kOneCol + 2, k2);
+}
+
+// frames -> swizzled fp16 hi/lo tiles.  One thread per (row, 16-byte chunk).
+__global__ void __launch_bounds__(256)
+k_tc_convert(int D, const float *__restrict__ X, size_t ldx, const unsigned *__restrict__ index,
+             long P, long P_pad, const float *__restrict__ gf, const float *__restrict__ rsf,
+             unsigned char *__restrict__ Xh) {
+  long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long p = gid >> 3;
+  int j = (int)(gid & 7);
+  if (p >= P_pad) return;
+  long tile = p / kTile;
+  int row = (int)(p - tile * kTile);
+  bool valid = p < P;
+  size_t fr = 0;
+  if (valid) {
+    if (index) {
+      unsigned ix = index[p];
+      valid = ix != kPadIndex;
+      fr = ix;
+    } else {
+      fr = (size_t)p;
+    }
+  }
+  __align__(16) __half ha[8], la[8], hb[8], lb[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    int k = j * 8 + e;
+    float xa = 0.f, xb = 0.f;
+    if (valid) {
+      if (k < D) {
+        float v = (X[fr * ldx + k] - gf[k]) * rsf[k];
+        v = fminf(fmaxf(v, -kXClamp), kXClamp);
+        xa = v;
+        xb = v * v;
+      } else if (k >= kOneCol && k < kOneCol + 3) {
+        xa = 1.f;
+      }
+    }
+    split2(xa, ha[e], la[e]);
+    split2(xb, hb[e], lb[e]);
+    if (k >= kOneCol) la[e] = __float2half_rn(0.f);
+  }
+  unsigned char *t = Xh + (size_t)tile * kTileBytes;
+  uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+  *reinterpret_cast<uint4 *>(t + 0 * kPanelBytes + off) = *reinterpret_cast<const uint4 *>(ha);
+  *reinterpret_cast<uint4 *>(t + 1 * kPanelBytes + off) = *reinterpret_cast<const uint4 *>(hb);
+  *reinterpret_cast<uint4 *>(t + 2 * kPanelBytes + off) = *reinterpret_cast<const uint4 *>(la);
+  *reinterpret_cast<uint4 *>(t + 3 * kPanelBytes + off) = *reinterpret_cast<const uint4 *>(lb);
+}
+
+// ------------------------------------------------------------------ shared kernel scaffolding
+struct Smem {
+  uint32_t w;           // weights slice: hi a | hi b | lo a | lo b
+  uint32_t stage[kStages];
+  uint32_t full[kStages], empty[kStages];
+  uint32_t s_full[2], s_empty[2], p_full[2];
+  uint32_t f_full, f_empty, w_full;
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char *raw) {
+  uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  Smem s;
+  s.w = base;
+  for (int i = 0; i < kStages; i++) s.stage[i] = base + 64 * 1024 + i * kTileBytes;
+  uint32_t b = base + 64 * 1024 + kStages * kTileBytes;
+  for (int i = 0; i < kStages; i++) {
+    s.full[i] = b + 8 * i;
+    s.empty[i] = b + 16 + 8 * i;
+  }
+  for (int i = 0; i < 2; i++) {
+    s.s_full[i] = b + 32 + 8 * i;
+    s.s_empty[i] = b + 48 + 8 * i;
+    s.p_full[i] = b + 64 + 8 * i;
+  }
+  s.f_full = b + 80;
+  s.f_empty = b + 88;
+  s.w_full = b + 96;
+  s.tmem_slot = b + 104;
+  return s;
+}
+
+// the likelihood GEMM of one tile: 3 products x 2 panels x 4 K-steps of 16
+//   w_is_a: true  -> D[c, t] (A = weights, B = frames)   (pass 2)
+//           false -> D[t, c] (A = frames,  B = weights)  (pass 1)
+__device__ __forceinline__ void issue_g1(uint32_t d_tmem, uint32_t w_base, uint32_t x_base,
+                                         bool w_is_a) {
+  constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
+  // (weights panel, frames panel): hi_a P1a, hi_b P1b, hi_a P2a, hi_b P2b, lo_a P1a, lo_b P1b
+  const int wp[6] = {0, 1, 0, 1, 2, 3};
+  const int xp[6] = {0, 1, 2, 3, 0, 1};
+  uint32_t acc = 0;
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      uint64_t wd = make_desc(w_base + wp[q] * kPanelBytes + kk * 32, 16, 1024);
+      uint64_t xd = make_desc(x_base + xp[q] * kPanelBytes + kk * 32, 16, 1024);
+      if (w_is_a)
+        umma_ss(d_tmem, wd, xd, idesc, acc);
+      else
+        umma_ss(d_tmem, xd, wd, idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pass 1
+// grid = slices * groups.  Partial (max, sum) of 2^S over the slice's components per frame.
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_tc_lse(int n_slices, const unsigned char *__restrict__ Wp, const unsigned char *__restrict__ Xh,
+         const int *__restrict__ group_tiles /*[groups + 1]*/, long P_pad,
+         float2 *__restrict__ part /*[slices][P_pad]*/) {
+  extern __shared__ unsigned char smem_raw[];
+  const Smem sm = carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % n_slices, group = blockIdx.x / n_slices;
+  const int t_begin = group_tiles[group], t_end = group_tiles[group + 1];
+  const int n_tiles = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; i++) {
+      mbar_init(sm.full[i], 1);
+      mbar_init(sm.empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(sm.s_full[i], 1);
+      mbar_init(sm.s_empty[i], 4);
+    }
+    mbar_init(sm.w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(sm.tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(sm.w_full, 4 * kPanelBytes);
+      for (int p = 0; p < 4; p++)
+        bulk_g2s(sm.w + p * kPanelBytes, Wp + (size_t)slice * 4 * kPanelBytes + (size_t)p * kPanelBytes,
+                 kPanelBytes, sm.w_full);
+      for (int i = 0; i < n_tiles; i++) {
+        int st = i % kStages;
+        mbar_wait(sm.empty[st], ((i / kStages) & 1) ^ 1);
+        mbar_expect_tx(sm.full[st], kTileBytes);
+        const unsigned char *src = Xh + (size_t)(t_begin + i) * kTileBytes;
+        for (int p = 0; p < 4; p++)
+          bulk_g2s(sm.stage[st] + p * kPanelBytes, src + (size_t)p * kPanelBytes, kPanelBytes,
+                   sm.full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(sm.w_full, 0);
+      for (int i = 0; i < n_tiles; i++) {
+        int st = i % kStages, buf = i & 1;
+        mbar_wait(sm.full[st], (i / kStages) & 1);
+        mbar_wait(sm.s_empty[buf], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        issue_g1(tmem_base + buf * 128, sm.w, sm.stage[st], false);
+        umma_commit(sm.empty[st]);
+        umma_commit(sm.s_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;  // TMEM lane quarter of this warp
+    for (int i = 0; i < n_tiles; i++) {
+      int buf = i & 1;
+      mbar_wait(sm.s_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      float m = -3.0e38f, s = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ch++) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + ch * 32, r);
+        tmem_wait_ld();
+        float cm = -3.0e38f;
+#pragma unroll
+        for (int e = 0; e < 32; e++) cm = fmaxf(cm, __uint_as_float(r[e]));
+        float mn = fmaxf(m, cm);
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e++) acc += ex2f(__uint_as_float(r[e]) - mn);
+        s = s * ex2f(m - mn) + acc;
+        m = mn;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.s_empty[buf]);
+      long p = (long)(t_begin + i) * kTile + q * 32 + lane;
+      part[(size_t)slice * P_pad + p] = make_float2(m, s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// combine the per-slice partials: lse2[p] = log2 sum_c 2^S ; llk_sum += ln2 * sum over valid p
+__global__ void k_tc_combine(int n_slices, long P, long P_pad, const unsigned *__restrict__ index,
+                             const float2 *__restrict__ part, float *__restrict__ lse2,
+                             double *__restrict__ llk_sum) {
+  long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double mine = 0.0;
+  if (p < P_pad) {
+    float m = -3.0e38f;
+    for (int sl = 0; sl < n_slices; sl++) m = fmaxf(m, part[(size_t)sl * P_pad + p].x);
+    float s = 0.f;
+    for (int sl = 0; sl < n_slices; sl++) {
+      float2 v = part[(size_t)sl * P_pad + p];
+      s += v.y * ex2f(v.x - m);
+    }
+    float l = m + log2f(s);
+    lse2[p] = l;
+    bool valid = p < P && (!index || index[p] != kPadIndex);
+    if (valid) mine = (double)l;
+  }
+  if (llk_sum) {
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+      if (t != 0.0) atomicAdd(llk_sum, t * 0.69314718055994530942);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pass 2
+// TMEM columns: S/P buffers at 0 and 128, statistics accumulator at 256 (N2 columns).
+template <bool EM>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_tc_acc(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
+         const unsigned char *__restrict__ Xh, const int *__restrict__ group_tiles,
+         const TileInfo *__restrict__ tinfo, const float *__restrict__ lse2,
+         const double *__restrict__ g, const double *__restrict__ s, double fw,
+         double *__restrict__ out_N, double *__restrict__ out_F, double *__restrict__ out_S2,
+         double *__restrict__ slab_N, double *__restrict__ slab_F, double *__restrict__ slab_S2) {
+  constexpr int N2 = EM ? 256 : 128;
+  constexpr uint32_t kLbo2 = EM ? 16384u : 32768u;  // distance between 64-wide MN chunks of B
+  constexpr uint32_t idesc2 = make_idesc(128, N2, 0, 1);
+  extern __shared__ unsigned char smem_raw[];
+  const Smem sm = carve(smem_raw);
+  __shared__ float nl_s[2][kTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % n_slices, group = blockIdx.x / n_slices;
+  const int t_begin = group_tiles[group], t_end = group_tiles[group + 1];
+  const int n_tiles = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; i++) {
+      mbar_init(sm.full[i], 1);
+      mbar_init(sm.empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(sm.s_full[i], 1);
+      mbar_init(sm.p_full[i], 4);
+    }
+    mbar_init(sm.f_full, 1);
+    mbar_init(sm.f_empty, 4);
+    mbar_init(sm.w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(sm.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot));
+  const uint32_t tmem_f = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(sm.w_full, 4 * kPanelBytes);
+      for (int p = 0; p < 4; p++)
+        bulk_g2s(sm.w + p * kPanelBytes, Wp + (size_t)slice * 4 * kPanelBytes + (size_t)p * kPanelBytes,
+                 kPanelBytes, sm.w_full);
+      for (int i = 0; i < n_tiles; i++) {
+        int st = i % kStages;
+        mbar_wait(sm.empty[st], ((i / kStages) & 1) ^ 1);
+        mbar_expect_tx(sm.full[st], kTileBytes);
+        const unsigned char *src = Xh + (size_t)(t_begin + i) * kTileBytes;
+        for (int p = 0; p < 4; p++)
+          bulk_g2s(sm.stage[st] + p * kPanelBytes, src + (size_t)p * kPanelBytes, kPanelBytes,
+                   sm.full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_tiles > 0) {
+      mbar_wait(sm.w_full, 0);
+      mbar_wait(sm.full[0], 0);
+      tc_fence_after();
+      issue_g1(tmem_base, sm.w, sm.stage[0], true);
+      umma_commit(sm.s_full[0]);
+      int n_flush = 0;  // flushes requested so far
+      for (int i = 0; i < n_tiles; i++) {
+        const int st = i % kStages, buf = i & 1;
+        if (i + 1 < n_tiles) {
+          const int st1 = (i + 1) % kStages, buf1 = (i + 1) & 1;
+          mbar_wait(sm.full[st1], ((i + 1) / kStages) & 1);
+          tc_fence_after();
+          issue_g1(tmem_base + buf1 * 128, sm.w, sm.stage[st1], true);
+          umma_commit(sm.s_full[buf1]);
+        }
+        const TileInfo ti = tinfo[t_begin + i];
+        mbar_wait(sm.p_full[buf], (i >> 1) & 1);
+        if ((ti.flags & 1) && n_flush > 0) mbar_wait(sm.f_empty, (n_flush - 1) & 1);
+        tc_fence_after();
+        // F[c, d] (+)= P[c, t] A[t, d]: 8 K-steps of 16 frames; P is fp16 packed in the S columns
+        uint32_t acc = (ti.flags & 1) ? 0u : 1u;
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+          uint64_t bd = make_desc(sm.stage[st] + kk * 2048, kLbo2, 1024);
+          umma_ts(tmem_f, tmem_base + buf * 128 + kk * 8, bd, idesc2, acc);
+          acc = 1;
+        }
+        umma_commit(sm.empty[st]);
+        if (ti.flags & 2) {
+          umma_commit(sm.f_full);
+          n_flush++;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int et = threadIdx.x - 128;  // 0..127
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int n_flush = 0;
+    for (int i = 0; i < n_tiles; i++) {
+      const int buf = i & 1;
+      // 14 - lse2 of the tile's frames (columns), shared by the four epilogue warps
+      nl_s[buf][et] = kGammaShift - lse2[(size_t)(t_begin + i) * kTile + et];
+      named_bar_sync(1, 128);
+      mbar_wait(sm.s_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ch++) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_addr + buf * 128 + ch * 32, r);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          float a = ex2f(__uint_as_float(r[2 * e]) + nl_s[buf][ch * 32 + 2 * e]);
+          float b = ex2f(__uint_as_float(r[2 * e + 1]) + nl_s[buf][ch * 32 + 2 * e + 1]);
+          a = fminf(a, 65504.f);
+          b = fminf(b, 65504.f);
+          __half2 h = __floats2half2_rn(a, b);
+          pk[e] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        tmem_st16(tmem_base + lane_addr + buf * 128 + ch * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.p_full[buf]);
+
+      const TileInfo ti = tinfo[t_begin + i];
+      if (ti.flags & 2) {
+        // flush the accumulator of this run: lane = component, columns = statistics
+        // EM : [xh hi,1 | xh^2 hi | xh lo | xh^2 lo] (4 x 64);  BW: [xh hi,1 | xh lo] (2 x 64)
+        mbar_wait(sm.f_full, n_flush & 1);
+        n_flush++;
+        tc_fence_after();
+        const int comp = slice * kSlice + q * 32 + lane;
+        const bool slab = (ti.flags & 4) != 0;
+        double *oN = slab ? slab_N : out_N, *oF = slab ? slab_F : out_F, *oS = slab ? slab_S2 : out_S2;
+        const double sc = 1.0 / 16384.0;  // undo the 2^14 posterior scale
+        constexpr int kLoCol = EM ? 128 : 64;
+        const double n = (double)__uint_as_float(tmem_ld1(tmem_f + lane_addr + kOneCol)) * sc;
+        const size_t rc = (size_t)ti.row * C + comp;
+        const bool live = comp < C;
+        if (live && oN) oN[rc] += fw * n;
+#pragma unroll 1
+        for (int h = 0; h < 4; h++) {
+          uint32_t a_hi[16], a_lo[16];
+          tmem_ld16(tmem_f + lane_addr + h * 16, a_hi);
+          tmem_ld16(tmem_f + lane_addr + kLoCol + h * 16, a_lo);
+          tmem_wait_ld();
+          double f[16];
+#pragma unroll
+          for (int e = 0; e < 16; e++)
+            f[e] = ((double)__uint_as_float(a_hi[e]) + (double)__uint_as_float(a_lo[e])) * sc;
+          if (live && oF) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+              int k = h * 16 + e;
+              if (k < D) oF[rc * D + k] += fw * (s[k] * f[e] + g[k] * n);
+            }
+          }
+          if (EM) {
+            tmem_ld16(tmem_f + lane_addr + 64 + h * 16, a_hi);
+            tmem_ld16(tmem_f + lane_addr + 192 + h * 16, a_lo);
+            tmem_wait_ld();
+            if (live && oS) {
+#pragma unroll
+              for (int e = 0; e < 16; e++) {
+                int k = h * 16 + e;
+                if (k < D) {
+                  double q2 = ((double)__uint_as_float(a_hi[e]) + (double)__uint_as_float(a_lo[e])) * sc;
+                  double sk = s[k], gk = g[k];
+                  oS[rc * D + k] += fw * (sk * sk * q2 + 2.0 * sk * gk * f[e] + gk * gk * n);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.f_empty);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// out[row(v)] += slab[v] for the virtual rows that share a real row
+__global__ void k_tc_reduce_slabs(int n_slab, const int *__restrict__ slab_row, size_t per_row,
+                                  const double *__restrict__ slab, double *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_row) return;
+  for (int v = 0; v < n_slab; v++) {
+    double x = slab[(size_t)v * per_row + i];
+    if (x != 0.0) atomicAdd(&out[(size_t)slab_row[v] * per_row + i], x);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+struct TcState {
+  unsigned char *d_W = nullptr;  // [slices][64 KB]
+  int *d_flag = nullptr;
+  bool ok = false;
+};
+
+bool tc_supported(const lr_gmm *g) {
+  if (!g || g->D > kOneCol) return false;
+  const TcState *st = (const TcState *)g->d_tc_w;
+  return st && st->ok;
+}
+
+// Auto mode (lr_set_gmm_kernel(0)) takes the tensor-core path when the model supports it and
+// has at least two slices of components; the SIMT path serves everything else.
+bool tc_selected(const lr_gmm *g, lr_status *err) {
+  Engine &e = engine();
+  if (err) *err = LR_OK;
+  if (e.gmm_kernel == 1) return false;
+  if (e.gmm_kernel == 2) {
+    if (!tc_supported(g)) {
+      if (err)
+        *err = fail(LR_ERR_ARG,
+                    "tcgen05 GMM kernel forced but this model (C=%d, D=%d) is outside its range",
+                    g->C, g->D);
+      return false;
+    }
+    return true;
+  }
+  return tc_supported(g) && g->C >= 256;
+}
+
 lr_status tc_derive(lr_gmm *g) {
-  (void)g;
+  Engine &e = engine();
+  if (g->D > kOneCol) return LR_OK;
+  TcState *st = (TcState *)g->d_tc_w;
+  if (!st) {
+    st = new TcState();
+    g->d_tc_w = st;
+    size_t wbytes = (size_t)(g->Cp / kSlice) * 4 * kPanelBytes;
+    LR_CUDA(cudaMalloc(&st->d_W, wbytes));
+    LR_CUDA(cudaMalloc(&st->d_flag, sizeof(int)));
+    LR_CUDA(cudaMalloc(&g->d_g, g->D * sizeof(double)));
+    LR_CUDA(cudaMalloc(&g->d_s, g->D * sizeof(double)));
+    LR_CUDA(cudaMalloc(&g->d_gf, 64 * sizeof(float)));
+    LR_CUDA(cudaMalloc(&g->d_rsf, 64 * sizeof(float)));
+  }
+  LR_CUDA(cudaMemsetAsync(st->d_flag, 0, sizeof(int), e.stream));
+  k_tc_norm<<<g->D, 256, 0, e.stream>>>(g->C, g->D, g->d_w, g->d_mean, g->d_cov, g->d_g, g->d_s,
+                                        g->d_gf, g->d_rsf);
+  LR_CHECK_LAUNCH();
+  k_tc_weights<<<ceil_div(g->Cp, 128), 128, 0, e.stream>>>(g->C, g->D, g->Cp, g->d_w, g->d_mean,
+                                                           g->d_covinv, g->d_cst, g->d_g, g->d_s,
+                                                           st->d_W, st->d_flag);
+  LR_CHECK_LAUNCH();
+  int flag = 0;
+  LR_CUDA(cudaMemcpyAsync(&flag, st->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  st->ok = flag == 0;  // weights outside the fp16 range -> this model stays on the SIMT path
   return LR_OK;
 }
-lr_status tc_pass_lse(lr_gmm *, const FrameList &, float *, double *) {
-  return fail(LR_ERR_ARG, "tcgen05 GMM pass not built");
+
+void tc_free(lr_gmm *g) {
+  TcState *st = (TcState *)g->d_tc_w;
+  if (!st) return;
+  cudaFree(st->d_W);
+  cudaFree(st->d_flag);
+  delete st;
+  g->d_tc_w = nullptr;
 }
+
+// Split [0, n_tiles) into `groups` contiguous ranges; cut points snap to run starts when a run
+// boundary is close so that most rows stay inside one group.
+static void split_groups(int n_tiles, int groups, std::vector<int> &cuts) {
+  cuts.resize(groups + 1);
+  for (int gidx = 0; gidx <= groups; gidx++) cuts[gidx] = (int)((long)n_tiles * gidx / groups);
+}
+
+static lr_status tc_set_attrs() {
+  static bool done = false;
+  if (done) return LR_OK;
+  LR_CUDA(cudaFuncSetAttribute(k_tc_lse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_acc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_acc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  done = true;
+  return LR_OK;
+}
+
+// The tensor-core path works on a PADDED frame list (P_pad = multiple of 128; padding entries
+// carry index 0xFFFFFFFF): see tc_pad_plan in gmm_api.cu.  fl.P is the padded length here.
+lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_llk_sum) {
+  Engine &e = engine();
+  TcState *st = (TcState *)g->d_tc_w;
+  lr_status rc = tc_set_attrs();
+  if (rc != LR_OK) return rc;
+  const long P = fl.P;
+  const long P_pad = (P + kTile - 1) / kTile * kTile;
+  const int n_tiles = (int)(P_pad / kTile);
+  const int n_slices = g->Cp / kSlice;
+  const int groups = std::max(1, std::min(n_tiles, e.sm_count / n_slices));
+  unsigned char *Xh = (unsigned char *)scratch_get(kSlotTmpA, (size_t)n_tiles * kTileBytes);
+  float2 *part = (float2 *)scratch_get(kSlotTmpB, (size_t)n_slices * P_pad * sizeof(float2));
+  int *d_cuts = (int *)scratch_get(kSlotRest, (groups + 1) * sizeof(int));
+  if (!Xh || !part || !d_cuts) return LR_ERR_CUDA;
+  std::vector<int> cuts;
+  split_groups(n_tiles, groups, cuts);
+  LR_CUDA(cudaMemcpyAsync(d_cuts, cuts.data(), (groups + 1) * sizeof(int), cudaMemcpyHostToDevice,
+                          e.stream));
+  k_tc_convert<<<(unsigned)((P_pad * 8 + 255) / 256), 256, 0, e.stream>>>(
+      g->D, fl.dX, fl.ldx, fl.d_index, P, P_pad, g->d_gf, g->d_rsf, Xh);
+  LR_CHECK_LAUNCH();
+  {
+    ProfileScope prof(0);
+    k_tc_lse<<<n_slices * groups, kTcThreads, kTcSmem, e.stream>>>(n_slices, st->d_W, Xh, d_cuts,
+                                                                   P_pad, part);
+    LR_CHECK_LAUNCH();
+  }
+  k_tc_combine<<<(unsigned)((P_pad + 255) / 256), 256, 0, e.stream>>>(n_slices, P, P_pad, fl.d_index,
+                                                                     part, d_lse2, d_llk_sum);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
 lr_status tc_pass_acc(lr_gmm *, const FrameList &, const float *, const LrChunk *, int, double,
                       double *, double *, double *) {
-  return fail(LR_ERR_ARG, "tcgen05 GMM pass not built");
+  return fail(LR_ERR_ARG, "tc_pass_acc: the tensor-core statistics pass is driven by tc_run_stats");
+}
+
+// Likelihood + statistics over a frame list whose row runs are padded to whole tiles
+// (build_plan(..., pad = true)): chunk.pos % 128 == 0, padding entries carry kPadIndex.
+lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk> &chunks,
+                       double fw, double *out_N, double *out_F, double *out_S2,
+                       double *d_llk_sum) {
+  Engine &e = engine();
+  TcState *st = (TcState *)g->d_tc_w;
+  lr_status rc = tc_set_attrs();
+  if (rc != LR_OK) return rc;
+  const long P_pad = (fl.P + kTile - 1) / kTile * kTile;
+  const int n_tiles = (int)(P_pad / kTile);
+  if (n_tiles == 0) return LR_OK;
+  const int n_slices = g->Cp / kSlice;
+  const int groups = std::max(1, std::min(n_tiles, e.sm_count / n_slices));
+  std::vector<int> cuts;
+  split_groups(n_tiles, groups, cuts);
+
+  // per-tile run info.  A run = consecutive tiles of one row inside one group, at most
+  // kMaxRunTiles long.  A row touched by more than one group accumulates through slab rows
+  // (exclusive, non-atomic fp64 read-modify-write everywhere; slabs are reduced afterwards).
+  std::vector<int> tile_row(n_tiles, -1);
+  for (const LrChunk &c : chunks) {
+    if (c.pos % kTile) return fail(LR_ERR_ARG, "tc_run_stats: chunk not tile aligned");
+    for (long t = c.pos / kTile; t < (c.pos + c.len + kTile - 1) / kTile; t++) tile_row[t] = c.row;
+  }
+  std::vector<int> tile_group(n_tiles);
+  for (int gi = 0; gi < groups; gi++)
+    for (int t = cuts[gi]; t < cuts[gi + 1]; t++) tile_group[t] = gi;
+  std::vector<TileInfo> tinfo(n_tiles);
+  std::vector<int> slab_row;  // slab v -> real row
+  for (int t = 0; t < n_tiles;) {
+    const int row = tile_row[t];
+    int t2 = t;
+    while (t2 < n_tiles && tile_row[t2] == row) t2++;
+    const bool split = tile_group[t] != tile_group[t2 - 1];
+    for (int u = t; u < t2;) {
+      const int gi = tile_group[u];
+      int u2 = u;
+      while (u2 < t2 && tile_group[u2] == gi) u2++;
+      int target = row, slabbit = 0;
+      if (row < 0) {
+        target = 0;  // tiles outside every chunk (cannot happen with build_plan): discard
+        slabbit = 8;
+      } else if (split) {
+        target = (int)slab_row.size();
+        slab_row.push_back(row);
+        slabbit = 4;
+      }
+      for (int k = u; k < u2; k++) {
+        const int in_run = (k - u) % kMaxRunTiles;
+        int flags = slabbit;
+        if (in_run == 0) flags |= 1;
+        if (in_run == kMaxRunTiles - 1 || k == u2 - 1) flags |= 2;
+        tinfo[k] = {target, flags};
+      }
+      u = u2;
+    }
+    t = t2;
+  }
+  const int n_slab = (int)slab_row.size();
+  const size_t C = g->C, cd = (size_t)g->C * g->D;
+  double *slabN = nullptr, *slabF = nullptr, *slabS = nullptr;
+  if (n_slab) {
+    const size_t per = C + 2 * cd;
+    double *slab = (double *)scratch_get(kSlotS, (size_t)n_slab * per * sizeof(double));
+    if (!slab) return LR_ERR_CUDA;
+    LR_CUDA(cudaMemsetAsync(slab, 0, (size_t)n_slab * per * sizeof(double), e.stream));
+    slabN = slab;
+    slabF = slab + (size_t)n_slab * C;
+    slabS = slabF + (size_t)n_slab * cd;
+  }
+
+  float *d_lse = (float *)scratch_get(kSlotLse, (size_t)P_pad * sizeof(float));
+  if (!d_lse) return LR_ERR_CUDA;
+  rc = tc_pass_lse(g, fl, d_lse, d_llk_sum);  // also leaves the converted tiles in kSlotTmpA
+  if (rc != LR_OK) return rc;
+  if (!out_N && !out_F && !out_S2) return LR_OK;
+  unsigned char *Xh = (unsigned char *)scratch_get(kSlotTmpA, (size_t)n_tiles * kTileBytes);
+  int *d_cuts = (int *)scratch_get(kSlotRest, (groups + 1) * sizeof(int));
+  TileInfo *d_tinfo = (TileInfo *)scratch_get(kSlotChunks, (size_t)n_tiles * sizeof(TileInfo));
+  if (!Xh || !d_cuts || !d_tinfo) return LR_ERR_CUDA;
+  LR_CUDA(cudaMemcpyAsync(d_tinfo, tinfo.data(), (size_t)n_tiles * sizeof(TileInfo),
+                          cudaMemcpyHostToDevice, e.stream));
+  {
+    ProfileScope prof(1);
+    if (out_S2)
+      k_tc_acc<true><<<n_slices * groups, kTcThreads, kTcSmem, e.stream>>>(
+          g->C, g->D, n_slices, st->d_W, Xh, d_cuts, d_tinfo, d_lse, g->d_g, g->d_s, fw, out_N,
+          out_F, out_S2, slabN, slabF, slabS);
+    else
+      k_tc_acc<false><<<n_slices * groups, kTcThreads, kTcSmem, e.stream>>>(
+          g->C, g->D, n_slices, st->d_W, Xh, d_cuts, d_tinfo, d_lse, g->d_g, g->d_s, fw, out_N,
+          out_F, nullptr, slabN, slabF, nullptr);
+    LR_CHECK_LAUNCH();
+  }
+  if (n_slab) {
+    int *d_map = (int *)scratch_get(kSlotIdx, (size_t)n_slab * sizeof(int));
+    if (!d_map) return LR_ERR_CUDA;
+    LR_CUDA(cudaMemcpyAsync(d_map, slab_row.data(), (size_t)n_slab * sizeof(int),
+                            cudaMemcpyHostToDevice, e.stream));
+    if (out_N) {
+      k_tc_reduce_slabs<<<ceil_div((long)C, 256), 256, 0, e.stream>>>(n_slab, d_map, C, slabN, out_N);
+      LR_CHECK_LAUNCH();
+    }
+    if (out_F) {
+      k_tc_reduce_slabs<<<ceil_div((long)cd, 256), 256, 0, e.stream>>>(n_slab, d_map, cd, slabF, out_F);
+      LR_CHECK_LAUNCH();
+    }
+    if (out_S2) {
+      k_tc_reduce_slabs<<<ceil_div((long)cd, 256), 256, 0, e.stream>>>(n_slab, d_map, cd, slabS, out_S2);
+      LR_CHECK_LAUNCH();
+    }
+  }
+  return LR_OK;
 }
 
 }  // namespace lr
