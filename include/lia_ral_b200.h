@@ -60,6 +60,10 @@ lr_status lr_profile_read(int kind, double *total_ms, uint64_t *n_launches);
 /* Kernel selection for the frames x components pass: 0 = auto, 1 = fp32 SIMT, 2 = tcgen05. */
 lr_status lr_set_gmm_kernel(int which);
 int lr_get_gmm_kernel(void);
+/* Profiling experiments only: disables parts of the tcgen05 statistics kernel (bit 0: no exp2,
+ * bit 1: no flush, bit 2: short statistics GEMM, bit 3: short likelihood GEMM).  Results are
+ * WRONG while any bit is set; never set by the product path. */
+void lr_debug_flags(int flags);
 
 /* ------------------------------------------------------------------ GMM (MixtureGD) ------
  * Replaces MixtureGD + DistribGD::computeAll (alize-core; constants probed on

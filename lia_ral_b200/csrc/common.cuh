@@ -24,6 +24,7 @@ struct Engine {
   cublasHandle_t blas = nullptr;
   uint64_t launches = 0;
   int gmm_kernel = 0;  // 0 auto, 1 simt, 2 tcgen05
+  int tc_debug = 0;    // profiling experiments only (lr_debug_flags): results are WRONG when set
   // grow-only device scratch slots reused across calls (freed by lr_shutdown)
   static constexpr int kScratchSlots = 12;
   void *scratch[kScratchSlots] = {};

@@ -199,5 +199,6 @@ lr_status lr_set_gmm_kernel(int which) {
   return LR_OK;
 }
 int lr_get_gmm_kernel(void) { return engine().gmm_kernel; }
+void lr_debug_flags(int flags) { engine().tc_debug = flags; }
 
 }  // extern "C"

@@ -39,8 +39,9 @@ constexpr int kOneCol = 60;                    // columns 60..62 of panel a carr
 constexpr float kGammaShift = 14.f;            // posteriors are stored as fp16(2^14 g)
 constexpr float kXClamp = 240.f;               // |xh| clamp (xh^2 must stay below fp16 max)
 constexpr int kMaxRunTiles = 32;               // fp32 TMEM partial sums are flushed at least this often
-constexpr int kTcThreads = 256;
-constexpr size_t kTcSmem = 1024 + 64 * 1024 + kStages * (size_t)kTileBytes + 1024;
+constexpr int kTcThreads = 384;                 // warps: 0 bulk-copy producer, 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kStageFloats = 32 * 32;             // per-warp flush staging: 32 comps x 32 dims
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -76,6 +77,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
           "r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+// the same copy delivered to the same smem offset (and mbarrier) of every CTA in cta_mask
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes,
+                                            uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -125,6 +144,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                    bar)
                : "memory");
 }
+// commit that arrives on the same mbarrier offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -172,6 +199,19 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// one lane of a converged warp (elect.sync): the MMA / bulk-copy issuer
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -187,6 +227,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // version
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
+}
+// descriptor of the same layout family displaced by `bytes` (bytes % 16 == 0, no field overflow)
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) {
+  return d + (uint64_t)(bytes >> 4);
 }
 // instruction descriptor: fp16 x fp16 -> fp32, M x N, operand majors (0 = K, 1 = MN)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
@@ -357,53 +401,72 @@ k_tc_convert(int D, const float *__restrict__ X, size_t ldx, const unsigned *__r
 }
 
 // ------------------------------------------------------------------ shared kernel scaffolding
+constexpr int kHStages = 5;                       // pass 2: ring of 64-frame half tiles
+constexpr int kHalfPanel = kPanelBytes / 2;      // 64 rows x 128 B
+constexpr int kHalfBytes = 4 * kHalfPanel;       // 32 KB
+// 1 KB alignment slack + weights 64 KB + 5 half-tile stages (pass 1: 2 tile stages) + barriers.
+// Pass 2's flush staging (8 warps x 4 KB) aliases the HI weights, which live in TMEM by then.
+constexpr size_t kTcSmem = 1024 + 64 * 1024 + kHStages * (size_t)kHalfBytes + 256;
+
 struct Smem {
   uint32_t w;           // weights slice: hi a | hi b | lo a | lo b
-  uint32_t stage[kStages];
-  uint32_t full[kStages], empty[kStages];
-  uint32_t s_full[2], s_empty[2], p_full[2];
+  uint32_t stage[kStages];     // pass 1: 2 x 64 KB
+  uint32_t hstage[kHStages];   // pass 2: 4 x 32 KB (same memory)
+  uint32_t full[kHStages], empty[kHStages];
+  uint32_t s_full[3], s_empty[2], p_full[3];
   uint32_t f_full, f_empty, w_full;
   uint32_t tmem_slot;
 };
+
+__device__ __forceinline__ uint32_t carve_base(unsigned char *raw) {
+  return (smem_u32(raw) + 1023u) & ~1023u;
+}
 
 __device__ __forceinline__ Smem carve(unsigned char *raw) {
   uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   Smem s;
   s.w = base;
   for (int i = 0; i < kStages; i++) s.stage[i] = base + 64 * 1024 + i * kTileBytes;
-  uint32_t b = base + 64 * 1024 + kStages * kTileBytes;
-  for (int i = 0; i < kStages; i++) {
+  for (int i = 0; i < kHStages; i++) s.hstage[i] = base + 64 * 1024 + i * kHalfBytes;
+  uint32_t b = base + 64 * 1024 + kHStages * kHalfBytes;
+  static_assert(kHStages <= 5, "barrier block layout");
+  for (int i = 0; i < kHStages; i++) {
     s.full[i] = b + 8 * i;
-    s.empty[i] = b + 16 + 8 * i;
+    s.empty[i] = b + 40 + 8 * i;
   }
-  for (int i = 0; i < 2; i++) {
-    s.s_full[i] = b + 32 + 8 * i;
-    s.s_empty[i] = b + 48 + 8 * i;
-    s.p_full[i] = b + 64 + 8 * i;
+  for (int i = 0; i < 3; i++) {
+    s.s_full[i] = b + 80 + 8 * i;
+    s.p_full[i] = b + 120 + 8 * i;
   }
-  s.f_full = b + 80;
-  s.f_empty = b + 88;
-  s.w_full = b + 96;
-  s.tmem_slot = b + 104;
+  for (int i = 0; i < 2; i++) s.s_empty[i] = b + 104 + 8 * i;
+  s.f_full = b + 144;
+  s.f_empty = b + 152;
+  s.w_full = b + 160;
+  s.tmem_slot = b + 168;
   return s;
 }
 
 // the likelihood GEMM of one tile: 3 products x 2 panels x 4 K-steps of 16
 //   w_is_a: true  -> D[c, t] (A = weights, B = frames)   (pass 2)
 //           false -> D[t, c] (A = frames,  B = weights)  (pass 1)
-__device__ __forceinline__ void issue_g1(uint32_t d_tmem, uint32_t w_base, uint32_t x_base,
-                                         bool w_is_a) {
-  constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
+template <int NFRAMES>
+__device__ __forceinline__ void issue_g1(uint32_t d_tmem, uint64_t w_desc0, uint64_t x_desc0,
+                                         bool w_is_a, int nq = 6) {
+  // frames panel = NFRAMES rows x 128 B; with the weights as A the frames are the N dimension.
+  // w_desc0 / x_desc0: K-major SW128 descriptors of the first weights / frames panel.
+  constexpr uint32_t idesc = make_idesc(128, NFRAMES, 0, 0);
+  constexpr int kXPanel = NFRAMES * 128;
   // (weights panel, frames panel): hi_a P1a, hi_b P1b, hi_a P2a, hi_b P2b, lo_a P1a, lo_b P1b
-  const int wp[6] = {0, 1, 0, 1, 2, 3};
-  const int xp[6] = {0, 1, 2, 3, 0, 1};
+  constexpr int wp[6] = {0, 1, 0, 1, 2, 3};
+  constexpr int xp[6] = {0, 1, 2, 3, 0, 1};
   uint32_t acc = 0;
 #pragma unroll
   for (int q = 0; q < 6; q++) {
+    if (q >= nq) break;
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
-      uint64_t wd = make_desc(w_base + wp[q] * kPanelBytes + kk * 32, 16, 1024);
-      uint64_t xd = make_desc(x_base + xp[q] * kPanelBytes + kk * 32, 16, 1024);
+      uint64_t wd = desc_add(w_desc0, wp[q] * kPanelBytes + kk * 32);
+      uint64_t xd = desc_add(x_desc0, xp[q] * kXPanel + kk * 32);
       if (w_is_a)
         umma_ss(d_tmem, wd, xd, idesc, acc);
       else
@@ -413,12 +476,43 @@ __device__ __forceinline__ void issue_g1(uint32_t d_tmem, uint32_t w_base, uint3
   }
 }
 
+// The same contraction with the weights as the A operand read from TMEM (tcgen05.mma "TS"):
+// only the frame half panels (B) are fetched from shared memory, 64 B/clk instead of the
+// 192 B/clk an SS issue of M=128 x N=64 needs (the SM delivers 128 B/clk).
+// w_tmem: 128 columns, panel p (hi a, hi b, lo a, lo b) at column 32 p, fp16 pairs per column.
+// w_tmem: 64 columns holding the HI weights (panel a at +0, panel b at +32, fp16 pairs per
+// column); the LO weights stay in shared memory (w_smem: lo a at +32 KB, lo b at +48 KB) and
+// their product is issued SS -- 16 of the 24 UMMAs read only the frame operand from smem.
+__device__ __forceinline__ void issue_g1_ts(uint32_t d_tmem, uint32_t w_tmem, uint64_t wlo_desc0,
+                                            uint64_t x_desc0, int nq) {
+  // wlo_desc0: descriptor of the LO a weights panel (LO b follows at +16 KB)
+  constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
+  constexpr int kXPanel = 64 * 128;
+  constexpr int wp[6] = {0, 1, 0, 1, 0, 1};
+  constexpr int xp[6] = {0, 1, 2, 3, 0, 1};
+  uint32_t acc = 0;
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    if (q >= nq) break;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      uint64_t xd = desc_add(x_desc0, xp[q] * kXPanel + kk * 32);
+      if (q < 4) {
+        umma_ts(d_tmem, w_tmem + wp[q] * 32 + kk * 8, xd, idesc, acc);
+      } else {
+        umma_ss(d_tmem, desc_add(wlo_desc0, wp[q] * kPanelBytes + kk * 32), xd, idesc, acc);
+      }
+      acc = 1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ pass 1
 // grid = slices * groups.  Partial (max, sum) of 2^S over the slice's components per frame.
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_tc_lse(int n_slices, const unsigned char *__restrict__ Wp, const unsigned char *__restrict__ Xh,
-         const int *__restrict__ group_tiles /*[groups + 1]*/, long P_pad,
-         float2 *__restrict__ part /*[slices][P_pad]*/) {
+k_tc_lse(int n_slices, int csize, const unsigned char *__restrict__ Wp,
+         const unsigned char *__restrict__ Xh, const int *__restrict__ group_tiles /*[groups + 1]*/,
+         long P_pad, float2 *__restrict__ part /*[slices][P_pad]*/, int dbg) {
   extern __shared__ unsigned char smem_raw[];
   const Smem sm = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -426,14 +520,16 @@ k_tc_lse(int n_slices, const unsigned char *__restrict__ Wp, const unsigned char
   const int t_begin = group_tiles[group], t_end = group_tiles[group + 1];
   const int n_tiles = t_end - t_begin;
 
+  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; i++) {
       mbar_init(sm.full[i], 1);
-      mbar_init(sm.empty[i], 1);
+      mbar_init(sm.empty[i], csize);  // one commit from every CTA sharing the multicast tile
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(sm.s_full[i], 1);
-      mbar_init(sm.s_empty[i], 4);
+      mbar_init(sm.s_empty[i], 4);  // the four warps of the team that owns the buffer
     }
     mbar_init(sm.w_full, 1);
     fence_barrier_init();
@@ -441,43 +537,65 @@ k_tc_lse(int n_slices, const unsigned char *__restrict__ Wp, const unsigned char
   if (warp == 2) tmem_alloc(sm.tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(sm.w_full, 4 * kPanelBytes);
       for (int p = 0; p < 4; p++)
         bulk_g2s(sm.w + p * kPanelBytes, Wp + (size_t)slice * 4 * kPanelBytes + (size_t)p * kPanelBytes,
                  kPanelBytes, sm.w_full);
-      for (int i = 0; i < n_tiles; i++) {
-        int st = i % kStages;
-        mbar_wait(sm.empty[st], ((i / kStages) & 1) ^ 1);
+    }
+    for (int i = 0; i < n_tiles; i++) {
+      int st = i % kStages;
+      mbar_wait(sm.empty[st], ((i / kStages) & 1) ^ 1);
+      if (leader) {
         mbar_expect_tx(sm.full[st], kTileBytes);
         const unsigned char *src = Xh + (size_t)(t_begin + i) * kTileBytes;
-        for (int p = 0; p < 4; p++)
-          bulk_g2s(sm.stage[st] + p * kPanelBytes, src + (size_t)p * kPanelBytes, kPanelBytes,
-                   sm.full[st]);
+        if (csize > 1) {
+          // this CTA fetches whole panels (4 / csize of them) for the entire cluster: large
+          // copies (>= 8 KB) are what the copy engine needs to run at full rate
+          for (int p = crank; p < 4; p += csize)
+            bulk_g2s_mc(sm.stage[st] + p * kPanelBytes, src + (size_t)p * kPanelBytes, kPanelBytes,
+                        sm.full[st], cmask);
+        } else {
+          for (int p = 0; p < 4; p++)
+            bulk_g2s(sm.stage[st] + p * kPanelBytes, src + (size_t)p * kPanelBytes, kPanelBytes,
+                     sm.full[st]);
+        }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(sm.w_full, 0);
-      for (int i = 0; i < n_tiles; i++) {
-        int st = i % kStages, buf = i & 1;
-        mbar_wait(sm.full[st], (i / kStages) & 1);
-        mbar_wait(sm.s_empty[buf], ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        issue_g1(tmem_base + buf * 128, sm.w, sm.stage[st], false);
-        umma_commit(sm.empty[st]);
+    const bool leader = elect_one();
+    const uint64_t w_desc0 = make_desc(sm.w, 16, 1024);
+    mbar_wait(sm.w_full, 0);
+    for (int i = 0; i < n_tiles; i++) {
+      int st = i % kStages, buf = i & 1;
+      mbar_wait(sm.full[st], (i / kStages) & 1);
+      mbar_wait(sm.s_empty[buf], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (leader) {
+        issue_g1<128>(tmem_base + buf * 128, w_desc0, make_desc(sm.stage[st], 16, 1024), false,
+                      (dbg & 8) ? 1 : 6);
+        if (csize > 1)
+          umma_commit_mc(sm.empty[st], cmask);
+        else
+          umma_commit(sm.empty[st]);
         umma_commit(sm.s_full[buf]);
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quarter of this warp
-    for (int i = 0; i < n_tiles; i++) {
-      int buf = i & 1;
+    // two teams of four warps (one per TMEM lane quarter) alternate tiles: team t owns S[t]
+    const int q = warp & 3;
+    const int team = (warp - 4) >> 2;
+    for (int i = team; i < n_tiles; i += 2) {
+      const int buf = team;
       mbar_wait(sm.s_full[buf], (i >> 1) & 1);
       tc_fence_after();
       float m = -3.0e38f, s = 0.f;
@@ -486,14 +604,18 @@ k_tc_lse(int n_slices, const unsigned char *__restrict__ Wp, const unsigned char
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + ch * 32, r);
         tmem_wait_ld();
-        float cm = -3.0e38f;
+        float c8[8];
 #pragma unroll
-        for (int e = 0; e < 32; e++) cm = fmaxf(cm, __uint_as_float(r[e]));
+        for (int e = 0; e < 8; e++)
+          c8[e] = fmaxf(fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 8])),
+                        fmaxf(__uint_as_float(r[e + 16]), __uint_as_float(r[e + 24])));
+        float cm = fmaxf(fmaxf(fmaxf(c8[0], c8[1]), fmaxf(c8[2], c8[3])),
+                         fmaxf(fmaxf(c8[4], c8[5]), fmaxf(c8[6], c8[7])));
         float mn = fmaxf(m, cm);
-        float acc = 0.f;
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 32; e++) acc += ex2f(__uint_as_float(r[e]) - mn);
-        s = s * ex2f(m - mn) + acc;
+        for (int e = 0; e < 32; e++) a4[e & 3] += ex2f(__uint_as_float(r[e]) - mn);
+        s = s * ex2f(m - mn) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
         m = mn;
       }
       tc_fence_before();
@@ -505,6 +627,7 @@ k_tc_lse(int n_slices, const unsigned char *__restrict__ Wp, const unsigned char
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal / write to it
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
@@ -542,192 +665,322 @@ __global__ void k_tc_combine(int n_slices, long P, long P_pad, const unsigned *_
 }
 
 // ------------------------------------------------------------------ pass 2
-// TMEM columns: S/P buffers at 0 and 128, statistics accumulator at 256 (N2 columns).
+// Pipeline unit = half tile (64 frames, 4 x 8 KB half panels) through a 4-stage ring, so the
+// bulk loads run three half tiles ahead of the tensor pipe.
+// TMEM columns: three S buffers of 64 columns at 0, 64, 128 (the fp16 posteriors overwrite the
+// first 16 columns of each 32-column half in place), the HI weights at 192..255 and the
+// statistics accumulator at 256..511.
 template <bool EM>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_tc_acc(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
+k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict__ Wp,
          const unsigned char *__restrict__ Xh, const int *__restrict__ group_tiles,
          const TileInfo *__restrict__ tinfo, const float *__restrict__ lse2,
          const double *__restrict__ g, const double *__restrict__ s, double fw,
          double *__restrict__ out_N, double *__restrict__ out_F, double *__restrict__ out_S2,
-         double *__restrict__ slab_N, double *__restrict__ slab_F, double *__restrict__ slab_S2) {
+         double *__restrict__ slab_N, double *__restrict__ slab_F, double *__restrict__ slab_S2,
+         int dbg) {
   constexpr int N2 = EM ? 256 : 128;
-  constexpr uint32_t kLbo2 = EM ? 16384u : 32768u;  // distance between 64-wide MN chunks of B
+  // B of the statistics GEMM: MN-major, 64-wide chunks = half panels
+  constexpr uint32_t kLbo2 = EM ? (uint32_t)kHalfPanel : 2u * kHalfPanel;
   constexpr uint32_t idesc2 = make_idesc(128, N2, 0, 1);
+  constexpr int kHF = 64;    // frames per half tile
+  constexpr int kWCol = 192;  // TMEM columns [192, 256): HI weights of the slice (A operand of G1)
+  constexpr int kNS = 3;      // S buffers: the likelihood GEMM runs two half tiles ahead
   extern __shared__ unsigned char smem_raw[];
   const Smem sm = carve(smem_raw);
-  __shared__ float nl_s[2][kTile];
+  __shared__ float nl_s[4][kHF];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % n_slices, group = blockIdx.x / n_slices;
   const int t_begin = group_tiles[group], t_end = group_tiles[group + 1];
-  const int n_tiles = t_end - t_begin;
+  const int n_half = 2 * (t_end - t_begin);
 
+  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; i++) {
+    for (int i = 0; i < kHStages; i++) {
       mbar_init(sm.full[i], 1);
-      mbar_init(sm.empty[i], 1);
+      mbar_init(sm.empty[i], csize);  // one commit from every CTA sharing the multicast tile
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
       mbar_init(sm.s_full[i], 1);
-      mbar_init(sm.p_full[i], 4);
+      mbar_init(sm.p_full[i], 4);  // the four warps of one epilogue team
     }
     mbar_init(sm.f_full, 1);
-    mbar_init(sm.f_empty, 4);
+    mbar_init(sm.f_empty, kEpiWarps);
     mbar_init(sm.w_full, 1);
+    mbar_init(sm.s_empty[0], kEpiWarps);  // "weights are in TMEM" (pass 2 has no s_empty use)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(sm.tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot));
   const uint32_t tmem_f = tmem_base + 256;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(sm.w_full, 4 * kPanelBytes);
       for (int p = 0; p < 4; p++)
         bulk_g2s(sm.w + p * kPanelBytes, Wp + (size_t)slice * 4 * kPanelBytes + (size_t)p * kPanelBytes,
                  kPanelBytes, sm.w_full);
-      for (int i = 0; i < n_tiles; i++) {
-        int st = i % kStages;
-        mbar_wait(sm.empty[st], ((i / kStages) & 1) ^ 1);
-        mbar_expect_tx(sm.full[st], kTileBytes);
-        const unsigned char *src = Xh + (size_t)(t_begin + i) * kTileBytes;
-        for (int p = 0; p < 4; p++)
-          bulk_g2s(sm.stage[st] + p * kPanelBytes, src + (size_t)p * kPanelBytes, kPanelBytes,
-                   sm.full[st]);
+    }
+    for (int h = 0; h < n_half; h++) {
+      const int st = h % kHStages;
+      mbar_wait(sm.empty[st], ((h / kHStages) & 1) ^ 1);
+      if (leader) {
+        mbar_expect_tx(sm.full[st], kHalfBytes);
+        const unsigned char *src =
+            Xh + (size_t)(t_begin + (h >> 1)) * kTileBytes + (size_t)(h & 1) * kHalfPanel;
+        if (csize > 1) {
+          for (int p = crank; p < 4; p += csize)
+            bulk_g2s_mc(sm.hstage[st] + p * kHalfPanel, src + (size_t)p * kPanelBytes, kHalfPanel,
+                        sm.full[st], cmask);
+        } else {
+          for (int p = 0; p < 4; p++)
+            bulk_g2s(sm.hstage[st] + p * kHalfPanel, src + (size_t)p * kPanelBytes, kHalfPanel,
+                     sm.full[st]);
+        }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_tiles > 0) {
-      mbar_wait(sm.w_full, 0);
-      mbar_wait(sm.full[0], 0);
+    // MMA issuer: the whole warp runs the loop converged, one elected lane issues
+    const bool leader = elect_one();
+    const int nq = (dbg & 8) ? 1 : 6;
+    const int n_k2 = (dbg & 4) ? 1 : kHF / 16;
+    const uint64_t wlo_desc0 = make_desc(sm.w + 2 * kPanelBytes, 16, 1024);
+    const uint64_t x_desc0 = make_desc(sm.hstage[0], 16, 1024);     // K-major view (likelihood GEMM)
+    const uint64_t b_desc0 = make_desc(sm.hstage[0], kLbo2, 1024);  // MN-major view (statistics GEMM)
+    mbar_wait(sm.w_full, 0);      // LO weights landed in shared memory
+    mbar_wait(sm.s_empty[0], 0);  // epilogue warps copied the HI weights into TMEM
+    for (int h0 = 0; h0 < 2 && h0 < n_half; h0++) {
+      mbar_wait(sm.full[h0], 0);
       tc_fence_after();
-      issue_g1(tmem_base, sm.w, sm.stage[0], true);
-      umma_commit(sm.s_full[0]);
-      int n_flush = 0;  // flushes requested so far
-      for (int i = 0; i < n_tiles; i++) {
-        const int st = i % kStages, buf = i & 1;
-        if (i + 1 < n_tiles) {
-          const int st1 = (i + 1) % kStages, buf1 = (i + 1) & 1;
-          mbar_wait(sm.full[st1], ((i + 1) / kStages) & 1);
-          tc_fence_after();
-          issue_g1(tmem_base + buf1 * 128, sm.w, sm.stage[st1], true);
-          umma_commit(sm.s_full[buf1]);
-        }
-        const TileInfo ti = tinfo[t_begin + i];
-        mbar_wait(sm.p_full[buf], (i >> 1) & 1);
-        if ((ti.flags & 1) && n_flush > 0) mbar_wait(sm.f_empty, (n_flush - 1) & 1);
-        tc_fence_after();
-        // F[c, d] (+)= P[c, t] A[t, d]: 8 K-steps of 16 frames; P is fp16 packed in the S columns
-        uint32_t acc = (ti.flags & 1) ? 0u : 1u;
-#pragma unroll
-        for (int kk = 0; kk < 8; kk++) {
-          uint64_t bd = make_desc(sm.stage[st] + kk * 2048, kLbo2, 1024);
-          umma_ts(tmem_f, tmem_base + buf * 128 + kk * 8, bd, idesc2, acc);
-          acc = 1;
-        }
-        umma_commit(sm.empty[st]);
-        if (ti.flags & 2) {
-          umma_commit(sm.f_full);
-          n_flush++;
-        }
+      if (leader) {
+        issue_g1_ts(tmem_base + h0 * kHF, tmem_base + kWCol, wlo_desc0,
+                    desc_add(x_desc0, h0 * kHalfBytes), nq);
+        umma_commit(sm.s_full[h0]);
       }
+      __syncwarp();
+    }
+    int n_flush = 0;  // flushes requested so far
+    TileInfo ti = n_half > 0 ? tinfo[t_begin] : TileInfo{0, 0};
+    TileInfo ti_next = ti;
+    for (int h = 0; h < n_half; h++) {
+      const int st = h % kHStages, buf = h % kNS;
+      if (!(h & 1)) {  // tile info of the NEXT tile is fetched a whole tile ahead of its use
+        ti = ti_next;
+        if (h + 2 < n_half) ti_next = tinfo[t_begin + (h >> 1) + 1];
+      }
+      if (h + 2 < n_half) {
+        const int st2 = (h + 2) % kHStages, buf2 = (h + 2) % kNS;
+        mbar_wait(sm.full[st2], ((h + 2) / kHStages) & 1);
+        tc_fence_after();
+        if (leader) {
+          issue_g1_ts(tmem_base + buf2 * kHF, tmem_base + kWCol, wlo_desc0,
+                      desc_add(x_desc0, st2 * kHalfBytes), nq);
+          umma_commit(sm.s_full[buf2]);
+        }
+        __syncwarp();
+      }
+      const bool first = (ti.flags & 1) && !(h & 1), last = (ti.flags & 2) && (h & 1);
+      mbar_wait(sm.p_full[buf], (h / kNS) & 1);
+      if (first && n_flush > 0) mbar_wait(sm.f_empty, (n_flush - 1) & 1);
+      tc_fence_after();
+      if (leader) {
+        // F[c, d] (+)= P[c, t] A[t, d]: 4 K-steps of 16 frames; P is fp16 packed in the S columns
+        uint32_t acc = first ? 0u : 1u;
+        const uint64_t bd0 = desc_add(b_desc0, st * kHalfBytes);
+#pragma unroll
+        for (int kk = 0; kk < kHF / 16; kk++) {
+          if (kk < n_k2) {
+            umma_ts(tmem_f, tmem_base + buf * kHF + (kk >> 1) * 32 + (kk & 1) * 8,
+                    desc_add(bd0, kk * 2048), idesc2, acc);
+            acc = 1;
+          }
+        }
+        if (csize > 1)
+          umma_commit_mc(sm.empty[st], cmask);
+        else
+          umma_commit(sm.empty[st]);
+        if (last) umma_commit(sm.f_full);
+      }
+      if (last) n_flush++;
+      __syncwarp();
     }
   } else if (warp >= 4) {
+    // 8 epilogue warps = two teams of four (one warp per TMEM lane quarter q).  Team t converts
+    // the half tiles h = t, t+2, ... (all 64 frame columns), so two half tiles are in flight;
+    // in the flush, warp (q, t) owns the statistics columns 32t.. of components 32q..
     const int q = warp & 3;
-    const int et = threadIdx.x - 128;  // 0..127
+    const int ch = (warp - 4) >> 2;  // team
+    const int et = threadIdx.x - 128 - ch * 128;  // 0..127 inside the team
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // flush staging: the HI weights' 32 KB of shared memory (free once they are in TMEM)
+    float *stg = reinterpret_cast<float *>(smem_raw + (carve_base(smem_raw) - smem_u32(smem_raw))) +
+                 (warp - 4) * kStageFloats;
     int n_flush = 0;
-    for (int i = 0; i < n_tiles; i++) {
-      const int buf = i & 1;
-      // 14 - lse2 of the tile's frames (columns), shared by the four epilogue warps
-      nl_s[buf][et] = kGammaShift - lse2[(size_t)(t_begin + i) * kTile + et];
-      named_bar_sync(1, 128);
-      mbar_wait(sm.s_full[buf], (i >> 1) & 1);
+    {
+      // HI weights: shared memory (swizzled panels) -> TMEM rows; warp (q, ch) copies the
+      // rows 32q.. of panel ch (hi a / hi b)
+      mbar_wait(sm.w_full, 0);
+      const int r = q * 32 + lane;
+      for (int p = ch; p < ch + 1; p++) {
+#pragma unroll
+        for (int half16 = 0; half16 < 2; half16++) {
+          uint32_t v[16];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int chunk = half16 * 4 + j;
+            const uint32_t a = sm.w + p * kPanelBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                         : "r"(a));
+          }
+          tmem_st16(tmem_base + lane_addr + kWCol + p * 32 + half16 * 16, v);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.s_empty[0]);
+    }
+    // 14 - lse2 of the half tile's frames (the TMEM columns), prefetched one team-step ahead
+    float nl_next = 0.f;
+    if (et < kHF && ch < n_half) nl_next = kGammaShift - lse2[(size_t)t_begin * kTile + (size_t)ch * kHF + et];
+    TileInfo eti_next = n_half > 0 ? tinfo[t_begin] : TileInfo{0, 0};
+    for (int h = ch; h < n_half; h += 2) {
+      const int buf = h % kNS;
+      const TileInfo eti = eti_next;
+      if (h + 2 < n_half) eti_next = tinfo[t_begin + ((h + 2) >> 1)];
+      if (et < kHF) nl_s[h & 3][et] = nl_next;
+      named_bar_sync(1 + ch, 128);
+      if (et < kHF && h + 2 < n_half)
+        nl_next = kGammaShift - lse2[(size_t)t_begin * kTile + (size_t)(h + 2) * kHF + et];
+      mbar_wait(sm.s_full[buf], (h / kNS) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ch++) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_addr + buf * 128 + ch * 32, r);
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem_base + lane_addr + buf * kHF, r0);
+        tmem_ld32(tmem_base + lane_addr + buf * kHF + 32, r1);
         tmem_wait_ld();
+        const float *nl = nl_s[h & 3];
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-          float a = ex2f(__uint_as_float(r[2 * e]) + nl_s[buf][ch * 32 + 2 * e]);
-          float b = ex2f(__uint_as_float(r[2 * e + 1]) + nl_s[buf][ch * 32 + 2 * e + 1]);
-          a = fminf(a, 65504.f);
-          b = fminf(b, 65504.f);
-          __half2 h = __floats2half2_rn(a, b);
-          pk[e] = *reinterpret_cast<uint32_t *>(&h);
+          float a = __uint_as_float(r0[2 * e]) + nl[2 * e];
+          float b = __uint_as_float(r0[2 * e + 1]) + nl[2 * e + 1];
+          if (!(dbg & 1)) {
+            a = ex2f(a);
+            b = ex2f(b);
+          }
+          __half2 hh = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+          pk[e] = *reinterpret_cast<uint32_t *>(&hh);
         }
-        tmem_st16(tmem_base + lane_addr + buf * 128 + ch * 16, pk);
+        tmem_st16(tmem_base + lane_addr + buf * kHF, pk);
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          float a = __uint_as_float(r1[2 * e]) + nl[32 + 2 * e];
+          float b = __uint_as_float(r1[2 * e + 1]) + nl[32 + 2 * e + 1];
+          if (!(dbg & 1)) {
+            a = ex2f(a);
+            b = ex2f(b);
+          }
+          __half2 hh = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+          pk[e] = *reinterpret_cast<uint32_t *>(&hh);
+        }
+        tmem_st16(tmem_base + lane_addr + buf * kHF + 32, pk);
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.p_full[buf]);
 
-      const TileInfo ti = tinfo[t_begin + i];
+      const TileInfo ti = eti;
       if (ti.flags & 2) {
-        // flush the accumulator of this run: lane = component, columns = statistics
-        // EM : [xh hi,1 | xh^2 hi | xh lo | xh^2 lo] (4 x 64);  BW: [xh hi,1 | xh lo] (2 x 64)
+        // Flush the accumulator of this run.  TMEM: lane = component, columns = statistics,
+        //   EM : [xh hi,1 | xh^2 hi | xh lo | xh^2 lo] (4 x 64);  BW: [xh hi,1 | xh lo] (2 x 64).
+        // The increments are staged through shared memory (fp32) so that the fp64
+        // read-modify-write of the row's [128 comps x D] block is coalesced (lane = dimension).
         mbar_wait(sm.f_full, n_flush & 1);
         n_flush++;
         tc_fence_after();
-        const int comp = slice * kSlice + q * 32 + lane;
+        const int comp0 = slice * kSlice + q * 32;
         const bool slab = (ti.flags & 4) != 0;
         double *oN = slab ? slab_N : out_N, *oF = slab ? slab_F : out_F, *oS = slab ? slab_S2 : out_S2;
         const double sc = 1.0 / 16384.0;  // undo the 2^14 posterior scale
         constexpr int kLoCol = EM ? 128 : 64;
         const double n = (double)__uint_as_float(tmem_ld1(tmem_f + lane_addr + kOneCol)) * sc;
-        const size_t rc = (size_t)ti.row * C + comp;
-        const bool live = comp < C;
-        if (live && oN) oN[rc] += fw * n;
-#pragma unroll 1
-        for (int h = 0; h < 4; h++) {
-          uint32_t a_hi[16], a_lo[16];
-          tmem_ld16(tmem_f + lane_addr + h * 16, a_hi);
-          tmem_ld16(tmem_f + lane_addr + kLoCol + h * 16, a_lo);
+        const size_t rc0 = (size_t)ti.row * C + comp0;
+        const int k0 = ch * 32;
+        uint32_t a_hi[32], a_lo[32];
+        tmem_ld32(tmem_f + lane_addr + k0, a_hi);
+        tmem_ld32(tmem_f + lane_addr + kLoCol + k0, a_lo);
+        tmem_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int e = 0; e < 32; e++)
+          f[e] = (__uint_as_float(a_hi[e]) + __uint_as_float(a_lo[e])) * (float)sc;
+        if (EM) {
+          tmem_ld32(tmem_f + lane_addr + 64 + k0, a_hi);
+          tmem_ld32(tmem_f + lane_addr + 192 + k0, a_lo);
           tmem_wait_ld();
-          double f[16];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.f_empty);  // accumulator columns are free again
+        if (!(dbg & 2)) {
+          if (ch == 1 && oN && comp0 + lane < C) atomicAdd(&oN[rc0 + lane], fw * n);
+          // first moments: F += fw (s_k f + g_k n)
+          __syncwarp();
 #pragma unroll
-          for (int e = 0; e < 16; e++)
-            f[e] = ((double)__uint_as_float(a_hi[e]) + (double)__uint_as_float(a_lo[e])) * sc;
-          if (live && oF) {
-#pragma unroll
-            for (int e = 0; e < 16; e++) {
-              int k = h * 16 + e;
-              if (k < D) oF[rc * D + k] += fw * (s[k] * f[e] + g[k] * n);
+          for (int e = 0; e < 32; e++) {
+            const int k = k0 + e;
+            float inc = 0.f;
+            if (k < D) inc = (float)(fw * (s[k] * (double)f[e] + g[k] * n));
+            stg[lane * 32 + (e ^ lane)] = inc;
+          }
+          __syncwarp();
+          if (oF && k0 + lane < D) {
+#pragma unroll 8
+            for (int c = 0; c < 32; c++) {
+              if (comp0 + c < C)
+                atomicAdd(&oF[(rc0 + c) * D + k0 + lane], (double)stg[c * 32 + (lane ^ c)]);
             }
           }
-          if (EM) {
-            tmem_ld16(tmem_f + lane_addr + 64 + h * 16, a_hi);
-            tmem_ld16(tmem_f + lane_addr + 192 + h * 16, a_lo);
-            tmem_wait_ld();
-            if (live && oS) {
+          if (EM && oS) {
+            __syncwarp();
 #pragma unroll
-              for (int e = 0; e < 16; e++) {
-                int k = h * 16 + e;
-                if (k < D) {
-                  double q2 = ((double)__uint_as_float(a_hi[e]) + (double)__uint_as_float(a_lo[e])) * sc;
-                  double sk = s[k], gk = g[k];
-                  oS[rc * D + k] += fw * (sk * sk * q2 + 2.0 * sk * gk * f[e] + gk * gk * n);
-                }
+            for (int e = 0; e < 32; e++) {
+              const int k = k0 + e;
+              float inc = 0.f;
+              if (k < D) {
+                double q2 = ((double)__uint_as_float(a_hi[e]) + (double)__uint_as_float(a_lo[e])) * sc;
+                double sk = s[k], gk = g[k];
+                inc = (float)(fw * (sk * sk * q2 + 2.0 * sk * gk * (double)f[e] + gk * gk * n));
+              }
+              stg[lane * 32 + (e ^ lane)] = inc;
+            }
+            __syncwarp();
+            if (k0 + lane < D) {
+#pragma unroll 4
+              for (int c = 0; c < 32; c++) {
+                if (comp0 + c < C)
+                  atomicAdd(&oS[(rc0 + c) * D + k0 + lane], (double)stg[c * 32 + (lane ^ c)]);
               }
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sm.f_empty);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal / write to it
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -822,6 +1075,63 @@ static void split_groups(int n_tiles, int groups, std::vector<int> &cuts) {
   for (int gidx = 0; gidx <= groups; gidx++) cuts[gidx] = (int)((long)n_tiles * gidx / groups);
 }
 
+// cluster size: the slices of one group that share a multicast tile (must divide n_slices)
+static int tc_cluster_size(int n_slices) {
+  // Measured on B200 (profiles/r01_tc_notes.md): multicast clusters cut L2->SM traffic 4x but the
+  // kernels are bound by copy LATENCY (prefetch depth), not bandwidth, and 4-CTA clusters leave 20
+  // SMs idle -- slower overall.  Kept behind debug bit 6 for experiments.
+  if (!(engine().tc_debug & 64)) return 1;
+  if (n_slices % 4 == 0) return 4;
+  if (n_slices % 2 == 0) return 2;
+  return 1;
+}
+
+template <typename... Args>
+static lr_status tc_launch(void (*kern)(Args...), int grid, int csize, Args... args) {
+  Engine &e = engine();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = kTcSmem;
+  cfg.stream = e.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LR_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  count_launch();
+  return LR_OK;
+}
+
+// number of groups: co-resident CTAs (1 per SM, whole clusters) / slices
+template <typename K>
+static int tc_groups(K kern, int n_slices, int csize, int n_tiles) {
+  Engine &e = engine();
+  int max_ctas = e.sm_count;
+  if (csize > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(csize * 64));
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = kTcSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) == cudaSuccess && n_clusters > 0)
+      max_ctas = n_clusters * csize;
+    else
+      cudaGetLastError();
+  }
+  return std::max(1, std::min(n_tiles, max_ctas / n_slices));
+}
+
 static lr_status tc_set_attrs() {
   static bool done = false;
   if (done) return LR_OK;
@@ -843,7 +1153,8 @@ lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_l
   const long P_pad = (P + kTile - 1) / kTile * kTile;
   const int n_tiles = (int)(P_pad / kTile);
   const int n_slices = g->Cp / kSlice;
-  const int groups = std::max(1, std::min(n_tiles, e.sm_count / n_slices));
+  const int csize = tc_cluster_size(n_slices);
+  const int groups = tc_groups(k_tc_lse, n_slices, csize, n_tiles);
   unsigned char *Xh = (unsigned char *)scratch_get(kSlotTmpA, (size_t)n_tiles * kTileBytes);
   float2 *part = (float2 *)scratch_get(kSlotTmpB, (size_t)n_slices * P_pad * sizeof(float2));
   int *d_cuts = (int *)scratch_get(kSlotRest, (groups + 1) * sizeof(int));
@@ -857,9 +1168,10 @@ lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_l
   LR_CHECK_LAUNCH();
   {
     ProfileScope prof(0);
-    k_tc_lse<<<n_slices * groups, kTcThreads, kTcSmem, e.stream>>>(n_slices, st->d_W, Xh, d_cuts,
-                                                                   P_pad, part);
-    LR_CHECK_LAUNCH();
+    rc = tc_launch(k_tc_lse, n_slices * groups, csize, n_slices, csize,
+                   (const unsigned char *)st->d_W, (const unsigned char *)Xh, (const int *)d_cuts,
+                   P_pad, part, e.tc_debug);
+    if (rc != LR_OK) return rc;
   }
   k_tc_combine<<<(unsigned)((P_pad + 255) / 256), 256, 0, e.stream>>>(n_slices, P, P_pad, fl.d_index,
                                                                      part, d_lse2, d_llk_sum);
@@ -885,7 +1197,9 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
   const int n_tiles = (int)(P_pad / kTile);
   if (n_tiles == 0) return LR_OK;
   const int n_slices = g->Cp / kSlice;
-  const int groups = std::max(1, std::min(n_tiles, e.sm_count / n_slices));
+  const int csize = tc_cluster_size(n_slices);
+  // both passes must cut the tiles identically (pass 2 reuses pass 1's group table)
+  const int groups = tc_groups(k_tc_lse, n_slices, csize, n_tiles);
   std::vector<int> cuts;
   split_groups(n_tiles, groups, cuts);
 
@@ -906,7 +1220,7 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
     const int row = tile_row[t];
     int t2 = t;
     while (t2 < n_tiles && tile_row[t2] == row) t2++;
-    const bool split = tile_group[t] != tile_group[t2 - 1];
+    const bool split = false;  // flushes are fp64 atomics (RED): rows may be shared between groups
     for (int u = t; u < t2;) {
       const int gi = tile_group[u];
       int u2 = u;
@@ -958,14 +1272,18 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
   {
     ProfileScope prof(1);
     if (out_S2)
-      k_tc_acc<true><<<n_slices * groups, kTcThreads, kTcSmem, e.stream>>>(
-          g->C, g->D, n_slices, st->d_W, Xh, d_cuts, d_tinfo, d_lse, g->d_g, g->d_s, fw, out_N,
-          out_F, out_S2, slabN, slabF, slabS);
+      rc = tc_launch(k_tc_acc<true>, n_slices * groups, csize, g->C, g->D, n_slices, csize,
+                     (const unsigned char *)st->d_W, (const unsigned char *)Xh, (const int *)d_cuts,
+                     (const TileInfo *)d_tinfo, (const float *)d_lse, (const double *)g->d_g,
+                     (const double *)g->d_s, fw, out_N, out_F, out_S2, slabN, slabF, slabS,
+                     e.tc_debug);
     else
-      k_tc_acc<false><<<n_slices * groups, kTcThreads, kTcSmem, e.stream>>>(
-          g->C, g->D, n_slices, st->d_W, Xh, d_cuts, d_tinfo, d_lse, g->d_g, g->d_s, fw, out_N,
-          out_F, nullptr, slabN, slabF, nullptr);
-    LR_CHECK_LAUNCH();
+      rc = tc_launch(k_tc_acc<false>, n_slices * groups, csize, g->C, g->D, n_slices, csize,
+                     (const unsigned char *)st->d_W, (const unsigned char *)Xh, (const int *)d_cuts,
+                     (const TileInfo *)d_tinfo, (const float *)d_lse, (const double *)g->d_g,
+                     (const double *)g->d_s, fw, out_N, out_F, (double *)nullptr, slabN, slabF,
+                     (double *)nullptr, e.tc_debug);
+    if (rc != LR_OK) return rc;
   }
   if (n_slab) {
     int *d_map = (int *)scratch_get(kSlotIdx, (size_t)n_slab * sizeof(int));
