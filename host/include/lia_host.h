@@ -1,0 +1,221 @@
+// lia_host.h -- C++ host mirror of the LIA_RAL / ALIZE surface that the hot path touches
+// (SURVEY.md Appendix B), written against the C ABI of liblia_ral_b200.so.
+//
+// This is NOT alize-core: it is the minimum object surface the five hot programs use (Config,
+// XList, MixtureGD + RAW/XML files, FeatureServer over SPRO3/SPRO4/RAW float32 files with
+// featureServerMask, label -> segment selection, Matrix DB/DT files), plus the LIA_SpkTools
+// batch functions re-expressed over the engine: accumulateStatEM, trainModel, TVAcc,
+// ComputeTest's frame loop, PLDA native scoring.  Names, parameter keys and error behaviour
+// follow the reference (file:line cited at each item); all numerics run on the GPU.
+#pragma once
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lia_ral_b200.h"
+
+namespace lia {
+
+// alize::Exception(msg, __FILE__, __LINE__) convention (AccumulateTVStat.cpp:481)
+class Exception : public std::runtime_error {
+ public:
+  Exception(const std::string &msg, const char *file, int line);
+  std::string toString() const { return what(); }
+};
+#define LIA_THROW(msg) throw ::lia::Exception((msg), __FILE__, __LINE__)
+// rethrows lr_last_error() when an engine call fails
+void check(lr_status st, const char *file, int line);
+#define LIA_CHECK(expr) ::lia::check((expr), __FILE__, __LINE__)
+
+// ---- Config: flat name -> value map; "name<ws>value" text files (banner lines "***" ignored),
+// overridden by "--name value" from the command line (TrainWorldMain.cpp:90-104).
+class Config {
+ public:
+  Config() {}
+  explicit Config(const std::string &file) { load(file); }
+  void load(const std::string &file);
+  void parseCmdLine(int argc, char **argv);  // handles --config <file> first, then overrides
+  bool existsParam(const std::string &n) const { return kv_.count(n) != 0; }
+  void setParam(const std::string &n, const std::string &v) { kv_[n] = v; }
+  const std::string &getParam(const std::string &n) const;  // throws when missing
+  std::string getString(const std::string &n, const std::string &def) const;
+  long getLong(const std::string &n) const;
+  long getLong(const std::string &n, long def) const;
+  double getDouble(const std::string &n) const;
+  double getDouble(const std::string &n, double def) const;
+  bool getBool(const std::string &n, bool def) const;
+
+ private:
+  std::map<std::string, std::string> kv_;
+};
+
+// ---- XList: whitespace separated tokens per line (NDX files, lists)
+class XList {
+ public:
+  XList() {}
+  explicit XList(const std::string &file) { load(file); }
+  void load(const std::string &file);
+  const std::vector<std::vector<std::string>> &lines() const { return lines_; }
+  std::vector<std::string> allElements() const;
+  std::vector<std::string> allUniqueElements() const;
+
+ private:
+  std::vector<std::vector<std::string>> lines_;
+};
+
+// ---- Matrix<double>: row-major; DB = uint32 rows, uint32 cols, double[]; DT = "rows cols\n" text
+struct Matrix {
+  size_t rows = 0, cols = 0;
+  std::vector<double> data;
+  Matrix() {}
+  Matrix(size_t r, size_t c) : rows(r), cols(c), data(r * c, 0.0) {}
+  double &operator()(size_t i, size_t j) { return data[i * cols + j]; }
+  double operator()(size_t i, size_t j) const { return data[i * cols + j]; }
+  void load(const std::string &file, const std::string &format /*DB|DT*/);
+  void save(const std::string &file, const std::string &format) const;
+};
+
+// ---- MixtureGD / DistribGD: diagonal GMM with the alize RAW and XML file formats
+struct MixtureGD {
+  std::string id;
+  int C = 0, D = 0;
+  std::vector<double> w, mean, cov, covinv, cst, det;
+  void resize(int c, int d);
+  void computeAll();  // covInv, det, cst (DistribGD::computeAll)
+  void load(const std::string &file, const std::string &format /*RAW|XML*/);
+  void save(const std::string &file, const std::string &format) const;
+  // mixtureFilesPath + name + loadMixtureFileExtension, format from the config
+  static MixtureGD loadFromConfig(const std::string &name, const Config &c);
+  void saveFromConfig(const std::string &name, const Config &c) const;
+};
+
+// ---- segments / labels
+struct Seg {
+  std::string source;
+  long begin = 0, length = 0;  // frames, relative to the source file
+  std::string label;
+};
+typedef std::vector<Seg> SegCluster;
+long timeToFrameIdx(double t, double frameLength);  // SegTools.cpp:135-142
+long totalFrame(const SegCluster &c);
+
+// ---- FeatureServer: featureServerBufferSize ALL_FEATURES semantics -- every listed file is read
+// into one float32 [frames x vectSize] block (after featureServerMask), sources indexed by name.
+class FeatureServer {
+ public:
+  FeatureServer(const Config &c, const std::vector<std::string> &files);
+  int getVectSize() const { return D_; }
+  size_t getFeatureCount() const { return D_ ? X_.size() / D_ : 0; }
+  size_t getSourceCount() const { return names_.size(); }
+  const std::string &getNameOfASource(size_t i) const { return names_[i]; }
+  size_t getFirstFeatureIndexOfASource(const std::string &name) const;
+  size_t getFeatureCountOfASource(const std::string &name) const;
+  const float *data() const { return X_.data(); }
+  size_t ld() const { return (size_t)D_; }
+
+ private:
+  int D_ = 0;
+  std::vector<float> X_;
+  std::vector<std::string> names_;
+  std::vector<size_t> first_, count_;
+};
+std::vector<int> parseMask(const std::string &mask);  // "0-15,17-32"
+// frames of label `labelSelectedFrames` for every source of fs (label files
+// labelFilesPath + source + labelFilesExtension; addDefaultLabel / defaultLabel honoured);
+// verifyClusterFile semantics: segments are clipped to the file length (SegTools.cpp:151-169)
+SegCluster selectedSegments(const Config &c, const FeatureServer &fs, const std::string &label);
+// segments -> engine segments (absolute frame index in the FeatureServer block), one row each
+std::vector<lr_seg> toEngineSegs(const FeatureServer &fs, const SegCluster &segs, int row = 0);
+
+// ---- engine RAII
+class Gmm {
+ public:
+  explicit Gmm(const MixtureGD &m, bool use_file_cst = false);
+  ~Gmm();
+  Gmm(const Gmm &) = delete;
+  Gmm &operator=(const Gmm &) = delete;
+  lr_gmm *h() const { return h_; }
+  void set(const MixtureGD &m);
+  void get(MixtureGD &m) const;  // parameters + computeAll products back from the device
+
+ private:
+  lr_gmm *h_ = nullptr;
+};
+
+// ---- TrainTools
+struct TrainCfg {  // TrainTools.cpp:67-93
+  double initVarianceFlooring, initVarianceCeiling, finalVarianceFlooring, finalVarianceCeiling;
+  long nbTrainIt;
+  double baggedFrameProbability;
+  explicit TrainCfg(const Config &c);
+};
+double setItParameter(double begin, double end, int nbIt, int it);  // TrainTools.cpp:560-564
+// bagging of 3..7-frame chunks with libc rand() exactly like GeneralTools.cpp:309-313, 455-500
+SegCluster baggedSegments(const SegCluster &in, double p, long minLen, long maxLen);
+// E-step over a cluster: returns sum log-likelihood; accumulates occ / m1 / m2 / n
+struct EmAcc {
+  std::vector<double> occ, m1, m2;
+  double n = 0;
+  void reset(int C, int D);
+};
+double accumulateStatEM(const FeatureServer &fs, const Gmm &g, const SegCluster &segs, EmAcc &acc,
+                        double weight = 1.0);  // AccumulateStat.cpp:131
+void computeMeanCov(const FeatureServer &fs, const SegCluster &segs, std::vector<double> &mean,
+                    std::vector<double> &cov);  // TrainTools.cpp:593-602
+void mixtureInit(const FeatureServer &fs, const SegCluster &segs, const std::vector<double> &globalCov,
+                 const Config &c, MixtureGD &world);  // TrainTools.cpp:674-766
+void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs,
+                const std::vector<double> &globalCov, MixtureGD &world, const TrainCfg &cfg);
+
+// ---- TVAcc (AccumulateTVStat.h): same method names, state in HBM
+class TVAcc {
+ public:
+  TVAcc(const std::string &ndxFile, const Config &c);  // :109, _init :129-196
+  TVAcc(const std::vector<std::vector<std::string>> &fileLines, const Config &c);  // XList variant
+  ~TVAcc();
+  void computeAndAccumulateTVStat(const Config &c);  // :268
+  void loadT(const std::string &name, const Config &c);  // :632 (transposes when rows > cols)
+  void initT(const Config &c);                            // :701 (Box-Muller on libc rand())
+  void saveT(const std::string &name, const Config &c);
+  void loadN(const Config &c);
+  void loadF_X(const Config &c);
+  void saveAccs(const Config &c);  // :1614
+  void substractM();
+  void estimateTETt();
+  void estimateW();
+  void estimateAandC();
+  void resetTmpAcc();
+  void updateTestimate();
+  void minDivergence();
+  void orthonormalizeT();
+  void saveWbyFile(const Config &c);  // :2799-2822
+  void loadMeanEstimate(const std::vector<double> &mean);  // :671
+  void reloadStats();      // resend the host copy of N / F_X (TotalVariability.cpp:149-153)
+  Matrix getUbmMeans();
+  Matrix getW();
+  size_t nSpeakers() const { return lines_.size(); }
+  int rank() const { return R_; }
+
+ private:
+  Config cfg_;
+  std::vector<std::vector<std::string>> lines_;  // NDX lines: id + files
+  MixtureGD world_;
+  int R_ = 0;
+  lr_tv *tv_ = nullptr;
+  Matrix N_, F_;
+  void init(const Config &c);
+};
+
+// ---- drivers: int Foo(Config&) like the reference programs
+int TrainWorld(Config &c);        // LIA_SpkDet/TrainWorld/src/TrainWorld.cpp:101
+int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:90
+int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:70
+int TotalVariability(Config &c);  // LIA_SpkDet/TotalVariability/src/TotalVariability.cpp:71
+int IvTest(Config &c);            // LIA_SpkDet/IvTest/src/IvTest.cpp:73 (scoring = plda, native)
+
+}  // namespace lia

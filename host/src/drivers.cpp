@@ -1,0 +1,283 @@
+// drivers.cpp -- int Foo(Config&) entry points with the reference programs' parameter names and
+// output formats.  Errors follow the reference: catch, print e.toString(), return 0.
+#include <algorithm>
+#include <fstream>
+#include <iostream>
+
+#include "lia_host.h"
+
+namespace lia {
+
+static char setDecision(double llr, double threshold) { return llr > threshold ? 1 : 0; }  // GeneralTools.cpp:232
+
+// "gender client decision seg [begin end] LLR" (IOFormat.cpp:112-120)
+static void outputResultLine(double llr, const std::string &client, const std::string &seg,
+                             const std::string &gender, int decision, std::ostream &os) {
+  os << gender << " " << client << " " << decision << " " << seg << " " << llr << std::endl;
+}
+static void outputResultLine(double llr, const std::string &client, const std::string &seg, double b,
+                             double e, const std::string &gender, int decision, std::ostream &os) {
+  os << gender << " " << client << " " << decision << " " << seg << " " << b << " " << e << " " << llr
+     << std::endl;
+}
+
+// ------------------------------------------------------------------ TrainWorld
+int TrainWorld(Config &c) {
+  try {
+    const bool verbose = c.getBool("verbose", false);
+    const std::string out = c.getParam("outputWorldFilename");
+    const std::string label = c.getParam("labelSelectedFrames");
+    TrainCfg cfg(c);
+    // single input stream: inputFeatureFilename is a feature file or a list of feature files
+    std::vector<std::string> files;
+    const std::string in = c.getParam("inputFeatureFilename");
+    if (in.size() > 4 && in.compare(in.size() - 4, 4, ".lst") == 0)
+      files = XList(in).allElements();
+    else
+      files.push_back(in);
+    FeatureServer fs(c, files);
+    SegCluster segs = selectedSegments(c, fs, label);
+    if (segs.empty()) LIA_THROW("TrainWorld error: no frame selected with label " + label);
+    std::vector<double> gMean, gCov;
+    if (c.getBool("use01", false)) {
+      gMean.assign(fs.getVectSize(), 0.0);
+      gCov.assign(fs.getVectSize(), 1.0);
+    } else {
+      computeMeanCov(fs, segs, gMean, gCov);
+    }
+    MixtureGD world;
+    if (c.existsParam("inputWorldFilename")) {
+      world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+    } else {
+      world.resize((int)c.getLong("mixtureDistribCount"), fs.getVectSize());
+      mixtureInit(fs, segs, gCov, c, world);
+      if (c.getBool("saveInitModel", true)) world.saveFromConfig(out + "init", c);
+    }
+    if (verbose) std::cout << "Train world model: " << world.C << " components, " << totalFrame(segs) << " frames" << std::endl;
+    trainModel(c, fs, segs, gCov, world, cfg);
+    world.saveFromConfig(out, c);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ ComputeTest
+int ComputeTest(Config &c) {
+  try {
+    const std::string gender = c.getParam("gender");
+    const std::string label = c.getParam("labelSelectedFrames");
+    const bool segmental = c.getBool("segmentLLR", false);
+    const double threshold = c.getDouble("decisionThreshold", 0.0);
+    const double frameLength = c.getDouble("frameLength", 0.01);
+    const int K = (int)c.getLong("topDistribsCount", 10);
+    const bool complete = c.getString("computeLLKWithTopDistribs", "COMPLETE") == "COMPLETE";
+    const double minLLK = c.getDouble("minLLK", -200.0), maxLLK = c.getDouble("maxLLK", 200.0);
+    if (c.getLong("worldDecime", 1) != 1) LIA_THROW("worldDecime != 1 is not supported by this engine");
+    XList ndx(c.getParam("ndxFilename"));
+    MixtureGD worldM = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+    Gmm world(worldM, true);
+    std::map<std::string, std::unique_ptr<Gmm>> cache;  // client models stay resident (TabClientLine)
+    std::ofstream outNist(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
+    for (auto &line : ndx.lines()) {
+      const std::string &test = line[0];
+      FeatureServer fs(c, {test});
+      SegCluster segs = selectedSegments(c, fs, label);
+      if (segs.empty()) {
+        std::cout << "ATTENTION, TEST FILE [" << test << "] is empty" << std::endl;
+        continue;
+      }
+      std::vector<lr_gmm *> clients;
+      for (size_t i = 1; i < line.size(); i++) {
+        auto it = cache.find(line[i]);
+        if (it == cache.end())
+          it = cache.emplace(line[i], std::unique_ptr<Gmm>(new Gmm(MixtureGD::loadFromConfig(line[i], c), true))).first;
+        clients.push_back(it->second->h());
+      }
+      std::vector<lr_seg> es = toEngineSegs(fs, segs);
+      const size_t nOut = segmental ? es.size() : 1;
+      std::vector<double> mw(nOut), mc(clients.size() * nOut);
+      LIA_CHECK(lr_compute_test(world.h(), clients.data(), (int)clients.size(), fs.data(), fs.getFeatureCount(),
+                                fs.ld(), es.data(), es.size(), K, complete ? 1 : 0, minLLK, maxLLK,
+                                segmental ? 1 : 0, mw.data(), mc.data()));
+      for (size_t o = 0; o < nOut; o++)
+        for (size_t i = 0; i < clients.size(); i++) {
+          double llr = mc[i * nOut + o] - mw[o];  // ComputeTest.cpp:196-199
+          if (segmental)
+            outputResultLine(llr, line[i + 1], test, es[o].begin * frameLength,
+                             (es[o].begin + es[o].length) * frameLength, gender, setDecision(llr, threshold), outNist);
+          else
+            outputResultLine(llr, line[i + 1], test, gender, setDecision(llr, threshold), outNist);
+        }
+    }
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ IvExtractor (classic mode)
+int IvExtractor(Config &c) {
+  try {
+    // the first element of each targetIdList line is the model name (IvExtractor.cpp:92-99)
+    XList ids(c.getParam("targetIdList"));
+    std::vector<std::vector<std::string>> files;
+    for (auto &l : ids.lines()) files.push_back(std::vector<std::string>(l.begin() + 1, l.end()));
+    TVAcc tv(files, c);
+    tv.loadT(c.getParam("totalVariabilityMatrix"), c);
+    if (c.getBool("loadAccs", false)) {
+      tv.loadN(c);
+      tv.loadF_X(c);
+    } else {
+      tv.computeAndAccumulateTVStat(c);
+      tv.saveAccs(c);
+    }
+    if (c.getBool("minDivergence", false)) {
+      Matrix m;
+      m.load(c.getString("matrixFilesPath", "") + c.getParam("meanEstimate") + c.getString("loadMatrixFilesExtension", ""),
+             c.getString("loadMatrixFormat", "DB"));
+      tv.loadMeanEstimate(m.data);
+    }
+    tv.substractM();
+    tv.estimateTETt();
+    tv.estimateW();
+    tv.saveWbyFile(c);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ TotalVariability
+int TotalVariability(Config &c) {
+  try {
+    TVAcc tv(c.getParam("ndxFilename"), c);
+    bool statsOnDisk = c.getBool("loadAccs", false);
+    if (statsOnDisk) {
+      tv.loadN(c);
+      tv.loadF_X(c);
+    } else {
+      tv.computeAndAccumulateTVStat(c);
+      tv.saveAccs(c);
+    }
+    if (c.getBool("loadInitTotalVariabilityMatrix", false))
+      tv.loadT(c.getParam("initTotalVariabilityMatrix"), c);
+    else
+      tv.initT(c);
+    if (c.getBool("saveInitTotalVariabilityMatrix", false)) tv.saveT(c.getParam("totalVariabilityMatrix") + "_init", c);
+    const bool minDiv = c.getBool("minDivergence", false);
+    const long nbIt = c.getLong("nbIt");
+    for (long it = 0; it < nbIt; it++) {
+      std::cout << "\t(TotalVariability) --------- start iteration " << it << " --------" << std::endl;
+      tv.substractM();
+      tv.estimateTETt();
+      tv.estimateAandC();
+      tv.updateTestimate();
+      if (minDiv) tv.minDivergence();
+      if (c.getBool("orthonormalizeT", false)) tv.orthonormalizeT();
+      tv.resetTmpAcc();
+      tv.reloadStats();  // the reference re-reads N / F_X from disk here (:149-153); we keep a host copy
+      if (c.getBool("saveAllTVMatrices", false)) tv.saveT(c.getParam("totalVariabilityMatrix") + std::to_string(it), c);
+    }
+    tv.saveT(c.getParam("totalVariabilityMatrix"), c);
+    if (minDiv) {
+      Matrix m = tv.getUbmMeans();
+      m.save(c.getString("matrixFilesPath", "") + c.getParam("meanEstimate") + c.getString("saveMatrixFilesExtension", ""),
+             c.getString("saveMatrixFormat", "DB"));
+    }
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ IvTest (scoring = plda, native)
+int IvTest(Config &c) {
+  try {
+    const std::string scoring = c.getString("scoring", "plda");
+    if (scoring != "plda") LIA_THROW("this engine implements scoring = plda (native); got " + scoring);
+    const std::string gender = c.getString("gender", "M");
+    const double threshold = c.getDouble("decisionThreshold", 0.0);
+    const std::string vpath = c.getParam("testVectorFilesPath") + "/", vext = c.getString("loadVectorFilesExtension", ".y");
+    const std::string mpath = c.getString("matrixFilesPath", ""), mext = c.getString("loadMatrixFilesExtension", "");
+    const std::string mfmt = c.getString("loadMatrixFormat", "DB");
+    // trials: "segment model1 model2 ..." ; enrolment: "model session1 session2 ..." (PldaTools.cpp:3437-3560)
+    XList trials(c.getParam("ndxFilename"));
+    std::vector<std::string> modelIds, enrolSessions, segIds;
+    std::vector<int32_t> modelOf;
+    std::map<std::string, int> modelIndex;
+    if (c.existsParam("targetIdList") && !c.getParam("targetIdList").empty()) {
+      XList enrol(c.getParam("targetIdList"));
+      auto lines = enrol.lines();
+      std::stable_sort(lines.begin(), lines.end(),
+                       [](const std::vector<std::string> &a, const std::vector<std::string> &b) { return a.size() > b.size(); });
+      for (auto &l : lines) {
+        if (!modelIndex.count(l[0])) {
+          modelIndex[l[0]] = (int)modelIds.size();
+          modelIds.push_back(l[0]);
+        }
+        for (size_t e = 1; e < l.size(); e++) {
+          enrolSessions.push_back(l[e]);
+          modelOf.push_back(modelIndex[l[0]]);
+        }
+      }
+    }
+    std::map<std::string, int> segIndex;
+    for (auto &l : trials.lines()) {
+      if (!segIndex.count(l[0])) {
+        segIndex[l[0]] = (int)segIds.size();
+        segIds.push_back(l[0]);
+      }
+      for (size_t e = 1; e < l.size(); e++)
+        if (!modelIndex.count(l[e])) {  // a model without enrolment list is its own single session
+          modelIndex[l[e]] = (int)modelIds.size();
+          modelIds.push_back(l[e]);
+          enrolSessions.push_back(l[e]);
+          modelOf.push_back(modelIndex[l[e]]);
+        }
+    }
+    auto loadVec = [&](const std::string &name) {
+      Matrix v;
+      v.load(vpath + name + vext, mfmt);
+      return v;
+    };
+    const size_t d = loadVec(enrolSessions[0]).cols;
+    const size_t nEnrol = enrolSessions.size(), nTest = segIds.size(), nModels = modelIds.size();
+    // mean subtraction with pldaMeanVec (PldaTest::center)
+    Matrix mean;
+    mean.load(mpath + c.getString("pldaMeanVec", "pldaMeanVec") + mext, mfmt);
+    Matrix models(d, nEnrol), segments(d, nTest);
+    for (size_t j = 0; j < nEnrol; j++) {
+      Matrix v = loadVec(enrolSessions[j]);
+      for (size_t i = 0; i < d; i++) models(i, j) = v.data[i] - mean.data[i];
+    }
+    for (size_t j = 0; j < nTest; j++) {
+      Matrix v = loadVec(segIds[j]);
+      for (size_t i = 0; i < d; i++) segments(i, j) = v.data[i] - mean.data[i];
+    }
+    Matrix F, G, Sigma;
+    F.load(mpath + c.getString("pldaEigenVoiceMatrix", "pldaEigenVoiceMatrix") + mext, mfmt);
+    Sigma.load(mpath + c.getString("pldaSigmaMatrix", "pldaSigmaMatrix") + mext, mfmt);
+    const int rG = (int)c.getLong("pldaEigenChannelNumber", 0);
+    if (rG > 0) G.load(mpath + c.getString("pldaEigenChannelMatrix", "pldaEigenChannelMatrix") + mext, mfmt);
+    Matrix scores(nModels, nTest);
+    LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
+                                     Sigma.data.data(), models.data.data(), nEnrol, modelOf.data(), nModels,
+                                     segments.data.data(), nTest, scores.data.data()));
+    // NIST ascii output of the trials listed in the NDX (IvTest.cpp:415-439)
+    std::ofstream outNist(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
+    for (auto &l : trials.lines()) {
+      int s = segIndex[l[0]];
+      for (size_t e = 1; e < l.size(); e++) {
+        int m = modelIndex[l[e]];
+        double sc = scores(m, s);
+        outputResultLine(sc, l[e], l[0], gender, setDecision(sc, threshold), outNist);
+      }
+    }
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+}  // namespace lia

@@ -1,0 +1,329 @@
+// engine.cpp -- the LIA_SpkTools batch functions re-expressed over the C ABI: Gmm handle,
+// accumulateStatEM / trainModel (TrainTools.cpp), TVAcc (AccumulateTVStat.cpp).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <iostream>
+#include <set>
+
+#include "lia_host.h"
+
+namespace lia {
+
+// ------------------------------------------------------------------ Gmm
+Gmm::Gmm(const MixtureGD &m, bool use_file_cst) {
+  h_ = lr_gmm_create(m.C, m.D, m.w.data(), m.mean.data(), m.cov.data());
+  if (!h_) LIA_THROW(std::string("engine: ") + lr_last_error());
+  // RAW / XML files carry their own cst records; the reference scores with the stored value
+  if (use_file_cst) LIA_CHECK(lr_gmm_set_cst(h_, m.cst.data()));
+}
+Gmm::~Gmm() { lr_gmm_destroy(h_); }
+void Gmm::set(const MixtureGD &m) { LIA_CHECK(lr_gmm_set(h_, m.w.data(), m.mean.data(), m.cov.data())); }
+void Gmm::get(MixtureGD &m) const {
+  LIA_CHECK(lr_gmm_get(h_, m.w.data(), m.mean.data(), m.cov.data(), m.covinv.data(), m.cst.data(),
+                       m.det.data()));
+}
+
+// ------------------------------------------------------------------ TrainTools
+TrainCfg::TrainCfg(const Config &c) {
+  initVarianceFlooring = c.getDouble("initVarianceFlooring");
+  initVarianceCeiling = c.getDouble("initVarianceCeiling");
+  finalVarianceFlooring = c.getDouble("finalVarianceFlooring");
+  finalVarianceCeiling = c.getDouble("finalVarianceCeiling");
+  nbTrainIt = c.getLong("nbTrainIt");
+  baggedFrameProbability = c.getDouble("baggedFrameProbability");
+}
+
+double setItParameter(double begin, double end, int nbIt, int it) {
+  if (nbIt < 2) return begin;
+  double itVal = (begin - end) / ((double)nbIt - 1.0);
+  return begin - itVal * it;
+}
+
+static bool baggedFrame(double p) { return ((double)rand() / (double)RAND_MAX) < p; }
+
+SegCluster baggedSegments(const SegCluster &in, double p, long minLen, long maxLen) {
+  SegCluster out;
+  for (const Seg &seg : in) {
+    long begin = seg.begin, left = seg.length;
+    while (true) {
+      long verify = std::min(std::max(left, minLen), maxLen);
+      bool move = left <= verify;
+      long length = move ? left : verify;
+      if (length > 0 && baggedFrame(p)) out.push_back({seg.source, begin, length, seg.label});
+      if (move) break;
+      left -= length;
+      begin += length;
+    }
+  }
+  return out;
+}
+
+void EmAcc::reset(int C, int D) {
+  occ.assign(C, 0.0);
+  m1.assign((size_t)C * D, 0.0);
+  m2.assign((size_t)C * D, 0.0);
+  n = 0;
+}
+
+double accumulateStatEM(const FeatureServer &fs, const Gmm &g, const SegCluster &segs, EmAcc &acc,
+                        double weight) {
+  std::vector<lr_seg> es = toEngineSegs(fs, segs);
+  double llk = 0.0;
+  LIA_CHECK(lr_gmm_em_accumulate(g.h(), fs.data(), fs.getFeatureCount(), fs.ld(), es.data(), es.size(),
+                                 weight, acc.occ.data(), acc.m1.data(), acc.m2.data(), &llk, &acc.n));
+  return llk;
+}
+
+void computeMeanCov(const FeatureServer &fs, const SegCluster &segs, std::vector<double> &mean,
+                    std::vector<double> &cov) {
+  // FrameAccGD over the selected frames: gather them (labels may skip frames), then one device pass
+  const int D = fs.getVectSize();
+  std::vector<float> sel;
+  for (auto &s : segs) {
+    const float *p = fs.data() + (fs.getFirstFeatureIndexOfASource(s.source) + s.begin) * fs.ld();
+    sel.insert(sel.end(), p, p + (size_t)s.length * D);
+  }
+  if (sel.empty()) LIA_THROW("computeMeanCov: no selected frame");
+  mean.assign(D, 0.0);
+  cov.assign(D, 0.0);
+  LIA_CHECK(lr_frames_mean_cov(sel.data(), sel.size() / D, D, D, mean.data(), cov.data()));
+}
+
+void mixtureInit(const FeatureServer &fs, const SegCluster &segs, const std::vector<double> &globalCov,
+                 const Config &c, MixtureGD &world) {
+  // mean of randomly picked 3..7-frame chunks per component, cov = global cov, equal weights
+  const long minLen = c.getLong("baggedMinimalLength", 3), maxLen = c.getLong("baggedMaximalLength", 7);
+  const double nbFrameToSelect = (double)c.getLong("nbFrameToSelect", 50);
+  const int C = world.C, D = world.D;
+  const long total = totalFrame(segs);
+  double proba = nbFrameToSelect / (double)std::max(1L, total);
+  std::vector<double> sum((size_t)C * D, 0.0), cnt(C, 0.0);
+  srand(100 + 1);  // ((stream+1)*100)+(baggedIt+1) for stream 0, iteration 0 (TrainTools.cpp:737)
+  // one pass over the segments, each chunk assigned to a random component when selected
+  for (const Seg &seg : segs) {
+    long begin = seg.begin, left = seg.length;
+    const size_t first = fs.getFirstFeatureIndexOfASource(seg.source);
+    while (left > 0) {
+      long length = std::min(std::min(std::max(left, minLen), maxLen), left);
+      for (int k = 0; k < C; k++) {
+        if (!baggedFrame(proba)) continue;
+        for (long t = 0; t < length; t++) {
+          const float *x = fs.data() + (first + begin + t) * fs.ld();
+          for (int i = 0; i < D; i++) sum[(size_t)k * D + i] += x[i];
+        }
+        cnt[k] += (double)length;
+      }
+      left -= length;
+      begin += length;
+    }
+  }
+  for (int k = 0; k < C; k++) {
+    for (int i = 0; i < D; i++) {
+      world.mean[(size_t)k * D + i] = cnt[k] > 0 ? sum[(size_t)k * D + i] / cnt[k] : 0.0;
+      world.cov[(size_t)k * D + i] = globalCov[i];
+    }
+    world.w[k] = 1.0 / C;
+  }
+  world.computeAll();
+}
+
+void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs,
+                const std::vector<double> &globalCov, MixtureGD &world, const TrainCfg &cfg) {
+  // trainModelStream (TrainTools.cpp:1030-1110), single stream
+  const long minLen = c.getLong("baggedMinimalLength", 3), maxLen = c.getLong("baggedMaximalLength", 7);
+  const long initRand = c.getLong("initRand", 0);
+  const bool verbose = c.getBool("verbose", false);
+  Gmm g(world);
+  EmAcc acc;
+  double llkPrev = 0;
+  for (long it = 0; it < cfg.nbTrainIt; it++) {
+    const double flooring = setItParameter(cfg.initVarianceFlooring, cfg.finalVarianceFlooring, (int)cfg.nbTrainIt, (int)it);
+    const double ceiling = setItParameter(cfg.initVarianceCeiling, cfg.finalVarianceCeiling, (int)cfg.nbTrainIt, (int)it);
+    acc.reset(world.C, world.D);  // emAcc.resetEM()
+    srand((unsigned)(((it + 1 + initRand) * 200) + 20 + 1));  // :1070 (stream 0, baggedIt 0)
+    SegCluster bagged = cfg.baggedFrameProbability >= 1.0 ? segs
+                                                          : baggedSegments(segs, cfg.baggedFrameProbability, minLen, maxLen);
+    double llk = accumulateStatEM(fs, g, bagged, acc);
+    // *world = emAcc.getEM(); varianceControl(world, flooring, ceiling, globalCov)  (:1076-1077)
+    LIA_CHECK(lr_gmm_em_update(g.h(), acc.occ.data(), acc.m1.data(), acc.m2.data(), flooring, ceiling,
+                               globalCov.data()));
+    if (verbose)
+      std::cout << "ML (partial) estimate it[" << it << "] (take care, it corresponds to the previous it,0 means init likelihood) = "
+                << (acc.n > 0 ? llk / acc.n : 0.0) << std::endl;
+    llkPrev = llk;
+  }
+  (void)llkPrev;
+  g.get(world);
+}
+
+// ------------------------------------------------------------------ TVAcc
+TVAcc::TVAcc(const std::string &ndxFile, const Config &c) : cfg_(c) {
+  XList ndx(ndxFile);
+  lines_ = ndx.lines();
+  if (lines_.empty()) LIA_THROW("TVAcc: empty NDX list " + ndxFile);
+  init(c);
+}
+TVAcc::TVAcc(const std::vector<std::vector<std::string>> &fileLines, const Config &c)
+    : cfg_(c), lines_(fileLines) {
+  if (lines_.empty()) LIA_THROW("TVAcc: empty file list");
+  init(c);
+}
+void TVAcc::init(const Config &c) {
+  world_ = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+  R_ = (int)c.getLong("totalVariabilityNumber", 1);
+  tv_ = lr_tv_create(world_.C, world_.D, R_, lines_.size(), world_.mean.data(), world_.covinv.data());
+  if (!tv_) LIA_THROW(std::string("engine: ") + lr_last_error());
+  N_ = Matrix(lines_.size(), world_.C);
+  F_ = Matrix(lines_.size(), (size_t)world_.C * world_.D);
+}
+TVAcc::~TVAcc() { lr_tv_destroy(tv_); }
+
+void TVAcc::computeAndAccumulateTVStat(const Config &c) {
+  // every file of every NDX line, once in the FeatureServer; a file listed on several lines
+  // feeds each of them (AccumulateTVStat.cpp:339-346)
+  std::vector<std::string> all;
+  {
+    XList tmp;
+    std::set<std::string> seen;
+    for (auto &l : lines_)
+      for (auto &f : l)
+        if (seen.insert(f).second) all.push_back(f);
+  }
+  FeatureServer fs(c, all);
+  SegCluster sel = selectedSegments(c, fs, c.getParam("labelSelectedFrames"));
+  std::vector<lr_seg> segs;
+  for (const Seg &s : sel)
+    for (size_t line = 0; line < lines_.size(); line++)
+      if (std::find(lines_[line].begin(), lines_[line].end(), s.source) != lines_[line].end()) {
+        lr_seg e;
+        e.begin = (int64_t)(fs.getFirstFeatureIndexOfASource(s.source) + s.begin);
+        e.length = s.length;
+        e.row = (int32_t)line;
+        e.pad_ = 0;
+        segs.push_back(e);
+      }
+  Gmm g(world_, true);
+  LIA_CHECK(lr_gmm_bwstats(g.h(), fs.data(), fs.getFeatureCount(), fs.ld(), segs.data(), segs.size(),
+                           lines_.size(), N_.data.data(), F_.data.data()));
+  LIA_CHECK(lr_tv_set_stats(tv_, N_.data.data(), F_.data.data()));
+}
+
+void TVAcc::loadT(const std::string &name, const Config &c) {
+  Matrix T;
+  T.load(c.getString("matrixFilesPath", "") + name + c.getString("loadMatrixFilesExtension", ""),
+         c.getString("loadMatrixFormat", "DB"));
+  if (T.cols < T.rows) {  // :636-639
+    Matrix t(T.cols, T.rows);
+    for (size_t i = 0; i < T.rows; i++)
+      for (size_t j = 0; j < T.cols; j++) t(j, i) = T(i, j);
+    T = t;
+  }
+  if ((long)T.rows != c.getLong("totalVariabilityNumber") || T.cols != (size_t)world_.C * world_.D)
+    LIA_THROW("Incorrect dimension of TotalVariability Matrix");
+  LIA_CHECK(lr_tv_set_T(tv_, T.data.data()));
+}
+
+void TVAcc::initT(const Config &c) {
+  const size_t sv = (size_t)world_.C * world_.D;
+  Matrix T(R_, sv);
+  const std::string law = c.getString("randomInitLaw", "normal");
+  double norm = 0.0;
+  for (double v : world_.covinv) norm += v;
+  if (law == "normal") {
+    // ScoreWarp.cpp:68-79 Box-Muller on libc rand(), cosine branch, float ratio
+    double x1 = rand() / (float)RAND_MAX, x2;
+    for (size_t i = 0; i < T.rows; i++)
+      for (size_t j = 0; j < T.cols; j++) {
+        double val;
+        do {
+          x2 = x1;
+          x1 = rand() / (float)RAND_MAX;
+          val = std::sqrt(-2.0 * std::log(x1)) * std::cos(2.0 * 3.14159265358979323846 * x2);
+        } while (std::isnan(val) || std::isinf(val));
+        T(i, j) = val * norm * 0.001;
+      }
+  } else if (law == "uniform") {
+    srand48((long)(sv * R_));
+    for (auto &v : T.data) v = drand48() * norm / (double)sv;
+  } else {
+    LIA_THROW("Selected random initialization law does not exist");
+  }
+  LIA_CHECK(lr_tv_set_T(tv_, T.data.data()));
+}
+
+void TVAcc::saveT(const std::string &name, const Config &c) {
+  Matrix T(R_, (size_t)world_.C * world_.D);
+  LIA_CHECK(lr_tv_get_T(tv_, T.data.data()));
+  T.save(c.getString("matrixFilesPath", "") + name + c.getString("saveMatrixFilesExtension", ""),
+         c.getString("saveMatrixFormat", "DB"));
+}
+
+void TVAcc::loadN(const Config &c) {
+  N_.load(c.getString("matrixFilesPath", "") + c.getParam("nullOrderStatSpeaker") +
+              c.getString("loadMatrixFilesExtension", ""),
+          c.getString("loadMatrixFormat", "DB"));
+  if (N_.rows != lines_.size() || N_.cols != (size_t)world_.C) LIA_THROW("Incorrect dimension of N Matrix");
+}
+void TVAcc::loadF_X(const Config &c) {
+  F_.load(c.getString("matrixFilesPath", "") + c.getParam("firstOrderStatSpeaker") +
+              c.getString("loadMatrixFilesExtension", ""),
+          c.getString("loadMatrixFormat", "DB"));
+  if (F_.rows != lines_.size() || F_.cols != (size_t)world_.C * world_.D)
+    LIA_THROW("Incorrect dimension of F_X Matrix");
+  LIA_CHECK(lr_tv_set_stats(tv_, N_.data.data(), F_.data.data()));
+}
+void TVAcc::saveAccs(const Config &c) {
+  std::string fx = "F_X.mat", n = "N.mat";
+  const std::string path = c.getString("matrixFilesPath", ""), ext = c.getString("saveMatrixFilesExtension", "");
+  if (c.existsParam("nullOrderStatSpeaker")) n = path + c.getParam("nullOrderStatSpeaker") + ext;
+  if (c.existsParam("firstOrderStatSpeaker")) fx = path + c.getParam("firstOrderStatSpeaker") + ext;
+  F_.save(fx, c.getString("saveMatrixFormat", "DB"));
+  N_.save(n, c.getString("saveMatrixFormat", "DB"));
+}
+
+void TVAcc::substractM() { LIA_CHECK(lr_tv_subtract_m(tv_)); }
+void TVAcc::estimateTETt() { LIA_CHECK(lr_tv_estimate_tett(tv_)); }
+void TVAcc::estimateW() { LIA_CHECK(lr_tv_estimate_w(tv_)); }
+void TVAcc::estimateAandC() { LIA_CHECK(lr_tv_estimate_a_and_c(tv_)); }
+void TVAcc::resetTmpAcc() { LIA_CHECK(lr_tv_reset_tmp_acc(tv_)); }
+void TVAcc::updateTestimate() { LIA_CHECK(lr_tv_update_t(tv_)); }
+void TVAcc::minDivergence() {
+  size_t sessions = 0;
+  for (auto &l : lines_) sessions += l.size();  // _n_sessions (:137)
+  LIA_CHECK(lr_tv_min_divergence(tv_, (double)sessions));
+}
+void TVAcc::orthonormalizeT() { LIA_CHECK(lr_tv_orthonormalize_t(tv_)); }
+
+void TVAcc::loadMeanEstimate(const std::vector<double> &mean) {
+  if (mean.size() != (size_t)world_.C * world_.D) LIA_THROW("Incorrect dimension of meanEstimate vector");
+  LIA_CHECK(lr_tv_set_mean(tv_, mean.data()));
+}
+void TVAcc::reloadStats() { LIA_CHECK(lr_tv_set_stats(tv_, N_.data.data(), F_.data.data())); }
+Matrix TVAcc::getUbmMeans() {
+  Matrix m(1, (size_t)world_.C * world_.D);
+  LIA_CHECK(lr_tv_get_mean(tv_, m.data.data()));
+  return m;
+}
+
+Matrix TVAcc::getW() {
+  Matrix W(lines_.size(), R_);
+  LIA_CHECK(lr_tv_get_W(tv_, W.data.data()));
+  return W;
+}
+
+void TVAcc::saveWbyFile(const Config &c) {
+  const std::string path = c.getParam("saveVectorFilesPath"), ext = c.getString("vectorFilesExtension", ".y");
+  XList ids(c.getParam("targetIdList"));
+  Matrix W = getW();
+  size_t session = 0;
+  for (auto &line : ids.lines()) {
+    if (session >= W.rows) break;
+    Matrix y(1, R_);
+    for (int i = 0; i < R_; i++) y(0, i) = W(session, i);
+    y.save(path + line[0] + ext, c.getString("saveMatrixFormat", "DB"));
+    session++;
+  }
+}
+
+}  // namespace lia

@@ -176,6 +176,7 @@ double *lr_tv_dev_F(lr_tv *tv);
 lr_status lr_tv_set_T(lr_tv *tv, const double *T); /* loadT / initT result */
 lr_status lr_tv_get_T(lr_tv *tv, double *T);
 lr_status lr_tv_get_mean(lr_tv *tv, double *ubm_mean);
+lr_status lr_tv_set_mean(lr_tv *tv, const double *ubm_mean); /* loadMeanEstimate :671 */
 lr_status lr_tv_get_W(lr_tv *tv, double *W);
 /* any output may be NULL; A[C x R*R], Cmx[R x C*D], Rm[R*R], r[R], meanW[R] */
 lr_status lr_tv_get_acc(lr_tv *tv, double *A, double *Cmx, double *Rm, double *r, double *meanW);

@@ -375,6 +375,11 @@ class TV:
         _check(lib().lr_tv_get_mean(self.h, _d(m)))
         return m
 
+    def set_mean(self, mean):
+        m = _f64(mean).reshape(-1)
+        assert m.size == self.C * self.D
+        _check(lib().lr_tv_set_mean(self.h, _d(m)))
+
     def get_W(self):
         W = np.empty((self.U, self.R))
         _check(lib().lr_tv_get_W(self.h, _d(W)))

@@ -31,6 +31,8 @@ struct lr_tv {
   double *d_acc = nullptr;  // [A C*R*R | Cmx R*sv | Rm R*R | r R | sumW R]
   double *d_meanW = nullptr;
   double *d_Lb = nullptr, *d_Eb = nullptr;  // [batch x R*R] work
+  double *d_Yb = nullptr;                   // [batch x R*R] triangular inverse (E-step)
+  double *d_invD = nullptr;                 // [batch x nblk x 64 x 64] diagonal-block inverses
   double *d_ones = nullptr;                 // [max(batch, R)]
   double **d_ptr_L = nullptr, **d_ptr_E = nullptr, **d_ptr_W = nullptr;  // batch pointers
   double **d_ptr_A = nullptr, **d_ptr_Tc = nullptr;                      // component pointers
@@ -74,15 +76,6 @@ __global__ void k_add_identity(int nb, int R, double *__restrict__ L) {
   if (i < nb * R) {
     int b = i / R, d = i - b * R;
     L[(size_t)b * R * R + (size_t)d * R + d] += 1.0;
-  }
-}
-
-__global__ void k_set_identity(int nb, int R, double *__restrict__ E) {
-  size_t total = (size_t)nb * R * R;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    size_t e = i % ((size_t)R * R);
-    E[i] = (e / R == e % R) ? 1.0 : 0.0;
   }
 }
 
@@ -137,6 +130,100 @@ __global__ void k_scale_row(size_t n, const double *__restrict__ nrm, double *__
     v[i] *= s;
 }
 
+// ---- batched dense helpers --------------------------------------------------------------
+// cusolverDnDpotrsBatched and cublasDtrsmBatched run at < 1 TFLOP/s for R = 400..600 (measured,
+// profiles/r01_extra.md); the two routines below replace them.
+//
+// Solve L L^T x = b for ONE right-hand side per matrix (column-major lower factor, ld = n).
+// One CTA per matrix; x lives in shared memory.  Forward substitution is column oriented
+// (axpy over the contiguous column j), the backward pass is a dot product with column j.
+constexpr int kSolveThreads = 256;
+__global__ void __launch_bounds__(kSolveThreads)
+k_chol_solve(int n, const double *__restrict__ Lall, size_t stride, double *__restrict__ rhs) {
+  extern __shared__ double xs[];
+  __shared__ double red[kSolveThreads / 32];
+  const double *L = Lall + (size_t)blockIdx.x * stride;
+  double *b = rhs + (size_t)blockIdx.x * n;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += kSolveThreads) xs[i] = b[i];
+  __syncthreads();
+  for (int j = 0; j < n; j++) {  // L y = b
+    const double xj = xs[j] / L[(size_t)j * n + j];
+    __syncthreads();
+    if (tid == 0) xs[j] = xj;
+    for (int i = j + 1 + tid; i < n; i += kSolveThreads) xs[i] -= L[(size_t)j * n + i] * xj;
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; j--) {  // L^T x = y :  x_j = (y_j - sum_{i>j} L_ij x_i) / L_jj
+    double part = 0.0;
+    for (int i = j + 1 + tid; i < n; i += kSolveThreads) part += L[(size_t)j * n + i] * xs[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kSolveThreads / 32; w++) t += red[w];
+      xs[j] = (xs[j] - t) / L[(size_t)j * n + j];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += kSolveThreads) b[i] = xs[i];
+}
+
+// Inverses of the NB x NB diagonal blocks of a batch of lower factors.  One CTA per
+// (block, matrix); thread j computes column j of the inverse by forward substitution.
+constexpr int kNB = 64;
+__global__ void __launch_bounds__(kNB)
+k_diag_inv(int n, const double *__restrict__ Lall, size_t stride, double *__restrict__ invD,
+           int nblk) {
+  extern __shared__ double dsm[];
+  double (*Ls)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm);
+  double (*Xs)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm + kNB * (kNB + 1));
+  const int blk = blockIdx.x, mat = blockIdx.y;
+  const int k0 = blk * kNB, nb = min(kNB, n - k0);
+  const double *L = Lall + (size_t)mat * stride;
+  const int j = threadIdx.x;
+  for (int c = 0; c < nb; c++)
+    if (j < nb) Ls[j][c] = (j >= c) ? L[(size_t)(k0 + c) * n + k0 + j] : 0.0;  // Ls[row][col]
+  __syncthreads();
+  if (j < nb) {
+    for (int i = 0; i < nb; i++) {
+      double v = (i == j) ? 1.0 : 0.0;
+      if (i < j) {
+        Xs[i][j] = 0.0;
+        continue;
+      }
+      for (int k = j; k < i; k++) v -= Ls[i][k] * Xs[k][j];
+      Xs[i][j] = v / Ls[i][i];
+    }
+  }
+  __syncthreads();
+  double *out = invD + ((size_t)mat * nblk + blk) * kNB * kNB;  // column-major, ld = kNB
+  for (int c = 0; c < kNB; c++) out[(size_t)c * kNB + j] = (j < nb && c < nb) ? Xs[j][c] : 0.0;
+}
+
+// dst[mat][0:nb, 0:nb] = src[mat][0:nb, 0:nb]  (column-major blocks with their own ld / stride)
+__global__ void k_copy_block(int nb, const double *__restrict__ src, int lds, size_t ss,
+                             double *__restrict__ dst, int ldd, size_t sd) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nb * nb) return;
+  int col = e / nb, row = e - col * nb;
+  dst[(size_t)blockIdx.y * sd + (size_t)col * ldd + row] =
+      src[(size_t)blockIdx.y * ss + (size_t)col * lds + row];
+}
+
+// zero the strictly upper triangle (column-major) of a batch of n x n matrices
+__global__ void k_zero_upper(int n, size_t stride, double *__restrict__ A, int batch) {
+  size_t total = (size_t)batch * n * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t m = i / ((size_t)n * n), e = i - m * (size_t)n * n;
+    int col = (int)(e / n), row = (int)(e - (size_t)col * n);
+    if (row < col) A[m * stride + e] = 0.0;
+  }
+}
+
 int grid_for(size_t n, int threads = 256) {
   size_t g = (n + threads - 1) / threads;
   return (int)std::min<size_t>(g, (size_t)engine().sm_count * 16);
@@ -156,6 +243,8 @@ void tv_free(lr_tv *tv) {
   cudaFree(tv->d_meanW);
   cudaFree(tv->d_Lb);
   cudaFree(tv->d_Eb);
+  cudaFree(tv->d_Yb);
+  cudaFree(tv->d_invD);
   cudaFree(tv->d_ones);
   cudaFree(tv->d_ptr_L);
   cudaFree(tv->d_ptr_E);
@@ -212,21 +301,52 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
   lr_status st = check_factor(tv, nb, "i-vector posterior precision L");
   if (st != LR_OK) return st;
   if (!want_inverse) {
-    // pointer array of the right-hand sides: rows of W for this batch
-    st = upload_ptrs(tv->d_ptr_W, tv->d_W + u0 * R, R, nb);
-    if (st != LR_OK) return st;
-    LR_CUSOLVER(cusolverDnDpotrsBatched(tv->solver, CUBLAS_FILL_MODE_LOWER, R, 1, tv->d_ptr_L, R,
-                                        tv->d_ptr_W, R, tv->d_info, nb));
-    count_launch();
+    // w = L^-1 aux: one CTA per utterance, aux sits in W and is overwritten by the i-vector
+    k_chol_solve<<<nb, kSolveThreads, R * sizeof(double), e.stream>>>(R, tv->d_Lb, rr,
+                                                                      tv->d_W + u0 * R);
+    LR_CHECK_LAUNCH();
     return LR_OK;
   }
-  k_set_identity<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>(nb, R, tv->d_Eb);
+  // Explicit inverse Linv = Y^T Y with Y = Lfac^-1, built block row by block row from the
+  // inverses of the 64 x 64 diagonal blocks -- everything heavy is a strided-batched DGEMM:
+  //   Y[i, 0:i] = -invD_ii (Lfac[i, 0:i] Y[0:i, 0:i]),   Y[i, i] = invD_ii
+  const int nblk = (R + kNB - 1) / kNB;
+  const double mone = -1.0;
+  k_zero_upper<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>(R, rr, tv->d_Lb, nb);
   LR_CHECK_LAUNCH();
-  LR_CUBLAS(cublasDtrsmBatched(e.blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N,
-                               CUBLAS_DIAG_NON_UNIT, R, R, &one, tv->d_ptr_L, R, tv->d_ptr_E, R, nb));
-  count_launch();
-  LR_CUBLAS(cublasDtrsmBatched(e.blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T,
-                               CUBLAS_DIAG_NON_UNIT, R, R, &one, tv->d_ptr_L, R, tv->d_ptr_E, R, nb));
+  static bool diag_attr = false;
+  const size_t diag_smem = 2 * kNB * (kNB + 1) * sizeof(double);
+  if (!diag_attr) {
+    LR_CUDA(cudaFuncSetAttribute(k_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
+    diag_attr = true;
+  }
+  k_diag_inv<<<dim3(nblk, nb), kNB, diag_smem, e.stream>>>(R, tv->d_Lb, rr, tv->d_invD, nblk);
+  LR_CHECK_LAUNCH();
+  LR_CUDA(cudaMemsetAsync(tv->d_Yb, 0, (size_t)nb * rr * sizeof(double), e.stream));
+  const long long sD = (long long)nblk * kNB * kNB;
+  for (int i = 0; i < nblk; i++) {
+    const int r0 = i * kNB, nbi = std::min(kNB, R - r0);
+    if (i > 0) {
+      // Tmp[nbi x r0] = Lfac[r0:r0+nbi, 0:r0] * Y[0:r0, 0:r0]   (Tmp lives in Eb)
+      LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, nbi, r0, r0, &one,
+                                          tv->d_Lb + r0, R, (long long)rr, tv->d_Yb, R,
+                                          (long long)rr, &zero, tv->d_Eb, R, (long long)rr, nb));
+      count_launch();
+      // Y[r0:, 0:r0] = -invD_ii * Tmp
+      LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, nbi, r0, nbi, &mone,
+                                          tv->d_invD + (size_t)i * kNB * kNB, kNB, sD, tv->d_Eb, R,
+                                          (long long)rr, &zero, tv->d_Yb + r0, R, (long long)rr, nb));
+      count_launch();
+    }
+    // Y[r0:, r0:] = invD_ii
+    k_copy_block<<<dim3(ceil_div((long)nbi * nbi, 256), nb), 256, 0, e.stream>>>(
+        nbi, tv->d_invD + (size_t)i * kNB * kNB, kNB, (size_t)sD, tv->d_Yb + (size_t)r0 * R + r0, R, rr);
+    LR_CHECK_LAUNCH();
+  }
+  // Linv = Y^T Y  -> Eb
+  LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, R, R, &one, tv->d_Yb, R,
+                                      (long long)rr, tv->d_Yb, R, (long long)rr, &zero, tv->d_Eb, R,
+                                      (long long)rr, nb));
   count_launch();
   // W_b = Linv_b aux_b : aux currently sits in W; go through Lb's first nb*R doubles as scratch
   LR_CUDA(cudaMemcpyAsync(tv->d_Lb, tv->d_W + u0 * R, (size_t)nb * R * sizeof(double),
@@ -266,6 +386,8 @@ lr_tv *lr_tv_create(int C, int D, int R, size_t U, const double *ubm_mean,
             A(&tv->d_Ts, R * tv->sv) && A(&tv->d_W, U * R) && A(&tv->d_mean, tv->sv) &&
             A(&tv->d_invvar, tv->sv) && A(&tv->d_tett, (size_t)C * rr) && A(&tv->d_acc, tv->acc_len()) &&
             A(&tv->d_meanW, R) && A(&tv->d_Lb, (size_t)nbmax * rr) && A(&tv->d_Eb, (size_t)nbmax * rr) &&
+            A(&tv->d_Yb, (size_t)nbmax * rr) &&
+            A(&tv->d_invD, (size_t)nbmax * ((R + kNB - 1) / kNB) * kNB * kNB) &&
             A(&tv->d_ones, std::max<size_t>(nbmax, R)) &&
             cudaMalloc(&tv->d_ptr_L, nbmax * sizeof(double *)) == cudaSuccess &&
             cudaMalloc(&tv->d_ptr_E, nbmax * sizeof(double *)) == cudaSuccess &&
@@ -351,6 +473,14 @@ lr_status lr_tv_get_mean(lr_tv *tv, double *ubm_mean) {
   LR_READY();
   LR_REQUIRE(tv && ubm_mean, "lr_tv_get_mean: null argument");
   TV_COPY(ubm_mean, tv->d_mean, tv->sv, cudaMemcpyDeviceToHost);
+  LR_CUDA(cudaStreamSynchronize(engine().stream));
+  return LR_OK;
+}
+
+lr_status lr_tv_set_mean(lr_tv *tv, const double *ubm_mean) {
+  LR_READY();
+  LR_REQUIRE(tv && ubm_mean, "lr_tv_set_mean: null argument");
+  TV_COPY(tv->d_mean, ubm_mean, tv->sv, cudaMemcpyHostToDevice);
   LR_CUDA(cudaStreamSynchronize(engine().stream));
   return LR_OK;
 }
