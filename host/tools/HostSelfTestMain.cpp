@@ -1,0 +1,70 @@
+// HostSelfTestMain.cpp -- CPU-only check of the host surface (no engine call): Config, XList,
+// MixtureGD RAW <-> XML, Matrix DB <-> DT, FeatureServer with mask, label selection, bagging.
+// Prints "key value" lines that tests/test_host_cpu.py compares with numpy.
+#include <cstdio>
+#include <iostream>
+
+#include "lia_host.h"
+
+int main(int argc, char **argv) {
+  try {
+    lia::Config c;
+    c.parseCmdLine(argc, argv);
+    std::cout.precision(17);
+    lia::MixtureGD m = lia::MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+    double sw = 0, sm = 0, sc = 0, scst = 0;
+    for (double v : m.w) sw += v;
+    for (double v : m.mean) sm += v;
+    for (double v : m.cov) sc += v;
+    lia::MixtureGD m2 = m;
+    m2.computeAll();
+    for (int k = 0; k < m.C; k++) scst += m2.cst[k] / m.cst[k];
+    std::cout << "gmm " << m.C << " " << m.D << " " << sw << " " << sm << " " << sc << " " << scst / m.C << "\n";
+    m.save(c.getParam("tmpPrefix") + ".xml", "XML");
+    lia::MixtureGD x;
+    x.load(c.getParam("tmpPrefix") + ".xml", "XML");
+    double dmax = 0;
+    for (size_t i = 0; i < m.mean.size(); i++) dmax = std::max(dmax, std::abs(m.mean[i] - x.mean[i]) + std::abs(m.covinv[i] - x.covinv[i]));
+    std::cout << "xml_roundtrip " << dmax << "\n";
+    lia::XList ndx(c.getParam("ndxFilename"));
+    std::cout << "ndx " << ndx.lines().size() << " " << ndx.allElements().size() << " " << ndx.allUniqueElements().size() << "\n";
+    std::vector<std::string> files;
+    for (auto &l : ndx.lines()) files.push_back(l[0]);
+    lia::FeatureServer fs(c, files);
+    double sx = 0;
+    for (size_t i = 0; i < fs.getFeatureCount() * fs.ld(); i++) sx += fs.data()[i];
+    std::cout << "features " << fs.getFeatureCount() << " " << fs.getVectSize() << " " << sx << "\n";
+    lia::SegCluster sel = lia::selectedSegments(c, fs, c.getParam("labelSelectedFrames"));
+    double ssel = 0;
+    for (auto &s : sel) {
+      const float *p = fs.data() + (fs.getFirstFeatureIndexOfASource(s.source) + s.begin) * fs.ld();
+      for (long i = 0; i < s.length * (long)fs.ld(); i++) ssel += p[i];
+    }
+    std::cout << "selected " << sel.size() << " " << lia::totalFrame(sel) << " " << ssel << "\n";
+    lia::Matrix a(3, 5);
+    for (size_t i = 0; i < a.data.size(); i++) a.data[i] = 0.1 * i - 0.7;
+    a.save(c.getParam("tmpPrefix") + ".db", "DB");
+    a.save(c.getParam("tmpPrefix") + ".dt", "DT");
+    lia::Matrix b, d;
+    b.load(c.getParam("tmpPrefix") + ".db", "DB");
+    d.load(c.getParam("tmpPrefix") + ".dt", "DT");
+    double md = 0;
+    for (size_t i = 0; i < a.data.size(); i++) md = std::max(md, std::abs(a.data[i] - b.data[i]) + std::abs(a.data[i] - d.data[i]));
+    std::cout << "matrix_roundtrip " << b.rows << " " << d.cols << " " << md << "\n";
+    srand(7);
+    lia::SegCluster bag = lia::baggedSegments(sel, 0.5, 3, 7);
+    long maxlen = 0;
+    for (auto &s : bag) maxlen = std::max(maxlen, s.length);
+    std::cout << "bagged " << bag.size() << " " << lia::totalFrame(bag) << " " << maxlen << "\n";
+    std::cout << "setItParameter " << lia::setItParameter(0.5, 0.1, 5, 2) << " " << lia::timeToFrameIdx(0.299999999, 0.01) << "\n";
+    try {
+      c.getParam("noSuchParameter");
+    } catch (lia::Exception &e) {
+      std::cout << "exception " << (e.toString().find("noSuchParameter") != std::string::npos) << "\n";
+    }
+  } catch (std::exception &e) {
+    std::cout << "FAILED " << e.what() << std::endl;
+    return 1;
+  }
+  return 0;
+}

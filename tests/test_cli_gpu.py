@@ -1,0 +1,197 @@
+"""The five command-line programs of the C++ host mirror (host/build/*), end to end on files in the
+reference's formats, against the oracle: same configs keys, same outputs (NIST result lines, RAW
+GMM, DB matrices, per-id i-vector files)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from lia_ral_b200 import synth
+from tests import lia_files as lf
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "host", "build")
+
+
+def _run(prog, cfg, **over):
+    cmd = [os.path.join(BIN, prog), "--config", str(cfg)]
+    for k, v in over.items():
+        cmd += [f"--{k}", str(v)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Exception" not in out.stdout, out.stdout
+    return out.stdout
+
+
+@pytest.fixture(scope="module")
+def world(tmp_path_factory, oracle):
+    if not os.path.exists(os.path.join(BIN, "TrainWorld")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s", "-j", "8"])
+    d = tmp_path_factory.mktemp("cli")
+    C, D = 32, 12
+    w, mean, cov = synth.make_ubm(C, D, seed=51)
+    lf.write_raw_gmm(d / "wld.gmm", w, mean, cov)
+    utts = {}
+    for i in range(6):
+        X = synth.make_frames(w, mean, cov * 2.0, 300 + 40 * i, seed=60 + i)
+        utts[f"utt{i}"] = X
+        lf.write_spro4(d / f"utt{i}.prm", X)
+        # label files: two speech segments with a gap; utt5 has no label file (default label)
+        if i < 5:
+            lf.write_lines(d / f"utt{i}.lbl", [f"0.10 {1.5 + 0.1 * i:.2f} speech", "1.80 1.95 noise", f"2.00 {2.6 + 0.1 * i:.2f} speech"])
+    common = dict(mixtureFilesPath=str(d) + "/", loadMixtureFileExtension=".gmm", saveMixtureFileExtension=".gmm",
+                  loadMixtureFileFormat="RAW", saveMixtureFileFormat="RAW", featureFilesPath=str(d) + "/",
+                  loadFeatureFileExtension=".prm", loadFeatureFileFormat="SPRO4", labelFilesPath=str(d) + "/",
+                  labelFilesExtension=".lbl", labelSelectedFrames="speech", addDefaultLabel="true",
+                  defaultLabel="speech", frameLength=0.01, matrixFilesPath=str(d) + "/", loadMatrixFormat="DB",
+                  saveMatrixFormat="DB", loadMatrixFilesExtension=".mat", saveMatrixFilesExtension=".mat",
+                  minLLK=-200, maxLLK=200)
+    return dict(dir=d, C=C, D=D, w=w, mean=mean, cov=cov, utts=utts, common=common)
+
+
+def _selected(name, X):
+    """frames selected by the label rule (end inclusive, clipped)"""
+    i = int(name[3:])
+    if i == 5:
+        return np.arange(len(X))
+    a = np.arange(10, int(round((1.5 + 0.1 * i) * 100)) + 1)
+    b = np.arange(200, int(round((2.6 + 0.1 * i) * 100)) + 1)
+    return np.concatenate([a, b[b < len(X)]])
+
+
+def test_compute_test_cli(world, oracle):
+    d = world["dir"]
+    clients = {}
+    for k in range(3):
+        p = synth.perturb_ubm(world["w"], world["mean"], world["cov"], seed=70 + k, frac=0.4, scale=0.5)
+        clients[f"spk{k}"] = p
+        lf.write_raw_gmm(d / f"spk{k}.gmm", *p)
+    lf.write_lines(d / "test.ndx", [["utt0", "spk0", "spk1"], ["utt3", "spk2"], ["utt5", "spk0", "spk1", "spk2"]])
+    lf.write_cfg(d / "ct.cfg", **world["common"], ndxFilename=str(d / "test.ndx"), inputWorldFilename="wld",
+                 outputFilename=str(d / "ct.res"), gender="F", topDistribsCount=5,
+                 computeLLKWithTopDistribs="COMPLETE")
+    _run("ComputeTest", d / "ct.cfg")
+    lines = [l.split() for l in open(d / "ct.res")]
+    assert [(l[1], l[3]) for l in lines] == [("spk0", "utt0"), ("spk1", "utt0"), ("spk2", "utt3"),
+                                             ("spk0", "utt5"), ("spk1", "utt5"), ("spk2", "utt5")]
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    for l in lines:
+        X = np.ascontiguousarray(world["utts"][l[3]][_selected(l[3], world["utts"][l[3]])])
+        llk_w, idx, _, rest, _ = oracle.llk_determine_top(ow, X, 5, True)
+        llk_c = oracle.llk_use_top(oracle.gmm(*clients[l[1]]), X, idx, rest, True)
+        ref = llk_c.mean() - llk_w.mean()
+        assert l[0] == "F" and int(l[2]) == int(ref > 0)
+        assert abs(float(l[4]) - ref) < 2e-4
+    # segmental mode: one line per selected segment with begin / end times
+    _run("ComputeTest", d / "ct.cfg", segmentLLR="true", outputFilename=str(d / "ct_seg.res"))
+    seg_lines = [l.split() for l in open(d / "ct_seg.res")]
+    assert len(seg_lines) == 2 * 2 + 2 * 1 + 1 * 3 and all(len(l) == 7 for l in seg_lines)
+
+
+def test_train_world_cli(world, oracle):
+    d = world["dir"]
+    start = synth.perturb_ubm(world["w"], world["mean"], world["cov"], seed=81, frac=1.0, scale=0.4)
+    lf.write_raw_gmm(d / "start.gmm", *start)
+    lf.write_lines(d / "train.lst", [[f"utt{i}"] for i in range(6)])
+    lf.write_cfg(d / "tw.cfg", **world["common"], inputFeatureFilename=str(d / "train.lst"),
+                 inputWorldFilename="start", outputWorldFilename="trained", nbTrainIt=3,
+                 baggedFrameProbability=1.0, initVarianceFlooring=0.4, finalVarianceFlooring=0.2,
+                 initVarianceCeiling=8.0, finalVarianceCeiling=6.0)
+    _run("TrainWorld", d / "tw.cfg")
+    w, mean, cov = lf.read_raw_gmm(d / "trained.gmm")
+    X = np.concatenate([world["utts"][f"utt{i}"][_selected(f"utt{i}", world["utts"][f"utt{i}"])] for i in range(6)])
+    X = np.ascontiguousarray(X)
+    _, gcov = oracle.mean_cov(X)
+    g = oracle.gmm(*start)
+    for it in range(3):
+        fl = oracle.set_it_parameter(0.4, 0.2, 3, it)
+        ce = oracle.set_it_parameter(8.0, 6.0, 3, it)
+        _, _, occ, m1, m2 = oracle.em_accumulate(g, X)
+        wn, mn, cn = oracle.em_get(g, occ, m1, m2)
+        cn, _, _ = oracle.variance_control(cn, fl, ce, gcov)
+        g = oracle.gmm(wn, mn, cn)
+    assert np.allclose(w, g.w, rtol=1e-3, atol=1e-6)
+    assert np.abs(mean - g.mean).max() < 1e-3 * np.abs(g.mean).max()
+    assert np.abs(cov - g.cov).max() < 2e-3 * np.abs(g.cov).max()
+
+
+def test_ivector_and_tv_cli(world, oracle):
+    d, C, D, R = world["dir"], world["C"], world["D"], 5
+    invvar = (1.0 / world["cov"]).reshape(-1)
+    T = synth.make_T(R, C, D, invvar, seed=91, scale=0.05)
+    lf.write_db(d / "TV.mat", T)
+    ids = [["idA", "utt0", "utt1"], ["idB", "utt2"], ["idC", "utt3", "utt4", "utt0"]]  # utt0 on two lines
+    lf.write_lines(d / "ids.ndx", ids)
+    os.makedirs(d / "iv", exist_ok=True)
+    lf.write_cfg(d / "iv.cfg", **world["common"], targetIdList=str(d / "ids.ndx"), inputWorldFilename="wld",
+                 totalVariabilityNumber=R, totalVariabilityMatrix="TV", nullOrderStatSpeaker="N_iv",
+                 firstOrderStatSpeaker="F_iv", saveVectorFilesPath=str(d / "iv") + "/", vectorFilesExtension=".y")
+    _run("IvExtractor", d / "iv.cfg")
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    N = np.zeros((3, C))
+    F = np.zeros((3, C * D))
+    for row, line in enumerate(ids):
+        for u in line[1:]:
+            X = np.ascontiguousarray(world["utts"][u][_selected(u, world["utts"][u])])
+            n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+            N[row] += n1[0]
+            F[row] += f1[0]
+    assert np.allclose(lf.read_db(d / "N_iv.mat"), N, rtol=1e-4, atol=1e-6)
+    Fc = oracle.tv_subtract_m(N, F, world["mean"].reshape(-1))
+    tett = oracle.tv_tett(T, invvar, C, D)
+    W = oracle.tv_ivectors(N, Fc, T, invvar, tett)
+    for row, line in enumerate(ids):
+        y = lf.read_db(d / "iv" / f"{line[0]}.y")
+        assert y.shape == (1, R) and np.abs(y[0] - W[row]).max() < 1e-4 * np.abs(W).max()
+    # TotalVariability: same lists without ids, statistics recomputed, 2 EM iterations + minDivergence
+    lf.write_lines(d / "tv.ndx", [l[1:] for l in ids])
+    lf.write_cfg(d / "tv.cfg", **world["common"], ndxFilename=str(d / "tv.ndx"), inputWorldFilename="wld",
+                 totalVariabilityNumber=R, totalVariabilityMatrix="TV_out", loadInitTotalVariabilityMatrix="true",
+                 initTotalVariabilityMatrix="TV", nullOrderStatSpeaker="N_tv", firstOrderStatSpeaker="F_tv",
+                 nbIt=2, minDivergence="true", meanEstimate="meanEst")
+    _run("TotalVariability", d / "tv.cfg")
+    Tr, mean = T.copy(), world["mean"].reshape(-1).copy()
+    n_sessions = sum(len(l) - 1 for l in ids)
+    for it in range(2):
+        Fc = oracle.tv_subtract_m(N, F, mean)
+        tett = oracle.tv_tett(Tr, invvar, C, D)
+        _, A, Cmx, Rm, r, mw = oracle.tv_estep(N, Fc, Tr, invvar, tett)
+        Tr = oracle.tv_mstep(A, Cmx, C, D)
+        mean, Tr = oracle.tv_mindiv(Rm, r, mw, mean, Tr, float(n_sessions), C, D)
+    got = lf.read_db(d / "TV_out.mat")
+    assert np.abs(got - Tr).max() < 1e-3 * np.abs(Tr).max()
+    assert np.abs(lf.read_db(d / "meanEst.mat")[0] - mean).max() < 1e-4 * np.abs(mean).max()
+
+
+def test_ivtest_plda_cli(world, oracle):
+    d = world["dir"]
+    F, G, Sigma, models, model_of, segments = synth.make_plda(d=20, rF=6, rG=3, sessions=[2, 2, 1, 1], n_test=7, seed=95)
+    os.makedirs(d / "vec", exist_ok=True)
+    mean = np.linspace(-0.5, 0.5, 20)
+    names_e = [f"e{j}" for j in range(models.shape[1])]
+    for j, n in enumerate(names_e):
+        lf.write_db(d / "vec" / f"{n}.y", (models[:, j] + mean)[None])
+    for j in range(segments.shape[1]):
+        lf.write_db(d / "vec" / f"t{j}.y", (segments[:, j] + mean)[None])
+    lf.write_db(d / "pF.mat", F)
+    lf.write_db(d / "pG.mat", G)
+    lf.write_db(d / "pS.mat", Sigma)
+    lf.write_db(d / "pMean.mat", mean[None])
+    enrol = [["m0", "e0", "e1"], ["m1", "e2", "e3"], ["m2", "e4"], ["m3", "e5"]]
+    lf.write_lines(d / "enrol.ndx", enrol)
+    trials = [[f"t{j}", "m0", "m1", "m2", "m3"] for j in range(7)]
+    lf.write_lines(d / "trials.ndx", trials)
+    lf.write_cfg(d / "it.cfg", **world["common"], ndxFilename=str(d / "trials.ndx"), targetIdList=str(d / "enrol.ndx"),
+                 testVectorFilesPath=str(d / "vec"), loadVectorFilesExtension=".y", scoring="plda",
+                 pldaEigenVoiceNumber=6, pldaEigenChannelNumber=3, iVectSize=20, pldaEigenVoiceMatrix="pF",
+                 pldaEigenChannelMatrix="pG", pldaSigmaMatrix="pS", pldaMeanVec="pMean",
+                 outputFilename=str(d / "it.res"), gender="M")
+    _run("IvTest", d / "it.cfg")
+    ref = oracle.plda_native_scoring(F, G, Sigma, models, model_of, segments)
+    lines = [l.split() for l in open(d / "it.res")]
+    assert len(lines) == 28
+    for l in lines:
+        m, s = int(l[1][1:]), int(l[3][1:])
+        assert abs(float(l[4]) - ref[m, s]) < 1e-5 * max(1.0, abs(ref[m, s]))

@@ -1,0 +1,72 @@
+"""C++ host mirror (host/): builds, file formats and selection rules agree with numpy -- no GPU."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from lia_ral_b200 import synth
+from tests import lia_files as lf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "host", "build")
+
+
+@pytest.fixture(scope="module")
+def built():
+    from lia_ral_b200 import capi
+    capi.build()
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s", "-j", "8"])
+    return BIN
+
+
+def test_programs_exist_and_print_help(built):
+    for p in ("TrainWorld", "ComputeTest", "IvExtractor", "TotalVariability", "IvTest"):
+        out = subprocess.run([os.path.join(built, p), "--help"], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0 and p in out.stdout
+
+
+def test_file_formats_and_selection(built, tmp_path):
+    C, D0 = 8, 10
+    w, mean, cov = synth.make_ubm(C, 9, seed=5)
+    lf.write_raw_gmm(tmp_path / "wld.gmm", w, mean, cov)
+    rng = np.random.default_rng(3)
+    feats = {}
+    for i, n in enumerate((57, 130)):
+        X = rng.standard_normal((n, D0)).astype(np.float32)
+        feats[f"f{i}"] = X
+        (lf.write_spro4 if i == 0 else lf.write_spro4)(tmp_path / f"f{i}.prm", X)
+    lf.write_lines(tmp_path / "f0.lbl", ["0.00 0.10 speech", "0.20 0.2999999 sil", "0.30 0.45 speech", "0.50 9.0 speech"])
+    lf.write_lines(tmp_path / "f1.lbl", ["0.05 0.80 speech"])
+    lf.write_lines(tmp_path / "ndx", [["f0", "spkA", "spkB"], ["f1", "spkA"]])
+    lf.write_cfg(tmp_path / "t.cfg", mixtureFilesPath=str(tmp_path) + "/", loadMixtureFileExtension=".gmm",
+                 loadMixtureFileFormat="RAW", featureFilesPath=str(tmp_path) + "/", loadFeatureFileExtension=".prm",
+                 loadFeatureFileFormat="SPRO4", featureServerMask="0-3,5-9", labelFilesPath=str(tmp_path) + "/",
+                 labelFilesExtension=".lbl", labelSelectedFrames="speech", frameLength=0.01,
+                 inputWorldFilename="wld", ndxFilename=str(tmp_path / "ndx"), tmpPrefix=str(tmp_path / "tmp"))
+    out = subprocess.run([os.path.join(built, "HostSelfTest"), "--config", str(tmp_path / "t.cfg")],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    r = {l.split()[0]: l.split()[1:] for l in out.stdout.strip().splitlines()}
+    assert "FAILED" not in r
+    g = r["gmm"]
+    assert (int(g[0]), int(g[1])) == (C, 9)
+    assert math.isclose(float(g[2]), w.sum(), rel_tol=1e-12) and math.isclose(float(g[3]), mean.sum(), rel_tol=1e-12)
+    assert math.isclose(float(g[4]), cov.sum(), rel_tol=1e-12) and math.isclose(float(g[5]), 1.0, rel_tol=1e-12)
+    assert float(r["xml_roundtrip"][0]) < 1e-14
+    assert [int(v) for v in r["ndx"]] == [2, 5, 4]
+    mask = [0, 1, 2, 3, 5, 6, 7, 8, 9]
+    allx = np.concatenate([feats["f0"][:, mask], feats["f1"][:, mask]])
+    assert (int(r["features"][0]), int(r["features"][1])) == (187, 9)
+    assert math.isclose(float(r["features"][2]), float(allx.astype(np.float64).sum()), rel_tol=1e-9, abs_tol=1e-6)
+    # label -> frames: end inclusive, clipped to the file, 0.2999999/0.01 rounds up to frame 30
+    sel0 = list(range(0, 11)) + list(range(30, 46)) + list(range(50, 57))
+    sel1 = list(range(5, 81))
+    ref = feats["f0"][sel0][:, mask].astype(np.float64).sum() + feats["f1"][sel1][:, mask].astype(np.float64).sum()
+    assert (int(r["selected"][0]), int(r["selected"][1])) == (4, len(sel0) + len(sel1))
+    assert math.isclose(float(r["selected"][2]), float(ref), rel_tol=1e-9, abs_tol=1e-6)
+    assert (int(r["matrix_roundtrip"][0]), int(r["matrix_roundtrip"][1])) == (3, 5) and float(r["matrix_roundtrip"][2]) < 1e-15
+    assert int(r["bagged"][2]) <= 7 and 0 < int(r["bagged"][1]) < len(sel0) + len(sel1)
+    assert math.isclose(float(r["setItParameter"][0]), 0.3) and int(r["setItParameter"][1]) == 30
+    assert r["exception"] == ["1"]
