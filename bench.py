@@ -31,6 +31,16 @@ FLOP_PER_FRAME_EM = 8 * C * D   # 4CD Mahalanobis + 2CD (g x) + 
 FLOP_PER_FRAME_BW = 6 * C * D
 
 
+def measured_traffic(frames_per_launch):
+    """DRAM bytes per launch of the statistics kernel, from the committed `ncu --set full` capture
+    (profiles/r01_tc_traffic.json: bytes per frame measured at 2**21 frames per launch)."""
+    p = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")
+    if not os.path.exists(p):
+        return None
+    j = json.load(open(p))
+    return j["dram_bytes_per_frame"] * frames_per_launch
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -173,7 +183,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from lia_ral_b200 import capi
+    from lia_ral_b200 import capi, dist as lrd
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -199,10 +209,8 @@ def main():
         with torch.cuda.stream(lr_stream):
             stats.zero_()
         g.em_accumulate_dev(feats, 0, T, 1.0, stats.data_ptr())
-        if world > 1:
-            # one all-reduce of {occ, m1, m2, llk, n} per iteration (emAcc.addAccEM analogue)
-            with torch.cuda.stream(lr_stream):
-                dist.all_reduce(stats)
+        # one all-reduce of {occ, m1, m2, llk, n} per iteration (emAcc.addAccEM analogue)
+        lrd.allreduce_stats(stats, lr_stream)
         g.em_update_dev(stats.data_ptr(), floor_, ceil_, cov_signal.data_ptr())
 
     def sync_all():
@@ -290,7 +298,8 @@ def main():
                     "d2h_bytes_per_step": stat_bytes, "steps": args.e2e_steps,
                     "mean_llk_per_frame": e2e_llk},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16"], "traffic": None,
+                         "frac": achieved / pk["bf16"],
+                         "traffic": measured_traffic(frames_per_launch) if args.kernel != 1 else None,
                          "kernel": "statistics pass (LLK recompute + g x / g x^2 accumulation)",
                          "flop_per_frame": FLOP_PER_FRAME_EM, "launches": dom_n,
                          "avg_launch_ms": dom_ms / max(dom_n, 1), "peak_source": pk["src"],

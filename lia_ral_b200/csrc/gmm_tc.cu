@@ -38,7 +38,7 @@ constexpr unsigned kPadIndex = 0xFFFFFFFFu;
 constexpr int kOneCol = 60;                    // columns 60..62 of panel a carry 1.0
 constexpr float kGammaShift = 14.f;            // posteriors are stored as fp16(2^14 g)
 constexpr float kXClamp = 240.f;               // |xh| clamp (xh^2 must stay below fp16 max)
-constexpr int kMaxRunTiles = 32;               // fp32 TMEM partial sums are flushed at least this often
+constexpr int kMaxRunTiles = 128;              // fp32 TMEM partial sums are flushed at least this often (16 k frames)
 constexpr int kTcThreads = 384;                 // warps: 0 bulk-copy producer, 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue
 constexpr int kEpiWarps = 8;
 constexpr int kStageFloats = 32 * 32;             // per-warp flush staging: 32 comps x 32 dims
@@ -413,7 +413,7 @@ struct Smem {
   uint32_t stage[kStages];     // pass 1: 2 x 64 KB
   uint32_t hstage[kHStages];   // pass 2: 4 x 32 KB (same memory)
   uint32_t full[kHStages], empty[kHStages];
-  uint32_t s_full[3], s_empty[2], p_full[3];
+  uint32_t s_full[3], s_empty[2], p_full[3], s_free[3];
   uint32_t f_full, f_empty, w_full;
   uint32_t tmem_slot;
 };
@@ -443,6 +443,7 @@ __device__ __forceinline__ Smem carve(unsigned char *raw) {
   s.f_empty = b + 152;
   s.w_full = b + 160;
   s.tmem_slot = b + 168;
+  for (int i = 0; i < 3; i++) s.s_free[i] = b + 176 + 8 * i;
   return s;
 }
 
@@ -571,11 +572,13 @@ k_tc_lse(int n_slices, int csize, const unsigned char *__restrict__ Wp,
       __syncwarp();
     }
   } else if (warp == 1) {
+    // single issuer: alternating two issuer warps by tile was measured SLOWER here (1.08 -> 1.34 ms
+    // per 1 M frames): this pass is bound by shared-memory operand bandwidth, not by issue latency
     const bool leader = elect_one();
     const uint64_t w_desc0 = make_desc(sm.w, 16, 1024);
     mbar_wait(sm.w_full, 0);
     for (int i = 0; i < n_tiles; i++) {
-      int st = i % kStages, buf = i & 1;
+      const int st = i % kStages, buf = i & 1;
       mbar_wait(sm.full[st], (i / kStages) & 1);
       mbar_wait(sm.s_empty[buf], ((i >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -704,6 +707,7 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
     for (int i = 0; i < 3; i++) {
       mbar_init(sm.s_full[i], 1);
       mbar_init(sm.p_full[i], 4);  // the four warps of one epilogue team
+      mbar_init(sm.s_free[i], 1);  // statistics GEMM done with the S / posterior buffer
     }
     mbar_init(sm.f_full, 1);
     mbar_init(sm.f_empty, kEpiWarps);
@@ -731,7 +735,9 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
     for (int h = 0; h < n_half; h++) {
       const int st = h % kHStages;
       mbar_wait(sm.empty[st], ((h / kHStages) & 1) ^ 1);
-      if (leader) {
+      if (leader && (dbg & 128) && h >= kHStages) {
+        mbar_arrive(sm.full[st]);
+      } else if (leader) {
         mbar_expect_tx(sm.full[st], kHalfBytes);
         const unsigned char *src =
             Xh + (size_t)(t_begin + (h >> 1)) * kTileBytes + (size_t)(h & 1) * kHalfPanel;
@@ -748,25 +754,33 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
       __syncwarp();
     }
   } else if (warp == 1) {
-    // MMA issuer: the whole warp runs the loop converged, one elected lane issues
+    // Likelihood-GEMM issuer.  Two issuer warps (this one and warp 3) keep the tensor pipe fed:
+    // the tcgen05 queue is shallow, so one warp's barrier round trips would drain it
+    // (measured: UMMA time was purely additive to the ~830 clk/half-tile wait latency).
     const bool leader = elect_one();
     const int nq = (dbg & 8) ? 1 : 6;
-    const int n_k2 = (dbg & 4) ? 1 : kHF / 16;
     const uint64_t wlo_desc0 = make_desc(sm.w + 2 * kPanelBytes, 16, 1024);
-    const uint64_t x_desc0 = make_desc(sm.hstage[0], 16, 1024);     // K-major view (likelihood GEMM)
-    const uint64_t b_desc0 = make_desc(sm.hstage[0], kLbo2, 1024);  // MN-major view (statistics GEMM)
+    const uint64_t x_desc0 = make_desc(sm.hstage[0], 16, 1024);  // K-major view of the frames
     mbar_wait(sm.w_full, 0);      // LO weights landed in shared memory
     mbar_wait(sm.s_empty[0], 0);  // epilogue warps copied the HI weights into TMEM
-    for (int h0 = 0; h0 < 2 && h0 < n_half; h0++) {
-      mbar_wait(sm.full[h0], 0);
+    for (int h = 0; h < n_half; h++) {
+      const int st = h % kHStages, buf = h % kNS;
+      mbar_wait(sm.full[st], (h / kHStages) & 1);
+      if (h >= kNS) mbar_wait(sm.s_free[buf], (h / kNS - 1) & 1);  // G2(h - 3) consumed the buffer
       tc_fence_after();
       if (leader) {
-        issue_g1_ts(tmem_base + h0 * kHF, tmem_base + kWCol, wlo_desc0,
-                    desc_add(x_desc0, h0 * kHalfBytes), nq);
-        umma_commit(sm.s_full[h0]);
+        issue_g1_ts(tmem_base + buf * kHF, tmem_base + kWCol, wlo_desc0,
+                    desc_add(x_desc0, st * kHalfBytes), nq);
+        umma_commit(sm.s_full[buf]);
       }
       __syncwarp();
     }
+  } else if (warp == 3) {
+    // Statistics-GEMM issuer: F[c, d] (+)= P[c, t] A[t, d], 4 K-steps of 16 frames per half
+    // tile; P is the fp16 posterior block the epilogue wrote over the S columns.
+    const bool leader = elect_one();
+    const int n_k2 = (dbg & 4) ? 1 : kHF / 16;
+    const uint64_t b_desc0 = make_desc(sm.hstage[0], kLbo2, 1024);  // MN-major view of the frames
     int n_flush = 0;  // flushes requested so far
     TileInfo ti = n_half > 0 ? tinfo[t_begin] : TileInfo{0, 0};
     TileInfo ti_next = ti;
@@ -776,23 +790,12 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
         ti = ti_next;
         if (h + 2 < n_half) ti_next = tinfo[t_begin + (h >> 1) + 1];
       }
-      if (h + 2 < n_half) {
-        const int st2 = (h + 2) % kHStages, buf2 = (h + 2) % kNS;
-        mbar_wait(sm.full[st2], ((h + 2) / kHStages) & 1);
-        tc_fence_after();
-        if (leader) {
-          issue_g1_ts(tmem_base + buf2 * kHF, tmem_base + kWCol, wlo_desc0,
-                      desc_add(x_desc0, st2 * kHalfBytes), nq);
-          umma_commit(sm.s_full[buf2]);
-        }
-        __syncwarp();
-      }
       const bool first = (ti.flags & 1) && !(h & 1), last = (ti.flags & 2) && (h & 1);
+      mbar_wait(sm.full[st], (h / kHStages) & 1);  // (already complete: warp 1 consumed it first)
       mbar_wait(sm.p_full[buf], (h / kNS) & 1);
       if (first && n_flush > 0) mbar_wait(sm.f_empty, (n_flush - 1) & 1);
       tc_fence_after();
       if (leader) {
-        // F[c, d] (+)= P[c, t] A[t, d]: 4 K-steps of 16 frames; P is fp16 packed in the S columns
         uint32_t acc = first ? 0u : 1u;
         const uint64_t bd0 = desc_add(b_desc0, st * kHalfBytes);
 #pragma unroll
@@ -807,6 +810,7 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
           umma_commit_mc(sm.empty[st], cmask);
         else
           umma_commit(sm.empty[st]);
+        umma_commit(sm.s_free[buf]);
         if (last) umma_commit(sm.f_full);
       }
       if (last) n_flush++;
@@ -863,7 +867,7 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
         nl_next = kGammaShift - lse2[(size_t)t_begin * kTile + (size_t)(h + 2) * kHF + et];
       mbar_wait(sm.s_full[buf], (h / kNS) & 1);
       tc_fence_after();
-      {
+      if (!(dbg & 16)) {
         uint32_t r0[32], r1[32];
         tmem_ld32(tmem_base + lane_addr + buf * kHF, r0);
         tmem_ld32(tmem_base + lane_addr + buf * kHF + 32, r1);
