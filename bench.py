@@ -261,6 +261,12 @@ def main():
 
     def e2e_step():
         llk, n, occ, m1, m2 = g2.em_accumulate(Xh_np)
+        if world > 1:  # the same single statistics all-reduce, from / to host buffers
+            packed = torch.from_numpy(np.concatenate([occ, m1.ravel(), m2.ravel(), [llk, n]])).to(dev)
+            dist.all_reduce(packed)
+            h = packed.cpu().numpy()
+            occ, m1, m2 = h[:C], h[C:C + C * D].reshape(C, D), h[C + C * D:C + 2 * C * D].reshape(C, D)
+            llk, n = h[-2], h[-1]
         g2.em_update(occ, m1, m2, floor_, ceil_, gc)
         return llk / n
 
