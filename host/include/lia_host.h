@@ -172,6 +172,20 @@ void mixtureInit(const FeatureServer &fs, const SegCluster &segs, const std::vec
 void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs,
                 const std::vector<double> &globalCov, MixtureGD &world, const TrainCfg &cfg);
 
+// ---- MAP adaptation (TrainTools.cpp:110-147, 445-489, 871-904): the "next" row TrainTarget
+struct MAPCfg {
+  bool mean = false, var = false, weight = false;
+  std::string method;  // MAPOccDep
+  double r[3] = {0, 0, 0};
+  long nbTrainIt = 1;
+  double baggedFrameProbability = 1.0;
+  explicit MAPCfg(const Config &c);
+};
+// client holds the ML (EM) estimate on entry, the MAP estimate on return (computeMAPOccDep)
+void computeMAPOccDep(const MixtureGD &initModel, MixtureGD &client, const MAPCfg &cfg, double frameCount);
+void adaptModel(const Config &c, const FeatureServer &fs, const SegCluster &segs, const MixtureGD &apriori,
+                MixtureGD &client, const MAPCfg &cfg);
+
 // ---- TVAcc (AccumulateTVStat.h): same method names, state in HBM
 class TVAcc {
  public:
@@ -217,5 +231,6 @@ int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:
 int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:70
 int TotalVariability(Config &c);  // LIA_SpkDet/TotalVariability/src/TotalVariability.cpp:71
 int IvTest(Config &c);            // LIA_SpkDet/IvTest/src/IvTest.cpp:73 (scoring = plda, native)
+int TrainTarget(Config &c);       // LIA_SpkDet/TrainTarget/src/TrainTarget.cpp:75 (MAPOccDep)
 
 }  // namespace lia

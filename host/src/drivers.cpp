@@ -62,6 +62,32 @@ int TrainWorld(Config &c) {
   return 0;
 }
 
+// ------------------------------------------------------------------ TrainTarget (MAPOccDep)
+int TrainTarget(Config &c) {
+  try {
+    const std::string label = c.getParam("labelSelectedFrames");
+    MAPCfg mapCfg(c);
+    MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+    XList ids(c.getParam("targetIdList"));  // "id file1 file2 ..." per line (TrainTarget.cpp:100-130)
+    for (auto &line : ids.lines()) {
+      std::vector<std::string> files(line.begin() + 1, line.end());
+      FeatureServer fs(c, files);
+      SegCluster segs = selectedSegments(c, fs, label);
+      if (segs.empty()) {
+        std::cout << "TrainTarget: no selected frame for [" << line[0] << "]" << std::endl;
+        continue;
+      }
+      MixtureGD client = world;  // the client starts from the world model
+      client.id = line[0];
+      adaptModel(c, fs, segs, world, client, mapCfg);
+      client.saveFromConfig(line[0], c);
+    }
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ ComputeTest
 int ComputeTest(Config &c) {
   try {

@@ -157,6 +157,71 @@ void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs
   g.get(world);
 }
 
+// ------------------------------------------------------------------ MAP
+MAPCfg::MAPCfg(const Config &c) {
+  mean = c.getBool("meanAdapt", false);
+  var = c.getBool("varAdapt", false);
+  weight = c.getBool("weightAdapt", false);
+  method = c.getParam("MAPAlgo");
+  if (method != "MAPOccDep") LIA_THROW("mapAlgo[" + method + "] is not implemented by this engine (MAPOccDep only)");
+  if (mean) r[0] = c.getDouble("MAPRegFactorMean");
+  if (var) r[1] = c.getDouble("MAPRegFactorVar");
+  if (weight) r[2] = c.getDouble("MAPRegFactorWeight");
+  nbTrainIt = c.getLong("nbTrainIt", 1);
+  baggedFrameProbability = c.getDouble("baggedFrameProbability", 1.0);
+}
+
+void computeMAPOccDep(const MixtureGD &w, MixtureGD &client, const MAPCfg &cfg, double frameCount) {
+  MixtureGD t = w;  // a priori data
+  const int C = w.C, D = w.D;
+  for (int k = 0; k < C; k++) {
+    const double alpha = client.w[k] * frameCount;  // occupation of the component
+    if (cfg.mean) {
+      const double a = alpha / (alpha + cfg.r[0]);
+      for (int i = 0; i < D; i++)
+        t.mean[(size_t)k * D + i] = (1 - a) * w.mean[(size_t)k * D + i] + a * client.mean[(size_t)k * D + i];
+    }
+    if (cfg.var) {
+      const double a = alpha / (alpha + cfg.r[1]);
+      for (int i = 0; i < D; i++) {
+        const double dm = w.mean[(size_t)k * D + i] - client.mean[(size_t)k * D + i];
+        t.cov[(size_t)k * D + i] = (1 - a) * w.cov[(size_t)k * D + i] + a * client.cov[(size_t)k * D + i] +
+                                   (1 - a) * a * dm * dm;
+      }
+    }
+  }
+  if (cfg.weight) {
+    double sum = 0;
+    for (int k = 0; k < C; k++) {
+      const double alpha = client.w[k] * frameCount, a = alpha / (alpha + cfg.r[2]);
+      t.w[k] = a * client.w[k] + (1 - a) * w.w[k];
+      sum += t.w[k];
+    }
+    for (int k = 0; k < C; k++) t.w[k] /= sum;
+  }
+  t.computeAll();
+  t.id = client.id;
+  client = t;
+}
+
+void adaptModel(const Config &c, const FeatureServer &fs, const SegCluster &segs, const MixtureGD &apriori,
+                MixtureGD &client, const MAPCfg &cfg) {
+  const long minLen = c.getLong("baggedMinimalLength", 3), maxLen = c.getLong("baggedMaximalLength", 7);
+  Gmm g(client);
+  EmAcc acc;
+  for (long it = 0; it < cfg.nbTrainIt; it++) {
+    SegCluster bagged = cfg.baggedFrameProbability >= 1.0 ? segs : baggedSegments(segs, cfg.baggedFrameProbability, minLen, maxLen);
+    acc.reset(client.C, client.D);
+    srand((unsigned)it);
+    accumulateStatEM(fs, g, bagged, acc);
+    // clientMixture = emAcc.getEM() on the device (no variance control), then MAP on the host (O(C D))
+    LIA_CHECK(lr_gmm_em_update(g.h(), acc.occ.data(), acc.m1.data(), acc.m2.data(), 0.0, 0.0, nullptr));
+    g.get(client);
+    computeMAPOccDep(apriori, client, cfg, acc.n);
+    g.set(client);
+  }
+}
+
 // ------------------------------------------------------------------ TVAcc
 TVAcc::TVAcc(const std::string &ndxFile, const Config &c) : cfg_(c) {
   XList ndx(ndxFile);

@@ -113,3 +113,21 @@ def plda_scores(F, G, Sigma, models, model_of, segments):
         b = 0.5 * np.einsum("it,ij,jt->t", ps, KL1 - K1, ps)
         out[i] = ps.T @ (KL1 @ m) + a + b
     return out
+
+
+def map_occ_dep(w0, mean0, cov0, w_ml, mean_ml, cov_ml, frame_count, r_mean=None, r_var=None, r_weight=None):
+    """computeMAPOccDep (TrainTools.cpp:445-489): occupation-dependent MAP of the ML estimate
+    (w_ml, mean_ml, cov_ml) towards the a-priori model; r_* = None disables that adaptation."""
+    alpha = w_ml * frame_count
+    w, mean, cov = w0.copy(), mean0.copy(), cov0.copy()
+    if r_mean is not None:
+        a = (alpha / (alpha + r_mean))[:, None]
+        mean = (1 - a) * mean0 + a * mean_ml
+    if r_var is not None:
+        a = (alpha / (alpha + r_var))[:, None]
+        cov = (1 - a) * cov0 + a * cov_ml + (1 - a) * a * (mean0 - mean_ml) ** 2
+    if r_weight is not None:
+        a = alpha / (alpha + r_weight)
+        w = a * w_ml + (1 - a) * w0
+        w = w / w.sum()
+    return w, mean, cov

@@ -195,3 +195,28 @@ def test_ivtest_plda_cli(world, oracle):
     for l in lines:
         m, s = int(l[1][1:]), int(l[3][1:])
         assert abs(float(l[4]) - ref[m, s]) < 1e-5 * max(1.0, abs(ref[m, s]))
+
+
+def test_train_target_cli(world, oracle):
+    """TrainTarget with MAPOccDep (mean + weight adaptation, 2 iterations) against the oracle's EM
+    statistics + the numpy restatement of computeMAPOccDep (TrainTools.cpp:445-489, 871-904)."""
+    from oracle import np_oracle
+    d = world["dir"]
+    lf.write_lines(d / "target.ndx", [["clientA", "utt1", "utt2"], ["clientB", "utt4"]])
+    lf.write_cfg(d / "tt.cfg", **world["common"], targetIdList=str(d / "target.ndx"), inputWorldFilename="wld",
+                 MAPAlgo="MAPOccDep", meanAdapt="true", weightAdapt="true", MAPRegFactorMean=14.0,
+                 MAPRegFactorWeight=10.0, nbTrainIt=2, baggedFrameProbability=1.0)
+    _run("TrainTarget", d / "tt.cfg")
+    for cid, files in (("clientA", ["utt1", "utt2"]), ("clientB", ["utt4"])):
+        X = np.ascontiguousarray(np.concatenate([world["utts"][u][_selected(u, world["utts"][u])] for u in files]))
+        w0, m0, c0 = world["w"], world["mean"], world["cov"]
+        w, m, c = w0, m0, c0
+        for it in range(2):
+            g = oracle.gmm(w, m, c)
+            _, n, occ, m1, m2 = oracle.em_accumulate(g, X)
+            w_ml, m_ml, c_ml = oracle.em_get(g, occ, m1, m2)
+            w, m, c = np_oracle.map_occ_dep(w0, m0, c0, w_ml, m_ml, c_ml, n, r_mean=14.0, r_weight=10.0)
+        gw, gm, gc = lf.read_raw_gmm(d / f"{cid}.gmm")
+        assert np.allclose(gw, w, rtol=1e-3, atol=1e-7)
+        assert np.abs(gm - m).max() < 1e-4 * np.abs(m).max()
+        assert np.allclose(gc, c, rtol=1e-9)
