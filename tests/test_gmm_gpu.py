@@ -299,3 +299,40 @@ def test_full_size_properties(capi, kern):
     segs = [(i * 3000, 3000, i) for i in range(100)]
     N, F = g.bwstats(X, segs, 100)
     assert np.allclose(N.sum(1), 3000.0, rtol=1e-6)
+
+
+def test_tc_range_guard_and_outliers(capi, oracle):
+    """Models whose normalised weights leave the fp16 range are refused by the tcgen05 path (and
+    served by the SIMT path in auto mode); absurd outlier frames give finite results."""
+    C, D, T = 256, 20, 640
+    w, mean, cov = synth.make_ubm(C, D, seed=7)
+    X = synth.make_frames(w, mean, cov, T, seed=8)
+    g_ok = capi.GMM(w, mean, cov)
+    bad_cov = cov.copy()
+    bad_mean = mean.copy()
+    bad_cov[3] = 1e-7          # a needle component far from the global mean: |K_c| >> 30000
+    bad_mean[3] = 40.0
+    g_bad = capi.GMM(w, bad_mean, bad_cov)
+    o_bad = oracle.gmm(w, bad_mean, bad_cov)
+    capi.set_gmm_kernel(2)
+    try:
+        g_ok.llk(X, -1e9, 1e9)                      # in range: served
+        with pytest.raises(capi.LrError):
+            g_bad.llk(X, -1e9, 1e9)                 # out of range: loud, never silently wrong
+    finally:
+        capi.set_gmm_kernel(0)
+    got = g_bad.llk(X, -1e9, 1e9)                   # auto -> SIMT
+    ref = oracle.llk_all(o_bad, X, -1e9, 1e9)
+    assert np.abs(got - ref).max() < 1e-4 * np.abs(ref).max()
+    # outliers: one frame 1e4 sigma away, one NaN-free huge negative; statistics stay finite
+    Xo = X.copy()
+    Xo[5] = 1e4
+    Xo[6] = -3e3
+    for k in (1, 2):
+        capi.set_gmm_kernel(k)
+        try:
+            llk, n, occ, m1, m2 = g_ok.em_accumulate(Xo)
+        finally:
+            capi.set_gmm_kernel(0)
+        assert np.isfinite(llk) and np.isfinite(occ).all() and np.isfinite(m1).all() and np.isfinite(m2).all()
+        assert abs(occ.sum() - T) < 1e-3 * T
