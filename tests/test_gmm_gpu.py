@@ -336,3 +336,48 @@ def test_tc_range_guard_and_outliers(capi, oracle):
             capi.set_gmm_kernel(0)
         assert np.isfinite(llk) and np.isfinite(occ).all() and np.isfinite(m1).all() and np.isfinite(m2).all()
         assert abs(occ.sum() - T) < 1e-3 * T
+
+
+@pytest.mark.parametrize("C,D", [(1, 1), (3, 2), (257, 60), (128, 63)])
+def test_shape_edges(capi, oracle, C, D):
+    """degenerate / boundary shapes: single component, single dimension, C just above a slice,
+    the largest supported vectSize; T = 1 and T not a multiple of any tile."""
+    w, mean, cov = synth.make_ubm(C, D, seed=17)
+    for T in (1, 131):
+        X = synth.make_frames(w, mean, cov * 3.0, T, seed=18)
+        g, o = capi.GMM(w, mean, cov), oracle.gmm(w, mean, cov)
+        ref = oracle.llk_all(o, X, -1e9, 1e9)
+        got = g.llk(X, -1e9, 1e9)
+        assert np.abs(got - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+        llk_r, n_r, occ_r, m1_r, m2_r = oracle.em_accumulate(o, X)
+        llk, n, occ, m1, m2 = g.em_accumulate(X)
+        assert n == T and abs(llk - llk_r) < 1e-4 * max(1.0, abs(llk_r))
+        assert np.allclose(occ, occ_r, rtol=1e-4, atol=1e-4) and np.allclose(m2, m2_r, rtol=1e-4, atol=1e-4 * np.abs(m2_r).max())
+        K = min(3, C)
+        _, idx_r, _, _, _ = oracle.llk_determine_top(o, X, K)
+        _, idx, _, _, _ = g.llk_topk(X, K)
+        assert np.array_equal(idx, idx_r)
+
+
+def test_block_boundaries(capi):
+    """frame counts straddling the staging block (2^18) and device block (2^21) sizes: the totals
+    must not depend on where the blocks are cut."""
+    import torch
+    w, mean, cov = synth.make_ubm(256, 20, seed=19)
+    g = capi.GMM(w, mean, cov)
+    T = (1 << 21) + (1 << 18) + 777
+    xd = torch.randn(T, 20, device="cuda") * 2.0
+    X = xd.cpu().numpy()
+    feats = capi.Feats(device_ptr=xd.data_ptr(), T=T, ldx=20, D=20)
+    stats = torch.zeros(g.em_stats_len(), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    g.em_accumulate_dev(feats, 0, T, 1.0, stats.data_ptr())
+    capi.synchronize()
+    s = stats.cpu().numpy()
+    llk, n, occ, m1, m2 = g.em_accumulate(X)          # host path, different block cuts
+    assert n == T == s[-1] and abs(occ.sum() - T) < 1e-6 * T
+    assert abs(s[-2] - llk) < 1e-9 * abs(llk)
+    # fp32 TMEM partial sums run over up to 128 tiles (16 k frames) before the fp64 flush: different
+    # block cuts regroup them, so agreement is ~3e-6, not 1e-9 (contract: 1e-4)
+    assert np.allclose(s[:256], occ, rtol=2e-5, atol=1e-5)
+    assert np.allclose(s[256:256 + 256 * 20], m1.ravel(), rtol=2e-5, atol=2e-5 * np.abs(m1).max())
