@@ -71,9 +71,6 @@ lr_status gmm_pass_acc(lr_gmm *g, const FrameList &fl, const float *d_lse2,
 bool tc_supported(const lr_gmm *g);
 lr_status tc_derive(lr_gmm *g);
 lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_llk_sum);
-lr_status tc_pass_acc(lr_gmm *g, const FrameList &fl, const float *d_lse2,
-                      const LrChunk *d_chunks, int n_chunks, double fw, double *out_N,
-                      double *out_F, double *out_S2);
 // likelihood + statistics over a tile-padded frame list (chunks tile aligned, host copy)
 lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk> &chunks,
                        double fw, double *out_N, double *out_F, double *out_S2,

@@ -165,16 +165,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
@@ -239,9 +229,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
 }
 
 struct TileInfo {
-  int row;    // output row: statistics row, or slab row when bit 2 is set
-  int flags;  // bit 0: first tile of a run (accumulator starts from zero); bit 1: flush after;
-              // bit 2: the run belongs to a row shared between groups -> flush into the slab
+  int row;    // statistics row the run is flushed into
+  int flags;  // bit 0: first tile of a run (accumulator starts from zero); bit 1: flush after
 };
 
 // split v into fp16 hi + lo
@@ -680,7 +669,6 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
          const TileInfo *__restrict__ tinfo, const float *__restrict__ lse2,
          const double *__restrict__ g, const double *__restrict__ s, double fw,
          double *__restrict__ out_N, double *__restrict__ out_F, double *__restrict__ out_S2,
-         double *__restrict__ slab_N, double *__restrict__ slab_F, double *__restrict__ slab_S2,
          int dbg) {
   constexpr int N2 = EM ? 256 : 128;
   // B of the statistics GEMM: MN-major, 64-wide chunks = half panels
@@ -914,8 +902,7 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
         n_flush++;
         tc_fence_after();
         const int comp0 = slice * kSlice + q * 32;
-        const bool slab = (ti.flags & 4) != 0;
-        double *oN = slab ? slab_N : out_N, *oF = slab ? slab_F : out_F, *oS = slab ? slab_S2 : out_S2;
+        double *oN = out_N, *oF = out_F, *oS = out_S2;
         const double sc = 1.0 / 16384.0;  // undo the 2^14 posterior scale
         constexpr int kLoCol = EM ? 128 : 64;
         const double n = (double)__uint_as_float(tmem_ld1(tmem_f + lane_addr + kOneCol)) * sc;
@@ -986,17 +973,6 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
   __syncthreads();
   if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal / write to it
   if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
-// out[row(v)] += slab[v] for the virtual rows that share a real row
-__global__ void k_tc_reduce_slabs(int n_slab, const int *__restrict__ slab_row, size_t per_row,
-                                  const double *__restrict__ slab, double *__restrict__ out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= per_row) return;
-  for (int v = 0; v < n_slab; v++) {
-    double x = slab[(size_t)v * per_row + i];
-    if (x != 0.0) atomicAdd(&out[(size_t)slab_row[v] * per_row + i], x);
-  }
 }
 
 }  // namespace
@@ -1183,11 +1159,6 @@ lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_l
   return LR_OK;
 }
 
-lr_status tc_pass_acc(lr_gmm *, const FrameList &, const float *, const LrChunk *, int, double,
-                      double *, double *, double *) {
-  return fail(LR_ERR_ARG, "tc_pass_acc: the tensor-core statistics pass is driven by tc_run_stats");
-}
-
 // Likelihood + statistics over a frame list whose row runs are padded to whole tiles
 // (build_plan(..., pad = true)): chunk.pos % 128 == 0, padding entries carry kPadIndex.
 lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk> &chunks,
@@ -1208,8 +1179,8 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
   split_groups(n_tiles, groups, cuts);
 
   // per-tile run info.  A run = consecutive tiles of one row inside one group, at most
-  // kMaxRunTiles long.  A row touched by more than one group accumulates through slab rows
-  // (exclusive, non-atomic fp64 read-modify-write everywhere; slabs are reduced afterwards).
+  // kMaxRunTiles long; runs are flushed with fp64 atomics (RED), so a row may be shared between
+  // groups (the EM case: one row, every group).
   std::vector<int> tile_row(n_tiles, -1);
   for (const LrChunk &c : chunks) {
     if (c.pos % kTile) return fail(LR_ERR_ARG, "tc_run_stats: chunk not tile aligned");
@@ -1219,47 +1190,19 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
   for (int gi = 0; gi < groups; gi++)
     for (int t = cuts[gi]; t < cuts[gi + 1]; t++) tile_group[t] = gi;
   std::vector<TileInfo> tinfo(n_tiles);
-  std::vector<int> slab_row;  // slab v -> real row
   for (int t = 0; t < n_tiles;) {
-    const int row = tile_row[t];
+    const int row = tile_row[t], gi = tile_group[t];
     int t2 = t;
-    while (t2 < n_tiles && tile_row[t2] == row) t2++;
-    const bool split = false;  // flushes are fp64 atomics (RED): rows may be shared between groups
-    for (int u = t; u < t2;) {
-      const int gi = tile_group[u];
-      int u2 = u;
-      while (u2 < t2 && tile_group[u2] == gi) u2++;
-      int target = row, slabbit = 0;
-      if (row < 0) {
-        target = 0;  // tiles outside every chunk (cannot happen with build_plan): discard
-        slabbit = 8;
-      } else if (split) {
-        target = (int)slab_row.size();
-        slab_row.push_back(row);
-        slabbit = 4;
-      }
-      for (int k = u; k < u2; k++) {
-        const int in_run = (k - u) % kMaxRunTiles;
-        int flags = slabbit;
-        if (in_run == 0) flags |= 1;
-        if (in_run == kMaxRunTiles - 1 || k == u2 - 1) flags |= 2;
-        tinfo[k] = {target, flags};
-      }
-      u = u2;
+    while (t2 < n_tiles && tile_row[t2] == row && tile_group[t2] == gi) t2++;
+    if (row < 0) return fail(LR_ERR_ARG, "tc_run_stats: tile %d is covered by no chunk", t);
+    for (int k = t; k < t2; k++) {
+      const int in_run = (k - t) % kMaxRunTiles;
+      int flags = 0;
+      if (in_run == 0) flags |= 1;
+      if (in_run == kMaxRunTiles - 1 || k == t2 - 1) flags |= 2;
+      tinfo[k] = {row, flags};
     }
     t = t2;
-  }
-  const int n_slab = (int)slab_row.size();
-  const size_t C = g->C, cd = (size_t)g->C * g->D;
-  double *slabN = nullptr, *slabF = nullptr, *slabS = nullptr;
-  if (n_slab) {
-    const size_t per = C + 2 * cd;
-    double *slab = (double *)scratch_get(kSlotS, (size_t)n_slab * per * sizeof(double));
-    if (!slab) return LR_ERR_CUDA;
-    LR_CUDA(cudaMemsetAsync(slab, 0, (size_t)n_slab * per * sizeof(double), e.stream));
-    slabN = slab;
-    slabF = slab + (size_t)n_slab * C;
-    slabS = slabF + (size_t)n_slab * cd;
   }
 
   float *d_lse = (float *)scratch_get(kSlotLse, (size_t)P_pad * sizeof(float));
@@ -1279,33 +1222,13 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
       rc = tc_launch(k_tc_acc<true>, n_slices * groups, csize, g->C, g->D, n_slices, csize,
                      (const unsigned char *)st->d_W, (const unsigned char *)Xh, (const int *)d_cuts,
                      (const TileInfo *)d_tinfo, (const float *)d_lse, (const double *)g->d_g,
-                     (const double *)g->d_s, fw, out_N, out_F, out_S2, slabN, slabF, slabS,
-                     e.tc_debug);
+                     (const double *)g->d_s, fw, out_N, out_F, out_S2, e.tc_debug);
     else
       rc = tc_launch(k_tc_acc<false>, n_slices * groups, csize, g->C, g->D, n_slices, csize,
                      (const unsigned char *)st->d_W, (const unsigned char *)Xh, (const int *)d_cuts,
                      (const TileInfo *)d_tinfo, (const float *)d_lse, (const double *)g->d_g,
-                     (const double *)g->d_s, fw, out_N, out_F, (double *)nullptr, slabN, slabF,
-                     (double *)nullptr, e.tc_debug);
+                     (const double *)g->d_s, fw, out_N, out_F, (double *)nullptr, e.tc_debug);
     if (rc != LR_OK) return rc;
-  }
-  if (n_slab) {
-    int *d_map = (int *)scratch_get(kSlotIdx, (size_t)n_slab * sizeof(int));
-    if (!d_map) return LR_ERR_CUDA;
-    LR_CUDA(cudaMemcpyAsync(d_map, slab_row.data(), (size_t)n_slab * sizeof(int),
-                            cudaMemcpyHostToDevice, e.stream));
-    if (out_N) {
-      k_tc_reduce_slabs<<<ceil_div((long)C, 256), 256, 0, e.stream>>>(n_slab, d_map, C, slabN, out_N);
-      LR_CHECK_LAUNCH();
-    }
-    if (out_F) {
-      k_tc_reduce_slabs<<<ceil_div((long)cd, 256), 256, 0, e.stream>>>(n_slab, d_map, cd, slabF, out_F);
-      LR_CHECK_LAUNCH();
-    }
-    if (out_S2) {
-      k_tc_reduce_slabs<<<ceil_div((long)cd, 256), 256, 0, e.stream>>>(n_slab, d_map, cd, slabS, out_S2);
-      LR_CHECK_LAUNCH();
-    }
   }
   return LR_OK;
 }
