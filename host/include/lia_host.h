@@ -207,6 +207,15 @@ class TVAcc {
   void updateTestimate();
   void minDivergence();
   void orthonormalizeT();
+  // approximate i-vector modes (IvExtractor.cpp:151-363, TotalVariability.cpp:181-241)
+  void normTMatrix();                                        // :1600
+  void normStatistics();                                     // :1215
+  Matrix getWeightedCov(const std::vector<double> &weight);  // :2826 (W is returned)
+  static void computeEigenProblem(const Matrix &EP, Matrix &eigenVect, long rank);  // :2988
+  Matrix approximateTcTc(const Matrix &Q);                   // :3106 (D is returned)
+  void estimateWUbmWeight(const Matrix &W);                  // :2337
+  void estimateWEigenDecomposition(const Matrix &D, const Matrix &Q);  // :2556
+  const MixtureGD &world() const { return world_; }
   void saveWbyFile(const Config &c);  // :2799-2822
   void loadMeanEstimate(const std::vector<double> &mean);  // :671
   void reloadStats();      // resend the host copy of N / F_X (TotalVariability.cpp:149-153)
@@ -228,7 +237,9 @@ class TVAcc {
 // ---- drivers: int Foo(Config&) like the reference programs
 int TrainWorld(Config &c);        // LIA_SpkDet/TrainWorld/src/TrainWorld.cpp:101
 int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:90
-int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:70
+int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:70 (mode classic)
+int IvExtractorUbmWeigth(Config &c);          // IvExtractor.cpp:151 (mode ubmWeight; the reference's spelling)
+int IvExtractorEigenDecomposition(Config &c); // IvExtractor.cpp:254 (mode eigenDecomposition)
 int TotalVariability(Config &c);  // LIA_SpkDet/TotalVariability/src/TotalVariability.cpp:71
 int IvTest(Config &c);            // LIA_SpkDet/IvTest/src/IvTest.cpp:73 (scoring = plda, native)
 int TrainTarget(Config &c);       // LIA_SpkDet/TrainTarget/src/TrainTarget.cpp:75 (MAPOccDep)

@@ -174,6 +174,83 @@ int IvExtractor(Config &c) {
   return 0;
 }
 
+// ------------------------------------------------------------------ IvExtractor (approximate modes)
+namespace {
+// shared head / tail of IvExtractorUbmWeigth and IvExtractorEigenDecomposition
+// (IvExtractor.cpp:151-252, 254-363)
+std::vector<std::vector<std::string>> ivFileList(const Config &c) {
+  XList ids(c.getParam("targetIdList"));
+  std::vector<std::vector<std::string>> files;
+  for (auto &l : ids.lines()) files.push_back(std::vector<std::string>(l.begin() + 1, l.end()));
+  return files;
+}
+void ivStatsAndMean(TVAcc &tv, const Config &c) {
+  if (c.getBool("loadAccs", false)) {
+    tv.loadN(c);
+    tv.loadF_X(c);
+  } else {
+    tv.computeAndAccumulateTVStat(c);
+    tv.saveAccs(c);
+  }
+  if (c.getBool("minDivergence", false)) {
+    Matrix m;
+    m.load(c.getString("matrixFilesPath", "") + c.getParam("meanEstimate") + c.getString("loadMatrixFilesExtension", ""),
+           c.getString("loadMatrixFormat", "DB"));
+    tv.loadMeanEstimate(m.data);
+  }
+  tv.normStatistics();  // subtract the mean and normalise by the UBM co-variance (:239, :350)
+}
+std::string approxName(const Config &c, const char *suffix) {
+  return c.getString("matrixFilesPath", "") + c.getParam("totalVariabilityMatrix") + suffix +
+         c.getString("loadMatrixFilesExtension", "");
+}
+}  // namespace
+
+int IvExtractorUbmWeigth(Config &c) {
+  try {
+    TVAcc tv(ivFileList(c), c);
+    Matrix W;
+    if (c.getBool("loadUbmWeightParam", false)) {
+      tv.loadT(c.getParam("totalVariabilityMatrix") + "_norm", c);
+      W.load(approxName(c, "_weightedCov"), c.getString("loadMatrixFormat", "DB"));
+    } else {
+      tv.loadT(c.getParam("totalVariabilityMatrix"), c);
+      tv.normTMatrix();
+      W = tv.getWeightedCov(tv.world().w);
+    }
+    ivStatsAndMean(tv, c);
+    tv.estimateWUbmWeight(W);
+    tv.saveWbyFile(c);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+int IvExtractorEigenDecomposition(Config &c) {
+  try {
+    TVAcc tv(ivFileList(c), c);
+    Matrix Q, D;
+    if (c.getBool("loadEigenDecompositionParam", false)) {
+      tv.loadT(c.getParam("totalVariabilityMatrix") + "_norm", c);
+      D.load(approxName(c, "_EigDec_D"), c.getString("loadMatrixFormat", "DB"));
+      Q.load(approxName(c, "_EigDec_Q"), c.getString("loadMatrixFormat", "DB"));
+    } else {
+      tv.loadT(c.getParam("totalVariabilityMatrix"), c);
+      tv.normTMatrix();
+      Matrix W = tv.getWeightedCov(tv.world().w);
+      TVAcc::computeEigenProblem(W, Q, tv.rank());
+      D = tv.approximateTcTc(Q);
+    }
+    ivStatsAndMean(tv, c);
+    tv.estimateWEigenDecomposition(D, Q);
+    tv.saveWbyFile(c);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ TotalVariability
 int TotalVariability(Config &c) {
   try {
@@ -210,6 +287,27 @@ int TotalVariability(Config &c) {
       Matrix m = tv.getUbmMeans();
       m.save(c.getString("matrixFilesPath", "") + c.getParam("meanEstimate") + c.getString("saveMatrixFilesExtension", ""),
              c.getString("saveMatrixFormat", "DB"));
+    }
+    // parameters of the approximate i-vector extraction modes (TotalVariability.cpp:181-241)
+    if (c.existsParam("approximationMode")) {
+      const std::string mode = c.getParam("approximationMode");
+      const std::string fmt = c.getString("saveMatrixFormat", "DB");
+      if (mode == "ubmWeight" || mode == "eigenDecomposition") {
+        tv.normTMatrix();
+        tv.saveT(c.getParam("totalVariabilityMatrix") + "_norm", c);
+        Matrix W = tv.getWeightedCov(tv.world().w);
+        if (mode == "ubmWeight") {
+          W.save(approxName(c, "_weightedCov"), fmt);
+        } else {
+          Matrix Q;
+          TVAcc::computeEigenProblem(W, Q, tv.rank());
+          Matrix D = tv.approximateTcTc(Q);
+          D.save(approxName(c, "_EigDec_D"), fmt);
+          Q.save(approxName(c, "_EigDec_Q"), fmt);
+        }
+      } else {
+        std::cout << "\t(TotalVariability) This approximation mode does not exists" << std::endl;
+      }
     }
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;

@@ -360,6 +360,36 @@ void TVAcc::minDivergence() {
 }
 void TVAcc::orthonormalizeT() { LIA_CHECK(lr_tv_orthonormalize_t(tv_)); }
 
+void TVAcc::normTMatrix() { LIA_CHECK(lr_tv_norm_t(tv_)); }
+void TVAcc::normStatistics() { LIA_CHECK(lr_tv_norm_statistics(tv_)); }
+Matrix TVAcc::getWeightedCov(const std::vector<double> &weight) {
+  if (weight.size() != (size_t)world_.C) LIA_THROW("getWeightedCov: weight vector size != distribCount");
+  Matrix W(R_, R_);
+  LIA_CHECK(lr_tv_weighted_cov(tv_, weight.data(), W.data.data()));
+  return W;
+}
+void TVAcc::computeEigenProblem(const Matrix &EP, Matrix &eigenVect, long rank) {
+  if (EP.rows != EP.cols) LIA_THROW("computeEigenProblem: matrix is not square");
+  eigenVect = Matrix(EP.rows, (size_t)rank);
+  std::vector<double> val((size_t)rank);
+  LIA_CHECK(lr_eigen_problem((int)EP.rows, EP.data.data(), (int)rank, eigenVect.data.data(), val.data()));
+}
+Matrix TVAcc::approximateTcTc(const Matrix &Q) {
+  if (Q.rows != (size_t)R_ || Q.cols != (size_t)R_) LIA_THROW("approximateTcTc: Q must be rankT x rankT");
+  Matrix D(world_.C, R_);
+  LIA_CHECK(lr_tv_approximate_tctc(tv_, Q.data.data(), D.data.data()));
+  return D;
+}
+void TVAcc::estimateWUbmWeight(const Matrix &W) {
+  if (W.rows != (size_t)R_ || W.cols != (size_t)R_) LIA_THROW("estimateWUbmWeight: W must be rankT x rankT");
+  LIA_CHECK(lr_tv_estimate_w_ubm_weight(tv_, W.data.data()));
+}
+void TVAcc::estimateWEigenDecomposition(const Matrix &D, const Matrix &Q) {
+  if (D.rows != (size_t)world_.C || D.cols != (size_t)R_ || Q.rows != (size_t)R_ || Q.cols != (size_t)R_)
+    LIA_THROW("estimateWEigenDecomposition: D must be distribCount x rankT, Q rankT x rankT");
+  LIA_CHECK(lr_tv_estimate_w_eigen_decomposition(tv_, D.data.data(), Q.data.data()));
+}
+
 void TVAcc::loadMeanEstimate(const std::vector<double> &mean) {
   if (mean.size() != (size_t)world_.C * world_.D) LIA_THROW("Incorrect dimension of meanEstimate vector");
   LIA_CHECK(lr_tv_set_mean(tv_, mean.data()));

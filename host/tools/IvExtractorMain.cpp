@@ -13,7 +13,13 @@ int main(int argc, char **argv) {
       return 0;
     }
     if (config.existsParam("device")) lr_init((int)config.getLong("device"));
-    return lia::IvExtractor(config);
+    // IvExtractorMain.cpp:99-111: classic (default) | ubmWeight | eigenDecomposition
+    const std::string mode = config.existsParam("mode") ? config.getParam("mode") : "classic";
+    if (mode == "classic") return lia::IvExtractor(config);
+    if (mode == "ubmWeight") return lia::IvExtractorUbmWeigth(config);
+    if (mode == "eigenDecomposition") return lia::IvExtractorEigenDecomposition(config);
+    std::cout << "Wrong mode, should be classic | ubmWeight | eigenDecomposition" << std::endl;
+    return 0;
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }

@@ -188,8 +188,30 @@ lr_status lr_tv_estimate_a_and_c(lr_tv *tv); /* estimateAandC :1691-1795 */
 lr_status lr_tv_update_t(lr_tv *tv);       /* updateTestimate :974-1005 */
 lr_status lr_tv_min_divergence(lr_tv *tv, double n_sessions); /* minDivergence :2056-2099 */
 lr_status lr_tv_orthonormalize_t(lr_tv *tv); /* orthonormalizeT :1548-1596 */
+/* ---- approximate i-vector extraction (IvExtractor --mode ubmWeight | eigenDecomposition,
+ * IvExtractor.cpp:151-363; TotalVariability approximationMode outputs, TotalVariability.cpp:181-241) */
+lr_status lr_tv_norm_t(lr_tv *tv);          /* normTMatrix :1600-1609: T[j,i] *= sqrt(invvar[i]) */
+lr_status lr_tv_norm_statistics(lr_tv *tv); /* normStatistics :1215-1242: F = (F - mean N) sqrt(invvar) */
+/* getWeightedCov :2826-2855: W[R x R] = sum_c weight[c] T_c T_c^T (T as currently held) */
+lr_status lr_tv_weighted_cov(lr_tv *tv, const double *weight, double *W);
+/* computeEigenProblem :2999-3052 (LAPACKE_dgeev on the symmetric W): eigenvalues sorted
+ * descending, eigvec[n x rank] row-major with eigenvector j in COLUMN j, unit norm.  The reference
+ * leaves the sign to LAPACK; here the component of largest magnitude is positive. */
+lr_status lr_eigen_problem(int n, const double *EP, int rank, double *eigvec, double *eigval);
+/* approximateTcTc :3106-3136: Dm[C x R], Dm[c,i] = diag(Q^T T_c T_c^T Q)_i.  Dm is overwritten
+ * (the reference accumulates into a matrix its caller zeroed). */
+lr_status lr_tv_approximate_tctc(lr_tv *tv, const double *Q, double *Dm);
+/* estimateWUbmWeight :2337-2396: W_s = (I + (sum_c N[s,c]) Wcov)^-1 T F_s on the normalised T / F.
+ * _W is overwritten. */
+lr_status lr_tv_estimate_w_ubm_weight(lr_tv *tv, const double *Wcov);
+/* estimateWEigenDecomposition :2556-2609: W_s += Q diag(1 / (1 + N_s Dm)) Q^T T F_s.  Like the
+ * reference this ACCUMULATES into _W (zero after lr_tv_create). */
+lr_status lr_tv_estimate_w_eigen_decomposition(lr_tv *tv, const double *Dm, const double *Q);
+
 /* multi-GPU: device pointer + length (doubles) of the contiguous E-step accumulator block
- * [A | Cmx | Rm | r | sumW] that one NCCL all-reduce per EM iteration exchanges */
+ * [A | Cmx | Rm | r | sumW] that one NCCL all-reduce per EM iteration exchanges.  Inside the
+ * block A is held as C packed lower triangles of R (R + 1) / 2 doubles (A_c is symmetric);
+ * lr_tv_get_acc expands it to the reference's full [C x R*R]. */
 double *lr_tv_dev_acc(lr_tv *tv);
 size_t lr_tv_acc_len(const lr_tv *tv);
 /* after the all-reduce: meanW = sumW / n_speakers_total */

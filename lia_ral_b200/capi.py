@@ -417,6 +417,37 @@ class TV:
     def orthonormalize_t(self):
         _check(lib().lr_tv_orthonormalize_t(self.h))
 
+    # ---- approximate i-vector modes (IvExtractor.cpp:151-363)
+    def norm_t(self):
+        _check(lib().lr_tv_norm_t(self.h))
+
+    def norm_statistics(self):
+        _check(lib().lr_tv_norm_statistics(self.h))
+
+    def weighted_cov(self, weight):
+        w = _f64(weight).reshape(-1)
+        assert w.size == self.C
+        W = np.empty((self.R, self.R))
+        _check(lib().lr_tv_weighted_cov(self.h, _d(w), _d(W)))
+        return W
+
+    def approximate_tctc(self, Q):
+        Q = _f64(Q)
+        assert Q.shape == (self.R, self.R)
+        Dm = np.empty((self.C, self.R))
+        _check(lib().lr_tv_approximate_tctc(self.h, _d(Q), _d(Dm)))
+        return Dm
+
+    def estimate_w_ubm_weight(self, Wcov):
+        Wcov = _f64(Wcov)
+        assert Wcov.shape == (self.R, self.R)
+        _check(lib().lr_tv_estimate_w_ubm_weight(self.h, _d(Wcov)))
+
+    def estimate_w_eigen_decomposition(self, Dm, Q):
+        Dm, Q = _f64(Dm), _f64(Q)
+        assert Dm.shape == (self.C, self.R) and Q.shape == (self.R, self.R)
+        _check(lib().lr_tv_estimate_w_eigen_decomposition(self.h, _d(Dm), _d(Q)))
+
     def dev_acc(self):
         return int(lib().lr_tv_dev_acc(self.h))
 
@@ -425,6 +456,16 @@ class TV:
 
     def finish_estep(self, n_speakers_total):
         _check(lib().lr_tv_finish_estep(self.h, ct.c_double(n_speakers_total)))
+
+
+def eigen_problem(EP, rank=None):
+    """computeEigenProblem (AccumulateTVStat.cpp:2999): eigvec[n x rank] (column j = j-th largest), eigval."""
+    EP = _f64(EP)
+    n = EP.shape[0]
+    rank = n if rank is None else int(rank)
+    vec, val = np.empty((n, rank)), np.empty(rank)
+    _check(lib().lr_eigen_problem(n, _d(EP), rank, _d(vec), _d(val)))
+    return vec, val
 
 
 def plda_native_scoring(F, G, Sigma, models, model_of, segments):

@@ -38,7 +38,12 @@ constexpr unsigned kPadIndex = 0xFFFFFFFFu;
 constexpr int kOneCol = 60;                    // columns 60..62 of panel a carry 1.0
 constexpr float kGammaShift = 14.f;            // posteriors are stored as fp16(2^14 g)
 constexpr float kXClamp = 240.f;               // |xh| clamp (xh^2 must stay below fp16 max)
-constexpr int kMaxRunTiles = 128;              // fp32 TMEM partial sums are flushed at least this often (16 k frames)
+// fp32 TMEM partial sums are flushed to fp64 at least this often (8 k frames).  The tensor core
+// TRUNCATES the fp32 accumulator at every UMMA (8 per tile), a systematic -2^-25.8 relative bias per
+// accumulation step (measured on B200: 128-tile runs sat 1.4e-5 below 27-tile runs), so the run
+// length bounds the bias: 64 tiles -> <= 9e-6 relative.  Statistics-pass time per 1 M frames at
+// 32 / 64 / 128 tiles: 1.80 / 1.68 / 1.63 ms.
+constexpr int kMaxRunTiles = 64;
 constexpr int kTcThreads = 384;                 // warps: 0 bulk-copy producer, 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue
 constexpr int kEpiWarps = 8;
 constexpr int kStageFloats = 32 * 32;             // per-warp flush staging: 32 comps x 32 dims
@@ -1190,16 +1195,18 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
   for (int gi = 0; gi < groups; gi++)
     for (int t = cuts[gi]; t < cuts[gi + 1]; t++) tile_group[t] = gi;
   std::vector<TileInfo> tinfo(n_tiles);
+  // profiling experiments: bits 16..23 of lr_debug_flags override the flush interval
+  const int run_tiles = ((e.tc_debug >> 16) & 0xFF) ? ((e.tc_debug >> 16) & 0xFF) : kMaxRunTiles;
   for (int t = 0; t < n_tiles;) {
     const int row = tile_row[t], gi = tile_group[t];
     int t2 = t;
     while (t2 < n_tiles && tile_row[t2] == row && tile_group[t2] == gi) t2++;
     if (row < 0) return fail(LR_ERR_ARG, "tc_run_stats: tile %d is covered by no chunk", t);
     for (int k = t; k < t2; k++) {
-      const int in_run = (k - t) % kMaxRunTiles;
+      const int in_run = (k - t) % run_tiles;
       int flags = 0;
       if (in_run == 0) flags |= 1;
-      if (in_run == kMaxRunTiles - 1 || k == t2 - 1) flags |= 2;
+      if (in_run == run_tiles - 1 || k == t2 - 1) flags |= 2;
       tinfo[k] = {row, flags};
     }
     t = t2;

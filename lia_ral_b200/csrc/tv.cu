@@ -3,8 +3,11 @@
 //
 // Round-1 formulation: every triple loop of the reference is restated as a dense fp64 GEMM
 // over a batch of utterances (cuBLAS on the fp64 tensor pipe), the per-utterance R x R systems
-// are factorised with batched Cholesky (L = I + sum_c N_c TETt_c is SPD), and the glue
-// (centring, rank-1 updates, reductions) is hand-written kernels.  Layout notes use
+// are factorised with a blocked batched Cholesky (L = I + sum_c N_c TETt_c is SPD), and the glue
+// (centring, rank-1 updates, reductions, triangle packing) is hand-written kernels.
+// Symmetric R x R quantities that only ever enter a GEMM as a flat vector -- TETt_c, L_s, E_s,
+// A_c -- are held as PACKED lower triangles (R (R + 1) / 2 doubles), which halves the two
+// dominant GEMMs (L = N TETt, A += N^T E) and the E-step all-reduce.  Layout notes use
 // "row-major X[a x b]" for the reference's Matrix<double> buffers; cuBLAS sees the same
 // memory as the column-major transpose.
 #include <cusolverDn.h>
@@ -28,7 +31,8 @@ struct lr_tv {
   int batch = 0;  // utterances per batch of the posterior solve
   double *d_N = nullptr, *d_F = nullptr, *d_T = nullptr, *d_Ts = nullptr, *d_W = nullptr;
   double *d_mean = nullptr, *d_invvar = nullptr, *d_tett = nullptr;
-  double *d_acc = nullptr;  // [A C*R*R | Cmx R*sv | Rm R*R | r R | sumW R]
+  double *d_tettp = nullptr;  // [C x Rp] packed lower triangles of TETt_c
+  double *d_acc = nullptr;    // [A C*Rp (packed lower triangles) | Cmx R*sv | Rm R*R | r R | sumW R]
   double *d_meanW = nullptr;
   double *d_Lb = nullptr, *d_Eb = nullptr;  // [batch x R*R] work
   double *d_Yb = nullptr;                   // [batch x R*R] triangular inverse (E-step)
@@ -38,12 +42,13 @@ struct lr_tv {
   double **d_ptr_A = nullptr, **d_ptr_Tc = nullptr;                      // component pointers
   int *d_info = nullptr;
   cusolverDnHandle_t solver = nullptr;
-  double *A() const { return d_acc; }
-  double *Cmx() const { return d_acc + (size_t)C * R * R; }
+  size_t Rp() const { return (size_t)R * (R + 1) / 2; }
+  double *A() const { return d_acc; }  // packed: A_c at d_acc + c * Rp
+  double *Cmx() const { return d_acc + (size_t)C * Rp(); }
   double *Rm() const { return Cmx() + (size_t)R * sv; }
   double *r() const { return Rm() + (size_t)R * R; }
   double *sumW() const { return r() + R; }
-  size_t acc_len() const { return (size_t)C * R * R + (size_t)R * sv + (size_t)R * R + 2 * (size_t)R; }
+  size_t acc_len() const { return (size_t)C * Rp() + (size_t)R * sv + (size_t)R * R + 2 * (size_t)R; }
 };
 
 namespace lr {
@@ -70,12 +75,36 @@ __global__ void k_scale_cols(int R, size_t sv, const double *__restrict__ T,
     Ts[i] = T[i] * invvar[i % sv];
 }
 
-// L[b] += I
-__global__ void k_add_identity(int nb, int R, double *__restrict__ L) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nb * R) {
-    int b = i / R, d = i - b * R;
-    L[(size_t)b * R * R + (size_t)d * R + d] += 1.0;
+// Packed lower triangle of a symmetric R x R matrix: column j holds rows j..R-1 at
+// off(j) = j R - j (j - 1) / 2 (the column-major lower triangle, columns concatenated).
+__device__ __forceinline__ size_t packed_off(int R, int col) {
+  return (size_t)col * R - (size_t)col * (col - 1) / 2;
+}
+__global__ void k_pack_lower(size_t n, int R, const double *__restrict__ full,
+                             double *__restrict__ packed) {
+  const size_t rr = (size_t)R * R, rp = (size_t)R * (R + 1) / 2, total = n * rr;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t m = i / rr, e = i - m * rr;
+    int col = (int)(e / R), row = (int)(e - (size_t)col * R);
+    if (row >= col) packed[m * rp + packed_off(R, col) + (row - col)] = full[i];
+  }
+}
+// full[m] (column-major, ld R): lower triangle from the packed form (+ diag_add on the diagonal);
+// the strict upper triangle is zeroed (sym == 0) or mirrored (sym != 0).
+__global__ void k_unpack_lower(size_t n, int R, const double *__restrict__ packed,
+                               double *__restrict__ full, double diag_add, int sym) {
+  const size_t rr = (size_t)R * R, rp = (size_t)R * (R + 1) / 2, total = n * rr;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t m = i / rr, e = i - m * rr;
+    int col = (int)(e / R), row = (int)(e - (size_t)col * R);
+    double v = 0.0;
+    if (row >= col)
+      v = packed[m * rp + packed_off(R, col) + (row - col)] + (row == col ? diag_add : 0.0);
+    else if (sym)
+      v = packed[m * rp + packed_off(R, row) + (col - row)];
+    full[i] = v;
   }
 }
 
@@ -171,22 +200,52 @@ k_chol_solve(int n, const double *__restrict__ Lall, size_t stride, double *__re
   for (int i = tid; i < n; i += kSolveThreads) b[i] = xs[i];
 }
 
-// Inverses of the NB x NB diagonal blocks of a batch of lower factors.  One CTA per
-// (block, matrix); thread j computes column j of the inverse by forward substitution.
+// Blocked batched Cholesky (cusolverDnDpotrfBatched runs at ~1.4 TFLOP/s for R = 400..600:
+// measured 52 us per 600 x 600 matrix, profiles/r01_tv_breakdown.md).  Left-looking over 64-wide
+// block columns; everything heavy is a strided-batched DGEMM:
+//   A[k0:, k] -= L[k0:, 0:k0] L[k, 0:k0]^T          (DGEMM)
+//   L_kk = chol(A_kk), invD_kk = L_kk^-1             (k_diag_chol_inv, one CTA per matrix)
+//   L[k1:, k] = A[k1:, k] invD_kk^T                  (DGEMM, through a panel buffer)
+// The diagonal-block inverses are kept: the explicit inverse of the E-step reuses them.
 constexpr int kNB = 64;
 __global__ void __launch_bounds__(kNB)
-k_diag_inv(int n, const double *__restrict__ Lall, size_t stride, double *__restrict__ invD,
-           int nblk) {
+k_diag_chol_inv(int n, double *__restrict__ Lall, size_t stride, double *__restrict__ invD,
+                int nblk, int blk, int *__restrict__ bad) {
   extern __shared__ double dsm[];
   double (*Ls)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm);
   double (*Xs)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm + kNB * (kNB + 1));
-  const int blk = blockIdx.x, mat = blockIdx.y;
+  __shared__ int fail_flag;
+  const int mat = blockIdx.x;
   const int k0 = blk * kNB, nb = min(kNB, n - k0);
-  const double *L = Lall + (size_t)mat * stride;
+  double *L = Lall + (size_t)mat * stride;
   const int j = threadIdx.x;
+  if (j == 0) fail_flag = 0;
   for (int c = 0; c < nb; c++)
     if (j < nb) Ls[j][c] = (j >= c) ? L[(size_t)(k0 + c) * n + k0 + j] : 0.0;  // Ls[row][col]
   __syncthreads();
+  // right-looking Cholesky of the block: thread j owns row j
+  for (int c = 0; c < nb; c++) {
+    if (j == c) {
+      double d = Ls[c][c];
+      if (!(d > 0.0)) {
+        fail_flag = 1;
+        d = 1.0;
+      }
+      Ls[c][c] = sqrt(d);
+    }
+    __syncthreads();
+    if (j > c && j < nb) Ls[j][c] /= Ls[c][c];
+    __syncthreads();
+    if (j > c && j < nb) {
+      const double ljc = Ls[j][c];
+      for (int k = c + 1; k <= j; k++) Ls[j][k] -= ljc * Ls[k][c];
+    }
+    __syncthreads();
+  }
+  if (j == 0 && fail_flag) atomicExch(bad, mat + 1);
+  for (int c = 0; c < nb; c++)
+    if (j < nb && j >= c) L[(size_t)(k0 + c) * n + k0 + j] = Ls[j][c];
+  // inverse of the block factor: thread j computes column j by forward substitution
   if (j < nb) {
     for (int i = 0; i < nb; i++) {
       double v = (i == j) ? 1.0 : 0.0;
@@ -203,26 +262,122 @@ k_diag_inv(int n, const double *__restrict__ Lall, size_t stride, double *__rest
   for (int c = 0; c < kNB; c++) out[(size_t)c * kNB + j] = (j < nb && c < nb) ? Xs[j][c] : 0.0;
 }
 
-// dst[mat][0:nb, 0:nb] = src[mat][0:nb, 0:nb]  (column-major blocks with their own ld / stride)
-__global__ void k_copy_block(int nb, const double *__restrict__ src, int lds, size_t ss,
-                             double *__restrict__ dst, int ldd, size_t sd) {
+// dst[mat][0:rows, 0:cols] = src[mat][0:rows, 0:cols]  (column-major, own ld / stride each)
+__global__ void k_copy_rect(int rows, int cols, const double *__restrict__ src, int lds, size_t ss,
+                            double *__restrict__ dst, int ldd, size_t sd) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nb * nb) return;
-  int col = e / nb, row = e - col * nb;
+  if (e >= rows * cols) return;
+  int col = e / rows, row = e - col * rows;
   dst[(size_t)blockIdx.y * sd + (size_t)col * ldd + row] =
       src[(size_t)blockIdx.y * ss + (size_t)col * lds + row];
 }
 
-// zero the strictly upper triangle (column-major) of a batch of n x n matrices
-__global__ void k_zero_upper(int n, size_t stride, double *__restrict__ A, int batch) {
-  size_t total = (size_t)batch * n * n;
+// ---- approximate i-vector modes (IvExtractor --mode ubmWeight | eigenDecomposition) ------
+// normTMatrix (:1600-1609): T[j, i] *= sqrt(invvar[i])
+__global__ void k_norm_t(int R, size_t sv, const double *__restrict__ invvar, double *__restrict__ T) {
+  size_t total = (size_t)R * sv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x)
+    T[i] *= sqrt(invvar[i % sv]);
+}
+// normStatistics (:1225-1242): F = (F - mean N) sqrt(invvar)
+__global__ void k_norm_stats(size_t U, int C, int D, const double *__restrict__ N,
+                             const double *__restrict__ mean, const double *__restrict__ invvar,
+                             double *__restrict__ F) {
+  size_t sv = (size_t)C * D, total = U * sv;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
-    size_t m = i / ((size_t)n * n), e = i - m * (size_t)n * n;
-    int col = (int)(e / n), row = (int)(e - (size_t)col * n);
-    if (row < col) A[m * stride + e] = 0.0;
+    size_t s = i / sv, k = i - s * sv;
+    F[i] = (F[i] - mean[k] * N[s * C + k / D]) * sqrt(invvar[k]);
   }
 }
+// Tw = T o weight[component of the column]
+__global__ void k_scale_cols_comp(int R, size_t sv, int D, const double *__restrict__ T,
+                                  const double *__restrict__ weight, double *__restrict__ Tw) {
+  size_t total = (size_t)R * sv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x)
+    Tw[i] = T[i] * weight[(i % sv) / D];
+}
+// Dm[c, i] = sum_{k < D} G[c D + k, i]^2   (approximateTcTc :3131-3134)
+__global__ void k_tctc_diag(int C, int D, int R, const double *__restrict__ G,
+                            double *__restrict__ Dm) {
+  size_t total = (size_t)C * R;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    size_t c = e / R, i = e - c * R;
+    double d = 0.0;
+    for (int k = 0; k < D; k++) {
+      double g = G[(c * D + k) * R + i];
+      d += g * g;
+    }
+    Dm[e] = d;
+  }
+}
+// den[s, i] = 1 + (sum_c N[s, c]) lambda_i   (estimateWUbmWeight :2367-2373, in the eigenbasis of W)
+__global__ void k_ubm_weight_den(size_t U, int C, int R, const double *__restrict__ N,
+                                 const double *__restrict__ lambda, double *__restrict__ den) {
+  size_t s = blockIdx.x;
+  __shared__ double nsum;
+  __shared__ double red[8];
+  double p = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) p += N[s * C + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+    nsum = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R; i += blockDim.x) den[s * R + i] = 1.0 + nsum * lambda[i];
+}
+// Z[s, i] /= den[s, i] (+ add_one: den holds N D without the leading 1, :2573-2578)
+__global__ void k_div_rows(size_t n, const double *__restrict__ den, double add, double *__restrict__ Z) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    Z[i] /= (den[i] + add);
+}
+// reverse the column order of a column-major n x n matrix and of the eigenvalue vector
+// (syevd returns ascending eigenvalues; the reference sorts descending), transposing into the
+// reference's row-major eigvec[k][j]; sign convention: largest-magnitude component positive.
+__global__ void k_eig_reorder(int n, int rank, const double *__restrict__ V, const double *__restrict__ lam,
+                              double *__restrict__ eigvec, double *__restrict__ eigval) {
+  int j = blockIdx.x;  // output column (j-th largest)
+  if (j >= rank) return;
+  const double *col = V + (size_t)(n - 1 - j) * n;
+  __shared__ double best[256];
+  __shared__ int besti[256];
+  double b = -1.0;
+  int bi = 0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    double a = fabs(col[k]);
+    if (a > b) {
+      b = a;
+      bi = k;
+    }
+  }
+  best[threadIdx.x] = b;
+  besti[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      double ob = best[threadIdx.x + o];
+      int oi = besti[threadIdx.x + o];
+      if (ob > best[threadIdx.x] || (ob == best[threadIdx.x] && oi < besti[threadIdx.x])) {
+        best[threadIdx.x] = ob;
+        besti[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  const double sg = col[besti[0]] < 0.0 ? -1.0 : 1.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) eigvec[(size_t)k * rank + j] = sg * col[k];
+  if (threadIdx.x == 0) eigval[j] = lam[n - 1 - j];
+}
+
 
 int grid_for(size_t n, int threads = 256) {
   size_t g = (n + threads - 1) / threads;
@@ -239,6 +394,7 @@ void tv_free(lr_tv *tv) {
   cudaFree(tv->d_mean);
   cudaFree(tv->d_invvar);
   cudaFree(tv->d_tett);
+  cudaFree(tv->d_tettp);
   cudaFree(tv->d_acc);
   cudaFree(tv->d_meanW);
   cudaFree(tv->d_Lb);
@@ -276,29 +432,79 @@ lr_status check_factor(lr_tv *tv, int n, const char *what) {
   return LR_OK;
 }
 
+// In-place blocked Cholesky of `nb` column-major n x n matrices (lower triangle; the strict upper
+// triangle is left with garbage).  invD receives the inverses of the diagonal-block factors;
+// panel: [nb x n x kNB] scratch.
+lr_status chol_batched(lr_tv *tv, double *Lb, int n, int nb, double *invD, double *panel,
+                       const char *what) {
+  Engine &e = engine();
+  const size_t rr = (size_t)n * n;
+  const int nblk = (n + kNB - 1) / kNB;
+  const long long sD = (long long)nblk * kNB * kNB;
+  const double one = 1.0, zero = 0.0, mone = -1.0;
+  static bool diag_attr = false;
+  const size_t diag_smem = 2 * kNB * (kNB + 1) * sizeof(double);
+  if (!diag_attr) {
+    LR_CUDA(cudaFuncSetAttribute(k_diag_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)diag_smem));
+    diag_attr = true;
+  }
+  int *bad = tv->d_info;
+  LR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), e.stream));
+  for (int k = 0; k < nblk; k++) {
+    const int k0 = k * kNB, nbk = std::min(kNB, n - k0), m = n - k0, m2 = m - nbk;
+    if (k0 > 0) {
+      LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, m, nbk, k0, &mone,
+                                          Lb + k0, n, (long long)rr, Lb + k0, n, (long long)rr, &one,
+                                          Lb + (size_t)k0 * n + k0, n, (long long)rr, nb));
+      count_launch();
+    }
+    k_diag_chol_inv<<<nb, kNB, diag_smem, e.stream>>>(n, Lb, rr, invD, nblk, k, bad);
+    LR_CHECK_LAUNCH();
+    if (m2 > 0) {
+      const long long sP = (long long)n * kNB;
+      LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, m2, nbk, nbk, &one,
+                                          Lb + (size_t)k0 * n + k0 + nbk, n, (long long)rr,
+                                          invD + (size_t)k * kNB * kNB, kNB, sD, &zero, panel, m2, sP,
+                                          nb));
+      count_launch();
+      k_copy_rect<<<dim3(ceil_div((long)m2 * nbk, 256), nb), 256, 0, e.stream>>>(
+          m2, nbk, panel, m2, (size_t)sP, Lb + (size_t)k0 * n + k0 + nbk, n, rr);
+      LR_CHECK_LAUNCH();
+    }
+  }
+  int h = 0;
+  LR_CUDA(cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  if (h != 0)
+    return fail(LR_ERR_NUMERIC, "%s: matrix %d of the batch is not positive definite", what, h - 1);
+  return LR_OK;
+}
+
 // Posterior of a batch of utterances [u0, u0+nb): L = I + N TETt (in d_Lb), Cholesky, then
-//   want_inverse == false: W[u] = L^-1 aux (potrs)
-//   want_inverse == true : d_Eb = L^-1 (two triangular solves on I), W[u] = L^-1 aux
+//   want_inverse == false: W[u] = L^-1 aux (substitution kernel)
+//   want_inverse == true : d_Eb = L^-1 (blocked triangular inverse), W[u] = L^-1 aux
 // (estimateW :2126-2168 / estimateAandC :1722-1760)
 lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
   Engine &e = engine();
   const int R = tv->R, C = tv->C;
   const size_t rr = (size_t)R * R;
+  const int rp = (int)tv->Rp();
   const double one = 1.0, zero = 0.0;
-  // Lb[nb x R*R] = N_b[nb x C] * TETt[C x R*R]
-  LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)rr, nb, C, &one, tv->d_tett, (int)rr,
-                        tv->d_N + u0 * C, C, &zero, tv->d_Lb, (int)rr));
+  // packed lower triangles: Lp[nb x Rp] = N_b[nb x C] * TETtp[C x Rp]  (staged in d_Eb), then
+  // L = I + unpack(Lp) with a zeroed upper triangle
+  LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, rp, nb, C, &one, tv->d_tettp, rp,
+                        tv->d_N + u0 * C, C, &zero, tv->d_Eb, rp));
   count_launch();
-  k_add_identity<<<ceil_div((long)nb * R, 256), 256, 0, e.stream>>>(nb, R, tv->d_Lb);
+  k_unpack_lower<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>((size_t)nb, R, tv->d_Eb, tv->d_Lb,
+                                                                   1.0, 0);
   LR_CHECK_LAUNCH();
   // aux[nb x R] = Fc_b[nb x sv] * Ts^T  -> written straight into W
   LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, nb, (int)tv->sv, &one, tv->d_Ts,
                         (int)tv->sv, tv->d_F + u0 * tv->sv, (int)tv->sv, &zero, tv->d_W + u0 * R, R));
   count_launch();
-  LR_CUSOLVER(cusolverDnDpotrfBatched(tv->solver, CUBLAS_FILL_MODE_LOWER, R, tv->d_ptr_L, R,
-                                      tv->d_info, nb));
-  count_launch();
-  lr_status st = check_factor(tv, nb, "i-vector posterior precision L");
+  lr_status st = chol_batched(tv, tv->d_Lb, R, nb, tv->d_invD, tv->d_Eb,
+                              "i-vector posterior precision L");
   if (st != LR_OK) return st;
   if (!want_inverse) {
     // w = L^-1 aux: one CTA per utterance, aux sits in W and is overwritten by the i-vector
@@ -308,20 +514,11 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
     return LR_OK;
   }
   // Explicit inverse Linv = Y^T Y with Y = Lfac^-1, built block row by block row from the
-  // inverses of the 64 x 64 diagonal blocks -- everything heavy is a strided-batched DGEMM:
+  // inverses of the 64 x 64 diagonal blocks (kept by chol_batched) -- everything heavy is a
+  // strided-batched DGEMM:
   //   Y[i, 0:i] = -invD_ii (Lfac[i, 0:i] Y[0:i, 0:i]),   Y[i, i] = invD_ii
   const int nblk = (R + kNB - 1) / kNB;
   const double mone = -1.0;
-  k_zero_upper<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>(R, rr, tv->d_Lb, nb);
-  LR_CHECK_LAUNCH();
-  static bool diag_attr = false;
-  const size_t diag_smem = 2 * kNB * (kNB + 1) * sizeof(double);
-  if (!diag_attr) {
-    LR_CUDA(cudaFuncSetAttribute(k_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
-    diag_attr = true;
-  }
-  k_diag_inv<<<dim3(nblk, nb), kNB, diag_smem, e.stream>>>(R, tv->d_Lb, rr, tv->d_invD, nblk);
-  LR_CHECK_LAUNCH();
   LR_CUDA(cudaMemsetAsync(tv->d_Yb, 0, (size_t)nb * rr * sizeof(double), e.stream));
   const long long sD = (long long)nblk * kNB * kNB;
   for (int i = 0; i < nblk; i++) {
@@ -339,8 +536,9 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
       count_launch();
     }
     // Y[r0:, r0:] = invD_ii
-    k_copy_block<<<dim3(ceil_div((long)nbi * nbi, 256), nb), 256, 0, e.stream>>>(
-        nbi, tv->d_invD + (size_t)i * kNB * kNB, kNB, (size_t)sD, tv->d_Yb + (size_t)r0 * R + r0, R, rr);
+    k_copy_rect<<<dim3(ceil_div((long)nbi * nbi, 256), nb), 256, 0, e.stream>>>(
+        nbi, nbi, tv->d_invD + (size_t)i * kNB * kNB, kNB, (size_t)sD,
+        tv->d_Yb + (size_t)r0 * R + r0, R, rr);
     LR_CHECK_LAUNCH();
   }
   // Linv = Y^T Y  -> Eb
@@ -384,7 +582,8 @@ lr_tv *lr_tv_create(int C, int D, int R, size_t U, const double *ubm_mean,
   auto A = [&](double **p, size_t n) { return cudaMalloc(p, n * sizeof(double)) == cudaSuccess; };
   bool ok = A(&tv->d_N, U * C) && A(&tv->d_F, U * tv->sv) && A(&tv->d_T, R * tv->sv) &&
             A(&tv->d_Ts, R * tv->sv) && A(&tv->d_W, U * R) && A(&tv->d_mean, tv->sv) &&
-            A(&tv->d_invvar, tv->sv) && A(&tv->d_tett, (size_t)C * rr) && A(&tv->d_acc, tv->acc_len()) &&
+            A(&tv->d_invvar, tv->sv) && A(&tv->d_tett, (size_t)C * rr) &&
+            A(&tv->d_tettp, (size_t)C * tv->Rp()) && A(&tv->d_acc, tv->acc_len()) &&
             A(&tv->d_meanW, R) && A(&tv->d_Lb, (size_t)nbmax * rr) && A(&tv->d_Eb, (size_t)nbmax * rr) &&
             A(&tv->d_Yb, (size_t)nbmax * rr) &&
             A(&tv->d_invD, (size_t)nbmax * ((R + kNB - 1) / kNB) * kNB * kNB) &&
@@ -497,7 +696,14 @@ lr_status lr_tv_get_acc(lr_tv *tv, double *A, double *Cmx, double *Rm, double *r
   LR_READY();
   LR_REQUIRE(tv, "lr_tv_get_acc: null handle");
   size_t rr = (size_t)tv->R * tv->R;
-  if (A) TV_COPY(A, tv->A(), (size_t)tv->C * rr, cudaMemcpyDeviceToHost);
+  if (A) {  // the packed lower triangles are expanded to the reference's full symmetric _A
+    double *full = (double *)scratch_get(kSlotTmpA, (size_t)tv->C * rr * sizeof(double));
+    if (!full) return LR_ERR_CUDA;
+    k_unpack_lower<<<grid_for((size_t)tv->C * rr), 256, 0, engine().stream>>>(
+        (size_t)tv->C, tv->R, tv->A(), full, 0.0, 1);
+    LR_CHECK_LAUNCH();
+    TV_COPY(A, full, (size_t)tv->C * rr, cudaMemcpyDeviceToHost);
+  }
   if (Cmx) TV_COPY(Cmx, tv->Cmx(), (size_t)tv->R * tv->sv, cudaMemcpyDeviceToHost);
   if (Rm) TV_COPY(Rm, tv->Rm(), rr, cudaMemcpyDeviceToHost);
   if (r) TV_COPY(r, tv->r(), tv->R, cudaMemcpyDeviceToHost);
@@ -537,6 +743,9 @@ lr_status lr_tv_estimate_tett(lr_tv *tv) {
                                       tv->d_Ts, (int)tv->sv, tv->D, tv->d_T, (int)tv->sv, tv->D,
                                       &zero, tv->d_tett, tv->R, (long long)tv->R * tv->R, tv->C));
   count_launch();
+  k_pack_lower<<<grid_for((size_t)tv->C * tv->R * tv->R), 256, 0, e.stream>>>(
+      (size_t)tv->C, tv->R, tv->d_tett, tv->d_tettp);
+  LR_CHECK_LAUNCH();
   return LR_OK;
 }
 
@@ -560,7 +769,8 @@ lr_status lr_tv_estimate_a_and_c(lr_tv *tv) {
   const size_t rr = (size_t)R * R;
   const double one = 1.0;
   // _A, _R, _r, _meanW are zeroed here; _Cmx is NOT (AccumulateTVStat.cpp:1719-1721)
-  LR_CUDA(cudaMemsetAsync(tv->A(), 0, (size_t)C * rr * sizeof(double), e.stream));
+  const int rp = (int)tv->Rp();
+  LR_CUDA(cudaMemsetAsync(tv->A(), 0, (size_t)C * rp * sizeof(double), e.stream));
   LR_CUDA(cudaMemsetAsync(tv->Rm(), 0, (rr + 2 * (size_t)R) * sizeof(double), e.stream));
   for (size_t u0 = 0; u0 < tv->U; u0 += tv->batch) {
     int nb = (int)std::min<size_t>(tv->batch, tv->U - u0);
@@ -577,9 +787,12 @@ lr_status lr_tv_estimate_a_and_c(lr_tv *tv) {
     LR_CUBLAS(cublasDgemv(e.blas, CUBLAS_OP_N, (int)rr, nb, &one, tv->d_Eb, (int)rr, tv->d_ones, 1,
                           &one, tv->Rm(), 1));
     count_launch();
-    // A[C x R*R] += N_b^T E_b (:1775-1782)
-    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)rr, C, nb, &one, tv->d_Eb, (int)rr,
-                          tv->d_N + u0 * C, C, &one, tv->A(), (int)rr));
+    // A[C x Rp] += N_b^T pack(E_b) (:1775-1782; E_b is symmetric, only its lower triangle is
+    // accumulated -- the reference's loop runs over the full R x R)
+    k_pack_lower<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>((size_t)nb, R, tv->d_Eb, tv->d_Lb);
+    LR_CHECK_LAUNCH();
+    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, rp, C, nb, &one, tv->d_Lb, rp,
+                          tv->d_N + u0 * C, C, &one, tv->A(), rp));
     count_launch();
     // Cmx[R x sv] += W_b^T Fc_b (:1784-1788)
     LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)tv->sv, R, nb, &one,
@@ -609,8 +822,9 @@ lr_status lr_tv_update_t(lr_tv *tv) {
   const size_t rr = (size_t)R * R;
   const double one = 1.0;
   // factor a copy of A in the TETt buffer (TETt is re-estimated from the new T anyway)
-  LR_CUDA(cudaMemcpyAsync(tv->d_tett, tv->A(), (size_t)C * rr * sizeof(double),
-                          cudaMemcpyDeviceToDevice, e.stream));
+  k_unpack_lower<<<grid_for((size_t)C * rr), 256, 0, e.stream>>>((size_t)C, R, tv->A(), tv->d_tett,
+                                                                0.0, 0);
+  LR_CHECK_LAUNCH();
   LR_CUSOLVER(cusolverDnDpotrfBatched(tv->solver, CUBLAS_FILL_MODE_LOWER, R, tv->d_ptr_A, R,
                                       tv->d_info, C));
   count_launch();
@@ -700,6 +914,190 @@ lr_status lr_tv_orthonormalize_t(lr_tv *tv) {
                           e.stream));
   LR_CUDA(cudaStreamSynchronize(e.stream));
   return LR_OK;
+}
+
+// ---- approximate i-vector modes ----------------------------------------------------------
+lr_status lr_tv_norm_t(lr_tv *tv) {
+  LR_READY();
+  LR_REQUIRE(tv, "lr_tv_norm_t: null handle");
+  k_norm_t<<<grid_for((size_t)tv->R * tv->sv), 256, 0, engine().stream>>>(tv->R, tv->sv, tv->d_invvar,
+                                                                        tv->d_T);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+lr_status lr_tv_norm_statistics(lr_tv *tv) {
+  LR_READY();
+  LR_REQUIRE(tv, "lr_tv_norm_statistics: null handle");
+  k_norm_stats<<<grid_for(tv->U * tv->sv), 256, 0, engine().stream>>>(tv->U, tv->C, tv->D, tv->d_N,
+                                                                      tv->d_mean, tv->d_invvar, tv->d_F);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+lr_status lr_tv_weighted_cov(lr_tv *tv, const double *weight, double *W) {
+  LR_READY();
+  LR_REQUIRE(tv && weight && W, "lr_tv_weighted_cov: null argument");
+  Engine &e = engine();
+  const int R = tv->R;
+  const double one = 1.0, zero = 0.0;
+  double *Tw = (double *)scratch_get(kSlotTmpB, ((size_t)R * tv->sv + tv->C) * sizeof(double));
+  if (!Tw) return LR_ERR_CUDA;
+  double *d_w = Tw + (size_t)R * tv->sv;
+  LR_CUDA(cudaMemcpyAsync(d_w, weight, tv->C * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  k_scale_cols_comp<<<grid_for((size_t)R * tv->sv), 256, 0, e.stream>>>(R, tv->sv, tv->D, tv->d_T,
+                                                                        d_w, Tw);
+  LR_CHECK_LAUNCH();
+  // W[R x R] = Tw T^T (symmetric): column-major (sv x R) views of the row-major matrices
+  LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, R, (int)tv->sv, &one, tv->d_T,
+                        (int)tv->sv, Tw, (int)tv->sv, &zero, tv->d_Lb, R));
+  count_launch();
+  LR_CUDA(cudaMemcpyAsync(W, tv->d_Lb, (size_t)R * R * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  return LR_OK;
+}
+
+namespace lr {
+namespace {
+// symmetric eigen-problem on the device: d_V (column-major n x n, overwritten with the
+// eigenvectors), d_lam ascending.  cusolverDnDsyevd.
+lr_status eig_sym_device(cusolverDnHandle_t solver, int n, double *d_V, double *d_lam, int *d_info) {
+  Engine &e = engine();
+  int lwork = 0;
+  LR_CUSOLVER(cusolverDnDsyevd_bufferSize(solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                          d_V, n, d_lam, &lwork));
+  double *work = (double *)scratch_get(kSlotTmpA, (size_t)std::max(lwork, 1) * sizeof(double));
+  if (!work) return LR_ERR_CUDA;
+  LR_CUSOLVER(cusolverDnDsyevd(solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, d_V, n,
+                               d_lam, work, lwork, d_info));
+  count_launch();
+  int h = 0;
+  LR_CUDA(cudaMemcpyAsync(&h, d_info, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  if (h != 0) return fail(LR_ERR_NUMERIC, "eigen-decomposition did not converge (info %d)", h);
+  return LR_OK;
+}
+
+// W_b (op)= Q diag(1 / den_b) Q^T aux_b for every utterance; aux = Fn Tn^T.
+// Qrm: device row-major Q[R x R] (reference layout: Q(i, k) = component i of eigenvector k).
+// den: device [U x R]; den_add is added to it.  accumulate: W += (the reference's
+// eigenDecomposition path never resets _W) or W = (ubmWeight path, :2354).
+lr_status approx_solve(lr_tv *tv, const double *Qrm, const double *den, double den_add,
+                       bool accumulate) {
+  Engine &e = engine();
+  const int R = tv->R;
+  const double one = 1.0, zero = 0.0, beta = accumulate ? 1.0 : 0.0;
+  double *aux = tv->d_Eb, *Z = tv->d_Yb;  // [batch x R] each
+  for (size_t u0 = 0; u0 < tv->U; u0 += tv->batch) {
+    const int nb = (int)std::min<size_t>(tv->batch, tv->U - u0);
+    // aux[nb x R] = Fn_b[nb x sv] Tn^T   (:2380-2384, :2589-2593)
+    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, nb, (int)tv->sv, &one, tv->d_T,
+                          (int)tv->sv, tv->d_F + u0 * tv->sv, (int)tv->sv, &zero, aux, R));
+    // Z = aux Q : column-major Z^T[R x nb] = (Q^T)[R x R] aux^T; row-major Q seen column-major is Q^T
+    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, R, nb, R, &one, Qrm, R, aux, R, &zero, Z, R));
+    k_div_rows<<<grid_for((size_t)nb * R), 256, 0, e.stream>>>((size_t)nb * R, den + u0 * R, den_add, Z);
+    LR_CHECK_LAUNCH();
+    // W_b (+)= Z Q^T : column-major W^T[R x nb] = Q[R x R] Z^T = op_T(Qrm seen column-major) Z^T
+    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, nb, R, &one, Qrm, R, Z, R, &beta,
+                          tv->d_W + u0 * R, R));
+    count_launch(3);
+  }
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  return LR_OK;
+}
+}  // namespace
+}  // namespace lr
+
+lr_status lr_eigen_problem(int n, const double *EP, int rank, double *eigvec, double *eigval) {
+  LR_READY();
+  LR_REQUIRE(n >= 1 && rank >= 1 && rank <= n && EP && eigvec && eigval,
+             "lr_eigen_problem: bad arguments (n=%d rank=%d)", n, rank);
+  Engine &e = engine();
+  cusolverDnHandle_t solver = nullptr;
+  LR_CUSOLVER(cusolverDnCreate(&solver));
+  struct Guard {
+    cusolverDnHandle_t h;
+    ~Guard() { cusolverDnDestroy(h); }
+  } guard{solver};
+  LR_CUSOLVER(cusolverDnSetStream(solver, e.stream));
+  const size_t nn = (size_t)n * n;
+  double *buf = (double *)scratch_get(kSlotTmpB, (nn + n + nn + n + 2) * sizeof(double));
+  if (!buf) return LR_ERR_CUDA;
+  double *d_V = buf, *d_lam = buf + nn, *d_out = d_lam + n, *d_val = d_out + nn;
+  int *d_info = (int *)(d_val + n);
+  LR_CUDA(cudaMemcpyAsync(d_V, EP, nn * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  lr_status st = eig_sym_device(solver, n, d_V, d_lam, d_info);
+  if (st != LR_OK) return st;
+  k_eig_reorder<<<rank, 256, 0, e.stream>>>(n, rank, d_V, d_lam, d_out, d_val);
+  LR_CHECK_LAUNCH();
+  LR_CUDA(cudaMemcpyAsync(eigvec, d_out, (size_t)n * rank * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaMemcpyAsync(eigval, d_val, rank * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  return LR_OK;
+}
+
+lr_status lr_tv_approximate_tctc(lr_tv *tv, const double *Q, double *Dm) {
+  LR_READY();
+  LR_REQUIRE(tv && Q && Dm, "lr_tv_approximate_tctc: null argument");
+  Engine &e = engine();
+  const int R = tv->R;
+  const double one = 1.0, zero = 0.0;
+  double *G = (double *)scratch_get(kSlotTmpB, (tv->sv * R + (size_t)R * R + (size_t)tv->C * R) * sizeof(double));
+  if (!G) return LR_ERR_CUDA;
+  double *d_Q = G + tv->sv * R, *d_D = d_Q + (size_t)R * R;
+  LR_CUDA(cudaMemcpyAsync(d_Q, Q, (size_t)R * R * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  // G[sv x R] (row-major) = T^T Q : column-major G^T[R x sv] = Q^T[R x R] T[R x sv]
+  //   = (row-major Q seen column-major) (row-major T seen column-major (sv x R), transposed)
+  LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, R, (int)tv->sv, R, &one, d_Q, R, tv->d_T,
+                        (int)tv->sv, &zero, G, R));
+  count_launch();
+  k_tctc_diag<<<grid_for((size_t)tv->C * R), 256, 0, e.stream>>>(tv->C, tv->D, R, G, d_D);
+  LR_CHECK_LAUNCH();
+  LR_CUDA(cudaMemcpyAsync(Dm, d_D, (size_t)tv->C * R * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  return LR_OK;
+}
+
+lr_status lr_tv_estimate_w_ubm_weight(lr_tv *tv, const double *W) {
+  LR_READY();
+  LR_REQUIRE(tv && W, "lr_tv_estimate_w_ubm_weight: null argument");
+  Engine &e = engine();
+  const int R = tv->R;
+  const size_t rr = (size_t)R * R;
+  // L_s = I + n_s W shares the eigenvectors of W: L_s^-1 = Q diag(1 / (1 + n_s lambda)) Q^T, so the
+  // reference's per-utterance R x R inversion (:2376-2378) becomes one eigen-decomposition + GEMMs.
+  double *buf = (double *)scratch_get(kSlotTmpB, (2 * rr + R + tv->U * R) * sizeof(double));
+  if (!buf) return LR_ERR_CUDA;
+  double *d_V = buf, *d_Qrm = buf + rr, *d_lam = d_Qrm + rr, *d_den = d_lam + R;
+  LR_CUDA(cudaMemcpyAsync(d_V, W, rr * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  lr_status st = eig_sym_device(tv->solver, R, d_V, d_lam, tv->d_info);
+  if (st != LR_OK) return st;
+  // column-major V (eigenvector k in column k) -> row-major Q(i, k): a transpose
+  const double one = 1.0, zero = 0.0;
+  LR_CUBLAS(cublasDgeam(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, R, &one, d_V, R, &zero, d_V, R, d_Qrm, R));
+  count_launch();
+  k_ubm_weight_den<<<(unsigned)tv->U, 256, 0, e.stream>>>(tv->U, tv->C, R, tv->d_N, d_lam, d_den);
+  LR_CHECK_LAUNCH();
+  return approx_solve(tv, d_Qrm, d_den, 0.0, false);
+}
+
+lr_status lr_tv_estimate_w_eigen_decomposition(lr_tv *tv, const double *Dm, const double *Q) {
+  LR_READY();
+  LR_REQUIRE(tv && Dm && Q, "lr_tv_estimate_w_eigen_decomposition: null argument");
+  Engine &e = engine();
+  const int R = tv->R, C = tv->C;
+  const size_t rr = (size_t)R * R;
+  const double one = 1.0, zero = 0.0;
+  double *buf = (double *)scratch_get(kSlotTmpB, (rr + (size_t)C * R + tv->U * R) * sizeof(double));
+  if (!buf) return LR_ERR_CUDA;
+  double *d_Qrm = buf, *d_D = buf + rr, *d_den = d_D + (size_t)C * R;
+  LR_CUDA(cudaMemcpyAsync(d_Qrm, Q, rr * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  LR_CUDA(cudaMemcpyAsync(d_D, Dm, (size_t)C * R * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  // den[U x R] = N[U x C] Dm[C x R]  (:2573-2578; the leading 1 is added in k_div_rows)
+  LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, R, (int)tv->U, C, &one, d_D, R, tv->d_N, C,
+                        &zero, d_den, R));
+  count_launch();
+  return approx_solve(tv, d_Qrm, d_den, 1.0, true);
 }
 
 double *lr_tv_dev_acc(lr_tv *tv) { return tv ? tv->d_acc : nullptr; }

@@ -234,6 +234,62 @@ class Oracle:
         self.lib.orc_tv_orthonormalize(T.shape[0], ct.c_size_t(T.shape[1]), _d(T))
         return T
 
+    # ---- approximate i-vector modes ------------------------------------------
+    def tv_norm_t(self, T, invvar):
+        T = _f64(T).copy()
+        self.lib.orc_tv_norm_t(T.shape[0], ct.c_size_t(T.shape[1]), _d(_f64(invvar)), _d(T))
+        return T
+
+    def tv_norm_statistics(self, N, F, ubm_mean, invvar):
+        N, F = _f64(N), _f64(F).copy()
+        U, C = N.shape
+        D = F.size // (U * C)
+        self.lib.orc_tv_norm_statistics(ct.c_size_t(U), C, D, _d(N), _d(_f64(ubm_mean)),
+                                        _d(_f64(invvar)), _d(F))
+        return F
+
+    def tv_weighted_cov(self, T, weight, C, D):
+        T = _f64(T)
+        R = T.shape[0]
+        W = np.empty((R, R))
+        self.lib.orc_tv_weighted_cov(C, D, R, _d(T), _d(_f64(weight)), _d(W))
+        return W
+
+    def eigen_sym(self, EP, rank=None):
+        EP = _f64(EP)
+        n = EP.shape[0]
+        rank = n if rank is None else rank
+        vec, val = np.empty((n, rank)), np.empty(rank)
+        self.lib.orc_eigen_sym(n, _d(EP), rank, _d(vec), _d(val))
+        return vec, val
+
+    def tv_approximate_tctc(self, T, Q, C, D):
+        T, Q = _f64(T), _f64(Q)
+        R = T.shape[0]
+        Dm = np.empty((C, R))
+        self.lib.orc_tv_approximate_tctc(C, D, R, _d(T), _d(Q), _d(Dm))
+        return Dm
+
+    def tv_ivectors_ubm_weight(self, N, F, T, Wcov):
+        N, F, T = _f64(N), _f64(F), _f64(T)
+        U, C = N.shape
+        R = T.shape[0]
+        D = T.shape[1] // C
+        W = np.empty((U, R))
+        self.lib.orc_tv_ivectors_ubm_weight(ct.c_size_t(U), C, D, R, _d(N), _d(F), _d(T),
+                                            _d(_f64(Wcov)), _d(W))
+        return W
+
+    def tv_ivectors_eigen(self, N, F, T, Dm, Q, W0=None):
+        N, F, T = _f64(N), _f64(F), _f64(T)
+        U, C = N.shape
+        R = T.shape[0]
+        D = T.shape[1] // C
+        W = np.zeros((U, R)) if W0 is None else _f64(W0).copy()
+        self.lib.orc_tv_ivectors_eigen(ct.c_size_t(U), C, D, R, _d(N), _d(F), _d(T),
+                                       _d(_f64(Dm)), _d(_f64(Q)), _d(W))
+        return W
+
     # ---- PLDA ---------------------------------------------------------------
     def plda_native_scoring(self, F, G, Sigma, models, model_of, segments):
         F, Sigma = _f64(F), _f64(Sigma)

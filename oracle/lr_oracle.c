@@ -813,3 +813,187 @@ int orc_plda_native_scoring(int d, int rF, int rG, const double *F, const double
   free(s1);
   return 0;
 }
+
+/* ====================================================================== approximate i-vectors
+ *  IvExtractor --mode ubmWeight | eigenDecomposition and the
+ * TotalVariability approximationMode outputs. */
+
+/* normTMatrix, AccumulateTVStat.cpp:1600-1609 */
+void orc_tv_norm_t(int R, size_t sv, const double *invvar, double *T) {
+  for (size_t i = 0; i < sv; i++) {
+    double sq = sqrt(invvar[i]);
+    for (int j = 0; j < R; j++) T[(size_t)j * sv + i] = T[(size_t)j * sv + i] * sq;
+  }
+}
+
+/* normStatisticsUnThreaded, AccumulateTVStat.cpp:1225-1242 */
+void orc_tv_norm_statistics(size_t U, int C, int D, const double *N, const double *ubm_mean,
+                            const double *invvar, double *F) {
+  size_t sv = (size_t)C * D;
+  for (int i = 0; i < C; i++)
+    for (int j = 0; j < D; j++) {
+      double sq = sqrt(invvar[(size_t)i * D + j]);
+      for (size_t spk = 0; spk < U; spk++) {
+        F[spk * sv + (size_t)i * D + j] -= ubm_mean[(size_t)i * D + j] * N[spk * C + i];
+        F[spk * sv + (size_t)i * D + j] *= sq;
+      }
+    }
+}
+
+/* getWeightedCovUnThreaded, AccumulateTVStat.cpp:2837-2855.  W[R x R] */
+void orc_tv_weighted_cov(int C, int D, int R, const double *T, const double *weight, double *W) {
+  size_t sv = (size_t)C * D;
+  for (int i = 0; i < R * R; i++) W[i] = 0.0;
+  for (int cc = 0; cc < C; cc++)
+    for (int i = 0; i < R; i++)
+      for (int j = 0; j < i + 1; j++) {
+        const double *ti = T + (size_t)i * sv + (size_t)cc * D, *tj = T + (size_t)j * sv + (size_t)cc * D;
+        for (int k = 0; k < D; k++) W[i * R + j] += weight[cc] * ti[k] * tj[k];
+      }
+  for (int i = 0; i < R; i++)
+    for (int j = i; j < R; j++) W[i * R + j] = W[j * R + i];
+}
+
+/* computeEigenProblem, AccumulateTVStat.cpp:2999-3052: LAPACKE_dgeev on the (symmetric) matrix,
+ * eigenvalues sorted descending, eigvec[k][j] = component k of the j-th largest eigenvector
+ * (unit Euclidean norm; the sign is LAPACK's and not defined by the reference).  LAPACK is not
+ * available here: cyclic Jacobi, which converges to the same eigen-pairs for a symmetric input.
+ * Our sign convention: the component of largest magnitude is positive. */
+int orc_eigen_sym(int n, const double *EP, int rank, double *eigvec, double *eigval) {
+  double *a = (double *)malloc(sizeof(double) * n * n), *v = (double *)calloc((size_t)n * n, sizeof(double));
+  memcpy(a, EP, sizeof(double) * n * n);
+  for (int i = 0; i < n; i++) v[i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        if (i == j) diag += a[i * n + j] * a[i * n + j];
+        else off += a[i * n + j] * a[i * n + j];
+      }
+    if (off <= 1e-30 * diag || off == 0.0) break;
+    for (int p = 0; p < n - 1; p++)
+      for (int q = p + 1; q < n; q++) {
+        double apq = a[p * n + q];
+        if (apq == 0.0) continue;
+        double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; k++) {
+          double akp = a[k * n + p], akq = a[k * n + q];
+          a[k * n + p] = c * akp - s * akq;
+          a[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          double apk = a[p * n + k], aqk = a[q * n + k];
+          a[p * n + k] = c * apk - s * aqk;
+          a[q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          double vkp = v[k * n + p], vkq = v[k * n + q];
+          v[k * n + p] = c * vkp - s * vkq;
+          v[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int *order = (int *)malloc(sizeof(int) * n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  for (int i = 0; i < n; i++)  /* descendingSort */
+    for (int j = i + 1; j < n; j++)
+      if (a[order[j] * n + order[j]] > a[order[i] * n + order[i]]) {
+        int t = order[i];
+        order[i] = order[j];
+        order[j] = t;
+      }
+  for (int j = 0; j < rank; j++) {
+    int col = order[j], big = 0;
+    for (int k = 1; k < n; k++)
+      if (fabs(v[k * n + col]) > fabs(v[big * n + col])) big = k;
+    double sg = v[big * n + col] < 0 ? -1.0 : 1.0;
+    for (int k = 0; k < n; k++) eigvec[(size_t)k * rank + j] = sg * v[k * n + col];
+    eigval[j] = a[col * n + col];
+  }
+  free(a);
+  free(v);
+  free(order);
+  return 0;
+}
+
+/* approximateTcTcUnThreaded, AccumulateTVStat.cpp:3116-3136.  Q[R x R], Dm[C x R] (overwritten;
+ * the reference accumulates into a zeroed D) */
+void orc_tv_approximate_tctc(int C, int D, int R, const double *T, const double *Q, double *Dm) {
+  size_t sv = (size_t)C * D;
+  double *A = (double *)malloc(sizeof(double) * D * R);
+  for (int cc = 0; cc < C; cc++) {
+    for (int i = 0; i < D * R; i++) A[i] = 0.0;
+    for (int i = 0; i < D; i++)
+      for (int j = 0; j < R; j++)
+        for (int k = 0; k < R; k++) A[i * R + j] += T[(size_t)k * sv + (size_t)cc * D + i] * Q[k * R + j];
+    for (int i = 0; i < R; i++) {
+      double d = 0.0;
+      for (int k = 0; k < D; k++) d += A[k * R + i] * A[k * R + i];
+      Dm[(size_t)cc * R + i] = d;
+    }
+  }
+  free(A);
+}
+
+/* estimateWUbmWeightUnThreaded, AccumulateTVStat.cpp:2348-2396.  T and F are the NORMALISED
+ * matrix / statistics; Wcov[R x R]; W[U x R] overwritten. */
+void orc_tv_ivectors_ubm_weight(size_t U, int C, int D, int R, const double *N, const double *F,
+                                const double *T, const double *Wcov, double *W) {
+  size_t sv = (size_t)C * D;
+  double *L = (double *)malloc(sizeof(double) * R * R), *Linv = (double *)malloc(sizeof(double) * R * R);
+  double *aux = (double *)malloc(sizeof(double) * R);
+  for (size_t spk = 0; spk < U; spk++) {
+    double n_sum = 0.0;
+    for (int c = 0; c < C; c++) n_sum += N[spk * C + c];
+    for (int i = 0; i < R; i++) {
+      for (int j = 0; j < R; j++) L[i * R + j] = n_sum * Wcov[i * R + j];
+      L[i * R + i] += 1.0;
+    }
+    orc_invert(R, L, Linv);
+    for (int i = 0; i < R; i++) {
+      aux[i] = 0.0;
+      for (size_t k = 0; k < sv; k++) aux[i] += F[spk * sv + k] * T[(size_t)i * sv + k];
+    }
+    for (int i = 0; i < R; i++) {
+      double y = 0.0;
+      for (int k = 0; k < R; k++) y += aux[k] * Linv[i * R + k];
+      W[spk * R + i] = y;
+    }
+  }
+  free(L);
+  free(Linv);
+  free(aux);
+}
+
+/* estimateWEigenDecompositionUnThreaded, AccumulateTVStat.cpp:2566-2609.  Dm[C x R], Q[R x R];
+ * W[U x R] is ACCUMULATED into (the reference never resets _W in this function). */
+void orc_tv_ivectors_eigen(size_t U, int C, int D, int R, const double *N, const double *F,
+                           const double *T, const double *Dm, const double *Q, double *W) {
+  size_t sv = (size_t)C * D;
+  double *invL = (double *)malloc(sizeof(double) * R), *aux = (double *)malloc(sizeof(double) * R);
+  double *appL = (double *)malloc(sizeof(double) * R * R);
+  for (size_t spk = 0; spk < U; spk++) {
+    for (int i = 0; i < R; i++) {
+      double tmp = 1.0;
+      for (int cc = 0; cc < C; cc++) tmp += N[spk * C + cc] * Dm[(size_t)cc * R + i];
+      invL[i] = 1 / tmp;
+    }
+    for (int i = 0; i < R; i++) {
+      aux[i] = 0.0;
+      for (size_t k = 0; k < sv; k++) aux[i] += F[spk * sv + k] * T[(size_t)i * sv + k];
+    }
+    for (int i = 0; i < R; i++)
+      for (int j = 0; j < R; j++) {
+        double s = 0.0;
+        for (int k = 0; k < R; k++) s += Q[i * R + k] * invL[k] * Q[j * R + k];
+        appL[i * R + j] = s;
+      }
+    for (int i = 0; i < R; i++)
+      for (int k = 0; k < R; k++) W[spk * R + i] += aux[k] * appL[i * R + k];
+  }
+  free(invL);
+  free(aux);
+  free(appL);
+}

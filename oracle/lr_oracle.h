@@ -123,6 +123,25 @@ int orc_tv_mindiv(int C, int D, int R, double n_sessions, double *Rm, double *r,
 /* orthonormalizeT :1548-1596 */
 void orc_tv_orthonormalize(int R, size_t sv, double *T);
 
+/* ---- A.8b approximate i-vector modes */
+/* normTMatrix :1600-1609 */
+void orc_tv_norm_t(int R, size_t sv, const double *invvar, double *T);
+/* normStatisticsUnThreaded :1225-1242 */
+void orc_tv_norm_statistics(size_t U, int C, int D, const double *N, const double *ubm_mean,
+                            const double *invvar, double *F);
+/* getWeightedCovUnThreaded :2837-2855 */
+void orc_tv_weighted_cov(int C, int D, int R, const double *T, const double *weight, double *W);
+/* computeEigenProblem :2999-3052 (dgeev on a symmetric matrix; here cyclic Jacobi); eigvec[n x rank] */
+int orc_eigen_sym(int n, const double *EP, int rank, double *eigvec, double *eigval);
+/* approximateTcTcUnThreaded :3116-3136 */
+void orc_tv_approximate_tctc(int C, int D, int R, const double *T, const double *Q, double *Dm);
+/* estimateWUbmWeightUnThreaded :2348-2396 */
+void orc_tv_ivectors_ubm_weight(size_t U, int C, int D, int R, const double *N, const double *F,
+                                const double *T, const double *Wcov, double *W);
+/* estimateWEigenDecompositionUnThreaded :2566-2609 (W += ...) */
+void orc_tv_ivectors_eigen(size_t U, int C, int D, int R, const double *N, const double *F,
+                           const double *T, const double *Dm, const double *Q, double *W);
+
 /* ---- A.9 PLDA native scoring (PldaTools.cpp:2950-2972, 4489-4519, 4186-4271).
  * F[d x rF], G[d x rG] (rG may be 0), Sigma[d x d].  models[d x n_enrol] and
  * segments[d x n_test] are column-per-i-vector like the reference.  model_of[n_enrol]

@@ -161,3 +161,37 @@ def test_plda_scoring(oracle, rG):
     s2 = np_oracle.plda_scores(F, G, Sigma, models, model_of, segments)
     assert s.shape == (6, 9)
     assert np.allclose(s, s2, rtol=1e-8, atol=1e-9)
+
+
+def test_approximate_ivector_modes_against_numpy(oracle):
+    """The restated approximate-extraction loops (AccumulateTVStat.cpp:1225-1242, 1600-1609,
+    2348-2396, 2566-2609, 2837-2855, 2999-3052, 3116-3136) against independent numpy algebra."""
+    rng = np.random.default_rng(0)
+    C, D, R, U = 6, 4, 5, 7
+    T = rng.standard_normal((R, C * D))
+    invvar = rng.uniform(0.5, 2, C * D)
+    w = rng.dirichlet(np.ones(C))
+    N = rng.uniform(0, 5, (U, C))
+    F = rng.standard_normal((U, C * D))
+    mean = rng.standard_normal(C * D)
+    Tn = oracle.tv_norm_t(T, invvar)
+    assert np.allclose(Tn, T * np.sqrt(invvar))
+    Fn = oracle.tv_norm_statistics(N, F, mean, invvar)
+    assert np.allclose(Fn, (F - np.repeat(N, D, axis=1) * mean) * np.sqrt(invvar))
+    Wc = oracle.tv_weighted_cov(Tn, w, C, D)
+    assert np.allclose(Wc, (Tn * np.repeat(w, D)) @ Tn.T)
+    Q, lam = oracle.eigen_sym(Wc)
+    l2, Q2 = np.linalg.eigh(Wc)
+    assert np.allclose(lam, l2[::-1]) and np.allclose(np.abs(Q), np.abs(Q2[:, ::-1]), atol=1e-10)
+    assert all(Q[np.abs(Q[:, j]).argmax(), j] > 0 for j in range(R))   # documented sign convention
+    Dm = oracle.tv_approximate_tctc(Tn, Q, C, D)
+    ref = np.stack([np.diag(Q.T @ Tn[:, c * D:(c + 1) * D] @ Tn[:, c * D:(c + 1) * D].T @ Q) for c in range(C)])
+    assert np.allclose(Dm, ref)
+    W1 = oracle.tv_ivectors_ubm_weight(N, Fn, Tn, Wc)
+    ref = np.stack([np.linalg.solve(np.eye(R) + N[s].sum() * Wc, Tn @ Fn[s]) for s in range(U)])
+    assert np.allclose(W1, ref)
+    W2 = oracle.tv_ivectors_eigen(N, Fn, Tn, Dm, Q)
+    ref = np.stack([Q @ np.diag(1 / (1 + N[s] @ Dm)) @ Q.T @ (Tn @ Fn[s]) for s in range(U)])
+    assert np.allclose(W2, ref)
+    # the reference accumulates into _W in the eigenDecomposition estimator
+    assert np.allclose(oracle.tv_ivectors_eigen(N, Fn, Tn, Dm, Q, W0=W1), W1 + W2)

@@ -156,3 +156,71 @@ def test_plda_larger_tile(capi, oracle):
     ref = oracle.plda_native_scoring(F, G, Sigma, models, model_of, segments)
     got = capi.plda_native_scoring(F, G, Sigma, models, model_of, segments)
     assert np.abs(got - ref).max() < 1e-8 * np.abs(ref).max()
+
+
+def test_approximate_ivector_modes(capi, oracle, tvcase):
+    """IvExtractor --mode ubmWeight / eigenDecomposition (IvExtractor.cpp:151-363): normTMatrix,
+    normStatistics, getWeightedCov, computeEigenProblem, approximateTcTc and the two estimators
+    against the literal restatement of AccumulateTVStat.cpp:1225-1242, 1600-1609, 2348-2396,
+    2566-2609, 2837-2855, 2999-3052, 3116-3136."""
+    c = tvcase
+    C, D, R = c["C"], c["D"], c["R"]
+    w, _, _ = synth.make_ubm(C, D, seed=21)
+    tv = _device(capi, c)
+    tv.norm_t()
+    Tn_ref = oracle.tv_norm_t(c["T"], c["invvar"])
+    assert _rel(tv.get_T(), Tn_ref) < 1e-14
+    Wcov = tv.weighted_cov(w)
+    Wcov_ref = oracle.tv_weighted_cov(Tn_ref, w, C, D)
+    assert _rel(Wcov, Wcov_ref) < 1e-12 and np.array_equal(Wcov_ref, Wcov_ref.T)
+    tv.norm_statistics()
+    Fn_ref = oracle.tv_norm_statistics(c["N"], c["F"], c["mean"], c["invvar"])
+    assert _rel(tv.get_stats()[1], Fn_ref) < 1e-13
+
+    # ubmWeight: the device inverts L_s = I + n_s W in the eigenbasis of W, the oracle explicitly
+    tv.estimate_w_ubm_weight(Wcov_ref)
+    W_ref = oracle.tv_ivectors_ubm_weight(c["N"], Fn_ref, Tn_ref, Wcov_ref)
+    assert _rel(tv.get_W(), W_ref) < 1e-9
+
+    # eigen problem: eigenvalues descending, eigenvectors equal up to the documented sign convention
+    Q, lam = capi.eigen_problem(Wcov_ref)
+    Q_ref, lam_ref = oracle.eigen_sym(Wcov_ref)
+    assert np.all(np.diff(lam) <= 0) and np.allclose(lam, lam_ref, rtol=1e-10, atol=1e-12 * lam_ref[0])
+    assert np.allclose(Q.T @ Q, np.eye(R), atol=1e-10)
+    assert np.allclose(Wcov_ref @ Q, Q * lam, atol=1e-9 * lam_ref[0])
+    gap = np.abs(np.diff(lam_ref)).min() / lam_ref[0]
+    if gap > 1e-6:   # well separated spectrum: the vectors themselves must agree
+        assert np.allclose(Q, Q_ref, atol=1e-6 / gap * 1e-6)
+    Dm = tv.approximate_tctc(Q)
+    Dm_ref = oracle.tv_approximate_tctc(Tn_ref, Q, C, D)
+    assert _rel(Dm, Dm_ref) < 1e-12
+
+    # eigenDecomposition: accumulates into _W like the reference (W0 = the ubmWeight result above)
+    W0 = tv.get_W()
+    tv.estimate_w_eigen_decomposition(Dm_ref, Q)
+    W2_ref = oracle.tv_ivectors_eigen(c["N"], Fn_ref, Tn_ref, Dm_ref, Q, W0=W0)
+    assert _rel(tv.get_W(), W2_ref) < 1e-9
+    # the approximation is exact when every T_c T_c^T shares the eigenvectors: sanity of the algebra
+    i = 0
+    dense = Q @ np.diag(1.0 / (1.0 + c["N"][i] @ Dm_ref)) @ Q.T @ (Tn_ref @ Fn_ref[i])
+    assert np.allclose(W2_ref[i] - W0[i], dense, rtol=1e-9, atol=1e-12)
+
+
+def test_packed_accumulator_roundtrip(capi, oracle, tvcase):
+    """A_c is held as a packed lower triangle on the device (half the GEMM and half the all-reduce);
+    lr_tv_get_acc must hand back the reference's full symmetric [C x R*R] layout."""
+    c = tvcase
+    tv = _device(capi, c)
+    tv.reset_tmp_acc()
+    tv.subtract_m()
+    tv.estimate_tett()
+    tv.estimate_a_and_c()
+    A, Cmx, Rm, r, mw = tv.get_acc()
+    R, C = c["R"], c["C"]
+    A3 = A.reshape(C, R, R)
+    assert np.array_equal(A3, A3.transpose(0, 2, 1))
+    assert tv.acc_len() == C * R * (R + 1) // 2 + R * C * c["D"] + R * R + 2 * R
+    Fc = oracle.tv_subtract_m(c["N"], c["F"], c["mean"])
+    tett = oracle.tv_tett(c["T"], c["invvar"], C, c["D"])
+    _, A_ref, _, _, _, _ = oracle.tv_estep(c["N"], Fc, c["T"], c["invvar"], tett)
+    assert _rel(A, A_ref) < 1e-9
