@@ -50,38 +50,104 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML every 5 ms when
+    pynvml is importable, else nvidia-smi (one query takes ~50 ms)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]   # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.nvml = index, [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_row(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        return [sm, self.sm_max] + [bool(mask & b) for b in self.BITS]
+
+    def _smi_row(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True,
+                             text=True, timeout=5).stdout.strip()
+        if not out:
+            return None
+        c = [x.strip() for x in out.split(",")]
+        return [float(c[0]), float(c[1])] + [x.lower().startswith("active") for x in c[2:6]]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                row = self._nvml_row() if self.nvml else self._smi_row()
+                if row:
+                    self.rows.append(row)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.005 if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag = True
         self.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons,
+                "samples": len(self.rows), "source": "nvml" if self.nvml else "nvidia-smi"}
+
+
+def ivector_rate(torch, capi, dev, U=1024, R=400, reps=3):
+    """The metric's second half: i-vectors/s of the classic extraction (estimateW: L = I + N TETt,
+    Cholesky, solve) at 2048c/60d, rank 400, on statistics resident in HBM.  Synthetic statistics:
+    64 active components per utterance, 3000 frames, F = N mu + noise."""
+    from lia_ral_b200 import synth
+    w, mean, cov = synth.make_ubm(C, D, seed=1)
+    invvar = (1.0 / cov).reshape(-1)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    occ = torch.zeros((U, C), device=dev, dtype=torch.float64)
+    act = torch.randint(0, C, (U, 64), device=dev, generator=g)
+    occ.scatter_add_(1, act, torch.rand((U, 64), device=dev, generator=g, dtype=torch.float64))
+    occ *= 3000.0 / occ.sum(1, keepdim=True)
+    mu = torch.tensor(mean.reshape(-1), device=dev)
+    sd = torch.tensor(np.sqrt(cov).reshape(-1), device=dev)
+    Nrep = occ.repeat_interleave(D, dim=1)
+    F = Nrep * mu + torch.sqrt(Nrep) * sd * torch.randn((U, C * D), device=dev, generator=g, dtype=torch.float64)
+    tv = capi.TV(C, D, R, U, mean.reshape(-1), invvar)
+    tv.set_stats(occ.cpu().numpy(), F.cpu().numpy())
+    del F, Nrep
+    tv.set_T(synth.make_T(R, C, D, invvar, seed=4, scale=0.02))
+    tv.subtract_m()
+    capi.synchronize()
+    t0 = time.perf_counter()
+    tv.estimate_tett()
+    capi.synchronize()
+    t_tett = time.perf_counter() - t0
+    tv.estimate_w()
+    capi.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        tv.estimate_w()
+    capi.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    flop = U * (C * R * (R + 1) + 2 * C * D * R + R ** 3 / 3 + 2 * R * R)   # SURVEY.md §8d per utterance
+    return {"value": U / dt, "unit": "i-vectors/s", "utterances": U, "rank": R, "ms": dt * 1e3,
+            "tett_ms_once_per_T": t_tett * 1e3, "algorithmic_fp64_tflops": flop / dt / 1e12,
+            "workload": "estimateW on resident BW statistics, 2048c/60d, R=400 (configs[2] per-GPU slice)"}
 
 
 def synth_model():
@@ -164,13 +230,14 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=10_000_000, help="frames per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-ivectors", action="store_true", help="skip the i-vectors/s side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -283,6 +350,23 @@ def main():
     e2e_val = world * Te * args.e2e_steps / float(te.item())
     stat_bytes = nstat * 8
 
+    # ---- i-vectors/s (second half of BASELINE.json's metric), every rank on its own utterances
+    iv = None
+    if not args.no_ivectors:
+        del X, feats
+        torch.cuda.empty_cache()
+        try:
+            iv = ivector_rate(torch, capi, dev)
+            tiv = torch.tensor([iv["value"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tiv)   # weak scaling: utterances shard with no collective
+            iv["value"] = float(tiv.item())
+            iv["n_gpus"] = world
+        except Exception as exc:  # the headline line must survive a failure of the side measurement
+            iv = {"value": None, "error": str(exc)[:200]}
+            if world > 1:
+                dist.all_reduce(torch.zeros(1, dtype=torch.float64, device=dev))
+
     if rank == 0:
         pk = peaks()
         dom_ms, dom_n = (acc_ms, acc_n) if acc_ms >= lse_ms else (lse_ms, lse_n)
@@ -311,6 +395,8 @@ def main():
                          "avg_launch_ms": dom_ms / max(dom_n, 1), "peak_source": pk["src"],
                          "llk_pass_ms_per_step": lse_ms / args.steps, "stat_pass_ms_per_step": acc_ms / args.steps},
         }
+        if iv is not None:
+            out["ivectors"] = iv
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"], _, _ = cpu_baseline()
         print(json.dumps(out))

@@ -228,6 +228,45 @@ lr_status lr_plda_native_scoring(int d, int rF, int rG, const double *F, const d
                                  const int32_t *model_of, size_t n_models,
                                  const double *segments, size_t n_test, double *scores);
 
+/* ------------------------------------------------------------------ i-vector back-end -----
+ * Development-set statistics / normalisations of PldaDev and the non-PLDA scorings of PldaTest
+ * (PldaTools.cpp; IvTest.cpp:112-391, IvNorm).  Vectors are COLUMNS of row-major [d x n] matrices
+ * like the reference's _data / _models / _segments.  class_of[n] = speaker index of each session
+ * (the reference's _class), n_spk speakers. */
+/* PldaDev::computeAll :353-385 + computeCovMat :516-571: global / speaker means, total (Sigma),
+ * within-class (W) and between-class (B) covariance, all divided by n.  Any output may be NULL. */
+lr_status lr_iv_cov_mat(int d, size_t n, const double *data, const int32_t *class_of, size_t n_spk,
+                        double *mean, double *spk_means, double *Sigma, double *W, double *B);
+/* PldaDev::computeWccnChol :1113-1175: WCCN = upperCholesky((mean over speakers of cov_spk)^-1) */
+lr_status lr_iv_wccn_chol(int d, size_t n, const double *data, const int32_t *class_of, size_t n_spk,
+                          double *WCCN);
+/* PldaDev::computeMahalanobis :1366-1378: M = W^-1 */
+lr_status lr_iv_mahalanobis_matrix(int d, size_t n, const double *data, const int32_t *class_of,
+                                   size_t n_spk, double *M);
+/* one sphericalNuisanceNormalization iteration's matrix :1853-1900: mat = (V diag(1/sqrt(lambda)))^T
+ * for cov = Sigma (mode EFR) or W (mode sphNorm); eigenvalues descending, sign: largest component > 0 */
+lr_status lr_iv_efr_matrix(int d, const double *cov, double *mat);
+/* PldaDev::computeLDA :1381-1415: rows of ldaMat[rank x d] = leading unit-norm eigenvectors of
+ * W^-1 B (dgeev in the reference; the symmetric-definite pencil B v = lambda W v here) */
+lr_status lr_iv_lda(int d, const double *W, const double *B, int rank, double *ldaMat);
+/* center (mu, may be NULL) -> rotateLeft (M[r x d], may be NULL) -> lengthNorm (if length_norm):
+ * PldaTools.cpp:466-474, 498-514, 436-464 (PldaTest: :3754-3790, :3706-3750) -- i.e. one
+ * applySphericalNuisanceNormalization iteration (:1931-1975), an LDA / WCCN rotation, or any
+ * prefix of it.  out[(M ? r : d) x n]. */
+lr_status lr_iv_normalize(int d, size_t n, const double *data, const double *mu, const double *M, int r,
+                          int length_norm, double *out);
+/* PldaTest::cosineDistance :3842-3880, mahalanobisDistance :3882-3910, twoCovScoring :4083-4173.
+ * models[d x n_models], segments[d x n_test], scores[n_models x n_test]; trials[n_models x n_test]
+ * (bytes, may be NULL = all): pairs outside the mask score 0 like the reference's untouched _scores. */
+lr_status lr_iv_cosine_scoring(int d, size_t n_models, size_t n_test, const double *models,
+                               const double *segments, const uint8_t *trials, double *scores);
+lr_status lr_iv_mahalanobis_scoring(int d, size_t n_models, size_t n_test, const double *models,
+                                    const double *segments, const double *Mah, const uint8_t *trials,
+                                    double *scores);
+lr_status lr_iv_two_cov_scoring(int d, size_t n_models, size_t n_test, const double *models,
+                                const double *segments, const double *W, const double *B,
+                                double *scores);
+
 #ifdef __cplusplus
 }
 #endif

@@ -482,3 +482,106 @@ def plda_native_scoring(F, G, Sigma, models, model_of, segments):
                                         model_of.ctypes.data_as(c_ip), ct.c_size_t(n_models),
                                         _d(segments), ct.c_size_t(segments.shape[1]), _d(scores)))
     return scores
+
+
+# ---- i-vector back-end (PldaDev statistics / normalisation, non-PLDA scorings) ----------------
+def _cls(class_of):
+    return np.ascontiguousarray(class_of, dtype=np.int32)
+
+
+def iv_cov_mat(data, class_of, n_spk):
+    """PldaDev::computeAll + computeCovMat -> (mean, speaker_means, Sigma, W, B)."""
+    data, cls = _f64(data), _cls(class_of)
+    d, n = data.shape
+    mean, sm = np.empty(d), np.empty((d, n_spk))
+    S, W, B = np.empty((d, d)), np.empty((d, d)), np.empty((d, d))
+    _check(lib().lr_iv_cov_mat(d, ct.c_size_t(n), _d(data), cls.ctypes.data_as(c_ip), ct.c_size_t(n_spk),
+                               _d(mean), _d(sm), _d(S), _d(W), _d(B)))
+    return mean, sm, S, W, B
+
+
+def iv_wccn_chol(data, class_of, n_spk):
+    data, cls = _f64(data), _cls(class_of)
+    d, n = data.shape
+    out = np.empty((d, d))
+    _check(lib().lr_iv_wccn_chol(d, ct.c_size_t(n), _d(data), cls.ctypes.data_as(c_ip),
+                                 ct.c_size_t(n_spk), _d(out)))
+    return out
+
+
+def iv_mahalanobis_matrix(data, class_of, n_spk):
+    data, cls = _f64(data), _cls(class_of)
+    d, n = data.shape
+    out = np.empty((d, d))
+    _check(lib().lr_iv_mahalanobis_matrix(d, ct.c_size_t(n), _d(data), cls.ctypes.data_as(c_ip),
+                                          ct.c_size_t(n_spk), _d(out)))
+    return out
+
+
+def iv_efr_matrix(cov):
+    cov = _f64(cov)
+    out = np.empty_like(cov)
+    _check(lib().lr_iv_efr_matrix(cov.shape[0], _d(cov), _d(out)))
+    return out
+
+
+def iv_lda(W, B, rank):
+    W, B = _f64(W), _f64(B)
+    out = np.empty((rank, W.shape[0]))
+    _check(lib().lr_iv_lda(W.shape[0], _d(W), _d(B), int(rank), _d(out)))
+    return out
+
+
+def iv_normalize(data, mu=None, M=None, length_norm=False):
+    """center -> rotateLeft -> lengthNorm (each optional), vectors in columns."""
+    data = _f64(data)
+    d, n = data.shape
+    r = 0
+    if M is not None:
+        M = _f64(M)
+        r = M.shape[0]
+        assert M.shape[1] == d
+    out = np.empty((r if M is not None else d, n))
+    _check(lib().lr_iv_normalize(d, ct.c_size_t(n), _d(data), _d(_f64(mu)) if mu is not None else None,
+                                 _d(M) if M is not None else None, r, int(bool(length_norm)), _d(out)))
+    return out
+
+
+def _trials(trials, nm, nt):
+    if trials is None:
+        return None, None
+    t = np.ascontiguousarray(trials, dtype=np.uint8)
+    assert t.shape == (nm, nt)
+    return t, t.ctypes.data_as(ct.POINTER(ct.c_uint8))
+
+
+def iv_cosine_scoring(models, segments, trials=None):
+    models, segments = _f64(models), _f64(segments)
+    d, nm = models.shape
+    nt = segments.shape[1]
+    keep, tp = _trials(trials, nm, nt)
+    sc = np.empty((nm, nt))
+    _check(lib().lr_iv_cosine_scoring(d, ct.c_size_t(nm), ct.c_size_t(nt), _d(models), _d(segments), tp,
+                                      _d(sc)))
+    return sc
+
+
+def iv_mahalanobis_scoring(models, segments, Mah, trials=None):
+    models, segments, Mah = _f64(models), _f64(segments), _f64(Mah)
+    d, nm = models.shape
+    nt = segments.shape[1]
+    keep, tp = _trials(trials, nm, nt)
+    sc = np.empty((nm, nt))
+    _check(lib().lr_iv_mahalanobis_scoring(d, ct.c_size_t(nm), ct.c_size_t(nt), _d(models), _d(segments),
+                                           _d(Mah), tp, _d(sc)))
+    return sc
+
+
+def iv_two_cov_scoring(models, segments, W, B):
+    models, segments = _f64(models), _f64(segments)
+    d, nm = models.shape
+    nt = segments.shape[1]
+    sc = np.empty((nm, nt))
+    _check(lib().lr_iv_two_cov_scoring(d, ct.c_size_t(nm), ct.c_size_t(nt), _d(models), _d(segments),
+                                       _d(_f64(W)), _d(_f64(B)), _d(sc)))
+    return sc

@@ -290,6 +290,105 @@ class Oracle:
                                        _d(_f64(Dm)), _d(_f64(Q)), _d(W))
         return W
 
+    # ---- i-vector back-end (PldaDev / PldaTest non-PLDA scorings) --------------
+    def iv_compute_all(self, data, class_of, n_spk):
+        data = _f64(data)
+        d, n = data.shape
+        cls = np.ascontiguousarray(class_of, dtype=np.int32)
+        mean, sm = np.empty(d), np.empty((d, n_spk))
+        self.lib.orc_iv_compute_all(d, ct.c_size_t(n), _d(data), cls.ctypes.data_as(c_ip),
+                                    ct.c_size_t(n_spk), _d(mean), _d(sm))
+        return mean, sm
+
+    def iv_cov_mat(self, data, class_of, n_spk):
+        data = _f64(data)
+        d, n = data.shape
+        cls = np.ascontiguousarray(class_of, dtype=np.int32)
+        mean, sm = self.iv_compute_all(data, cls, n_spk)
+        S, W, B = np.empty((d, d)), np.empty((d, d)), np.empty((d, d))
+        self.lib.orc_iv_cov_mat(d, ct.c_size_t(n), _d(data), cls.ctypes.data_as(c_ip),
+                                ct.c_size_t(n_spk), _d(mean), _d(sm), _d(S), _d(W), _d(B))
+        return mean, sm, S, W, B
+
+    def iv_wccn_chol(self, data, class_of, n_spk):
+        data = _f64(data)
+        d, n = data.shape
+        cls = np.ascontiguousarray(class_of, dtype=np.int32)
+        _, sm = self.iv_compute_all(data, cls, n_spk)
+        out = np.empty((d, d))
+        rc = self.lib.orc_iv_wccn_chol(d, ct.c_size_t(n), _d(data), cls.ctypes.data_as(c_ip),
+                                       ct.c_size_t(n_spk), _d(sm), _d(out))
+        if rc != 0:
+            raise ArithmeticError("WCCN: singular within-class covariance")
+        return out
+
+    def iv_length_norm(self, data):
+        data = _f64(data).copy()
+        self.lib.orc_iv_length_norm(data.shape[0], ct.c_size_t(data.shape[1]), _d(data))
+        return data
+
+    def iv_center(self, data, mu):
+        data = _f64(data).copy()
+        self.lib.orc_iv_center(data.shape[0], ct.c_size_t(data.shape[1]), _d(_f64(mu)), _d(data))
+        return data
+
+    def iv_rotate_left(self, M, data):
+        M, data = _f64(M), _f64(data)
+        out = np.empty((M.shape[0], data.shape[1]))
+        self.lib.orc_iv_rotate_left(M.shape[0], M.shape[1], ct.c_size_t(data.shape[1]), _d(M),
+                                    _d(data), _d(out))
+        return out
+
+    def iv_efr_matrix(self, cov):
+        cov = _f64(cov)
+        out = np.empty_like(cov)
+        if self.lib.orc_iv_efr_matrix(cov.shape[0], _d(cov), _d(out)) != 0:
+            raise ArithmeticError("EFR: covariance is not positive definite")
+        return out
+
+    def iv_lda(self, W, B, rank):
+        W, B = _f64(W), _f64(B)
+        out = np.empty((rank, W.shape[0]))
+        if self.lib.orc_iv_lda(W.shape[0], _d(W), _d(B), rank, _d(out)) != 0:
+            raise ArithmeticError("LDA: singular within-class covariance")
+        return out
+
+    def _trials(self, trials, nm, nt):
+        if trials is None:
+            return None, None
+        t = np.ascontiguousarray(trials, dtype=np.uint8)
+        assert t.shape == (nm, nt)
+        return t, t.ctypes.data_as(ct.POINTER(ct.c_uint8))
+
+    def iv_cosine(self, models, segments, trials=None):
+        models, segments = _f64(models), _f64(segments)
+        d, nm = models.shape
+        nt = segments.shape[1]
+        keep, tp = self._trials(trials, nm, nt)
+        sc = np.empty((nm, nt))
+        self.lib.orc_iv_cosine(d, ct.c_size_t(nm), ct.c_size_t(nt), _d(models), _d(segments), tp, _d(sc))
+        return sc
+
+    def iv_mahalanobis(self, models, segments, Mah, trials=None):
+        models, segments = _f64(models), _f64(segments)
+        d, nm = models.shape
+        nt = segments.shape[1]
+        keep, tp = self._trials(trials, nm, nt)
+        sc = np.empty((nm, nt))
+        self.lib.orc_iv_mahalanobis(d, ct.c_size_t(nm), ct.c_size_t(nt), _d(models), _d(segments),
+                                    _d(_f64(Mah)), tp, _d(sc))
+        return sc
+
+    def iv_two_cov(self, models, segments, W, B):
+        models, segments = _f64(models), _f64(segments)
+        d, nm = models.shape
+        nt = segments.shape[1]
+        sc = np.empty((nm, nt))
+        if self.lib.orc_iv_two_cov(d, ct.c_size_t(nm), ct.c_size_t(nt), _d(models), _d(segments),
+                                   _d(_f64(W)), _d(_f64(B)), _d(sc)) != 0:
+            raise ArithmeticError("2cov: singular covariance")
+        return sc
+
     # ---- PLDA ---------------------------------------------------------------
     def plda_native_scoring(self, F, G, Sigma, models, model_of, segments):
         F, Sigma = _f64(F), _f64(Sigma)

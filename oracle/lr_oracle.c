@@ -997,3 +997,282 @@ void orc_tv_ivectors_eigen(size_t U, int C, int D, int R, const double *N, const
   free(aux);
   free(appL);
 }
+
+/* ====================================================================== i-vector back-end
+ *  PldaDev statistics / normalisation and the non-PLDA scorings of IvTest.
+ * Vectors are COLUMNS: data[d x n] like the reference's _data / _models / _segments. */
+
+/* PldaDev::computeAll, PldaTools.cpp:353-385.  class_of[n] = speaker of each session */
+void orc_iv_compute_all(int d, size_t n, const double *data, const int32_t *class_of, size_t n_spk,
+                        double *mean, double *spk_means) {
+  size_t *cnt = (size_t *)calloc(n_spk, sizeof(size_t));
+  for (int k = 0; k < d; k++) mean[k] = 0.0;
+  for (size_t i = 0; i < (size_t)d * n_spk; i++) spk_means[i] = 0.0;
+  for (size_t s = 0; s < n; s++) {
+    cnt[class_of[s]]++;
+    for (int k = 0; k < d; k++) {
+      spk_means[(size_t)k * n_spk + class_of[s]] += data[(size_t)k * n + s];
+      mean[k] += data[(size_t)k * n + s];
+    }
+  }
+  for (int k = 0; k < d; k++) {
+    mean[k] /= (double)n;
+    for (size_t c = 0; c < n_spk; c++) spk_means[(size_t)k * n_spk + c] /= (double)cnt[c];
+  }
+  free(cnt);
+}
+
+/* PldaDev::computeCovMatUnThreaded, PldaTools.cpp:527-571: total, within and between covariance */
+void orc_iv_cov_mat(int d, size_t n, const double *data, const int32_t *class_of, size_t n_spk,
+                    const double *mean, const double *spk_means, double *Sigma, double *W, double *B) {
+  size_t *cnt = (size_t *)calloc(n_spk, sizeof(size_t));
+  for (size_t s = 0; s < n; s++) cnt[class_of[s]]++;
+  for (int i = 0; i < d * d; i++) Sigma[i] = W[i] = B[i] = 0.0;
+  for (int i = 0; i < d; i++)
+    for (int j = i; j < d; j++) {
+      double sg = 0.0, w = 0.0, b = 0.0;
+      for (size_t s = 0; s < n; s++) {
+        size_t c = (size_t)class_of[s];
+        sg += (data[(size_t)i * n + s] - mean[i]) * (data[(size_t)j * n + s] - mean[j]);
+        w += (data[(size_t)i * n + s] - spk_means[(size_t)i * n_spk + c]) *
+             (data[(size_t)j * n + s] - spk_means[(size_t)j * n_spk + c]);
+      }
+      for (size_t c = 0; c < n_spk; c++)
+        b += (double)cnt[c] * (spk_means[(size_t)i * n_spk + c] - mean[i]) *
+             (spk_means[(size_t)j * n_spk + c] - mean[j]);
+      Sigma[i * d + j] = Sigma[j * d + i] = sg / (double)n;
+      W[i * d + j] = W[j * d + i] = w / (double)n;
+      B[i * d + j] = B[j * d + i] = b / (double)n;
+    }
+  free(cnt);
+}
+
+/* PldaDev::computeWccnCholUnThreaded, PldaTools.cpp:1124-1175: W = mean over speakers of the
+ * per-speaker covariance, WCCN = upperCholesky(W^-1) */
+int orc_iv_wccn_chol(int d, size_t n, const double *data, const int32_t *class_of, size_t n_spk,
+                     const double *spk_means, double *WCCN) {
+  double *W = (double *)calloc((size_t)d * d, sizeof(double)), *cov = (double *)malloc(sizeof(double) * d * d);
+  double *invW = (double *)malloc(sizeof(double) * d * d);
+  size_t *cnt = (size_t *)calloc(n_spk, sizeof(size_t));
+  for (size_t s = 0; s < n; s++) cnt[class_of[s]]++;
+  size_t s = 0;
+  while (s < n) {
+    size_t spk = (size_t)class_of[s];
+    for (int i = 0; i < d * d; i++) cov[i] = 0.0;
+    while (s < n && (size_t)class_of[s] == spk) {
+      for (int i = 0; i < d; i++)
+        for (int j = i; j < d; j++)
+          cov[i * d + j] += (data[(size_t)i * n + s] - spk_means[(size_t)i * n_spk + spk]) *
+                            (data[(size_t)j * n + s] - spk_means[(size_t)j * n_spk + spk]);
+      s++;
+    }
+    for (int i = 0; i < d; i++)
+      for (int j = i; j < d; j++) W[i * d + j] += cov[i * d + j] / (double)cnt[spk];
+  }
+  for (int i = 0; i < d; i++)
+    for (int j = i; j < d; j++) {
+      W[i * d + j] /= (double)n_spk;
+      W[j * d + i] = W[i * d + j];
+    }
+  int rc = orc_invert(d, W, invW);
+  if (rc == 0) rc = orc_upper_cholesky(d, invW, WCCN);
+  free(W);
+  free(cov);
+  free(invW);
+  free(cnt);
+  return rc;
+}
+
+/* lengthNorm, PldaTools.cpp:436-464 / 3706-3750 */
+void orc_iv_length_norm(int d, size_t n, double *data) {
+  for (size_t s = 0; s < n; s++) {
+    double t = 0.0;
+    for (int k = 0; k < d; k++) t += data[(size_t)k * n + s] * data[(size_t)k * n + s];
+    t = sqrt(t);
+    for (int k = 0; k < d; k++) data[(size_t)k * n + s] /= t;
+  }
+}
+/* center, PldaTools.cpp:466-474 / 3754-3767 */
+void orc_iv_center(int d, size_t n, const double *mu, double *data) {
+  for (size_t s = 0; s < n; s++)
+    for (int k = 0; k < d; k++) data[(size_t)k * n + s] -= mu[k];
+}
+/* rotateLeft, PldaTools.cpp:498-514 / 3770-3790: out[r x n] = M[r x d] data[d x n] */
+void orc_iv_rotate_left(int r, int d, size_t n, const double *M, const double *data, double *out) {
+  for (int i = 0; i < r; i++)
+    for (size_t s = 0; s < n; s++) {
+      double t = 0.0;
+      for (int k = 0; k < d; k++) t += M[i * d + k] * data[(size_t)k * n + s];
+      out[(size_t)i * n + s] = t;
+    }
+}
+/* the normalisation matrix of one sphericalNuisanceNormalization iteration,
+ * PldaTools.cpp:1853-1900: (eigenVect diag(1 / sqrt(eigenVal)))^T of Sigma (EFR) or W (sphNorm) */
+int orc_iv_efr_matrix(int d, const double *cov, double *mat) {
+  double *vec = (double *)malloc(sizeof(double) * d * d), *val = (double *)malloc(sizeof(double) * d);
+  orc_eigen_sym(d, cov, d, vec, val);
+  int rc = 0;
+  for (int i = 0; i < d; i++) {   /* mat[i][k] = vec[k][i] / sqrt(val[i]) */
+    if (!(val[i] > 0.0)) rc = 1;
+    for (int k = 0; k < d; k++) mat[i * d + k] = vec[k * d + i] / sqrt(val[i]);
+  }
+  free(vec);
+  free(val);
+  return rc;
+}
+
+/* PldaDev::computeLDA, PldaTools.cpp:1381-1415: leading eigenvectors of W^-1 B (dgeev in the
+ * reference; here through the symmetric form U^-T B U^-1 with W = U^T U), unit norm, rows of
+ * ldaMat[rank x d]; sign: largest-magnitude component positive. */
+int orc_iv_lda(int d, const double *W, const double *B, int rank, double *ldaMat) {
+  double *U = (double *)malloc(sizeof(double) * d * d), *Ui = (double *)malloc(sizeof(double) * d * d);
+  double *Cm = (double *)malloc(sizeof(double) * d * d), *tmp = (double *)malloc(sizeof(double) * d * d);
+  double *vec = (double *)malloc(sizeof(double) * d * rank), *val = (double *)malloc(sizeof(double) * rank);
+  int rc = orc_upper_cholesky(d, W, U);
+  if (rc == 0) rc = orc_invert(d, U, Ui);
+  if (rc == 0) {
+    /* Cm = Ui^T B Ui */
+    for (int i = 0; i < d; i++)
+      for (int j = 0; j < d; j++) {
+        double t = 0.0;
+        for (int k = 0; k < d; k++) t += B[i * d + k] * Ui[k * d + j];
+        tmp[i * d + j] = t;
+      }
+    for (int i = 0; i < d; i++)
+      for (int j = 0; j < d; j++) {
+        double t = 0.0;
+        for (int k = 0; k < d; k++) t += Ui[k * d + i] * tmp[k * d + j];
+        Cm[i * d + j] = t;
+      }
+    for (int i = 0; i < d; i++)
+      for (int j = i + 1; j < d; j++) Cm[i * d + j] = Cm[j * d + i] = 0.5 * (Cm[i * d + j] + Cm[j * d + i]);
+    orc_eigen_sym(d, Cm, rank, vec, val);
+    for (int j = 0; j < rank; j++) {   /* v = Ui y, normalised */
+      double nrm = 0.0;
+      int big = 0;
+      for (int i = 0; i < d; i++) {
+        double t = 0.0;
+        for (int k = 0; k < d; k++) t += Ui[i * d + k] * vec[(size_t)k * rank + j];
+        ldaMat[(size_t)j * d + i] = t;
+        nrm += t * t;
+      }
+      nrm = sqrt(nrm);
+      for (int i = 1; i < d; i++)
+        if (fabs(ldaMat[(size_t)j * d + i]) > fabs(ldaMat[(size_t)j * d + big])) big = i;
+      double sg = ldaMat[(size_t)j * d + big] < 0 ? -1.0 : 1.0;
+      for (int i = 0; i < d; i++) ldaMat[(size_t)j * d + i] *= sg / nrm;
+    }
+  }
+  free(U);
+  free(Ui);
+  free(Cm);
+  free(tmp);
+  free(vec);
+  free(val);
+  return rc;
+}
+
+/* PldaTest::cosineDistance, PldaTools.cpp:3842-3880.  trials[nm x nt] (may be NULL = all);
+ * untested pairs keep the score 0 (the reference's zero-initialised _scores). */
+void orc_iv_cosine(int d, size_t nm, size_t nt, const double *models, const double *segments,
+                   const uint8_t *trials, double *scores) {
+  double *nM = (double *)calloc(nm, sizeof(double)), *nS = (double *)calloc(nt, sizeof(double));
+  for (int k = 0; k < d; k++) {
+    for (size_t m = 0; m < nm; m++) nM[m] += models[(size_t)k * nm + m] * models[(size_t)k * nm + m];
+    for (size_t s = 0; s < nt; s++) nS[s] += segments[(size_t)k * nt + s] * segments[(size_t)k * nt + s];
+  }
+  for (size_t m = 0; m < nm; m++) nM[m] = sqrt(nM[m]);
+  for (size_t s = 0; s < nt; s++) nS[s] = sqrt(nS[s]);
+  for (size_t m = 0; m < nm; m++)
+    for (size_t s = 0; s < nt; s++) {
+      double sc = 0.0;
+      if (!trials || trials[m * nt + s]) {
+        for (int k = 0; k < d; k++) sc += models[(size_t)k * nm + m] * segments[(size_t)k * nt + s];
+        sc /= (nM[m] * nS[s]);
+      }
+      scores[m * nt + s] = sc;
+    }
+  free(nM);
+  free(nS);
+}
+
+/* PldaTest::mahalanobisDistance, PldaTools.cpp:3882-3910 */
+void orc_iv_mahalanobis(int d, size_t nm, size_t nt, const double *models, const double *segments,
+                        const double *Mah, const uint8_t *trials, double *scores) {
+  double *tmp = (double *)malloc(sizeof(double) * d), *t = (double *)malloc(sizeof(double) * d);
+  for (size_t m = 0; m < nm; m++)
+    for (size_t s = 0; s < nt; s++) {
+      double sc = 0.0;
+      if (!trials || trials[m * nt + s]) {
+        for (int k = 0; k < d; k++) tmp[k] = models[(size_t)k * nm + m] - segments[(size_t)k * nt + s];
+        for (int k = 0; k < d; k++) {
+          t[k] = 0.0;
+          for (int i = 0; i < d; i++) t[k] += -0.5 * tmp[i] * Mah[i * d + k];
+        }
+        for (int i = 0; i < d; i++) sc += t[i] * tmp[i];
+      }
+      scores[m * nt + s] = sc;
+    }
+  free(tmp);
+  free(t);
+}
+
+/* PldaTest::twoCovScoring + twoCovScoringMixPartUnThreaded, PldaTools.cpp:4083-4173, 3923-3950 */
+int orc_iv_two_cov(int d, size_t nm, size_t nt, const double *models, const double *segments,
+                   const double *W, const double *B, double *scores) {
+  size_t dd = (size_t)d * d;
+  double *invW = (double *)malloc(sizeof(double) * dd), *invB = (double *)malloc(sizeof(double) * dd);
+  double *sumG = (double *)malloc(sizeof(double) * dd), *sumH = (double *)malloc(sizeof(double) * dd);
+  double *tG = (double *)malloc(sizeof(double) * dd), *tH = (double *)malloc(sizeof(double) * dd);
+  double *tG2 = (double *)calloc(dd, sizeof(double)), *tH2 = (double *)calloc(dd, sizeof(double));
+  double *G = (double *)calloc(dd, sizeof(double)), *H = (double *)calloc(dd, sizeof(double));
+  int rc = orc_invert(d, W, invW) | orc_invert(d, B, invB);
+  for (size_t i = 0; i < dd; i++) {
+    sumG[i] = invB[i] + 2 * invW[i];
+    sumH[i] = invB[i] + invW[i];
+  }
+  rc |= orc_invert(d, sumG, tG) | orc_invert(d, sumH, tH);
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++)
+      for (int k = 0; k < d; k++) {
+        tH2[i * d + j] += invW[i * d + k] * tH[k * d + j];
+        tG2[i * d + j] += invW[i * d + k] * tG[k * d + j];
+      }
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++)
+      for (int k = 0; k < d; k++) {
+        G[i * d + j] += tG2[i * d + k] * invW[k * d + j];
+        H[i * d + j] += tH2[i * d + k] * invW[k * d + j];
+      }
+  double *mds = (double *)calloc(nm, sizeof(double)), *sds = (double *)calloc(nt, sizeof(double));
+  double *a = (double *)malloc(sizeof(double) * d);
+  for (size_t m = 0; m < nm; m++) {
+    for (int k = 0; k < d; k++) {
+      a[k] = 0.0;
+      for (int i = 0; i < d; i++) a[k] += models[(size_t)i * nm + m] * H[i * d + k];
+    }
+    for (int j = 0; j < d; j++) mds[m] += a[j] * models[(size_t)j * nm + m];
+  }
+  for (size_t s = 0; s < nt; s++) {
+    for (int k = 0; k < d; k++) {
+      a[k] = 0.0;
+      for (int i = 0; i < d; i++) a[k] += segments[(size_t)i * nt + s] * H[i * d + k];
+    }
+    for (int j = 0; j < d; j++) sds[s] += a[j] * segments[(size_t)j * nt + s];
+  }
+  double *diff = (double *)malloc(sizeof(double) * d);
+  for (size_t m = 0; m < nm; m++)
+    for (size_t s = 0; s < nt; s++) {
+      double sc = 0.0;
+      for (int j = 0; j < d; j++) diff[j] = models[(size_t)j * nm + m] + segments[(size_t)j * nt + s];
+      for (int k = 0; k < d; k++) {
+        a[k] = 0.0;
+        for (int i = 0; i < d; i++) a[k] += diff[i] * G[i * d + k];
+      }
+      for (int j = 0; j < d; j++) sc += a[j] * diff[j];
+      scores[m * nt + s] = sc - (mds[m] + sds[s]);
+    }
+  free(invW); free(invB); free(sumG); free(sumH); free(tG); free(tH); free(tG2); free(tH2);
+  free(G); free(H); free(mds); free(sds); free(a); free(diff);
+  return rc;
+}

@@ -152,6 +152,28 @@ int orc_plda_native_scoring(int d, int rF, int rG, const double *F, const double
                             const int32_t *model_of, size_t n_models, const double *segments,
                             size_t n_test, double *scores);
 
+/* ---- A.10 i-vector back-end: PldaDev statistics / normalisation and the
+ * cosine / Mahalanobis / two-covariance scorings of IvTest.  Vectors are columns: data[d x n]. */
+void orc_iv_compute_all(int d, size_t n, const double *data, const int32_t *class_of, size_t n_spk,
+                        double *mean, double *spk_means);                 /* PldaTools.cpp:353-385 */
+void orc_iv_cov_mat(int d, size_t n, const double *data, const int32_t *class_of, size_t n_spk,
+                    const double *mean, const double *spk_means, double *Sigma, double *W,
+                    double *B);                                            /* :527-571 */
+int orc_iv_wccn_chol(int d, size_t n, const double *data, const int32_t *class_of, size_t n_spk,
+                     const double *spk_means, double *WCCN);               /* :1124-1175 */
+void orc_iv_length_norm(int d, size_t n, double *data);                    /* :436-464, 3706-3750 */
+void orc_iv_center(int d, size_t n, const double *mu, double *data);       /* :466-474, 3754-3767 */
+void orc_iv_rotate_left(int r, int d, size_t n, const double *M, const double *data,
+                        double *out);                                      /* :498-514, 3770-3790 */
+int orc_iv_efr_matrix(int d, const double *cov, double *mat);              /* :1853-1900 */
+int orc_iv_lda(int d, const double *W, const double *B, int rank, double *ldaMat); /* :1381-1415 */
+void orc_iv_cosine(int d, size_t nm, size_t nt, const double *models, const double *segments,
+                   const uint8_t *trials, double *scores);                 /* :3842-3880 */
+void orc_iv_mahalanobis(int d, size_t nm, size_t nt, const double *models, const double *segments,
+                        const double *Mah, const uint8_t *trials, double *scores); /* :3882-3910 */
+int orc_iv_two_cov(int d, size_t nm, size_t nt, const double *models, const double *segments,
+                   const double *W, const double *B, double *scores);      /* :4083-4173 */
+
 /* dense helpers ([ALIZE] DoubleSquareMatrix::invert / upperCholesky) */
 int orc_invert(int n, const double *a, double *inv);
 int orc_upper_cholesky(int n, const double *a, double *u); /* a = u^T u, u upper */

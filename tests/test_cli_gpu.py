@@ -3,6 +3,7 @@ reference's formats, against the oracle: same configs keys, same outputs (NIST r
 GMM, DB matrices, per-id i-vector files)."""
 import os
 import subprocess
+import time
 
 import numpy as np
 import pytest
@@ -19,7 +20,11 @@ def _run(prog, cfg, **over):
     cmd = [os.path.join(BIN, prog), "--config", str(cfg)]
     for k, v in over.items():
         cmd += [f"--{k}", str(v)]
+    t0 = time.perf_counter()
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if os.environ.get("LIA_CLI_TIMES"):   # per-program wall times for profiling the suite itself
+        with open(os.environ["LIA_CLI_TIMES"], "a") as f:
+            f.write(f"{prog} {time.perf_counter() - t0:.2f}s\n")
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Exception" not in out.stdout, out.stdout
     return out.stdout
@@ -163,6 +168,67 @@ def test_ivector_and_tv_cli(world, oracle):
     got = lf.read_db(d / "TV_out.mat")
     assert np.abs(got - Tr).max() < 1e-3 * np.abs(Tr).max()
     assert np.abs(lf.read_db(d / "meanEst.mat")[0] - mean).max() < 1e-4 * np.abs(mean).max()
+
+
+def test_ivextractor_approximate_modes_cli(world, oracle):
+    """IvExtractor --mode ubmWeight / eigenDecomposition (IvExtractor.cpp:151-363), both computing the
+    approximation parameters on the fly and loading the ones TotalVariability wrote with
+    approximationMode (TotalVariability.cpp:181-241)."""
+    d, C, D, R = world["dir"], world["C"], world["D"], 5
+    invvar = (1.0 / world["cov"]).reshape(-1)
+    T = synth.make_T(R, C, D, invvar, seed=92, scale=0.05)
+    lf.write_db(d / "TVa.mat", T)
+    ids = [["idA", "utt0", "utt1"], ["idB", "utt2"], ["idC", "utt3", "utt4"]]
+    lf.write_lines(d / "ids_a.ndx", ids)
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    N = np.zeros((3, C))
+    F = np.zeros((3, C * D))
+    for row, line in enumerate(ids):
+        for u in line[1:]:
+            X = np.ascontiguousarray(world["utts"][u][_selected(u, world["utts"][u])])
+            n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+            N[row] += n1[0]
+            F[row] += f1[0]
+    Tn = oracle.tv_norm_t(T, invvar)
+    Fn = oracle.tv_norm_statistics(N, F, world["mean"].reshape(-1), invvar)
+    Wcov = oracle.tv_weighted_cov(Tn, world["w"], C, D)
+    Q, _ = oracle.eigen_sym(Wcov)
+    Dm = oracle.tv_approximate_tctc(Tn, Q, C, D)
+    W_ubm = oracle.tv_ivectors_ubm_weight(N, Fn, Tn, Wcov)
+    W_eig = oracle.tv_ivectors_eigen(N, Fn, Tn, Dm, Q)
+
+    def check(sub, W):
+        for row, line in enumerate(ids):
+            y = lf.read_db(d / sub / f"{line[0]}.y")
+            assert y.shape == (1, R) and np.abs(y[0] - W[row]).max() < 1e-4 * np.abs(W).max(), sub
+
+    base = dict(world["common"], targetIdList=str(d / "ids_a.ndx"), inputWorldFilename="wld",
+                totalVariabilityNumber=R, totalVariabilityMatrix="TVa", nullOrderStatSpeaker="N_a",
+                firstOrderStatSpeaker="F_a", vectorFilesExtension=".y")
+    for mode, W in (("ubmWeight", W_ubm), ("eigenDecomposition", W_eig)):
+        os.makedirs(d / f"iv_{mode}", exist_ok=True)
+        lf.write_cfg(d / f"iv_{mode}.cfg", **base, saveVectorFilesPath=str(d / f"iv_{mode}") + "/", mode=mode)
+        _run("IvExtractor", d / f"iv_{mode}.cfg")
+        check(f"iv_{mode}", W)
+    # TotalVariability with nbIt = 0 only writes the approximation parameters of the loaded matrix
+    lf.write_lines(d / "tv_a.ndx", [l[1:] for l in ids])
+    for mode in ("ubmWeight", "eigenDecomposition"):
+        lf.write_cfg(d / f"tv_{mode}.cfg", **world["common"], ndxFilename=str(d / "tv_a.ndx"), inputWorldFilename="wld",
+                     totalVariabilityNumber=R, totalVariabilityMatrix="TVa", loadInitTotalVariabilityMatrix="true",
+                     initTotalVariabilityMatrix="TVa", nullOrderStatSpeaker="N_a", firstOrderStatSpeaker="F_a",
+                     loadAccs="true", nbIt=0, approximationMode=mode)
+        _run("TotalVariability", d / f"tv_{mode}.cfg")
+        lf.write_db(d / "TVa.mat", T)   # nbIt = 0 re-saves the (unchanged) matrix; keep the input pristine
+        assert np.allclose(lf.read_db(d / "TVa_norm.mat"), Tn, rtol=1e-12)
+    assert np.allclose(lf.read_db(d / "TVa_weightedCov.mat"), Wcov, rtol=1e-9, atol=1e-12 * np.abs(Wcov).max())
+    Qg, Dg = lf.read_db(d / "TVa_EigDec_Q.mat"), lf.read_db(d / "TVa_EigDec_D.mat")
+    assert np.allclose(np.abs(Qg.T @ Q), np.eye(R), atol=1e-6) and np.allclose(Dg, Dm, rtol=1e-6, atol=1e-9 * Dm.max())
+    for mode, W, flag in (("ubmWeight", W_ubm, "loadUbmWeightParam"), ("eigenDecomposition", W_eig, "loadEigenDecompositionParam")):
+        os.makedirs(d / f"ivl_{mode}", exist_ok=True)
+        lf.write_cfg(d / f"ivl_{mode}.cfg", **base, saveVectorFilesPath=str(d / f"ivl_{mode}") + "/", mode=mode,
+                     loadAccs="true", **{flag: "true"})
+        _run("IvExtractor", d / f"ivl_{mode}.cfg")
+        check(f"ivl_{mode}", W)
 
 
 def test_ivtest_plda_cli(world, oracle):

@@ -195,3 +195,40 @@ def test_approximate_ivector_modes_against_numpy(oracle):
     assert np.allclose(W2, ref)
     # the reference accumulates into _W in the eigenDecomposition estimator
     assert np.allclose(oracle.tv_ivectors_eigen(N, Fn, Tn, Dm, Q, W0=W1), W1 + W2)
+
+
+def test_ivector_backend_against_numpy(oracle):
+    """PldaDev statistics / normalisation matrices and the cosine / Mahalanobis / 2cov scorings
+    (PldaTools.cpp:353-385, 527-571, 1124-1175, 1381-1415, 1853-1900, 3842-3910, 4083-4173)
+    against independent numpy algebra."""
+    rng = np.random.default_rng(1)
+    d, nspk = 8, 12
+    cls = np.repeat(np.arange(nspk), rng.integers(2, 6, nspk))
+    n = len(cls)
+    data = (rng.standard_normal((d, nspk)) * 1.5)[:, cls] + rng.standard_normal((d, n))
+    mean, sm, S, W, B = oracle.iv_cov_mat(data, cls, nspk)
+    assert np.allclose(mean, data.mean(1)) and np.allclose(S, np.cov(data, bias=True)) and np.allclose(S, W + B)
+    wc = oracle.iv_wccn_chol(data, cls, nspk)
+    Ww = np.mean([np.cov(data[:, cls == c], bias=True) for c in range(nspk)], axis=0)
+    assert np.allclose(wc.T @ wc, np.linalg.inv(Ww)) and np.allclose(wc, np.triu(wc))
+    E = oracle.iv_efr_matrix(S)
+    assert np.allclose(E @ S @ E.T, np.eye(d))
+    L = oracle.iv_lda(W, B, 3)
+    ev = np.linalg.eig(np.linalg.inv(W) @ B)
+    order = np.argsort(-ev[0].real)
+    for j in range(3):
+        v = ev[1][:, order[j]].real
+        v /= np.linalg.norm(v)
+        assert min(np.abs(L[j] - v).max(), np.abs(L[j] + v).max()) < 1e-8
+    M, Sg = data[:, :5], data[:, 5:12]
+    assert np.allclose(oracle.iv_cosine(M, Sg), (M.T @ Sg) / np.outer(np.linalg.norm(M, axis=0), np.linalg.norm(Sg, axis=0)))
+    Mah = np.linalg.inv(W)
+    ref = np.array([[-0.5 * (M[:, i] - Sg[:, j]) @ Mah @ (M[:, i] - Sg[:, j]) for j in range(7)] for i in range(5)])
+    assert np.allclose(oracle.iv_mahalanobis(M, Sg, Mah), ref)
+    iW, iB = np.linalg.inv(W), np.linalg.inv(B)
+    G, H = iW @ np.linalg.inv(iB + 2 * iW) @ iW, iW @ np.linalg.inv(iB + iW) @ iW
+    ref = np.array([[(M[:, i] + Sg[:, j]) @ G @ (M[:, i] + Sg[:, j]) - M[:, i] @ H @ M[:, i] - Sg[:, j] @ H @ Sg[:, j]
+                     for j in range(7)] for i in range(5)])
+    assert np.allclose(oracle.iv_two_cov(M, Sg, W, B), ref)
+    tr = rng.random((5, 7)) < 0.5
+    assert np.all(oracle.iv_cosine(M, Sg, tr)[~tr] == 0)
