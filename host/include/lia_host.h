@@ -234,6 +234,37 @@ class TVAcc {
   void init(const Config &c);
 };
 
+// ---- PldaDev (PldaTools.h): development i-vectors, one NDX line per speaker (every element a
+// session); statistics and normalisations run on the engine (lr_iv_*), data stays on the host
+class PldaDev {
+ public:
+  PldaDev(const std::string &ndxFilename, const Config &c);  // :97, load :274-350
+  size_t getVectSize() const { return data_.rows; }
+  size_t getSpeakerNumber() const { return nSpk_; }
+  size_t getSessionNumber() const { return data_.cols; }
+  const Matrix &getData() const { return data_; }
+  const std::vector<double> &getMean() const { return mean_; }
+  void computeAll();                                             // :353-385
+  void lengthNorm();                                             // :436-464
+  void center(const std::vector<double> &mu);                    // :466-474
+  void rotateLeft(const Matrix &M);                              // :498-514
+  void computeCovMat(Matrix &Sigma, Matrix &W, Matrix &B);       // :516-571
+  void computeWccnChol(Matrix &WCCN);                            // :1113-1175
+  void computeMahalanobis(Matrix &M);                            // :1366-1378
+  void computeLDA(Matrix &ldaMat, long ldaRank, const Config &c);  // :1381-1415 (ldaMode covariance)
+  void sphericalNuisanceNormalization(const Config &c);          // :1822-1929 (estimates, saves, applies)
+  void applySphericalNuisanceNormalization(const Config &c);     // :1931-1975
+
+ private:
+  Matrix data_;  // [vectSize x sessions]
+  std::vector<int32_t> class_;
+  size_t nSpk_ = 0;
+  std::vector<double> mean_;
+};
+// file names of the EFR / sphNorm parameters of iteration `it` (:1836-1842, :1907-1913)
+std::string efrMatrixFilename(const Config &c, unsigned long it, bool forLoad);
+std::string efrMeanFilename(const Config &c, unsigned long it, bool forLoad);
+
 // ---- drivers: int Foo(Config&) like the reference programs
 int TrainWorld(Config &c);        // LIA_SpkDet/TrainWorld/src/TrainWorld.cpp:101
 int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:90
@@ -241,7 +272,8 @@ int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:
 int IvExtractorUbmWeigth(Config &c);          // IvExtractor.cpp:151 (mode ubmWeight; the reference's spelling)
 int IvExtractorEigenDecomposition(Config &c); // IvExtractor.cpp:254 (mode eigenDecomposition)
 int TotalVariability(Config &c);  // LIA_SpkDet/TotalVariability/src/TotalVariability.cpp:71
-int IvTest(Config &c);            // LIA_SpkDet/IvTest/src/IvTest.cpp:73 (scoring = plda, native)
+int IvTest(Config &c);            // LIA_SpkDet/IvTest/src/IvTest.cpp:73 (scoring = cosine | mahalanobis | 2cov | plda native)
+int IvNorm(Config &c);            // LIA_SpkDet/IvNorm/src/IvNorm.cpp:72
 int TrainTarget(Config &c);       // LIA_SpkDet/TrainTarget/src/TrainTarget.cpp:75 (MAPOccDep)
 
 }  // namespace lia

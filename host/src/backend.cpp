@@ -1,0 +1,396 @@
+// backend.cpp -- i-vector back-end of the host mirror: PldaDev (development set statistics and
+// normalisations), the test-side normalisation chain, the cosine / Mahalanobis / two-covariance
+// branches of IvTest and the IvNorm program (LIA_SpkTools/src/PldaTools.cpp,
+// LIA_SpkDet/IvTest/src/IvTest.cpp:112-391, LIA_SpkDet/IvNorm/src/IvNorm.cpp:72-128).
+// All numerics go through the lr_iv_* entry points of the engine.
+#include <algorithm>
+#include <fstream>
+#include <iostream>
+
+#include "lia_host.h"
+
+namespace lia {
+
+namespace {
+Matrix loadVector(const std::string &path, const std::string &name, const Config &c) {
+  Matrix v;
+  v.load(path + "/" + name + c.getString("loadVectorFilesExtension", ".y"), c.getString("loadMatrixFormat", "DB"));
+  return v;
+}
+}  // namespace
+
+// ------------------------------------------------------------------ PldaDev
+PldaDev::PldaDev(const std::string &ndxFilename, const Config &c) {
+  XList list(ndxFilename);
+  auto lines = list.lines();
+  if (lines.empty()) LIA_THROW("PldaDev: empty development list " + ndxFilename);
+  // sortByElementNumber("descend") (:278)
+  std::stable_sort(lines.begin(), lines.end(),
+                   [](const std::vector<std::string> &a, const std::vector<std::string> &b) { return a.size() > b.size(); });
+  nSpk_ = lines.size();
+  size_t n = 0;
+  for (auto &l : lines) n += l.size();
+  const std::string path = c.getParam("loadVectorFilesPath");
+  const size_t d = loadVector(path, lines[0][0], c).cols;
+  data_ = Matrix(d, n);
+  class_.resize(n);
+  size_t s = 0;
+  for (size_t spk = 0; spk < lines.size(); spk++)
+    for (auto &f : lines[spk]) {
+      Matrix v = loadVector(path, f, c);
+      if (v.rows != 1 || v.cols != d) LIA_THROW("Incorrect dimension of vector to load");
+      class_[s] = (int32_t)spk;
+      for (size_t k = 0; k < d; k++) data_(k, s) = v.data[k];
+      s++;
+    }
+  computeAll();
+}
+
+void PldaDev::computeAll() {
+  mean_.assign(data_.rows, 0.0);
+  LIA_CHECK(lr_iv_cov_mat((int)data_.rows, data_.cols, data_.data.data(), class_.data(), nSpk_, mean_.data(),
+                          nullptr, nullptr, nullptr, nullptr));
+}
+void PldaDev::lengthNorm() {
+  Matrix out(data_.rows, data_.cols);
+  LIA_CHECK(lr_iv_normalize((int)data_.rows, data_.cols, data_.data.data(), nullptr, nullptr, 0, 1, out.data.data()));
+  data_ = out;
+  computeAll();
+}
+void PldaDev::center(const std::vector<double> &mu) {
+  if (mu.size() != data_.rows) LIA_THROW("PldaDev::center: mean dimension mismatch");
+  Matrix out(data_.rows, data_.cols);
+  LIA_CHECK(lr_iv_normalize((int)data_.rows, data_.cols, data_.data.data(), mu.data(), nullptr, 0, 0, out.data.data()));
+  data_ = out;
+  computeAll();
+}
+void PldaDev::rotateLeft(const Matrix &M) {
+  if (M.cols != data_.rows) LIA_THROW("Rotation dimension mismatch !");
+  Matrix out(M.rows, data_.cols);
+  LIA_CHECK(lr_iv_normalize((int)data_.rows, data_.cols, data_.data.data(), nullptr, M.data.data(), (int)M.rows, 0,
+                            out.data.data()));
+  data_ = out;
+  computeAll();
+}
+void PldaDev::computeCovMat(Matrix &Sigma, Matrix &W, Matrix &B) {
+  const size_t d = data_.rows;
+  Sigma = Matrix(d, d);
+  W = Matrix(d, d);
+  B = Matrix(d, d);
+  LIA_CHECK(lr_iv_cov_mat((int)d, data_.cols, data_.data.data(), class_.data(), nSpk_, nullptr, nullptr,
+                          Sigma.data.data(), W.data.data(), B.data.data()));
+}
+void PldaDev::computeWccnChol(Matrix &WCCN) {
+  WCCN = Matrix(data_.rows, data_.rows);
+  LIA_CHECK(lr_iv_wccn_chol((int)data_.rows, data_.cols, data_.data.data(), class_.data(), nSpk_, WCCN.data.data()));
+}
+void PldaDev::computeMahalanobis(Matrix &M) {
+  M = Matrix(data_.rows, data_.rows);
+  LIA_CHECK(lr_iv_mahalanobis_matrix((int)data_.rows, data_.cols, data_.data.data(), class_.data(), nSpk_,
+                                     M.data.data()));
+}
+void PldaDev::computeLDA(Matrix &ldaMat, long ldaRank, const Config &c) {
+  if (c.getString("ldaMode", "covariance") == "scatterMatrices")
+    LIA_THROW("computeLDA: ldaMode scatterMatrices is not implemented by this engine");
+  Matrix Sigma, W, B;
+  computeCovMat(Sigma, W, B);
+  ldaMat = Matrix((size_t)ldaRank, data_.rows);
+  LIA_CHECK(lr_iv_lda((int)data_.rows, W.data.data(), B.data.data(), (int)ldaRank, ldaMat.data.data()));
+}
+
+static std::string efrName(const Config &c, const char *baseKey, const char *baseDefault, unsigned long it, bool forLoad) {
+  const std::string mode = c.getString("ivNormEfrMode", "EFR");
+  return c.getString("matrixFilesPath", "") + mode + "_" + c.getString(baseKey, baseDefault) + std::to_string(it) +
+         c.getString(forLoad ? "loadMatrixFilesExtension" : "saveMatrixFilesExtension", "");
+}
+std::string efrMatrixFilename(const Config &c, unsigned long it, bool forLoad) {
+  return efrName(c, "ivNormEfrMatrixBaseName", "ivNormEfrMatrix_it", it, forLoad);
+}
+std::string efrMeanFilename(const Config &c, unsigned long it, bool forLoad) {
+  return efrName(c, "ivNormEfrMeanBaseName", "ivNormEfrMean_it", it, forLoad);
+}
+
+void PldaDev::sphericalNuisanceNormalization(const Config &c) {
+  const unsigned long nbIt = (unsigned long)c.getLong("ivNormIterationNb", 1);
+  const bool sph = c.getString("ivNormEfrMode", "EFR") == "sphNorm";
+  const std::string fmt = c.getString("saveMatrixFormat", "DB");
+  for (unsigned long it = 0; it < nbIt; it++) {
+    Matrix Sigma, W, B;
+    computeCovMat(Sigma, W, B);
+    const size_t d = data_.rows;
+    Matrix mat(d, d);
+    LIA_CHECK(lr_iv_efr_matrix((int)d, (sph ? W : Sigma).data.data(), mat.data.data()));
+    mat.save(efrMatrixFilename(c, it, false), fmt);
+    Matrix mean(1, d);
+    mean.data = mean_;
+    mean.save(efrMeanFilename(c, it, false), fmt);
+    // center, rotate, length-normalise in one engine call, then refresh the means (:1916-1926)
+    Matrix out(d, data_.cols);
+    LIA_CHECK(lr_iv_normalize((int)d, data_.cols, data_.data.data(), mean_.data(), mat.data.data(), (int)d, 1,
+                              out.data.data()));
+    data_ = out;
+    computeAll();
+  }
+}
+
+namespace {
+// one applySphericalNuisanceNormalization pass over a [d x n] set (PldaDev :1931-1975, PldaTest :3793-3840)
+void applyEfr(const Config &c, Matrix &X) {
+  const unsigned long nbIt = (unsigned long)c.getLong("ivNormIterationNb", 1);
+  const std::string fmt = c.getString("loadMatrixFormat", "DB");
+  for (unsigned long it = 0; it < nbIt; it++) {
+    Matrix mat, mean;
+    mat.load(efrMatrixFilename(c, it, true), fmt);
+    mean.load(efrMeanFilename(c, it, true), fmt);
+    if (mat.cols != X.rows || mean.cols != X.rows) LIA_THROW("EFR parameters do not match the vector size");
+    Matrix out(mat.rows, X.cols);
+    LIA_CHECK(lr_iv_normalize((int)X.rows, X.cols, X.data.data(), mean.data.data(), mat.data.data(), (int)mat.rows, 1,
+                              out.data.data()));
+    X = out;
+  }
+}
+void rotate(const Matrix &M, Matrix &X) {
+  if (M.cols != X.rows) LIA_THROW("Rotation dimension mismatch !");
+  Matrix out(M.rows, X.cols);
+  LIA_CHECK(lr_iv_normalize((int)X.rows, X.cols, X.data.data(), nullptr, M.data.data(), (int)M.rows, 0, out.data.data()));
+  X = out;
+}
+
+// PldaTest::load (:3437-3622): trials "segment model1 model2 ...", optional enrolment list
+// "model session1 session2 ..."; or inputVectorFilename: one list, every vector against every vector
+struct TestData {
+  std::vector<std::string> modelIds, enrolSessions, segIds;
+  std::vector<int32_t> modelOf;
+  std::map<std::string, int> modelIndex, segIndex;
+  std::vector<std::vector<std::string>> trialLines;
+  Matrix models, segments;  // [d x enrol sessions], [d x segments]
+  std::vector<uint8_t> trials;
+  bool fromVectorList = false;
+
+  explicit TestData(const Config &c) {
+    std::string vpath;
+    if (c.existsParam("inputVectorFilename")) {
+      fromVectorList = true;
+      vpath = c.getParam("loadVectorFilesPath");
+      XList all(c.getParam("inputVectorFilename"));
+      for (auto &e : all.allElements()) {
+        modelIndex[e] = (int)modelIds.size();
+        modelIds.push_back(e);
+        enrolSessions.push_back(e);
+        modelOf.push_back(modelIndex[e]);
+        segIndex[e] = (int)segIds.size();
+        segIds.push_back(e);
+      }
+    } else {
+      vpath = c.getParam("testVectorFilesPath");
+      XList tr(c.getParam("ndxFilename"));
+      trialLines = tr.lines();
+      if (c.existsParam("targetIdList") && !c.getParam("targetIdList").empty()) {
+        XList enrol(c.getParam("targetIdList"));
+        auto lines = enrol.lines();
+        std::stable_sort(lines.begin(), lines.end(), [](const std::vector<std::string> &a,
+                                                        const std::vector<std::string> &b) { return a.size() > b.size(); });
+        for (auto &l : lines) {
+          if (!modelIndex.count(l[0])) {
+            modelIndex[l[0]] = (int)modelIds.size();
+            modelIds.push_back(l[0]);
+          }
+          for (size_t e = 1; e < l.size(); e++) {
+            enrolSessions.push_back(l[e]);
+            modelOf.push_back(modelIndex[l[0]]);
+          }
+        }
+      }
+      for (auto &l : trialLines) {
+        if (!segIndex.count(l[0])) {
+          segIndex[l[0]] = (int)segIds.size();
+          segIds.push_back(l[0]);
+        }
+        for (size_t e = 1; e < l.size(); e++)
+          if (!modelIndex.count(l[e])) {  // a model without enrolment list is its own single session
+            modelIndex[l[e]] = (int)modelIds.size();
+            modelIds.push_back(l[e]);
+            enrolSessions.push_back(l[e]);
+            modelOf.push_back(modelIndex[l[e]]);
+          }
+      }
+    }
+    if (enrolSessions.empty() || segIds.empty()) LIA_THROW("PldaTest: no trial to score");
+    const size_t d = loadVector(vpath, enrolSessions[0], c).cols;
+    models = Matrix(d, enrolSessions.size());
+    segments = Matrix(d, segIds.size());
+    for (size_t j = 0; j < enrolSessions.size(); j++) {
+      Matrix v = loadVector(vpath, enrolSessions[j], c);
+      for (size_t i = 0; i < d; i++) models(i, j) = v.data[i];
+    }
+    for (size_t j = 0; j < segIds.size(); j++) {
+      Matrix v = loadVector(vpath, segIds[j], c);
+      for (size_t i = 0; i < d; i++) segments(i, j) = v.data[i];
+    }
+    trials.assign(modelIds.size() * segIds.size(), fromVectorList ? 1 : 0);
+    for (auto &l : trialLines)
+      for (size_t e = 1; e < l.size(); e++) trials[(size_t)modelIndex[l[e]] * segIds.size() + segIndex[l[0]]] = 1;
+  }
+  // test-side normalisation (IvTest.cpp:301-318, IvNorm.cpp:101-112)
+  void normalize(const Config &c) {
+    if (!c.getBool("ivNorm", false)) return;
+    if (c.getLong("ivNormIterationNb", 1) > 0) {
+      applyEfr(c, models);
+      applyEfr(c, segments);
+    }
+    if (c.getBool("LDA", false)) {
+      Matrix lda;
+      lda.load(c.getString("matrixFilesPath", "") + c.getParam("ldaMatrix") + c.getString("loadMatrixFilesExtension", ""),
+               c.getString("loadMatrixFormat", "DB"));
+      rotate(lda, models);
+      rotate(lda, segments);
+    }
+  }
+};
+
+void saveColumns(const Matrix &X, const std::vector<std::string> &names, const std::string &dir, const Config &c) {
+  for (size_t j = 0; j < names.size(); j++) {
+    Matrix v(1, X.rows);
+    for (size_t i = 0; i < X.rows; i++) v(0, i) = X(i, j);
+    v.save(dir + "/" + names[j] + c.getString("vectorFilesExtension", c.getString("loadVectorFilesExtension", ".y")),
+           c.getString("saveMatrixFormat", "DB"));
+  }
+}
+
+// development-side estimation shared by IvTest and IvNorm (IvTest.cpp:131-180, IvNorm.cpp:79-98)
+void estimateNormalisation(PldaDev &dev, const Config &c) {
+  if (!c.getBool("ivNormLoadParam", false)) {
+    if (c.getLong("ivNormIterationNb", 1) > 0) dev.sphericalNuisanceNormalization(c);
+    if (c.getBool("LDA", false)) {
+      Matrix lda;
+      dev.computeLDA(lda, c.getLong("ldaRank"), c);
+      dev.rotateLeft(lda);
+      lda.save(c.getString("matrixFilesPath", "") + c.getParam("ldaMatrix") + c.getString("loadMatrixFilesExtension", ""),
+               c.getString("saveMatrixFormat", "DB"));
+    }
+  } else {
+    if (c.getLong("ivNormIterationNb", 1) > 0) dev.applySphericalNuisanceNormalization(c);
+    if (c.getBool("LDA", false)) {
+      Matrix lda;
+      lda.load(c.getString("matrixFilesPath", "") + c.getParam("ldaMatrix") + c.getString("loadMatrixFilesExtension", ""),
+               c.getString("loadMatrixFormat", "DB"));
+      dev.rotateLeft(lda);
+    }
+  }
+}
+}  // namespace
+
+void PldaDev::applySphericalNuisanceNormalization(const Config &c) {
+  applyEfr(c, data_);
+  computeAll();
+}
+
+// the cosine / mahalanobis / 2cov branches of IvTest (IvTest.cpp:112-391); returns the score
+// matrix [models x segments] and fills ids / trial lines for the NIST output written by the caller
+bool IvTestNonPlda(Config &c, const std::string &scoring, Matrix &scores, std::vector<std::vector<std::string>> &trialLines,
+                   std::map<std::string, int> &modelIndex, std::map<std::string, int> &segIndex) {
+  const std::string mpath = c.getString("matrixFilesPath", "");
+  const std::string lext = c.getString("loadMatrixFilesExtension", ""), sext = c.getString("saveMatrixFilesExtension", "");
+  const std::string lfmt = c.getString("loadMatrixFormat", "DB"), sfmt = c.getString("saveMatrixFormat", "DB");
+  const bool wccn = c.getBool("wccn", false);
+  const bool computeWccn = wccn && c.existsParam("loadWccnMatrix") && !c.getBool("loadWccnMatrix", false);
+  const bool loadMah = scoring == "mahalanobis" && c.getBool("loadMahalanobisMatrix", false);
+  const bool loadWccn = scoring == "cosine" && wccn && c.getBool("loadWccnMatrix", false);
+  const bool load2cov = scoring == "2cov" && c.getBool("load2covMatrix", false);
+  const bool ivNorm = c.getBool("ivNorm", false);
+  const std::string wccnFile = mpath + c.getString("wccnMatrix", "WCCN") + lext;
+  std::string w2 = "2Cov_W", b2 = "2Cov_B";
+  if (c.existsParam("TwoCovFilename")) {
+    w2 = c.getParam("TwoCovFilename") + "_W";
+    b2 = c.getParam("TwoCovFilename") + "_B";
+  }
+  auto mahFile = [&](const std::string &ext) {
+    return c.existsParam("mahalanobisMatrix") ? mpath + c.getParam("mahalanobisMatrix") + ext : std::string("Mahalanobis");
+  };
+
+  TestData test(c);
+  if ((ivNorm && !c.getBool("ivNormLoadParam", false)) || (scoring == "mahalanobis" && !loadMah) ||
+      (wccn && !loadWccn) || (scoring == "2cov" && !load2cov)) {
+    PldaDev dev(c.getParam("backgroundNdxFilename"), c);
+    if (ivNorm) estimateNormalisation(dev, c);
+    if (computeWccn) {
+      Matrix W;
+      dev.computeWccnChol(W);
+      W.save(wccnFile, sfmt);
+    }
+    if (scoring == "mahalanobis") {
+      Matrix M;
+      dev.computeMahalanobis(M);
+      M.save(mahFile(sext), sfmt);
+    }
+    if (scoring == "2cov") {
+      Matrix Sigma, W, B;
+      dev.computeCovMat(Sigma, W, B);
+      W.save(mpath + w2 + sext, sfmt);
+      B.save(mpath + b2 + sext, sfmt);
+    }
+  }
+  test.normalize(c);
+  const size_t d = test.models.rows, nm = test.modelIds.size(), nt = test.segIds.size();
+  if (test.models.cols != nm)
+    LIA_THROW("scoring " + scoring + " takes one enrolment vector per model (PldaTools.cpp:3842-3910 index _models by model)");
+  scores = Matrix(nm, nt);
+  if (scoring == "cosine") {
+    if (wccn) {
+      Matrix W;
+      W.load(wccnFile, lfmt);
+      rotate(W, test.models);
+      rotate(W, test.segments);
+    }
+    LIA_CHECK(lr_iv_cosine_scoring((int)test.models.rows, nm, nt, test.models.data.data(), test.segments.data.data(),
+                                   test.trials.data(), scores.data.data()));
+  } else if (scoring == "mahalanobis") {
+    Matrix M;
+    M.load(mahFile(lext), lfmt);
+    if (M.rows != d || M.cols != d) LIA_THROW("Mahalanobis matrix does not match the vector size");
+    LIA_CHECK(lr_iv_mahalanobis_scoring((int)d, nm, nt, test.models.data.data(), test.segments.data.data(),
+                                        M.data.data(), test.trials.data(), scores.data.data()));
+  } else {
+    Matrix W, B;
+    W.load(mpath + w2 + lext, lfmt);
+    B.load(mpath + b2 + lext, lfmt);
+    if (W.rows != d || B.rows != d) LIA_THROW("two-covariance matrices do not match the vector size");
+    LIA_CHECK(lr_iv_two_cov_scoring((int)d, nm, nt, test.models.data.data(), test.segments.data.data(), W.data.data(),
+                                    B.data.data(), scores.data.data()));
+  }
+  trialLines = test.trialLines;
+  modelIndex = test.modelIndex;
+  segIndex = test.segIndex;
+  return true;
+}
+
+// ------------------------------------------------------------------ IvNorm (IvNorm.cpp:72-128)
+int IvNorm(Config &c) {
+  try {
+    if (!c.getBool("ivNormLoadParam", false)) {
+      PldaDev dev(c.getString("backgroundNdxFilename", ""), c);
+      if (c.getLong("ivNormIterationNb", 1) > 0) dev.sphericalNuisanceNormalization(c);
+      if (c.getBool("LDA", false)) {
+        Matrix lda;
+        dev.computeLDA(lda, c.getLong("ldaRank"), c);
+        lda.save(c.getString("matrixFilesPath", "") + c.getParam("ldaMatrix") + c.getString("loadMatrixFilesExtension", ""),
+                 c.getString("saveMatrixFormat", "DB"));
+      }
+    }
+    if (c.existsParam("inputVectorFilename") || c.existsParam("ndxFilename")) {
+      TestData test(c);
+      Config apply = c;
+      apply.setParam("ivNorm", "true");
+      test.normalize(apply);
+      const std::string out = c.getParam("saveVectorFilesPath");
+      saveColumns(test.segments, test.segIds, out, c);  // saveSegments (:4712-4731)
+      if (!(c.existsParam("inputVectorFilename") && !c.existsParam("targetIdList")))
+        saveColumns(test.models, test.enrolSessions, out, c);  // saveVectors (:4734-)
+    }
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+}  // namespace lia

@@ -315,13 +315,33 @@ int TotalVariability(Config &c) {
   return 0;
 }
 
-// ------------------------------------------------------------------ IvTest (scoring = plda, native)
+// ------------------------------------------------------------------ IvTest
+// cosine / mahalanobis / 2cov branches live in backend.cpp
+bool IvTestNonPlda(Config &c, const std::string &scoring, Matrix &scores, std::vector<std::vector<std::string>> &trialLines,
+                   std::map<std::string, int> &modelIndex, std::map<std::string, int> &segIndex);
+
 int IvTest(Config &c) {
   try {
     const std::string scoring = c.getString("scoring", "plda");
-    if (scoring != "plda") LIA_THROW("this engine implements scoring = plda (native); got " + scoring);
     const std::string gender = c.getString("gender", "M");
     const double threshold = c.getDouble("decisionThreshold", 0.0);
+    if (scoring == "cosine" || scoring == "mahalanobis" || scoring == "2cov") {
+      Matrix sc;
+      std::vector<std::vector<std::string>> lines;
+      std::map<std::string, int> mi, si;
+      IvTestNonPlda(c, scoring, sc, lines, mi, si);
+      std::ofstream out(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
+      for (auto &l : lines)
+        for (size_t e = 1; e < l.size(); e++) {
+          const double v = sc(mi[l[e]], si[l[0]]);
+          outputResultLine(v, l[e], l[0], gender, setDecision(v, threshold), out);
+        }
+      return 0;
+    }
+    if (scoring != "plda") {
+      std::cout << "Scoring option is invalid, must be: cosine OR mahalanobis OR 2cov OR plda" << std::endl;
+      return 0;
+    }
     const std::string vpath = c.getParam("testVectorFilesPath") + "/", vext = c.getString("loadVectorFilesExtension", ".y");
     const std::string mpath = c.getString("matrixFilesPath", ""), mext = c.getString("loadMatrixFilesExtension", "");
     const std::string mfmt = c.getString("loadMatrixFormat", "DB");

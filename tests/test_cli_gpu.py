@@ -263,6 +263,82 @@ def test_ivtest_plda_cli(world, oracle):
         assert abs(float(l[4]) - ref[m, s]) < 1e-5 * max(1.0, abs(ref[m, s]))
 
 
+def test_ivtest_backend_and_ivnorm_cli(world, oracle):
+    """IvTest scoring = cosine (+ WCCN) / mahalanobis / 2cov with EFR + LDA normalisation estimated on
+    a development list (IvTest.cpp:112-391), and the IvNorm program (IvNorm.cpp:72-128), against the
+    restated PldaTools.cpp loops."""
+    d = world["dir"]
+    dim, n_spk = 12, 30
+    rng = np.random.default_rng(97)
+    sizes = rng.integers(2, 6, n_spk)
+    spk = rng.standard_normal((dim, n_spk)) * 1.5
+    os.makedirs(d / "bvec", exist_ok=True)
+    dev_lines, cols = [], []
+    for sidx in np.argsort(-sizes, kind="stable"):          # the reference sorts speakers by session count
+        names = []
+        for j in range(sizes[sidx]):
+            v = spk[:, sidx] + rng.standard_normal(dim) + 0.4
+            names.append(f"dev{sidx}_{j}")
+            cols.append((v, len(dev_lines)))
+            lf.write_db(d / "bvec" / f"{names[-1]}.y", v[None])
+        dev_lines.append(names)
+    order = rng.permutation(len(dev_lines))                 # ... whatever the order in the file
+    lf.write_lines(d / "dev.ndx", [dev_lines[i] for i in order])
+    data = np.stack([c[0] for c in cols], axis=1)
+    cls = np.array([c[1] for c in cols], dtype=np.int32)
+    models = rng.standard_normal((dim, 4)) + 0.4
+    segments = rng.standard_normal((dim, 6)) + 0.4
+    for j in range(4):
+        lf.write_db(d / "bvec" / f"bm{j}.y", models[:, j][None])
+    for j in range(6):
+        lf.write_db(d / "bvec" / f"bt{j}.y", segments[:, j][None])
+    trials = [[f"bt{j}"] + [f"bm{m}" for m in range(4) if (m + j) % 3 != 0] for j in range(6)]
+    lf.write_lines(d / "btrials.ndx", trials)
+
+    # the reference chain: EFR iteration (center, whiten, length-norm) then LDA, estimated on the dev set
+    mean, _, S, _, _ = oracle.iv_cov_mat(data, cls, n_spk)
+    E = oracle.iv_efr_matrix(S)
+    norm = lambda X: oracle.iv_length_norm(oracle.iv_rotate_left(E, oracle.iv_center(X, mean)))
+    dev1 = norm(data)
+    _, _, _, W1, B1 = oracle.iv_cov_mat(dev1, cls, n_spk)
+    lda = oracle.iv_lda(W1, B1, 8)
+    dev2 = oracle.iv_rotate_left(lda, dev1)
+    m2, s2 = oracle.iv_rotate_left(lda, norm(models)), oracle.iv_rotate_left(lda, norm(segments))
+    _, _, _, W2, B2 = oracle.iv_cov_mat(dev2, cls, n_spk)
+    wccn = oracle.iv_wccn_chol(dev2, cls, n_spk)
+    refs = {"cosine": oracle.iv_cosine(oracle.iv_rotate_left(wccn, m2), oracle.iv_rotate_left(wccn, s2)),
+            "mahalanobis": oracle.iv_mahalanobis(m2, s2, oracle.invert(W2)),
+            "2cov": oracle.iv_two_cov(m2, s2, W2, B2)}
+    base = dict(world["common"], ndxFilename=str(d / "btrials.ndx"), testVectorFilesPath=str(d / "bvec"),
+                loadVectorFilesPath=str(d / "bvec"), loadVectorFilesExtension=".y", backgroundNdxFilename=str(d / "dev.ndx"),
+                ivNorm="true", ivNormLoadParam="false", ivNormIterationNb=1, ivNormEfrMode="EFR", LDA="true", ldaRank=8,
+                ldaMatrix="ldaB", gender="M", wccn="true", loadWccnMatrix="false", loadMahalanobisMatrix="false",
+                mahalanobisMatrix="MahB", load2covMatrix="false", TwoCovFilename="TwoCovB")
+    for scoring, ref in refs.items():
+        lf.write_cfg(d / f"bk_{scoring}.cfg", **base, scoring=scoring, outputFilename=str(d / f"bk_{scoring}.res"))
+        _run("IvTest", d / f"bk_{scoring}.cfg")
+        lines = [l.split() for l in open(d / f"bk_{scoring}.res")]
+        assert len(lines) == sum(len(t) - 1 for t in trials)
+        for l in lines:
+            m, sg = int(l[1][2:]), int(l[3][2:])
+            assert abs(float(l[4]) - ref[m, sg]) < 1e-5 * max(1.0, np.abs(ref).max()), (scoring, l)
+    assert np.allclose(lf.read_db(d / "EFR_ivNormEfrMatrix_it0.mat"), E, atol=1e-7 * np.abs(E).max())
+    assert np.allclose(lf.read_db(d / "EFR_ivNormEfrMean_it0.mat")[0], mean)
+    # second run loading every parameter the first one saved: same scores
+    lf.write_cfg(d / "bk_load.cfg", **dict(base, ivNormLoadParam="true", loadMahalanobisMatrix="true"),
+                 scoring="mahalanobis", outputFilename=str(d / "bk_load.res"))
+    _run("IvTest", d / "bk_load.cfg")
+    assert open(d / "bk_load.res").read() == open(d / "bk_mahalanobis.res").read()
+    # IvNorm: normalise a plain list of vectors with the saved parameters
+    lf.write_lines(d / "bvlist.lst", [[f"bt{j}"] for j in range(6)])
+    os.makedirs(d / "bnorm", exist_ok=True)
+    lf.write_cfg(d / "ivnorm.cfg", **dict(base, ivNormLoadParam="true"), inputVectorFilename=str(d / "bvlist.lst"),
+                 saveVectorFilesPath=str(d / "bnorm"), vectorFilesExtension=".y")
+    _run("IvNorm", d / "ivnorm.cfg")
+    for j in range(6):
+        assert np.allclose(lf.read_db(d / "bnorm" / f"bt{j}.y")[0], s2[:, j], atol=1e-7)
+
+
 def test_train_target_cli(world, oracle):
     """TrainTarget with MAPOccDep (mean + weight adaptation, 2 iterations) against the oracle's EM
     statistics + the numpy restatement of computeMAPOccDep (TrainTools.cpp:445-489, 871-904)."""
