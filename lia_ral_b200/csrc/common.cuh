@@ -26,7 +26,7 @@ struct Engine {
   int gmm_kernel = 0;  // 0 auto, 1 simt, 2 tcgen05
   int tc_debug = 0;    // profiling experiments only (lr_debug_flags): results are WRONG when set
   // grow-only device scratch slots reused across calls (freed by lr_shutdown)
-  static constexpr int kScratchSlots = 12;
+  static constexpr int kScratchSlots = 13;
   void *scratch[kScratchSlots] = {};
   size_t scratch_cap[kScratchSlots] = {};
   cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
@@ -45,7 +45,7 @@ struct ProfileScope {
 
 enum ScratchSlot {
   kSlotX0 = 0, kSlotX1, kSlotLse, kSlotIndex, kSlotChunks, kSlotS, kSlotStats, kSlotLlk,
-  kSlotIdx, kSlotRest, kSlotTmpA, kSlotTmpB
+  kSlotIdx, kSlotRest, kSlotTmpA, kSlotTmpB, kSlotSpans
 };
 // returns nullptr (and sets the error) on allocation failure
 void *scratch_get(int slot, size_t bytes);

@@ -12,11 +12,34 @@ namespace {
 
 constexpr long kBlockFrames = 1L << 18;  // frames per staged block (63 MB at D = 60)
 
+// positions [pos, pos + len) of the frame list map to the frames begin, begin + 1, ...; positions
+// covered by no span are padding.  The per-position index is expanded ON THE DEVICE from the spans
+// (k_expand_index): a host loop over every frame cost more than the kernels it feeds.
+struct Span {
+  long long pos, begin, len;
+};
+
 struct Plan {
-  std::vector<unsigned> index;  // empty -> identity
+  std::vector<Span> spans;  // empty -> identity
   std::vector<LrChunk> chunks;
   long P = 0;
 };
+
+__global__ void k_expand_index(const Span *__restrict__ spans, int n, long P,
+                               unsigned *__restrict__ index) {
+  long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int lo = 0, hi = n - 1;  // last span starting at or before p
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (spans[mid].pos <= p)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const long long off = p - spans[lo].pos;
+  index[p] = (off >= 0 && off < spans[lo].len) ? (unsigned)(spans[lo].begin + off) : kPadFrame;
+}
 
 struct Clip {
   int row;
@@ -30,15 +53,12 @@ struct Clip {
 // to a whole number of 128-frame tiles, so chunks are tile aligned.
 void build_plan(const lr_seg *segs, size_t n_segs, long b0, long b1, long base, bool use_rows,
                 bool pad, Plan &plan) {
-  plan.index.clear();
+  plan.spans.clear();
   plan.chunks.clear();
   plan.P = 0;
   if (!segs) {
     plan.P = b1 - b0;
-    if (b0 != base) {
-      plan.index.resize(plan.P);
-      for (long p = 0; p < plan.P; p++) plan.index[p] = (unsigned)(b0 - base + p);
-    }
+    if (b0 != base) plan.spans.push_back({0, b0 - base, plan.P});
     for (long p = 0; p < plan.P; p += kChunkFrames)
       plan.chunks.push_back({p, (int)std::min<long>(kChunkFrames, plan.P - p), 0});
     return;
@@ -50,28 +70,23 @@ void build_plan(const lr_seg *segs, size_t n_segs, long b0, long b1, long base, 
   }
   std::stable_sort(clips.begin(), clips.end(),
                    [](const Clip &a, const Clip &b) { return a.row < b.row; });
-  size_t total = 0;
-  for (auto &c : clips) total += (size_t)c.len;
-  plan.index.reserve(total + (pad ? 128 * (clips.size() + 1) : 0));
+  plan.spans.reserve(clips.size());
   long pos = 0;
   size_t i = 0;
   while (i < clips.size()) {
     int row = clips[i].row;
     long row_start = pos;
     while (i < clips.size() && clips[i].row == row) {
-      for (long k = 0; k < clips[i].len; k++) plan.index.push_back((unsigned)(clips[i].begin + k));
+      plan.spans.push_back({pos, clips[i].begin, clips[i].len});
       pos += clips[i].len;
       i++;
     }
     for (long p = row_start; p < pos; p += kChunkFrames)
       plan.chunks.push_back({p, (int)std::min<long>(kChunkFrames, pos - p), row});
-    if (pad)
-      while (pos % 128) {
-        plan.index.push_back(kPadFrame);
-        pos++;
-      }
+    if (pad) pos = (pos + 127) / 128 * 128;  // the gap up to the next tile is padding
   }
   plan.P = pos;
+  if (plan.spans.empty() && plan.P > 0) plan.spans.push_back({0, 0, 0});  // all padding
 }
 
 lr_status check_segs(const lr_seg *segs, size_t n_segs, size_t T, size_t U, bool use_rows) {
@@ -91,27 +106,21 @@ lr_status run_plan(lr_gmm *g, const float *dX, size_t ldx, const Plan &plan, boo
                    double *dN, double *dF, double *dS2, double *d_llk_sum) {
   if (plan.P == 0) return LR_OK;
   Engine &e = engine();
-  if (tc) {
-    unsigned *d_index = nullptr;
-    if (!plan.index.empty()) {
-      d_index = (unsigned *)scratch_get(kSlotIndex, plan.index.size() * sizeof(unsigned));
-      if (!d_index) return LR_ERR_CUDA;
-      LR_CUDA(cudaMemcpyAsync(d_index, plan.index.data(), plan.index.size() * sizeof(unsigned),
-                              cudaMemcpyHostToDevice, e.stream));
-    }
-    FrameList fl{dX, ldx, d_index, plan.P};
-    return tc_run_stats(g, fl, plan.chunks, fw, dN, dF, dS2, d_llk_sum);
-  }
-  float *d_lse = (float *)scratch_get(kSlotLse, (plan.P + 128) * sizeof(float));
-  if (!d_lse) return LR_ERR_CUDA;
   unsigned *d_index = nullptr;
-  if (!plan.index.empty()) {
-    d_index = (unsigned *)scratch_get(kSlotIndex, plan.index.size() * sizeof(unsigned));
-    if (!d_index) return LR_ERR_CUDA;
-    LR_CUDA(cudaMemcpyAsync(d_index, plan.index.data(), plan.index.size() * sizeof(unsigned),
+  if (!plan.spans.empty()) {
+    d_index = (unsigned *)scratch_get(kSlotIndex, (size_t)plan.P * sizeof(unsigned));
+    Span *d_spans = (Span *)scratch_get(kSlotSpans, plan.spans.size() * sizeof(Span));
+    if (!d_index || !d_spans) return LR_ERR_CUDA;
+    LR_CUDA(cudaMemcpyAsync(d_spans, plan.spans.data(), plan.spans.size() * sizeof(Span),
                             cudaMemcpyHostToDevice, e.stream));
+    k_expand_index<<<(unsigned)((plan.P + 255) / 256), 256, 0, e.stream>>>(d_spans, (int)plan.spans.size(),
+                                                                          plan.P, d_index);
+    LR_CHECK_LAUNCH();
   }
   FrameList fl{dX, ldx, d_index, plan.P};
+  if (tc) return tc_run_stats(g, fl, plan.chunks, fw, dN, dF, dS2, d_llk_sum);
+  float *d_lse = (float *)scratch_get(kSlotLse, (plan.P + 128) * sizeof(float));
+  if (!d_lse) return LR_ERR_CUDA;
   lr_status st = gmm_pass_lse(g, fl, d_lse, nullptr, d_llk_sum);
   if (st != LR_OK) return st;
   if (dN || dF || dS2) {
@@ -122,6 +131,17 @@ lr_status run_plan(lr_gmm *g, const float *dX, size_t ldx, const Plan &plan, boo
     st = gmm_pass_acc(g, fl, d_lse, d_chunks, (int)plan.chunks.size(), fw, dN, dF, dS2);
   }
   return st;
+}
+
+// Device-resident frames are processed in blocks of at most 2^22 frames (2 GB of fp16 hi/lo
+// operand + 0.5 GB of per-slice partials); the range is cut into EQUAL blocks so that no launch is
+// a short tail (multiple of 128 frames: tile aligned for the identity frame list).
+long dev_block_step(long lo, long hi) {
+  const long kMax = 1L << 22;
+  const long total = std::max<long>(hi - lo, 1);
+  const long n_blocks = (total + kMax - 1) / kMax;
+  const long step = (total + n_blocks - 1) / n_blocks;
+  return (step + 127) / 128 * 128;
 }
 
 // Frame range touched by the segments (or [0, T) without segments).
@@ -229,7 +249,7 @@ lr_status lr_gmm_em_accumulate_dev(lr_gmm *g, const lr_feats *f, size_t t0, size
   lr_status sel = LR_OK;
   const bool tc = tc_selected(g, &sel);
   if (sel != LR_OK) return sel;
-  const long step = 1L << 21;
+  const long step = dev_block_step((long)t0, (long)(t0 + T));
   for (long b0 = (long)t0; b0 < (long)(t0 + T); b0 += step) {
     long b1 = std::min<long>((long)(t0 + T), b0 + step);
     build_plan(nullptr, 0, b0, b1, b0, false, tc, plan);
@@ -291,7 +311,7 @@ lr_status lr_gmm_bwstats_dev(lr_gmm *g, const lr_feats *f, const lr_seg *segs, s
   lr_status sel = LR_OK;
   const bool tc = tc_selected(g, &sel);
   if (sel != LR_OK) return sel;
-  const long step = 1L << 21;
+  const long step = dev_block_step(lo, hi);
   for (long b0 = lo; b0 < hi; b0 += step) {
     long b1 = std::min(hi, b0 + step);
     build_plan(segs, n_segs, b0, b1, 0, true, tc, plan);
