@@ -408,6 +408,20 @@ class Oracle:
             raise ArithmeticError("singular Sigma")
         return scores
 
+    def plda_em_iteration(self, data, class_of, n_spk, F, G, Sigma, Delta):
+        """One PldaModel::em_iteration -> (data centred, F, G, Sigma, Delta)."""
+        data, F, Sigma, Delta = _f64(data).copy(), _f64(F).copy(), _f64(Sigma).copy(), _f64(Delta).copy()
+        d, n = data.shape
+        rF = F.shape[1]
+        rG = 0 if G is None else G.shape[1]
+        G = np.zeros((d, 0)) if G is None else _f64(G).copy()
+        cls = np.ascontiguousarray(class_of, dtype=np.int32)
+        rc = self.lib.orc_plda_em_iteration(d, rF, rG, ct.c_size_t(n), _d(data), cls.ctypes.data_as(c_ip),
+                                            ct.c_size_t(n_spk), _d(F), _d(G) if rG else None, _d(Sigma), _d(Delta))
+        if rc != 0:
+            raise ArithmeticError("PLDA EM: singular matrix")
+        return data, F, G, Sigma, Delta
+
     def invert(self, a):
         a = _f64(a)
         out = np.empty_like(a)

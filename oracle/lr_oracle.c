@@ -1276,3 +1276,175 @@ int orc_iv_two_cov(int d, size_t nm, size_t nt, const double *models, const doub
   free(G); free(H); free(mds); free(sds); free(a); free(diff);
   return rc;
 }
+
+/* ====================================================================== PLDA EM training
+ * PldaModel::em_iteration, PldaTools.cpp:2329-2343: _Dev.center(_Delta), computeCovMatEigen
+ * (:931-950, the un-normalised scatter), getExpectedValuesUnThreaded (:2359-2485) and mStep
+ * (:2790-2813), restated without Eigen.  data[d x n] is centred in place; class_of is
+ * non-decreasing (sessions of a speaker are adjacent, :2428-2434).  F[d x rF], G[d x rG],
+ * Sigma[d x d], Delta[d] are updated in place.  The EigenSolver / dgeev call on the symmetric
+ * matrix A (:2377-2400) is the cyclic Jacobi solver here. */
+static void mm(int m, int n, int k, const double *A, int ta, const double *B, int tb, double *Cm) {
+  /* Cm[m x n] = op(A) op(B); A is [m x k] (or [k x m] when ta), B is [k x n] (or [n x k] when tb) */
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) {
+      double t = 0.0;
+      for (int l = 0; l < k; l++) t += (ta ? A[(size_t)l * m + i] : A[(size_t)i * k + l]) * (tb ? B[(size_t)j * k + l] : B[(size_t)l * n + j]);
+      Cm[(size_t)i * n + j] = t;
+    }
+}
+
+int orc_plda_em_iteration(int d, int rF, int rG, size_t n, double *data, const int32_t *class_of,
+                          size_t n_spk, double *F, double *G, double *Sigma, double *Delta) {
+  const int r = rF + rG;
+  int rc = 0;
+#define NEW(count) ((double *)calloc((size_t)(count) > 0 ? (size_t)(count) : 1, sizeof(double)))
+  /* _Dev.center(_Delta) */
+  for (size_t s = 0; s < n; s++)
+    for (int k = 0; k < d; k++) data[(size_t)k * n + s] -= Delta[k];
+  /* computeCovMatEigen: sigmaObs = X X^T */
+  double *sigmaObs = NEW((size_t)d * d);
+  for (int i = 0; i < d; i++)
+    for (int j = i; j < d; j++) {
+      double t = 0.0;
+      for (size_t s = 0; s < n; s++) t += data[(size_t)i * n + s] * data[(size_t)j * n + s];
+      sigmaObs[i * d + j] = sigmaObs[j * d + i] = t;
+    }
+  /* preComputation :2950-2972 */
+  double *iS = NEW((size_t)d * d), *Ftw = NEW((size_t)rF * d), *Gtw = NEW((size_t)rG * d);
+  double *GtwG = NEW((size_t)rG * rG), *FtwG = NEW((size_t)rF * rG), *iGG = NEW((size_t)rG * rG);
+  rc |= orc_invert(d, Sigma, iS);
+  mm(rF, d, d, F, 1, iS, 0, Ftw);
+  mm(rG, d, d, G, 1, iS, 0, Gtw);
+  mm(rG, rG, d, Gtw, 0, G, 0, GtwG);
+  mm(rF, rG, d, Ftw, 0, G, 0, FtwG);
+  for (int i = 0; i < rG; i++) GtwG[i * rG + i] += 1.0;
+  if (rG > 0) rc |= orc_invert(rG, GtwG, iGG);
+  /* :2370-2373 */
+  double *FtwF = NEW((size_t)rF * rF), *S = NEW((size_t)rG * rF), *A = NEW((size_t)rF * rF), *tmp = NEW((size_t)rF * rG);
+  mm(rF, rF, d, Ftw, 0, F, 0, FtwF);
+  mm(rG, rF, rG, iGG, 0, FtwG, 1, S);
+  mm(rF, rG, rG, FtwG, 0, iGG, 0, tmp);
+  mm(rF, rF, rG, tmp, 0, FtwG, 1, A);
+  for (int i = 0; i < rF * rF; i++) A[i] = FtwF[i] - A[i];
+  for (int i = 0; i < rF; i++)
+    for (int j = i + 1; j < rF; j++) A[i * rF + j] = A[j * rF + i] = 0.5 * (A[i * rF + j] + A[j * rF + i]);
+  double *V = NEW((size_t)rF * rF), *Dv = NEW(rF);
+  orc_eigen_sym(rF, A, rF, V, Dv);
+  /* accumulators :2403-2405 */
+  double *Ehh = NEW((size_t)r * r), *xh = NEW((size_t)d * r), *U = NEW(r);
+  double *M = NEW((size_t)rF * rF), *MsT = NEW((size_t)rF * rG), *SMsT = NEW((size_t)rG * rG);
+  size_t curNb = 0, sc = 0;
+  for (size_t spk = 0; spk < n_spk && sc < n; spk++) {
+    const size_t first = sc;
+    const int32_t cls = class_of[sc];
+    while (sc < n && class_of[sc] == cls) sc++;
+    const size_t ns = sc - first;
+    if (ns != curNb) { /* :2417-2427 */
+      curNb = ns;
+      for (int i = 0; i < rF; i++)
+        for (int j = 0; j < rF; j++) {
+          double t = 0.0;
+          for (int k = 0; k < rF; k++) t += V[i * rF + k] * V[j * rF + k] / ((double)ns * Dv[k] + 1.0);
+          M[i * rF + j] = t;
+        }
+      mm(rF, rG, rF, M, 0, S, 1, MsT);
+      mm(rG, rG, rF, S, 0, MsT, 0, SMsT);
+    }
+    /* Sigma_x, fi, gi :2436-2451 */
+    double *Sx = NEW((size_t)d * ns), *fi = NEW((size_t)rF * ns), *gi = NEW((size_t)rG * ns);
+    double *f = NEW(rF), *g = NEW(rG), *eh = NEW(rF), *v = NEW(rF), *Eh = NEW((size_t)r * ns);
+    for (int i = 0; i < d; i++)
+      for (size_t j = 0; j < ns; j++) {
+        double t = 0.0;
+        for (int k = 0; k < d; k++) t += iS[i * d + k] * data[(size_t)k * n + first + j];
+        Sx[(size_t)i * ns + j] = t;
+      }
+    mm(rF, (int)ns, d, F, 1, Sx, 0, fi);
+    mm(rG, (int)ns, d, G, 1, Sx, 0, gi);
+    for (int i = 0; i < rF; i++)
+      for (size_t j = 0; j < ns; j++) f[i] += fi[(size_t)i * ns + j];
+    for (int i = 0; i < rG; i++)
+      for (size_t j = 0; j < ns; j++) g[i] += gi[(size_t)i * ns + j];
+    /* thisEh = M (f - S^T g) :2453 */
+    for (int i = 0; i < rF; i++) {
+      double t = f[i];
+      for (int k = 0; k < rG; k++) t -= S[k * rF + i] * g[k];
+      v[i] = t;
+    }
+    for (int i = 0; i < rF; i++) {
+      double t = 0.0;
+      for (int k = 0; k < rF; k++) t += M[i * rF + k] * v[k];
+      eh[i] = t;
+    }
+    /* Eh :2455-2464 */
+    for (int i = 0; i < rF; i++)
+      for (size_t j = 0; j < ns; j++) Eh[(size_t)i * ns + j] = eh[i];
+    for (int i = 0; i < rG; i++) {
+      double se = 0.0;
+      for (int k = 0; k < rF; k++) se += S[i * rF + k] * eh[k];
+      for (size_t j = 0; j < ns; j++) {
+        double t = 0.0;
+        for (int k = 0; k < rG; k++) t += iGG[i * rG + k] * gi[(size_t)k * ns + j];
+        Eh[(size_t)(rF + i) * ns + j] = t - se;
+      }
+    }
+    /* EhhSum += ns * tmpM + Eh Eh^T :2467-2473 */
+    for (int i = 0; i < r; i++)
+      for (int j = 0; j < r; j++) {
+        double tm;
+        if (i < rF && j < rF) tm = M[i * rF + j];
+        else if (i < rF) tm = -MsT[i * rG + (j - rF)];
+        else if (j < rF) tm = -MsT[j * rG + (i - rF)];
+        else tm = iGG[(i - rF) * rG + (j - rF)] + SMsT[(i - rF) * rG + (j - rF)];
+        double e2 = 0.0;
+        for (size_t k = 0; k < ns; k++) e2 += Eh[(size_t)i * ns + k] * Eh[(size_t)j * ns + k];
+        Ehh[i * r + j] += (double)ns * tm + e2;
+      }
+    /* xhSum :2476-2479, Umx :2482-2483 */
+    for (int i = 0; i < d; i++)
+      for (int j = 0; j < r; j++)
+        for (size_t k = 0; k < ns; k++) xh[(size_t)i * r + j] += data[(size_t)i * n + first + k] * Eh[(size_t)j * ns + k];
+    for (size_t k = 0; k < ns; k++)
+      for (int j = 0; j < r; j++) U[j] += Eh[(size_t)j * ns + k];
+    free(Sx); free(fi); free(gi); free(f); free(g); free(eh); free(v); free(Eh);
+  }
+  /* mStep :2790-2813 */
+  double *iEhh = NEW((size_t)r * r), *FG = NEW((size_t)d * r), *SL = NEW((size_t)d * d);
+  rc |= orc_invert(r, Ehh, iEhh);
+  mm(d, r, r, xh, 0, iEhh, 0, FG);
+  mm(d, d, r, FG, 0, xh, 1, SL);
+  for (int i = 0; i < d * d; i++) Sigma[i] = (sigmaObs[i] - SL[i]) / (double)n;
+  for (int j = 0; j < r; j++) U[j] /= (double)n;
+  double *c = NEW((size_t)r * r), *cF = NEW((size_t)rF * rF), *cG = NEW((size_t)rG * rG);
+  double *Rh = NEW((size_t)rF * rF), *Rw = NEW((size_t)rG * rG);
+  for (int i = 0; i < r; i++)
+    for (int j = 0; j < r; j++) c[i * r + j] = Ehh[i * r + j] / (double)n - U[i] * U[j];
+  for (int i = 0; i < rF; i++)
+    for (int j = 0; j < rF; j++) cF[i * rF + j] = c[i * r + j];
+  for (int i = 0; i < rG; i++)
+    for (int j = 0; j < rG; j++) cG[i * rG + j] = c[(rF + i) * r + rF + j];
+  rc |= orc_upper_cholesky(rF, cF, Rh);
+  if (rG > 0) rc |= orc_upper_cholesky(rG, cG, Rw);
+  /* F = FGEst[:, :rF] Rh^T ; G = FGEst[:, rF:] Rw^T ; Delta += FGEst Umx */
+  for (int i = 0; i < d; i++) {
+    for (int j = 0; j < rF; j++) {
+      double t = 0.0;
+      for (int k = 0; k < rF; k++) t += FG[(size_t)i * r + k] * Rh[j * rF + k];
+      F[(size_t)i * rF + j] = t;
+    }
+    for (int j = 0; j < rG; j++) {
+      double t = 0.0;
+      for (int k = 0; k < rG; k++) t += FG[(size_t)i * r + rF + k] * Rw[j * rG + k];
+      G[(size_t)i * rG + j] = t;
+    }
+    double t = 0.0;
+    for (int k = 0; k < r; k++) t += FG[(size_t)i * r + k] * U[k];
+    Delta[i] += t;
+  }
+  free(sigmaObs); free(iS); free(Ftw); free(Gtw); free(GtwG); free(FtwG); free(iGG); free(FtwF); free(S);
+  free(A); free(tmp); free(V); free(Dv); free(Ehh); free(xh); free(U); free(M); free(MsT); free(SMsT);
+  free(iEhh); free(FG); free(SL); free(c); free(cF); free(cG); free(Rh); free(Rw);
+#undef NEW
+  return rc;
+}

@@ -174,6 +174,11 @@ void orc_iv_mahalanobis(int d, size_t nm, size_t nt, const double *models, const
 int orc_iv_two_cov(int d, size_t nm, size_t nt, const double *models, const double *segments,
                    const double *W, const double *B, double *scores);      /* :4083-4173 */
 
+/* ---- A.11 PLDA EM training: one PldaModel::em_iteration (PldaTools.cpp:2329-2343, 2359-2485,
+ * 2790-2813, 931-950).  data[d x n] is centred by Delta in place; F, G, Sigma, Delta updated. */
+int orc_plda_em_iteration(int d, int rF, int rG, size_t n, double *data, const int32_t *class_of,
+                          size_t n_spk, double *F, double *G, double *Sigma, double *Delta);
+
 /* dense helpers ([ALIZE] DoubleSquareMatrix::invert / upperCholesky) */
 int orc_invert(int n, const double *a, double *inv);
 int orc_upper_cholesky(int n, const double *a, double *u); /* a = u^T u, u upper */
