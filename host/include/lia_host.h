@@ -244,6 +244,8 @@ class PldaDev {
   size_t getSessionNumber() const { return data_.cols; }
   const Matrix &getData() const { return data_; }
   const std::vector<double> &getMean() const { return mean_; }
+  const std::vector<int32_t> &getClass() const { return class_; }
+  void setData(const Matrix &X) { data_ = X; computeAll(); }  // the engine centres _data in place
   void computeAll();                                             // :353-385
   void lengthNorm();                                             // :436-464
   void center(const std::vector<double> &mu);                    // :466-474
@@ -261,6 +263,29 @@ class PldaDev {
   size_t nSpk_ = 0;
   std::vector<double> mean_;
 };
+// ---- PldaModel in training mode (PldaTools.cpp:2028-2122, 2176-2343, 2790-2870): the model
+// matrices live on the host, every EM iteration is one lr_plda_em_iteration call
+class PldaModel {
+ public:
+  PldaModel(const std::string &mode /*train*/, const Config &c);  // :2028
+  PldaDev &getDev() { return dev_; }
+  void updateModel(const Config &c);  // :2302-2326 (after the development data changed dimension)
+  void updateMean();                  // :2290
+  void centerData();                  // :2297
+  void em_iteration(const Config &c, unsigned long it);  // :2329-2343
+  void saveModel(const Config &c);    // :2816-2870
+  const Matrix &F() const { return F_; }
+  const Matrix &G() const { return G_; }
+  const Matrix &Sigma() const { return Sigma_; }
+
+ private:
+  PldaDev dev_;
+  size_t rankF_ = 0, rankG_ = 0;
+  Matrix F_, G_, Sigma_;
+  std::vector<double> originalMean_, delta_;
+  void initModel(const Config &c);  // :2176-2203 (Sigma from the data, Box-Muller F / G)
+};
+
 // file names of the EFR / sphNorm parameters of iteration `it` (:1836-1842, :1907-1913)
 std::string efrMatrixFilename(const Config &c, unsigned long it, bool forLoad);
 std::string efrMeanFilename(const Config &c, unsigned long it, bool forLoad);
@@ -274,6 +299,7 @@ int IvExtractorEigenDecomposition(Config &c); // IvExtractor.cpp:254 (mode eigen
 int TotalVariability(Config &c);  // LIA_SpkDet/TotalVariability/src/TotalVariability.cpp:71
 int IvTest(Config &c);            // LIA_SpkDet/IvTest/src/IvTest.cpp:73 (scoring = cosine | mahalanobis | 2cov | plda native)
 int IvNorm(Config &c);            // LIA_SpkDet/IvNorm/src/IvNorm.cpp:72
+int PLDA(Config &c);              // LIA_SpkDet/PLDA/src/PLDA.cpp:73 (PLDA model training)
 int TrainTarget(Config &c);       // LIA_SpkDet/TrainTarget/src/TrainTarget.cpp:75 (MAPOccDep)
 
 }  // namespace lia

@@ -4,6 +4,8 @@
 // LIA_SpkDet/IvTest/src/IvTest.cpp:112-391, LIA_SpkDet/IvNorm/src/IvNorm.cpp:72-128).
 // All numerics go through the lr_iv_* entry points of the engine.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 
@@ -362,6 +364,127 @@ bool IvTestNonPlda(Config &c, const std::string &scoring, Matrix &scores, std::v
   modelIndex = test.modelIndex;
   segIndex = test.segIndex;
   return true;
+}
+
+// ------------------------------------------------------------------ PldaModel (training)
+PldaModel::PldaModel(const std::string &mode, const Config &c) : dev_(c.getParam("backgroundNdxFilename"), c) {
+  if (mode != "train") LIA_THROW("PldaModel: only the training mode is a host object (scoring loads the matrices directly)");
+  rankF_ = (size_t)c.getLong("pldaEigenVoiceNumber");
+  rankG_ = (size_t)c.getLong("pldaEigenChannelNumber", 0);
+  const size_t d = dev_.getVectSize();
+  delta_.assign(d, 0.0);
+  if (c.getBool("pldaLoadInitMatrices", false)) {  // :2075-2113
+    const std::string path = c.getString("matrixFilesPath", ""), ext = c.getString("loadMatrixFilesExtension", "");
+    const std::string fmt = c.getString("loadMatrixFormat", "DB");
+    F_.load(path + c.getParam("pldaEigenVoiceMatrixInit") + ext, fmt);
+    if (rankG_ > 0) G_.load(path + c.getParam("pldaEigenChannelMatrixInit") + ext, fmt);
+    Sigma_.load(path + c.getParam("pldaSigmaMatrixInit") + ext, fmt);
+    Matrix m;
+    m.load(path + c.getParam("pldaMeanVecInit") + ext, fmt);
+    originalMean_ = m.data;
+    if (F_.rows != d || F_.cols != rankF_ || Sigma_.rows != d || Sigma_.cols != d || originalMean_.size() != d ||
+        (rankG_ > 0 && (G_.rows != d || G_.cols != rankG_)))
+      LIA_THROW("PldaModel: initial matrices do not match vectSize / ranks");
+  } else {
+    initModel(c);
+  }
+}
+
+void PldaModel::initModel(const Config &c) {
+  const size_t d = dev_.getVectSize();
+  Matrix W, B;
+  dev_.computeCovMat(Sigma_, W, B);  // Sigma is initialised from the total covariance (:2179-2186)
+  const std::string law = c.getString("pldaRandomInitLaw", "normal");
+  auto fill = [&](Matrix &M, size_t cols) {
+    M = Matrix(d, cols);
+    if (law == "normal") {
+      // boxMullerGeneratorInit + boxMullerGenerator(0, 1) on libc rand() (ScoreWarp.cpp:68-79)
+      double x1 = rand() / (float)RAND_MAX, x2;
+      for (auto &v : M.data) {
+        double val;
+        do {
+          x2 = x1;
+          x1 = rand() / (float)RAND_MAX;
+          val = std::sqrt(-2.0 * std::log(x1)) * std::cos(2.0 * 3.14159265358979323846 * x2);
+        } while (std::isnan(val) || std::isinf(val));
+        v = val;
+      }
+    } else if (law == "uniform") {
+      for (auto &v : M.data) v = 2.0 * drand48() - 1.0;  // Eigen's Random(): uniform in [-1, 1]
+    } else {
+      LIA_THROW("Selected random initialization law does not exist");
+    }
+  };
+  fill(F_, rankF_);
+  fill(G_, rankG_);
+  originalMean_ = dev_.getMean();
+}
+
+void PldaModel::updateModel(const Config &) {  // :2302-2326
+  originalMean_ = dev_.getMean();
+  delta_.assign(dev_.getVectSize(), 0.0);
+}
+void PldaModel::updateMean() { originalMean_ = dev_.getMean(); }
+void PldaModel::centerData() { dev_.center(originalMean_); }
+
+void PldaModel::em_iteration(const Config &, unsigned long) {
+  Matrix X = dev_.getData();
+  const size_t d = X.rows;
+  if (F_.rows != d || Sigma_.rows != d) LIA_THROW("PldaModel: model dimension does not match the development data");
+  LIA_CHECK(lr_plda_em_iteration((int)d, (int)rankF_, (int)rankG_, X.cols, X.data.data(), dev_.getClass().data(),
+                                 dev_.getSpeakerNumber(), F_.data.data(), rankG_ ? G_.data.data() : nullptr,
+                                 Sigma_.data.data(), delta_.data()));
+  dev_.setData(X);  // _Dev.center(_Delta) changed the development data (:2333)
+}
+
+void PldaModel::saveModel(const Config &c) {
+  const std::string path = c.getString("matrixFilesPath", ""), ext = c.getString("saveMatrixFilesExtension", "");
+  const std::string fmt = c.getString("saveMatrixFormat", "DB");
+  const size_t d = dev_.getVectSize();
+  Matrix mean(d, 1), md(d, 1);  // column vectors like the reference (:2819-2823)
+  mean.data = originalMean_;
+  md.data = delta_;
+  mean.save(path + c.getString("pldaMeanVec", "pldaMeanVec") + ext, fmt);
+  F_.save(path + c.getString("pldaEigenVoiceMatrix", "pldaEigenVoiceMatrix") + ext, fmt);
+  if (rankG_ > 0) G_.save(path + c.getString("pldaEigenChannelMatrix", "pldaEigenChannelMatrix") + ext, fmt);
+  Sigma_.save(path + c.getString("pldaSigmaMatrix", "pldaSigmaMatrix") + ext, fmt);
+  md.save(path + c.getString("pldaMinDivMean", "pldaMinDivMean") + ext, fmt);
+}
+
+// ------------------------------------------------------------------ PLDA (PLDA.cpp:73-101)
+int PLDA(Config &c) {
+  try {
+    PldaModel plda("train", c);
+    plda.updateMean();
+    plda.centerData();
+    const unsigned long nbIt = (unsigned long)c.getLong("pldaNbIt");
+    for (unsigned long it = 0; it < nbIt; it++) plda.em_iteration(c, it);
+    plda.saveModel(c);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// training branch of IvTest for scoring = plda (IvTest.cpp:255-298): optional normalisation of the
+// development data, EM, saveModel; the scoring branch then loads what was saved
+void IvTestTrainPlda(Config &c) {
+  PldaModel plda("train", c);
+  if (c.getBool("ivNorm", false) && !c.getBool("ivNormLoadParam", false)) {
+    if (c.getLong("ivNormIterationNb", 1) > 0) plda.getDev().sphericalNuisanceNormalization(c);
+    if (c.getBool("LDA", false)) {
+      Matrix lda;
+      plda.getDev().computeLDA(lda, c.getLong("ldaRank"), c);
+      plda.getDev().rotateLeft(lda);
+      lda.save(c.getString("matrixFilesPath", "") + c.getParam("ldaMatrix") + c.getString("loadMatrixFilesExtension", ""),
+               c.getString("saveMatrixFormat", "DB"));
+    }
+  }
+  plda.updateModel(c);
+  plda.centerData();
+  const unsigned long nbIt = (unsigned long)c.getLong("pldaNbIt");
+  for (unsigned long it = 0; it < nbIt; it++) plda.em_iteration(c, it);
+  plda.saveModel(c);
 }
 
 // ------------------------------------------------------------------ IvNorm (IvNorm.cpp:72-128)

@@ -316,7 +316,8 @@ int TotalVariability(Config &c) {
 }
 
 // ------------------------------------------------------------------ IvTest
-// cosine / mahalanobis / 2cov branches live in backend.cpp
+// cosine / mahalanobis / 2cov branches and PLDA training live in backend.cpp
+void IvTestTrainPlda(Config &c);
 bool IvTestNonPlda(Config &c, const std::string &scoring, Matrix &scores, std::vector<std::vector<std::string>> &trialLines,
                    std::map<std::string, int> &modelIndex, std::map<std::string, int> &segIndex);
 
@@ -342,6 +343,9 @@ int IvTest(Config &c) {
       std::cout << "Scoring option is invalid, must be: cosine OR mahalanobis OR 2cov OR plda" << std::endl;
       return 0;
     }
+    // the model is trained first unless pldaLoadModel is set (IvTest.cpp:255-298; this mirror
+    // defaults to loading, the reference requires the parameter)
+    if (!c.getBool("pldaLoadModel", true)) IvTestTrainPlda(c);
     const std::string vpath = c.getParam("testVectorFilesPath") + "/", vext = c.getString("loadVectorFilesExtension", ".y");
     const std::string mpath = c.getString("matrixFilesPath", ""), mext = c.getString("loadMatrixFilesExtension", "");
     const std::string mfmt = c.getString("loadMatrixFormat", "DB");

@@ -1,0 +1,21 @@
+// PLDAMain.cpp -- command-line entry point: "--config <file>" plus "--name value" overrides,
+// like LIA_SpkDet/PLDA/src/PLDAMain.cpp.
+#include <iostream>
+
+#include "lia_host.h"
+
+int main(int argc, char **argv) {
+  try {
+    lia::Config config;
+    config.parseCmdLine(argc, argv);
+    if (config.existsParam("help")) {
+      std::cout << "PLDA (lia_ral_b200 engine): --config <file> [--param value ...]" << std::endl;
+      return 0;
+    }
+    if (config.existsParam("device")) lr_init((int)config.getLong("device"));
+    return lia::PLDA(config);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}

@@ -267,6 +267,14 @@ lr_status lr_iv_two_cov_scoring(int d, size_t n_models, size_t n_test, const dou
                                 const double *segments, const double *W, const double *B,
                                 double *scores);
 
+/* PLDA training: one PldaModel::em_iteration (PldaTools.cpp:2329-2343) -- _Dev.center(_Delta),
+ * computeCovMatEigen (:931-950), getExpectedValues (:2359-2485), mStep with minimum divergence
+ * (:2790-2813).  data[d x n] (vectors in columns, sessions of a speaker adjacent, class_of
+ * non-decreasing) is centred by Delta IN PLACE like the reference's _Dev; F[d x rF], G[d x rG]
+ * (rG may be 0, G NULL), Sigma[d x d], Delta[d] are updated in place. */
+lr_status lr_plda_em_iteration(int d, int rF, int rG, size_t n, double *data, const int32_t *class_of,
+                               size_t n_spk, double *F, double *G, double *Sigma, double *Delta);
+
 #ifdef __cplusplus
 }
 #endif

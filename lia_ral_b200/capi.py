@@ -585,3 +585,16 @@ def iv_two_cov_scoring(models, segments, W, B):
     _check(lib().lr_iv_two_cov_scoring(d, ct.c_size_t(nm), ct.c_size_t(nt), _d(models), _d(segments),
                                        _d(_f64(W)), _d(_f64(B)), _d(sc)))
     return sc
+
+
+def plda_em_iteration(data, class_of, n_spk, F, G, Sigma, Delta):
+    """One PldaModel::em_iteration -> (data centred by Delta, F, G, Sigma, Delta)."""
+    data, F, Sigma, Delta = _f64(data).copy(), _f64(F).copy(), _f64(Sigma).copy(), _f64(Delta).copy()
+    d, n = data.shape
+    rF = F.shape[1]
+    rG = 0 if G is None else G.shape[1]
+    G = np.zeros((d, 0)) if rG == 0 else _f64(G).copy()
+    cls = _cls(class_of)
+    _check(lib().lr_plda_em_iteration(d, rF, rG, ct.c_size_t(n), _d(data), cls.ctypes.data_as(c_ip),
+                                      ct.c_size_t(n_spk), _d(F), _d(G) if rG else None, _d(Sigma), _d(Delta)))
+    return data, F, G, Sigma, Delta

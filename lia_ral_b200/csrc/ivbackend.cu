@@ -225,6 +225,106 @@ __global__ void k_axpby(int n, double alpha, const double *__restrict__ A, doubl
   }
 }
 
+// ---- PLDA EM kernels -------------------------------------------------------------------------
+// per-class column sums of a row-major [r x n] matrix: out[i, class_of[s]] += X[i, s]
+__global__ void k_class_colsum(int r, size_t n, size_t n_spk, const double *__restrict__ X,
+                               const int *__restrict__ class_of, double *__restrict__ out) {
+  size_t total = (size_t)r * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t k = i / n, s = i - k * n;
+    atomicAdd(&out[k * n_spk + class_of[s]], X[i]);
+  }
+}
+__global__ void k_count_classes(size_t n, const int *__restrict__ class_of, double *__restrict__ cnt) {
+  size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) atomicAdd(&cnt[class_of[s]], 1.0);
+}
+// Z[i, spk] /= (cnt[spk] * lam[i] + 1)   (M_n = V (n D + I)^-1 V^T applied in the eigenbasis, :2417-2424)
+__global__ void k_scale_posterior(int rF, size_t n_spk, const double *__restrict__ cnt,
+                                  const double *__restrict__ lam, double *__restrict__ Z) {
+  size_t total = (size_t)rF * n_spk;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    size_t i = e / n_spk, c = e - i * n_spk;
+    Z[e] /= (cnt[c] * lam[i] + 1.0);
+  }
+}
+// w[i] = sum_spk cnt / (cnt lam_i + 1)  -> sum over speakers of n_spk M_{n_spk} in the eigenbasis
+__global__ void k_mbar_weights(int rF, size_t n_spk, const double *__restrict__ cnt,
+                               const double *__restrict__ lam, double *__restrict__ w) {
+  int i = blockIdx.x;
+  if (i >= rF) return;
+  double p = 0.0;
+  for (size_t c = threadIdx.x; c < n_spk; c += blockDim.x) p += cnt[c] / (cnt[c] * lam[i] + 1.0);
+  __shared__ double red[kThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < kThreads / 32; k++) t += red[k];
+    w[i] = t;
+  }
+}
+// Y[i, :] = w[i] X[i, :]  (row scaling of a row-major [r x c] matrix)
+__global__ void k_scale_rows(int r, int c, const double *__restrict__ w, const double *__restrict__ X,
+                             double *__restrict__ Y) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < r * c) Y[e] = w[e / c] * X[e];
+}
+// Eh[(rF + rG) x n]: rows 0..rF = thisEh[:, class], rows rF.. = low[:, s] - SE[:, class]  (:2455-2464)
+__global__ void k_build_eh(int rF, int rG, size_t n, size_t n_spk, const int *__restrict__ class_of,
+                           const double *__restrict__ thisEh, const double *__restrict__ low,
+                           const double *__restrict__ SE, double *__restrict__ Eh) {
+  size_t total = (size_t)(rF + rG) * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    size_t i = e / n, s = e - i * n;
+    int c = class_of[s];
+    Eh[e] = i < (size_t)rF ? thisEh[i * n_spk + c]
+                           : low[(i - rF) * n + s] - SE[(i - rF) * n_spk + c];
+  }
+}
+// dst[row0 + i, col0 + j] += alpha * (transpose ? src[j, i] : src[i, j])  (row-major, src is rows x cols
+// as seen AFTER the optional transposition)
+__global__ void k_add_block(double *__restrict__ dst, int ldd, int row0, int col0,
+                            const double *__restrict__ src, int lds, int rows, int cols, double alpha,
+                            int transpose) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < rows * cols) {
+    int i = e / cols, j = e - i * cols;
+    dst[(size_t)(row0 + i) * ldd + col0 + j] += alpha * (transpose ? src[(size_t)j * lds + i] : src[(size_t)i * lds + j]);
+  }
+}
+__global__ void k_add_diag(int n, double v, double *__restrict__ A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[(size_t)i * n + i] += v;
+}
+// c = Ehh / n - u u^T with u = U / n (U scaled in place)   (:2806-2807)
+__global__ void k_mindiv_cov(int r, double n, const double *__restrict__ Ehh, double *__restrict__ U,
+                             double *__restrict__ c) {
+  __shared__ double u[1024];
+  for (int i = threadIdx.x; i < r; i += blockDim.x) u[i] = U[i] / n;
+  __syncthreads();
+  for (int e = threadIdx.x; e < r * r; e += blockDim.x) c[e] = Ehh[e] / n - u[e / r] * u[e % r];
+  __syncthreads();
+  for (int i = threadIdx.x; i < r; i += blockDim.x) U[i] = u[i];
+}
+// out[i, j] = src[row0 + i, col0 + j] (row-major block copy)
+__global__ void k_copy_block_rm(const double *__restrict__ src, int lds, int row0, int col0, int rows,
+                                int cols, double *__restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < rows * cols) out[e] = src[(size_t)(row0 + e / cols) * lds + col0 + e % cols];
+}
+// Sigma = (sigmaObs - SL) / n
+__global__ void k_sigma_update(int dd, double n, const double *__restrict__ obs, const double *__restrict__ SL,
+                               double *__restrict__ Sigma) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < dd) Sigma[e] = (obs[e] - SL[e]) / n;
+}
+
 // ---- dense helpers -------------------------------------------------------------------------
 struct Dense {
   cusolverDnHandle_t solver = nullptr;
@@ -677,6 +777,188 @@ lr_status lr_iv_two_cov_scoring(int d, size_t nm, size_t nt, const double *model
   st = gemm_rm(false, false, d, (int)nt, d, T1.p, d, dS.p, (int)nt, P.p, (int)nt);
   if (st != LR_OK) return st;
   return score_blocks(d, nm, nt, dM.p, P.p, a.p, b.p, nullptr, 2, scores);
+}
+
+// ---- PLDA EM training: one PldaModel::em_iteration (PldaTools.cpp:2329-2343) -------------------
+// center by Delta, scatter matrix (computeCovMatEigen :931-950), E-step (getExpectedValues
+// :2359-2485), M-step with minimum divergence (:2790-2813).  The reference walks the speakers one
+// at a time with Eigen; here every per-speaker product is one GEMM over ALL sessions / speakers:
+//   fi = F^T S^-1 X, gi = G^T S^-1 X (all sessions), f / g = per-speaker column sums,
+//   E[h_spk] = V diag(1 / (n_spk lam + 1)) V^T (f - S^T g)        (M_n in the eigenbasis of A)
+//   Eh = [E[h_spk] per session ; iGG gi - S E[h_spk]],  EhhSum = Eh Eh^T + sum_spk n_spk tmpM_{n_spk},
+//   xhSum = X Eh^T, Umx = row sums of Eh.
+lr_status lr_plda_em_iteration(int d, int rF, int rG, size_t n, double *data, const int32_t *class_of,
+                               size_t n_spk, double *F, double *G, double *Sigma, double *Delta) {
+  LR_READY();
+  LR_REQUIRE(d >= 1 && rF >= 1 && rG >= 0 && rF + rG <= 1024 && n >= 1 && n_spk >= 1 && data && class_of && F &&
+                 (G || rG == 0) && Sigma && Delta,
+             "lr_plda_em_iteration: bad arguments (d=%d rF=%d rG=%d)", d, rF, rG);
+  for (size_t s = 0; s < n; s++)
+    LR_REQUIRE(class_of[s] >= 0 && (size_t)class_of[s] < n_spk && (s == 0 || class_of[s] >= class_of[s - 1]),
+               "lr_plda_em_iteration: class_of must be non-decreasing in [0, %zu)", n_spk);
+  Engine &e = engine();
+  Dense dn;
+  lr_status st = dn.init();
+  if (st != LR_OK) return st;
+  const int r = rF + rG;
+  const size_t dd = (size_t)d * d;
+  const double nn = (double)n;
+  DevBuf<double> X, dF, dG, dS, dDelta, obs, iS, Ftw, Gtw, iGG, FtwG, Sm, A, lam, fi, gi, fs, gs, cnt, R, Z, eh, SE,
+      low, Eh, Ehh, Ehh0, xh, U, w, T1, Mbar, MsT, SMsT, FG, SL, cm, cF, cG, Fn, Gn;
+  DevBuf<int> cls;
+#define ALLOC(buf, count) LR_CUDA(buf.alloc(std::max<size_t>((size_t)(count), 1)))
+  ALLOC(X, (size_t)d * n); ALLOC(dF, (size_t)d * rF); ALLOC(dG, (size_t)d * rG); ALLOC(dS, dd); ALLOC(dDelta, d);
+  ALLOC(obs, dd); ALLOC(iS, dd); ALLOC(Ftw, (size_t)rF * d); ALLOC(Gtw, (size_t)rG * d);
+  ALLOC(iGG, (size_t)rG * rG); ALLOC(FtwG, (size_t)rF * rG); ALLOC(Sm, (size_t)rG * rF); ALLOC(A, (size_t)rF * rF);
+  ALLOC(lam, rF); ALLOC(fi, (size_t)rF * n); ALLOC(gi, (size_t)rG * n); ALLOC(fs, (size_t)rF * n_spk);
+  ALLOC(gs, (size_t)rG * n_spk); ALLOC(cnt, n_spk); ALLOC(R, (size_t)rF * n_spk); ALLOC(Z, (size_t)rF * n_spk);
+  ALLOC(eh, (size_t)rF * n_spk); ALLOC(SE, (size_t)rG * n_spk); ALLOC(low, (size_t)rG * n); ALLOC(Eh, (size_t)r * n);
+  ALLOC(Ehh, (size_t)r * r); ALLOC(Ehh0, (size_t)r * r); ALLOC(xh, (size_t)d * r); ALLOC(U, r); ALLOC(w, rF);
+  ALLOC(T1, (size_t)rF * rF); ALLOC(Mbar, (size_t)rF * rF); ALLOC(MsT, (size_t)rF * rG); ALLOC(SMsT, (size_t)rG * rG);
+  ALLOC(FG, (size_t)d * r); ALLOC(SL, dd); ALLOC(cm, (size_t)r * r); ALLOC(cF, (size_t)rF * rF);
+  ALLOC(cG, (size_t)rG * rG); ALLOC(Fn, (size_t)d * rF); ALLOC(Gn, (size_t)d * rG); ALLOC(cls, n);
+#undef ALLOC
+  auto up = [&](double *dst, const double *src, size_t count) {
+    return count ? cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, e.stream) : cudaSuccess;
+  };
+  LR_CUDA(up(X.p, data, (size_t)d * n));
+  LR_CUDA(up(dF.p, F, (size_t)d * rF));
+  LR_CUDA(up(dG.p, G, (size_t)d * rG));
+  LR_CUDA(up(dS.p, Sigma, dd));
+  LR_CUDA(up(dDelta.p, Delta, d));
+  LR_CUDA(cudaMemcpyAsync(cls.p, class_of, n * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  auto g1 = [](size_t count) { return ceil_div((long)std::max<size_t>(count, 1), kThreads); };
+#define GEMM(...)                   \
+  do {                              \
+    st = gemm_rm(__VA_ARGS__);      \
+    if (st != LR_OK) return st;     \
+  } while (0)
+#define LAUNCHED() LR_CHECK_LAUNCH()
+  // _Dev.center(_Delta); sigmaObs = X X^T
+  k_sub_mu<<<grid_for((size_t)d * n), kThreads, 0, e.stream>>>(d, n, dDelta.p, X.p);
+  LAUNCHED();
+  st = outer_rm(d, n, X.p, 1.0, obs.p);
+  if (st != LR_OK) return st;
+  // preComputation (:2950-2972)
+  LR_CUDA(cudaMemcpyAsync(iS.p, dS.p, dd * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  st = dn.spd_inverse(d, iS.p, "PLDA Sigma");
+  if (st != LR_OK) return st;
+  GEMM(true, false, rF, d, d, dF.p, rF, iS.p, d, Ftw.p, d);            // Ftw = F^T S^-1
+  GEMM(false, false, rF, rF, d, Ftw.p, d, dF.p, rF, A.p, rF);          // A = Ftw F (- FtwG iGG FtwG^T below)
+  if (rG > 0) {
+    GEMM(true, false, rG, d, d, dG.p, rG, iS.p, d, Gtw.p, d);          // Gtw = G^T S^-1
+    GEMM(false, false, rG, rG, d, Gtw.p, d, dG.p, rG, iGG.p, rG);      // GtwG
+    k_add_diag<<<g1(rG), kThreads, 0, e.stream>>>(rG, 1.0, iGG.p);
+    LAUNCHED();
+    st = dn.spd_inverse(rG, iGG.p, "PLDA G^T S^-1 G + I");
+    if (st != LR_OK) return st;
+    GEMM(false, false, rF, rG, d, Ftw.p, d, dG.p, rG, FtwG.p, rG);     // FtwG
+    GEMM(false, true, rG, rF, rG, iGG.p, rG, FtwG.p, rG, Sm.p, rF);    // S = iGG FtwG^T  [rG x rF]
+    GEMM(false, false, rF, rF, rG, FtwG.p, rG, Sm.p, rF, A.p, rF, -1.0, 1.0);  // A -= FtwG S
+  }
+  // A = V diag(lam) V^T.  Column-major eigenvectors: the row-major view of the buffer is V^T.
+  st = dn.syevd(rF, A.p, lam.p, "PLDA E-step matrix A");
+  if (st != LR_OK) return st;
+  const double *Vt = A.p;
+  // per-session / per-speaker first-order terms
+  GEMM(false, false, rF, (int)n, d, Ftw.p, d, X.p, (int)n, fi.p, (int)n);  // fi = F^T S^-1 X
+  LR_CUDA(cudaMemsetAsync(fs.p, 0, (size_t)rF * n_spk * sizeof(double), e.stream));
+  LR_CUDA(cudaMemsetAsync(cnt.p, 0, n_spk * sizeof(double), e.stream));
+  k_class_colsum<<<grid_for((size_t)rF * n), kThreads, 0, e.stream>>>(rF, n, n_spk, fi.p, cls.p, fs.p);
+  LAUNCHED();
+  k_count_classes<<<g1(n), kThreads, 0, e.stream>>>(n, cls.p, cnt.p);
+  LAUNCHED();
+  LR_CUDA(cudaMemcpyAsync(R.p, fs.p, (size_t)rF * n_spk * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  if (rG > 0) {
+    GEMM(false, false, rG, (int)n, d, Gtw.p, d, X.p, (int)n, gi.p, (int)n);  // gi = G^T S^-1 X
+    LR_CUDA(cudaMemsetAsync(gs.p, 0, (size_t)rG * n_spk * sizeof(double), e.stream));
+    k_class_colsum<<<grid_for((size_t)rG * n), kThreads, 0, e.stream>>>(rG, n, n_spk, gi.p, cls.p, gs.p);
+    LAUNCHED();
+    GEMM(true, false, rF, (int)n_spk, rG, Sm.p, rF, gs.p, (int)n_spk, R.p, (int)n_spk, -1.0, 1.0);  // R = f - S^T g
+  }
+  // E[h_spk] = V diag(1 / (n_spk lam + 1)) V^T R    (:2417-2424, :2453)
+  GEMM(false, false, rF, (int)n_spk, rF, Vt, rF, R.p, (int)n_spk, Z.p, (int)n_spk);
+  k_scale_posterior<<<grid_for((size_t)rF * n_spk), kThreads, 0, e.stream>>>(rF, n_spk, cnt.p, lam.p, Z.p);
+  LAUNCHED();
+  GEMM(true, false, rF, (int)n_spk, rF, Vt, rF, Z.p, (int)n_spk, eh.p, (int)n_spk);
+  if (rG > 0) {
+    GEMM(false, false, rG, (int)n_spk, rF, Sm.p, rF, eh.p, (int)n_spk, SE.p, (int)n_spk);  // S E[h_spk]
+    GEMM(false, false, rG, (int)n, rG, iGG.p, rG, gi.p, (int)n, low.p, (int)n);            // iGG gi
+  }
+  k_build_eh<<<grid_for((size_t)r * n), kThreads, 0, e.stream>>>(rF, rG, n, n_spk, cls.p, eh.p, low.p, SE.p, Eh.p);
+  LAUNCHED();
+  // EhhSum = Eh Eh^T + sum_spk n_spk tmpM_{n_spk}   (:2467-2473), with Mbar = sum_spk n_spk M_{n_spk}
+  st = outer_rm(r, n, Eh.p, 1.0, Ehh.p);
+  if (st != LR_OK) return st;
+  k_mbar_weights<<<rF, kThreads, 0, e.stream>>>(rF, n_spk, cnt.p, lam.p, w.p);
+  LAUNCHED();
+  k_scale_rows<<<g1((size_t)rF * rF), kThreads, 0, e.stream>>>(rF, rF, w.p, Vt, T1.p);
+  LAUNCHED();
+  GEMM(true, false, rF, rF, rF, Vt, rF, T1.p, rF, Mbar.p, rF);  // Mbar = V diag(w) V^T
+  k_add_block<<<g1((size_t)rF * rF), kThreads, 0, e.stream>>>(Ehh.p, r, 0, 0, Mbar.p, rF, rF, rF, 1.0, 0);
+  LAUNCHED();
+  if (rG > 0) {
+    GEMM(false, true, rF, rG, rF, Mbar.p, rF, Sm.p, rF, MsT.p, rG);   // Mbar S^T
+    GEMM(false, false, rG, rG, rF, Sm.p, rF, MsT.p, rG, SMsT.p, rG);  // S Mbar S^T
+    k_add_block<<<g1((size_t)rF * rG), kThreads, 0, e.stream>>>(Ehh.p, r, 0, rF, MsT.p, rG, rF, rG, -1.0, 0);
+    LAUNCHED();
+    k_add_block<<<g1((size_t)rF * rG), kThreads, 0, e.stream>>>(Ehh.p, r, rF, 0, MsT.p, rG, rG, rF, -1.0, 1);
+    LAUNCHED();
+    k_add_block<<<g1((size_t)rG * rG), kThreads, 0, e.stream>>>(Ehh.p, r, rF, rF, iGG.p, rG, rG, rG, nn, 0);
+    LAUNCHED();
+    k_add_block<<<g1((size_t)rG * rG), kThreads, 0, e.stream>>>(Ehh.p, r, rF, rF, SMsT.p, rG, rG, rG, 1.0, 0);
+    LAUNCHED();
+  }
+  // xhSum = X Eh^T (:2476-2479), Umx = row sums of Eh (:2482-2483)
+  GEMM(false, true, d, r, (int)n, X.p, (int)n, Eh.p, (int)n, xh.p, r);
+  k_row_sum<<<r, kThreads, 0, e.stream>>>(n, Eh.p, 1.0, U.p);
+  LAUNCHED();
+  // ---- M-step (:2790-2813)
+  LR_CUDA(cudaMemcpyAsync(Ehh0.p, Ehh.p, (size_t)r * r * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  st = dn.spd_inverse(r, Ehh.p, "PLDA EhhSum");
+  if (st != LR_OK) return st;
+  GEMM(false, false, d, r, r, xh.p, r, Ehh.p, r, FG.p, r);       // FGEst = xhSum EhhSum^-1
+  GEMM(false, true, d, d, r, FG.p, r, xh.p, r, SL.p, d);         // SigmaLat = FGEst xhSum^T
+  k_sigma_update<<<g1(dd), kThreads, 0, e.stream>>>((int)dd, nn, obs.p, SL.p, dS.p);
+  LAUNCHED();
+  k_mindiv_cov<<<1, 1024, 0, e.stream>>>(r, nn, Ehh0.p, U.p, cm.p);  // U <- Umx / n, c = EhhSum / n - u u^T
+  LAUNCHED();
+  // Rh = upper Cholesky factor of c[0:rF, 0:rF]; F = FGEst[:, 0:rF] Rh^T.  potrf LOWER on the
+  // column-major buffer leaves, read row-major, exactly Rh in the upper triangle.
+  k_copy_block_rm<<<g1((size_t)rF * rF), kThreads, 0, e.stream>>>(cm.p, r, 0, 0, rF, rF, cF.p);
+  LAUNCHED();
+  st = dn.potrf(rF, cF.p, "PLDA minimum-divergence covariance (speaker factors)");
+  if (st != LR_OK) return st;
+  k_keep_upper_rm<<<g1((size_t)rF * rF), kThreads, 0, e.stream>>>(rF, cF.p);
+  LAUNCHED();
+  GEMM(false, true, d, rF, rF, FG.p, r, cF.p, rF, Fn.p, rF);
+  if (rG > 0) {
+    k_copy_block_rm<<<g1((size_t)rG * rG), kThreads, 0, e.stream>>>(cm.p, r, rF, rF, rG, rG, cG.p);
+    LAUNCHED();
+    st = dn.potrf(rG, cG.p, "PLDA minimum-divergence covariance (channel factors)");
+    if (st != LR_OK) return st;
+    k_keep_upper_rm<<<g1((size_t)rG * rG), kThreads, 0, e.stream>>>(rG, cG.p);
+    LAUNCHED();
+    GEMM(false, true, d, rG, rG, FG.p + rF, r, cG.p, rG, Gn.p, rG);
+  }
+  // Delta += FGEst Umx
+  {
+    const double one = 1.0;
+    LR_CUBLAS(cublasDgemv(e.blas, CUBLAS_OP_T, r, d, &one, FG.p, r, U.p, 1, &one, dDelta.p, 1));
+    count_launch();
+  }
+#undef GEMM
+#undef LAUNCHED
+  auto down = [&](double *dst, const double *src, size_t count) {
+    return count ? cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, e.stream) : cudaSuccess;
+  };
+  LR_CUDA(down(data, X.p, (size_t)d * n));
+  LR_CUDA(down(F, Fn.p, (size_t)d * rF));
+  LR_CUDA(down(G, Gn.p, (size_t)d * rG));
+  LR_CUDA(down(Sigma, dS.p, dd));
+  LR_CUDA(down(Delta, dDelta.p, d));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  return LR_OK;
 }
 
 }  // extern "C"

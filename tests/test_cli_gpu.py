@@ -339,6 +339,62 @@ def test_ivtest_backend_and_ivnorm_cli(world, oracle):
         assert np.allclose(lf.read_db(d / "bnorm" / f"bt{j}.y")[0], s2[:, j], atol=1e-7)
 
 
+def test_plda_training_cli(world, oracle):
+    """The PLDA program (PLDA.cpp:73-101): load a development list + initial matrices, centre, three EM
+    iterations, saveModel -- against the restated PldaModel::em_iteration chain; then IvTest scores with
+    the trained model files."""
+    d = world["dir"]
+    dim, n_spk, rF, rG = 10, 24, 4, 2
+    rng = np.random.default_rng(101)
+    sizes = rng.integers(2, 5, n_spk)
+    os.makedirs(d / "pvec", exist_ok=True)
+    lines, cols = [], []
+    for sidx in np.argsort(-sizes, kind="stable"):
+        center = rng.standard_normal(dim) * 1.5
+        names = []
+        for j in range(sizes[sidx]):
+            v = center + rng.standard_normal(dim) + 0.3
+            names.append(f"p{sidx}_{j}")
+            cols.append((v, len(lines)))
+            lf.write_db(d / "pvec" / f"{names[-1]}.y", v[None])
+        lines.append(names)
+    lf.write_lines(d / "pdev.ndx", lines)
+    data = np.stack([c[0] for c in cols], axis=1)
+    cls = np.array([c[1] for c in cols], dtype=np.int32)
+    F0, G0 = rng.standard_normal((dim, rF)), rng.standard_normal((dim, rG))
+    S0 = np.cov(data, bias=True) + 0.05 * np.eye(dim)
+    lf.write_db(d / "pF0.mat", F0)
+    lf.write_db(d / "pG0.mat", G0)
+    lf.write_db(d / "pS0.mat", S0)
+    lf.write_db(d / "pM0.mat", np.zeros((dim, 1)))
+    cfg = dict(world["common"], backgroundNdxFilename=str(d / "pdev.ndx"), loadVectorFilesPath=str(d / "pvec"),
+               loadVectorFilesExtension=".y", pldaEigenVoiceNumber=rF, pldaEigenChannelNumber=rG, pldaNbIt=3,
+               pldaLoadInitMatrices="true", pldaEigenVoiceMatrixInit="pF0", pldaEigenChannelMatrixInit="pG0",
+               pldaSigmaMatrixInit="pS0", pldaMeanVecInit="pM0", pldaEigenVoiceMatrix="tF", pldaEigenChannelMatrix="tG",
+               pldaSigmaMatrix="tS", pldaMeanVec="tMean", pldaMinDivMean="tDelta")
+    lf.write_cfg(d / "plda_train.cfg", **cfg)
+    _run("PLDA", d / "plda_train.cfg")
+    mean = data.mean(1)
+    st = (data - mean[:, None], F0, G0, S0, np.zeros(dim))
+    for it in range(3):
+        st = oracle.plda_em_iteration(st[0], cls, n_spk, *st[1:])
+    for name, ref in (("tF", st[1]), ("tG", st[2]), ("tS", st[3])):
+        got = lf.read_db(d / f"{name}.mat")
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-6 * np.abs(ref).max(), name
+    assert np.allclose(lf.read_db(d / "tMean.mat")[:, 0], mean)
+    assert np.allclose(lf.read_db(d / "tDelta.mat")[:, 0], st[4], atol=1e-8)
+    # score two development speakers against each other with the trained model
+    lf.write_lines(d / "ptrials.ndx", [[lines[0][0], lines[0][1], lines[1][0]], [lines[1][1], lines[0][1], lines[1][0]]])
+    lf.write_cfg(d / "plda_test.cfg", **dict(cfg, ndxFilename=str(d / "ptrials.ndx"), testVectorFilesPath=str(d / "pvec"),
+                                           scoring="plda", iVectSize=dim, outputFilename=str(d / "plda_test.res"), gender="M"))
+    _run("IvTest", d / "plda_test.cfg")
+    sc = {(l.split()[1], l.split()[3]): float(l.split()[4]) for l in open(d / "plda_test.res")}
+    assert len(sc) == 4
+    # target trials (same speaker) outscore the non-target ones
+    assert sc[(lines[0][1], lines[0][0])] > sc[(lines[1][0], lines[0][0])]
+    assert sc[(lines[1][0], lines[1][1])] > sc[(lines[0][1], lines[1][1])]
+
+
 def test_train_target_cli(world, oracle):
     """TrainTarget with MAPOccDep (mean + weight adaptation, 2 iterations) against the oracle's EM
     statistics + the numpy restatement of computeMAPOccDep (TrainTools.cpp:445-489, 871-904)."""

@@ -82,3 +82,31 @@ def test_scorings(capi, oracle, d, nm, nt):
     assert _rel(got, ref) < 1e-8
     with pytest.raises(capi.LrError):
         capi.iv_two_cov_scoring(models, segments, W - 10 * np.eye(d), B)   # not positive definite
+
+
+@pytest.mark.parametrize("d,rF,rG,n_spk", [(12, 5, 3, 40), (60, 20, 0, 200), (100, 30, 10, 300)],
+                         ids=["small", "no-channel", "d100"])
+def test_plda_em_iterations(capi, oracle, d, rF, rG, n_spk):
+    """Three PldaModel::em_iteration steps (PldaTools.cpp:2329-2343, 2359-2485, 2790-2813) chained on
+    the device against the restated loops: F, G, Sigma, the minimum-divergence mean and the centred
+    development data after every iteration."""
+    data, cls = _dev_set(d, n_spk, seed=11, lo=1, hi=6)
+    rng = np.random.default_rng(12)
+    F, G = rng.standard_normal((d, rF)), (rng.standard_normal((d, rG)) if rG else None)
+    _, _, Sigma, _, _ = oracle.iv_cov_mat(data, cls, n_spk)
+    data = data - data.mean(1, keepdims=True)          # PLDA.cpp: updateMean + centerData
+    Delta = np.zeros(d)
+    dev = (data, F, G, Sigma, Delta)
+    ref = (data, F, G, Sigma, Delta)
+    for it in range(3):
+        dev = capi.plda_em_iteration(dev[0], cls, n_spk, *dev[1:])
+        ref = oracle.plda_em_iteration(ref[0], cls, n_spk, *ref[1:])
+        names = ("data", "F", "G", "Sigma", "Delta")
+        for name, a, b in zip(names, dev, ref):
+            if name == "G" and rG == 0:
+                continue
+            tol = 1e-12 if name == "data" else 1e-7
+            assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-3), (it, name)
+    # the speaker subspace explains between-speaker variance: F F^T is no longer the random start
+    assert np.linalg.norm(dev[1]) > 0 and np.all(np.isfinite(dev[3]))
+    assert np.all(np.linalg.eigvalsh((dev[3] + dev[3].T) / 2) > 0)

@@ -232,3 +232,53 @@ def test_ivector_backend_against_numpy(oracle):
     assert np.allclose(oracle.iv_two_cov(M, Sg, W, B), ref)
     tr = rng.random((5, 7)) < 0.5
     assert np.all(oracle.iv_cosine(M, Sg, tr)[~tr] == 0)
+
+
+def test_plda_em_iteration_against_numpy(oracle):
+    """The restated PldaModel::em_iteration (PldaTools.cpp:2329-2343, 2359-2485, 2790-2813) against an
+    independent numpy formulation (per-speaker dense inverses instead of the eigenbasis trick)."""
+    def em_np(data, cls, F, G, Sigma, Delta):
+        X = data - Delta[:, None]
+        d, n = X.shape
+        rF, rG = F.shape[1], G.shape[1]
+        obs = X @ X.T
+        iS = np.linalg.inv(Sigma)
+        Ftw, Gtw = F.T @ iS, G.T @ iS
+        iGG = np.linalg.inv(Gtw @ G + np.eye(rG))
+        FtwG = Ftw @ G
+        S = iGG @ FtwG.T
+        A = Ftw @ F - FtwG @ iGG @ FtwG.T
+        Ehh, xh, U = np.zeros((rF + rG, rF + rG)), np.zeros((d, rF + rG)), np.zeros(rF + rG)
+        for c in np.unique(cls):
+            Xs = X[:, cls == c]
+            ns = Xs.shape[1]
+            M = np.linalg.inv(ns * A + np.eye(rF))
+            Sx = iS @ Xs
+            fi, gi = F.T @ Sx, G.T @ Sx
+            eh = M @ (fi.sum(1) - S.T @ gi.sum(1))
+            Eh = np.vstack([np.repeat(eh[:, None], ns, 1), iGG @ gi - (S @ eh)[:, None]])
+            MsT = M @ S.T
+            Ehh += ns * np.block([[M, -MsT], [-MsT.T, iGG + S @ MsT]]) + Eh @ Eh.T
+            xh += Xs @ Eh.T
+            U += Eh.sum(1)
+        FG = xh @ np.linalg.inv(Ehh)
+        Sig = (obs - FG @ xh.T) / n
+        U /= n
+        c = Ehh / n - np.outer(U, U)
+        Fn = FG[:, :rF] @ np.linalg.cholesky(c[:rF, :rF])
+        Gn = FG[:, rF:] @ np.linalg.cholesky(c[rF:, rF:]) if rG else np.zeros((d, 0))
+        return X, Fn, Gn, Sig, Delta + FG @ U
+
+    rng = np.random.default_rng(3)
+    for d, rF, rG in ((10, 4, 3), (12, 5, 0)):
+        nspk = 25
+        cls = np.repeat(np.arange(nspk), rng.integers(1, 5, nspk)).astype(np.int32)
+        n = len(cls)
+        data = (rng.standard_normal((d, nspk)) * 1.2)[:, cls] + rng.standard_normal((d, n))
+        a = b = (data, rng.standard_normal((d, rF)), rng.standard_normal((d, rG)),
+                 np.cov(data, bias=True) + 0.1 * np.eye(d), 0.05 * rng.standard_normal(d))
+        for it in range(3):
+            a = oracle.plda_em_iteration(a[0], cls, nspk, a[1], a[2] if rG else None, a[3], a[4])
+            b = em_np(b[0], cls, *b[1:])
+            for x, y in zip(a, b):
+                assert np.allclose(x, y, rtol=1e-8, atol=1e-10), it
