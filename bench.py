@@ -376,11 +376,14 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16" if args.kernel != 1 else "f32", "data": "synthetic",
             "config": {"workload": "TrainWorld EM iteration, 2048c/60d diagonal UBM, 10M frames/GPU (configs[1])",
                        "frames_per_gpu": T, "components": C, "dim": D,
                        "l2": "inputs (2.4 GB/GPU) exceed L2, no flush needed",
                        "kernel": {0: "auto", 1: "simt-fp32", 2: "tcgen05"}[args.kernel],
+                       "arithmetic": "fp16 hi/lo split operands (22 significand bits, 3 UMMA products), fp32 TMEM "
+                                     "accumulation, fp64 statistics" if args.kernel != 1 else "fp32 FMA, fp64 statistics",
                        "mean_llk_per_frame": llk_per_frame},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -393,7 +396,12 @@ def main():
                          "kernel": "statistics pass (LLK recompute + g x / g x^2 accumulation)",
                          "flop_per_frame": FLOP_PER_FRAME_EM, "launches": dom_n,
                          "avg_launch_ms": dom_ms / max(dom_n, 1), "peak_source": pk["src"],
-                         "llk_pass_ms_per_step": lse_ms / args.steps, "stat_pass_ms_per_step": acc_ms / args.steps},
+                         "llk_pass_ms_per_step": lse_ms / args.steps, "stat_pass_ms_per_step": acc_ms / args.steps,
+                         # what the tensor pipe actually executes (fp16 hi/lo split = 3 products, likelihood GEMM in
+                         # both passes): 2048 x 384 MAC (pass 1) + 2048 x (384 + 256) MAC (pass 2) per frame
+                         "issued_flop_per_frame": 2 * C * (384 + 384 + 256),
+                         "issued_tflops_both_passes": (2 * C * (384 + 384 + 256)) * T * args.steps
+                         / max((lse_ms + acc_ms) * 1e-3, 1e-9) / 1e12},
         }
         if iv is not None:
             out["ivectors"] = iv
