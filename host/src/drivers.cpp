@@ -409,9 +409,29 @@ int IvTest(Config &c) {
     const int rG = (int)c.getLong("pldaEigenChannelNumber", 0);
     if (rG > 0) G.load(mpath + c.getString("pldaEigenChannelMatrix", "pldaEigenChannelMatrix") + mext, mfmt);
     Matrix scores(nModels, nTest);
-    LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
-                                     Sigma.data.data(), models.data.data(), nEnrol, modelOf.data(), nModels,
-                                     segments.data.data(), nTest, scores.data.data()));
+    if (c.getString("pldaScoring", "native") == "enrollMean") {
+      // PldaTest::pldaMeanScoring (PldaTools.cpp:4612-4709): each model is the MEAN of its enrolment
+      // i-vectors scored as one session -- K_two = (2 FTJF + I)^-1 is exactly the native K_{L+1} at
+      // L = 1, so this is the native scorer on one averaged column per model.
+      Matrix avg(d, nModels);
+      std::vector<double> cnt(nModels, 0.0);
+      std::vector<int32_t> one(nModels);
+      for (size_t j = 0; j < nEnrol; j++) {
+        cnt[modelOf[j]] += 1.0;
+        for (size_t i = 0; i < d; i++) avg(i, modelOf[j]) += models(i, j);
+      }
+      for (size_t m = 0; m < nModels; m++) {
+        one[m] = (int32_t)m;
+        for (size_t i = 0; i < d; i++) avg(i, m) /= cnt[m];
+      }
+      LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
+                                       Sigma.data.data(), avg.data.data(), nModels, one.data(), nModels,
+                                       segments.data.data(), nTest, scores.data.data()));
+    } else {
+      LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
+                                       Sigma.data.data(), models.data.data(), nEnrol, modelOf.data(), nModels,
+                                       segments.data.data(), nTest, scores.data.data()));
+    }
     // NIST ascii output of the trials listed in the NDX (IvTest.cpp:415-439)
     std::ofstream outNist(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
     for (auto &l : trials.lines()) {
