@@ -2,7 +2,7 @@
 // (SURVEY.md Appendix B), written against the C ABI of liblia_ral_b200.so.
 //
 // This is NOT alize-core: it is the minimum object surface the five hot programs use (Config,
-// XList, MixtureGD + RAW/XML files, FeatureServer over SPRO3/SPRO4/RAW float32 files with
+// XList, MixtureGD + RAW/XML files, FeatureServer over SPRO3/SPRO4/RAW/HTK float32 files (bigEndian honoured) with
 // featureServerMask, label -> segment selection, Matrix DB/DT files), plus the LIA_SpkTools
 // batch functions re-expressed over the engine: accumulateStatEM, trainModel, TVAcc,
 // ComputeTest's frame loop, PLDA native scoring.  Names, parameter keys and error behaviour

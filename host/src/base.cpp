@@ -317,7 +317,12 @@ std::vector<int> parseMask(const std::string &mask) {
 }
 
 // ------------------------------------------------------------------ FeatureServer
-static void readFeatureFile(const std::string &path, const std::string &format, int vectSizeCfg,
+static uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24); }
+static uint16_t bswap16(uint16_t v) { return (uint16_t)((v >> 8) | (v << 8)); }
+
+// bigEndian: the payload (and the binary header fields) of SPRO3 / SPRO4 / RAW files are byte
+// swapped; HTK files are big-endian by definition.
+static void readFeatureFile(const std::string &path, const std::string &format, int vectSizeCfg, bool bigEndian,
                             std::vector<float> &raw, int &dim, size_t &frames) {
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) LIA_THROW("Feature file not found: " + path);
@@ -333,7 +338,7 @@ static void readFeatureFile(const std::string &path, const std::string &format, 
       LIA_THROW("Truncated SPRO3 file: " + path);
     }
     off = 16;
-    frames = h[2];
+    frames = bigEndian ? bswap32(h[2]) : h[2];
     if (frames == 0 || (size - off) % (4 * (long)frames) != 0) {
       fclose(f);
       LIA_THROW("Inconsistent SPRO3 header: " + path);
@@ -362,8 +367,31 @@ static void readFeatureFile(const std::string &path, const std::string &format, 
       LIA_THROW("Truncated SPRO4 file: " + path);
     }
     off += 10;
-    dim = d16;
+    dim = bigEndian ? bswap16(d16) : d16;
+    if (dim <= 0) {
+      fclose(f);
+      LIA_THROW("Bad SPRO4 dimension: " + path);
+    }
     frames = (size_t)((size - off) / (4 * (long)dim));
+  } else if (format == "HTK") {
+    // 12-byte big-endian header: int32 nSamples, int32 sampPeriod (100 ns), int16 sampSize (bytes),
+    // int16 parmKind; uncompressed float32 parameters, big-endian
+    uint32_t ns, period;
+    uint16_t ssize, kind;
+    if (fread(&ns, 4, 1, f) != 1 || fread(&period, 4, 1, f) != 1 || fread(&ssize, 2, 1, f) != 1 ||
+        fread(&kind, 2, 1, f) != 1) {
+      fclose(f);
+      LIA_THROW("Truncated HTK file: " + path);
+    }
+    off = 12;
+    frames = bswap32(ns);
+    dim = bswap16(ssize) / 4;
+    kind = bswap16(kind);
+    if ((kind & 0x0400) || dim <= 0 || (long)frames * dim * 4 > size - off) {  // _C: compressed
+      fclose(f);
+      LIA_THROW("Unsupported (compressed) or inconsistent HTK file: " + path);
+    }
+    bigEndian = true;
   } else if (format == "RAW") {
     if (vectSizeCfg <= 0) {
       fclose(f);
@@ -380,19 +408,23 @@ static void readFeatureFile(const std::string &path, const std::string &format, 
   size_t got = fread(raw.data(), 4, raw.size(), f);
   fclose(f);
   if (got != raw.size()) LIA_THROW("Truncated feature file: " + path);
+  if (bigEndian) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(raw.data());
+    for (size_t i = 0; i < raw.size(); i++) w[i] = bswap32(w[i]);
+  }
 }
 
 FeatureServer::FeatureServer(const Config &c, const std::vector<std::string> &files) {
   const std::string path = c.getString("featureFilesPath", ""), ext = c.getString("loadFeatureFileExtension", "");
   const std::string format = c.getString("loadFeatureFileFormat", "SPRO4");
-  if (c.getBool("bigEndian", false)) LIA_THROW("bigEndian feature files are not supported");
+  const bool bigEndian = c.getBool("bigEndian", false);
   std::vector<int> mask;
   if (c.existsParam("featureServerMask")) mask = parseMask(c.getParam("featureServerMask"));
   for (auto &name : files) {
     std::vector<float> raw;
     int dim = 0;
     size_t frames = 0;
-    readFeatureFile(path + name + ext, format, (int)c.getLong("vectSize", 0), raw, dim, frames);
+    readFeatureFile(path + name + ext, format, (int)c.getLong("vectSize", 0), bigEndian, raw, dim, frames);
     std::vector<int> m = mask;
     if (m.empty())
       for (int i = 0; i < dim; i++) m.push_back(i);

@@ -47,6 +47,14 @@ def write_spro3(path, X):
         f.write(np.ascontiguousarray(X, "<f4").tobytes())
 
 
+def write_htk(path, X, period=100000, kind=9):
+    """HTK parameter file: 12-byte big-endian header + big-endian float32 (kind 9 = USER)."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    with open(path, "wb") as f:
+        f.write(struct.pack(">iihh", X.shape[0], period, 4 * X.shape[1], kind))
+        f.write(X.astype(">f4").tobytes())
+
+
 def write_db(path, M):
     M = np.atleast_2d(np.asarray(M, dtype="<f8"))
     with open(path, "wb") as f:

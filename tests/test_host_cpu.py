@@ -22,7 +22,7 @@ def built():
 
 
 def test_programs_exist_and_print_help(built):
-    for p in ("TrainWorld", "ComputeTest", "IvExtractor", "TotalVariability", "IvTest"):
+    for p in ("TrainWorld", "TrainTarget", "ComputeTest", "IvExtractor", "TotalVariability", "IvTest", "IvNorm", "PLDA"):
         out = subprocess.run([os.path.join(built, p), "--help"], capture_output=True, text=True, timeout=60)
         assert out.returncode == 0 and p in out.stdout
 
@@ -70,3 +70,20 @@ def test_file_formats_and_selection(built, tmp_path):
     assert int(r["bagged"][2]) <= 7 and 0 < int(r["bagged"][1]) < len(sel0) + len(sel1)
     assert math.isclose(float(r["setItParameter"][0]), 0.3) and int(r["setItParameter"][1]) == 30
     assert r["exception"] == ["1"]
+    # the same features through the other on-disk formats: HTK (big-endian by definition), SPRO3,
+    # RAW and byte-swapped RAW (bigEndian) -- the FeatureServer block must be identical
+    for fmt, ext, extra in (("HTK", ".htk", {}), ("SPRO3", ".sp3", {}), ("RAW", ".raw", {"vectSize": D0}),
+                            ("RAW", ".rawbe", {"vectSize": D0, "bigEndian": "true"})):
+        for name, X in feats.items():
+            if fmt == "HTK":
+                lf.write_htk(tmp_path / f"{name}{ext}", X)
+            elif fmt == "SPRO3":
+                lf.write_spro3(tmp_path / f"{name}{ext}", X)
+            else:
+                X.astype(">f4" if extra.get("bigEndian") else "<f4").tofile(tmp_path / f"{name}{ext}")
+        out2 = subprocess.run([os.path.join(built, "HostSelfTest"), "--config", str(tmp_path / "t.cfg"),
+                               "--loadFeatureFileFormat", fmt, "--loadFeatureFileExtension", ext] +
+                              [a for k, v in extra.items() for a in (f"--{k}", str(v))],
+                              capture_output=True, text=True, timeout=60)
+        r2 = {l.split()[0]: l.split()[1:] for l in out2.stdout.strip().splitlines()}
+        assert r2["features"] == r["features"] and r2["selected"] == r["selected"], (fmt, ext, out2.stdout)
