@@ -214,6 +214,14 @@ lr_status lr_tv_estimate_w_eigen_decomposition(lr_tv *tv, const double *Dm, cons
  * lr_tv_get_acc expands it to the reference's full [C x R*R]. */
 double *lr_tv_dev_acc(lr_tv *tv);
 size_t lr_tv_acc_len(const lr_tv *tv);
+/* component-sharded M-step (updateTestimate is independent per component, :981-1000):
+ * reduce-scatter the A part of the block by component (lr_tv_acc_a_stride doubles per component,
+ * components contiguous), all-reduce the rest, lr_tv_update_t_range on the rank's components, then
+ * all-gather the new columns of T through lr_tv_pack_t / lr_tv_unpack_t ([R x (c1 - c0) D] blocks). */
+lr_status lr_tv_update_t_range(lr_tv *tv, int c0, int c1);
+lr_status lr_tv_pack_t(lr_tv *tv, int c0, int c1, double *d_dst);
+lr_status lr_tv_unpack_t(lr_tv *tv, int c0, int c1, const double *d_src);
+size_t lr_tv_acc_a_stride(const lr_tv *tv);
 /* after the all-reduce: meanW = sumW / n_speakers_total */
 lr_status lr_tv_finish_estep(lr_tv *tv, double n_speakers_total);
 

@@ -59,7 +59,7 @@ def lib():
     for name in ("lr_gmm_create", "lr_feats_upload", "lr_feats_wrap_device", "lr_tv_create",
                  "lr_tv_dev_N", "lr_tv_dev_F", "lr_tv_dev_acc"):
         getattr(L, name).restype = ct.c_void_p
-    for name in ("lr_gmm_em_stats_len", "lr_tv_acc_len"):
+    for name in ("lr_gmm_em_stats_len", "lr_tv_acc_len", "lr_tv_acc_a_stride"):
         getattr(L, name).restype = ct.c_size_t
     for name in ("lr_gmm_destroy", "lr_feats_destroy", "lr_tv_destroy"):
         getattr(L, name).restype = None
@@ -447,6 +447,19 @@ class TV:
         Dm, Q = _f64(Dm), _f64(Q)
         assert Dm.shape == (self.C, self.R) and Q.shape == (self.R, self.R)
         _check(lib().lr_tv_estimate_w_eigen_decomposition(self.h, _d(Dm), _d(Q)))
+
+    # ---- component-sharded M-step (multi-GPU)
+    def update_t_range(self, c0, c1):
+        _check(lib().lr_tv_update_t_range(self.h, int(c0), int(c1)))
+
+    def pack_t(self, c0, c1, dev_ptr):
+        _check(lib().lr_tv_pack_t(self.h, int(c0), int(c1), ct.c_void_p(int(dev_ptr))))
+
+    def unpack_t(self, c0, c1, dev_ptr):
+        _check(lib().lr_tv_unpack_t(self.h, int(c0), int(c1), ct.c_void_p(int(dev_ptr))))
+
+    def acc_a_stride(self):
+        return int(lib().lr_tv_acc_a_stride(self.h))
 
     def dev_acc(self):
         return int(lib().lr_tv_dev_acc(self.h))

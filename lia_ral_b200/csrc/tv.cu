@@ -814,36 +814,67 @@ lr_status lr_tv_finish_estep(lr_tv *tv, double n_speakers_total) {
   return LR_OK;
 }
 
-lr_status lr_tv_update_t(lr_tv *tv) {
+// M-step of the components [c0, c1): T_c = A_c^-1 Cmx_c (updateTestimate :981-1000 is independent
+// per component, so a multi-GPU run gives every rank C / world of them).
+lr_status lr_tv_update_t_range(lr_tv *tv, int c0, int c1) {
   LR_READY();
-  LR_REQUIRE(tv, "lr_tv_update_t: null handle");
+  LR_REQUIRE(tv && c0 >= 0 && c0 < c1 && c1 <= tv->C, "lr_tv_update_t_range: bad component range");
   Engine &e = engine();
-  const int R = tv->R, C = tv->C, D = tv->D;
+  const int R = tv->R, D = tv->D, nc = c1 - c0;
   const size_t rr = (size_t)R * R;
   const double one = 1.0;
   // factor a copy of A in the TETt buffer (TETt is re-estimated from the new T anyway)
-  k_unpack_lower<<<grid_for((size_t)C * rr), 256, 0, e.stream>>>((size_t)C, R, tv->A(), tv->d_tett,
-                                                                0.0, 0);
+  k_unpack_lower<<<grid_for((size_t)nc * rr), 256, 0, e.stream>>>((size_t)nc, R, tv->A() + (size_t)c0 * tv->Rp(),
+                                                                 tv->d_tett + (size_t)c0 * rr, 0.0, 0);
   LR_CHECK_LAUNCH();
-  LR_CUSOLVER(cusolverDnDpotrfBatched(tv->solver, CUBLAS_FILL_MODE_LOWER, R, tv->d_ptr_A, R,
-                                      tv->d_info, C));
+  LR_CUSOLVER(cusolverDnDpotrfBatched(tv->solver, CUBLAS_FILL_MODE_LOWER, R, tv->d_ptr_A + c0, R,
+                                      tv->d_info, nc));
   count_launch();
-  lr_status st = check_factor(tv, C, "M-step accumulator A_c");
+  lr_status st = check_factor(tv, nc, "M-step accumulator A_c");
   if (st != LR_OK) return st;
   // T_c = A_c^-1 Cmx_c: column-major we hold T_c^T (D x R, ld sv): X^T L L^T = Cmx_c^T
-  LR_CUDA(cudaMemcpyAsync(tv->d_T, tv->Cmx(), (size_t)R * tv->sv * sizeof(double),
-                          cudaMemcpyDeviceToDevice, e.stream));
+  LR_CUDA(cudaMemcpy2DAsync(tv->d_T + (size_t)c0 * D, tv->sv * sizeof(double), tv->Cmx() + (size_t)c0 * D,
+                            tv->sv * sizeof(double), (size_t)nc * D * sizeof(double), R,
+                            cudaMemcpyDeviceToDevice, e.stream));
   LR_CUBLAS(cublasDtrsmBatched(e.blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T,
-                               CUBLAS_DIAG_NON_UNIT, D, R, &one, tv->d_ptr_A, R, tv->d_ptr_Tc,
-                               (int)tv->sv, C));
+                               CUBLAS_DIAG_NON_UNIT, D, R, &one, tv->d_ptr_A + c0, R, tv->d_ptr_Tc + c0,
+                               (int)tv->sv, nc));
   count_launch();
   LR_CUBLAS(cublasDtrsmBatched(e.blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N,
-                               CUBLAS_DIAG_NON_UNIT, D, R, &one, tv->d_ptr_A, R, tv->d_ptr_Tc,
-                               (int)tv->sv, C));
+                               CUBLAS_DIAG_NON_UNIT, D, R, &one, tv->d_ptr_A + c0, R, tv->d_ptr_Tc + c0,
+                               (int)tv->sv, nc));
   count_launch();
   LR_CUDA(cudaStreamSynchronize(e.stream));
   return LR_OK;
 }
+
+lr_status lr_tv_update_t(lr_tv *tv) {
+  LR_READY();
+  LR_REQUIRE(tv, "lr_tv_update_t: null handle");
+  return lr_tv_update_t_range(tv, 0, tv->C);
+}
+
+// The columns of T that belong to the components [c0, c1) as one contiguous device block
+// [R x (c1 - c0) D] (and back): the all-gather payload of the component-sharded M-step.
+lr_status lr_tv_pack_t(lr_tv *tv, int c0, int c1, double *d_dst) {
+  LR_READY();
+  LR_REQUIRE(tv && d_dst && c0 >= 0 && c0 < c1 && c1 <= tv->C, "lr_tv_pack_t: bad arguments");
+  const size_t w = (size_t)(c1 - c0) * tv->D * sizeof(double);
+  LR_CUDA(cudaMemcpy2DAsync(d_dst, w, tv->d_T + (size_t)c0 * tv->D, tv->sv * sizeof(double), w, tv->R,
+                            cudaMemcpyDeviceToDevice, engine().stream));
+  return LR_OK;
+}
+lr_status lr_tv_unpack_t(lr_tv *tv, int c0, int c1, const double *d_src) {
+  LR_READY();
+  LR_REQUIRE(tv && d_src && c0 >= 0 && c0 < c1 && c1 <= tv->C, "lr_tv_unpack_t: bad arguments");
+  const size_t w = (size_t)(c1 - c0) * tv->D * sizeof(double);
+  LR_CUDA(cudaMemcpy2DAsync(tv->d_T + (size_t)c0 * tv->D, tv->sv * sizeof(double), d_src, w, w, tv->R,
+                            cudaMemcpyDeviceToDevice, engine().stream));
+  return LR_OK;
+}
+// length (doubles) of the packed A_c block of ONE component inside lr_tv_dev_acc (components are
+// contiguous: a reduce-scatter by component works on the block directly)
+size_t lr_tv_acc_a_stride(const lr_tv *tv) { return tv ? tv->Rp() : 0; }
 
 lr_status lr_tv_min_divergence(lr_tv *tv, double n_sessions) {
   LR_READY();

@@ -3,7 +3,8 @@
 The data path shards embarrassingly (frames for TrainWorld, utterances for TotalVariability /
 IvExtractor); the ONLY exchange is one all-reduce of sufficient statistics per EM iteration -- the
 analogue of `emAcc.addAccEM` merging per-thread accumulators (AccumulateStat.cpp:286-292) and of
-the mutex-guarded A / C updates (AccumulateTVStat.cpp:1920-1937).  `torch.distributed` is plumbing:
+the mutex-guarded A / C updates (AccumulateTVStat.cpp:1920-1937) -- or, for TotalVariability, its
+component-sharded form (reduce-scatter A, M-step on C / world components, all-gather T).  `torch.distributed` is plumbing:
 NCCL on GPUs, gloo in the CPU tests.
 """
 import torch
@@ -67,6 +68,61 @@ def tv_allreduce_estep(tv, n_speakers_local, stream=None):
         torch.cuda.synchronize()
     tv.finish_estep(float(n_total.item()))
     return float(n_total.item())
+
+
+def tv_sharded_mstep(tv, n_speakers_local, stream=None):
+    """Component-sharded exchange + M-step of one TotalVariability iteration: after
+    lr_tv_estimate_a_and_c on this rank's utterances,
+      reduce-scatter A by component (each rank receives the sum of ITS C / world components),
+      all-reduce [Cmx | R | r | sumW], meanW = sumW / total speakers,
+      updateTestimate on the rank's components only (it is independent per component, :981-1000),
+      all-gather the new columns of T.
+    minDivergence (replicated, O(R^2 C D)) follows on every rank.  Needs C % world == 0; falls back to
+    the single all-reduce + replicated M-step otherwise.  Returns the total speaker count."""
+    rank, ws = world()
+    C = tv.C
+    if ws == 1 or C % ws != 0:
+        n_total = tv_allreduce_estep(tv, n_speakers_local, stream)
+        tv.update_t()
+        return n_total
+    ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+    stride, cw = tv.acc_a_stride(), C // ws
+    acc = _device_tensor(tv.dev_acc(), tv.acc_len())
+    a_part, rest = acc[:C * stride], acc[C * stride:]
+    with ctx:
+        mine = torch.empty(cw * stride, dtype=torch.float64, device="cuda")
+        dist.reduce_scatter_tensor(mine, a_part)
+        a_part[rank * cw * stride:(rank + 1) * cw * stride].copy_(mine)
+        dist.all_reduce(rest)
+        n_total = torch.tensor([float(n_speakers_local)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(n_total)
+    torch.cuda.synchronize()
+    tv.finish_estep(float(n_total.item()))
+    tv.update_t_range(rank * cw, (rank + 1) * cw)
+    blk = tv.R * cw * tv.D
+    with ctx:
+        send = torch.empty(blk, dtype=torch.float64, device="cuda")
+        recv = torch.empty(ws * blk, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    from . import capi
+    tv.pack_t(rank * cw, (rank + 1) * cw, send.data_ptr())
+    capi.synchronize()   # the library enqueues on its own stream
+    with ctx:
+        dist.all_gather_into_tensor(recv, send)
+    torch.cuda.synchronize()
+    for r in range(ws):
+        if r != rank:
+            tv.unpack_t(r * cw, (r + 1) * cw, recv.data_ptr() + r * blk * 8)
+    capi.synchronize()
+    return float(n_total.item())
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def _device_tensor(ptr, n_doubles):

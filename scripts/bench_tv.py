@@ -20,6 +20,7 @@ capi.init(local)
 C, D, R = 2048, 60, int(os.environ.get("R", 600))
 U = int(os.environ.get("U_PER_GPU", 2048))
 ITERS = int(os.environ.get("ITERS", 3))
+SHARD = os.environ.get("SHARD_MSTEP", "1") == "1" and world > 1
 w, mean, cov = synth.make_ubm(C, D, seed=1)
 invvar = (1.0 / cov).reshape(-1)
 N, F = synth.make_bw_stats(U, w, mean, cov, frames_per_utt=3000, active=64, seed=5 + rank)
@@ -35,9 +36,14 @@ for it in range(ITERS + 1):   # first iteration = warm-up
     t0 = time.perf_counter()
     tv.subtract_m(); tv.estimate_tett(); tv.estimate_a_and_c()
     capi.synchronize(); t1 = time.perf_counter()
-    lrd.tv_allreduce_estep(tv, U)
-    torch.cuda.synchronize(); t2 = time.perf_counter()
-    tv.update_t(); tv.min_divergence(float(U * world))
+    if SHARD:   # reduce-scatter A, M-step on C / world components, all-gather T
+        lrd.tv_sharded_mstep(tv, U)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+    else:       # one all-reduce of the whole block, replicated M-step
+        lrd.tv_allreduce_estep(tv, U)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        tv.update_t()
+    tv.min_divergence(float(U * world))
     capi.synchronize(); t3 = time.perf_counter()
     if it > 0:
         t_e.append(t1 - t0); t_ar.append(t2 - t1); t_m.append(t3 - t2)
@@ -51,6 +57,8 @@ if rank == 0:
                       "utterances_per_gpu": U, "seconds_per_iteration": t[0], "estep_s": t[1], "allreduce_s": t[2],
                       "mstep_mindiv_s": t[3], "value": U * world / t[0], "unit": "utterances/s",
                       "estep_algorithmic_tflops_total": flop / t[1] / 1e12,
-                      "allreduce_bytes": tv.acc_len() * 8, "scaling": "weak"}))
+                      "allreduce_bytes": tv.acc_len() * 8, "scaling": "weak",
+                      "exchange": "reduce-scatter A + all-reduce rest + sharded M-step + all-gather T (timed under allreduce_s)" if SHARD
+                      else "one all-reduce, replicated M-step"}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
