@@ -247,6 +247,11 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version
+    # there) are sent to stderr until the result is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -407,7 +412,10 @@ def main():
             out["ivectors"] = iv
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"], _, _ = cpu_baseline()
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
