@@ -222,7 +222,7 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "TrainWorld EM iteration, 2048c/60d diagonal UBM, 10M frames/GPU (configs[1])",
                    "components": C, "dim": D, "frames_per_step": n,
-                   "sample": "each step is a bounded sample of the workload (the CPU path needs ~100 s per 10 M frames x 1 iteration per 1000 cores)"},
+                   "sample": "each step is a bounded sample of the workload, sized from a probe to about 8 s of host time"},
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
