@@ -290,6 +290,12 @@ class PldaModel {
 std::string efrMatrixFilename(const Config &c, unsigned long it, bool forLoad);
 std::string efrMeanFilename(const Config &c, unsigned long it, bool forLoad);
 
+// score output of IvTest (IvTest.cpp:412-465): outputScoreFormat ascii = one NIST line per trial,
+// segments outer / models inner in matrix order; binary = <out>_model.txt, <out>_testSeg.txt and the
+// [models x segments] score matrix saved as <out> + saveMatrixFilesExtension
+void writeIvTestScores(const Config &c, const Matrix &scores, const std::vector<uint8_t> &trials,
+                       const std::vector<std::string> &modelIds, const std::vector<std::string> &segIds);
+
 // ---- drivers: int Foo(Config&) like the reference programs
 int TrainWorld(Config &c);        // LIA_SpkDet/TrainWorld/src/TrainWorld.cpp:101
 int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:90

@@ -287,10 +287,36 @@ void PldaDev::applySphericalNuisanceNormalization(const Config &c) {
   computeAll();
 }
 
-// the cosine / mahalanobis / 2cov branches of IvTest (IvTest.cpp:112-391); returns the score
-// matrix [models x segments] and fills ids / trial lines for the NIST output written by the caller
-bool IvTestNonPlda(Config &c, const std::string &scoring, Matrix &scores, std::vector<std::vector<std::string>> &trialLines,
-                   std::map<std::string, int> &modelIndex, std::map<std::string, int> &segIndex) {
+void writeIvTestScores(const Config &c, const Matrix &scores, const std::vector<uint8_t> &trials,
+                       const std::vector<std::string> &modelIds, const std::vector<std::string> &segIds) {
+  const size_t nm = modelIds.size(), nt = segIds.size();
+  if (scores.rows != nm || scores.cols != nt || trials.size() != nm * nt) LIA_THROW("writeIvTestScores: dimension mismatch");
+  const std::string out = c.getParam("outputFilename");
+  const std::string format = c.getString("outputScoreFormat", "ascii");
+  if (format == "ascii") {
+    const std::string gender = c.getString("gender", "M");
+    const double threshold = c.getDouble("decisionThreshold", 0.0);
+    std::ofstream os(out.c_str(), std::ios::out | std::ios::trunc);
+    for (size_t s = 0; s < nt; s++)
+      for (size_t m = 0; m < nm; m++)
+        if (trials[m * nt + s]) {
+          const double v = scores(m, s);  // "gender client decision seg LLR" (IOFormat.cpp:112-120)
+          os << gender << " " << modelIds[m] << " " << (v > threshold ? 1 : 0) << " " << segIds[s] << " " << v << std::endl;
+        }
+  } else if (format == "binary") {
+    std::ofstream om((out + "_model.txt").c_str(), std::ios::out | std::ios::trunc);
+    for (auto &m : modelIds) om << m << std::endl;
+    std::ofstream osg((out + "_testSeg.txt").c_str(), std::ios::out | std::ios::trunc);
+    for (auto &sg : segIds) osg << sg << std::endl;
+    scores.save(out + c.getString("saveMatrixFilesExtension", ""), c.getString("saveMatrixFormat", "DB"));
+  } else {
+    LIA_THROW("outputScoreFormat must be ascii or binary, got " + format);
+  }
+}
+
+// the cosine / mahalanobis / 2cov branches of IvTest (IvTest.cpp:112-391), output included
+void IvTestNonPlda(Config &c, const std::string &scoring) {
+  Matrix scores;
   const std::string mpath = c.getString("matrixFilesPath", "");
   const std::string lext = c.getString("loadMatrixFilesExtension", ""), sext = c.getString("saveMatrixFilesExtension", "");
   const std::string lfmt = c.getString("loadMatrixFormat", "DB"), sfmt = c.getString("saveMatrixFormat", "DB");
@@ -360,10 +386,7 @@ bool IvTestNonPlda(Config &c, const std::string &scoring, Matrix &scores, std::v
     LIA_CHECK(lr_iv_two_cov_scoring((int)d, nm, nt, test.models.data.data(), test.segments.data.data(), W.data.data(),
                                     B.data.data(), scores.data.data()));
   }
-  trialLines = test.trialLines;
-  modelIndex = test.modelIndex;
-  segIndex = test.segIndex;
-  return true;
+  writeIvTestScores(c, scores, test.trials, test.modelIds, test.segIds);
 }
 
 // ------------------------------------------------------------------ PldaModel (training)

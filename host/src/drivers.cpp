@@ -318,25 +318,13 @@ int TotalVariability(Config &c) {
 // ------------------------------------------------------------------ IvTest
 // cosine / mahalanobis / 2cov branches and PLDA training live in backend.cpp
 void IvTestTrainPlda(Config &c);
-bool IvTestNonPlda(Config &c, const std::string &scoring, Matrix &scores, std::vector<std::vector<std::string>> &trialLines,
-                   std::map<std::string, int> &modelIndex, std::map<std::string, int> &segIndex);
+void IvTestNonPlda(Config &c, const std::string &scoring);
 
 int IvTest(Config &c) {
   try {
     const std::string scoring = c.getString("scoring", "plda");
-    const std::string gender = c.getString("gender", "M");
-    const double threshold = c.getDouble("decisionThreshold", 0.0);
     if (scoring == "cosine" || scoring == "mahalanobis" || scoring == "2cov") {
-      Matrix sc;
-      std::vector<std::vector<std::string>> lines;
-      std::map<std::string, int> mi, si;
-      IvTestNonPlda(c, scoring, sc, lines, mi, si);
-      std::ofstream out(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
-      for (auto &l : lines)
-        for (size_t e = 1; e < l.size(); e++) {
-          const double v = sc(mi[l[e]], si[l[0]]);
-          outputResultLine(v, l[e], l[0], gender, setDecision(v, threshold), out);
-        }
+      IvTestNonPlda(c, scoring);
       return 0;
     }
     if (scoring != "plda") {
@@ -432,16 +420,11 @@ int IvTest(Config &c) {
                                        Sigma.data.data(), models.data.data(), nEnrol, modelOf.data(), nModels,
                                        segments.data.data(), nTest, scores.data.data()));
     }
-    // NIST ascii output of the trials listed in the NDX (IvTest.cpp:415-439)
-    std::ofstream outNist(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
-    for (auto &l : trials.lines()) {
-      int s = segIndex[l[0]];
-      for (size_t e = 1; e < l.size(); e++) {
-        int m = modelIndex[l[e]];
-        double sc = scores(m, s);
-        outputResultLine(sc, l[e], l[0], gender, setDecision(sc, threshold), outNist);
-      }
-    }
+    // output (IvTest.cpp:412-465): the trials listed in the NDX, segment-major in matrix order
+    std::vector<uint8_t> mask(nModels * nTest, 0);
+    for (auto &l : trials.lines())
+      for (size_t e = 1; e < l.size(); e++) mask[(size_t)modelIndex[l[e]] * nTest + segIndex[l[0]]] = 1;
+    writeIvTestScores(c, scores, mask, modelIds, segIds);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }

@@ -57,6 +57,23 @@ int main(int argc, char **argv) {
     for (auto &s : bag) maxlen = std::max(maxlen, s.length);
     std::cout << "bagged " << bag.size() << " " << lia::totalFrame(bag) << " " << maxlen << "\n";
     std::cout << "setItParameter " << lia::setItParameter(0.5, 0.1, 5, 2) << " " << lia::timeToFrameIdx(0.299999999, 0.01) << "\n";
+    {  // IvTest score output: ascii (segments outer, models inner, trial mask) and binary
+      lia::Matrix sc(2, 3);
+      for (size_t i = 0; i < 6; i++) sc.data[i] = 0.5 * (double)i - 1.0;
+      std::vector<uint8_t> mask = {1, 0, 1, 1, 1, 0};
+      lia::Config oc = c;
+      oc.setParam("outputFilename", c.getParam("tmpPrefix") + "_scores.res");
+      oc.setParam("gender", "F");
+      lia::writeIvTestScores(oc, sc, mask, {"m0", "m1"}, {"s0", "s1", "s2"});
+      oc.setParam("outputScoreFormat", "binary");
+      oc.setParam("outputFilename", c.getParam("tmpPrefix") + "_scores");
+      oc.setParam("saveMatrixFilesExtension", ".mat");
+      oc.setParam("saveMatrixFormat", "DB");
+      lia::writeIvTestScores(oc, sc, mask, {"m0", "m1"}, {"s0", "s1", "s2"});
+      lia::Matrix back;
+      back.load(c.getParam("tmpPrefix") + "_scores.mat", "DB");
+      std::cout << "scores_binary " << back.rows << " " << back.cols << " " << back.data[5] << "\n";
+    }
     try {
       c.getParam("noSuchParameter");
     } catch (lia::Exception &e) {

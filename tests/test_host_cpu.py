@@ -70,6 +70,13 @@ def test_file_formats_and_selection(built, tmp_path):
     assert int(r["bagged"][2]) <= 7 and 0 < int(r["bagged"][1]) < len(sel0) + len(sel1)
     assert math.isclose(float(r["setItParameter"][0]), 0.3) and int(r["setItParameter"][1]) == 30
     assert r["exception"] == ["1"]
+    # IvTest score output (IvTest.cpp:412-465): segments outer, models inner, masked; binary variant
+    lines = [l.split() for l in open(str(tmp_path / "tmp") + "_scores.res")]
+    assert lines == [["F", "m0", "0", "s0", "-1"], ["F", "m1", "1", "s0", "0.5"], ["F", "m1", "1", "s1", "1"],
+                     ["F", "m0", "0", "s2", "0"]]
+    assert open(str(tmp_path / "tmp") + "_scores_model.txt").read().split() == ["m0", "m1"]
+    assert open(str(tmp_path / "tmp") + "_scores_testSeg.txt").read().split() == ["s0", "s1", "s2"]
+    assert r["scores_binary"] == ["2", "3", "1.5"]
     # the same features through the other on-disk formats: HTK (big-endian by definition), SPRO3,
     # RAW and byte-swapped RAW (bigEndian) -- the FeatureServer block must be identical
     for fmt, ext, extra in (("HTK", ".htk", {}), ("SPRO3", ".sp3", {}), ("RAW", ".raw", {"vectSize": D0}),
