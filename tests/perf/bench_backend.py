@@ -4,7 +4,7 @@ approximate i-vector extraction (ubmWeight / eigenDecomposition), the PldaDev st
 normalisation matrices, cosine / Mahalanobis / two-covariance scoring, one PLDA EM iteration.
 Writes one JSON object per line; summarised in profiles/r01_extra.md."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from lia_ral_b200 import capi, synth
 from oracle.ffi import Oracle

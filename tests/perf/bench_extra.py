@@ -4,7 +4,7 @@ each with the CPU restatement of the reference loop (oracle -O3 -ffast-math buil
 threads where the reference has a threaded variant) timed beside it on a bounded sample.
 Writes one JSON object per line; results are summarised under profiles/."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from lia_ral_b200 import capi, synth
 

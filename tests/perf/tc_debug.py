@@ -1,6 +1,6 @@
 """Bring-up check of the tcgen05 path against the SIMT path and the oracle (run on the GPU box)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from lia_ral_b200 import capi, synth
 from oracle.ffi import Oracle
