@@ -13,7 +13,8 @@
 // as the K-major operand of the likelihood GEMM and, read MN-major, as the B operand of the
 // statistics GEMM.  Each CTA owns a slice of 128 components whose weights (64 KB) stay resident
 // in shared memory for the whole kernel; the grid is (slices x groups), every group streaming a
-// contiguous range of frame tiles through a two-stage mbarrier ring.
+// contiguous range of frame tiles through an mbarrier ring (pass 1: two 64 KB tiles, pass 2: five
+// 32 KB half tiles).
 //
 // Pass 1 (k_tc_lse):   D[t, c] = A W^T  (frames on TMEM lanes), per-frame online (max, sum) over
 //                      the slice's 128 columns -> partial log-sum-exp per (slice, frame).
@@ -405,7 +406,7 @@ constexpr size_t kTcSmem = 1024 + 64 * 1024 + kHStages * (size_t)kHalfBytes + 25
 struct Smem {
   uint32_t w;           // weights slice: hi a | hi b | lo a | lo b
   uint32_t stage[kStages];     // pass 1: 2 x 64 KB
-  uint32_t hstage[kHStages];   // pass 2: 4 x 32 KB (same memory)
+  uint32_t hstage[kHStages];   // pass 2: 5 x 32 KB (same memory)
   uint32_t full[kHStages], empty[kHStages];
   uint32_t s_full[3], s_empty[2], p_full[3], s_free[3];
   uint32_t f_full, f_empty, w_full;
@@ -662,8 +663,8 @@ __global__ void k_tc_combine(int n_slices, long P, long P_pad, const unsigned *_
 }
 
 // ------------------------------------------------------------------ pass 2
-// Pipeline unit = half tile (64 frames, 4 x 8 KB half panels) through a 4-stage ring, so the
-// bulk loads run three half tiles ahead of the tensor pipe.
+// Pipeline unit = half tile (64 frames, 4 x 8 KB half panels) through a 5-stage ring, so the
+// bulk loads run up to four half tiles ahead of the tensor pipe.
 // TMEM columns: three S buffers of 64 columns at 0, 64, 128 (the fp16 posteriors overwrite the
 // first 16 columns of each 32-column half in place), the HI weights at 192..255 and the
 // statistics accumulator at 256..511.
