@@ -23,10 +23,13 @@ struct Engine {
   cudaStream_t copy_stream = nullptr;  // H2D staging for the host-buffer entry points
   cublasHandle_t blas = nullptr;
   uint64_t launches = 0;
-  int gmm_kernel = 0;  // 0 auto, 1 simt, 2 tcgen05
-  int tc_debug = 0;    // profiling experiments only (lr_debug_flags): results are WRONG when set
+  int gmm_kernel = 0;  // 0 auto, 1 simt, 2 tcgen05 (one-pass statistics), 3 tcgen05 two-pass
+  int tc_debug = 0;    // profiling experiments only (LR_TC_DEBUG builds): results are WRONG when set
+  // per-device "cudaFuncSetAttribute done" flags (reset by lr_shutdown: the attribute is per context)
+  enum { kAttrTc = 0, kAttrSimtLse, kAttrSimtAcc, kAttrTopk, kAttrTvDiag, kAttrTvGemm, kAttrPlda, kAttrCount };
+  bool attr_set[kAttrCount] = {};
   // grow-only device scratch slots reused across calls (freed by lr_shutdown)
-  static constexpr int kScratchSlots = 13;
+  static constexpr int kScratchSlots = 14;
   void *scratch[kScratchSlots] = {};
   size_t scratch_cap[kScratchSlots] = {};
   cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
@@ -45,7 +48,7 @@ struct ProfileScope {
 
 enum ScratchSlot {
   kSlotX0 = 0, kSlotX1, kSlotLse, kSlotIndex, kSlotChunks, kSlotS, kSlotStats, kSlotLlk,
-  kSlotIdx, kSlotRest, kSlotTmpA, kSlotTmpB, kSlotSpans
+  kSlotIdx, kSlotRest, kSlotTmpA, kSlotTmpB, kSlotSpans, kSlotXchg
 };
 // returns nullptr (and sets the error) on allocation failure
 void *scratch_get(int slot, size_t bytes);

@@ -135,6 +135,7 @@ lr_status lr_shutdown(void) {
   if (e.copy_stream) cudaStreamSynchronize(e.copy_stream);
   profile_clear();
   e.profile = false;
+  for (bool &b : e.attr_set) b = false;
   for (int i = 0; i < Engine::kScratchSlots; i++) {
     if (e.scratch[i]) cudaFree(e.scratch[i]);
     e.scratch[i] = nullptr;
@@ -194,7 +195,8 @@ lr_status lr_profile_read(int kind, double *total_ms, uint64_t *n_launches) {
 }
 
 lr_status lr_set_gmm_kernel(int which) {
-  LR_REQUIRE(which >= 0 && which <= 2, "kernel selector must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+  LR_REQUIRE(which >= 0 && which <= 3,
+             "kernel selector must be 0 (auto), 1 (simt), 2 (tcgen05) or 3 (tcgen05, two-pass statistics)");
   engine().gmm_kernel = which;
   return LR_OK;
 }

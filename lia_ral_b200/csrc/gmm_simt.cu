@@ -322,7 +322,7 @@ lr_status gmm_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, float *d_S
   if (fl.P <= 0) return LR_OK;
   Engine &e = engine();
   size_t sm = lse_smem(g->D);
-  static bool attr_set = false;
+  bool &attr_set = engine().attr_set[Engine::kAttrSimtLse];
   if (!attr_set) {
     LR_CUDA(cudaFuncSetAttribute(k_lse, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
@@ -342,7 +342,7 @@ lr_status gmm_pass_acc(lr_gmm *g, const FrameList &fl, const float *d_lse2,
   if (n_chunks <= 0) return LR_OK;
   Engine &e = engine();
   size_t sm = acc_smem(g->D);
-  static bool attr_set = false;
+  bool &attr_set = engine().attr_set[Engine::kAttrSimtAcc];
   if (!attr_set) {
     LR_CUDA(cudaFuncSetAttribute(k_acc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  100 * 1024));

@@ -981,6 +981,547 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------ one-pass kernel
+// Likelihood GEMM, per-frame log-sum-exp and statistics GEMM in ONE sweep over the frames: the
+// per-frame normaliser is not precomputed by a first pass, it is exchanged between the slice-CTAs
+// of a frame group while the posteriors wait in TMEM.
+//
+// Per CTA (slice of 128 components, one frame group) and half tile h (64 frames):
+//   G1(h)   : S[c, t] = W A^T, ALL weights (hi and lo) resident in TMEM -> 24 TS UMMAs that read only
+//             the frame half panels from shared memory
+//   epi-1(h): S is read with the 16x256b TMEM shape (a thread holds 4 component rows x 16 frame
+//             columns), so the per-frame max / sum over the 128 lanes is 3 in-thread steps, a 3-step
+//             shuffle reduce-scatter and a 4-way combine through shared memory.  The slice's (max, sum)
+//             of every frame goes to the group's exchange ring in global memory as ONE 64-bit word whose
+//             top bit is the ring-lap tag (data = flag: no fence, no counter); the posteriors wait as
+//             fp16(2^14 2^(S - max_slice)) in one of kNP TMEM slots
+//   epi-2(h): (one team iteration later) poll the n_slices words of each frame, combine -> lse,
+//             rescale the waiting posteriors by 2^(max_slice - lse) (fp16 mantissa x exact power of 2)
+//   G2(h)   : F[c, :] += P[c, t] A[t, :] as TS UMMAs, the hi and the lo frame panels accumulated into
+//             the SAME columns (EM: [xh,1 | xh^2] = 128 columns, BW: [xh,1] = 64), so the accumulator
+//             takes a quarter of TMEM instead of half
+// TMEM: accumulator [0,128) | weights hi a, hi b, lo a, lo b [128,256) | S 2 x 64 [256,384) |
+//       posterior slots 4 x 32 [384,512).
+// All CTAs of a group advance in lock step (each needs every slice's partials), so the grid must be
+// co-resident: launched cooperatively with grid <= SM count.
+constexpr int kNP = 4;        // waiting posterior slots
+constexpr int kXRing = 16;    // exchange ring slots per group (>= 2 kNP, see tc_run_stats_one)
+constexpr int kOColAcc = 0, kOColW = 128, kOColS = 256, kOColP = 384;
+
+struct SmemOne {
+  uint32_t w, hstage[kHStages];
+  uint32_t full[kHStages], empty[kHStages];
+  uint32_t s_full[2], s_free[2], p_ready[kNP], p_free[kNP];
+  uint32_t f_full, f_empty, w_full, w_tmem, tmem_slot;
+};
+
+__device__ __forceinline__ SmemOne carve_one(unsigned char *raw) {
+  const uint32_t base = carve_base(raw);
+  SmemOne s;
+  s.w = base;
+  for (int i = 0; i < kHStages; i++) s.hstage[i] = base + 64 * 1024 + i * kHalfBytes;
+  uint32_t b = base + 64 * 1024 + kHStages * kHalfBytes;
+  for (int i = 0; i < kHStages; i++) {
+    s.full[i] = b + 8 * i;
+    s.empty[i] = b + 40 + 8 * i;
+  }
+  for (int i = 0; i < 2; i++) {
+    s.s_full[i] = b + 80 + 8 * i;
+    s.s_free[i] = b + 96 + 8 * i;
+  }
+  for (int i = 0; i < kNP; i++) {
+    s.p_ready[i] = b + 112 + 8 * i;
+    s.p_free[i] = b + 144 + 8 * i;
+  }
+  s.f_full = b + 176;
+  s.f_empty = b + 184;
+  s.w_full = b + 192;
+  s.w_tmem = b + 200;
+  s.tmem_slot = b + 208;
+  static_assert(kNP == 4 && kHStages == 5, "barrier block layout");
+  return s;
+}
+
+// 16 lanes x 256 bits, 8 repeats along the columns: thread t of the warp receives the lanes
+// (t / 4) and (t / 4 + 8) of the 16-lane group addressed, columns 8 j + 2 (t % 4) + e, in register
+// 4 j + 2 rs + e  (j = 0..7 repeat, rs = 0/1 lane select, e = 0/1).
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 16 lanes x 128 bits, 8 repeats: lanes (t / 4), (t / 4 + 8), column 4 j + (t % 4) in register 2 j + rs
+__device__ __forceinline__ void tmem_ld_16x128b_x8(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x128b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x128b_x8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// One step of the lane reduce-scatter: the lanes whose bit `xr` is set keep the upper half of
+// in[0 .. 2n), the others the lower half; the halves not kept are combined into the partner.
+template <int N, bool MAX>
+__device__ __forceinline__ void lane_halve(const float (&in)[2 * N], float (&out)[N], bool up,
+                                           int xr) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const float mine = up ? in[N + i] : in[i];
+    const float send = up ? in[i] : in[N + i];
+    const float got = __shfl_xor_sync(0xFFFFFFFFu, send, xr);
+    out[i] = MAX ? fmaxf(mine, got) : mine + got;
+  }
+}
+
+template <bool EM>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
+         const unsigned char *__restrict__ Xh, const int *__restrict__ group_tiles,
+         const TileInfo *__restrict__ tinfo, unsigned long long *xch,
+         float *__restrict__ lse_out, const unsigned *__restrict__ index, long P,
+         double *llk_sum, const double *__restrict__ g, const double *__restrict__ s, double fw,
+         double *__restrict__ out_N, double *__restrict__ out_F, double *__restrict__ out_S2,
+         int dbg) {
+  constexpr int N2 = EM ? 128 : 64;  // statistics columns: [xh, 1 | xh^2] or [xh, 1]
+  constexpr uint32_t idesc1 = make_idesc(128, 64, 0, 0);
+  constexpr uint32_t idesc2 = make_idesc(128, N2, 0, 1);
+  constexpr int kHF = 64;
+  extern __shared__ unsigned char smem_raw[];
+  const SmemOne sm = carve_one(smem_raw);
+  unsigned char *base_ptr = smem_raw + (carve_base(smem_raw) - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % n_slices, group = blockIdx.x / n_slices;
+  const int t_begin = group_tiles[group], t_end = group_tiles[group + 1];
+  const int n_half = 2 * (t_end - t_begin);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kHStages; i++) {
+      mbar_init(sm.full[i], 1);
+      mbar_init(sm.empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(sm.s_full[i], 1);
+      mbar_init(sm.s_free[i], 4);  // the four warps of the team that read the buffer
+    }
+    for (int i = 0; i < kNP; i++) {
+      mbar_init(sm.p_ready[i], 4);
+      mbar_init(sm.p_free[i], 1);
+    }
+    mbar_init(sm.f_full, 1);
+    mbar_init(sm.f_empty, kEpiWarps);
+    mbar_init(sm.w_full, 1);
+    mbar_init(sm.w_tmem, kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(sm.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot));
+  const uint32_t tmem_f = tmem_base + kOColAcc;
+
+  if (warp == 0) {
+    // ---- bulk-copy producer
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(sm.w_full, 4 * kPanelBytes);
+      for (int p = 0; p < 4; p++)
+        bulk_g2s(sm.w + p * kPanelBytes, Wp + (size_t)slice * 4 * kPanelBytes + (size_t)p * kPanelBytes,
+                 kPanelBytes, sm.w_full);
+    }
+    for (int h = 0; h < n_half; h++) {
+      const int st = h % kHStages;
+      mbar_wait(sm.empty[st], ((h / kHStages) & 1) ^ 1);
+      if (leader) {
+        mbar_expect_tx(sm.full[st], kHalfBytes);
+        const unsigned char *src =
+            Xh + (size_t)(t_begin + (h >> 1)) * kTileBytes + (size_t)(h & 1) * kHalfPanel;
+        for (int p = 0; p < 4; p++)
+          bulk_g2s(sm.hstage[st] + p * kHalfPanel, src + (size_t)p * kPanelBytes, kHalfPanel,
+                   sm.full[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---- likelihood-GEMM issuer: hi_a P1a, hi_b P1b, hi_a P2a, hi_b P2b, lo_a P1a, lo_b P1b
+    const bool leader = elect_one();
+    const uint64_t x_desc0 = make_desc(sm.hstage[0], 16, 1024);  // K-major view of the frames
+    constexpr int wp[6] = {0, 1, 0, 1, 2, 3};
+    constexpr int xp[6] = {0, 1, 2, 3, 0, 1};
+    mbar_wait(sm.w_tmem, 0);  // epilogue warps copied the weights into TMEM
+    for (int h = 0; h < n_half; h++) {
+      const int st = h % kHStages, sb = h & 1;
+      mbar_wait(sm.full[st], (h / kHStages) & 1);
+      if (h >= 2) mbar_wait(sm.s_free[sb], ((h >> 1) - 1) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d_tmem = tmem_base + kOColS + sb * kHF;
+        const uint64_t xd0 = desc_add(x_desc0, st * kHalfBytes);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            umma_ts(d_tmem, tmem_base + kOColW + wp[q] * 32 + kk * 8,
+                    desc_add(xd0, xp[q] * kHalfPanel + kk * 32), idesc1, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(sm.s_full[sb]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ---- statistics-GEMM issuer: F[c, :] (+)= P[c, t] A[t, :]; B = hi panels, then lo panels,
+    // read MN-major (64-wide chunks = half panels, kHalfPanel apart)
+    const bool leader = elect_one();
+    const uint64_t b_desc0 = make_desc(sm.hstage[0], (uint32_t)kHalfPanel, 1024);
+    int n_flush = 0;
+    TileInfo ti = n_half > 0 ? tinfo[t_begin] : TileInfo{0, 0};
+    TileInfo ti_next = ti;
+    for (int h = 0; h < n_half; h++) {
+      const int st = h % kHStages, ps = h % kNP;
+      if (!(h & 1)) {
+        ti = ti_next;
+        if (h + 2 < n_half) ti_next = tinfo[t_begin + (h >> 1) + 1];
+      }
+      const bool first = (ti.flags & 1) && !(h & 1), last = (ti.flags & 2) && (h & 1);
+      mbar_wait(sm.full[st], (h / kHStages) & 1);
+      mbar_wait(sm.p_ready[ps], (h / kNP) & 1);
+      if (first && n_flush > 0) mbar_wait(sm.f_empty, (n_flush - 1) & 1);
+      tc_fence_after();
+      if (leader) {
+        uint32_t acc = first ? 0u : 1u;
+        const uint64_t bd0 = desc_add(b_desc0, st * kHalfBytes);
+#pragma unroll
+        for (int part = 0; part < 2; part++) {
+#pragma unroll
+          for (int kk = 0; kk < kHF / 16; kk++) {
+            umma_ts(tmem_f, tmem_base + kOColP + ps * 32 + kk * 8,
+                    desc_add(bd0, part * 2 * kHalfPanel + kk * 2048), idesc2, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(sm.empty[st]);
+        umma_commit(sm.p_free[ps]);
+        if (last) umma_commit(sm.f_full);
+      }
+      if (last) n_flush++;
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ---- two epilogue teams of four warps (one per TMEM lane quarter q); team t owns the half
+    // tiles h = t, t + 2, ...
+    const int q = warp & 3, team = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128 - team * 128;  // 0..127 inside the team
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t lane_addr16 = (uint32_t)(q * 32 + 16) << 16;
+    // shared memory of the weights is free once they live in TMEM: [0, 32 KB) flush staging
+    // (8 warps x 4 KB), then 4 KB of exchange area per team
+    float *stg = reinterpret_cast<float *>(base_ptr) + (warp - 4) * kStageFloats;
+    unsigned char *xa = base_ptr + 32 * 1024 + team * 4096;
+    float *wmax = reinterpret_cast<float *>(xa);            // [4 warps][64 frames]
+    float *wsum = reinterpret_cast<float *>(xa + 1024);     // [4 warps][64 frames]
+    __half *fm = reinterpret_cast<__half *>(xa + 2048);     // [64] mantissa of the rescale factor
+    __half *fp = reinterpret_cast<__half *>(xa + 2048 + 128);  // [64] its power of two
+    {
+      // weights: shared memory (swizzled panels) -> TMEM rows; team t copies the panels t, t + 2
+      mbar_wait(sm.w_full, 0);
+      const int r = q * 32 + lane;
+      for (int p = team; p < 4; p += 2) {
+#pragma unroll
+        for (int half16 = 0; half16 < 2; half16++) {
+          uint32_t v[16];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int chunk = half16 * 4 + j;
+            const uint32_t a = sm.w + p * kPanelBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                         : "r"(a));
+          }
+          tmem_st16(tmem_base + lane_addr + kOColW + p * 32 + half16 * 16, v);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.w_tmem);
+    }
+    const long frame0 = (long)t_begin * kTile;
+    unsigned long long *ring = xch + (size_t)group * kXRing * n_slices * kHF;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const int c4 = 2 * (lane & 3);  // first of this thread's two columns inside every group of 8
+    double llk_acc = 0.0;
+    int n_flush = 0;
+
+    auto epi1 = [&](int h) {
+      const int sb = h & 1, ps = h % kNP;
+      mbar_wait(sm.s_full[sb], (h >> 1) & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];  // lanes 32q + {t/4, t/4+8} and 32q + 16 + {t/4, t/4+8}
+      tmem_ld_16x256b_x8(tmem_base + lane_addr + kOColS + sb * kHF, v0);
+      tmem_ld_16x256b_x8(tmem_base + lane_addr16 + kOColS + sb * kHF, v1);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.s_free[sb]);  // S is in registers: the next G1 may overwrite it
+      // ---- per-frame max over the slice's 128 components
+      float a16[16], a8[8], a4[4], a2[2];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+          a16[2 * j + e] = fmaxf(fmaxf(__uint_as_float(v0[4 * j + e]), __uint_as_float(v0[4 * j + 2 + e])),
+                                 fmaxf(__uint_as_float(v1[4 * j + e]), __uint_as_float(v1[4 * j + 2 + e])));
+      }
+      lane_halve<8, true>(a16, a8, b4, 16);
+      lane_halve<4, true>(a8, a4, b3, 8);
+      lane_halve<2, true>(a4, a2, b2, 4);
+      // this thread now holds the warp's maxima of the frame columns 2 lane, 2 lane + 1
+      *reinterpret_cast<float2 *>(wmax + q * kHF + 2 * lane) = make_float2(a2[0], a2[1]);
+      named_bar_sync(1 + team, 128);
+      float nm[16];  // 14 - max over the four warps, for this thread's 16 columns
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float2 m0 = *reinterpret_cast<const float2 *>(wmax + 0 * kHF + 8 * j + c4);
+        const float2 m1 = *reinterpret_cast<const float2 *>(wmax + 1 * kHF + 8 * j + c4);
+        const float2 m2 = *reinterpret_cast<const float2 *>(wmax + 2 * kHF + 8 * j + c4);
+        const float2 m3 = *reinterpret_cast<const float2 *>(wmax + 3 * kHF + 8 * j + c4);
+        nm[2 * j] = kGammaShift - fmaxf(fmaxf(m0.x, m1.x), fmaxf(m2.x, m3.x));
+        nm[2 * j + 1] = kGammaShift - fmaxf(fmaxf(m0.y, m1.y), fmaxf(m2.y, m3.y));
+      }
+      // ---- posteriors relative to the slice maximum, scaled by 2^14
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          v0[4 * j + k] = __float_as_uint(ex2f(__uint_as_float(v0[4 * j + k]) + nm[2 * j + (k & 1)]));
+          v1[4 * j + k] = __float_as_uint(ex2f(__uint_as_float(v1[4 * j + k]) + nm[2 * j + (k & 1)]));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+          a16[2 * j + e] = (__uint_as_float(v0[4 * j + e]) + __uint_as_float(v0[4 * j + 2 + e])) +
+                           (__uint_as_float(v1[4 * j + e]) + __uint_as_float(v1[4 * j + 2 + e]));
+      }
+      lane_halve<8, false>(a16, a8, b4, 16);
+      lane_halve<4, false>(a8, a4, b3, 8);
+      lane_halve<2, false>(a4, a2, b2, 4);
+      *reinterpret_cast<float2 *>(wsum + q * kHF + 2 * lane) = make_float2(a2[0], a2[1]);
+      // ---- pack the frame pairs (2 pc, 2 pc + 1) into the fp16 column pc = 4 j + t % 4
+      uint32_t pk0[16], pk1[16];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int rs = 0; rs < 2; rs++) {
+          __half2 h0 = __floats2half2_rn(__uint_as_float(v0[4 * j + 2 * rs]), __uint_as_float(v0[4 * j + 2 * rs + 1]));
+          __half2 h1 = __floats2half2_rn(__uint_as_float(v1[4 * j + 2 * rs]), __uint_as_float(v1[4 * j + 2 * rs + 1]));
+          pk0[2 * j + rs] = *reinterpret_cast<uint32_t *>(&h0);
+          pk1[2 * j + rs] = *reinterpret_cast<uint32_t *>(&h1);
+        }
+      }
+      if (h >= kNP) {
+        mbar_wait(sm.p_free[ps], ((h / kNP) - 1) & 1);  // G2(h - kNP) is done with the slot
+        tc_fence_after();
+      }
+      tmem_st_16x128b_x8(tmem_base + lane_addr + kOColP + ps * 32, pk0);
+      tmem_st_16x128b_x8(tmem_base + lane_addr16 + kOColP + ps * 32, pk1);
+      tmem_wait_st();
+      named_bar_sync(1 + team, 128);  // every warp's sums are in shared memory
+      if (et < kHF) {
+        const float m = fmaxf(fmaxf(wmax[et], wmax[kHF + et]), fmaxf(wmax[2 * kHF + et], wmax[3 * kHF + et]));
+        const float z = ((wsum[et] + wsum[kHF + et]) + (wsum[2 * kHF + et] + wsum[3 * kHF + et])) *
+                        (1.f / 16384.f);
+        const unsigned tag = (((unsigned)h / kXRing) & 1u) ^ 1u;
+        const unsigned long long word =
+            ((unsigned long long)(__float_as_uint(z) | (tag << 31)) << 32) | __float_as_uint(m);
+        st_relaxed_u64(ring + ((size_t)(h % kXRing) * n_slices + slice) * kHF + et, word);
+      }
+    };
+
+    auto epi2 = [&](int h) {
+      const int ps = h % kNP;
+      if (et < kHF) {
+        const unsigned long long *src = ring + (size_t)(h % kXRing) * n_slices * kHF + et;
+        const unsigned long long tag = ((((unsigned)h / kXRing) & 1u) ^ 1u);
+        float m = -3.0e38f, z = 0.f, m_own = 0.f;
+        for (int sl = 0; sl < n_slices; sl++) {
+          unsigned long long u;
+          do {
+            u = ld_relaxed_u64(src + (size_t)sl * kHF);
+          } while ((u >> 63) != tag && !(dbg & 1));
+          const float ms = __uint_as_float((unsigned)u);
+          const float zs = __uint_as_float((unsigned)(u >> 32) & 0x7FFFFFFFu);
+          if (sl == slice) m_own = ms;
+          const float mn = fmaxf(m, ms);
+          z = z * ex2f(m - mn) + zs * ex2f(ms - mn);
+          m = mn;
+        }
+        const float lse = m + log2f(z);
+        const long f = frame0 + (long)h * kHF + et;
+        if (slice == 0) {
+          if (lse_out) lse_out[f] = lse;
+          if (f < P && (!index || index[f] != kPadIndex)) llk_acc += (double)lse;
+        }
+        // rescale factor 2^d, d = max_slice - lse <= 0 (up to rounding), applied as two fp16
+        // factors: a mantissa in (0.5, 1] times 2^ka (ka >= -13: a normal fp16) and the exact
+        // power of two 2^(k - ka) >= 2^-24; below 2^-38 nothing of the slice survives in fp16
+        const float d = m_own - lse;
+        const float k = ceilf(d);
+        const float ka = fmaxf(k, -13.f);
+        const bool dead = !(d > -38.f);
+        fm[et] = __float2half_rn(dead ? 0.f : ex2f((d - k) + ka));
+        fp[et] = __float2half_rn(dead ? 0.f : ex2f(fmaxf(k - ka, -24.f)));
+      }
+      named_bar_sync(1 + team, 128);
+      uint32_t p0[16], p1[16];
+      tmem_ld_16x128b_x8(tmem_base + lane_addr + kOColP + ps * 32, p0);
+      tmem_ld_16x128b_x8(tmem_base + lane_addr16 + kOColP + ps * 32, p1);
+      tmem_wait_ld();
+      const __half2 *fm2 = reinterpret_cast<const __half2 *>(fm), *fp2 = reinterpret_cast<const __half2 *>(fp);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const __half2 a = fm2[4 * j + (lane & 3)], b = fp2[4 * j + (lane & 3)];
+#pragma unroll
+        for (int rs = 0; rs < 2; rs++) {
+          __half2 x = *reinterpret_cast<__half2 *>(&p0[2 * j + rs]);
+          x = __hmul2(__hmul2(x, a), b);
+          p0[2 * j + rs] = *reinterpret_cast<uint32_t *>(&x);
+          __half2 y = *reinterpret_cast<__half2 *>(&p1[2 * j + rs]);
+          y = __hmul2(__hmul2(y, a), b);
+          p1[2 * j + rs] = *reinterpret_cast<uint32_t *>(&y);
+        }
+      }
+      tmem_st_16x128b_x8(tmem_base + lane_addr + kOColP + ps * 32, p0);
+      tmem_st_16x128b_x8(tmem_base + lane_addr16 + kOColP + ps * 32, p1);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.p_ready[ps]);
+      named_bar_sync(1 + team, 128);  // fm / fp (and wmax / wsum) may be rewritten from here on
+    };
+
+    // Flush of the run that ends with the tile of half tile h.  TMEM: lane = component, columns
+    // [xh, 1 (64) | xh^2 (64)]; warp (q, team) owns the statistics columns 32 team.. of the
+    // components 32 q..  The increments are staged through shared memory (fp32) so that the fp64
+    // read-modify-write of the row's [128 comps x D] block is coalesced (lane = dimension).
+    auto flush = [&](const TileInfo ti) {
+      mbar_wait(sm.f_full, n_flush & 1);
+      n_flush++;
+      tc_fence_after();
+      const int comp0 = slice * kSlice + q * 32;
+      const double sc = 1.0 / 16384.0;  // undo the 2^14 posterior scale
+      const double n = (double)__uint_as_float(tmem_ld1(tmem_f + lane_addr + kOneCol)) * sc;
+      const size_t rc0 = (size_t)ti.row * C + comp0;
+      const int k0 = team * 32;
+      uint32_t a1[32], a2[32];
+      tmem_ld32(tmem_f + lane_addr + k0, a1);
+      if (EM) tmem_ld32(tmem_f + lane_addr + 64 + k0, a2);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.f_empty);  // accumulator columns are free again
+      if (dbg & 2) return;
+      if (team == 1 && out_N && comp0 + lane < C) atomicAdd(&out_N[rc0 + lane], fw * n);
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < 32; e++) {
+        const int k = k0 + e;
+        float inc = 0.f;
+        if (k < D) inc = (float)(fw * (s[k] * ((double)__uint_as_float(a1[e]) * sc) + g[k] * n));
+        stg[lane * 32 + (e ^ lane)] = inc;
+      }
+      __syncwarp();
+      if (out_F && k0 + lane < D) {
+#pragma unroll 8
+        for (int c = 0; c < 32; c++) {
+          if (comp0 + c < C)
+            atomicAdd(&out_F[(rc0 + c) * D + k0 + lane], (double)stg[c * 32 + (lane ^ c)]);
+        }
+      }
+      if (EM && out_S2) {
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const int k = k0 + e;
+          float inc = 0.f;
+          if (k < D) {
+            const double f1 = (double)__uint_as_float(a1[e]) * sc, q2 = (double)__uint_as_float(a2[e]) * sc;
+            const double sk = s[k], gk = g[k];
+            inc = (float)(fw * (sk * sk * q2 + 2.0 * sk * gk * f1 + gk * gk * n));
+          }
+          stg[lane * 32 + (e ^ lane)] = inc;
+        }
+        __syncwarp();
+        if (k0 + lane < D) {
+#pragma unroll 4
+          for (int c = 0; c < 32; c++) {
+            if (comp0 + c < C)
+              atomicAdd(&out_S2[(rc0 + c) * D + k0 + lane], (double)stg[c * 32 + (lane ^ c)]);
+          }
+        }
+      }
+      __syncwarp();
+    };
+
+    int prev = -1;
+    for (int h = team; h < n_half; h += 2) {
+      epi1(h);
+      if (prev >= 0) {
+        epi2(prev);
+        const TileInfo ti = tinfo[t_begin + (prev >> 1)];
+        if (ti.flags & 2) flush(ti);
+      }
+      prev = h;
+    }
+    if (prev >= 0) {
+      epi2(prev);
+      const TileInfo ti = tinfo[t_begin + (prev >> 1)];
+      if (ti.flags & 2) flush(ti);
+    }
+    if (slice == 0 && llk_sum && q < 2) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) llk_acc += __shfl_xor_sync(0xFFFFFFFFu, llk_acc, o);
+      if (lane == 0 && llk_acc != 0.0) atomicAdd(llk_sum, llk_acc * 0.69314718055994530942);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ host side
@@ -1002,7 +1543,7 @@ bool tc_selected(const lr_gmm *g, lr_status *err) {
   Engine &e = engine();
   if (err) *err = LR_OK;
   if (e.gmm_kernel == 1) return false;
-  if (e.gmm_kernel == 2) {
+  if (e.gmm_kernel >= 2) {
     if (!tc_supported(g)) {
       if (err)
         *err = fail(LR_ERR_ARG,
@@ -1119,12 +1660,34 @@ static int tc_groups(K kern, int n_slices, int csize, int n_tiles) {
 }
 
 static lr_status tc_set_attrs() {
-  static bool done = false;
+  bool &done = engine().attr_set[Engine::kAttrTc];
   if (done) return LR_OK;
   LR_CUDA(cudaFuncSetAttribute(k_tc_lse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   LR_CUDA(cudaFuncSetAttribute(k_tc_acc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   LR_CUDA(cudaFuncSetAttribute(k_tc_acc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   done = true;
+  return LR_OK;
+}
+
+// Cooperative launch of the one-pass kernel: every CTA of a frame group waits for its peers'
+// partial log-sum-exps, so the whole grid must be co-resident (the launch fails otherwise).
+template <typename... Args>
+static lr_status tc_launch_coop(void (*kern)(Args...), int grid, Args... args) {
+  Engine &e = engine();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = kTcSmem;
+  cfg.stream = e.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LR_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  count_launch();
   return LR_OK;
 }
 
@@ -1213,11 +1776,44 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
     t = t2;
   }
 
+  const bool want_stats = out_N || out_F || out_S2;
+  if (want_stats && e.gmm_kernel != 3 && n_slices <= e.sm_count) {
+    // ---- one pass: likelihood GEMM, log-sum-exp exchange and statistics GEMM in one kernel
+    unsigned char *Xh1 = (unsigned char *)scratch_get(kSlotTmpA, (size_t)n_tiles * kTileBytes);
+    int *d_cuts1 = (int *)scratch_get(kSlotRest, (groups + 1) * sizeof(int));
+    TileInfo *d_tinfo1 = (TileInfo *)scratch_get(kSlotChunks, (size_t)n_tiles * sizeof(TileInfo));
+    // exchange ring: kXRing half tiles x n_slices x 64 frames of (max, sum) words per group.  A CTA
+    // overwrites a ring slot 16 half tiles after it was written; by then every CTA of the group has
+    // read it (a CTA reaches half tile h only after all peers posted h - 4, i.e. finished h - 8).
+    const size_t xbytes = (size_t)groups * kXRing * n_slices * 64 * sizeof(unsigned long long);
+    unsigned long long *d_xch = (unsigned long long *)scratch_get(kSlotXchg, xbytes);
+    if (!Xh1 || !d_cuts1 || !d_tinfo1 || !d_xch) return LR_ERR_CUDA;
+    LR_CUDA(cudaMemcpyAsync(d_cuts1, cuts.data(), (groups + 1) * sizeof(int), cudaMemcpyHostToDevice,
+                            e.stream));
+    LR_CUDA(cudaMemcpyAsync(d_tinfo1, tinfo.data(), (size_t)n_tiles * sizeof(TileInfo),
+                            cudaMemcpyHostToDevice, e.stream));
+    LR_CUDA(cudaMemsetAsync(d_xch, 0, xbytes, e.stream));  // lap tags start at 1
+    k_tc_convert<<<(unsigned)((P_pad * 8 + 255) / 256), 256, 0, e.stream>>>(
+        g->D, fl.dX, fl.ldx, fl.d_index, fl.P, P_pad, g->d_gf, g->d_rsf, Xh1);
+    LR_CHECK_LAUNCH();
+    ProfileScope prof(1);
+    if (out_S2)
+      return tc_launch_coop(k_tc_one<true>, n_slices * groups, g->C, g->D, n_slices,
+                            (const unsigned char *)st->d_W, (const unsigned char *)Xh1,
+                            (const int *)d_cuts1, (const TileInfo *)d_tinfo1, d_xch, (float *)nullptr,
+                            fl.d_index, fl.P, d_llk_sum, (const double *)g->d_g,
+                            (const double *)g->d_s, fw, out_N, out_F, out_S2, e.tc_debug);
+    return tc_launch_coop(k_tc_one<false>, n_slices * groups, g->C, g->D, n_slices,
+                          (const unsigned char *)st->d_W, (const unsigned char *)Xh1,
+                          (const int *)d_cuts1, (const TileInfo *)d_tinfo1, d_xch, (float *)nullptr,
+                          fl.d_index, fl.P, d_llk_sum, (const double *)g->d_g,
+                          (const double *)g->d_s, fw, out_N, out_F, (double *)nullptr, e.tc_debug);
+  }
   float *d_lse = (float *)scratch_get(kSlotLse, (size_t)P_pad * sizeof(float));
   if (!d_lse) return LR_ERR_CUDA;
   rc = tc_pass_lse(g, fl, d_lse, d_llk_sum);  // also leaves the converted tiles in kSlotTmpA
   if (rc != LR_OK) return rc;
-  if (!out_N && !out_F && !out_S2) return LR_OK;
+  if (!want_stats) return LR_OK;
   unsigned char *Xh = (unsigned char *)scratch_get(kSlotTmpA, (size_t)n_tiles * kTileBytes);
   int *d_cuts = (int *)scratch_get(kSlotRest, (groups + 1) * sizeof(int));
   TileInfo *d_tinfo = (TileInfo *)scratch_get(kSlotChunks, (size_t)n_tiles * sizeof(TileInfo));

@@ -202,7 +202,7 @@ lr_status gmm_topk(lr_gmm *g, const FrameList &fl, const float *d_S, int K, int 
   size_t sm = (size_t)kWarps * g->Cp * sizeof(float);
   if (sm > 200 * 1024) return fail(LR_ERR_ARG, "top-K selection supports at most %d components",
                                    200 * 1024 / (kWarps * 4));
-  static bool attr_set = false;
+  bool &attr_set = engine().attr_set[Engine::kAttrTopk];
   if (!attr_set) {
     LR_CUDA(cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;

@@ -442,7 +442,7 @@ lr_status chol_batched(lr_tv *tv, double *Lb, int n, int nb, double *invD, doubl
   const int nblk = (n + kNB - 1) / kNB;
   const long long sD = (long long)nblk * kNB * kNB;
   const double one = 1.0, zero = 0.0, mone = -1.0;
-  static bool diag_attr = false;
+  bool &diag_attr = engine().attr_set[Engine::kAttrTvDiag];
   const size_t diag_smem = 2 * kNB * (kNB + 1) * sizeof(double);
   if (!diag_attr) {
     LR_CUDA(cudaFuncSetAttribute(k_diag_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,

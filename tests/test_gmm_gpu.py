@@ -21,19 +21,22 @@ def capi():
     return capi
 
 
-@pytest.fixture(params=["simt", "tc"])
+KERNELS = {"simt": 1, "tc": 2, "tc2p": 3}
+
+
+@pytest.fixture(params=["simt", "tc", "tc2p"])
 def kern(request, capi):
-    """Run the test under the fp32 SIMT kernels and under the tcgen05 kernels (forced, so a
-    silent fall back to the other path is impossible)."""
-    capi.set_gmm_kernel(1 if request.param == "simt" else 2)
+    """Run the test under the fp32 SIMT kernels, the tcgen05 one-pass statistics kernel and the
+    tcgen05 two-pass kernels (forced, so a silent fall back to another path is impossible)."""
+    capi.set_gmm_kernel(KERNELS[request.param])
     yield request.param
     capi.set_gmm_kernel(0)
 
 
 # (rtol, atol relative to max|ref|) per kernel: the tcgen05 path rounds posteriors to fp16
 # (11 bits) before the statistics GEMM, the same rounded posterior feeding N and F.
-STAT_TOL = {"simt": (1e-4, 1e-7), "tc": (1e-4, 5e-5)}
-LLK_ABS = {"simt": 2e-4, "tc": 1e-3}
+STAT_TOL = {"simt": (1e-4, 1e-7), "tc": (1e-4, 5e-5), "tc2p": (1e-4, 5e-5)}
+LLK_ABS = {"simt": 2e-4, "tc": 1e-3, "tc2p": 1e-3}
 
 
 def _relmax(a, b):
