@@ -387,7 +387,7 @@ def main():
             "config": {"workload": "TrainWorld EM iteration, 2048c/60d diagonal UBM, 10M frames/GPU (configs[1])",
                        "frames_per_gpu": T, "components": C, "dim": D,
                        "l2": "inputs (2.4 GB/GPU) exceed L2, no flush needed",
-                       "kernel": {0: "auto", 1: "simt-fp32", 2: "tcgen05"}[args.kernel],
+                       "kernel": {0: "auto", 1: "simt-fp32", 2: "tcgen05", 3: "tcgen05-two-pass"}[args.kernel],
                        "arithmetic": "fp16 hi/lo split operands (22 significand bits, 3 UMMA products), fp32 TMEM "
                                      "accumulation, fp64 statistics" if args.kernel != 1 else "fp32 FMA, fp64 statistics",
                        "mean_llk_per_frame": llk_per_frame},

@@ -1080,7 +1080,9 @@ __device__ __forceinline__ void tmem_st_16x128b_x8(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
   unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  // weak load that bypasses L1 (.cg): the exchange words are polled, ordering comes from the lap tag
+  // inside each word; ld.relaxed.gpu (LDG.STRONG.GPU) was measured at ~300 clk PER LOAD, unpipelined
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
@@ -1101,7 +1103,18 @@ __device__ __forceinline__ void lane_halve(const float (&in)[2 * N], float (&out
   }
 }
 
-template <bool EM>
+// PROF: clock64() phase accounting of the issuer warps and of warp 0 of both epilogue teams, summed
+// over the grid into prof[role * 16 + phase] (LR_TC_PROF=1; never the product path).
+#define LR_PT(i)                       \
+  do {                                 \
+    if (PROF) {                        \
+      const long long now_ = clock64(); \
+      pacc[i] += now_ - tlast;         \
+      tlast = now_;                    \
+    }                                  \
+  } while (0)
+
+template <bool EM, bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
          const unsigned char *__restrict__ Xh, const int *__restrict__ group_tiles,
@@ -1109,8 +1122,10 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
          float *__restrict__ lse_out, const unsigned *__restrict__ index, long P,
          double *llk_sum, const double *__restrict__ g, const double *__restrict__ s, double fw,
          double *__restrict__ out_N, double *__restrict__ out_F, double *__restrict__ out_S2,
-         int dbg) {
+         int dbg, long long *prof) {
   constexpr int N2 = EM ? 128 : 64;  // statistics columns: [xh, 1 | xh^2] or [xh, 1]
+  long long pacc[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = PROF ? clock64() : 0;
   constexpr uint32_t idesc1 = make_idesc(128, 64, 0, 0);
   constexpr uint32_t idesc2 = make_idesc(128, N2, 0, 1);
   constexpr int kHF = 64;
@@ -1178,10 +1193,13 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
     constexpr int wp[6] = {0, 1, 0, 1, 2, 3};
     constexpr int xp[6] = {0, 1, 2, 3, 0, 1};
     mbar_wait(sm.w_tmem, 0);  // epilogue warps copied the weights into TMEM
+    LR_PT(0);
     for (int h = 0; h < n_half; h++) {
       const int st = h % kHStages, sb = h & 1;
       mbar_wait(sm.full[st], (h / kHStages) & 1);
+      LR_PT(1);
       if (h >= 2) mbar_wait(sm.s_free[sb], ((h >> 1) - 1) & 1);
+      LR_PT(2);
       tc_fence_after();
       if (leader) {
         const uint32_t d_tmem = tmem_base + kOColS + sb * kHF;
@@ -1199,7 +1217,10 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
         umma_commit(sm.s_full[sb]);
       }
       __syncwarp();
+      LR_PT(3);
     }
+    if (PROF && lane == 0)
+      for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)prof + 32 + i, (unsigned long long)pacc[i]);
   } else if (warp == 3) {
     // ---- statistics-GEMM issuer: F[c, :] (+)= P[c, t] A[t, :]; B = hi panels, then lo panels,
     // read MN-major (64-wide chunks = half panels, kHalfPanel apart)
@@ -1216,8 +1237,11 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       }
       const bool first = (ti.flags & 1) && !(h & 1), last = (ti.flags & 2) && (h & 1);
       mbar_wait(sm.full[st], (h / kHStages) & 1);
+      LR_PT(1);
       mbar_wait(sm.p_ready[ps], (h / kNP) & 1);
+      LR_PT(2);
       if (first && n_flush > 0) mbar_wait(sm.f_empty, (n_flush - 1) & 1);
+      LR_PT(3);
       tc_fence_after();
       if (leader) {
         uint32_t acc = first ? 0u : 1u;
@@ -1237,7 +1261,10 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       }
       if (last) n_flush++;
       __syncwarp();
+      LR_PT(4);
     }
+    if (PROF && lane == 0)
+      for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)prof + 48 + i, (unsigned long long)pacc[i]);
   } else if (warp >= 4) {
     // ---- two epilogue teams of four warps (one per TMEM lane quarter q); team t owns the half
     // tiles h = t, t + 2, ...
@@ -1280,13 +1307,14 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
     const long frame0 = (long)t_begin * kTile;
     unsigned long long *ring = xch + (size_t)group * kXRing * n_slices * kHF;
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    const int c4 = 2 * (lane & 3);  // first of this thread's two columns inside every group of 8
     double llk_acc = 0.0;
     int n_flush = 0;
 
     auto epi1 = [&](int h) {
       const int sb = h & 1, ps = h % kNP;
+      LR_PT(0);
       mbar_wait(sm.s_full[sb], (h >> 1) & 1);
+      LR_PT(1);
       tc_fence_after();
       uint32_t v0[32], v1[32];  // lanes 32q + {t/4, t/4+8} and 32q + 16 + {t/4, t/4+8}
       tmem_ld_16x256b_x8(tmem_base + lane_addr + kOColS + sb * kHF, v0);
@@ -1295,6 +1323,7 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.s_free[sb]);  // S is in registers: the next G1 may overwrite it
+      LR_PT(2);
       // ---- per-frame max over the slice's 128 components
       float a16[16], a8[8], a4[4], a2[2];
 #pragma unroll
@@ -1309,16 +1338,24 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       lane_halve<2, true>(a4, a2, b2, 4);
       // this thread now holds the warp's maxima of the frame columns 2 lane, 2 lane + 1
       *reinterpret_cast<float2 *>(wmax + q * kHF + 2 * lane) = make_float2(a2[0], a2[1]);
+      LR_PT(3);
       named_bar_sync(1 + team, 128);
+      LR_PT(4);
       float nm[16];  // 14 - max over the four warps, for this thread's 16 columns
+      {
+        const float2 m0 = *reinterpret_cast<const float2 *>(wmax + 0 * kHF + 2 * lane);
+        const float2 m1 = *reinterpret_cast<const float2 *>(wmax + 1 * kHF + 2 * lane);
+        const float2 m2 = *reinterpret_cast<const float2 *>(wmax + 2 * kHF + 2 * lane);
+        const float2 m3 = *reinterpret_cast<const float2 *>(wmax + 3 * kHF + 2 * lane);
+        // this lane: 14 - slice maximum of the columns 2 lane, 2 lane + 1; the columns
+        // 8 j + 2 (lane % 4) + e this thread works on belong to the lane 4 j + lane % 4
+        const float own0 = kGammaShift - fmaxf(fmaxf(m0.x, m1.x), fmaxf(m2.x, m3.x));
+        const float own1 = kGammaShift - fmaxf(fmaxf(m0.y, m1.y), fmaxf(m2.y, m3.y));
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const float2 m0 = *reinterpret_cast<const float2 *>(wmax + 0 * kHF + 8 * j + c4);
-        const float2 m1 = *reinterpret_cast<const float2 *>(wmax + 1 * kHF + 8 * j + c4);
-        const float2 m2 = *reinterpret_cast<const float2 *>(wmax + 2 * kHF + 8 * j + c4);
-        const float2 m3 = *reinterpret_cast<const float2 *>(wmax + 3 * kHF + 8 * j + c4);
-        nm[2 * j] = kGammaShift - fmaxf(fmaxf(m0.x, m1.x), fmaxf(m2.x, m3.x));
-        nm[2 * j + 1] = kGammaShift - fmaxf(fmaxf(m0.y, m1.y), fmaxf(m2.y, m3.y));
+        for (int j = 0; j < 8; j++) {
+          nm[2 * j] = __shfl_sync(0xFFFFFFFFu, own0, 4 * j + (lane & 3));
+          nm[2 * j + 1] = __shfl_sync(0xFFFFFFFFu, own1, 4 * j + (lane & 3));
+        }
       }
       // ---- posteriors relative to the slice maximum, scaled by 2^14
 #pragma unroll
@@ -1352,14 +1389,18 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
           pk1[2 * j + rs] = *reinterpret_cast<uint32_t *>(&h1);
         }
       }
+      LR_PT(5);
       if (h >= kNP) {
         mbar_wait(sm.p_free[ps], ((h / kNP) - 1) & 1);  // G2(h - kNP) is done with the slot
         tc_fence_after();
       }
+      LR_PT(6);
       tmem_st_16x128b_x8(tmem_base + lane_addr + kOColP + ps * 32, pk0);
       tmem_st_16x128b_x8(tmem_base + lane_addr16 + kOColP + ps * 32, pk1);
       tmem_wait_st();
+      LR_PT(7);
       named_bar_sync(1 + team, 128);  // every warp's sums are in shared memory
+      LR_PT(8);
       if (et < kHF) {
         const float m = fmaxf(fmaxf(wmax[et], wmax[kHF + et]), fmaxf(wmax[2 * kHF + et], wmax[3 * kHF + et]));
         const float z = ((wsum[et] + wsum[kHF + et]) + (wsum[2 * kHF + et] + wsum[3 * kHF + et])) *
@@ -1373,21 +1414,53 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
 
     auto epi2 = [&](int h) {
       const int ps = h % kNP;
+      LR_PT(9);
       if (et < kHF) {
         const unsigned long long *src = ring + (size_t)(h % kXRing) * n_slices * kHF + et;
         const unsigned long long tag = ((((unsigned)h / kXRing) & 1u) ^ 1u);
         float m = -3.0e38f, z = 0.f, m_own = 0.f;
-        for (int sl = 0; sl < n_slices; sl++) {
-          unsigned long long u;
+        // Cheap probe first: lane i of this warp watches ONE word of the slices i, i + 32, ... (the
+        // first frame of this warp's 32, written by the same store instruction as the other 31), with
+        // a short sleep between attempts, so that waiting costs 8 B per slice and attempt instead of
+        // the whole 512 B block -- spinning on the full block took half of the L2 bandwidth.
+        {
+          const unsigned long long *probe = ring + (size_t)(h % kXRing) * n_slices * kHF + (et & 32);
+          bool ok;
           do {
-            u = ld_relaxed_u64(src + (size_t)sl * kHF);
-          } while ((u >> 63) != tag && !(dbg & 1));
-          const float ms = __uint_as_float((unsigned)u);
-          const float zs = __uint_as_float((unsigned)(u >> 32) & 0x7FFFFFFFu);
-          if (sl == slice) m_own = ms;
-          const float mn = fmaxf(m, ms);
-          z = z * ex2f(m - mn) + zs * ex2f(ms - mn);
-          m = mn;
+            ok = true;
+            for (int sl = lane; sl < n_slices; sl += 32)
+              ok = ok && ((ld_relaxed_u64(probe + (size_t)sl * kHF) >> 63) == tag);
+            ok = __all_sync(0xFFFFFFFFu, ok) || (dbg & 1);
+            if (!ok) __nanosleep(40);
+          } while (!ok);
+        }
+        LR_PT(16);
+        // the words of up to 16 slices are fetched together (independent loads: one L2 round trip
+        // per batch instead of one per slice) and re-fetched until every lap tag matches
+        for (int s0 = 0; s0 < n_slices; s0 += 16) {
+          unsigned long long u[16];
+          bool ready;
+          do {
+            ready = true;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              u[i] = (s0 + i < n_slices) ? ld_relaxed_u64(src + (size_t)(s0 + i) * kHF) : (tag << 63);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) ready = ready && ((u[i] >> 63) == tag);
+          } while (!ready && !(dbg & 1));
+          LR_PT(17);
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            if (s0 + i < n_slices) {
+              const float ms = __uint_as_float((unsigned)u[i]);
+              const float zs = __uint_as_float((unsigned)(u[i] >> 32) & 0x7FFFFFFFu);
+              if (s0 + i == slice) m_own = ms;
+              const float mn = fmaxf(m, ms);
+              z = z * ex2f(m - mn) + zs * ex2f(ms - mn);
+              m = mn;
+            }
+          }
         }
         const float lse = m + log2f(z);
         const long f = frame0 + (long)h * kHF + et;
@@ -1405,7 +1478,9 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
         fm[et] = __float2half_rn(dead ? 0.f : ex2f((d - k) + ka));
         fp[et] = __float2half_rn(dead ? 0.f : ex2f(fmaxf(k - ka, -24.f)));
       }
+      LR_PT(18);
       named_bar_sync(1 + team, 128);
+      LR_PT(11);
       uint32_t p0[16], p1[16];
       tmem_ld_16x128b_x8(tmem_base + lane_addr + kOColP + ps * 32, p0);
       tmem_ld_16x128b_x8(tmem_base + lane_addr16 + kOColP + ps * 32, p1);
@@ -1430,7 +1505,9 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.p_ready[ps]);
+      LR_PT(12);
       named_bar_sync(1 + team, 128);  // fm / fp (and wmax / wsum) may be rewritten from here on
+      LR_PT(13);
     };
 
     // Flush of the run that ends with the tile of half tile h.  TMEM: lane = component, columns
@@ -1438,7 +1515,9 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
     // components 32 q..  The increments are staged through shared memory (fp32) so that the fp64
     // read-modify-write of the row's [128 comps x D] block is coalesced (lane = dimension).
     auto flush = [&](const TileInfo ti) {
+      LR_PT(0);
       mbar_wait(sm.f_full, n_flush & 1);
+      LR_PT(14);
       n_flush++;
       tc_fence_after();
       const int comp0 = slice * kSlice + q * 32;
@@ -1494,33 +1573,52 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
         }
       }
       __syncwarp();
+      LR_PT(15);
     };
 
     int prev = -1;
+    TileInfo ti_prev{0, 0};
     for (int h = team; h < n_half; h += 2) {
+      const TileInfo ti_h = tinfo[t_begin + (h >> 1)];  // consumed one iteration later
       epi1(h);
       if (prev >= 0) {
         epi2(prev);
-        const TileInfo ti = tinfo[t_begin + (prev >> 1)];
-        if (ti.flags & 2) flush(ti);
+        if (ti_prev.flags & 2) flush(ti_prev);
       }
       prev = h;
+      ti_prev = ti_h;
     }
     if (prev >= 0) {
       epi2(prev);
-      const TileInfo ti = tinfo[t_begin + (prev >> 1)];
-      if (ti.flags & 2) flush(ti);
+      if (ti_prev.flags & 2) flush(ti_prev);
     }
     if (slice == 0 && llk_sum && q < 2) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) llk_acc += __shfl_xor_sync(0xFFFFFFFFu, llk_acc, o);
       if (lane == 0 && llk_acc != 0.0) atomicAdd(llk_sum, llk_acc * 0.69314718055994530942);
     }
+    if (PROF && lane == 0 && q == 0) {
+      for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)prof + team * 16 + i, (unsigned long long)pacc[i]);
+      if (team == 0) {
+        atomicAdd((unsigned long long *)prof + 10, (unsigned long long)pacc[16]);   // probe
+        atomicAdd((unsigned long long *)prof + 48 + 10, (unsigned long long)pacc[17]);  // batch loads
+        atomicAdd((unsigned long long *)prof + 48 + 11, (unsigned long long)pacc[18]);  // combine  // per-CTA: poll wait, everything else, waits on the tensor pipe (s_full + p_free)
+        long long tot = 0;
+        for (int i = 0; i < 16; i++) tot += pacc[i];
+        prof[64 + blockIdx.x * 4 + 0] = pacc[10];
+        prof[64 + blockIdx.x * 4 + 1] = tot - pacc[10];
+        prof[64 + blockIdx.x * 4 + 2] = pacc[1] + pacc[6];
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        prof[64 + blockIdx.x * 4 + 3] = smid;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
+#undef LR_PT
 
 }  // namespace
 
@@ -1665,8 +1763,10 @@ static lr_status tc_set_attrs() {
   LR_CUDA(cudaFuncSetAttribute(k_tc_lse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   LR_CUDA(cudaFuncSetAttribute(k_tc_acc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   LR_CUDA(cudaFuncSetAttribute(k_tc_acc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-  LR_CUDA(cudaFuncSetAttribute(k_tc_one<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-  LR_CUDA(cudaFuncSetAttribute(k_tc_one<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   done = true;
   return LR_OK;
 }
@@ -1796,18 +1896,43 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
     k_tc_convert<<<(unsigned)((P_pad * 8 + 255) / 256), 256, 0, e.stream>>>(
         g->D, fl.dX, fl.ldx, fl.d_index, fl.P, P_pad, g->d_gf, g->d_rsf, Xh1);
     LR_CHECK_LAUNCH();
-    ProfileScope prof(1);
-    if (out_S2)
-      return tc_launch_coop(k_tc_one<true>, n_slices * groups, g->C, g->D, n_slices,
-                            (const unsigned char *)st->d_W, (const unsigned char *)Xh1,
-                            (const int *)d_cuts1, (const TileInfo *)d_tinfo1, d_xch, (float *)nullptr,
-                            fl.d_index, fl.P, d_llk_sum, (const double *)g->d_g,
-                            (const double *)g->d_s, fw, out_N, out_F, out_S2, e.tc_debug);
-    return tc_launch_coop(k_tc_one<false>, n_slices * groups, g->C, g->D, n_slices,
-                          (const unsigned char *)st->d_W, (const unsigned char *)Xh1,
-                          (const int *)d_cuts1, (const TileInfo *)d_tinfo1, d_xch, (float *)nullptr,
-                          fl.d_index, fl.P, d_llk_sum, (const double *)g->d_g,
-                          (const double *)g->d_s, fw, out_N, out_F, (double *)nullptr, e.tc_debug);
+    static const bool kProf = getenv("LR_TC_PROF") != nullptr;
+    static const int kEnvDbg = getenv("LR_TC_DEBUG") ? atoi(getenv("LR_TC_DEBUG")) : 0;
+    long long *d_prof = nullptr;
+    if (kProf) {
+      d_prof = (long long *)scratch_get(kSlotLse, (64 + 4 * 160) * sizeof(long long));
+      if (!d_prof) return LR_ERR_CUDA;
+      LR_CUDA(cudaMemsetAsync(d_prof, 0, (64 + 4 * 160) * sizeof(long long), e.stream));
+    }
+    auto kern = out_S2 ? (kProf ? k_tc_one<true, true> : k_tc_one<true, false>)
+                       : (kProf ? k_tc_one<false, true> : k_tc_one<false, false>);
+    {
+      ProfileScope prof(1);
+      rc = tc_launch_coop(kern, n_slices * groups, g->C, g->D, n_slices, (const unsigned char *)st->d_W,
+                          (const unsigned char *)Xh1, (const int *)d_cuts1, (const TileInfo *)d_tinfo1,
+                          d_xch, (float *)nullptr, fl.d_index, fl.P, d_llk_sum, (const double *)g->d_g,
+                          (const double *)g->d_s, fw, out_N, out_F, out_S2, e.tc_debug | kEnvDbg, d_prof);
+    }
+    if (rc == LR_OK && kProf) {
+      long long hp[64 + 4 * 160];
+      LR_CUDA(cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, e.stream));
+      LR_CUDA(cudaStreamSynchronize(e.stream));
+      {
+        const double ph = 2.0 / std::max(1, 2 * (n_tiles / groups));
+        for (int b = 0; b < n_slices * groups && b < 160; b++)
+          fprintf(stderr, "[tc_cta] cta %d slice %d group %d sm %lld: poll %.0f other %.0f tensor-wait %.0f\n", b,
+                  b % n_slices, b / n_slices, hp[64 + 4 * b + 3], hp[64 + 4 * b] * ph, hp[64 + 4 * b + 1] * ph,
+                  hp[64 + 4 * b + 2] * ph);
+      }
+      const double per = 1.0 / ((double)n_slices * groups) / std::max(1, 2 * (n_tiles / groups));
+      static const char *role[4] = {"epi team0", "epi team1", "G1 issuer", "G2 issuer"};
+      for (int r = 0; r < 4; r++) {
+        fprintf(stderr, "[tc_prof] %s clk/half-tile:", role[r]);
+        for (int i = 0; i < 16; i++) fprintf(stderr, " %d:%.0f", i, hp[r * 16 + i] * per * (r < 2 ? 2.0 : 1.0));
+        fprintf(stderr, "\n");
+      }
+    }
+    return rc;
   }
   float *d_lse = (float *)scratch_get(kSlotLse, (size_t)P_pad * sizeof(float));
   if (!d_lse) return LR_ERR_CUDA;
