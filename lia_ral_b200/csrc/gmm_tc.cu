@@ -985,84 +985,80 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
 // ------------------------------------------------------------------ one-pass kernel
 // Likelihood GEMM, per-frame log-sum-exp and statistics GEMM in ONE sweep over the frames: the
 // per-frame normaliser is not precomputed by a first pass, it is exchanged between the slice-CTAs
-// of a frame group while the posteriors wait in TMEM.
+// of a frame group while the posteriors wait IN REGISTERS.
 //
 // Per CTA (slice of 128 components, one frame group) and half tile h (64 frames):
-//   G1(h)   : S[c, t] = W A^T, ALL weights (hi and lo) resident in TMEM -> 24 TS UMMAs that read only
-//             the frame half panels from shared memory
-//   epi-1(h): S is read with the 16x256b TMEM shape (a thread holds 4 component rows x 16 frame
-//             columns), so the per-frame max / sum over the 128 lanes is 3 in-thread steps, a 3-step
-//             shuffle reduce-scatter and a 4-way combine through shared memory.  The slice's (max, sum)
-//             of every frame goes to the group's exchange ring in global memory as ONE 64-bit word whose
-//             top bit is the ring-lap tag (data = flag: no fence, no counter); the posteriors wait as
-//             fp16(2^14 2^(S - max_slice)) in one of kNP TMEM slots
-//   epi-2(h): (one team iteration later) poll the n_slices words of each frame, combine -> lse,
-//             rescale the waiting posteriors by 2^(max_slice - lse) (fp16 mantissa x exact power of 2)
-//   G2(h)   : F[c, :] += P[c, t] A[t, :] as TS UMMAs, the hi and the lo frame panels accumulated into
-//             the SAME columns (EM: [xh,1 | xh^2] = 128 columns, BW: [xh,1] = 64), so the accumulator
-//             takes a quarter of TMEM instead of half
-// TMEM: accumulator [0,128) | weights hi a, hi b, lo a, lo b [128,256) | S 2 x 64 [256,384) |
-//       posterior slots 4 x 32 [384,512).
-// All CTAs of a group advance in lock step (each needs every slice's partials), so the grid must be
-// co-resident: launched cooperatively with grid <= SM count.
-constexpr int kNP = 4;        // waiting posterior slots
-constexpr int kXRing = 16;    // exchange ring slots per group (>= 2 kNP, see tc_run_stats_one)
-constexpr int kOColAcc = 0, kOColW = 128, kOColS = 256, kOColP = 384;
+//   G1(h) : S[c, t] = W A^T, ALL weights (hi and lo) resident in TMEM -> 24 TS UMMAs that read only
+//           the frame half panels from shared memory                                     (warp 1)
+//   E1(h) : 16 warps = 2 parities x 2 column halves x 4 TMEM lane quarters; the warps of parity
+//           h & 1 take half tile h, 32 of its 64 frame columns each.  S is read with the 16x256b TMEM
+//           shape (a thread holds 4 component rows x 8 frame columns), so the per-frame max / sum over
+//           a warp's 32 components is 3 in-thread steps + a 3-step shuffle butterfly.  Posteriors are
+//           formed RELATIVE TO THE WARP'S MAXIMUM, fp16(2^14 2^(S - max_warp)), and stay in registers;
+//           the warp's (max, sum) go to a shared-memory ring.
+//   L(h)  : four warps (parity x column half), lane = frame: combine the four lane quarters' (max, sum)
+//           and post the slice's pair to the group's exchange ring in global memory as ONE 64-bit word
+//           whose top bit is the ring-lap tag (data = flag: no fence, no counter); then fetch the
+//           n_slices words of the frame with weak no-allocate loads (served by L2), repeated until every
+//           lap tag matches, combine -> lse
+//   E1'(h): the same E1 warps, one iteration (two half tiles) later: rescale the held posteriors by
+//           2^(max_warp - lse) (fp16 mantissa x exact power of two), store them to a TMEM slot
+//   G2(h) : F[c, :] += P[c, t] A[t, :] as TS UMMAs, the hi and the lo frame panels accumulated into
+//           the SAME columns (EM: [xh,1 | xh^2] = 128 columns, BW: [xh,1] = 64)           (warp 3)
+// TMEM: accumulator [0,128) | weights hi a, hi b, lo a, lo b [128,256) | S 3 x 64 [256,448) |
+//       posterior slots 2 x 32 [448,512).
+// Shared memory: six 32 KB half-tile stages (a stage lives from its bulk copy until G2 has read it,
+// about five half-tile periods); the weights pass through the last two stages on their way to TMEM.
+// No block-level barrier in the main loop: every hand-over is an mbarrier.  All CTAs of a group
+// advance in lock step (each needs every slice's partials), so the grid must be co-resident:
+// launched cooperatively with grid <= SM count.
+constexpr int kXRing = 16;    // exchange ring slots per group (see tc_run_stats)
+constexpr int kOStages = 6;   // half-tile stages
+constexpr int kNS = 3;        // S buffers
+constexpr int kNR = 4;        // depth of the (max, sum) and lse rings in shared memory
+constexpr int kOneThreads = 768;
+constexpr int kOColAcc = 0, kOColW = 128, kOColS = 256, kOColP = 448;
+constexpr int kOStgOff = kOStages * kHalfBytes;        // flush staging: 16 warps x 512 B (32 x 4 floats)
+constexpr int kORingOff = kOStgOff + 16 * 512;         // lane-quarter (max, sum) ring: 2 x [kNR][4][64] floats
+constexpr int kOLseOff = kORingOff + 2 * kNR * 4 * 64 * 4;  // lse ring [kNR][64]
+constexpr int kOBarOff = kOLseOff + kNR * 64 * 4;
+constexpr size_t kOneSmem = 1024 + kOBarOff + 384;
+static_assert(kOneSmem <= 227 * 1024, "one-pass kernel: shared memory budget");
 
+// mbarrier addresses are computed (base + offset + 8 i), not kept in arrays: dynamically indexed
+// arrays of a struct end up in local memory
 struct SmemOne {
-  uint32_t w, hstage[kHStages];
-  uint32_t full[kHStages], empty[kHStages];
-  uint32_t s_full[2], s_free[2], p_ready[kNP], p_free[kNP];
-  uint32_t f_full, f_empty, w_full, w_tmem, tmem_slot;
+  uint32_t base, stage0, bar;
+  __device__ __forceinline__ uint32_t full(int i) const { return bar + 8 * i; }
+  __device__ __forceinline__ uint32_t empty(int i) const { return bar + 48 + 8 * i; }
+  __device__ __forceinline__ uint32_t s_full(int i) const { return bar + 96 + 8 * i; }
+  __device__ __forceinline__ uint32_t s_free(int i) const { return bar + 120 + 8 * i; }
+  __device__ __forceinline__ uint32_t ms_written(int i) const { return bar + 144 + 8 * i; }
+  __device__ __forceinline__ uint32_t lse_ready(int i) const { return bar + 176 + 8 * i; }
+  __device__ __forceinline__ uint32_t p_ready(int i) const { return bar + 240 + 8 * i; }
+  __device__ __forceinline__ uint32_t p_free(int i) const { return bar + 256 + 8 * i; }
+  __device__ __forceinline__ uint32_t f_full() const { return bar + 272; }
+  __device__ __forceinline__ uint32_t f_empty() const { return bar + 280; }
+  __device__ __forceinline__ uint32_t w_full() const { return bar + 288; }
+  __device__ __forceinline__ uint32_t w_tmem() const { return bar + 296; }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return bar + 304; }
 };
+static_assert(kNS == 3 && kNR == 4 && kOStages == 6, "barrier block layout");
 
 __device__ __forceinline__ SmemOne carve_one(unsigned char *raw) {
-  const uint32_t base = carve_base(raw);
   SmemOne s;
-  s.w = base;
-  for (int i = 0; i < kHStages; i++) s.hstage[i] = base + 64 * 1024 + i * kHalfBytes;
-  uint32_t b = base + 64 * 1024 + kHStages * kHalfBytes;
-  for (int i = 0; i < kHStages; i++) {
-    s.full[i] = b + 8 * i;
-    s.empty[i] = b + 40 + 8 * i;
-  }
-  for (int i = 0; i < 2; i++) {
-    s.s_full[i] = b + 80 + 8 * i;
-    s.s_free[i] = b + 96 + 8 * i;
-  }
-  for (int i = 0; i < kNP; i++) {
-    s.p_ready[i] = b + 112 + 8 * i;
-    s.p_free[i] = b + 144 + 8 * i;
-  }
-  s.f_full = b + 176;
-  s.f_empty = b + 184;
-  s.w_full = b + 192;
-  s.w_tmem = b + 200;
-  s.tmem_slot = b + 208;
-  static_assert(kNP == 4 && kHStages == 5, "barrier block layout");
+  s.base = carve_base(raw);
+  s.stage0 = s.base;
+  s.bar = s.base + kOBarOff;
   return s;
 }
 
-// 16 lanes x 256 bits, 8 repeats along the columns: thread t of the warp receives the lanes
+// 16 lanes x 256 bits, N repeats along the columns: thread t of the warp receives the lanes
 // (t / 4) and (t / 4 + 8) of the 16-lane group addressed, columns 8 j + 2 (t % 4) + e, in register
-// 4 j + 2 rs + e  (j = 0..7 repeat, rs = 0/1 lane select, e = 0/1).
-__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+// 4 j + 2 rs + e  (j repeat, rs = 0/1 lane select, e = 0/1).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-// 16 lanes x 128 bits, 8 repeats: lanes (t / 4), (t / 4 + 8), column 4 j + (t % 4) in register 2 j + rs
-__device__ __forceinline__ void tmem_ld_16x128b_x8(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x128b.x8.b32 "
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
         "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
@@ -1070,23 +1066,40 @@ __device__ __forceinline__ void tmem_ld_16x128b_x8(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_16x128b_x8(uint32_t taddr, const uint32_t (&r)[16]) {
+// 16 lanes x 128 bits, N repeats: lanes (t / 4), (t / 4 + 8), column 4 j + (t % 4) in register 2 j + rs
+__device__ __forceinline__ void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile(
-      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      "tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+__device__ __forceinline__ void st_relaxed_v2u64(unsigned long long *p, unsigned long long a,
+                                                 unsigned long long b) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+// weak load that does not allocate in L1: the exchange ring is touched by nothing else on the SM, so
+// every such load is served by L2 (the coherence point) and, unlike ld.relaxed.gpu / .cg (both
+// LDG.STRONG.GPU, ~50 issue clocks each, measured), a batch of them pipelines
+__device__ __forceinline__ unsigned long long ld_na_u64(const unsigned long long *p) {
   unsigned long long v;
-  // weak load that bypasses L1 (.cg): the exchange words are polled, ordering comes from the lap tag
-  // inside each word; ld.relaxed.gpu (LDG.STRONG.GPU) was measured at ~300 clk PER LOAD, unpipelined
-  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // One step of the lane reduce-scatter: the lanes whose bit `xr` is set keep the upper half of
@@ -1103,19 +1116,25 @@ __device__ __forceinline__ void lane_halve(const float (&in)[2 * N], float (&out
   }
 }
 
-// PROF: clock64() phase accounting of the issuer warps and of warp 0 of both epilogue teams, summed
-// over the grid into prof[role * 16 + phase] (LR_TC_PROF=1; never the product path).
-#define LR_PT(i)                       \
-  do {                                 \
-    if (PROF) {                        \
+// PROF: clock64() phase accounting of one warp per role, summed over the grid into
+// prof[role * 16 + phase] (LR_TC_PROF=1; never the product path).
+#define LR_PT(i)                        \
+  do {                                  \
+    if (PROF) {                         \
       const long long now_ = clock64(); \
-      pacc[i] += now_ - tlast;         \
-      tlast = now_;                    \
-    }                                  \
+      pacc[i] += now_ - tlast;          \
+      tlast = now_;                     \
+    }                                   \
+  } while (0)
+#define LR_PDUMP(role)                                                                          \
+  do {                                                                                          \
+    if (PROF && lane == 0)                                                                      \
+      for (int i_ = 0; i_ < 8; i_++)                                                            \
+        atomicAdd((unsigned long long *)prof + (role) * 16 + i_, (unsigned long long)pacc[i_]); \
   } while (0)
 
 template <bool EM, bool PROF>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kOneThreads, 1)
 k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
          const unsigned char *__restrict__ Xh, const int *__restrict__ group_tiles,
          const TileInfo *__restrict__ tinfo, unsigned long long *xch,
@@ -1124,242 +1143,352 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
          double *__restrict__ out_N, double *__restrict__ out_F, double *__restrict__ out_S2,
          int dbg, long long *prof) {
   constexpr int N2 = EM ? 128 : 64;  // statistics columns: [xh, 1 | xh^2] or [xh, 1]
-  long long pacc[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long tlast = PROF ? clock64() : 0;
   constexpr uint32_t idesc1 = make_idesc(128, 64, 0, 0);
   constexpr uint32_t idesc2 = make_idesc(128, N2, 0, 1);
   constexpr int kHF = 64;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = PROF ? clock64() : 0;
   extern __shared__ unsigned char smem_raw[];
   const SmemOne sm = carve_one(smem_raw);
-  unsigned char *base_ptr = smem_raw + (carve_base(smem_raw) - smem_u32(smem_raw));
+  unsigned char *base_ptr = smem_raw + (sm.base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % n_slices, group = blockIdx.x / n_slices;
   const int t_begin = group_tiles[group], t_end = group_tiles[group + 1];
   const int n_half = 2 * (t_end - t_begin);
+  // the lane quarters' (max, sum) per frame: [h % kNR][4 quarters][64 frames].  Depth 4: the slot of
+  // half tile h is rewritten for h + 4, i.e. after this CTA's E1 warps finished h + 2 > h, which
+  // needed every peer's (hence also this CTA's) publication of h -- so it has been read.
+  float *wmax = reinterpret_cast<float *>(base_ptr + kORingOff);
+  float *wsum = wmax + kNR * 4 * kHF;
+  float *lse_s = reinterpret_cast<float *>(base_ptr + kOLseOff);  // [kNR][64]
+  const uint32_t w_smem = sm.stage0 + 4 * kHalfBytes;             // weights staging = stages 4, 5
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kHStages; i++) {
-      mbar_init(sm.full[i], 1);
-      mbar_init(sm.empty[i], 1);
+    for (int i = 0; i < kOStages; i++) {
+      mbar_init(sm.full(i), 1);
+      mbar_init(sm.empty(i), 1);
+    }
+    for (int i = 0; i < kNS; i++) {
+      mbar_init(sm.s_full(i), 1);
+      mbar_init(sm.s_free(i), 8);  // the eight E1 warps of the half tile's parity have S in registers
+    }
+    for (int i = 0; i < kNR; i++) {
+      mbar_init(sm.ms_written(i), 8);  // E1 warps: (max, sum) of the half tile are in the ring
+      mbar_init(sm.lse_ready(i), 2);   // L warps: lse of the half tile is in shared memory
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(sm.s_full[i], 1);
-      mbar_init(sm.s_free[i], 4);  // the four warps of the team that read the buffer
+      mbar_init(sm.p_ready(i), 8);  // E1 warps: rescaled posteriors are in the TMEM slot
+      mbar_init(sm.p_free(i), 1);   // G2 done with the slot
     }
-    for (int i = 0; i < kNP; i++) {
-      mbar_init(sm.p_ready[i], 4);
-      mbar_init(sm.p_free[i], 1);
-    }
-    mbar_init(sm.f_full, 1);
-    mbar_init(sm.f_empty, kEpiWarps);
-    mbar_init(sm.w_full, 1);
-    mbar_init(sm.w_tmem, kEpiWarps);
+    mbar_init(sm.f_full(), 1);
+    mbar_init(sm.f_empty(), 16);
+    mbar_init(sm.w_full(), 1);
+    mbar_init(sm.w_tmem(), 16);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(sm.tmem_slot, 512);
+  if (warp == 2) tmem_alloc(sm.tmem_slot(), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot));
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot()));
   const uint32_t tmem_f = tmem_base + kOColAcc;
+  const long frame0 = (long)t_begin * kTile;
+  // exchange ring of the group: [kXRing][2 column halves][n_slices][32 frames] words
+  unsigned long long *ring = xch + (size_t)group * kXRing * n_slices * kHF;
 
-  if (warp == 0) {
-    // ---- bulk-copy producer
-    const bool leader = elect_one();
-    if (leader) {
-      mbar_expect_tx(sm.w_full, 4 * kPanelBytes);
-      for (int p = 0; p < 4; p++)
-        bulk_g2s(sm.w + p * kPanelBytes, Wp + (size_t)slice * 4 * kPanelBytes + (size_t)p * kPanelBytes,
-                 kPanelBytes, sm.w_full);
-    }
-    for (int h = 0; h < n_half; h++) {
-      const int st = h % kHStages;
-      mbar_wait(sm.empty[st], ((h / kHStages) & 1) ^ 1);
+  if (warp < 4) {
+    reg_dealloc<24>();
+    if (warp == 0) {
+      // ---- bulk-copy producer
+      const bool leader = elect_one();
       if (leader) {
-        mbar_expect_tx(sm.full[st], kHalfBytes);
-        const unsigned char *src =
-            Xh + (size_t)(t_begin + (h >> 1)) * kTileBytes + (size_t)(h & 1) * kHalfPanel;
+        mbar_expect_tx(sm.w_full(), 4 * kPanelBytes);
         for (int p = 0; p < 4; p++)
-          bulk_g2s(sm.hstage[st] + p * kHalfPanel, src + (size_t)p * kPanelBytes, kHalfPanel,
-                   sm.full[st]);
+          bulk_g2s(w_smem + p * kPanelBytes, Wp + (size_t)slice * 4 * kPanelBytes + (size_t)p * kPanelBytes,
+                   kPanelBytes, sm.w_full());
       }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // ---- likelihood-GEMM issuer: hi_a P1a, hi_b P1b, hi_a P2a, hi_b P2b, lo_a P1a, lo_b P1b
-    const bool leader = elect_one();
-    const uint64_t x_desc0 = make_desc(sm.hstage[0], 16, 1024);  // K-major view of the frames
-    constexpr int wp[6] = {0, 1, 0, 1, 2, 3};
-    constexpr int xp[6] = {0, 1, 2, 3, 0, 1};
-    mbar_wait(sm.w_tmem, 0);  // epilogue warps copied the weights into TMEM
-    LR_PT(0);
-    for (int h = 0; h < n_half; h++) {
-      const int st = h % kHStages, sb = h & 1;
-      mbar_wait(sm.full[st], (h / kHStages) & 1);
-      LR_PT(1);
-      if (h >= 2) mbar_wait(sm.s_free[sb], ((h >> 1) - 1) & 1);
-      LR_PT(2);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t d_tmem = tmem_base + kOColS + sb * kHF;
-        const uint64_t xd0 = desc_add(x_desc0, st * kHalfBytes);
-        uint32_t acc = 0;
-#pragma unroll
-        for (int q = 0; q < 6; q++) {
-#pragma unroll
-          for (int kk = 0; kk < 4; kk++) {
-            umma_ts(d_tmem, tmem_base + kOColW + wp[q] * 32 + kk * 8,
-                    desc_add(xd0, xp[q] * kHalfPanel + kk * 32), idesc1, acc);
-            acc = 1;
-          }
+      for (int h = 0; h < n_half; h++) {
+        const int st = h % kOStages;
+        if (h == 4) mbar_wait(sm.w_tmem(), 0);  // stages 4, 5 held the weights until they were in TMEM
+        mbar_wait(sm.empty(st), ((h / kOStages) & 1) ^ 1);
+        if (leader) {
+          mbar_expect_tx(sm.full(st), kHalfBytes);
+          const unsigned char *src =
+              Xh + (size_t)(t_begin + (h >> 1)) * kTileBytes + (size_t)(h & 1) * kHalfPanel;
+          for (int p = 0; p < 4; p++)
+            bulk_g2s(sm.stage0 + st * kHalfBytes + p * kHalfPanel, src + (size_t)p * kPanelBytes,
+                     kHalfPanel, sm.full(st));
         }
-        umma_commit(sm.s_full[sb]);
+        __syncwarp();
       }
-      __syncwarp();
-      LR_PT(3);
-    }
-    if (PROF && lane == 0)
-      for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)prof + 32 + i, (unsigned long long)pacc[i]);
-  } else if (warp == 3) {
-    // ---- statistics-GEMM issuer: F[c, :] (+)= P[c, t] A[t, :]; B = hi panels, then lo panels,
-    // read MN-major (64-wide chunks = half panels, kHalfPanel apart)
-    const bool leader = elect_one();
-    const uint64_t b_desc0 = make_desc(sm.hstage[0], (uint32_t)kHalfPanel, 1024);
-    int n_flush = 0;
-    TileInfo ti = n_half > 0 ? tinfo[t_begin] : TileInfo{0, 0};
-    TileInfo ti_next = ti;
-    for (int h = 0; h < n_half; h++) {
-      const int st = h % kHStages, ps = h % kNP;
-      if (!(h & 1)) {
-        ti = ti_next;
-        if (h + 2 < n_half) ti_next = tinfo[t_begin + (h >> 1) + 1];
-      }
-      const bool first = (ti.flags & 1) && !(h & 1), last = (ti.flags & 2) && (h & 1);
-      mbar_wait(sm.full[st], (h / kHStages) & 1);
-      LR_PT(1);
-      mbar_wait(sm.p_ready[ps], (h / kNP) & 1);
-      LR_PT(2);
-      if (first && n_flush > 0) mbar_wait(sm.f_empty, (n_flush - 1) & 1);
-      LR_PT(3);
-      tc_fence_after();
-      if (leader) {
-        uint32_t acc = first ? 0u : 1u;
-        const uint64_t bd0 = desc_add(b_desc0, st * kHalfBytes);
+    } else if (warp == 1) {
+      // ---- likelihood-GEMM issuer: hi_a P1a, hi_b P1b, hi_a P2a, hi_b P2b, lo_a P1a, lo_b P1b
+      const bool leader = elect_one();
+      const uint64_t x_desc0 = make_desc(sm.stage0, 16, 1024);  // K-major view of the frames
+      constexpr int wp[6] = {0, 1, 0, 1, 2, 3};
+      constexpr int xp[6] = {0, 1, 2, 3, 0, 1};
+      mbar_wait(sm.w_tmem(), 0);  // the weights are in TMEM
+      LR_PT(0);
+      for (int h = 0; h < n_half; h++) {
+        const int st = h % kOStages, sb = h % kNS;
+        mbar_wait(sm.full(st), (h / kOStages) & 1);
+        LR_PT(1);
+        if (h >= kNS) mbar_wait(sm.s_free(sb), ((h / kNS) - 1) & 1);
+        LR_PT(2);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t d_tmem = tmem_base + kOColS + sb * kHF;
+          const uint64_t xd0 = desc_add(x_desc0, st * kHalfBytes);
+          uint32_t acc = 0;
 #pragma unroll
-        for (int part = 0; part < 2; part++) {
+          for (int q = 0; q < 6; q++) {
 #pragma unroll
-          for (int kk = 0; kk < kHF / 16; kk++) {
-            umma_ts(tmem_f, tmem_base + kOColP + ps * 32 + kk * 8,
-                    desc_add(bd0, part * 2 * kHalfPanel + kk * 2048), idesc2, acc);
-            acc = 1;
+            for (int kk = 0; kk < 4; kk++) {
+              umma_ts(d_tmem, tmem_base + kOColW + wp[q] * 32 + kk * 8,
+                      desc_add(xd0, xp[q] * kHalfPanel + kk * 32), idesc1, acc);
+              acc = 1;
+            }
           }
+          umma_commit(sm.s_full(sb));
         }
-        umma_commit(sm.empty[st]);
-        umma_commit(sm.p_free[ps]);
-        if (last) umma_commit(sm.f_full);
+        __syncwarp();
+        LR_PT(3);
       }
-      if (last) n_flush++;
-      __syncwarp();
-      LR_PT(4);
+      LR_PDUMP(3);
+    } else if (warp == 2) {
+      // (TMEM allocator: nothing to do in the main loop)
+    } else {
+      // ---- statistics-GEMM issuer: F[c, :] (+)= P[c, t] A[t, :]; B = hi panels, then lo panels,
+      // read MN-major (64-wide chunks = half panels, kHalfPanel apart)
+      const bool leader = elect_one();
+      const uint64_t b_desc0 = make_desc(sm.stage0, (uint32_t)kHalfPanel, 1024);
+      int n_flush = 0;
+      TileInfo ti = n_half > 0 ? tinfo[t_begin] : TileInfo{0, 0};
+      TileInfo ti_next = ti;
+      for (int h = 0; h < n_half; h++) {
+        const int st = h % kOStages, ps = h & 1;
+        if (!(h & 1)) {
+          ti = ti_next;
+          if (h + 2 < n_half) ti_next = tinfo[t_begin + (h >> 1) + 1];
+        }
+        const bool first = (ti.flags & 1) && !(h & 1), last = (ti.flags & 2) && (h & 1);
+        mbar_wait(sm.full(st), (h / kOStages) & 1);
+        LR_PT(1);
+        mbar_wait(sm.p_ready(ps), (h >> 1) & 1);
+        LR_PT(2);
+        if (first && n_flush > 0) mbar_wait(sm.f_empty(), (n_flush - 1) & 1);
+        LR_PT(3);
+        tc_fence_after();
+        if (leader) {
+          uint32_t acc = first ? 0u : 1u;
+          const uint64_t bd0 = desc_add(b_desc0, st * kHalfBytes);
+#pragma unroll
+          for (int part = 0; part < 2; part++) {
+#pragma unroll
+            for (int kk = 0; kk < kHF / 16; kk++) {
+              umma_ts(tmem_f, tmem_base + kOColP + ps * 32 + kk * 8,
+                      desc_add(bd0, part * 2 * kHalfPanel + kk * 2048), idesc2, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(sm.empty(st));
+          umma_commit(sm.p_free(ps));
+          if (last) umma_commit(sm.f_full());
+        }
+        if (last) n_flush++;
+        __syncwarp();
+        LR_PT(4);
+      }
+      LR_PDUMP(4);
     }
-    if (PROF && lane == 0)
-      for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)prof + 48 + i, (unsigned long long)pacc[i]);
-  } else if (warp >= 4) {
-    // ---- two epilogue teams of four warps (one per TMEM lane quarter q); team t owns the half
-    // tiles h = t, t + 2, ...
-    const int q = warp & 3, team = (warp - 4) >> 2;
-    const int et = threadIdx.x - 128 - team * 128;  // 0..127 inside the team
+  } else if (warp < 20) {
+    // ---- E1: 16 warps = parity (2) x column half (2) x TMEM lane quarter q (4)
+    // 4 x 24 + 16 x 104 + 4 x 40 = 24 x 80: the CTA's register allocation is redistributed, not grown
+    reg_alloc<104>();
+    const int q = warp & 3, ch = ((warp - 4) >> 2) & 1, par = (warp - 4) >> 3;
+    const int t4 = 2 * par + ch;  // 0..3: the statistics columns 32 (t4 & 1).. of F (t4 < 2) or S2 in the flush
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t lane_addr16 = (uint32_t)(q * 32 + 16) << 16;
-    // shared memory of the weights is free once they live in TMEM: [0, 32 KB) flush staging
-    // (8 warps x 4 KB), then 4 KB of exchange area per team
-    float *stg = reinterpret_cast<float *>(base_ptr) + (warp - 4) * kStageFloats;
-    unsigned char *xa = base_ptr + 32 * 1024 + team * 4096;
-    float *wmax = reinterpret_cast<float *>(xa);            // [4 warps][64 frames]
-    float *wsum = reinterpret_cast<float *>(xa + 1024);     // [4 warps][64 frames]
-    __half *fm = reinterpret_cast<__half *>(xa + 2048);     // [64] mantissa of the rescale factor
-    __half *fp = reinterpret_cast<__half *>(xa + 2048 + 128);  // [64] its power of two
+    float *stg = reinterpret_cast<float *>(base_ptr + kOStgOff) + (warp - 4) * 128;  // 32 x 4 floats
     {
-      // weights: shared memory (swizzled panels) -> TMEM rows; team t copies the panels t, t + 2
-      mbar_wait(sm.w_full, 0);
+      // weights: shared memory (swizzled panels) -> TMEM rows; warp (t4, q) copies the rows 32 q.. of panel t4
+      mbar_wait(sm.w_full(), 0);
       const int r = q * 32 + lane;
-      for (int p = team; p < 4; p += 2) {
 #pragma unroll
-        for (int half16 = 0; half16 < 2; half16++) {
-          uint32_t v[16];
+      for (int half16 = 0; half16 < 2; half16++) {
+        uint32_t v[16];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int chunk = half16 * 4 + j;
-            const uint32_t a = sm.w + p * kPanelBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
-                         : "r"(a));
-          }
-          tmem_st16(tmem_base + lane_addr + kOColW + p * 32 + half16 * 16, v);
+        for (int j = 0; j < 4; j++) {
+          const int chunk = half16 * 4 + j;
+          const uint32_t a = w_smem + t4 * kPanelBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                       : "r"(a));
         }
+        tmem_st16(tmem_base + lane_addr + kOColW + t4 * 32 + half16 * 16, v);
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sm.w_tmem);
+      if (lane == 0) mbar_arrive(sm.w_tmem());
     }
-    const long frame0 = (long)t_begin * kTile;
-    unsigned long long *ring = xch + (size_t)group * kXRing * n_slices * kHF;
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    double llk_acc = 0.0;
+    const bool b4 = lane & 16, b3 = lane & 8;
+    const int jo = (lane >> 3) & 3;  // the column group (of 8) whose warp results this lane ends up holding
+    const int mycol = ch * 32 + 8 * jo + 2 * (lane & 3);  // first of the two frame columns this lane owns
     int n_flush = 0;
+    uint32_t pk0[8], pk1[8];   // posteriors of the HELD half tile (fp16 pairs), relative to the warp maximum
+    float mw0 = 0.f, mw1 = 0.f;  // warp maxima of the frames mycol, mycol + 1 of that half tile
 
-    auto epi1 = [&](int h) {
-      const int sb = h & 1, ps = h % kNP;
-      LR_PT(0);
-      mbar_wait(sm.s_full[sb], (h >> 1) & 1);
-      LR_PT(1);
+    // ---- second half of a half tile's life: rescale the held posteriors, store them, flush at run ends
+    auto finish = [&](int h, const TileInfo ti) {
+      const int rs = h % kNR;
+      LR_PT(4);
+      mbar_wait(sm.lse_ready(rs), (h / kNR) & 1);
+      LR_PT(5);
+      // rescale factors 2^d, d = max_warp - lse <= 0 (up to rounding), for the frames mycol, mycol + 1,
+      // applied as two fp16 factors: a mantissa in (0.5, 1] times 2^ka (ka >= -13: a normal fp16) and
+      // the exact power of two 2^(k - ka) >= 2^-24; below 2^-38 nothing of the warp's components
+      // survives in fp16
+      uint32_t fm2, fp2;
+      {
+        const float2 l2 = *reinterpret_cast<const float2 *>(lse_s + rs * kHF + mycol);
+        const float d0 = mw0 - l2.x, d1 = mw1 - l2.y;
+        const float k0 = ceilf(d0), k1 = ceilf(d1);
+        const float ka0 = fmaxf(k0, -13.f), ka1 = fmaxf(k1, -13.f);
+        const bool dead0 = !(d0 > -38.f), dead1 = !(d1 > -38.f);
+        __half2 a = __floats2half2_rn(dead0 ? 0.f : ex2f((d0 - k0) + ka0), dead1 ? 0.f : ex2f((d1 - k1) + ka1));
+        __half2 b = __floats2half2_rn(dead0 ? 0.f : ex2f(fmaxf(k0 - ka0, -24.f)),
+                                      dead1 ? 0.f : ex2f(fmaxf(k1 - ka1, -24.f)));
+        fm2 = *reinterpret_cast<uint32_t *>(&a);
+        fp2 = *reinterpret_cast<uint32_t *>(&b);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        // packed column 4 j + lane % 4 = frames 8 j + 2 (lane % 4), +1: factors held by the lane 8 j + lane % 4
+        const uint32_t ua = __shfl_sync(0xFFFFFFFFu, fm2, 8 * j + (lane & 3));
+        const uint32_t ub = __shfl_sync(0xFFFFFFFFu, fp2, 8 * j + (lane & 3));
+        const __half2 a = *reinterpret_cast<const __half2 *>(&ua), b = *reinterpret_cast<const __half2 *>(&ub);
+#pragma unroll
+        for (int r2 = 0; r2 < 2; r2++) {
+          __half2 x = *reinterpret_cast<__half2 *>(&pk0[2 * j + r2]);
+          x = __hmul2(__hmul2(x, a), b);
+          pk0[2 * j + r2] = *reinterpret_cast<uint32_t *>(&x);
+          __half2 y = *reinterpret_cast<__half2 *>(&pk1[2 * j + r2]);
+          y = __hmul2(__hmul2(y, a), b);
+          pk1[2 * j + r2] = *reinterpret_cast<uint32_t *>(&y);
+        }
+      }
+      if (h >= 2) {
+        mbar_wait(sm.p_free(par), ((h >> 1) - 1) & 1);  // G2(h - 2) is done with the slot
+        tc_fence_after();
+      }
+      LR_PT(6);
+      tmem_st_16x128b_x4(tmem_base + lane_addr + kOColP + par * 32 + ch * 16, pk0);
+      tmem_st_16x128b_x4(tmem_base + lane_addr16 + kOColP + par * 32 + ch * 16, pk1);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.p_ready(par));
+      LR_PT(7);
+      if (!(ti.flags & 2)) return;
+      // ---- flush of the run that ends with this tile.  TMEM: lane = component, columns
+      // [xh, 1 (64) | xh^2 (64)]; warp (t4, q) owns the components 32 q.. and the columns 32 (t4 & 1)..
+      // of F (t4 < 2) or of S2 (t4 >= 2).  The increments are staged through shared memory (fp32),
+      // 4 columns at a time, so that the fp64 atomics of a row's block are coalesced.
+      mbar_wait(sm.f_full(), n_flush & 1);
+      n_flush++;
       tc_fence_after();
-      uint32_t v0[32], v1[32];  // lanes 32q + {t/4, t/4+8} and 32q + 16 + {t/4, t/4+8}
-      tmem_ld_16x256b_x8(tmem_base + lane_addr + kOColS + sb * kHF, v0);
-      tmem_ld_16x256b_x8(tmem_base + lane_addr16 + kOColS + sb * kHF, v1);
+      const int comp0 = slice * kSlice + q * 32;
+      const double sc = 1.0 / 16384.0;  // undo the 2^14 posterior scale
+      const double n = (double)__uint_as_float(tmem_ld1(tmem_f + lane_addr + kOneCol)) * sc;
+      const size_t rc0 = (size_t)ti.row * C + comp0;
+      const int k0 = 32 * (t4 & 1);
+      uint32_t a1[32], a2[32];
+      tmem_ld32(tmem_f + lane_addr + k0, a1);
+      if (EM && t4 >= 2) tmem_ld32(tmem_f + lane_addr + 64 + k0, a2);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sm.s_free[sb]);  // S is in registers: the next G1 may overwrite it
-      LR_PT(2);
-      // ---- per-frame max over the slice's 128 components
-      float a16[16], a8[8], a4[4], a2[2];
+      if (lane == 0) mbar_arrive(sm.f_empty());  // accumulator columns are free again
+      if (dbg & 2) return;
+      if (t4 == 1 && out_N && comp0 + lane < C) atomicAdd(&out_N[rc0 + lane], fw * n);
+      double *dst = t4 < 2 ? out_F : out_S2;
+      if ((!EM && t4 >= 2) || !dst) return;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
+      for (int c4 = 0; c4 < 8; c4++) {  // 4 statistics columns per round
+        __syncwarp();
 #pragma unroll
-        for (int e = 0; e < 2; e++)
-          a16[2 * j + e] = fmaxf(fmaxf(__uint_as_float(v0[4 * j + e]), __uint_as_float(v0[4 * j + 2 + e])),
-                                 fmaxf(__uint_as_float(v1[4 * j + e]), __uint_as_float(v1[4 * j + 2 + e])));
-      }
-      lane_halve<8, true>(a16, a8, b4, 16);
-      lane_halve<4, true>(a8, a4, b3, 8);
-      lane_halve<2, true>(a4, a2, b2, 4);
-      // this thread now holds the warp's maxima of the frame columns 2 lane, 2 lane + 1
-      *reinterpret_cast<float2 *>(wmax + q * kHF + 2 * lane) = make_float2(a2[0], a2[1]);
-      LR_PT(3);
-      named_bar_sync(1 + team, 128);
-      LR_PT(4);
-      float nm[16];  // 14 - max over the four warps, for this thread's 16 columns
-      {
-        const float2 m0 = *reinterpret_cast<const float2 *>(wmax + 0 * kHF + 2 * lane);
-        const float2 m1 = *reinterpret_cast<const float2 *>(wmax + 1 * kHF + 2 * lane);
-        const float2 m2 = *reinterpret_cast<const float2 *>(wmax + 2 * kHF + 2 * lane);
-        const float2 m3 = *reinterpret_cast<const float2 *>(wmax + 3 * kHF + 2 * lane);
-        // this lane: 14 - slice maximum of the columns 2 lane, 2 lane + 1; the columns
-        // 8 j + 2 (lane % 4) + e this thread works on belong to the lane 4 j + lane % 4
-        const float own0 = kGammaShift - fmaxf(fmaxf(m0.x, m1.x), fmaxf(m2.x, m3.x));
-        const float own1 = kGammaShift - fmaxf(fmaxf(m0.y, m1.y), fmaxf(m2.y, m3.y));
+        for (int e = 0; e < 4; e++) {
+          const int k = k0 + 4 * c4 + e;
+          float inc = 0.f;
+          if (k < D) {
+            const double f1 = (double)__uint_as_float(a1[4 * c4 + e]) * sc;
+            if (t4 < 2) {
+              inc = (float)(fw * (s[k] * f1 + g[k] * n));
+            } else {
+              const double q2 = (double)__uint_as_float(a2[4 * c4 + e]) * sc;
+              const double sk = s[k], gk = g[k];
+              inc = (float)(fw * (sk * sk * q2 + 2.0 * sk * gk * f1 + gk * gk * n));
+            }
+          }
+          stg[lane * 4 + (e ^ (lane & 3))] = inc;
+        }
+        __syncwarp();
+        // lane -> (component lane / 4 + 8 i, column lane % 4): 4 consecutive doubles per component
+        const int kk = k0 + 4 * c4 + (lane & 3);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          nm[2 * j] = __shfl_sync(0xFFFFFFFFu, own0, 4 * j + (lane & 3));
-          nm[2 * j + 1] = __shfl_sync(0xFFFFFFFFu, own1, 4 * j + (lane & 3));
+        for (int i = 0; i < 4; i++) {
+          const int c = (lane >> 2) + 8 * i;
+          if (kk < D && comp0 + c < C)
+            atomicAdd(&dst[(rc0 + c) * D + kk], (double)stg[c * 4 + ((lane & 3) ^ (c & 3))]);
         }
       }
-      // ---- posteriors relative to the slice maximum, scaled by 2^14
+      __syncwarp();
+    };
+
+    int prev = -1;
+    TileInfo ti_prev{0, 0};
+    for (int h = par; h < n_half; h += 2) {
+      const int sb = h % kNS, rs = h % kNR;
+      const TileInfo ti_h = tinfo[t_begin + (h >> 1)];  // consumed one iteration later (run ends)
+      LR_PT(0);
+      mbar_wait(sm.s_full(sb), (h / kNS) & 1);
+      LR_PT(1);
+      tc_fence_after();
+      uint32_t v0[16], v1[16];  // lanes 32q + {t/4, t/4+8} and 32q + 16 + {t/4, t/4+8}; reg 4 j + 2 rs + e
+      tmem_ld_16x256b_x4(tmem_base + lane_addr + kOColS + sb * kHF + ch * 32, v0);
+      tmem_ld_16x256b_x4(tmem_base + lane_addr16 + kOColS + sb * kHF + ch * 32, v1);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.s_free(sb));  // S is in registers: a later G1 may overwrite it
+      LR_PT(2);
+      // ---- per-frame max over the warp's 32 components
+      float a8[8], a4[4], a2[2];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
+      for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+          a8[2 * j + e] = fmaxf(fmaxf(__uint_as_float(v0[4 * j + e]), __uint_as_float(v0[4 * j + 2 + e])),
+                                fmaxf(__uint_as_float(v1[4 * j + e]), __uint_as_float(v1[4 * j + 2 + e])));
+      }
+      lane_halve<4, true>(a8, a4, b4, 16);
+      lane_halve<2, true>(a4, a2, b3, 8);
+      a2[0] = fmaxf(a2[0], __shfl_xor_sync(0xFFFFFFFFu, a2[0], 4));
+      a2[1] = fmaxf(a2[1], __shfl_xor_sync(0xFFFFFFFFu, a2[1], 4));
+      // this lane holds the warp maxima of the columns 8 jo + 2 (lane % 4) + {0, 1}; the columns
+      // 8 j + 2 (lane % 4) + e it works on are held by the lane 8 j + lane % 4
+      const float nw0 = a2[0], nw1 = a2[1];
+      float nm[8];  // 14 - warp maximum of this thread's 8 columns
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        nm[2 * j] = kGammaShift - __shfl_sync(0xFFFFFFFFu, nw0, 8 * j + (lane & 3));
+        nm[2 * j + 1] = kGammaShift - __shfl_sync(0xFFFFFFFFu, nw1, 8 * j + (lane & 3));
+      }
+      // ---- posteriors relative to the warp maximum, scaled by 2^14
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           v0[4 * j + k] = __float_as_uint(ex2f(__uint_as_float(v0[4 * j + k]) + nm[2 * j + (k & 1)]));
@@ -1367,258 +1496,125 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
+      for (int j = 0; j < 4; j++) {
 #pragma unroll
         for (int e = 0; e < 2; e++)
-          a16[2 * j + e] = (__uint_as_float(v0[4 * j + e]) + __uint_as_float(v0[4 * j + 2 + e])) +
-                           (__uint_as_float(v1[4 * j + e]) + __uint_as_float(v1[4 * j + 2 + e]));
+          a8[2 * j + e] = (__uint_as_float(v0[4 * j + e]) + __uint_as_float(v0[4 * j + 2 + e])) +
+                          (__uint_as_float(v1[4 * j + e]) + __uint_as_float(v1[4 * j + 2 + e]));
       }
-      lane_halve<8, false>(a16, a8, b4, 16);
-      lane_halve<4, false>(a8, a4, b3, 8);
-      lane_halve<2, false>(a4, a2, b2, 4);
-      *reinterpret_cast<float2 *>(wsum + q * kHF + 2 * lane) = make_float2(a2[0], a2[1]);
+      lane_halve<4, false>(a8, a4, b4, 16);
+      lane_halve<2, false>(a4, a2, b3, 8);
+      a2[0] += __shfl_xor_sync(0xFFFFFFFFu, a2[0], 4);
+      a2[1] += __shfl_xor_sync(0xFFFFFFFFu, a2[1], 4);
+      if (!(lane & 4)) {  // lanes with bit 2 set hold duplicates
+        *reinterpret_cast<float2 *>(wmax + (rs * 4 + q) * kHF + mycol) = make_float2(nw0, nw1);
+        *reinterpret_cast<float2 *>(wsum + (rs * 4 + q) * kHF + mycol) = make_float2(a2[0], a2[1]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.ms_written(rs));
       // ---- pack the frame pairs (2 pc, 2 pc + 1) into the fp16 column pc = 4 j + t % 4
-      uint32_t pk0[16], pk1[16];
+      uint32_t n0[8], n1[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
+      for (int j = 0; j < 4; j++) {
 #pragma unroll
-        for (int rs = 0; rs < 2; rs++) {
-          __half2 h0 = __floats2half2_rn(__uint_as_float(v0[4 * j + 2 * rs]), __uint_as_float(v0[4 * j + 2 * rs + 1]));
-          __half2 h1 = __floats2half2_rn(__uint_as_float(v1[4 * j + 2 * rs]), __uint_as_float(v1[4 * j + 2 * rs + 1]));
-          pk0[2 * j + rs] = *reinterpret_cast<uint32_t *>(&h0);
-          pk1[2 * j + rs] = *reinterpret_cast<uint32_t *>(&h1);
+        for (int r2 = 0; r2 < 2; r2++) {
+          __half2 h0 = __floats2half2_rn(__uint_as_float(v0[4 * j + 2 * r2]), __uint_as_float(v0[4 * j + 2 * r2 + 1]));
+          __half2 h1 = __floats2half2_rn(__uint_as_float(v1[4 * j + 2 * r2]), __uint_as_float(v1[4 * j + 2 * r2 + 1]));
+          n0[2 * j + r2] = *reinterpret_cast<uint32_t *>(&h0);
+          n1[2 * j + r2] = *reinterpret_cast<uint32_t *>(&h1);
         }
       }
-      LR_PT(5);
-      if (h >= kNP) {
-        mbar_wait(sm.p_free[ps], ((h / kNP) - 1) & 1);  // G2(h - kNP) is done with the slot
-        tc_fence_after();
-      }
-      LR_PT(6);
-      tmem_st_16x128b_x8(tmem_base + lane_addr + kOColP + ps * 32, pk0);
-      tmem_st_16x128b_x8(tmem_base + lane_addr16 + kOColP + ps * 32, pk1);
-      tmem_wait_st();
-      LR_PT(7);
-      named_bar_sync(1 + team, 128);  // every warp's sums are in shared memory
-      LR_PT(8);
-      if (et < kHF) {
-        const float m = fmaxf(fmaxf(wmax[et], wmax[kHF + et]), fmaxf(wmax[2 * kHF + et], wmax[3 * kHF + et]));
-        const float z = ((wsum[et] + wsum[kHF + et]) + (wsum[2 * kHF + et] + wsum[3 * kHF + et])) *
-                        (1.f / 16384.f);
-        const unsigned tag = (((unsigned)h / kXRing) & 1u) ^ 1u;
-        const unsigned long long word =
-            ((unsigned long long)(__float_as_uint(z) | (tag << 31)) << 32) | __float_as_uint(m);
-        st_relaxed_u64(ring + ((size_t)(h % kXRing) * n_slices + slice) * kHF + et, word);
-      }
-    };
-
-    auto epi2 = [&](int h) {
-      const int ps = h % kNP;
-      LR_PT(9);
-      if (et < kHF) {
-        const unsigned long long *src = ring + (size_t)(h % kXRing) * n_slices * kHF + et;
-        const unsigned long long tag = ((((unsigned)h / kXRing) & 1u) ^ 1u);
-        float m = -3.0e38f, z = 0.f, m_own = 0.f;
-        // Cheap probe first: lane i of this warp watches ONE word of the slices i, i + 32, ... (the
-        // first frame of this warp's 32, written by the same store instruction as the other 31), with
-        // a short sleep between attempts, so that waiting costs 8 B per slice and attempt instead of
-        // the whole 512 B block -- spinning on the full block took half of the L2 bandwidth.
-        {
-          const unsigned long long *probe = ring + (size_t)(h % kXRing) * n_slices * kHF + (et & 32);
-          bool ok;
-          do {
-            ok = true;
-            for (int sl = lane; sl < n_slices; sl += 32)
-              ok = ok && ((ld_relaxed_u64(probe + (size_t)sl * kHF) >> 63) == tag);
-            ok = __all_sync(0xFFFFFFFFu, ok) || (dbg & 1);
-            if (!ok) __nanosleep(40);
-          } while (!ok);
-        }
-        LR_PT(16);
-        // the words of up to 16 slices are fetched together (independent loads: one L2 round trip
-        // per batch instead of one per slice) and re-fetched until every lap tag matches
-        for (int s0 = 0; s0 < n_slices; s0 += 16) {
-          unsigned long long u[16];
-          bool ready;
-          do {
-            ready = true;
+      LR_PT(3);
+      // the previous half tile of this warp: its normaliser has had this whole iteration to arrive
+      if (prev >= 0) finish(prev, ti_prev);
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-              u[i] = (s0 + i < n_slices) ? ld_relaxed_u64(src + (size_t)(s0 + i) * kHF) : (tag << 63);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i++) ready = ready && ((u[i] >> 63) == tag);
-          } while (!ready && !(dbg & 1));
-          LR_PT(17);
-#pragma unroll
-          for (int i = 0; i < 16; i++) {
-            if (s0 + i < n_slices) {
-              const float ms = __uint_as_float((unsigned)u[i]);
-              const float zs = __uint_as_float((unsigned)(u[i] >> 32) & 0x7FFFFFFFu);
-              if (s0 + i == slice) m_own = ms;
-              const float mn = fmaxf(m, ms);
-              z = z * ex2f(m - mn) + zs * ex2f(ms - mn);
-              m = mn;
-            }
-          }
-        }
-        const float lse = m + log2f(z);
-        const long f = frame0 + (long)h * kHF + et;
-        if (slice == 0) {
-          if (lse_out) lse_out[f] = lse;
-          if (f < P && (!index || index[f] != kPadIndex)) llk_acc += (double)lse;
-        }
-        // rescale factor 2^d, d = max_slice - lse <= 0 (up to rounding), applied as two fp16
-        // factors: a mantissa in (0.5, 1] times 2^ka (ka >= -13: a normal fp16) and the exact
-        // power of two 2^(k - ka) >= 2^-24; below 2^-38 nothing of the slice survives in fp16
-        const float d = m_own - lse;
-        const float k = ceilf(d);
-        const float ka = fmaxf(k, -13.f);
-        const bool dead = !(d > -38.f);
-        fm[et] = __float2half_rn(dead ? 0.f : ex2f((d - k) + ka));
-        fp[et] = __float2half_rn(dead ? 0.f : ex2f(fmaxf(k - ka, -24.f)));
+      for (int i = 0; i < 8; i++) {
+        pk0[i] = n0[i];
+        pk1[i] = n1[i];
       }
-      LR_PT(18);
-      named_bar_sync(1 + team, 128);
-      LR_PT(11);
-      uint32_t p0[16], p1[16];
-      tmem_ld_16x128b_x8(tmem_base + lane_addr + kOColP + ps * 32, p0);
-      tmem_ld_16x128b_x8(tmem_base + lane_addr16 + kOColP + ps * 32, p1);
-      tmem_wait_ld();
-      const __half2 *fm2 = reinterpret_cast<const __half2 *>(fm), *fp2 = reinterpret_cast<const __half2 *>(fp);
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const __half2 a = fm2[4 * j + (lane & 3)], b = fp2[4 * j + (lane & 3)];
-#pragma unroll
-        for (int rs = 0; rs < 2; rs++) {
-          __half2 x = *reinterpret_cast<__half2 *>(&p0[2 * j + rs]);
-          x = __hmul2(__hmul2(x, a), b);
-          p0[2 * j + rs] = *reinterpret_cast<uint32_t *>(&x);
-          __half2 y = *reinterpret_cast<__half2 *>(&p1[2 * j + rs]);
-          y = __hmul2(__hmul2(y, a), b);
-          p1[2 * j + rs] = *reinterpret_cast<uint32_t *>(&y);
-        }
-      }
-      tmem_st_16x128b_x8(tmem_base + lane_addr + kOColP + ps * 32, p0);
-      tmem_st_16x128b_x8(tmem_base + lane_addr16 + kOColP + ps * 32, p1);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sm.p_ready[ps]);
-      LR_PT(12);
-      named_bar_sync(1 + team, 128);  // fm / fp (and wmax / wsum) may be rewritten from here on
-      LR_PT(13);
-    };
-
-    // Flush of the run that ends with the tile of half tile h.  TMEM: lane = component, columns
-    // [xh, 1 (64) | xh^2 (64)]; warp (q, team) owns the statistics columns 32 team.. of the
-    // components 32 q..  The increments are staged through shared memory (fp32) so that the fp64
-    // read-modify-write of the row's [128 comps x D] block is coalesced (lane = dimension).
-    auto flush = [&](const TileInfo ti) {
-      LR_PT(0);
-      mbar_wait(sm.f_full, n_flush & 1);
-      LR_PT(14);
-      n_flush++;
-      tc_fence_after();
-      const int comp0 = slice * kSlice + q * 32;
-      const double sc = 1.0 / 16384.0;  // undo the 2^14 posterior scale
-      const double n = (double)__uint_as_float(tmem_ld1(tmem_f + lane_addr + kOneCol)) * sc;
-      const size_t rc0 = (size_t)ti.row * C + comp0;
-      const int k0 = team * 32;
-      uint32_t a1[32], a2[32];
-      tmem_ld32(tmem_f + lane_addr + k0, a1);
-      if (EM) tmem_ld32(tmem_f + lane_addr + 64 + k0, a2);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sm.f_empty);  // accumulator columns are free again
-      if (dbg & 2) return;
-      if (team == 1 && out_N && comp0 + lane < C) atomicAdd(&out_N[rc0 + lane], fw * n);
-      __syncwarp();
-#pragma unroll
-      for (int e = 0; e < 32; e++) {
-        const int k = k0 + e;
-        float inc = 0.f;
-        if (k < D) inc = (float)(fw * (s[k] * ((double)__uint_as_float(a1[e]) * sc) + g[k] * n));
-        stg[lane * 32 + (e ^ lane)] = inc;
-      }
-      __syncwarp();
-      if (out_F && k0 + lane < D) {
-#pragma unroll 8
-        for (int c = 0; c < 32; c++) {
-          if (comp0 + c < C)
-            atomicAdd(&out_F[(rc0 + c) * D + k0 + lane], (double)stg[c * 32 + (lane ^ c)]);
-        }
-      }
-      if (EM && out_S2) {
-        __syncwarp();
-#pragma unroll
-        for (int e = 0; e < 32; e++) {
-          const int k = k0 + e;
-          float inc = 0.f;
-          if (k < D) {
-            const double f1 = (double)__uint_as_float(a1[e]) * sc, q2 = (double)__uint_as_float(a2[e]) * sc;
-            const double sk = s[k], gk = g[k];
-            inc = (float)(fw * (sk * sk * q2 + 2.0 * sk * gk * f1 + gk * gk * n));
-          }
-          stg[lane * 32 + (e ^ lane)] = inc;
-        }
-        __syncwarp();
-        if (k0 + lane < D) {
-#pragma unroll 4
-          for (int c = 0; c < 32; c++) {
-            if (comp0 + c < C)
-              atomicAdd(&out_S2[(rc0 + c) * D + k0 + lane], (double)stg[c * 32 + (lane ^ c)]);
-          }
-        }
-      }
-      __syncwarp();
-      LR_PT(15);
-    };
-
-    int prev = -1;
-    TileInfo ti_prev{0, 0};
-    for (int h = team; h < n_half; h += 2) {
-      const TileInfo ti_h = tinfo[t_begin + (h >> 1)];  // consumed one iteration later
-      epi1(h);
-      if (prev >= 0) {
-        epi2(prev);
-        if (ti_prev.flags & 2) flush(ti_prev);
-      }
+      mw0 = nw0;
+      mw1 = nw1;
       prev = h;
       ti_prev = ti_h;
     }
-    if (prev >= 0) {
-      epi2(prev);
-      if (ti_prev.flags & 2) flush(ti_prev);
+    if (prev >= 0) finish(prev, ti_prev);
+    if (q == 0 && ch == 0) LR_PDUMP(par);
+  } else {
+    // ---- L: four warps (parity x column half), lane = frame: publish the slice's (max, sum), then the
+    // log-sum-exp over all slices
+    reg_dealloc<40>();
+    const int ch = (warp - 20) & 1, par = (warp - 20) >> 1;
+    const int lw = warp - 20;
+    double llk_acc = 0.0;
+    for (int h = par; h < n_half; h += 2) {
+      const int rs = h % kNR;
+      LR_PT(0);
+      mbar_wait(sm.ms_written(rs), (h / kNR) & 1);  // the E1 warps' (max, sum) are in shared memory
+      LR_PT(1);
+      const unsigned long long tag = ((((unsigned)h / kXRing) & 1u) ^ 1u);
+      unsigned long long *slot = ring + ((size_t)(h % kXRing) * 2 + ch) * n_slices * 32 + lane;
+      {
+        const float *pm = wmax + rs * 4 * kHF + ch * 32 + lane, *pz = wsum + rs * 4 * kHF + ch * 32 + lane;
+        const float m0 = pm[0], m1 = pm[kHF], m2 = pm[2 * kHF], m3 = pm[3 * kHF];
+        const float ms = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const float zs = ((pz[0] * ex2f(m0 - ms) + pz[kHF] * ex2f(m1 - ms)) +
+                          (pz[2 * kHF] * ex2f(m2 - ms) + pz[3 * kHF] * ex2f(m3 - ms))) * (1.f / 16384.f);
+        st_relaxed_u64(slot + (size_t)slice * 32,
+                       ((unsigned long long)(__float_as_uint(zs) | ((unsigned)tag << 31)) << 32) | __float_as_uint(ms));
+      }
+      LR_PT(2);
+      // this frame's word from each slice, 8 slices per round, fetched with weak no-allocate loads and
+      // re-fetched until every lap tag matches
+      float m = -3.0e38f, z = 0.f;
+      for (int s0 = 0; s0 < n_slices; s0 += 8) {
+        const int ns = min(8, n_slices - s0);
+        unsigned long long u[8];
+        for (int attempt = 0;; attempt++) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) u[i] = (i < ns) ? ld_na_u64(slot + (size_t)(s0 + i) * 32) : (tag << 63);
+          bool ready = true;
+#pragma unroll
+          for (int i = 0; i < 8; i++) ready = ready && ((u[i] >> 63) == tag);
+          if (__all_sync(0xFFFFFFFFu, ready) || (dbg & 1)) break;
+          if (PROF) pacc[4] += 1000;  // 1000 per repeated fetch
+          if (attempt > 2) __nanosleep(100);
+        }
+        float mn = m;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (i < ns) mn = fmaxf(mn, __uint_as_float((unsigned)u[i]));
+        float zb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (i < ns)
+            zb += __uint_as_float((unsigned)(u[i] >> 32) & 0x7FFFFFFFu) * ex2f(__uint_as_float((unsigned)u[i]) - mn);
+        z = z * ex2f(m - mn) + zb;
+        m = mn;
+      }
+      const float lse = m + lg2f(z);
+      lse_s[rs * kHF + ch * 32 + lane] = lse;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.lse_ready(rs));
+      LR_PT(3);
+      if (slice == 0) {
+        const long f = frame0 + (long)h * kHF + ch * 32 + lane;
+        if (lse_out) lse_out[f] = lse;
+        if (f < P && (!index || index[f] != kPadIndex)) llk_acc += (double)lse;
+      }
     }
-    if (slice == 0 && llk_sum && q < 2) {
+    if (slice == 0 && llk_sum) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) llk_acc += __shfl_xor_sync(0xFFFFFFFFu, llk_acc, o);
       if (lane == 0 && llk_acc != 0.0) atomicAdd(llk_sum, llk_acc * 0.69314718055994530942);
     }
-    if (PROF && lane == 0 && q == 0) {
-      for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)prof + team * 16 + i, (unsigned long long)pacc[i]);
-      if (team == 0) {
-        atomicAdd((unsigned long long *)prof + 10, (unsigned long long)pacc[16]);   // probe
-        atomicAdd((unsigned long long *)prof + 48 + 10, (unsigned long long)pacc[17]);  // batch loads
-        atomicAdd((unsigned long long *)prof + 48 + 11, (unsigned long long)pacc[18]);  // combine  // per-CTA: poll wait, everything else, waits on the tensor pipe (s_full + p_free)
-        long long tot = 0;
-        for (int i = 0; i < 16; i++) tot += pacc[i];
-        prof[64 + blockIdx.x * 4 + 0] = pacc[10];
-        prof[64 + blockIdx.x * 4 + 1] = tot - pacc[10];
-        prof[64 + blockIdx.x * 4 + 2] = pacc[1] + pacc[6];
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        prof[64 + blockIdx.x * 4 + 3] = smid;
-      }
-    }
+    if (lw == 0) LR_PDUMP(2);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 #undef LR_PT
+#undef LR_PDUMP
 
 }  // namespace
 
@@ -1763,10 +1759,10 @@ static lr_status tc_set_attrs() {
   LR_CUDA(cudaFuncSetAttribute(k_tc_lse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   LR_CUDA(cudaFuncSetAttribute(k_tc_acc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   LR_CUDA(cudaFuncSetAttribute(k_tc_acc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-  LR_CUDA(cudaFuncSetAttribute(k_tc_one<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-  LR_CUDA(cudaFuncSetAttribute(k_tc_one<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-  LR_CUDA(cudaFuncSetAttribute(k_tc_one<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-  LR_CUDA(cudaFuncSetAttribute(k_tc_one<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOneSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOneSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOneSmem));
+  LR_CUDA(cudaFuncSetAttribute(k_tc_one<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOneSmem));
   done = true;
   return LR_OK;
 }
@@ -1778,8 +1774,8 @@ static lr_status tc_launch_coop(void (*kern)(Args...), int grid, Args... args) {
   Engine &e = engine();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = kTcSmem;
+  cfg.blockDim = dim3(kOneThreads);
+  cfg.dynamicSmemBytes = kOneSmem;
   cfg.stream = e.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;
@@ -1900,9 +1896,9 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
     static const int kEnvDbg = getenv("LR_TC_DEBUG") ? atoi(getenv("LR_TC_DEBUG")) : 0;
     long long *d_prof = nullptr;
     if (kProf) {
-      d_prof = (long long *)scratch_get(kSlotLse, (64 + 4 * 160) * sizeof(long long));
+      d_prof = (long long *)scratch_get(kSlotLse, 96 * sizeof(long long));
       if (!d_prof) return LR_ERR_CUDA;
-      LR_CUDA(cudaMemsetAsync(d_prof, 0, (64 + 4 * 160) * sizeof(long long), e.stream));
+      LR_CUDA(cudaMemsetAsync(d_prof, 0, 96 * sizeof(long long), e.stream));
     }
     auto kern = out_S2 ? (kProf ? k_tc_one<true, true> : k_tc_one<true, false>)
                        : (kProf ? k_tc_one<false, true> : k_tc_one<false, false>);
@@ -1914,21 +1910,14 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
                           (const double *)g->d_s, fw, out_N, out_F, out_S2, e.tc_debug | kEnvDbg, d_prof);
     }
     if (rc == LR_OK && kProf) {
-      long long hp[64 + 4 * 160];
+      long long hp[96];
       LR_CUDA(cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, e.stream));
       LR_CUDA(cudaStreamSynchronize(e.stream));
-      {
-        const double ph = 2.0 / std::max(1, 2 * (n_tiles / groups));
-        for (int b = 0; b < n_slices * groups && b < 160; b++)
-          fprintf(stderr, "[tc_cta] cta %d slice %d group %d sm %lld: poll %.0f other %.0f tensor-wait %.0f\n", b,
-                  b % n_slices, b / n_slices, hp[64 + 4 * b + 3], hp[64 + 4 * b] * ph, hp[64 + 4 * b + 1] * ph,
-                  hp[64 + 4 * b + 2] * ph);
-      }
       const double per = 1.0 / ((double)n_slices * groups) / std::max(1, 2 * (n_tiles / groups));
-      static const char *role[4] = {"epi team0", "epi team1", "G1 issuer", "G2 issuer"};
-      for (int r = 0; r < 4; r++) {
-        fprintf(stderr, "[tc_prof] %s clk/half-tile:", role[r]);
-        for (int i = 0; i < 16; i++) fprintf(stderr, " %d:%.0f", i, hp[r * 16 + i] * per * (r < 2 ? 2.0 : 1.0));
+      static const char *role[5] = {"E1 parity0", "E1 parity1", "L (publish + lse)", "G1 issuer", "G2 issuer"};
+      for (int r = 0; r < 5; r++) {
+        fprintf(stderr, "[tc_prof] %s clk per %s:", role[r], r < 3 ? "iteration (2 half tiles)" : "half tile");
+        for (int i = 0; i < 8; i++) fprintf(stderr, " %d:%.0f", i, hp[r * 16 + i] * per * (r < 3 ? 2.0 : 1.0));
         fprintf(stderr, "\n");
       }
     }
