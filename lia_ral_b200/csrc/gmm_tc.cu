@@ -985,7 +985,7 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
 // ------------------------------------------------------------------ one-pass kernel
 // Likelihood GEMM, per-frame log-sum-exp and statistics GEMM in ONE sweep over the frames: the
 // per-frame normaliser is not precomputed by a first pass, it is exchanged between the slice-CTAs
-// of a frame group while the posteriors wait IN REGISTERS.
+// of a frame group while the posteriors wait in TMEM.
 //
 // Per CTA (slice of 128 components, one frame group) and half tile h (64 frames):
 //   G1(h) : S[c, t] = W A^T, ALL weights (hi and lo) resident in TMEM -> 24 TS UMMAs that read only
@@ -994,19 +994,20 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
 //           h & 1 take half tile h, 32 of its 64 frame columns each.  S is read with the 16x256b TMEM
 //           shape (a thread holds 4 component rows x 8 frame columns), so the per-frame max / sum over
 //           a warp's 32 components is 3 in-thread steps + a 3-step shuffle butterfly.  Posteriors are
-//           formed RELATIVE TO THE WARP'S MAXIMUM, fp16(2^14 2^(S - max_warp)), and stay in registers;
-//           the warp's (max, sum) go to a shared-memory ring.
-//   L(h)  : four warps (parity x column half), lane = frame: combine the four lane quarters' (max, sum)
-//           and post the slice's pair to the group's exchange ring in global memory as ONE 64-bit word
-//           whose top bit is the ring-lap tag (data = flag: no fence, no counter); then fetch the
-//           n_slices words of the frame with weak no-allocate loads (served by L2), repeated until every
-//           lap tag matches, combine -> lse
-//   E1'(h): the same E1 warps, one iteration (two half tiles) later: rescale the held posteriors by
-//           2^(max_warp - lse) (fp16 mantissa x exact power of two), store them to a TMEM slot
+//           formed RELATIVE TO THE WARP'S MAXIMUM, fp16(2^14 2^(S - max_warp)), and parked in a TMEM
+//           slot (holding them in registers over the exchange made the hot loop spill); the warp's
+//           (max, sum) go to a shared-memory ring.
+//   X(h)  : (warp 2) combines the four lane quarters' (max, sum) per frame and posts the slice's pair
+//           to the group's exchange ring in global memory as ONE 64-bit word whose top bit is the
+//           ring-lap tag (data = flag: no fence, no counter)
+//   L(h)  : four warps (parity x column half), lane = frame: fetch the n_slices words of the frame with
+//           weak no-allocate loads (served by L2), repeated until every lap tag matches, combine -> lse
+//   E1'(h): the same E1 warps, one iteration (two half tiles) later: read the parked posteriors back,
+//           rescale them by 2^(max_warp - lse) (fp16 mantissa x exact power of two), store them again
 //   G2(h) : F[c, :] += P[c, t] A[t, :] as TS UMMAs, the hi and the lo frame panels accumulated into
 //           the SAME columns (EM: [xh,1 | xh^2] = 128 columns, BW: [xh,1] = 64)           (warp 3)
-// TMEM: accumulator [0,128) | weights hi a, hi b, lo a, lo b [128,256) | S 3 x 64 [256,448) |
-//       posterior slots 2 x 32 [448,512).
+// TMEM: accumulator [0,128) | weights hi a, hi b, lo a, lo b [128,256) | S 2 x 64 [256,384) |
+//       posterior slots 4 x 32 [384,512).
 // Shared memory: six 32 KB half-tile stages (a stage lives from its bulk copy until G2 has read it,
 // about five half-tile periods); the weights pass through the last two stages on their way to TMEM.
 // No block-level barrier in the main loop: every hand-over is an mbarrier.  All CTAs of a group
@@ -1014,10 +1015,11 @@ k_tc_acc(int C, int D, int n_slices, int csize, const unsigned char *__restrict_
 // launched cooperatively with grid <= SM count.
 constexpr int kXRing = 16;    // exchange ring slots per group (see tc_run_stats)
 constexpr int kOStages = 6;   // half-tile stages
-constexpr int kNS = 3;        // S buffers
+constexpr int kNS = 2;        // S buffers
+constexpr int kNP = 4;        // posterior slots in TMEM
 constexpr int kNR = 4;        // depth of the (max, sum) and lse rings in shared memory
 constexpr int kOneThreads = 768;
-constexpr int kOColAcc = 0, kOColW = 128, kOColS = 256, kOColP = 448;
+constexpr int kOColAcc = 0, kOColW = 128, kOColS = 256, kOColP = 384;
 constexpr int kOStgOff = kOStages * kHalfBytes;        // flush staging: 16 warps x 512 B (32 x 4 floats)
 constexpr int kORingOff = kOStgOff + 16 * 512;         // lane-quarter (max, sum) ring: 2 x [kNR][4][64] floats
 constexpr int kOLseOff = kORingOff + 2 * kNR * 4 * 64 * 4;  // lse ring [kNR][64]
@@ -1035,15 +1037,15 @@ struct SmemOne {
   __device__ __forceinline__ uint32_t s_free(int i) const { return bar + 120 + 8 * i; }
   __device__ __forceinline__ uint32_t ms_written(int i) const { return bar + 144 + 8 * i; }
   __device__ __forceinline__ uint32_t lse_ready(int i) const { return bar + 176 + 8 * i; }
-  __device__ __forceinline__ uint32_t p_ready(int i) const { return bar + 240 + 8 * i; }
-  __device__ __forceinline__ uint32_t p_free(int i) const { return bar + 256 + 8 * i; }
+  __device__ __forceinline__ uint32_t p_ready(int i) const { return bar + 208 + 8 * i; }
+  __device__ __forceinline__ uint32_t p_free(int i) const { return bar + 240 + 8 * i; }
   __device__ __forceinline__ uint32_t f_full() const { return bar + 272; }
   __device__ __forceinline__ uint32_t f_empty() const { return bar + 280; }
   __device__ __forceinline__ uint32_t w_full() const { return bar + 288; }
   __device__ __forceinline__ uint32_t w_tmem() const { return bar + 296; }
   __device__ __forceinline__ uint32_t tmem_slot() const { return bar + 304; }
 };
-static_assert(kNS == 3 && kNR == 4 && kOStages == 6, "barrier block layout");
+static_assert(kNS <= 3 && kNR == 4 && kNP == 4 && kOStages == 6, "barrier block layout");
 
 __device__ __forceinline__ SmemOne carve_one(unsigned char *raw) {
   SmemOne s;
@@ -1067,6 +1069,12 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 // 16 lanes x 128 bits, N repeats: lanes (t / 4), (t / 4 + 8), column 4 j + (t % 4) in register 2 j + rs
+__device__ __forceinline__ void tmem_ld_16x128b_x4(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile(
       "tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
@@ -1176,7 +1184,7 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       mbar_init(sm.ms_written(i), 8);  // E1 warps: (max, sum) of the half tile are in the ring
       mbar_init(sm.lse_ready(i), 2);   // L warps: lse of the half tile is in shared memory
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kNP; i++) {
       mbar_init(sm.p_ready(i), 8);  // E1 warps: rescaled posteriors are in the TMEM slot
       mbar_init(sm.p_free(i), 1);   // G2 done with the slot
     }
@@ -1198,7 +1206,7 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
   unsigned long long *ring = xch + (size_t)group * kXRing * n_slices * kHF;
 
   if (warp < 4) {
-    reg_dealloc<24>();
+    reg_dealloc<40>();
     if (warp == 0) {
       // ---- bulk-copy producer
       const bool leader = elect_one();
@@ -1257,7 +1265,30 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       }
       LR_PDUMP(3);
     } else if (warp == 2) {
-      // (TMEM allocator: nothing to do in the main loop)
+      // ---- publisher: slice (max, sum) of every frame of the half tile -> exchange ring
+      for (int h = 0; h < n_half; h++) {
+        const int rs = h % kNR;
+        mbar_wait(sm.ms_written(rs), (h / kNR) & 1);
+        const float *pm = wmax + rs * 4 * kHF + 2 * lane, *pz = wsum + rs * 4 * kHF + 2 * lane;
+        const float2 m0 = *reinterpret_cast<const float2 *>(pm), m1 = *reinterpret_cast<const float2 *>(pm + kHF);
+        const float2 m2 = *reinterpret_cast<const float2 *>(pm + 2 * kHF), m3 = *reinterpret_cast<const float2 *>(pm + 3 * kHF);
+        const float2 z0 = *reinterpret_cast<const float2 *>(pz), z1 = *reinterpret_cast<const float2 *>(pz + kHF);
+        const float2 z2 = *reinterpret_cast<const float2 *>(pz + 2 * kHF), z3 = *reinterpret_cast<const float2 *>(pz + 3 * kHF);
+        const float ma = fmaxf(fmaxf(m0.x, m1.x), fmaxf(m2.x, m3.x));
+        const float mb = fmaxf(fmaxf(m0.y, m1.y), fmaxf(m2.y, m3.y));
+        const float za = ((z0.x * ex2f(m0.x - ma) + z1.x * ex2f(m1.x - ma)) +
+                          (z2.x * ex2f(m2.x - ma) + z3.x * ex2f(m3.x - ma))) * (1.f / 16384.f);
+        const float zb = ((z0.y * ex2f(m0.y - mb) + z1.y * ex2f(m1.y - mb)) +
+                          (z2.y * ex2f(m2.y - mb) + z3.y * ex2f(m3.y - mb))) * (1.f / 16384.f);
+        const unsigned tag = (((unsigned)h / kXRing) & 1u) ^ 1u;
+        const unsigned long long wa =
+            ((unsigned long long)(__float_as_uint(za) | (tag << 31)) << 32) | __float_as_uint(ma);
+        const unsigned long long wb =
+            ((unsigned long long)(__float_as_uint(zb) | (tag << 31)) << 32) | __float_as_uint(mb);
+        // frames 2 lane, 2 lane + 1 -> column half lane / 16, position (2 lane) % 32
+        st_relaxed_v2u64(ring + (((size_t)(h % kXRing) * 2 + (lane >> 4)) * n_slices + slice) * 32 + (2 * lane & 31),
+                         wa, wb);
+      }
     } else {
       // ---- statistics-GEMM issuer: F[c, :] (+)= P[c, t] A[t, :]; B = hi panels, then lo panels,
       // read MN-major (64-wide chunks = half panels, kHalfPanel apart)
@@ -1267,7 +1298,7 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       TileInfo ti = n_half > 0 ? tinfo[t_begin] : TileInfo{0, 0};
       TileInfo ti_next = ti;
       for (int h = 0; h < n_half; h++) {
-        const int st = h % kOStages, ps = h & 1;
+        const int st = h % kOStages, ps = h % kNP;
         if (!(h & 1)) {
           ti = ti_next;
           if (h + 2 < n_half) ti_next = tinfo[t_begin + (h >> 1) + 1];
@@ -1275,7 +1306,7 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
         const bool first = (ti.flags & 1) && !(h & 1), last = (ti.flags & 2) && (h & 1);
         mbar_wait(sm.full(st), (h / kOStages) & 1);
         LR_PT(1);
-        mbar_wait(sm.p_ready(ps), (h >> 1) & 1);
+        mbar_wait(sm.p_ready(ps), (h / kNP) & 1);
         LR_PT(2);
         if (first && n_flush > 0) mbar_wait(sm.f_empty(), (n_flush - 1) & 1);
         LR_PT(3);
@@ -1304,8 +1335,8 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
     }
   } else if (warp < 20) {
     // ---- E1: 16 warps = parity (2) x column half (2) x TMEM lane quarter q (4)
-    // 4 x 24 + 16 x 104 + 4 x 40 = 24 x 80: the CTA's register allocation is redistributed, not grown
-    reg_alloc<104>();
+    // 4 x 40 + 16 x 96 + 4 x 56 = 24 x 80: the CTA's register allocation is redistributed, not grown
+    reg_alloc<96>();
     const int q = warp & 3, ch = ((warp - 4) >> 2) & 1, par = (warp - 4) >> 3;
     const int t4 = 2 * par + ch;  // 0..3: the statistics columns 32 (t4 & 1).. of F (t4 < 2) or S2 in the flush
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -1337,11 +1368,10 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
     const int jo = (lane >> 3) & 3;  // the column group (of 8) whose warp results this lane ends up holding
     const int mycol = ch * 32 + 8 * jo + 2 * (lane & 3);  // first of the two frame columns this lane owns
     int n_flush = 0;
-    uint32_t pk0[8], pk1[8];   // posteriors of the HELD half tile (fp16 pairs), relative to the warp maximum
-    float mw0 = 0.f, mw1 = 0.f;  // warp maxima of the frames mycol, mycol + 1 of that half tile
+    float mw0 = 0.f, mw1 = 0.f;  // warp maxima of the frames mycol, mycol + 1 of the parked half tile
 
     // ---- second half of a half tile's life: rescale the held posteriors, store them, flush at run ends
-    auto finish = [&](int h, const TileInfo ti) {
+    auto finish = [&](int h, const TileInfo ti, float mw0, float mw1) {
       const int rs = h % kNR;
       LR_PT(4);
       mbar_wait(sm.lse_ready(rs), (h / kNR) & 1);
@@ -1363,6 +1393,11 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
         fm2 = *reinterpret_cast<uint32_t *>(&a);
         fp2 = *reinterpret_cast<uint32_t *>(&b);
       }
+      const int ps = h % kNP;
+      uint32_t pk0[8], pk1[8];
+      tmem_ld_16x128b_x4(tmem_base + lane_addr + kOColP + ps * 32 + ch * 16, pk0);
+      tmem_ld_16x128b_x4(tmem_base + lane_addr16 + kOColP + ps * 32 + ch * 16, pk1);
+      tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         // packed column 4 j + lane % 4 = frames 8 j + 2 (lane % 4), +1: factors held by the lane 8 j + lane % 4
@@ -1379,17 +1414,13 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
           pk1[2 * j + r2] = *reinterpret_cast<uint32_t *>(&y);
         }
       }
-      if (h >= 2) {
-        mbar_wait(sm.p_free(par), ((h >> 1) - 1) & 1);  // G2(h - 2) is done with the slot
-        tc_fence_after();
-      }
       LR_PT(6);
-      tmem_st_16x128b_x4(tmem_base + lane_addr + kOColP + par * 32 + ch * 16, pk0);
-      tmem_st_16x128b_x4(tmem_base + lane_addr16 + kOColP + par * 32 + ch * 16, pk1);
+      tmem_st_16x128b_x4(tmem_base + lane_addr + kOColP + ps * 32 + ch * 16, pk0);
+      tmem_st_16x128b_x4(tmem_base + lane_addr16 + kOColP + ps * 32 + ch * 16, pk1);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sm.p_ready(par));
+      if (lane == 0) mbar_arrive(sm.p_ready(ps));
       LR_PT(7);
       if (!(ti.flags & 2)) return;
       // ---- flush of the run that ends with this tile.  TMEM: lane = component, columns
@@ -1512,37 +1543,43 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.ms_written(rs));
-      // ---- pack the frame pairs (2 pc, 2 pc + 1) into the fp16 column pc = 4 j + t % 4
-      uint32_t n0[8], n1[8];
+      // ---- pack the frame pairs (2 pc, 2 pc + 1) into the fp16 column pc = 4 j + t % 4 and park them in
+      // the TMEM slot of the half tile
+      {
+        uint32_t n0[8], n1[8];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 4; j++) {
 #pragma unroll
-        for (int r2 = 0; r2 < 2; r2++) {
-          __half2 h0 = __floats2half2_rn(__uint_as_float(v0[4 * j + 2 * r2]), __uint_as_float(v0[4 * j + 2 * r2 + 1]));
-          __half2 h1 = __floats2half2_rn(__uint_as_float(v1[4 * j + 2 * r2]), __uint_as_float(v1[4 * j + 2 * r2 + 1]));
-          n0[2 * j + r2] = *reinterpret_cast<uint32_t *>(&h0);
-          n1[2 * j + r2] = *reinterpret_cast<uint32_t *>(&h1);
+          for (int r2 = 0; r2 < 2; r2++) {
+            __half2 h0 = __floats2half2_rn(__uint_as_float(v0[4 * j + 2 * r2]), __uint_as_float(v0[4 * j + 2 * r2 + 1]));
+            __half2 h1 = __floats2half2_rn(__uint_as_float(v1[4 * j + 2 * r2]), __uint_as_float(v1[4 * j + 2 * r2 + 1]));
+            n0[2 * j + r2] = *reinterpret_cast<uint32_t *>(&h0);
+            n1[2 * j + r2] = *reinterpret_cast<uint32_t *>(&h1);
+          }
         }
+        const int ps = h % kNP;
+        if (h >= kNP) {
+          mbar_wait(sm.p_free(ps), ((h / kNP) - 1) & 1);  // G2(h - kNP) is done with the slot
+          tc_fence_after();
+        }
+        tmem_st_16x128b_x4(tmem_base + lane_addr + kOColP + ps * 32 + ch * 16, n0);
+        tmem_st_16x128b_x4(tmem_base + lane_addr16 + kOColP + ps * 32 + ch * 16, n1);
       }
       LR_PT(3);
       // the previous half tile of this warp: its normaliser has had this whole iteration to arrive
-      if (prev >= 0) finish(prev, ti_prev);
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        pk0[i] = n0[i];
-        pk1[i] = n1[i];
-      }
+      if (prev >= 0) finish(prev, ti_prev, mw0, mw1);
+      tmem_wait_st();  // (the parked posteriors of h are in TMEM before the next iteration may read them back)
       mw0 = nw0;
       mw1 = nw1;
       prev = h;
       ti_prev = ti_h;
     }
-    if (prev >= 0) finish(prev, ti_prev);
+    tmem_wait_st();
+    if (prev >= 0) finish(prev, ti_prev, mw0, mw1);
     if (q == 0 && ch == 0) LR_PDUMP(par);
   } else {
-    // ---- L: four warps (parity x column half), lane = frame: publish the slice's (max, sum), then the
-    // log-sum-exp over all slices
-    reg_dealloc<40>();
+    // ---- L: four warps (parity x column half), lane = frame: log-sum-exp over all slices
+    reg_dealloc<56>();
     const int ch = (warp - 20) & 1, par = (warp - 20) >> 1;
     const int lw = warp - 20;
     double llk_acc = 0.0;
@@ -1552,40 +1589,30 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
       mbar_wait(sm.ms_written(rs), (h / kNR) & 1);  // the E1 warps' (max, sum) are in shared memory
       LR_PT(1);
       const unsigned long long tag = ((((unsigned)h / kXRing) & 1u) ^ 1u);
-      unsigned long long *slot = ring + ((size_t)(h % kXRing) * 2 + ch) * n_slices * 32 + lane;
-      {
-        const float *pm = wmax + rs * 4 * kHF + ch * 32 + lane, *pz = wsum + rs * 4 * kHF + ch * 32 + lane;
-        const float m0 = pm[0], m1 = pm[kHF], m2 = pm[2 * kHF], m3 = pm[3 * kHF];
-        const float ms = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        const float zs = ((pz[0] * ex2f(m0 - ms) + pz[kHF] * ex2f(m1 - ms)) +
-                          (pz[2 * kHF] * ex2f(m2 - ms) + pz[3 * kHF] * ex2f(m3 - ms))) * (1.f / 16384.f);
-        st_relaxed_u64(slot + (size_t)slice * 32,
-                       ((unsigned long long)(__float_as_uint(zs) | ((unsigned)tag << 31)) << 32) | __float_as_uint(ms));
-      }
-      LR_PT(2);
-      // this frame's word from each slice, 8 slices per round, fetched with weak no-allocate loads and
+      const unsigned long long *slot = ring + ((size_t)(h % kXRing) * 2 + ch) * n_slices * 32 + lane;
+      // this frame's word from each slice, 16 slices per round, fetched with weak no-allocate loads and
       // re-fetched until every lap tag matches
       float m = -3.0e38f, z = 0.f;
-      for (int s0 = 0; s0 < n_slices; s0 += 8) {
-        const int ns = min(8, n_slices - s0);
-        unsigned long long u[8];
+      for (int s0 = 0; s0 < n_slices; s0 += 16) {
+        const int ns = min(16, n_slices - s0);
+        unsigned long long u[16];
         for (int attempt = 0;; attempt++) {
 #pragma unroll
-          for (int i = 0; i < 8; i++) u[i] = (i < ns) ? ld_na_u64(slot + (size_t)(s0 + i) * 32) : (tag << 63);
+          for (int i = 0; i < 16; i++) u[i] = (i < ns) ? ld_na_u64(slot + (size_t)(s0 + i) * 32) : (tag << 63);
           bool ready = true;
 #pragma unroll
-          for (int i = 0; i < 8; i++) ready = ready && ((u[i] >> 63) == tag);
+          for (int i = 0; i < 16; i++) ready = ready && ((u[i] >> 63) == tag);
           if (__all_sync(0xFFFFFFFFu, ready) || (dbg & 1)) break;
           if (PROF) pacc[4] += 1000;  // 1000 per repeated fetch
           if (attempt > 2) __nanosleep(100);
         }
         float mn = m;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < 16; i++)
           if (i < ns) mn = fmaxf(mn, __uint_as_float((unsigned)u[i]));
         float zb = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < 16; i++)
           if (i < ns)
             zb += __uint_as_float((unsigned)(u[i] >> 32) & 0x7FFFFFFFu) * ex2f(__uint_as_float((unsigned)u[i]) - mn);
         z = z * ex2f(m - mn) + zb;
