@@ -510,6 +510,63 @@ void IvTestTrainPlda(Config &c) {
   plda.saveModel(c);
 }
 
+
+// scoring branch of IvTest for scoring = plda (IvTest.cpp:301-318, 392-410; PldaTools.cpp:4489-4519)
+void IvTestPldaScoring(Config &c) {
+  const std::string mpath = c.getString("matrixFilesPath", ""), mext = c.getString("loadMatrixFilesExtension", "");
+  const std::string mfmt = c.getString("loadMatrixFormat", "DB");
+  // trials, enrolment lists and vectors exactly as the other scorings load them (PldaTest::load,
+  // PldaTools.cpp:3437-3622), then the test-side normalisation every scoring mode goes through
+  // (IvTest.cpp:301-318: EFR / sphNorm, then LDA).  pldaNativeScoring itself never centres the data
+  // (PldaTools.cpp:4489-4519); PldaTest::center is only reached through sphericalNuisanceNormalization.
+  TestData test(c);
+  test.normalize(c);
+  const std::vector<std::string> &modelIds = test.modelIds, &segIds = test.segIds;
+  const std::vector<int32_t> &modelOf = test.modelOf;
+  const std::map<std::string, int> &modelIndex = test.modelIndex, &segIndex = test.segIndex;
+  const Matrix &models = test.models, &segments = test.segments;
+  const size_t d = models.rows;
+  const size_t nEnrol = test.enrolSessions.size(), nTest = segIds.size(), nModels = modelIds.size();
+  Matrix F, G, Sigma;
+  F.load(mpath + c.getString("pldaEigenVoiceMatrix", "pldaEigenVoiceMatrix") + mext, mfmt);
+  Sigma.load(mpath + c.getString("pldaSigmaMatrix", "pldaSigmaMatrix") + mext, mfmt);
+  const int rG = (int)c.getLong("pldaEigenChannelNumber", 0);
+  if (rG > 0) G.load(mpath + c.getString("pldaEigenChannelMatrix", "pldaEigenChannelMatrix") + mext, mfmt);
+  // the model lives in the space of the NORMALISED vectors (after LDA: ldaRank dimensions)
+  if (F.rows != d || Sigma.rows != d || Sigma.cols != d || (rG > 0 && G.rows != d))
+    LIA_THROW("IvTest: PLDA model dimension (F " + std::to_string(F.rows) + " x " + std::to_string(F.cols) +
+              ", Sigma " + std::to_string(Sigma.rows) + " x " + std::to_string(Sigma.cols) +
+              ") does not match the (normalised) i-vector size " + std::to_string(d));
+  Matrix scores(nModels, nTest);
+  if (c.getString("pldaScoring", "native") == "enrollMean") {
+    // PldaTest::pldaMeanScoring (PldaTools.cpp:4612-4709): each model is the MEAN of its enrolment
+    // i-vectors scored as one session -- K_two = (2 FTJF + I)^-1 is exactly the native K_{L+1} at
+    // L = 1, so this is the native scorer on one averaged column per model.
+    Matrix avg(d, nModels);
+    std::vector<double> cnt(nModels, 0.0);
+    std::vector<int32_t> one(nModels);
+    for (size_t j = 0; j < nEnrol; j++) {
+      cnt[modelOf[j]] += 1.0;
+      for (size_t i = 0; i < d; i++) avg(i, modelOf[j]) += models(i, j);
+    }
+    for (size_t m = 0; m < nModels; m++) {
+      one[m] = (int32_t)m;
+      for (size_t i = 0; i < d; i++) avg(i, m) /= cnt[m];
+    }
+    LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
+                                     Sigma.data.data(), avg.data.data(), nModels, one.data(), nModels,
+                                     segments.data.data(), nTest, scores.data.data()));
+  } else {
+    LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
+                                     Sigma.data.data(), models.data.data(), nEnrol, modelOf.data(), nModels,
+                                     segments.data.data(), nTest, scores.data.data()));
+  }
+  // output (IvTest.cpp:412-465): the trials listed in the NDX, segment-major in matrix order
+  (void)modelIndex;
+  (void)segIndex;
+  writeIvTestScores(c, scores, test.trials, modelIds, segIds);
+}
+
 // ------------------------------------------------------------------ IvNorm (IvNorm.cpp:72-128)
 int IvNorm(Config &c) {
   try {

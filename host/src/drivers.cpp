@@ -318,6 +318,7 @@ int TotalVariability(Config &c) {
 // ------------------------------------------------------------------ IvTest
 // cosine / mahalanobis / 2cov branches and PLDA training live in backend.cpp
 void IvTestTrainPlda(Config &c);
+void IvTestPldaScoring(Config &c);
 void IvTestNonPlda(Config &c, const std::string &scoring);
 
 int IvTest(Config &c) {
@@ -334,97 +335,7 @@ int IvTest(Config &c) {
     // the model is trained first unless pldaLoadModel is set (IvTest.cpp:255-298; this mirror
     // defaults to loading, the reference requires the parameter)
     if (!c.getBool("pldaLoadModel", true)) IvTestTrainPlda(c);
-    const std::string vpath = c.getParam("testVectorFilesPath") + "/", vext = c.getString("loadVectorFilesExtension", ".y");
-    const std::string mpath = c.getString("matrixFilesPath", ""), mext = c.getString("loadMatrixFilesExtension", "");
-    const std::string mfmt = c.getString("loadMatrixFormat", "DB");
-    // trials: "segment model1 model2 ..." ; enrolment: "model session1 session2 ..." (PldaTools.cpp:3437-3560)
-    XList trials(c.getParam("ndxFilename"));
-    std::vector<std::string> modelIds, enrolSessions, segIds;
-    std::vector<int32_t> modelOf;
-    std::map<std::string, int> modelIndex;
-    if (c.existsParam("targetIdList") && !c.getParam("targetIdList").empty()) {
-      XList enrol(c.getParam("targetIdList"));
-      auto lines = enrol.lines();
-      std::stable_sort(lines.begin(), lines.end(),
-                       [](const std::vector<std::string> &a, const std::vector<std::string> &b) { return a.size() > b.size(); });
-      for (auto &l : lines) {
-        if (!modelIndex.count(l[0])) {
-          modelIndex[l[0]] = (int)modelIds.size();
-          modelIds.push_back(l[0]);
-        }
-        for (size_t e = 1; e < l.size(); e++) {
-          enrolSessions.push_back(l[e]);
-          modelOf.push_back(modelIndex[l[0]]);
-        }
-      }
-    }
-    std::map<std::string, int> segIndex;
-    for (auto &l : trials.lines()) {
-      if (!segIndex.count(l[0])) {
-        segIndex[l[0]] = (int)segIds.size();
-        segIds.push_back(l[0]);
-      }
-      for (size_t e = 1; e < l.size(); e++)
-        if (!modelIndex.count(l[e])) {  // a model without enrolment list is its own single session
-          modelIndex[l[e]] = (int)modelIds.size();
-          modelIds.push_back(l[e]);
-          enrolSessions.push_back(l[e]);
-          modelOf.push_back(modelIndex[l[e]]);
-        }
-    }
-    auto loadVec = [&](const std::string &name) {
-      Matrix v;
-      v.load(vpath + name + vext, mfmt);
-      return v;
-    };
-    const size_t d = loadVec(enrolSessions[0]).cols;
-    const size_t nEnrol = enrolSessions.size(), nTest = segIds.size(), nModels = modelIds.size();
-    // mean subtraction with pldaMeanVec (PldaTest::center)
-    Matrix mean;
-    mean.load(mpath + c.getString("pldaMeanVec", "pldaMeanVec") + mext, mfmt);
-    Matrix models(d, nEnrol), segments(d, nTest);
-    for (size_t j = 0; j < nEnrol; j++) {
-      Matrix v = loadVec(enrolSessions[j]);
-      for (size_t i = 0; i < d; i++) models(i, j) = v.data[i] - mean.data[i];
-    }
-    for (size_t j = 0; j < nTest; j++) {
-      Matrix v = loadVec(segIds[j]);
-      for (size_t i = 0; i < d; i++) segments(i, j) = v.data[i] - mean.data[i];
-    }
-    Matrix F, G, Sigma;
-    F.load(mpath + c.getString("pldaEigenVoiceMatrix", "pldaEigenVoiceMatrix") + mext, mfmt);
-    Sigma.load(mpath + c.getString("pldaSigmaMatrix", "pldaSigmaMatrix") + mext, mfmt);
-    const int rG = (int)c.getLong("pldaEigenChannelNumber", 0);
-    if (rG > 0) G.load(mpath + c.getString("pldaEigenChannelMatrix", "pldaEigenChannelMatrix") + mext, mfmt);
-    Matrix scores(nModels, nTest);
-    if (c.getString("pldaScoring", "native") == "enrollMean") {
-      // PldaTest::pldaMeanScoring (PldaTools.cpp:4612-4709): each model is the MEAN of its enrolment
-      // i-vectors scored as one session -- K_two = (2 FTJF + I)^-1 is exactly the native K_{L+1} at
-      // L = 1, so this is the native scorer on one averaged column per model.
-      Matrix avg(d, nModels);
-      std::vector<double> cnt(nModels, 0.0);
-      std::vector<int32_t> one(nModels);
-      for (size_t j = 0; j < nEnrol; j++) {
-        cnt[modelOf[j]] += 1.0;
-        for (size_t i = 0; i < d; i++) avg(i, modelOf[j]) += models(i, j);
-      }
-      for (size_t m = 0; m < nModels; m++) {
-        one[m] = (int32_t)m;
-        for (size_t i = 0; i < d; i++) avg(i, m) /= cnt[m];
-      }
-      LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
-                                       Sigma.data.data(), avg.data.data(), nModels, one.data(), nModels,
-                                       segments.data.data(), nTest, scores.data.data()));
-    } else {
-      LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
-                                       Sigma.data.data(), models.data.data(), nEnrol, modelOf.data(), nModels,
-                                       segments.data.data(), nTest, scores.data.data()));
-    }
-    // output (IvTest.cpp:412-465): the trials listed in the NDX, segment-major in matrix order
-    std::vector<uint8_t> mask(nModels * nTest, 0);
-    for (auto &l : trials.lines())
-      for (size_t e = 1; e < l.size(); e++) mask[(size_t)modelIndex[l[e]] * nTest + segIndex[l[0]]] = 1;
-    writeIvTestScores(c, scores, mask, modelIds, segIds);
+    IvTestPldaScoring(c);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }

@@ -57,13 +57,11 @@ void lr_reset_launch_count(void);
  * kind 0 = log-likelihood pass, 1 = statistics pass.  lr_profile_read synchronises. */
 lr_status lr_profile(int enable);
 lr_status lr_profile_read(int kind, double *total_ms, uint64_t *n_launches);
-/* Kernel selection for the frames x components pass: 0 = auto, 1 = fp32 SIMT, 2 = tcgen05. */
+/* Kernel selection for the frames x components pass: 0 = auto, 1 = fp32 SIMT, 2 = tcgen05 (one-pass
+ * likelihood + statistics kernel, two-pass for likelihoods only), 3 = tcgen05 with the two-pass
+ * statistics kernels of round 1 (kept as the cross-check of the one-pass kernel). */
 lr_status lr_set_gmm_kernel(int which);
 int lr_get_gmm_kernel(void);
-/* Profiling experiments only: disables parts of the tcgen05 statistics kernel (bit 0: no exp2,
- * bit 1: no flush, bit 2: short statistics GEMM, bit 3: short likelihood GEMM).  Results are
- * WRONG while any bit is set; never set by the product path. */
-void lr_debug_flags(int flags);
 
 /* ------------------------------------------------------------------ GMM (MixtureGD) ------
  * Replaces MixtureGD + DistribGD::computeAll (alize-core; constants probed on
@@ -101,7 +99,9 @@ typedef struct {
 /* ---- a4/a5: accumulateStatEM (AccumulateStat.cpp:103-140, threaded :170-299) over
  * MixtureGDStat::computeAndAccumulateEM.  occ[C] += g, m1[C*D] += g x, m2[C*D] += g x^2
  * (g = frame_weight * posterior), *sum_log_lk += sum_t log(sum_c w_c lk_c(x_t)),
- * *n_frames += frame_weight * #frames.  segs == NULL -> all T frames. */
+ * *n_frames += frame_weight * #frames.  The log-likelihood sum is NOT weighted: it is the reference's
+ * llkAcc (AccumulateStat.cpp:104-107 adds log(computeAndAccumulateEM(f)) per frame), n_frames its
+ * getEMFeatureCount().  segs == NULL -> all T frames. */
 lr_status lr_gmm_em_accumulate(lr_gmm *g, const float *X, size_t T, size_t ldx,
                                const lr_seg *segs, size_t n_segs, double frame_weight,
                                double *occ, double *m1, double *m2, double *sum_log_lk,
@@ -114,7 +114,9 @@ size_t lr_gmm_em_stats_len(const lr_gmm *g); /* C + 2*C*D + 2 */
 /* MixtureGDStat::getEM + varianceControl (TrainTools.cpp:567-587,1076-1077) on the device:
  * w = occ/sum occ, mean = m1/occ, cov = m2/occ - mean^2, then clamp cov to
  * [flooring*cov_signal, ceiling*cov_signal] (floor first), then computeAll.  d_cov_signal may
- * be NULL (no variance control).  Runs without a host sync; g is updated in place. */
+ * be NULL (no variance control).  g is updated in place on the device; the call ends with ONE 4-byte
+ * readback (the fp16 range guard of the tensor-core operands), i.e. it waits for the M-step kernels.
+ * Weights are left unchanged when the total occupation is not positive. */
 lr_status lr_gmm_em_update_dev(lr_gmm *g, const double *d_stats, double flooring, double ceiling,
                                const double *d_cov_signal);
 /* host convenience: getEM + varianceControl from host statistics */

@@ -201,6 +201,9 @@ lr_status lr_set_gmm_kernel(int which) {
   return LR_OK;
 }
 int lr_get_gmm_kernel(void) { return engine().gmm_kernel; }
+#ifdef LR_DEBUG_BUILD
+// profiling experiments (results are WRONG while set): only in `make DEBUG=1` builds, not part of the product ABI
 void lr_debug_flags(int flags) { engine().tc_debug = flags; }
+#endif
 
 }  // extern "C"

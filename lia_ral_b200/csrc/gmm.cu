@@ -85,7 +85,7 @@ __global__ void k_em_update(int C, int D, const double *__restrict__ occ,
   if (idx >= C * D) return;
   int c = idx / D, i = idx - c * D;
   double o = occ[c];
-  if (i == 0) w[c] = o / *tot;
+  if (i == 0 && *tot > 0.0) w[c] = o / *tot;  // (no frame selected at all: the weights stay)
   double cv = cov[idx];
   if (o > 0.0) {  // components with no occupation keep their parameters
     double mu = m1[idx] / o;

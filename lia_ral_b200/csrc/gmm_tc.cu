@@ -1919,8 +1919,13 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
     k_tc_convert<<<(unsigned)((P_pad * 8 + 255) / 256), 256, 0, e.stream>>>(
         g->D, fl.dX, fl.ldx, fl.d_index, fl.P, P_pad, g->d_gf, g->d_rsf, Xh1);
     LR_CHECK_LAUNCH();
+#ifdef LR_DEBUG_BUILD  // phase profiler / experiment switches: `make DEBUG=1` builds only
     static const bool kProf = getenv("LR_TC_PROF") != nullptr;
     static const int kEnvDbg = getenv("LR_TC_DEBUG") ? atoi(getenv("LR_TC_DEBUG")) : 0;
+#else
+    constexpr bool kProf = false;
+    constexpr int kEnvDbg = 0;
+#endif
     long long *d_prof = nullptr;
     if (kProf) {
       d_prof = (long long *)scratch_get(kSlotLse, 96 * sizeof(long long));

@@ -577,7 +577,11 @@ lr_tv *lr_tv_create(int C, int D, int R, size_t U, const double *ubm_mean,
   tv->U = U;
   tv->sv = (size_t)C * D;
   size_t rr = (size_t)R * R;
-  tv->batch = (int)std::min<size_t>(U, std::max<size_t>(32, ((size_t)1 << 29) / (rr * sizeof(double))));
+  // utterances per posterior batch: 512 MB for the largest of the per-utterance buffers (L / E / Y
+  // hold R x R doubles, invD ceil(R / 64) 64 x 64 blocks -- the larger one at small R), capped at
+  // 4096 so that small ranks with many utterances do not over-allocate
+  const size_t per_utt = std::max(rr, (size_t)((R + kNB - 1) / kNB) * kNB * kNB) * sizeof(double);
+  tv->batch = (int)std::min<size_t>(std::min<size_t>(U, 4096), std::max<size_t>(32, ((size_t)1 << 29) / per_utt));
   const int nbmax = tv->batch;
   auto A = [&](double **p, size_t n) { return cudaMalloc(p, n * sizeof(double)) == cudaSuccess; };
   bool ok = A(&tv->d_N, U * C) && A(&tv->d_F, U * tv->sv) && A(&tv->d_T, R * tv->sv) &&
@@ -595,7 +599,11 @@ lr_tv *lr_tv_create(int C, int D, int R, size_t U, const double *ubm_mean,
             cudaMalloc(&tv->d_ptr_Tc, C * sizeof(double *)) == cudaSuccess &&
             cudaMalloc(&tv->d_info, (std::max(nbmax, C) + 1) * sizeof(int)) == cudaSuccess;
   if (!ok) {
-    fail(LR_ERR_CUDA, "lr_tv_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const double gb = ((double)U * C + 2.0 * U * tv->sv / 2 + 2.0 * R * tv->sv + (double)U * R + (double)C * rr +
+                       (double)C * tv->Rp() + (double)tv->acc_len() + 3.0 * nbmax * rr +
+                       (double)nbmax * ((R + kNB - 1) / kNB) * kNB * kNB) * sizeof(double) / 1e9;
+    fail(LR_ERR_CUDA, "lr_tv_create: cudaMalloc failed (%s) while allocating about %.1f GB for C=%d D=%d R=%d U=%zu, "
+                      "batch %d", cudaGetErrorString(cudaGetLastError()), gb, C, D, R, U, nbmax);
     tv_free(tv);
     return nullptr;
   }

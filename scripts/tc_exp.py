@@ -15,7 +15,7 @@ stats = torch.zeros(g.em_stats_len(), dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
 flag_sets = [int(a) for a in sys.argv[1:]] or [0, 32, 2, 8, 15, 15 | 32]
 for flags in flag_sets:
-    capi.lib().lr_debug_flags(flags)
+    capi.lib().lr_debug_flags(flags)  # needs a `make DEBUG=1` build
     for rep in range(2):
         capi.profile(True)
         g.em_accumulate_dev(feats, 0, T, 1.0, stats.data_ptr())

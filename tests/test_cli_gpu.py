@@ -232,15 +232,17 @@ def test_ivextractor_approximate_modes_cli(world, oracle):
 
 
 def test_ivtest_plda_cli(world, oracle):
+    """scoring = plda without ivNorm: pldaNativeScoring never centres the vectors (PldaTools.cpp:4489-4519;
+    PldaTest::center is only reached through sphericalNuisanceNormalization), so pldaMeanVec is not applied."""
     d = world["dir"]
     F, G, Sigma, models, model_of, segments = synth.make_plda(d=20, rF=6, rG=3, sessions=[2, 2, 1, 1], n_test=7, seed=95)
     os.makedirs(d / "vec", exist_ok=True)
     mean = np.linspace(-0.5, 0.5, 20)
     names_e = [f"e{j}" for j in range(models.shape[1])]
     for j, n in enumerate(names_e):
-        lf.write_db(d / "vec" / f"{n}.y", (models[:, j] + mean)[None])
+        lf.write_db(d / "vec" / f"{n}.y", models[:, j][None])
     for j in range(segments.shape[1]):
-        lf.write_db(d / "vec" / f"t{j}.y", (segments[:, j] + mean)[None])
+        lf.write_db(d / "vec" / f"t{j}.y", segments[:, j][None])
     lf.write_db(d / "pF.mat", F)
     lf.write_db(d / "pG.mat", G)
     lf.write_db(d / "pS.mat", Sigma)
@@ -329,6 +331,31 @@ def test_ivtest_backend_and_ivnorm_cli(world, oracle):
                  scoring="mahalanobis", outputFilename=str(d / "bk_load.res"))
     _run("IvTest", d / "bk_load.cfg")
     assert open(d / "bk_load.res").read() == open(d / "bk_mahalanobis.res").read()
+    # scoring = plda on top of the same normalisation (IvTest.cpp:301-318 runs before EVERY scoring mode):
+    # the PLDA model lives in the EFR + LDA space (ldaRank = 8 dimensions)
+    Fp, Gp, Sp, _, _, _ = synth.make_plda(d=8, rF=3, rG=2, sessions=[1], n_test=1, seed=99)
+    lf.write_db(d / "npF.mat", Fp)
+    lf.write_db(d / "npG.mat", Gp)
+    lf.write_db(d / "npS.mat", Sp)
+    lf.write_cfg(d / "bk_plda.cfg", **dict(base, ivNormLoadParam="true"), scoring="plda", pldaLoadModel="true",
+                 pldaEigenVoiceNumber=3, pldaEigenChannelNumber=2, iVectSize=dim, pldaEigenVoiceMatrix="npF",
+                 pldaEigenChannelMatrix="npG", pldaSigmaMatrix="npS", outputFilename=str(d / "bk_plda.res"))
+    _run("IvTest", d / "bk_plda.cfg")
+    ref = oracle.plda_native_scoring(Fp, Gp, Sp, m2, np.arange(4, dtype=np.int32), s2)
+    lines = [l.split() for l in open(d / "bk_plda.res")]
+    assert len(lines) == sum(len(t) - 1 for t in trials)
+    for l in lines:
+        m, sg = int(l[1][2:]), int(l[3][2:])
+        assert abs(float(l[4]) - ref[m, sg]) < 1e-5 * max(1.0, np.abs(ref).max()), ("plda", l)
+    # a model whose dimension is not that of the normalised vectors is refused, not read out of bounds
+    lf.write_db(d / "npFbad.mat", np.zeros((dim, 3)))
+    lf.write_cfg(d / "bk_plda_bad.cfg", **dict(base, ivNormLoadParam="true"), scoring="plda", pldaLoadModel="true",
+                 pldaEigenVoiceNumber=3, pldaEigenChannelNumber=0, iVectSize=dim, pldaEigenVoiceMatrix="npFbad",
+                 pldaSigmaMatrix="npS", outputFilename=str(d / "bk_plda_bad.res"))
+    bad = subprocess.run([os.path.join(BIN, "IvTest"), "--config", str(d / "bk_plda_bad.cfg")], capture_output=True,
+                         text=True, timeout=600)
+    assert "does not match" in bad.stdout
+    assert not os.path.exists(d / "bk_plda_bad.res") or not open(d / "bk_plda_bad.res").read().strip()
     # IvNorm: normalise a plain list of vectors with the saved parameters
     lf.write_lines(d / "bvlist.lst", [[f"bt{j}"] for j in range(6)])
     os.makedirs(d / "bnorm", exist_ok=True)
