@@ -10,6 +10,14 @@ Outputs (small, committed):
                        top-20 confusion matrix (the .ref was produced with topDistribsCount 20).
     wld_validate.npz   LIA_SpkDet/TrainWorld/test/wld.validate (XML GMM 10x32): weight/cst/det/
                        covInv/mean as printed -> computeAll identity KAT.
+    traintarget.npz    LIA_SpkDet/TrainTarget/test/{wld,test1.prm,test1.lbl,test1.validate.gmm}: RAW world GMM
+                       (128x32), the 32 label-selected frames, and the means of the reference's adapted
+                       model.  The .validate.gmm is DAMAGED (68743 bytes, one byte of component 65's record is
+                       missing): components 0..64 are read in place, 66..127 one byte earlier (their covInv
+                       blocks then equal the world's bit for bit, which is how the cut was located), component
+                       65 is dropped.  An INDICATIVE pin of the posterior / EM / MAPOccDep semantics: one
+                       MAP iteration (MAPRegFactorMean 10) from the world model reproduces these means to
+                       1e-3 absolute (the fixture's values sit on a 1.8e-4 grid).
 Only DATA is converted; no reference source is copied.
 """
 import math
@@ -101,6 +109,37 @@ def wld_validate():
     print("wld_validate:", C, D, w.sum())
 
 
+def traintarget():
+    d = os.path.join(REF, "LIA_SpkDet/TrainTarget/test")
+    w, cst, det, ci, mu = read_raw_gmm(os.path.join(d, "wld"))
+    raw = open(os.path.join(d, "test1.validate.gmm"), "rb").read()
+    C, D = struct.unpack("<II", raw[:8])
+    rec, off0 = 17 + 16 * D, 8 + 8 * C
+    assert len(raw) == off0 + C * rec - 1          # the damaged fixture: one byte short
+    mean_ref = np.full((C, D), np.nan)
+    ok = np.ones(C, dtype=bool)
+    for c in range(C):
+        if c == 65:
+            ok[c] = False
+            continue
+        o = off0 + c * rec - (0 if c < 65 else 1)
+        assert np.array_equal(np.frombuffer(raw, "<f8", D, o + 17), ci[c])   # only the means are adapted
+        mean_ref[c] = np.frombuffer(raw, "<f8", D, o + 17 + 8 * D)
+    prm = open(os.path.join(d, "test1.prm"), "rb").read()
+    hdr = struct.unpack("<4I", prm[:16])
+    x = np.frombuffer(prm, "<f4", -1, 16).reshape(hdr[2], -1)[:, parse_mask("0-15,17-32")].copy()
+    sel = []
+    for line in open(os.path.join(d, "test1.lbl")):
+        b, e, lab = line.split()
+        if lab == "speech":
+            sel += list(range(time_to_frame(float(b), 0.01), time_to_frame(float(e), 0.01) + 1))
+    np.savez_compressed(os.path.join(HERE, "traintarget.npz"), w=w, cst=cst, covinv=ci, mean=mu, frames=x,
+                        selected=np.array(sel, dtype=np.int64), mean_ref=mean_ref, ok=ok,
+                        map_reg_factor_mean=np.float64(10.0))
+    print("traintarget:", x.shape, len(sel), int(ok.sum()), np.nanmax(np.abs(mean_ref - mu)))
+
+
 if __name__ == "__main__":
     gmmtokenizer()
     wld_validate()
+    traintarget()

@@ -384,3 +384,61 @@ def test_block_boundaries(capi):
     # block cuts regroup them, so agreement is ~3e-6, not 1e-9 (contract: 1e-4)
     assert np.allclose(s[:256], occ, rtol=2e-5, atol=1e-5)
     assert np.allclose(s[256:256 + 256 * 20], m1.ravel(), rtol=2e-5, atol=2e-5 * np.abs(m1).max())
+
+
+def test_traintarget_validate_gmm_on_gpu(capi, golden_dir):
+    """The reference's TrainTarget fixture (indicative pin, see tests/test_oracle_golden.py) through the CUDA
+    EM-statistics path: occupancies -> MAPOccDep means vs the reference's adapted model."""
+    from oracle import np_oracle
+    z = np.load(os.path.join(golden_dir, "traintarget.npz"))
+    cov = 1.0 / z["covinv"]
+    g = capi.GMM(z["w"], z["mean"], cov)
+    X = np.ascontiguousarray(z["frames"][z["selected"]], dtype=np.float32)
+    _, n, occ, m1, m2 = g.em_accumulate(X)
+    w_ml = occ / occ.sum()
+    m_ml = np.where(occ[:, None] > 0, m1 / np.maximum(occ, 1e-300)[:, None], z["mean"])
+    _, mean, _ = np_oracle.map_occ_dep(z["w"], z["mean"], cov, w_ml, m_ml, cov, n,
+                                       r_mean=float(z["map_reg_factor_mean"]))
+    ok = z["ok"]
+    assert n == 32 and np.abs(mean - z["mean_ref"])[ok].max() < 1.2e-3
+
+
+@pytest.mark.parametrize("kname", ["tc", "tc2p"])
+def test_full_size_oracle_parity(capi, oracle, kname):
+    """BASELINE's own shape (2048c / 60d) against the fp64 oracle on 200 k frames in 50 utterances of 4000
+    frames (the oracle runs threaded: seconds).  Beyond the max-norm bound of the small cases:
+      * per (utterance, component) RELATIVE checks wherever the occupation is >= 1: 1e-4 for occ >= 100 and
+        the 3-sigma bound of the fp16 posterior rounding, 1.2e-3 / sqrt(occ), below that;
+      * the contract itself: i-vectors (rank 40) computed from the GPU statistics vs from the oracle's agree
+        to 1e-4 of the largest coefficient."""
+    capi.set_gmm_kernel(KERNELS[kname])
+    try:
+        C, D, U, per = 2048, 60, 50, 4000
+        w, mean, cov = synth.make_ubm(C, D, seed=1)
+        X = synth.make_frames(w, mean, cov, U * per, seed=21)
+        w2, m2, c2 = synth.perturb_ubm(w, mean, cov * 2.0, seed=22, frac=0.5, scale=0.5)
+        g, o = capi.GMM(w2, m2, c2), oracle.gmm(w2, m2, c2)
+        f2r = (np.arange(U * per) // per).astype(np.int32)
+        N_ref, F_ref = oracle.bwstats(o, X, f2r, U, threads=os.cpu_count() or 1)
+        N, F = g.bwstats(X, [(u * per, per, u) for u in range(U)], U)
+    finally:
+        capi.set_gmm_kernel(0)
+    assert np.abs(N.sum(1) - per).max() < 1e-5 * per
+    rel = np.abs(N - N_ref) / np.maximum(N_ref, 1e-300)
+    big = N_ref >= 100.0
+    mid = (N_ref >= 1.0) & ~big
+    assert big.sum() > 100 and mid.sum() > 1000
+    assert rel[big].max() < 1e-4, rel[big].max()
+    assert (rel[mid] * np.sqrt(N_ref[mid])).max() < 1.2e-3, (rel[mid] * np.sqrt(N_ref[mid])).max()
+    F3, F3r = F.reshape(U, C, D), F_ref.reshape(U, C, D)
+    relF = np.linalg.norm(F3 - F3r, axis=2) / np.maximum(np.linalg.norm(F3r, axis=2), 1e-300)
+    assert relF[big].max() < 1e-4, relF[big].max()
+    assert (relF[mid] * np.sqrt(N_ref[mid])).max() < 1.2e-3
+    # i-vectors from both sets of statistics
+    R = 40
+    invvar = (1.0 / c2).reshape(-1)
+    Tm = synth.make_T(R, C, D, invvar, seed=23, scale=0.05)
+    tett = oracle.tv_tett(Tm, invvar, C, D, threads=os.cpu_count() or 1)
+    W_ref = oracle.tv_ivectors(N_ref, oracle.tv_subtract_m(N_ref, F_ref, m2.reshape(-1)), Tm, invvar, tett)
+    W_gpu = oracle.tv_ivectors(N, oracle.tv_subtract_m(N, F, m2.reshape(-1)), Tm, invvar, tett)
+    assert np.abs(W_gpu - W_ref).max() < 1e-4 * np.abs(W_ref).max(), np.abs(W_gpu - W_ref).max() / np.abs(W_ref).max()

@@ -67,3 +67,28 @@ def test_numpy_twin_agrees_on_fixture(oracle, golden_dir):
     llk = oracle.llk_all(g, X)
     _, llk_np = np_oracle.posteriors(z["w"], z["mean"], cov, X)
     assert np.allclose(llk, llk_np, rtol=1e-12, atol=1e-10)
+
+
+def test_traintarget_validate_gmm_indicative(oracle, golden_dir):
+    """LIA_SpkDet/TrainTarget/test/test1.validate.gmm (damaged fixture: 127 of 128 components recovered, see
+    make_golden.py): one MAPOccDep iteration (MAPRegFactorMean 10, means only; TrainTools.cpp:445-489) from
+    the world model over the 32 label-selected frames reproduces the reference's adapted means.  INDICATIVE pin
+    of computeAndAccumulateEM / getEM / computeMAPOccDep: the fixture's values sit on a 1.8e-4 grid, so the bound
+    is 1e-3 absolute (2.5e-3 of the largest mean shift) and 2e-4 on the implied adaptation factors."""
+    z = np.load(os.path.join(golden_dir, "traintarget.npz"))
+    cov = 1.0 / z["covinv"]
+    g = oracle.gmm(z["w"], z["mean"], cov)
+    X = np.ascontiguousarray(z["frames"][z["selected"]], dtype=np.float32)
+    assert X.shape == (32, 32)
+    _, n, occ, m1, m2 = oracle.em_accumulate(g, X)
+    w_ml, m_ml, c_ml = oracle.em_get(g, occ, m1, m2)
+    _, mean, _ = np_oracle.map_occ_dep(z["w"], z["mean"], cov, w_ml, m_ml, c_ml, n,
+                                       r_mean=float(z["map_reg_factor_mean"]))
+    ok = z["ok"]
+    assert np.abs(mean - z["mean_ref"])[ok].max() < 1.2e-3
+    assert np.abs(z["mean_ref"] - z["mean"])[ok].max() > 2.0      # the adaptation moved the means by up to 2.5
+    # the adaptation factor occ / (occ + r) the reference applied, recovered from its output
+    dm = m_ml - z["mean"]
+    alpha = ((z["mean_ref"] - z["mean"]) * dm).sum(1) / np.maximum((dm * dm).sum(1), 1e-300)
+    sel = ok & (occ > 0.05)
+    assert np.abs(alpha - occ / (occ + 10.0))[sel].max() < 2e-4
