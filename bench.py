@@ -151,6 +151,144 @@ def ivector_rate(torch, capi, dev, U=1024, R=400, reps=3):
             "workload": "estimateW on resident BW statistics, 2048c/60d, R=400 (configs[2] per-GPU slice)"}
 
 
+def _max_over_ranks(torch, dist, world, dev, seconds):
+    t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def tv_em_block(torch, dist, capi, lrd, dev, rank, world, U=6250, R=600, iters=2):
+    """configs[3]: TotalVariability T-matrix EM at 2048c/60d, rank 600 -- 50 k utterances over 8 GPUs =
+    6250 utterances per GPU (weak scaling: the same per-GPU share at every N).  One iteration =
+    substractM + estimateTETt + estimateAandC on the rank's utterances, then the exchange: reduce-scatter
+    of A by component + all-reduce of [Cmx | R | r | sumW], updateTestimate on C / world components,
+    all-gather of the new T columns (one all-reduce + replicated M-step at N = 1), minDivergence.
+    Statistics are synthesised on the device (64 active components per utterance, 3000 frames,
+    F = N mu + noise) and restored (device copy, untimed) before every iteration, as the reference
+    re-reads F_X from disk (TotalVariability.cpp:149-153)."""
+    from lia_ral_b200 import synth
+    w, mean, cov = synth.make_ubm(C, D, seed=1)
+    invvar = (1.0 / cov).reshape(-1)
+    tv = capi.TV(C, D, R, U, mean.reshape(-1), invvar)
+    Nd = lrd._device_tensor(tv.dev_N(), U * C).view(U, C)
+    Fd = lrd._device_tensor(tv.dev_F(), U * C * D).view(U, C * D)
+    g = torch.Generator(device=dev)
+    g.manual_seed(50 + rank)
+    mu = torch.tensor(mean.reshape(-1), device=dev)
+    sd = torch.tensor(np.sqrt(cov).reshape(-1), device=dev)
+    for u0 in range(0, U, 256):
+        n = min(256, U - u0)
+        occ = torch.zeros((n, C), device=dev, dtype=torch.float64)
+        act = torch.randint(0, C, (n, 64), device=dev, generator=g)
+        occ.scatter_add_(1, act, torch.rand((n, 64), device=dev, generator=g, dtype=torch.float64))
+        occ *= 3000.0 / occ.sum(1, keepdim=True)
+        Nd[u0:u0 + n] = occ
+        rep = occ.repeat_interleave(D, dim=1)
+        Fd[u0:u0 + n] = rep * mu + torch.sqrt(rep) * sd * torch.randn((n, C * D), device=dev, generator=g,
+                                                                      dtype=torch.float64)
+        del rep, occ
+    F_raw = Fd.clone()
+    tv.set_T(synth.make_T(R, C, D, invvar, seed=4, scale=0.02))
+    torch.cuda.synchronize()
+    times, parts = [], []
+    for it in range(iters + 1):          # first iteration = warm-up (cuBLAS / cuSOLVER module loads)
+        Fd.copy_(F_raw)
+        tv.reset_tmp_acc()
+        capi.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tv.subtract_m()
+        tv.estimate_tett()
+        tv.estimate_a_and_c()
+        capi.synchronize()
+        t1 = time.perf_counter()
+        lrd.tv_sharded_mstep(tv, U)        # world == 1: plain finish_estep + updateTestimate
+        capi.synchronize()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        tv.min_divergence(float(U * world))
+        capi.synchronize()
+        t3 = time.perf_counter()
+        if it > 0:
+            times.append(t3 - t0)
+            parts.append((t1 - t0, t2 - t1, t3 - t2))
+    dt = _max_over_ranks(torch, dist, world, dev, float(np.mean(times)))
+    p = np.mean(np.array(parts), axis=0)
+    flop = U * world * (2 * C * R * (R + 1) + 4 * R * C * D + R ** 3)     # SURVEY.md §8d per utterance
+    out = {"value": U * world / dt, "unit": "utterances/s", "n_gpus": world, "utterances_per_gpu": U, "rank": R,
+           "iterations_timed": iters, "seconds_per_iteration": dt, "estep_s": float(p[0]),
+           "exchange_mstep_s": float(p[1]), "mindiv_s": float(p[2]),
+           "estep_algorithmic_tflops_per_gpu": flop / world / max(float(p[0]), 1e-9) / 1e12, "scaling": "weak",
+           "exchange": ("reduce-scatter A by component (%.2f GB fp64) + all-reduce [Cmx|R|r|sumW] + M-step on C/N "
+                        "components + all-gather T" % (C * tv.acc_a_stride() * 8 / 1e9)) if world > 1 and C % world == 0
+           else "none (one GPU): finish_estep + updateTestimate",
+           "timing": "host clock around device-synchronised iterations, max over ranks",
+           "workload": "TotalVariability EM iteration, 2048c/60d, R=600, configs[3] per-GPU share (50k utterances / 8)"}
+    del F_raw, Nd, Fd
+    tv.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def ivector_pipeline_block(torch, dist, capi, lrd, dev, rank, world, U=1250, frames_per_utt=3000, R=400):
+    """configs[2] sharded by NDX line (AccumulateTVStat.cpp:498-507): every rank takes 10 k / 8 = 1250
+    utterances x 3000 frames, frames -> Baum-Welch statistics (device resident) -> substractM -> TETt ->
+    estimateW, then the i-vectors are gathered (all_gather of [U x R])."""
+    from lia_ral_b200 import synth
+    w, mean, cov = synth.make_ubm(C, D, seed=1)
+    invvar = (1.0 / cov).reshape(-1)
+    T = U * frames_per_utt
+    X = make_frames_gpu(torch, w, mean, cov, T, seed=7 + 1000 * rank, device=dev)
+    feats = capi.Feats(device_ptr=X.data_ptr(), T=T, ldx=D, D=D)
+    g = capi.GMM(w, mean, cov)
+    tv = capi.TV(C, D, R, U, mean.reshape(-1), invvar)
+    tv.set_T(synth.make_T(R, C, D, invvar, seed=4, scale=0.02))
+    Nd = lrd._device_tensor(tv.dev_N(), U * C)
+    Fd = lrd._device_tensor(tv.dev_F(), U * C * D)
+    segs = [(u * frames_per_utt, frames_per_utt, u) for u in range(U)]
+    gathered = None
+    times = []
+    for it in range(2):                   # first pass = warm-up
+        Nd.zero_()
+        Fd.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g.bwstats_dev(feats, segs, U, tv.dev_N(), tv.dev_F())
+        capi.synchronize()
+        t1 = time.perf_counter()
+        tv.subtract_m()
+        tv.estimate_tett()
+        tv.estimate_w()
+        Wl = torch.from_numpy(tv.get_W()).to(dev)
+        if world > 1:
+            gathered = torch.empty((world * U, R), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, Wl)
+        else:
+            gathered = Wl
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        times = [t2 - t0, t1 - t0, t2 - t1]
+    dt = _max_over_ranks(torch, dist, world, dev, times[0])
+    out = {"value": U * world / dt, "unit": "i-vectors/s", "n_gpus": world, "utterances_per_gpu": U,
+           "frames_per_utterance": frames_per_utt, "rank": R, "seconds": dt, "bwstats_s": times[1],
+           "solve_and_gather_s": times[2], "frames_per_s": U * world * frames_per_utt / dt, "scaling": "weak",
+           "finite": bool(torch.isfinite(gathered).all().item()),
+           "workload": "IvExtractor: frames -> BW statistics -> i-vector solve, gather W; configs[2] per-GPU share "
+                       "(10k utterances / 8)"}
+    del X, Nd, Fd, gathered
+    tv.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+
 def synth_model():
     from lia_ral_b200 import synth
     w, mean, cov = synth.make_ubm(C, D, seed=1)
@@ -241,6 +379,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-ivectors", action="store_true", help="skip the i-vectors/s side measurement")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the strong-scaling line, the sharded IvExtractor pipeline and the TotalVariability EM block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -280,13 +420,16 @@ def main():
     floor_, ceil_ = 0.5, 10.0   # floors 0.5 -> 0.5, ceilings 10 -> 10
     ev_stats = torch.cuda.Event()
 
-    def step():
+    def step_frames(n_frames):
         with torch.cuda.stream(lr_stream):
             stats.zero_()
-        g.em_accumulate_dev(feats, 0, T, 1.0, stats.data_ptr())
+        g.em_accumulate_dev(feats, 0, n_frames, 1.0, stats.data_ptr())
         # one all-reduce of {occ, m1, m2, llk, n} per iteration (emAcc.addAccEM analogue)
         lrd.allreduce_stats(stats, lr_stream)
         g.em_update_dev(stats.data_ptr(), floor_, ceil_, cov_signal.data_ptr())
+
+    def step():
+        step_frames(T)
 
     def sync_all():
         capi.synchronize()
@@ -358,11 +501,32 @@ def main():
     e2e_val = world * Te * args.e2e_steps / float(te.item())
     stat_bytes = nstat * 8
 
-    # ---- i-vectors/s (second half of BASELINE.json's metric), every rank on its own utterances
+    # ---- strong scaling of the same EM step: 10 M frames IN TOTAL, split over the ranks
+    strong = None
+    if not args.no_extra and feats is not None:
+        Ts = args.frames // world
+        for _ in range(3):
+            step_frames(Ts)
+        sync_all()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(lr_stream):
+            s0.record()
+        for _ in range(5):
+            step_frames(Ts)
+        with torch.cuda.stream(lr_stream):
+            s1.record()
+        sync_all()
+        tms = _max_over_ranks(torch, dist, world, dev, s0.elapsed_time(s1) / 5.0)
+        strong = {"value": Ts * world / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms, "frames_total": Ts * world,
+                  "n_gpus": world, "scaling": "strong",
+                  "workload": "the same EM iteration with configs[1]'s 10 M frames in total, frames / N per GPU"}
+    # ---- side measurements (each rank on its own shard): i-vectors/s, the sharded IvExtractor pipeline,
+    # TotalVariability EM
     iv = None
+    extra = {}
+    del X, feats
+    torch.cuda.empty_cache()
     if not args.no_ivectors:
-        del X, feats
-        torch.cuda.empty_cache()
         try:
             iv = ivector_rate(torch, capi, dev)
             tiv = torch.tensor([iv["value"]], dtype=torch.float64, device=dev)
@@ -374,6 +538,13 @@ def main():
             iv = {"value": None, "error": str(exc)[:200]}
             if world > 1:
                 dist.all_reduce(torch.zeros(1, dtype=torch.float64, device=dev))
+    if not args.no_extra:
+        for name, fn in (("ivector_pipeline", ivector_pipeline_block), ("tv_em", tv_em_block)):
+            try:
+                extra[name] = fn(torch, dist, capi, lrd, dev, rank, world)
+            except Exception as exc:
+                extra[name] = {"value": None, "error": str(exc)[:300]}
+                torch.cuda.empty_cache()
 
     if rank == 0:
         pk = peaks()
@@ -435,6 +606,9 @@ def main():
         }
         if iv is not None:
             out["ivectors"] = iv
+        if strong is not None:
+            out["strong_scaling"] = strong
+        out.update(extra)
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"], _, _ = cpu_baseline()
         sys.stdout.flush()

@@ -403,6 +403,9 @@ def test_traintarget_validate_gmm_on_gpu(capi, golden_dir):
     assert n == 32 and np.abs(mean - z["mean_ref"])[ok].max() < 1.2e-3
 
 
+_FULL_REF = {}
+
+
 @pytest.mark.parametrize("kname", ["tc", "tc2p"])
 def test_full_size_oracle_parity(capi, oracle, kname):
     """BASELINE's own shape (2048c / 60d) against the fp64 oracle on 200 k frames in 50 utterances of 4000
@@ -419,7 +422,9 @@ def test_full_size_oracle_parity(capi, oracle, kname):
         w2, m2, c2 = synth.perturb_ubm(w, mean, cov * 2.0, seed=22, frac=0.5, scale=0.5)
         g, o = capi.GMM(w2, m2, c2), oracle.gmm(w2, m2, c2)
         f2r = (np.arange(U * per) // per).astype(np.int32)
-        N_ref, F_ref = oracle.bwstats(o, X, f2r, U, threads=os.cpu_count() or 1)
+        if "bw" not in _FULL_REF:      # the oracle pass (about 10 s) is shared by the two kernels
+            _FULL_REF["bw"] = oracle.bwstats(o, X, f2r, U, threads=os.cpu_count() or 1)
+        N_ref, F_ref = _FULL_REF["bw"]
         N, F = g.bwstats(X, [(u * per, per, u) for u in range(U)], U)
     finally:
         capi.set_gmm_kernel(0)
