@@ -408,18 +408,21 @@ _FULL_REF = {}
 
 @pytest.mark.parametrize("kname", ["tc", "tc2p"])
 def test_full_size_oracle_parity(capi, oracle, kname):
-    """BASELINE's own shape (2048c / 60d) against the fp64 oracle on 200 k frames in 50 utterances of 4000
-    frames (the oracle runs threaded: seconds).  Beyond the max-norm bound of the small cases:
+    """BASELINE's own shape (2048c / 60d) against the fp64 oracle on 200 k frames in 10 utterances of 20 000
+    frames (the oracle runs threaded: seconds).  The model is deliberately BLURRED (means shrunk towards the
+    global mean, variances x 5): with the generator's own model every posterior is one-hot in 60 dimensions
+    and fp16 posteriors are exact -- here a frame spreads over ~100 components (perplexity ~ 40), the case
+    that exercises the fp16 posterior rounding.  Beyond the max-norm bound of the small cases:
       * per (utterance, component) RELATIVE checks wherever the occupation is >= 1: 1e-4 for occ >= 100 and
         the 3-sigma bound of the fp16 posterior rounding, 1.2e-3 / sqrt(occ), below that;
       * the contract itself: i-vectors (rank 40) computed from the GPU statistics vs from the oracle's agree
         to 1e-4 of the largest coefficient."""
     capi.set_gmm_kernel(KERNELS[kname])
     try:
-        C, D, U, per = 2048, 60, 50, 4000
+        C, D, U, per = 2048, 60, 10, 20000
         w, mean, cov = synth.make_ubm(C, D, seed=1)
         X = synth.make_frames(w, mean, cov, U * per, seed=21)
-        w2, m2, c2 = synth.perturb_ubm(w, mean, cov * 2.0, seed=22, frac=0.5, scale=0.5)
+        w2, m2, c2 = w, mean * 0.15, cov * 5.0
         g, o = capi.GMM(w2, m2, c2), oracle.gmm(w2, m2, c2)
         f2r = (np.arange(U * per) // per).astype(np.int32)
         if "bw" not in _FULL_REF:      # the oracle pass (about 10 s) is shared by the two kernels
@@ -428,11 +431,11 @@ def test_full_size_oracle_parity(capi, oracle, kname):
         N, F = g.bwstats(X, [(u * per, per, u) for u in range(U)], U)
     finally:
         capi.set_gmm_kernel(0)
-    assert np.abs(N.sum(1) - per).max() < 1e-5 * per
+    assert np.abs(N.sum(1) - per).max() < 1e-4 * per
     rel = np.abs(N - N_ref) / np.maximum(N_ref, 1e-300)
     big = N_ref >= 100.0
     mid = (N_ref >= 1.0) & ~big
-    assert big.sum() > 100 and mid.sum() > 1000
+    assert big.sum() > 50 and mid.sum() > 10000
     assert rel[big].max() < 1e-4, rel[big].max()
     assert (rel[mid] * np.sqrt(N_ref[mid])).max() < 1.2e-3, (rel[mid] * np.sqrt(N_ref[mid])).max()
     F3, F3r = F.reshape(U, C, D), F_ref.reshape(U, C, D)
