@@ -237,6 +237,16 @@ lr_status lr_plda_native_scoring(int d, int rF, int rG, const double *F, const d
                                  const double *Sigma, const double *models, size_t n_enrol,
                                  const int32_t *model_of, size_t n_models,
                                  const double *segments, size_t n_test, double *scores);
+/* The same scoring for trial matrices that do not fit / should not travel through host memory (1 M x 10 k
+ * at configs[4]): d_models / d_segments are DEVICE pointers ([d x n] row-major as above), d_scores a
+ * device fp32 [n_models x n_test] block with leading dimension ld_scores.  A rank scores its own shard of
+ * the models (PldaTools.cpp:4302-4412 splits the models over threads the same way); no collective.
+ * The trial matrix is computed in fp16 hi/lo split precision (22 bits) with fp32 accumulation: scores
+ * agree with the fp64 loops to ~1e-6 of the largest score.  rF <= 256. */
+lr_status lr_plda_native_scoring_dev(int d, int rF, int rG, const double *F, const double *G,
+                                     const double *Sigma, const double *d_models, size_t n_enrol,
+                                     const int32_t *model_of, size_t n_models, const double *d_segments,
+                                     size_t n_test, float *d_scores, size_t ld_scores);
 
 /* ------------------------------------------------------------------ i-vector back-end -----
  * Development-set statistics / normalisations of PldaDev and the non-PLDA scorings of PldaTest

@@ -497,6 +497,24 @@ def plda_native_scoring(F, G, Sigma, models, model_of, segments):
     return scores
 
 
+def plda_native_scoring_dev(F, G, Sigma, d_models_ptr, n_enrol, model_of, d_segments_ptr, n_test, d_scores_ptr,
+                            ld_scores=None):
+    """device-resident variant: models [d x n_enrol] / segments [d x n_test] fp64 and the fp32 score block
+    [n_models x ld_scores] live in device memory (pointers as integers)."""
+    F, Sigma = _f64(F), _f64(Sigma)
+    d, rF = F.shape
+    rG = 0 if G is None else G.shape[1]
+    Gp = _d(_f64(G)) if rG else None
+    model_of = np.ascontiguousarray(model_of, dtype=np.int32)
+    n_models = len(np.unique(model_of))
+    _check(lib().lr_plda_native_scoring_dev(d, rF, rG, _d(F), Gp, _d(Sigma), ct.c_void_p(d_models_ptr),
+                                            ct.c_size_t(n_enrol), model_of.ctypes.data_as(c_ip),
+                                            ct.c_size_t(n_models), ct.c_void_p(d_segments_ptr),
+                                            ct.c_size_t(n_test), ct.c_void_p(d_scores_ptr),
+                                            ct.c_size_t(ld_scores or n_test)))
+    return n_models
+
+
 # ---- i-vector back-end (PldaDev statistics / normalisation, non-PLDA scorings) ----------------
 def _cls(class_of):
     return np.ascontiguousarray(class_of, dtype=np.int32)

@@ -22,6 +22,7 @@ struct Engine {
   cudaStream_t stream = nullptr;   // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging for the host-buffer entry points
   cublasHandle_t blas = nullptr;
+  void *solver = nullptr;          // cusolverDnHandle_t, created on first use (plda.cu / ivbackend.cu)
   uint64_t launches = 0;
   int gmm_kernel = 0;  // 0 auto, 1 simt, 2 tcgen05 (one-pass statistics), 3 tcgen05 two-pass
   int tc_debug = 0;    // profiling experiments only (LR_TC_DEBUG builds): results are WRONG when set
@@ -92,7 +93,17 @@ inline void count_launch(int n = 1) { engine().launches += (uint64_t)n; }
     if (!lr::ensure_ready()) return LR_ERR_CUDA;                                           \
   } while (0)
 
-// RAII device buffer (typed), freed on scope exit; used for per-call scratch.
+// Per-call device scratch comes from a small caching pool (engine.cu): cudaMalloc / cudaFree cost
+// 0.1-1 ms each and cudaFree synchronises the device, which dominated calls such as PLDA scoring
+// (~25 buffers per call).  Blocks go back to the pool on release and to the driver at lr_shutdown
+// (or when the pool holds more than 8 GB).  Everything the library enqueues runs on the engine's
+// streams and every entry point that uses the copy stream joins it before returning, so reuse of a
+// released block is stream-ordered.
+cudaError_t pool_alloc(void **p, size_t bytes);
+void pool_free(void *p);
+void pool_release_all();
+
+// RAII device buffer (typed), returned to the pool on scope exit; used for per-call scratch.
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -105,10 +116,10 @@ struct DevBuf {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc(&p, count * sizeof(T));
+    return pool_alloc(reinterpret_cast<void **>(&p), count * sizeof(T));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p);
     p = nullptr;
     n = 0;
   }

@@ -1,6 +1,11 @@
 // engine.cu -- process-wide engine state: device binding, streams, cuBLAS handle, errors.
 #include "common.cuh"
 
+#include <cusolverDn.h>
+
+#include <map>
+#include <unordered_map>
+
 namespace lr {
 
 static thread_local std::string g_error;
@@ -93,6 +98,68 @@ bool ensure_ready() {
 
 using namespace lr;
 
+// ---- caching pool behind DevBuf
+namespace lr {
+namespace {
+struct Pool {
+  std::multimap<size_t, void *> free_blocks;
+  std::unordered_map<void *, size_t> live;
+  size_t pooled_bytes = 0;
+};
+Pool &pool() {
+  static Pool p;
+  return p;
+}
+constexpr size_t kPoolCap = (size_t)8 << 30;
+}  // namespace
+
+cudaError_t pool_alloc(void **p, size_t bytes) {
+  Pool &pl = pool();
+  const size_t want = bytes <= (1u << 20) ? (bytes + 255) / 256 * 256 : (bytes + (1u << 20) - 1) >> 20 << 20;
+  auto it = pl.free_blocks.lower_bound(want);
+  if (it != pl.free_blocks.end() && it->first <= 2 * want + (1u << 20)) {
+    *p = it->second;
+    pl.live[*p] = it->first;
+    pl.pooled_bytes -= it->first;
+    pl.free_blocks.erase(it);
+    return cudaSuccess;
+  }
+  cudaError_t err = cudaMalloc(p, want);
+  if (err != cudaSuccess) {  // give the pooled blocks back to the driver and try once more
+    cudaGetLastError();
+    pool_release_all();
+    err = cudaMalloc(p, want);
+  }
+  if (err == cudaSuccess) pl.live[*p] = want;
+  return err;
+}
+
+void pool_free(void *p) {
+  Pool &pl = pool();
+  auto it = pl.live.find(p);
+  if (it == pl.live.end()) {
+    cudaFree(p);
+    return;
+  }
+  const size_t sz = it->second;
+  pl.live.erase(it);
+  if (pl.pooled_bytes + sz > kPoolCap) {
+    cudaFree(p);
+    return;
+  }
+  pl.free_blocks.emplace(sz, p);
+  pl.pooled_bytes += sz;
+}
+
+void pool_release_all() {
+  Pool &pl = pool();
+  for (auto &kv : pl.free_blocks) cudaFree(kv.second);
+  pl.free_blocks.clear();
+  pl.pooled_bytes = 0;
+}
+}  // namespace lr
+
+
 extern "C" {
 
 const char *lr_last_error(void) { return g_error.c_str(); }
@@ -136,6 +203,7 @@ lr_status lr_shutdown(void) {
   profile_clear();
   e.profile = false;
   for (bool &b : e.attr_set) b = false;
+  pool_release_all();
   for (int i = 0; i < Engine::kScratchSlots; i++) {
     if (e.scratch[i]) cudaFree(e.scratch[i]);
     e.scratch[i] = nullptr;
@@ -146,6 +214,8 @@ lr_status lr_shutdown(void) {
     if (e.ev_consumed[i]) cudaEventDestroy(e.ev_consumed[i]);
     e.ev_copied[i] = e.ev_consumed[i] = nullptr;
   }
+  if (e.solver) cusolverDnDestroy((cusolverDnHandle_t)e.solver);
+  e.solver = nullptr;
   if (e.blas) cublasDestroy(e.blas);
   if (e.stream) cudaStreamDestroy(e.stream);
   if (e.copy_stream) cudaStreamDestroy(e.copy_stream);

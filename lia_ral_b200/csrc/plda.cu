@@ -7,13 +7,16 @@
 //   score(m, t) = t^T K' m  +  1/2 t^T (K' - K_1) t  +  1/2 m^T (K' - K_L) m  +  const_L
 // with K' = K_{L+1}, so the trial matrix is ONE GEMM  [Nt x r] [r x Nm]  plus a rank-1 style
 // epilogue; per-L quantities are recomputed only when the session count changes, like the
-// reference (:4221-4250).  All fp64.
+// reference (:4221-4250).  The small r x r / d x d algebra is fp64 (cuBLAS / cuSOLVER); the trial
+// matrix itself -- the 2 Nm Nt r flop and the Nm Nt output write that dominate -- is the repo's own
+// tcgen05 split-precision kernel (gemm_split.cu) with the row / column terms fused into its epilogue.
 #include <cusolverDn.h>
 
 #include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
+#include "gemm_split.cuh"
 
 #define LR_CUSOLVER(expr)                                                                  \
   do {                                                                                     \
@@ -71,38 +74,35 @@ __global__ void k_half_quad(int r, long n, const double *__restrict__ V,
 
 // model m = sum of its enrolment columns (pldaScoring :4205-4218); pm column-major [r x n_enrol]
 __global__ void k_model_sums(int r, const double *__restrict__ pm, const long *__restrict__ first,
-                             const int *__restrict__ count, long n_models,
+                             long first_offset, const int *__restrict__ count, long n_models,
                              double *__restrict__ M) {
   long m = blockIdx.x;
   if (m >= n_models) return;
   for (int i = threadIdx.x; i < r; i += blockDim.x) {
     double s = 0.0;
-    for (int k = 0; k < count[m]; k++) s += pm[(size_t)(first[m] + k) * r + i];
+    for (int k = 0; k < count[m]; k++) s += pm[(size_t)(first[m] - first_offset + k) * r + i];
     M[(size_t)m * r + i] = s;
   }
 }
 
-// S[t, m] += a[t] + b[m] + cst   (S column-major [n_test x n_m])
-__global__ void k_score_epilogue(long n_test, long n_m, const double *__restrict__ a,
-                                 const double *__restrict__ b, double cst, double *__restrict__ S) {
-  size_t total = (size_t)n_test * n_m;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (size_t)gridDim.x * blockDim.x) {
-    size_t m = e / n_test, t = e - m * n_test;
-    S[e] += a[t] + b[m] + cst;
-  }
+__global__ void k_add_const(long n, double c, double *__restrict__ v) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] += c;
 }
 
 struct Dense {
-  cusolverDnHandle_t solver = nullptr;
+  cusolverDnHandle_t solver = nullptr;  // the engine's handle (created once: ~10 ms)
   DevBuf<double> work;
   DevBuf<int> info;
-  ~Dense() {
-    if (solver) cusolverDnDestroy(solver);
-  }
   lr_status init() {
-    LR_CUSOLVER(cusolverDnCreate(&solver));
-    LR_CUSOLVER(cusolverDnSetStream(solver, engine().stream));
+    Engine &e = engine();
+    if (!e.solver) {
+      cusolverDnHandle_t h = nullptr;
+      LR_CUSOLVER(cusolverDnCreate(&h));
+      LR_CUSOLVER(cusolverDnSetStream(h, e.stream));
+      e.solver = h;
+    }
+    solver = (cusolverDnHandle_t)e.solver;
     LR_CUDA(info.alloc(1));
     return LR_OK;
   }
@@ -156,16 +156,21 @@ lr_status gemm_rm(bool ta, bool tb, int m, int n, int k, const double *A, int ld
 
 using namespace lr;
 
-extern "C" lr_status lr_plda_native_scoring(int d, int rF, int rG, const double *F, const double *G,
-                                            const double *Sigma, const double *models,
-                                            size_t n_enrol, const int32_t *model_of,
-                                            size_t n_models, const double *segments, size_t n_test,
-                                            double *scores) {
+// models / segments: [d x n] row-major (the reference's _models / _segments), in host memory
+// (dev_in = false) or device memory (dev_in = true).  Output: scores_host (fp64, host, [n_models x
+// n_test]) or d_scores_f32 (fp32, device, leading dimension ld_scores) -- exactly one is non-null.
+static lr_status plda_score_impl(int d, int rF, int rG, const double *F, const double *G,
+                                 const double *Sigma, const double *models, bool dev_in, size_t n_enrol,
+                                 const int32_t *model_of, size_t n_models, const double *segments,
+                                 size_t n_test, double *scores_host, float *d_scores_f32,
+                                 size_t ld_scores) {
   LR_READY();
   LR_REQUIRE(d > 0 && rF > 0 && rF <= d && rG >= 0 && F && Sigma && models && model_of &&
-                 segments && scores && n_enrol > 0 && n_models > 0 && n_test > 0,
+                 segments && (scores_host || d_scores_f32) && n_enrol > 0 && n_models > 0 && n_test > 0,
              "lr_plda_native_scoring: bad arguments");
   LR_REQUIRE(rG == 0 || G, "lr_plda_native_scoring: G is null but rG = %d", rG);
+  LR_REQUIRE(rF <= 256, "lr_plda_native_scoring: rank %d above the 256 the scoring kernel holds in TMEM", rF);
+  const cudaMemcpyKind in_kind = dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   Engine &e = engine();
   const int r = rF;
   // model -> (first enrolment column, count); consecutive columns of a model are adjacent
@@ -230,7 +235,7 @@ extern "C" lr_status lr_plda_native_scoring(int d, int rF, int rG, const double 
   {
     DevBuf<double> dSeg;
     LR_CUDA(dSeg.alloc((size_t)d * n_test));
-    LR_CUDA(cudaMemcpyAsync(dSeg.p, segments, (size_t)d * n_test * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+    LR_CUDA(cudaMemcpyAsync(dSeg.p, segments, (size_t)d * n_test * sizeof(double), in_kind, e.stream));
     // Ps[n_test x r] = segments^T[n_test x d] FTJ^T[d x r]
     if ((st = gemm_rm(true, true, (int)n_test, r, d, dSeg.p, (int)n_test, dFTJ.p, d, dPs.p, r)) != LR_OK) return st;
     LR_CUDA(cudaStreamSynchronize(e.stream));
@@ -244,21 +249,63 @@ extern "C" lr_status lr_plda_native_scoring(int d, int rF, int rG, const double 
   LR_CUDA(cudaStreamSynchronize(e.stream));
   const double alpha1 = -h_ld[0];  // dScal held log det (Phi + I)
 
-  // ---- pldaScoring (:4186-4271), models in blocks so the score tile fits in HBM
-  const size_t mblk = std::max<size_t>(1, std::min<size_t>(n_models, ((size_t)1 << 28) / n_test));
+  // ---- pldaScoring (:4186-4271).  Segment operand of the trial GEMM (fp16 hi / lo panels) once;
+  // models in blocks: u = M K' is the model operand, row term b[m] + const, column term a[t].
+  DevBuf<unsigned char> dBp, dAp;
+  DevBuf<double> dRow, dOut[2];
+  double scaleB = 1.0, scaleA = 1.0;
+  LR_CUDA(dBp.alloc(gemm_split_panel_bytes((long)n_test, r)));
+  if ((st = gemm_split_prepare(dPs.p, r, (long)n_test, r, dBp.p, dScal.p + 3, &scaleB)) != LR_OK) return st;
+  // host output: two device score blocks of <= 1 GB alternate with their D2H copies; device output: the
+  // block only bounds the temporaries
+  const size_t mblk = scores_host ? std::max<size_t>(128, std::min<size_t>((n_models + 127) / 128 * 128,
+                                                                          (((size_t)1 << 27) / n_test + 127) / 128 * 128))
+                                  : std::min<size_t>((n_models + 127) / 128 * 128, 32768);
   LR_CUDA(dM.alloc(mblk * r));
   LR_CUDA(dTmp.alloc(std::max(mblk, n_test) * r));
   LR_CUDA(dA.alloc(n_test));
   LR_CUDA(dB.alloc(mblk));
-  LR_CUDA(dS.alloc(mblk * n_test));
+  LR_CUDA(dAp.alloc(gemm_split_panel_bytes((long)mblk, r)));
+  if (scores_host) {
+    LR_CUDA(dOut[0].alloc(mblk * n_test));
+    LR_CUDA(dOut[1].alloc(mblk * n_test));
+  }
   LR_CUDA(dFirst.alloc(n_models));
   LR_CUDA(dCount.alloc(n_models));
   LR_CUDA(cudaMemcpyAsync(dFirst.p, first.data(), n_models * sizeof(long), cudaMemcpyHostToDevice, e.stream));
   LR_CUDA(cudaMemcpyAsync(dCount.p, count.data(), n_models * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-  DevBuf<double> dEnr;
+  DevBuf<double> dEnr, dDiff;
+  LR_CUDA(dDiff.alloc((size_t)r * r));
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  struct EvGuard {
+    cudaEvent_t *a, *b;
+    ~EvGuard() {
+      for (int i = 0; i < 2; i++) {
+        if (a[i]) cudaEventDestroy(a[i]);
+        if (b[i]) cudaEventDestroy(b[i]);
+      }
+    }
+  } guard{ev_done, ev_copied};
+  if (scores_host)
+    for (int i = 0; i < 2; i++) {
+      LR_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+      LR_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+    }
   size_t m0 = 0;
-  int cur_nb = -1;
+  int cur_nb = -1, blk = 0;
   double constant = 0.0;
+  size_t pend_m0 = 0, pend_nm = 0;
+  int pend_buf = -1;
+  // the D2H copy of a finished block runs on the copy stream while the next block is computed
+  auto drain = [&]() -> lr_status {
+    if (pend_buf < 0) return LR_OK;
+    LR_CUDA(cudaStreamWaitEvent(e.copy_stream, ev_done[pend_buf], 0));
+    LR_CUDA(cudaMemcpyAsync(scores_host + pend_m0 * n_test, dOut[pend_buf].p, pend_nm * n_test * sizeof(double),
+                            cudaMemcpyDeviceToHost, e.copy_stream));
+    LR_CUDA(cudaEventRecord(ev_copied[pend_buf], e.copy_stream));
+    pend_buf = -1;
+    return LR_OK;
+  };
   while (m0 < n_models) {
     // a run of models with the same session count, capped at the block size
     size_t m1 = m0;
@@ -279,60 +326,90 @@ extern "C" lr_status lr_plda_native_scoring(int d, int rF, int rG, const double 
       constant = ((-h_ld[2]) - (-h_ld[1]) - alpha1) / 2.0;
       // a[t] = 1/2 t^T (K' - K_1) t : Tmp = Ps (K' - K_1)
       const double mone = -1.0;
-      DevBuf<double> dDiff;
-      LR_CUDA(dDiff.alloc((size_t)r * r));
       LR_CUDA(cudaMemcpyAsync(dDiff.p, dKL1.p, (size_t)r * r * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
       LR_CUBLAS(cublasDaxpy(e.blas, r * r, &mone, dK1.p, 1, dDiff.p, 1));
       count_launch();
       if ((st = gemm_rm(false, false, (int)n_test, r, r, dPs.p, r, dDiff.p, r, dTmp.p, r)) != LR_OK) return st;
       k_half_quad<<<ceil_div((long)n_test, 8), 256, 0, e.stream>>>(r, (long)n_test, dPs.p, dTmp.p, dA.p);
       LR_CHECK_LAUNCH();
-      LR_CUDA(cudaStreamSynchronize(e.stream));
     }
     // project this block's enrolment vectors and sum them per model
     const long e0 = first[m0];
     const long e1 = (m1 < n_models) ? first[m1] : (long)n_enrol;
     const size_t ne = (size_t)(e1 - e0);
     {
-      // gather the d x ne column block of the row-major models matrix through a strided copy
-      LR_CUDA(dEnr.alloc((size_t)d * ne));
-      LR_CUDA(cudaMemcpy2DAsync(dEnr.p, ne * sizeof(double), models + e0, n_enrol * sizeof(double),
-                                ne * sizeof(double), d, cudaMemcpyHostToDevice, e.stream));
-      LR_CUDA(dPm.alloc(ne * r));
-      if ((st = gemm_rm(true, true, (int)ne, r, d, dEnr.p, (int)ne, dFTJ.p, d, dPm.p, r)) != LR_OK) return st;
+      // Pm[ne x r] = (models[:, e0 .. e1))^T FTJ^T.  Device input: the column block is read in place
+      // (leading dimension n_enrol); host input: gathered through a strided copy first.
+      if (dPm.n < ne * r) LR_CUDA(dPm.alloc(ne * r));
+      if (dev_in) {
+        if ((st = gemm_rm(true, true, (int)ne, r, d, models + e0, (int)n_enrol, dFTJ.p, d, dPm.p, r)) != LR_OK)
+          return st;
+      } else {
+        if (dEnr.n < (size_t)d * ne) LR_CUDA(dEnr.alloc((size_t)d * ne));
+        LR_CUDA(cudaMemcpy2DAsync(dEnr.p, ne * sizeof(double), models + e0, n_enrol * sizeof(double),
+                                  ne * sizeof(double), d, in_kind, e.stream));
+        if ((st = gemm_rm(true, true, (int)ne, r, d, dEnr.p, (int)ne, dFTJ.p, d, dPm.p, r)) != LR_OK) return st;
+      }
     }
-    // block-relative first indices
-    {
-      std::vector<long> rel(nm);
-      for (size_t i = 0; i < nm; i++) rel[i] = first[m0 + i] - e0;
-      LR_CUDA(cudaMemcpyAsync(dFirst.p, rel.data(), nm * sizeof(long), cudaMemcpyHostToDevice, e.stream));
-      LR_CUDA(cudaStreamSynchronize(e.stream));
-    }
-    k_model_sums<<<(unsigned)nm, 128, 0, e.stream>>>(r, dPm.p, dFirst.p, dCount.p + m0, (long)nm, dM.p);
+    k_model_sums<<<(unsigned)nm, 128, 0, e.stream>>>(r, dPm.p, dFirst.p + m0, e0, dCount.p + m0, (long)nm, dM.p);
     LR_CHECK_LAUNCH();
-    // b[m] = 1/2 m^T (K' - K_L) m
+    // row term b[m] + const = 1/2 m^T (K' - K_L) m + const
     {
       const double mone = -1.0;
-      DevBuf<double> dDiff;
-      LR_CUDA(dDiff.alloc((size_t)r * r));
       LR_CUDA(cudaMemcpyAsync(dDiff.p, dKL1.p, (size_t)r * r * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
       LR_CUBLAS(cublasDaxpy(e.blas, r * r, &mone, dKL.p, 1, dDiff.p, 1));
       count_launch();
       if ((st = gemm_rm(false, false, (int)nm, r, r, dM.p, r, dDiff.p, r, dTmp.p, r)) != LR_OK) return st;
       k_half_quad<<<ceil_div((long)nm, 8), 256, 0, e.stream>>>(r, (long)nm, dM.p, dTmp.p, dB.p);
       LR_CHECK_LAUNCH();
-      LR_CUDA(cudaStreamSynchronize(e.stream));
+      k_add_const<<<ceil_div((long)nm, 256), 256, 0, e.stream>>>((long)nm, constant, dB.p);
+      LR_CHECK_LAUNCH();
     }
-    // cross term: S[nm x n_test] (row-major) = (M K') Ps^T
+    // cross term: scores[nm x n_test] = (M K') Ps^T + row + column terms, in the tcgen05 kernel
     if ((st = gemm_rm(false, false, (int)nm, r, r, dM.p, r, dKL1.p, r, dTmp.p, r)) != LR_OK) return st;
-    if ((st = gemm_rm(false, true, (int)nm, (int)n_test, r, dTmp.p, r, dPs.p, r, dS.p, (int)n_test)) != LR_OK) return st;
-    k_score_epilogue<<<std::min<long>(ceil_div((long)(nm * n_test), 256), (long)e.sm_count * 16), 256, 0, e.stream>>>(
-        (long)n_test, (long)nm, dA.p, dB.p, constant, dS.p);
-    LR_CHECK_LAUNCH();
-    LR_CUDA(cudaMemcpyAsync(scores + m0 * n_test, dS.p, nm * n_test * sizeof(double),
-                            cudaMemcpyDeviceToHost, e.stream));
-    LR_CUDA(cudaStreamSynchronize(e.stream));
+    if ((st = gemm_split_prepare(dTmp.p, r, (long)nm, r, dAp.p, dScal.p + 3, &scaleA)) != LR_OK) return st;
+    if (scores_host) {
+      const int buf = blk & 1;
+      if (blk >= 2) LR_CUDA(cudaStreamWaitEvent(e.stream, ev_copied[buf], 0));  // its previous copy is out
+      if ((st = gemm_split_run<double>(dAp.p, scaleA, (long)nm, dBp.p, scaleB, (long)n_test, r, dOut[buf].p,
+                                       n_test, dB.p, dA.p)) != LR_OK)
+        return st;
+      LR_CUDA(cudaEventRecord(ev_done[buf], e.stream));
+      // the D2H copy of the PREVIOUS block is issued now: a copy to pageable host memory holds the
+      // host thread, and this block's kernels are already queued behind it on the compute stream
+      if ((st = drain()) != LR_OK) return st;
+      pend_buf = buf;
+      pend_m0 = m0;
+      pend_nm = nm;
+    } else {
+      if ((st = gemm_split_run<float>(dAp.p, scaleA, (long)nm, dBp.p, scaleB, (long)n_test, r,
+                                      d_scores_f32 + m0 * ld_scores, ld_scores, dB.p, dA.p)) != LR_OK)
+        return st;
+    }
+    blk++;
     m0 = m1;
   }
+  if (scores_host && (st = drain()) != LR_OK) return st;
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.copy_stream));
   return LR_OK;
+}
+
+extern "C" lr_status lr_plda_native_scoring(int d, int rF, int rG, const double *F, const double *G,
+                                            const double *Sigma, const double *models,
+                                            size_t n_enrol, const int32_t *model_of,
+                                            size_t n_models, const double *segments, size_t n_test,
+                                            double *scores) {
+  return plda_score_impl(d, rF, rG, F, G, Sigma, models, false, n_enrol, model_of, n_models, segments, n_test,
+                         scores, nullptr, 0);
+}
+
+extern "C" lr_status lr_plda_native_scoring_dev(int d, int rF, int rG, const double *F, const double *G,
+                                                const double *Sigma, const double *d_models,
+                                                size_t n_enrol, const int32_t *model_of, size_t n_models,
+                                                const double *d_segments, size_t n_test, float *d_scores,
+                                                size_t ld_scores) {
+  LR_REQUIRE(d_scores && ld_scores >= n_test, "lr_plda_native_scoring_dev: bad output");
+  return plda_score_impl(d, rF, rG, F, G, Sigma, d_models, true, n_enrol, model_of, n_models, d_segments,
+                         n_test, nullptr, d_scores, ld_scores);
 }
