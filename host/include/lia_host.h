@@ -172,6 +172,24 @@ void mixtureInit(const FeatureServer &fs, const SegCluster &segs, const std::vec
 void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs,
                 const std::vector<double> &globalCov, MixtureGD &world, const TrainCfg &cfg);
 
+// ---- one process per GPU.  Every program accepts --lrWorldSize N --lrRank r --lrCommFile <path on a
+// filesystem all ranks see> (or the environment: LR_WORLD_SIZE / LR_RANK / LR_COMM_FILE); the rank's device is
+// --device (default: rank % device count).  The data shard the way the reference's threaded variants split
+// them: contiguous NDX-line ranges (AccumulateTVStat.cpp:498-507), segment ranges balanced by frames for the
+// EM accumulation (AccumulateStat.cpp:183-208 hands segments to threads), model rows for PLDA scoring
+// (PldaTools.cpp:4302-4412).
+struct Shard {
+  int rank = 0, world = 1;
+  static Shard &get();
+  // [begin, end) of n units for this rank: contiguous, balanced
+  std::pair<size_t, size_t> range(size_t n) const;
+  // contiguous ranges balanced by weight (frames per unit)
+  std::pair<size_t, size_t> rangeByWeight(const std::vector<double> &w) const;
+  void barrier() const;
+};
+// lr_init on the rank's device + the communicator; called by every main before the driver
+void initEngine(const Config &c);
+
 // ---- MAP adaptation (TrainTools.cpp:110-147, 445-489, 871-904): the "next" row TrainTarget
 struct MAPCfg {
   bool mean = false, var = false, weight = false;
@@ -226,7 +244,9 @@ class TVAcc {
 
  private:
   Config cfg_;
-  std::vector<std::vector<std::string>> lines_;  // NDX lines: id + files
+  std::vector<std::vector<std::string>> lines_;  // THIS RANK's NDX lines: id + files
+  size_t firstLine_ = 0, totalLines_ = 0, totalSessions_ = 0;  // position of the shard in the whole list
+  void shardLines();
   MixtureGD world_;
   int R_ = 0;
   lr_tv *tv_ = nullptr;

@@ -538,28 +538,66 @@ void IvTestPldaScoring(Config &c) {
               ", Sigma " + std::to_string(Sigma.rows) + " x " + std::to_string(Sigma.cols) +
               ") does not match the (normalised) i-vector size " + std::to_string(d));
   Matrix scores(nModels, nTest);
-  if (c.getString("pldaScoring", "native") == "enrollMean") {
-    // PldaTest::pldaMeanScoring (PldaTools.cpp:4612-4709): each model is the MEAN of its enrolment
-    // i-vectors scored as one session -- K_two = (2 FTJF + I)^-1 is exactly the native K_{L+1} at
-    // L = 1, so this is the native scorer on one averaged column per model.
-    Matrix avg(d, nModels);
-    std::vector<double> cnt(nModels, 0.0);
-    std::vector<int32_t> one(nModels);
-    for (size_t j = 0; j < nEnrol; j++) {
-      cnt[modelOf[j]] += 1.0;
-      for (size_t i = 0; i < d; i++) avg(i, modelOf[j]) += models(i, j);
+  // several ranks: contiguous ranges of MODELS (rows of the score matrix; PldaTools.cpp:4302-4412 splits the
+  // models over threads the same way), segments replicated, no collective in the scoring; the row blocks are
+  // gathered so that rank 0 writes the file a single process writes
+  const Shard &sh = Shard::get();
+  const auto mr = sh.range(nModels);
+  const size_t myModels = mr.second - mr.first;
+  // enrolment columns of the rank's models (model_of is non-decreasing)
+  size_t e0 = 0, e1 = nEnrol;
+  if (sh.world > 1) {
+    e0 = std::lower_bound(modelOf.begin(), modelOf.end(), (int32_t)mr.first) - modelOf.begin();
+    e1 = std::lower_bound(modelOf.begin(), modelOf.end(), (int32_t)mr.second) - modelOf.begin();
+  }
+  Matrix mine(std::max<size_t>(myModels, 1), nTest);
+  if (myModels > 0) {
+    if (c.getString("pldaScoring", "native") == "enrollMean") {
+      // PldaTest::pldaMeanScoring (PldaTools.cpp:4612-4709): each model is the MEAN of its enrolment
+      // i-vectors scored as one session -- K_two = (2 FTJF + I)^-1 is exactly the native K_{L+1} at
+      // L = 1, so this is the native scorer on one averaged column per model.
+      Matrix avg(d, myModels);
+      std::vector<double> cnt(myModels, 0.0);
+      std::vector<int32_t> one(myModels);
+      for (size_t j = e0; j < e1; j++) {
+        cnt[modelOf[j] - mr.first] += 1.0;
+        for (size_t i = 0; i < d; i++) avg(i, modelOf[j] - mr.first) += models(i, j);
+      }
+      for (size_t m = 0; m < myModels; m++) {
+        one[m] = (int32_t)m;
+        for (size_t i = 0; i < d; i++) avg(i, m) /= cnt[m];
+      }
+      LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
+                                       Sigma.data.data(), avg.data.data(), myModels, one.data(), myModels,
+                                       segments.data.data(), nTest, mine.data.data()));
+    } else {
+      // the rank's enrolment columns as a compact [d x (e1 - e0)] block
+      Matrix part(d, e1 - e0);
+      std::vector<int32_t> partOf(e1 - e0);
+      for (size_t j = e0; j < e1; j++) {
+        partOf[j - e0] = modelOf[j] - (int32_t)mr.first;
+        for (size_t i = 0; i < d; i++) part(i, j - e0) = models(i, j);
+      }
+      LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
+                                       Sigma.data.data(), part.data.data(), e1 - e0, partOf.data(), myModels,
+                                       segments.data.data(), nTest, mine.data.data()));
     }
-    for (size_t m = 0; m < nModels; m++) {
-      one[m] = (int32_t)m;
-      for (size_t i = 0; i < d; i++) avg(i, m) /= cnt[m];
-    }
-    LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
-                                     Sigma.data.data(), avg.data.data(), nModels, one.data(), nModels,
-                                     segments.data.data(), nTest, scores.data.data()));
+  }
+  if (sh.world == 1) {
+    scores = mine;
   } else {
-    LIA_CHECK(lr_plda_native_scoring((int)d, (int)F.cols, rG, F.data.data(), rG ? G.data.data() : nullptr,
-                                     Sigma.data.data(), models.data.data(), nEnrol, modelOf.data(), nModels,
-                                     segments.data.data(), nTest, scores.data.data()));
+    const size_t blockRows = (nModels + sh.world - 1) / sh.world;
+    std::vector<double> send(blockRows * nTest, 0.0), recv(send.size() * sh.world);
+    if (myModels > 0) std::copy(mine.data.begin(), mine.data.begin() + myModels * nTest, send.begin());
+    LIA_CHECK(lr_allgather_host(send.data(), send.size(), recv.data()));
+    Shard probe = sh;
+    for (int r = 0; r < sh.world; r++) {
+      probe.rank = r;
+      auto rg = probe.range(nModels);
+      std::copy(recv.begin() + (size_t)r * send.size(), recv.begin() + (size_t)r * send.size() + (rg.second - rg.first) * nTest,
+                scores.data.begin() + rg.first * nTest);
+    }
+    if (sh.rank != 0) return;
   }
   // output (IvTest.cpp:412-465): the trials listed in the NDX, segment-major in matrix order
   (void)modelIndex;

@@ -50,12 +50,12 @@ int TrainWorld(Config &c) {
       world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
     } else {
       world.resize((int)c.getLong("mixtureDistribCount"), fs.getVectSize());
-      mixtureInit(fs, segs, gCov, c, world);
-      if (c.getBool("saveInitModel", true)) world.saveFromConfig(out + "init", c);
+      mixtureInit(fs, segs, gCov, c, world);  // (deterministic: every rank builds the same initial model)
+      if (c.getBool("saveInitModel", true) && Shard::get().rank == 0) world.saveFromConfig(out + "init", c);
     }
     if (verbose) std::cout << "Train world model: " << world.C << " components, " << totalFrame(segs) << " frames" << std::endl;
     trainModel(c, fs, segs, gCov, world, cfg);
-    world.saveFromConfig(out, c);
+    if (Shard::get().rank == 0) world.saveFromConfig(out, c);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }
@@ -104,8 +104,16 @@ int ComputeTest(Config &c) {
     MixtureGD worldM = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
     Gmm world(worldM, true);
     std::map<std::string, std::unique_ptr<Gmm>> cache;  // client models stay resident (TabClientLine)
-    std::ofstream outNist(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
-    for (auto &line : ndx.lines()) {
+    // several ranks: contiguous ranges of NDX lines (independent test files, no collective); every rank
+    // writes its part, rank 0 concatenates them in rank order -- the file a single process writes
+    const Shard &sh = Shard::get();
+    const std::string outName = c.getParam("outputFilename");
+    auto partName = [&](int r) { return sh.world > 1 ? outName + ".part" + std::to_string(r) : outName; };
+    std::ofstream outNist(partName(sh.rank).c_str(), std::ios::out | std::ios::trunc);
+    const auto allLines = ndx.lines();
+    const auto myRange = sh.range(allLines.size());
+    for (size_t li = myRange.first; li < myRange.second; li++) {
+      const auto &line = allLines[li];
       const std::string &test = line[0];
       FeatureServer fs(c, {test});
       SegCluster segs = selectedSegments(c, fs, label);
@@ -135,6 +143,19 @@ int ComputeTest(Config &c) {
           else
             outputResultLine(llr, line[i + 1], test, gender, setDecision(llr, threshold), outNist);
         }
+    }
+    outNist.close();
+    if (sh.world > 1) {
+      sh.barrier();
+      if (sh.rank == 0) {
+        std::ofstream all(outName.c_str(), std::ios::out | std::ios::trunc);
+        for (int r = 0; r < sh.world; r++) {
+          std::ifstream part(partName(r).c_str());
+          all << part.rdbuf();
+          part.close();
+          std::remove(partName(r).c_str());
+        }
+      }
     }
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
@@ -267,7 +288,8 @@ int TotalVariability(Config &c) {
       tv.loadT(c.getParam("initTotalVariabilityMatrix"), c);
     else
       tv.initT(c);
-    if (c.getBool("saveInitTotalVariabilityMatrix", false)) tv.saveT(c.getParam("totalVariabilityMatrix") + "_init", c);
+    const bool root = Shard::get().rank == 0;  // T, the mean estimate and the approximation matrices are replicated
+    if (c.getBool("saveInitTotalVariabilityMatrix", false) && root) tv.saveT(c.getParam("totalVariabilityMatrix") + "_init", c);
     const bool minDiv = c.getBool("minDivergence", false);
     const long nbIt = c.getLong("nbIt");
     for (long it = 0; it < nbIt; it++) {
@@ -280,10 +302,10 @@ int TotalVariability(Config &c) {
       if (c.getBool("orthonormalizeT", false)) tv.orthonormalizeT();
       tv.resetTmpAcc();
       tv.reloadStats();  // the reference re-reads N / F_X from disk here (:149-153); we keep a host copy
-      if (c.getBool("saveAllTVMatrices", false)) tv.saveT(c.getParam("totalVariabilityMatrix") + std::to_string(it), c);
+      if (c.getBool("saveAllTVMatrices", false) && root) tv.saveT(c.getParam("totalVariabilityMatrix") + std::to_string(it), c);
     }
-    tv.saveT(c.getParam("totalVariabilityMatrix"), c);
-    if (minDiv) {
+    if (root) tv.saveT(c.getParam("totalVariabilityMatrix"), c);
+    if (minDiv && root) {
       Matrix m = tv.getUbmMeans();
       m.save(c.getString("matrixFilesPath", "") + c.getParam("meanEstimate") + c.getString("saveMatrixFilesExtension", ""),
              c.getString("saveMatrixFormat", "DB"));
@@ -294,16 +316,16 @@ int TotalVariability(Config &c) {
       const std::string fmt = c.getString("saveMatrixFormat", "DB");
       if (mode == "ubmWeight" || mode == "eigenDecomposition") {
         tv.normTMatrix();
-        tv.saveT(c.getParam("totalVariabilityMatrix") + "_norm", c);
+        if (root) tv.saveT(c.getParam("totalVariabilityMatrix") + "_norm", c);
         Matrix W = tv.getWeightedCov(tv.world().w);
         if (mode == "ubmWeight") {
-          W.save(approxName(c, "_weightedCov"), fmt);
+          if (root) W.save(approxName(c, "_weightedCov"), fmt);
         } else {
           Matrix Q;
           TVAcc::computeEigenProblem(W, Q, tv.rank());
           Matrix D = tv.approximateTcTc(Q);
-          D.save(approxName(c, "_EigDec_D"), fmt);
-          Q.save(approxName(c, "_EigDec_Q"), fmt);
+          if (root) D.save(approxName(c, "_EigDec_D"), fmt);
+          if (root) Q.save(approxName(c, "_EigDec_Q"), fmt);
         }
       } else {
         std::cout << "\t(TotalVariability) This approximation mode does not exists" << std::endl;

@@ -144,7 +144,32 @@ void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs
     srand((unsigned)(((it + 1 + initRand) * 200) + 20 + 1));  // :1070 (stream 0, baggedIt 0)
     SegCluster bagged = cfg.baggedFrameProbability >= 1.0 ? segs
                                                           : baggedSegments(segs, cfg.baggedFrameProbability, minLen, maxLen);
-    double llk = accumulateStatEM(fs, g, bagged, acc);
+    // several ranks: each accumulates a contiguous range of the (identically bagged) segments balanced by
+    // frames, then ONE all-reduce of {occ, m1, m2, llk, n} -- emAcc.addAccEM (AccumulateStat.cpp:286-292)
+    const Shard &sh = Shard::get();
+    double llk;
+    if (sh.world > 1) {
+      std::vector<double> wgt(bagged.size());
+      for (size_t i = 0; i < bagged.size(); i++) wgt[i] = (double)bagged[i].length;
+      auto r = sh.rangeByWeight(wgt);
+      SegCluster mine(bagged.begin() + r.first, bagged.begin() + r.second);
+      llk = mine.empty() ? 0.0 : accumulateStatEM(fs, g, mine, acc);
+      const size_t cC = world.C, cd = (size_t)world.C * world.D;
+      std::vector<double> pack(cC + 2 * cd + 2);
+      std::copy(acc.occ.begin(), acc.occ.end(), pack.begin());
+      std::copy(acc.m1.begin(), acc.m1.end(), pack.begin() + cC);
+      std::copy(acc.m2.begin(), acc.m2.end(), pack.begin() + cC + cd);
+      pack[cC + 2 * cd] = llk;
+      pack[cC + 2 * cd + 1] = acc.n;
+      LIA_CHECK(lr_allreduce_host(pack.data(), pack.size()));
+      std::copy(pack.begin(), pack.begin() + cC, acc.occ.begin());
+      std::copy(pack.begin() + cC, pack.begin() + cC + cd, acc.m1.begin());
+      std::copy(pack.begin() + cC + cd, pack.begin() + cC + 2 * cd, acc.m2.begin());
+      llk = pack[cC + 2 * cd];
+      acc.n = pack[cC + 2 * cd + 1];
+    } else {
+      llk = accumulateStatEM(fs, g, bagged, acc);
+    }
     // *world = emAcc.getEM(); varianceControl(world, flooring, ceiling, globalCov)  (:1076-1077)
     LIA_CHECK(lr_gmm_em_update(g.h(), acc.occ.data(), acc.m1.data(), acc.m2.data(), flooring, ceiling,
                                globalCov.data()));
@@ -222,16 +247,79 @@ void adaptModel(const Config &c, const FeatureServer &fs, const SegCluster &segs
   }
 }
 
+// ------------------------------------------------------------------ one process per GPU
+Shard &Shard::get() {
+  static Shard s;
+  return s;
+}
+std::pair<size_t, size_t> Shard::range(size_t n) const {
+  const size_t per = n / world, rem = n % world;
+  const size_t b = rank * per + std::min<size_t>(rank, rem);
+  return {b, b + per + ((size_t)rank < rem ? 1 : 0)};
+}
+std::pair<size_t, size_t> Shard::rangeByWeight(const std::vector<double> &w) const {
+  // cut k goes where the prefix sum is closest to k / world of the total (cuts stay monotone)
+  std::vector<double> prefix(w.size() + 1, 0.0);
+  for (size_t i = 0; i < w.size(); i++) prefix[i + 1] = prefix[i] + w[i];
+  std::vector<size_t> cuts(world + 1, w.size());
+  cuts[0] = 0;
+  size_t i = 0;
+  for (int k = 1; k < world; k++) {
+    const double target = prefix.back() * k / world;
+    while (i < w.size() && prefix[i + 1] < target) i++;
+    size_t cut = (i < w.size() && target - prefix[i] > prefix[i + 1] - target) ? i + 1 : i;
+    cuts[k] = std::max(cut, cuts[k - 1]);
+  }
+  return {cuts[rank], cuts[rank + 1]};
+}
+void Shard::barrier() const {
+  if (world > 1) {
+    double one = 1.0;
+    LIA_CHECK(lr_allreduce_host(&one, 1));
+  }
+}
+void initEngine(const Config &c) {
+  auto env = [](const char *k) -> const char * { const char *v = getenv(k); return (v && *v) ? v : nullptr; };
+  Shard &s = Shard::get();
+  s.world = (int)c.getLong("lrWorldSize", env("LR_WORLD_SIZE") ? atol(env("LR_WORLD_SIZE")) : 1);
+  s.rank = (int)c.getLong("lrRank", env("LR_RANK") ? atol(env("LR_RANK")) : 0);
+  if (s.world < 1 || s.rank < 0 || s.rank >= s.world) LIA_THROW("lrRank / lrWorldSize out of range");
+  if (c.existsParam("device"))
+    LIA_CHECK(lr_init((int)c.getLong("device")));
+  else if (s.world > 1)
+    LIA_CHECK(lr_init(s.rank));
+  if (s.world > 1) {
+    const std::string f = c.getString("lrCommFile", env("LR_COMM_FILE") ? env("LR_COMM_FILE") : "");
+    if (f.empty()) LIA_THROW("lrWorldSize > 1 needs lrCommFile (rendezvous file on a shared filesystem)");
+    LIA_CHECK(lr_comm_init_file(s.rank, s.world, f.c_str()));
+  }
+}
+
 // ------------------------------------------------------------------ TVAcc
+// With several ranks a TVAcc holds the rank's contiguous range of NDX lines (AccumulateTVStat.cpp:498-507
+// splits the lines over threads the same way); the statistics files on disk stay whole.
+void TVAcc::shardLines() {
+  totalLines_ = lines_.size();
+  totalSessions_ = 0;
+  for (auto &l : lines_) totalSessions_ += l.size();
+  auto r = Shard::get().range(lines_.size());
+  firstLine_ = r.first;
+  if (r.second - r.first < lines_.size())
+    lines_ = std::vector<std::vector<std::string>>(lines_.begin() + r.first, lines_.begin() + r.second);
+  if (lines_.empty()) LIA_THROW("TVAcc: fewer NDX lines than ranks");
+}
+
 TVAcc::TVAcc(const std::string &ndxFile, const Config &c) : cfg_(c) {
   XList ndx(ndxFile);
   lines_ = ndx.lines();
   if (lines_.empty()) LIA_THROW("TVAcc: empty NDX list " + ndxFile);
+  shardLines();
   init(c);
 }
 TVAcc::TVAcc(const std::vector<std::vector<std::string>> &fileLines, const Config &c)
     : cfg_(c), lines_(fileLines) {
   if (lines_.empty()) LIA_THROW("TVAcc: empty file list");
+  shardLines();
   init(c);
 }
 void TVAcc::init(const Config &c) {
@@ -328,14 +416,26 @@ void TVAcc::loadN(const Config &c) {
   N_.load(c.getString("matrixFilesPath", "") + c.getParam("nullOrderStatSpeaker") +
               c.getString("loadMatrixFilesExtension", ""),
           c.getString("loadMatrixFormat", "DB"));
-  if (N_.rows != lines_.size() || N_.cols != (size_t)world_.C) LIA_THROW("Incorrect dimension of N Matrix");
+  if (N_.rows != totalLines_ || N_.cols != (size_t)world_.C) LIA_THROW("Incorrect dimension of N Matrix");
+  if (lines_.size() != totalLines_) {  // several ranks: the file holds every line, keep this rank's rows
+    Matrix mine(lines_.size(), N_.cols);
+    std::copy(N_.data.begin() + firstLine_ * N_.cols, N_.data.begin() + (firstLine_ + lines_.size()) * N_.cols,
+              mine.data.begin());
+    N_ = mine;
+  }
 }
 void TVAcc::loadF_X(const Config &c) {
   F_.load(c.getString("matrixFilesPath", "") + c.getParam("firstOrderStatSpeaker") +
               c.getString("loadMatrixFilesExtension", ""),
           c.getString("loadMatrixFormat", "DB"));
-  if (F_.rows != lines_.size() || F_.cols != (size_t)world_.C * world_.D)
+  if (F_.rows != totalLines_ || F_.cols != (size_t)world_.C * world_.D)
     LIA_THROW("Incorrect dimension of F_X Matrix");
+  if (lines_.size() != totalLines_) {
+    Matrix mine(lines_.size(), F_.cols);
+    std::copy(F_.data.begin() + firstLine_ * F_.cols, F_.data.begin() + (firstLine_ + lines_.size()) * F_.cols,
+              mine.data.begin());
+    F_ = mine;
+  }
   LIA_CHECK(lr_tv_set_stats(tv_, N_.data.data(), F_.data.data()));
 }
 void TVAcc::saveAccs(const Config &c) {
@@ -343,8 +443,32 @@ void TVAcc::saveAccs(const Config &c) {
   const std::string path = c.getString("matrixFilesPath", ""), ext = c.getString("saveMatrixFilesExtension", "");
   if (c.existsParam("nullOrderStatSpeaker")) n = path + c.getParam("nullOrderStatSpeaker") + ext;
   if (c.existsParam("firstOrderStatSpeaker")) fx = path + c.getParam("firstOrderStatSpeaker") + ext;
-  F_.save(fx, c.getString("saveMatrixFormat", "DB"));
-  N_.save(n, c.getString("saveMatrixFormat", "DB"));
+  const Shard &sh = Shard::get();
+  if (sh.world == 1) {
+    F_.save(fx, c.getString("saveMatrixFormat", "DB"));
+    N_.save(n, c.getString("saveMatrixFormat", "DB"));
+    return;
+  }
+  // several ranks: the rows are gathered (equal-size blocks of ceil(lines / world) rows, then cut) and rank 0
+  // writes the files the single-process run writes
+  const size_t blockRows = (totalLines_ + sh.world - 1) / sh.world;
+  auto gather = [&](const Matrix &mine, const std::string &file) {
+    std::vector<double> send(blockRows * mine.cols, 0.0), recv(send.size() * sh.world);
+    std::copy(mine.data.begin(), mine.data.end(), send.begin());
+    LIA_CHECK(lr_allgather_host(send.data(), send.size(), recv.data()));
+    if (sh.rank != 0) return;
+    Matrix all(totalLines_, mine.cols);
+    Shard probe = sh;
+    for (int r = 0; r < sh.world; r++) {
+      probe.rank = r;
+      auto rg = probe.range(totalLines_);
+      std::copy(recv.begin() + (size_t)r * send.size(), recv.begin() + (size_t)r * send.size() + (rg.second - rg.first) * mine.cols,
+                all.data.begin() + rg.first * mine.cols);
+    }
+    all.save(file, c.getString("saveMatrixFormat", "DB"));
+  };
+  gather(F_, fx);
+  gather(N_, n);
 }
 
 void TVAcc::substractM() { LIA_CHECK(lr_tv_subtract_m(tv_)); }
@@ -352,11 +476,18 @@ void TVAcc::estimateTETt() { LIA_CHECK(lr_tv_estimate_tett(tv_)); }
 void TVAcc::estimateW() { LIA_CHECK(lr_tv_estimate_w(tv_)); }
 void TVAcc::estimateAandC() { LIA_CHECK(lr_tv_estimate_a_and_c(tv_)); }
 void TVAcc::resetTmpAcc() { LIA_CHECK(lr_tv_reset_tmp_acc(tv_)); }
-void TVAcc::updateTestimate() { LIA_CHECK(lr_tv_update_t(tv_)); }
+void TVAcc::updateTestimate() {
+  // several ranks: the one exchange step of the iteration + the component-sharded M-step
+  if (Shard::get().world > 1) {
+    double total = 0;
+    LIA_CHECK(lr_tv_exchange_sharded(tv_, (double)lines_.size(), &total));
+  } else {
+    LIA_CHECK(lr_tv_update_t(tv_));
+  }
+}
 void TVAcc::minDivergence() {
-  size_t sessions = 0;
-  for (auto &l : lines_) sessions += l.size();  // _n_sessions (:137)
-  LIA_CHECK(lr_tv_min_divergence(tv_, (double)sessions));
+  // _n_sessions (:137) counts the sessions of the WHOLE list; the accumulators were summed over the ranks
+  LIA_CHECK(lr_tv_min_divergence(tv_, (double)totalSessions_));
 }
 void TVAcc::orthonormalizeT() { LIA_CHECK(lr_tv_orthonormalize_t(tv_)); }
 
@@ -411,8 +542,9 @@ void TVAcc::saveWbyFile(const Config &c) {
   const std::string path = c.getParam("saveVectorFilesPath"), ext = c.getString("vectorFilesExtension", ".y");
   XList ids(c.getParam("targetIdList"));
   Matrix W = getW();
-  size_t session = 0;
+  size_t session = 0, lineNo = 0;
   for (auto &line : ids.lines()) {
+    if (lineNo++ < firstLine_) continue;  // another rank's i-vector (one file per line: nothing to gather)
     if (session >= W.rows) break;
     Matrix y(1, R_);
     for (int i = 0; i < R_; i++) y(0, i) = W(session, i);

@@ -74,6 +74,22 @@ int main(int argc, char **argv) {
       back.load(c.getParam("tmpPrefix") + "_scores.mat", "DB");
       std::cout << "scores_binary " << back.rows << " " << back.cols << " " << back.data[5] << "\n";
     }
+    {  // rank sharding (no device needed): contiguous balanced ranges, by count and by frames
+      lia::Shard sh;
+      sh.world = 3;
+      std::cout << "shard_range";
+      for (sh.rank = 0; sh.rank < 3; sh.rank++) {
+        auto r = sh.range(10);
+        std::cout << " " << r.first << "-" << r.second;
+      }
+      std::cout << "\nshard_weight";
+      const std::vector<double> frames = {100, 100, 100, 900, 100, 100, 100, 300};
+      for (sh.rank = 0; sh.rank < 3; sh.rank++) {
+        auto r = sh.rangeByWeight(frames);
+        std::cout << " " << r.first << "-" << r.second;
+      }
+      std::cout << "\n";
+    }
     try {
       c.getParam("noSuchParameter");
     } catch (lia::Exception &e) {

@@ -12,7 +12,7 @@ int main(int argc, char **argv) {
       std::cout << "IvExtractor (lia_ral_b200 engine): --config <file> [--param value ...]" << std::endl;
       return 0;
     }
-    if (config.existsParam("device")) lr_init((int)config.getLong("device"));
+    lia::initEngine(config);  // device + (several ranks) the NCCL communicator
     // IvExtractorMain.cpp:99-111: classic (default) | ubmWeight | eigenDecomposition
     const std::string mode = config.existsParam("mode") ? config.getParam("mode") : "classic";
     if (mode == "classic") return lia::IvExtractor(config);

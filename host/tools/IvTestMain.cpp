@@ -12,7 +12,7 @@ int main(int argc, char **argv) {
       std::cout << "IvTest (lia_ral_b200 engine): --config <file> [--param value ...]" << std::endl;
       return 0;
     }
-    if (config.existsParam("device")) lr_init((int)config.getLong("device"));
+    lia::initEngine(config);  // device + (several ranks) the NCCL communicator
     return lia::IvTest(config);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;

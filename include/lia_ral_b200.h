@@ -36,7 +36,8 @@ enum {
   LR_OK = 0,
   LR_ERR_ARG = 1,   /* bad argument (reference: Exception thrown by the caller-side checks) */
   LR_ERR_CUDA = 2,  /* CUDA / cuBLAS failure, or no device */
-  LR_ERR_NUMERIC = 3 /* singular / non-SPD matrix (reference: invert()/upperCholesky() failing) */
+  LR_ERR_NUMERIC = 3, /* singular / non-SPD matrix (reference: invert()/upperCholesky() failing) */
+  LR_ERR_IO = 4      /* rendezvous file of lr_comm_init_file unreadable / unwritable */
 };
 
 const char *lr_last_error(void);
@@ -226,6 +227,35 @@ lr_status lr_tv_unpack_t(lr_tv *tv, int c0, int c1, const double *d_src);
 size_t lr_tv_acc_a_stride(const lr_tv *tv);
 /* after the all-reduce: meanW = sumW / n_speakers_total */
 lr_status lr_tv_finish_estep(lr_tv *tv, double n_speakers_total);
+
+/* ------------------------------------------------------------------ collectives (NCCL) ------
+ * One process per GPU (lr_init(local rank) first).  The hot path has ONE exchange step per EM
+ * iteration -- the sum of the ranks' sufficient statistics, the analogue of emAcc.addAccEM
+ * (AccumulateStat.cpp:286-292) and of the mutex-guarded A / C updates (AccumulateTVStat.cpp:1920-1937);
+ * everything else (BW statistics, ComputeTest, PLDA scoring) shards by NDX line / model row with no
+ * collective.  NCCL is loaded at run time (dlopen), the library has no link-time dependency on it. */
+#define LR_COMM_ID_BYTES 128
+/* rank 0 creates the id (ncclGetUniqueId), distributes it by any means, every rank calls lr_comm_init */
+lr_status lr_comm_unique_id(void *id128);
+lr_status lr_comm_init(int rank, int world, const void *id128);
+/* the same through a rendezvous file on a shared filesystem (rank 0 writes, the others wait) */
+lr_status lr_comm_init_file(int rank, int world, const char *path);
+int lr_comm_rank(void);
+int lr_comm_world(void);
+lr_status lr_comm_destroy(void);
+/* in-place SUM all-reduce of n doubles, device resident, on the engine stream (no host sync) /
+ * host buffer (H2D, all-reduce, D2H, sync) */
+lr_status lr_allreduce_stats(double *d_buf, size_t n);
+lr_status lr_allreduce_host(double *buf, size_t n);
+/* dst[world * n] = the ranks' src[n] in rank order */
+lr_status lr_allgather(const double *d_src, size_t n, double *d_dst);
+lr_status lr_allgather_host(const double *src, size_t n, double *dst);
+/* TotalVariability exchange + M-step after lr_tv_estimate_a_and_c on this rank's utterances:
+ * reduce-scatter A by component, all-reduce [Cmx | R | r | sumW], meanW = sumW / total speakers,
+ * updateTestimate on the rank's C / world components (:974-1005 is independent per component), all-gather
+ * of the new T columns.  C % world != 0: one all-reduce + replicated M-step.  world == 1: finish + M-step. */
+lr_status lr_tv_exchange_sharded(lr_tv *tv, double n_speakers_local, double *n_speakers_total);
+lr_status lr_tv_dims(const lr_tv *tv, int *C, int *D, int *R);
 
 /* ------------------------------------------------------------------ PLDA scoring ----------
  * PldaTest::pldaNativeScoring + pldaScoring (PldaTools.cpp:4489-4519, 4175-4271) with

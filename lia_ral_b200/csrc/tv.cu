@@ -882,6 +882,14 @@ lr_status lr_tv_unpack_t(lr_tv *tv, int c0, int c1, const double *d_src) {
 }
 // length (doubles) of the packed A_c block of ONE component inside lr_tv_dev_acc (components are
 // contiguous: a reduce-scatter by component works on the block directly)
+lr_status lr_tv_dims(const lr_tv *tv, int *C, int *D, int *R) {
+  LR_REQUIRE(tv, "lr_tv_dims: null handle");
+  if (C) *C = tv->C;
+  if (D) *D = tv->D;
+  if (R) *R = tv->R;
+  return LR_OK;
+}
+
 size_t lr_tv_acc_a_stride(const lr_tv *tv) { return tv ? tv->Rp() : 0; }
 
 lr_status lr_tv_min_divergence(lr_tv *tv, double n_sessions) {

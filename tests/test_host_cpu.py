@@ -77,6 +77,9 @@ def test_file_formats_and_selection(built, tmp_path):
     assert open(str(tmp_path / "tmp") + "_scores_model.txt").read().split() == ["m0", "m1"]
     assert open(str(tmp_path / "tmp") + "_scores_testSeg.txt").read().split() == ["s0", "s1", "s2"]
     assert r["scores_binary"] == ["2", "3", "1.5"]
+    # rank sharding of NDX lines / segments (one process per GPU): contiguous, balanced, covering
+    assert r["shard_range"] == ["0-4", "4-7", "7-10"]
+    assert r["shard_weight"] == ["0-3", "3-4", "4-8"]      # cut after 1/3 and 2/3 of the 1800 frames
     # the same features through the other on-disk formats: HTK (big-endian by definition), SPRO3,
     # RAW and byte-swapped RAW (bigEndian) -- the FeatureServer block must be identical
     for fmt, ext, extra in (("HTK", ".htk", {}), ("SPRO3", ".sp3", {}), ("RAW", ".raw", {"vectSize": D0}),
