@@ -289,6 +289,44 @@ def ivector_pipeline_block(torch, dist, capi, lrd, dev, rank, world, U=1250, fra
 
 
 
+def plda_block(torch, dist, capi, lrd, dev, rank, world, NM=125000, NT=10000, d=400, r=200):
+    """configs[4]: IvTest PLDA native scoring, 1 M models x 10 k segments, d = 400, rank 200 -- the models
+    (rows of the trial matrix) shard over the ranks (PldaTools.cpp:4302-4412 splits them over threads the same
+    way), segments replicated, no collective; fp32 scores stay in HBM (5 GB per rank).  The kernel is bound by
+    the score write: 4 B per trial against the measured HBM copy bandwidth."""
+    from lia_ral_b200 import synth
+    F, G, Sigma, _, _, _ = synth.make_plda(d=d, rF=r, rG=0, n_models=4, n_test=4, seed=6)
+    g = torch.Generator(device=dev)
+    g.manual_seed(60 + rank)
+    models = torch.randn((d, NM), device=dev, dtype=torch.float64, generator=g)
+    g.manual_seed(61)
+    segs = torch.randn((d, NT), device=dev, dtype=torch.float64, generator=g)
+    out = torch.empty((NM, NT), dtype=torch.float32, device=dev)
+    model_of = np.arange(NM, dtype=np.int32)
+    torch.cuda.synchronize()
+    dt = None
+    for it in range(3):
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        capi.plda_native_scoring_dev(F, G, Sigma, models.data_ptr(), NM, model_of, segs.data_ptr(), NT, out.data_ptr())
+        capi.synchronize()
+        dt = time.perf_counter() - t0
+    dt = _max_over_ranks(torch, dist, world, dev, dt)
+    pk = peaks()
+    res = {"value": NM * world * NT / dt, "unit": "trials/s", "n_gpus": world, "models_per_gpu": NM, "segments": NT,
+           "dim": d, "rank": r, "seconds": dt, "score_bytes_per_gpu": NM * NT * 4,
+           "hbm_write_gbs_per_gpu": NM * NT * 4 / dt / 1e9, "hbm_write_frac": NM * NT * 4 / dt / 1e9 / pk["hbm"],
+           "finite": bool(torch.isfinite(out[:: max(1, NM // 64)]).all().item()), "scaling": "weak",
+           "timing": "host clock around the whole C-ABI call (precomputation, projections, operand split, trial "
+                     "kernel), device-synchronised, max over ranks",
+           "workload": "IvTest PLDA native scoring, configs[4] per-GPU share (1M models / 8) x 10k segments"}
+    del models, segs, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def synth_model():
     from lia_ral_b200 import synth
     w, mean, cov = synth.make_ubm(C, D, seed=1)
@@ -539,7 +577,7 @@ def main():
             if world > 1:
                 dist.all_reduce(torch.zeros(1, dtype=torch.float64, device=dev))
     if not args.no_extra:
-        for name, fn in (("ivector_pipeline", ivector_pipeline_block), ("tv_em", tv_em_block)):
+        for name, fn in (("ivector_pipeline", ivector_pipeline_block), ("tv_em", tv_em_block), ("plda", plda_block)):
             try:
                 extra[name] = fn(torch, dist, capi, lrd, dev, rank, world)
             except Exception as exc:
