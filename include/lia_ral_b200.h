@@ -256,6 +256,18 @@ lr_status lr_allgather_host(const double *src, size_t n, double *dst);
  * of the new T columns.  C % world != 0: one all-reduce + replicated M-step.  world == 1: finish + M-step. */
 lr_status lr_tv_exchange_sharded(lr_tv *tv, double n_speakers_local, double *n_speakers_total);
 lr_status lr_tv_dims(const lr_tv *tv, int *C, int *D, int *R);
+/* The contraction kernel behind lr_tv_estimate_w / lr_tv_estimate_a_and_c (the scalar triple loops
+ * AccumulateTVStat.cpp:2129-2137, :2146-2153, :1776-1782, :1784-1788), exposed for the parity tests:
+ * C[M x N] = beta C + alpha A[M x K] B[N x K]^T, host buffers, row-major, fp64 in and out.  The product
+ * runs on the INT8 tensor pipe: every operand row is scaled by a power of two and cut into `planes`
+ * signed 7-bit digit planes (0 = the engine's setting, default 6); digit products accumulate exactly
+ * in int32 and are recombined in fp64 (error ~ 2^-(7 planes) of row scale x column scale). */
+lr_status lr_gemm_digits(size_t M, size_t N, size_t K, const double *A, const double *B, double *C,
+                         double alpha, double beta, int planes);
+/* Contraction kernel of the TV rows: which = 0 the INT8 digit GEMM (default), 1 cuBLAS fp64 (the
+ * cross-check of the parity tests); planes = digit planes per operand (3..8, 0 = keep).  Takes effect
+ * at the next lr_tv_estimate_tett. */
+lr_status lr_set_tv_gemm(int which, int planes);
 
 /* ------------------------------------------------------------------ PLDA scoring ----------
  * PldaTest::pldaNativeScoring + pldaScoring (PldaTools.cpp:4489-4519, 4175-4271) with

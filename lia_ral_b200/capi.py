@@ -147,6 +147,24 @@ def get_gmm_kernel():
     return int(lib().lr_get_gmm_kernel())
 
 
+def set_tv_gemm(which=0, planes=0):
+    """Contraction kernel of the TV rows: 0 = INT8 digit GEMM (default), 1 = cuBLAS fp64 cross-check;
+    planes = digit planes per operand (3..8, 0 = keep).  Effective at the next estimate_tett()."""
+    _check(lib().lr_set_tv_gemm(int(which), int(planes)))
+
+
+def gemm_digits(A, B, C=None, alpha=1.0, beta=0.0, planes=0):
+    """C = beta C + alpha A B^T through the INT8 digit GEMM (A [M x K], B [N x K], fp64)."""
+    A, B = _f64(A), _f64(B)
+    M, K = A.shape
+    N = B.shape[0]
+    assert B.shape[1] == K
+    out = np.zeros((M, N)) if C is None else _f64(C).copy()
+    _check(lib().lr_gemm_digits(ct.c_size_t(M), ct.c_size_t(N), ct.c_size_t(K), _d(A), _d(B), _d(out),
+                                ct.c_double(alpha), ct.c_double(beta), int(planes)))
+    return out
+
+
 class Feats:
     """Frames resident in HBM (FeatureServer buffer twin)."""
 

@@ -26,8 +26,10 @@ struct Engine {
   uint64_t launches = 0;
   int gmm_kernel = 0;  // 0 auto, 1 simt, 2 tcgen05 (one-pass statistics), 3 tcgen05 two-pass
   int tc_debug = 0;    // profiling experiments only (LR_TC_DEBUG builds): results are WRONG when set
+  int tv_gemm = 0;     // TV contractions: 0 = INT8 digit GEMM (gemm_i8.cu), 1 = cuBLAS fp64 (cross-check)
+  int tv_planes = 6;   // digit planes per operand of the INT8 digit GEMM
   // per-device "cudaFuncSetAttribute done" flags (reset by lr_shutdown: the attribute is per context)
-  enum { kAttrTc = 0, kAttrSimtLse, kAttrSimtAcc, kAttrTopk, kAttrTvDiag, kAttrTvGemm, kAttrPlda, kAttrCount };
+  enum { kAttrTc = 0, kAttrSimtLse, kAttrSimtAcc, kAttrTopk, kAttrTvDiag, kAttrTvGemm, kAttrPlda, kAttrGemmI8, kAttrCount };
   bool attr_set[kAttrCount] = {};
   // grow-only device scratch slots reused across calls (freed by lr_shutdown)
   static constexpr int kScratchSlots = 14;

@@ -1702,11 +1702,18 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
     int t2 = t;
     while (t2 < n_tiles && tile_row[t2] == row && tile_group[t2] == gi) t2++;
     if (row < 0) return fail(LR_ERR_ARG, "tc_run_stats: tile %d is covered by no chunk", t);
+    // Runs of at most run_tiles tiles.  A long stretch of one row (the EM case: one row, every group)
+    // starts with a SHORTER first run that differs from group to group, so that the groups do not
+    // flush their accumulators into the same C x D addresses at the same moment (144 CTAs x 15 k fp64
+    // atomics in one burst otherwise).
+    const int first_run = (t2 - t > 2 * run_tiles) ? std::max(1, run_tiles * (gi % groups + 1) / groups) : run_tiles;
     for (int k = t; k < t2; k++) {
-      const int in_run = (k - t) % run_tiles;
+      const int off = k - t;
+      const int in_run = off < first_run ? off : (off - first_run) % run_tiles;
+      const int run_len = off < first_run ? first_run : run_tiles;
       int flags = 0;
       if (in_run == 0) flags |= 1;
-      if (in_run == run_tiles - 1 || k == t2 - 1) flags |= 2;
+      if (in_run == run_len - 1 || k == t2 - 1) flags |= 2;
       tinfo[k] = {row, flags};
     }
     t = t2;

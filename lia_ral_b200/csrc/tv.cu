@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_i8.cuh"
 
 #define LR_CUSOLVER(expr)                                                                  \
   do {                                                                                     \
@@ -42,6 +43,10 @@ struct lr_tv {
   double **d_ptr_A = nullptr, **d_ptr_Tc = nullptr;                      // component pointers
   int *d_info = nullptr;
   cusolverDnHandle_t solver = nullptr;
+  // digit planes (gemm_i8.cu) of the two operands that only change with T: TETt^T [Rp x C] and Ts [R x sv]
+  unsigned char *d_tett_planes = nullptr, *d_ts_planes = nullptr;
+  double *d_tett_scale = nullptr, *d_ts_scale = nullptr;
+  int planes = 0;  // digit planes the two were cut into (0: not prepared, cuBLAS path)
   size_t Rp() const { return (size_t)R * (R + 1) / 2; }
   double *A() const { return d_acc; }  // packed: A_c at d_acc + c * Rp
   double *Cmx() const { return d_acc + (size_t)C * Rp(); }
@@ -408,6 +413,10 @@ void tv_free(lr_tv *tv) {
   cudaFree(tv->d_ptr_A);
   cudaFree(tv->d_ptr_Tc);
   cudaFree(tv->d_info);
+  cudaFree(tv->d_tett_planes);
+  cudaFree(tv->d_ts_planes);
+  cudaFree(tv->d_tett_scale);
+  cudaFree(tv->d_ts_scale);
   if (tv->solver) cusolverDnDestroy(tv->solver);
   delete tv;
 }
@@ -493,16 +502,40 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
   const double one = 1.0, zero = 0.0;
   // packed lower triangles: Lp[nb x Rp] = N_b[nb x C] * TETtp[C x Rp]  (staged in d_Eb), then
   // L = I + unpack(Lp) with a zeroed upper triangle
-  LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, rp, nb, C, &one, tv->d_tettp, rp,
-                        tv->d_N + u0 * C, C, &zero, tv->d_Eb, rp));
-  count_launch();
+  const int s = tv->planes;  // > 0: the INT8 digit GEMM (gemm_i8.cu); 0: cuBLAS fp64 (cross-check)
+  if (s > 0) {
+    DevBuf<unsigned char> pN;
+    DevBuf<double> sN;
+    LR_CUDA(pN.alloc(gemm_i8_panel_bytes(nb, C, s, kI8TileM)));
+    LR_CUDA(sN.alloc(gemm_i8_scale_count(nb, kI8TileM)));
+    lr_status st = gemm_i8_prepare(tv->d_N + u0 * C, (size_t)C, 1, nb, C, s, kI8TileM, pN.p, sN.p);
+    if (st != LR_OK) return st;
+    st = gemm_i8_run(pN.p, sN.p, nb, tv->d_tett_planes, tv->d_tett_scale, rp, C, s, 1.0, 0.0, tv->d_Eb, (size_t)rp);
+    if (st != LR_OK) return st;
+  } else {
+    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, rp, nb, C, &one, tv->d_tettp, rp,
+                          tv->d_N + u0 * C, C, &zero, tv->d_Eb, rp));
+    count_launch();
+  }
   k_unpack_lower<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>((size_t)nb, R, tv->d_Eb, tv->d_Lb,
                                                                    1.0, 0);
   LR_CHECK_LAUNCH();
   // aux[nb x R] = Fc_b[nb x sv] * Ts^T  -> written straight into W
-  LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, nb, (int)tv->sv, &one, tv->d_Ts,
-                        (int)tv->sv, tv->d_F + u0 * tv->sv, (int)tv->sv, &zero, tv->d_W + u0 * R, R));
-  count_launch();
+  if (s > 0) {
+    DevBuf<unsigned char> pF;
+    DevBuf<double> sF;
+    LR_CUDA(pF.alloc(gemm_i8_panel_bytes(nb, (long)tv->sv, s, kI8TileM)));
+    LR_CUDA(sF.alloc(gemm_i8_scale_count(nb, kI8TileM)));
+    lr_status st = gemm_i8_prepare(tv->d_F + u0 * tv->sv, tv->sv, 1, nb, (long)tv->sv, s, kI8TileM, pF.p, sF.p);
+    if (st != LR_OK) return st;
+    st = gemm_i8_run(pF.p, sF.p, nb, tv->d_ts_planes, tv->d_ts_scale, R, (long)tv->sv, s, 1.0, 0.0,
+                     tv->d_W + u0 * R, (size_t)R);
+    if (st != LR_OK) return st;
+  } else {
+    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, nb, (int)tv->sv, &one, tv->d_Ts,
+                          (int)tv->sv, tv->d_F + u0 * tv->sv, (int)tv->sv, &zero, tv->d_W + u0 * R, R));
+    count_launch();
+  }
   lr_status st = chol_batched(tv, tv->d_Lb, R, nb, tv->d_invD, tv->d_Eb,
                               "i-vector posterior precision L");
   if (st != LR_OK) return st;
@@ -556,6 +589,36 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
   return LR_OK;
 }
 
+// Digit planes of the operands that change only with T (after estimateTETt): TETt^T as the [Rp x C]
+// B operand of L = N TETt, and Ts = T o invvar as the [R x sv] B operand of aux = F Ts^T.
+lr_status prepare_t_planes(lr_tv *tv) {
+  Engine &e = engine();
+  const int s = e.tv_gemm == 1 ? 0 : e.tv_planes;
+  if (s != tv->planes) {
+    cudaFree(tv->d_tett_planes);
+    cudaFree(tv->d_ts_planes);
+    cudaFree(tv->d_tett_scale);
+    cudaFree(tv->d_ts_scale);
+    tv->d_tett_planes = tv->d_ts_planes = nullptr;
+    tv->d_tett_scale = tv->d_ts_scale = nullptr;
+    tv->planes = 0;
+    if (s > 0) {
+      const long rp = (long)tv->Rp();
+      LR_CUDA(cudaMalloc(&tv->d_tett_planes, gemm_i8_panel_bytes(rp, tv->C, s, kI8TileN)));
+      LR_CUDA(cudaMalloc(&tv->d_tett_scale, gemm_i8_scale_count(rp, kI8TileN) * sizeof(double)));
+      LR_CUDA(cudaMalloc(&tv->d_ts_planes, gemm_i8_panel_bytes(tv->R, (long)tv->sv, s, kI8TileN)));
+      LR_CUDA(cudaMalloc(&tv->d_ts_scale, gemm_i8_scale_count(tv->R, kI8TileN) * sizeof(double)));
+      tv->planes = s;
+    }
+  }
+  if (s == 0) return LR_OK;
+  const long rp = (long)tv->Rp();
+  lr_status st = gemm_i8_prepare(tv->d_tettp, 1, (size_t)rp, rp, tv->C, s, kI8TileN, tv->d_tett_planes,
+                                 tv->d_tett_scale);
+  if (st != LR_OK) return st;
+  return gemm_i8_prepare(tv->d_Ts, tv->sv, 1, tv->R, (long)tv->sv, s, kI8TileN, tv->d_ts_planes, tv->d_ts_scale);
+}
+
 }  // namespace
 }  // namespace lr
 
@@ -577,11 +640,12 @@ lr_tv *lr_tv_create(int C, int D, int R, size_t U, const double *ubm_mean,
   tv->U = U;
   tv->sv = (size_t)C * D;
   size_t rr = (size_t)R * R;
-  // utterances per posterior batch: 512 MB for the largest of the per-utterance buffers (L / E / Y
+  // utterances per posterior batch: 2 GB for the largest of the per-utterance buffers (L / E / Y
   // hold R x R doubles, invD ceil(R / 64) 64 x 64 blocks -- the larger one at small R), capped at
   // 4096 so that small ranks with many utterances do not over-allocate
   const size_t per_utt = std::max(rr, (size_t)((R + kNB - 1) / kNB) * kNB * kNB) * sizeof(double);
-  tv->batch = (int)std::min<size_t>(std::min<size_t>(U, 4096), std::max<size_t>(32, ((size_t)1 << 29) / per_utt));
+  tv->batch = (int)std::min<size_t>(std::min<size_t>(U, 4096), std::max<size_t>(32, ((size_t)1 << 31) / per_utt));
+  if (tv->batch > 128) tv->batch -= tv->batch % 128;  // whole 128-row tiles / K chunks of the digit GEMM
   const int nbmax = tv->batch;
   auto A = [&](double **p, size_t n) { return cudaMalloc(p, n * sizeof(double)) == cudaSuccess; };
   bool ok = A(&tv->d_N, U * C) && A(&tv->d_F, U * tv->sv) && A(&tv->d_T, R * tv->sv) &&
@@ -754,6 +818,42 @@ lr_status lr_tv_estimate_tett(lr_tv *tv) {
   k_pack_lower<<<grid_for((size_t)tv->C * tv->R * tv->R), 256, 0, e.stream>>>(
       (size_t)tv->C, tv->R, tv->d_tett, tv->d_tettp);
   LR_CHECK_LAUNCH();
+  return prepare_t_planes(tv);
+}
+
+lr_status lr_set_tv_gemm(int which, int planes) {
+  LR_REQUIRE(which == 0 || which == 1, "lr_set_tv_gemm: kernel %d (0 = INT8 digit GEMM, 1 = cuBLAS fp64)", which);
+  LR_REQUIRE(planes == 0 || (planes >= 3 && planes <= kI8MaxSlices), "lr_set_tv_gemm: %d digit planes outside [3, %d]",
+             planes, kI8MaxSlices);
+  engine().tv_gemm = which;
+  if (planes) engine().tv_planes = planes;
+  return LR_OK;
+}
+
+lr_status lr_gemm_digits(size_t M, size_t N, size_t K, const double *A, const double *B, double *Cm, double alpha,
+                         double beta, int planes) {
+  LR_READY();
+  LR_REQUIRE(A && B && Cm && M && N && K, "lr_gemm_digits: null / empty argument");
+  Engine &e = engine();
+  const int s = planes ? planes : e.tv_planes;
+  DevBuf<double> dA, dB, dC, sA, sB;
+  DevBuf<unsigned char> pA, pB;
+  LR_CUDA(dA.alloc(M * K));
+  LR_CUDA(dB.alloc(N * K));
+  LR_CUDA(dC.alloc(M * N));
+  LR_CUDA(pA.alloc(gemm_i8_panel_bytes((long)M, (long)K, s, kI8TileM)));
+  LR_CUDA(pB.alloc(gemm_i8_panel_bytes((long)N, (long)K, s, kI8TileN)));
+  LR_CUDA(sA.alloc(gemm_i8_scale_count((long)M, kI8TileM)));
+  LR_CUDA(sB.alloc(gemm_i8_scale_count((long)N, kI8TileN)));
+  LR_CUDA(cudaMemcpyAsync(dA.p, A, M * K * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  LR_CUDA(cudaMemcpyAsync(dB.p, B, N * K * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  LR_CUDA(cudaMemcpyAsync(dC.p, Cm, M * N * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  lr_status st = gemm_i8_prepare(dA.p, K, 1, (long)M, (long)K, s, kI8TileM, pA.p, sA.p);
+  if (st != LR_OK) return st;
+  if ((st = gemm_i8_prepare(dB.p, K, 1, (long)N, (long)K, s, kI8TileN, pB.p, sB.p)) != LR_OK) return st;
+  if ((st = gemm_i8_run(pA.p, sA.p, (long)M, pB.p, sB.p, (long)N, (long)K, s, alpha, beta, dC.p, N)) != LR_OK) return st;
+  LR_CUDA(cudaMemcpyAsync(Cm, dC.p, M * N * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
   return LR_OK;
 }
 
@@ -799,13 +899,39 @@ lr_status lr_tv_estimate_a_and_c(lr_tv *tv) {
     // accumulated -- the reference's loop runs over the full R x R)
     k_pack_lower<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>((size_t)nb, R, tv->d_Eb, tv->d_Lb);
     LR_CHECK_LAUNCH();
-    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, rp, C, nb, &one, tv->d_Lb, rp,
-                          tv->d_N + u0 * C, C, &one, tv->A(), rp));
-    count_launch();
-    // Cmx[R x sv] += W_b^T Fc_b (:1784-1788)
-    LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)tv->sv, R, nb, &one,
-                          tv->d_F + u0 * tv->sv, (int)tv->sv, Wb, R, &one, tv->Cmx(), (int)tv->sv));
-    count_launch();
+    if (tv->planes > 0) {
+      const int s = tv->planes;
+      {  // rows = components, K = the batch's utterances
+        DevBuf<unsigned char> pNt, pE;
+        DevBuf<double> sNt, sE;
+        LR_CUDA(pNt.alloc(gemm_i8_panel_bytes(C, nb, s, kI8TileM)));
+        LR_CUDA(sNt.alloc(gemm_i8_scale_count(C, kI8TileM)));
+        LR_CUDA(pE.alloc(gemm_i8_panel_bytes(rp, nb, s, kI8TileN)));
+        LR_CUDA(sE.alloc(gemm_i8_scale_count(rp, kI8TileN)));
+        if ((st = gemm_i8_prepare(tv->d_N + u0 * C, 1, (size_t)C, C, nb, s, kI8TileM, pNt.p, sNt.p)) != LR_OK) return st;
+        if ((st = gemm_i8_prepare(tv->d_Lb, 1, (size_t)rp, rp, nb, s, kI8TileN, pE.p, sE.p)) != LR_OK) return st;
+        if ((st = gemm_i8_run(pNt.p, sNt.p, C, pE.p, sE.p, rp, nb, s, 1.0, 1.0, tv->A(), (size_t)rp)) != LR_OK) return st;
+      }
+      {  // Cmx[R x sv] += W_b^T Fc_b (:1784-1788)
+        DevBuf<unsigned char> pWt, pFt;
+        DevBuf<double> sWt, sFt;
+        LR_CUDA(pWt.alloc(gemm_i8_panel_bytes(R, nb, s, kI8TileM)));
+        LR_CUDA(sWt.alloc(gemm_i8_scale_count(R, kI8TileM)));
+        LR_CUDA(pFt.alloc(gemm_i8_panel_bytes((long)tv->sv, nb, s, kI8TileN)));
+        LR_CUDA(sFt.alloc(gemm_i8_scale_count((long)tv->sv, kI8TileN)));
+        if ((st = gemm_i8_prepare(Wb, 1, (size_t)R, R, nb, s, kI8TileM, pWt.p, sWt.p)) != LR_OK) return st;
+        if ((st = gemm_i8_prepare(tv->d_F + u0 * tv->sv, 1, tv->sv, (long)tv->sv, nb, s, kI8TileN, pFt.p, sFt.p)) != LR_OK) return st;
+        if ((st = gemm_i8_run(pWt.p, sWt.p, R, pFt.p, sFt.p, (long)tv->sv, nb, s, 1.0, 1.0, tv->Cmx(), tv->sv)) != LR_OK) return st;
+      }
+    } else {
+      LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, rp, C, nb, &one, tv->d_Lb, rp,
+                            tv->d_N + u0 * C, C, &one, tv->A(), rp));
+      count_launch();
+      // Cmx[R x sv] += W_b^T Fc_b (:1784-1788)
+      LR_CUBLAS(cublasDgemm(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)tv->sv, R, nb, &one,
+                            tv->d_F + u0 * tv->sv, (int)tv->sv, Wb, R, &one, tv->Cmx(), (int)tv->sv));
+      count_launch();
+    }
   }
   LR_CUDA(cudaMemcpyAsync(tv->sumW(), tv->r(), R * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
   return lr_tv_finish_estep(tv, (double)tv->U);
