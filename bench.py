@@ -111,6 +111,51 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+def bind_to_gpu_numa(index):
+    """e2e only: keep the rank's pinned staging memory and its host thread on the NUMA node the GPU's PCIe
+    root port hangs off (eight ranks pulling 2.4 GB/step through one socket's memory controllers and the
+    inter-socket link is what held the round-1 e2e curve at 0.46 efficiency).  Best effort: reports what
+    it could do; never fails the run."""
+    info = {"numa_node": None, "mempolicy": False, "cpus_bound": None, "pcie": None}
+    try:
+        import ctypes
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        try:
+            gen = pynvml.nvmlDeviceGetCurrPcieLinkGeneration(h)
+            width = pynvml.nvmlDeviceGetCurrPcieLinkWidth(h)
+            per_lane = {3: 0.985, 4: 1.969, 5: 3.938, 6: 7.563}.get(int(gen), 0.0)
+            info["pcie"] = {"gen": int(gen), "width": int(width), "raw_gbs": round(per_lane * int(width), 1)}
+        except Exception:
+            pass
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus_bound"] = len(allowed)
+        # set_mempolicy(MPOL_PREFERRED = 1, nodemask): pinned pages are placed when cudaHostAlloc touches them
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        rc = libc.syscall(238, 1, mask, 16 * 64 + 1)
+        info["mempolicy"] = rc == 0
+    except Exception as exc:
+        info["error"] = str(exc)[:120]
+    return info
+
+
 def ivector_rate(torch, capi, dev, U=1024, R=400, reps=3):
     """The metric's second half: i-vectors/s of the classic extraction (estimateW: L = I + N TETt,
     Cholesky, solve) at 2048c/60d, rank 400, on statistics resident in HBM.  Synthetic statistics:
@@ -438,6 +483,7 @@ def main():
     import torch.distributed as dist
     from lia_ral_b200 import capi, dist as lrd
 
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -618,7 +664,13 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": Te * D * 4 + 2 * C * D * 8 * 2,
                     "d2h_bytes_per_step": stat_bytes, "steps": args.e2e_steps,
-                    "mean_llk_per_frame": e2e_llk},
+                    "mean_llk_per_frame": e2e_llk,
+                    # the e2e step is the H2D copy of the step's float32 frames (240 B each) overlapped with the
+                    # kernels: its ceiling is the PCIe link, not the GPU
+                    "h2d_gbs_per_rank": e2e_val / world * (D * 4) / 1e9,
+                    "bound": "PCIe host->device copy of the frames (2.4 GB/step/GPU, staged in 2^18-frame blocks "
+                             "behind the kernels)",
+                    "host_binding": numa},
             "roofline": {"bound": "tensor", "achieved": path_tf, "peak": pk["bf16"], "unit": "TFLOP/s",
                          "frac": path_tf / pk["bf16"],
                          "frac_scope": "PATH: 8 C D flop/frame x frames of the step / ms_per_step (conversion, GMM "

@@ -99,7 +99,8 @@ int ComputeTest(Config &c) {
     const int K = (int)c.getLong("topDistribsCount", 10);
     const bool complete = c.getString("computeLLKWithTopDistribs", "COMPLETE") == "COMPLETE";
     const double minLLK = c.getDouble("minLLK", -200.0), maxLLK = c.getDouble("maxLLK", 200.0);
-    if (c.getLong("worldDecime", 1) != 1) LIA_THROW("worldDecime != 1 is not supported by this engine");
+    const long worldDecime = c.getLong("worldDecime", 1);  // ComputeTest.cpp:111-113
+    if (worldDecime < 1) LIA_THROW("worldDecime must be >= 1");
     XList ndx(c.getParam("ndxFilename"));
     MixtureGD worldM = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
     Gmm world(worldM, true);
@@ -131,9 +132,9 @@ int ComputeTest(Config &c) {
       std::vector<lr_seg> es = toEngineSegs(fs, segs);
       const size_t nOut = segmental ? es.size() : 1;
       std::vector<double> mw(nOut), mc(clients.size() * nOut);
-      LIA_CHECK(lr_compute_test(world.h(), clients.data(), (int)clients.size(), fs.data(), fs.getFeatureCount(),
-                                fs.ld(), es.data(), es.size(), K, complete ? 1 : 0, minLLK, maxLLK,
-                                segmental ? 1 : 0, mw.data(), mc.data()));
+      LIA_CHECK(lr_compute_test_decime(world.h(), clients.data(), (int)clients.size(), fs.data(),
+                                       fs.getFeatureCount(), fs.ld(), es.data(), es.size(), K, complete ? 1 : 0,
+                                       minLLK, maxLLK, segmental ? 1 : 0, (int)worldDecime, mw.data(), mc.data()));
       for (size_t o = 0; o < nOut; o++)
         for (size_t i = 0; i < clients.size(); i++) {
           double llr = mc[i * nOut + o] - mw[o];  // ComputeTest.cpp:196-199

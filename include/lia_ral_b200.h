@@ -155,13 +155,20 @@ lr_status lr_gmm_llk_use_topk(lr_gmm *client, const float *X, size_t T, size_t l
 lr_status lr_gmm_llk(lr_gmm *g, const float *X, size_t T, size_t ldx, double min_llk,
                      double max_llk, double *llk);
 /* The frame loop of ComputeTest() (ComputeTest.cpp:154-199) for one test file: world top-K
- * every frame (worldDecime 1), n_clients client models through USE_TOP_DISTRIBS;
+ * every frame (worldDecime 1; lr_compute_test_decime below for the general case), n_clients client models through USE_TOP_DISTRIBS;
  * mean_llk_world[n_segs_out], mean_llk_client[n_clients * n_segs_out]; per_segment != 0 =
  * segmentalMode (one mean per segment) else one mean over all segments (n_segs_out = 1). */
 lr_status lr_compute_test(lr_gmm *world, lr_gmm *const *clients, int n_clients, const float *X,
                           size_t T, size_t ldx, const lr_seg *segs, size_t n_segs, int K,
                           int complete, double min_llk, double max_llk, int per_segment,
                           double *mean_llk_world, double *mean_llk_client);
+/* The same loop with the reference's worldDecime (ComputeTest.cpp:111-113, 162-165): inside every segment
+ * only frames idxFrame % world_decime == 0 run DETERMINE_TOP_DISTRIBS on the world; the others score the
+ * world AND the clients through USE_TOP_DISTRIBS with the top list (and COMPLETE rest) of the last such frame. */
+lr_status lr_compute_test_decime(lr_gmm *world, lr_gmm *const *clients, int n_clients, const float *X,
+                                 size_t T, size_t ldx, const lr_seg *segs, size_t n_segs, int K,
+                                 int complete, double min_llk, double max_llk, int per_segment,
+                                 int world_decime, double *mean_llk_world, double *mean_llk_client);
 
 /* ------------------------------------------------------------------ Total Variability -----
  * Device twin of the TVAcc object (AccumulateTVStat.h): owns _statN [U x C], _statF

@@ -325,7 +325,7 @@ def frames_mean_cov(X):
 
 
 def compute_test(world, clients, X, segs=None, K=10, complete=True, min_llk=-200.0, max_llk=200.0,
-                 per_segment=False):
+                 per_segment=False, world_decime=1):
     """Frame loop of ComputeTest() for one test file -> (mean_llk_world[n_out],
     mean_llk_client[n_clients, n_out])."""
     X = _f32(X)
@@ -334,10 +334,10 @@ def compute_test(world, clients, X, segs=None, K=10, complete=True, min_llk=-200
     mw = np.empty(n_out)
     mc = np.empty((len(clients), n_out))
     arr = (ct.c_void_p * max(1, len(clients)))(*[c.h.value for c in clients])
-    _check(lib().lr_compute_test(world.h, arr, len(clients), X.ctypes.data_as(c_fp),
-                                 ct.c_size_t(X.shape[0]), ct.c_size_t(X.strides[0] // 4), sa,
-                                 ct.c_size_t(ns), K, int(complete), ct.c_double(min_llk),
-                                 ct.c_double(max_llk), int(per_segment), _d(mw), _d(mc)))
+    _check(lib().lr_compute_test_decime(world.h, arr, len(clients), X.ctypes.data_as(c_fp),
+                                        ct.c_size_t(X.shape[0]), ct.c_size_t(X.strides[0] // 4), sa,
+                                        ct.c_size_t(ns), K, int(complete), ct.c_double(min_llk),
+                                        ct.c_double(max_llk), int(per_segment), int(world_decime), _d(mw), _d(mc)))
     return mw, mc
 
 

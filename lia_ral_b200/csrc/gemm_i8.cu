@@ -30,6 +30,7 @@
 // then one read-modify-write (or fp64 RED adds when the K range is split between CTAs).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "gemm_i8.cuh"
 #include "tc_ptx.cuh"
@@ -163,11 +164,16 @@ struct Bars {
 // one moment share a few B panels and all of A through L2
 struct Sched {
   int mt_count, nt_count, ksplit, nchunk, n_items;
-  __host__ __device__ void get(int it, int &mt, int &nt, int &c0, int &c1) const {
+  int csz;  // CTAs per cluster: one item = csz adjacent column tiles (same A planes, multicast)
+  // `nt` is clamped to the last column tile (a surplus CTA of the cluster recomputes it); live = false
+  // tells its epilogue not to store
+  __host__ __device__ void get(int it, int crank, int &mt, int &nt, int &c0, int &c1, bool &live) const {
     mt = it % mt_count;
     const int rest = it / mt_count;
     const int ks = rest % ksplit;
-    nt = rest / ksplit;
+    nt = (rest / ksplit) * csz + crank;
+    live = nt < nt_count;
+    if (!live) nt = nt_count - 1;
     c0 = (int)((long)nchunk * ks / ksplit);
     c1 = (int)((long)nchunk * (ks + 1) / ksplit);
   }
@@ -192,10 +198,14 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
   sm.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   sm.bar = sm.base + kAStages * kABytes + kBStages * s * kBBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int csz = sched.csz;
+  const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
+  const int first_item = blockIdx.x / csz, item_step = gridDim.x / csz;
+  const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kAStages; i++) {
       mbar_init(sm.a_full(i), 1);
-      mbar_init(sm.a_empty(i), 1);
+      mbar_init(sm.a_empty(i), csz);  // every CTA of the cluster has consumed the multicast plane
     }
     for (int i = 0; i < kBStages; i++) {
       mbar_init(sm.b_full(i), 1);
@@ -208,6 +218,7 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
   if (warp == 2) tmem_alloc(sm.tmem_slot(), 512);
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();  // the peers' barriers exist before anything is multicast at them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot()));
@@ -217,9 +228,10 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
     // ---- producer
     const bool leader = elect_one();
     long aseq = 0, bseq = 0;
-    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x) {
+    for (int it = first_item; it < sched.n_items; it += item_step) {
       int mt, nt, c0, c1;
-      sched.get(it, mt, nt, c0, c1);
+      bool live;
+      sched.get(it, crank, mt, nt, c0, c1, live);
       for (int kc = c0; kc < c1; kc++) {
         const int bst = (int)(bseq % kBStages);
         mbar_wait(sm.b_empty(bst), (uint32_t)(((bseq / kBStages) & 1) ^ 1));
@@ -237,8 +249,13 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
           mbar_wait(sm.a_empty(ast), (uint32_t)(((aseq / kAStages) & 1) ^ 1));
           if (leader) {
             const unsigned char *src = Ap + (((size_t)mt * sched.nchunk + kc) * s + i) * kABytes;
-            mbar_expect_tx(sm.a_full(ast), kABytes);
-            bulk_g2s(sm.a_stage(ast), src, kABytes, sm.a_full(ast));
+            mbar_expect_tx(sm.a_full(ast), kABytes);  // the whole plane: 1 / csz of it from every CTA
+            if (csz > 1) {
+              const uint32_t part = kABytes / csz;
+              bulk_g2s_mc(sm.a_stage(ast) + crank * part, src + (size_t)crank * part, part, sm.a_full(ast), cmask);
+            } else {
+              bulk_g2s(sm.a_stage(ast), src, kABytes, sm.a_full(ast));
+            }
           }
           __syncwarp();
         }
@@ -248,9 +265,10 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
     // ---- UMMA issuer
     const bool leader = elect_one();
     long aseq = 0, bseq = 0, tile_seq = 0;
-    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x, tile_seq++) {
+    for (int it = first_item; it < sched.n_items; it += item_step, tile_seq++) {
       int mt, nt, c0, c1;
-      sched.get(it, mt, nt, c0, c1);
+      bool live;
+      sched.get(it, crank, mt, nt, c0, c1, live);
       if (tile_seq > 0) mbar_wait(sm.acc_empty(), (uint32_t)((tile_seq - 1) & 1));
       tc_fence_after();
       uint32_t touched = 0;  // classes that already hold a product of this item
@@ -273,7 +291,8 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
               for (int kk = 0; kk < 4; kk++)
                 umma_ss_i8(dcol, desc_add(adesc, kk * 32), desc_add(bdesc, kk * 32), idesc, kk ? 1u : first);
             }
-            umma_commit(sm.a_empty(ast));
+            if (csz > 1) umma_commit_mc(sm.a_empty(ast), cmask);
+            else umma_commit(sm.a_empty(ast));
           }
           __syncwarp();
           touched |= ((1u << (s - i)) - 1u) << i;
@@ -290,9 +309,10 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     long tile_seq = 0;
     const bool split = sched.ksplit > 1;
-    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x, tile_seq++) {
+    for (int it = first_item; it < sched.n_items; it += item_step, tile_seq++) {
       int mt, nt, c0, c1;
-      sched.get(it, mt, nt, c0, c1);
+      bool live;
+      sched.get(it, crank, mt, nt, c0, c1, live);
       mbar_wait(sm.acc_full(), (uint32_t)(tile_seq & 1));
       tc_fence_after();
       double v[32];
@@ -310,7 +330,7 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
       if (lane == 0) mbar_arrive(sm.acc_empty());
       const long m = (long)mt * kI8TileM + q * 32 + lane;
       const long n_base = (long)nt * kI8TileN + h * 32;
-      if (m < M && n_base < N) {
+      if (live && m < M && n_base < N) {
         const double sa = scaleA[m] * alpha * (1.0 / 4096.0);  // digit weights 2^-6 x 2^-6
         double *dst = Cout + (size_t)m * ldc + n_base;
         const bool full = n_base + 32 <= N;
@@ -342,6 +362,7 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
   }
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast at it
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -419,7 +440,13 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
   int ksplit = ceil_div(sc.nchunk, 256);
   if (tiles < 2L * e.sm_count) ksplit = std::max<int>(ksplit, std::min<long>(sc.nchunk / 4, ceil_div(2L * e.sm_count, tiles)));
   sc.ksplit = std::max(1, std::min(ksplit, sc.nchunk));
-  sc.n_items = (int)(tiles * sc.ksplit);
+  // clusters of csz CTAs take csz adjacent column tiles and share every A plane by multicast
+  int csz = e.i8_cluster;
+  if (const char *env = getenv("LR_I8_CLUSTER")) csz = atoi(env);  // A/B switch (temporary)
+  if (csz != 1 && csz != 2 && csz != 4) csz = 1;
+  if (sc.nt_count < 2) csz = 1;
+  sc.csz = csz;
+  sc.n_items = sc.mt_count * ceil_div(sc.nt_count, csz) * sc.ksplit;
   if (sc.ksplit > 1) {
     LR_REQUIRE(beta == 0.0 || beta == 1.0, "gemm_i8: beta must be 0 or 1 when the K range is split");
     if (beta == 0.0) {
@@ -427,10 +454,36 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
       LR_CHECK_LAUNCH();
     }
   }
-  const int grid = std::min(e.sm_count, sc.n_items);
-  k_gemm_i8<<<grid, kThreads, smem_bytes(s), e.stream>>>(sc, s, dAp, dBp, dAscale, dBscale, dC, ldc, M, N, alpha,
-                                                         beta);
-  LR_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes(s);
+  cfg.stream = e.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csz;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = e.sm_count / csz;
+  if (csz > 1) {  // whole clusters that fit the GPCs (one CTA per SM)
+    int &cached = e.i8_max_clusters[csz];
+    if (cached == 0) {
+      cfg.gridDim = dim3((unsigned)(csz * 64));
+      cfg.dynamicSmemBytes = smem_bytes(kI8MaxSlices);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, k_gemm_i8, &cfg) == cudaSuccess && n > 0) cached = n;
+      else {
+        cudaGetLastError();
+        cached = max_clusters;
+      }
+      cfg.dynamicSmemBytes = smem_bytes(s);
+    }
+    max_clusters = std::min(max_clusters, cached);
+  }
+  cfg.gridDim = dim3((unsigned)(csz * std::min(max_clusters, sc.n_items)));
+  LR_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_i8, sc, s, dAp, dBp, dAscale, dBscale, dC, ldc, M, N, alpha, beta));
+  count_launch();
   return LR_OK;
 }
 

@@ -347,6 +347,21 @@ lr_status lr_gmm_llk(lr_gmm *g, const float *X, size_t T, size_t ldx, double min
 }
 
 // world top-K over a device block; outputs stay on the device in scratch slots
+// worldDecime (ComputeTest.cpp:111-113, 162): frame t of a block that starts on the grid
+__global__ void k_decime_propagate(long P, int K, int decime, unsigned *__restrict__ idx, double *__restrict__ rest) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P) return;
+  const long off = t % decime;
+  if (off == 0) return;
+  const long src = t - off;
+  for (int k = 0; k < K; k++) idx[t * K + k] = idx[src * K + k];
+  rest[t] = rest[src];
+}
+__global__ void k_decime_select(long P, int decime, const double *__restrict__ use, double *__restrict__ llk) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < P && t % decime != 0) llk[t] = use[t];
+}
+
 static lr_status topk_block(lr_gmm *world, const float *dX, size_t ldx, long P, int K, int complete,
                             double min_llk, double max_llk, double **d_llk, unsigned **d_idx,
                             double **d_top, double **d_rest, double **d_restw) {
@@ -437,7 +452,19 @@ lr_status lr_compute_test(lr_gmm *world, lr_gmm *const *clients, int n_clients, 
                           size_t T, size_t ldx, const lr_seg *segs, size_t n_segs, int K,
                           int complete, double min_llk, double max_llk, int per_segment,
                           double *mean_llk_world, double *mean_llk_client) {
+  return lr_compute_test_decime(world, clients, n_clients, X, T, ldx, segs, n_segs, K, complete, min_llk,
+                                max_llk, per_segment, 1, mean_llk_world, mean_llk_client);
+}
+
+lr_status lr_compute_test_decime(lr_gmm *world, lr_gmm *const *clients, int n_clients, const float *X,
+                                 size_t T, size_t ldx, const lr_seg *segs, size_t n_segs, int K,
+                                 int complete, double min_llk, double max_llk, int per_segment,
+                                 int world_decime, double *mean_llk_world, double *mean_llk_client) {
   LR_READY();
+  LR_REQUIRE(world_decime >= 1 && world_decime <= 4096, "lr_compute_test: worldDecime %d outside [1, 4096]",
+             world_decime);
+  // blocks start on the decimation grid of their segment (idxFrame % worldDecime == 0, ComputeTest.cpp:162)
+  const long block = kTopkBlock - kTopkBlock % world_decime;
   LR_REQUIRE(world && X && mean_llk_world && (n_clients == 0 || (clients && mean_llk_client)),
              "lr_compute_test: null argument");
   LR_REQUIRE(ldx >= (size_t)world->D && T > 0, "lr_compute_test: bad T / ldx");
@@ -460,8 +487,8 @@ lr_status lr_compute_test(lr_gmm *world, lr_gmm *const *clients, int n_clients, 
   // frames are scored segment by segment in blocks (frames outside the segments are never read)
   for (size_t s = 0; s < n_segs; s++) {
     size_t o = per_segment ? s : 0;
-    for (long b0 = segs[s].begin; b0 < segs[s].begin + segs[s].length; b0 += kTopkBlock) {
-      long b1 = std::min<long>(segs[s].begin + segs[s].length, b0 + kTopkBlock), P = b1 - b0;
+    for (long b0 = segs[s].begin; b0 < segs[s].begin + segs[s].length; b0 += block) {
+      long b1 = std::min<long>(segs[s].begin + segs[s].length, b0 + block), P = b1 - b0;
       float *dX = (float *)scratch_get(kSlotX0, (size_t)kTopkBlock * ldx * sizeof(float));
       if (!dX) return LR_ERR_CUDA;
       LR_CUDA(cudaMemcpyAsync(dX, X + (size_t)b0 * ldx, (size_t)P * ldx * sizeof(float),
@@ -471,11 +498,23 @@ lr_status lr_compute_test(lr_gmm *world, lr_gmm *const *clients, int n_clients, 
       lr_status st = topk_block(world, dX, ldx, P, K, complete, min_llk, max_llk, &d_llk, &d_idx,
                                 &d_top, &d_rest, &d_restw);
       if (st != LR_OK) return st;
+      FrameList fl{dX, ldx, nullptr, P};
+      if (world_decime > 1) {
+        // frames off the grid keep the top list (and the COMPLETE rest) of the last grid frame, and the
+        // world itself is scored through USE_TOP_DISTRIBS there (ComputeTest.cpp:162-165)
+        k_decime_propagate<<<ceil_div(P, 256), 256, 0, e.stream>>>(P, K, world_decime, d_idx, d_rest);
+        LR_CHECK_LAUNCH();
+        double *d_use = (double *)scratch_get(kSlotSpans, (size_t)P * sizeof(double));
+        if (!d_use) return LR_ERR_CUDA;
+        st = gmm_use_topk(world, fl, K, d_idx, d_rest, complete, min_llk, max_llk, d_use);
+        if (st != LR_OK) return st;
+        k_decime_select<<<ceil_div(P, 256), 256, 0, e.stream>>>(P, world_decime, d_use, d_llk);
+        LR_CHECK_LAUNCH();
+      }
       h_w.resize(P);
       LR_CUDA(cudaMemcpyAsync(h_w.data(), d_llk, P * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
       double *d_cl = (double *)scratch_get(kSlotTmpB, (size_t)P * std::max(1, n_clients) * sizeof(double));
       if (!d_cl) return LR_ERR_CUDA;
-      FrameList fl{dX, ldx, nullptr, P};
       for (int i = 0; i < n_clients; i++) {
         st = gmm_use_topk(clients[i], fl, K, d_idx, d_rest, complete, min_llk, max_llk,
                           d_cl + (size_t)i * P);

@@ -113,6 +113,62 @@ __global__ void k_unpack_lower(size_t n, int R, const double *__restrict__ packe
   }
 }
 
+// estimateTETt (AccumulateTVStat.cpp:777-805): TETt_c[i, j] = sum_d (T o invvar)[i, cD + d] T[j, cD + d],
+// written straight into the packed lower triangles [C x Rp] (only the block pairs bj <= bi are
+// computed: half the reference's R x R loop, no full-matrix round trip).  One CTA per (64 x 64 tile
+// pair, component); 4 x 4 outputs per thread, K chunks of 32 through shared memory.
+constexpr int kTtTile = 64, kTtK = 32;
+__global__ void __launch_bounds__(256)
+k_tett_packed(int R, int D, size_t sv, const double *__restrict__ Ts, const double *__restrict__ T,
+              double *__restrict__ out /*[C x Rp]*/) {
+  __shared__ double As[kTtTile][kTtK + 1], Bs[kTtTile][kTtK + 1];
+  const int c = blockIdx.y;
+  int bi = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) bi++;
+  while (bi * (bi + 1) / 2 > (int)blockIdx.x) bi--;
+  const int bj = blockIdx.x - bi * (bi + 1) / 2;
+  const int i0 = bi * kTtTile, j0 = bj * kTtTile;
+  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+  const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 8;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < D; k0 += kTtK) {
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const int k = k0 + lk + e;
+      const bool kin = k < D;
+      As[lr][lk + e] = (kin && i0 + lr < R) ? Ts[(size_t)(i0 + lr) * sv + (size_t)c * D + k] : 0.0;
+      Bs[lr][lk + e] = (kin && j0 + lr < R) ? T[(size_t)(j0 + lr) * sv + (size_t)c * D + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kTtK; k++) {
+      double a[4], b[4];
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        a[x] = As[ti + 16 * x][k];
+        b[x] = Bs[tj * 4 + x][k];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int y = 0; y < 4; y++) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+  const size_t rp = (size_t)R * (R + 1) / 2;
+#pragma unroll
+  for (int y = 0; y < 4; y++) {
+    const int j = j0 + tj * 4 + y;
+    if (j >= R) continue;
+    double *col = out + (size_t)c * rp + packed_off(R, j);
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+      const int i = i0 + ti + 16 * x;
+      if (i < R && i >= j) col[i - j] = acc[x][y];
+    }
+  }
+}
+
 // E[b] += w_b w_b^T  (Linv += y y^T, AccumulateTVStat.cpp:1766-1768)
 __global__ void k_rank1(int nb, int R, const double *__restrict__ W, double *__restrict__ E) {
   size_t total = (size_t)nb * R * R;
@@ -120,6 +176,15 @@ __global__ void k_rank1(int nb, int R, const double *__restrict__ W, double *__r
        i += (size_t)gridDim.x * blockDim.x) {
     size_t b = i / ((size_t)R * R), e = i - b * (size_t)R * R;
     E[i] += W[b * R + e / R] * W[b * R + e % R];
+  }
+}
+
+// column-major R x R: upper triangle <- lower triangle
+__global__ void k_mirror_lower(int R, double *__restrict__ M) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < R * R) {
+    int col = e / R, row = e - col * R;
+    if (row < col) M[e] = M[(size_t)row * R + col];
   }
 }
 
@@ -213,7 +278,8 @@ k_chol_solve(int n, const double *__restrict__ Lall, size_t stride, double *__re
 //   L[k1:, k] = A[k1:, k] invD_kk^T                  (DGEMM, through a panel buffer)
 // The diagonal-block inverses are kept: the explicit inverse of the E-step reuses them.
 constexpr int kNB = 64;
-__global__ void __launch_bounds__(kNB)
+constexpr int kDiagThreads = 4 * kNB;  // four lanes per row / column (adjacent lanes of one warp)
+__global__ void __launch_bounds__(kDiagThreads)
 k_diag_chol_inv(int n, double *__restrict__ Lall, size_t stride, double *__restrict__ invD,
                 int nblk, int blk, int *__restrict__ bad) {
   extern __shared__ double dsm[];
@@ -223,48 +289,47 @@ k_diag_chol_inv(int n, double *__restrict__ Lall, size_t stride, double *__restr
   const int mat = blockIdx.x;
   const int k0 = blk * kNB, nb = min(kNB, n - k0);
   double *L = Lall + (size_t)mat * stride;
-  const int j = threadIdx.x;
-  if (j == 0) fail_flag = 0;
-  for (int c = 0; c < nb; c++)
+  const int j = threadIdx.x >> 2, q = threadIdx.x & 3;
+  if (threadIdx.x == 0) fail_flag = 0;
+  for (int c = q; c < nb; c += 4)
     if (j < nb) Ls[j][c] = (j >= c) ? L[(size_t)(k0 + c) * n + k0 + j] : 0.0;  // Ls[row][col]
   __syncthreads();
-  // right-looking Cholesky of the block: thread j owns row j
+  // right-looking Cholesky of the block: the four lanes of row j share its trailing update
   for (int c = 0; c < nb; c++) {
-    if (j == c) {
-      double d = Ls[c][c];
-      if (!(d > 0.0)) {
-        fail_flag = 1;
-        d = 1.0;
-      }
-      Ls[c][c] = sqrt(d);
+    double d = Ls[c][c];
+    if (!(d > 0.0)) {
+      if (threadIdx.x == 0) fail_flag = 1;
+      d = 1.0;
+    }
+    const double s = sqrt(d);
+    const double ljc = (j > c && j < nb) ? Ls[j][c] / s : 0.0;
+    __syncthreads();  // everyone has read column c as it was
+    if (q == 0) {
+      if (j == c) Ls[c][c] = s;
+      else if (j > c && j < nb) Ls[j][c] = ljc;
     }
     __syncthreads();
-    if (j > c && j < nb) Ls[j][c] /= Ls[c][c];
-    __syncthreads();
-    if (j > c && j < nb) {
-      const double ljc = Ls[j][c];
-      for (int k = c + 1; k <= j; k++) Ls[j][k] -= ljc * Ls[k][c];
-    }
+    if (j > c && j < nb)
+      for (int k = c + 1 + q; k <= j; k += 4) Ls[j][k] -= ljc * Ls[k][c];
     __syncthreads();
   }
-  if (j == 0 && fail_flag) atomicExch(bad, mat + 1);
-  for (int c = 0; c < nb; c++)
+  if (threadIdx.x == 0 && fail_flag) atomicExch(bad, mat + 1);
+  for (int c = q; c < nb; c += 4)
     if (j < nb && j >= c) L[(size_t)(k0 + c) * n + k0 + j] = Ls[j][c];
-  // inverse of the block factor: thread j computes column j by forward substitution
-  if (j < nb) {
-    for (int i = 0; i < nb; i++) {
-      double v = (i == j) ? 1.0 : 0.0;
-      if (i < j) {
-        Xs[i][j] = 0.0;
-        continue;
-      }
-      for (int k = j; k < i; k++) v -= Ls[i][k] * Xs[k][j];
-      Xs[i][j] = v / Ls[i][i];
-    }
+  // inverse of the block factor: the four lanes of column j split the dot product of the forward
+  // substitution (they sit in one warp: shuffles + __syncwarp, no block barrier)
+  for (int i = 0; i < nb; i++) {
+    double v = 0.0;
+    if (j < nb && i > j)
+      for (int k = j + q; k < i; k += 4) v -= Ls[i][k] * Xs[k][j];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (q == 0 && j < nb) Xs[i][j] = i < j ? 0.0 : ((i == j ? 1.0 : 0.0) + v) / Ls[i][i];
+    __syncwarp();
   }
   __syncthreads();
   double *out = invD + ((size_t)mat * nblk + blk) * kNB * kNB;  // column-major, ld = kNB
-  for (int c = 0; c < kNB; c++) out[(size_t)c * kNB + j] = (j < nb && c < nb) ? Xs[j][c] : 0.0;
+  for (int c = q; c < kNB; c += 4) out[(size_t)c * kNB + j] = (j < nb && c < nb) ? Xs[j][c] : 0.0;
 }
 
 // dst[mat][0:rows, 0:cols] = src[mat][0:rows, 0:cols]  (column-major, own ld / stride each)
@@ -468,7 +533,7 @@ lr_status chol_batched(lr_tv *tv, double *Lb, int n, int nb, double *invD, doubl
                                           Lb + (size_t)k0 * n + k0, n, (long long)rr, nb));
       count_launch();
     }
-    k_diag_chol_inv<<<nb, kNB, diag_smem, e.stream>>>(n, Lb, rr, invD, nblk, k, bad);
+    k_diag_chol_inv<<<nb, kDiagThreads, diag_smem, e.stream>>>(n, Lb, rr, invD, nblk, k, bad);
     LR_CHECK_LAUNCH();
     if (m2 > 0) {
       const long long sP = (long long)n * kNB;
@@ -574,17 +639,23 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
         tv->d_Yb + (size_t)r0 * R + r0, R, rr);
     LR_CHECK_LAUNCH();
   }
-  // Linv = Y^T Y  -> Eb
-  LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, R, R, &one, tv->d_Yb, R,
-                                      (long long)rr, tv->d_Yb, R, (long long)rr, &zero, tv->d_Eb, R,
-                                      (long long)rr, nb));
+  // Linv = Y^T Y -> Eb, LOWER TRIANGLE ONLY, block column by block column: Y is lower triangular, so
+  // Linv[c0:R, c0:c0+nbi] = Y[c0:R, c0:R]^T Y[c0:R, c0:c0+nbi] (a third of the full product's work; the
+  // strict upper triangle of Eb keeps whatever the inverse left there and is never read)
+  for (int i = 0; i < nblk; i++) {
+    const int c0 = i * kNB, nbi = std::min(kNB, R - c0), m = R - c0;
+    const double *Ysub = tv->d_Yb + (size_t)c0 * R + c0;
+    LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, m, nbi, m, &one, Ysub, R,
+                                        (long long)rr, Ysub, R, (long long)rr, &zero,
+                                        tv->d_Eb + (size_t)c0 * R + c0, R, (long long)rr, nb));
+    count_launch();
+  }
+  // W_b = Linv_b aux_b = Y^T (Y aux): aux sits in W; t = Y aux goes through Lb's first nb*R doubles
+  LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, R, 1, R, &one, tv->d_Yb, R,
+                                      (long long)rr, tv->d_W + u0 * R, R, R, &zero, tv->d_Lb, R, R, nb));
   count_launch();
-  // W_b = Linv_b aux_b : aux currently sits in W; go through Lb's first nb*R doubles as scratch
-  LR_CUDA(cudaMemcpyAsync(tv->d_Lb, tv->d_W + u0 * R, (size_t)nb * R * sizeof(double),
-                          cudaMemcpyDeviceToDevice, e.stream));
-  LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_N, CUBLAS_OP_N, R, 1, R, &one, tv->d_Eb, R,
-                                      (long long)rr, tv->d_Lb, R, R, &zero, tv->d_W + u0 * R, R, R,
-                                      nb));
+  LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, R, 1, R, &one, tv->d_Yb, R,
+                                      (long long)rr, tv->d_Lb, R, R, &zero, tv->d_W + u0 * R, R, R, nb));
   count_launch();
   return LR_OK;
 }
@@ -805,19 +876,16 @@ lr_status lr_tv_estimate_tett(lr_tv *tv) {
   LR_READY();
   LR_REQUIRE(tv, "lr_tv_estimate_tett: null handle");
   Engine &e = engine();
-  const double one = 1.0, zero = 0.0;
   k_scale_cols<<<grid_for((size_t)tv->R * tv->sv), 256, 0, e.stream>>>(tv->R, tv->sv, tv->d_T,
                                                                        tv->d_invvar, tv->d_Ts);
   LR_CHECK_LAUNCH();
-  // TETt_c = (T_c o invvar_c) T_c^T : column-major view of the row-major slice T[:, cD:(c+1)D]
-  // is the D x R matrix T_c^T with leading dimension C*D.
-  LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_T, CUBLAS_OP_N, tv->R, tv->R, tv->D, &one,
-                                      tv->d_Ts, (int)tv->sv, tv->D, tv->d_T, (int)tv->sv, tv->D,
-                                      &zero, tv->d_tett, tv->R, (long long)tv->R * tv->R, tv->C));
-  count_launch();
-  k_pack_lower<<<grid_for((size_t)tv->C * tv->R * tv->R), 256, 0, e.stream>>>(
-      (size_t)tv->C, tv->R, tv->d_tett, tv->d_tettp);
-  LR_CHECK_LAUNCH();
+  // TETt_c = (T_c o invvar_c) T_c^T, lower triangles only, packed
+  {
+    const int nblk = (tv->R + kTtTile - 1) / kTtTile;
+    dim3 grid((unsigned)(nblk * (nblk + 1) / 2), (unsigned)tv->C);
+    k_tett_packed<<<grid, 256, 0, e.stream>>>(tv->R, tv->D, tv->sv, tv->d_Ts, tv->d_T, tv->d_tettp);
+    LR_CHECK_LAUNCH();
+  }
   return prepare_t_planes(tv);
 }
 
@@ -933,6 +1001,9 @@ lr_status lr_tv_estimate_a_and_c(lr_tv *tv) {
       count_launch();
     }
   }
+  // only the lower triangles of the E_b were formed: mirror the sum
+  k_mirror_lower<<<ceil_div((long)rr, 256), 256, 0, e.stream>>>(R, tv->Rm());
+  LR_CHECK_LAUNCH();
   LR_CUDA(cudaMemcpyAsync(tv->sumW(), tv->r(), R * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
   return lr_tv_finish_estep(tv, (double)tv->U);
 }

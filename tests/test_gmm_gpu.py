@@ -236,6 +236,24 @@ def test_use_topk_and_compute_test(capi, oracle, case):
     # reference fixture property (ComputeTest/test/test1.validate.res): client == world => LLR 0
     mw, mc = capi.compute_test(world, [world], X, K=K, complete=True)
     assert abs(mc[0, 0] - mw[0]) < 1e-12
+    # worldDecime (ComputeTest.cpp:111-113, 162-165): inside every segment only frames idxFrame % 3 == 0 pick
+    # the top list; the others reuse it (and its COMPLETE rest) for the world and for the clients
+    dec = 3
+    src = np.arange(T)
+    for (b0, n) in segs:
+        r = np.arange(n)
+        src[b0:b0 + n] = b0 + r - r % dec
+    idx_d, rest_d = idx[src], rest[src]
+    on_grid = src == np.arange(T)
+    llk_wd = np.where(on_grid, llk_w, oracle.llk_use_top(o_w, X, idx_d, rest_d, True))
+    mw, mc = capi.compute_test(world, clients, X, segs=segs, K=K, complete=True, per_segment=True,
+                               world_decime=dec)
+    for o_i, sel in enumerate([np.r_[0:a], np.r_[b:b + c]]):
+        assert abs(mw[o_i] - llk_wd[sel].mean()) < 1e-4 * abs(llk_wd[sel].mean())
+        for i, oc in enumerate(o_cl):
+            ref = oracle.llk_use_top(oc, X, idx_d, rest_d, True)[sel].mean()
+            assert abs((mc[i, o_i] - mw[o_i]) - (ref - llk_wd[sel].mean())) < 2e-4
+    assert abs(mw[0] - llk_w[0:a].mean()) > 1e-9   # decimation changes the world score
 
 
 def test_gmmtokenizer_golden_on_gpu(capi, golden_dir):
