@@ -165,6 +165,18 @@ struct EmAcc {
 };
 double accumulateStatEM(const FeatureServer &fs, const Gmm &g, const SegCluster &segs, EmAcc &acc,
                         double weight = 1.0);  // AccumulateStat.cpp:131
+// one input stream of TrainWorld (inputStreamList / weightStreamList, TrainWorld.cpp:120-141): its
+// feature server, its selected segments and its weight in the final model (default 1 / nbStream)
+struct TrainStream {
+  const FeatureServer *fs;
+  SegCluster segs;
+  double weight;
+};
+void computeMeanCov(const std::vector<TrainStream> &streams, std::vector<double> &mean, std::vector<double> &cov);
+void mixtureInit(const std::vector<TrainStream> &streams, const std::vector<double> &globalCov, const Config &c,
+                 MixtureGD &world);
+void trainModel(const Config &c, const std::vector<TrainStream> &streams, const std::vector<double> &globalCov,
+                MixtureGD &world, const TrainCfg &cfg);  // trainModelStream, TrainTools.cpp:1030-1110
 void computeMeanCov(const FeatureServer &fs, const SegCluster &segs, std::vector<double> &mean,
                     std::vector<double> &cov);  // TrainTools.cpp:593-602
 void mixtureInit(const FeatureServer &fs, const SegCluster &segs, const std::vector<double> &globalCov,

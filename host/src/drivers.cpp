@@ -1,5 +1,6 @@
 // drivers.cpp -- int Foo(Config&) entry points with the reference programs' parameter names and
 // output formats.  Errors follow the reference: catch, print e.toString(), return 0.
+#include <memory>
 #include <algorithm>
 #include <fstream>
 #include <iostream>
@@ -28,33 +29,60 @@ int TrainWorld(Config &c) {
     const std::string out = c.getParam("outputWorldFilename");
     const std::string label = c.getParam("labelSelectedFrames");
     TrainCfg cfg(c);
-    // single input stream: inputFeatureFilename is a feature file or a list of feature files
-    std::vector<std::string> files;
-    const std::string in = c.getParam("inputFeatureFilename");
-    if (in.size() > 4 && in.compare(in.size() - 4, 4, ".lst") == 0)
-      files = XList(in).allElements();
-    else
-      files.push_back(in);
-    FeatureServer fs(c, files);
-    SegCluster segs = selectedSegments(c, fs, label);
-    if (segs.empty()) LIA_THROW("TrainWorld error: no frame selected with label " + label);
+    // one stream (inputFeatureFilename: a feature file or a list of feature files) or several
+    // (inputStreamList: one list per stream, weightStreamList: their weights; TrainWorld.cpp:120-141)
+    std::vector<std::string> streamNames;
+    std::vector<double> weights;
+    if (c.existsParam("inputStreamList")) {
+      streamNames = XList(c.getParam("inputStreamList")).allElements();
+      if (streamNames.empty()) LIA_THROW("TrainWorld error:no input stream");
+      weights.assign(streamNames.size(), 1.0 / (double)streamNames.size());
+      if (c.existsParam("weightStreamList")) {
+        std::vector<std::string> w = XList(c.getParam("weightStreamList")).allElements();
+        if (w.size() != streamNames.size())
+          LIA_THROW("TrainWorld error: number of weigths differs than number of input streams");
+        for (size_t i = 0; i < w.size(); i++) weights[i] = std::stod(w[i]);
+      }
+    } else {
+      streamNames.push_back(c.getParam("inputFeatureFilename"));
+      weights.push_back(1.0);
+    }
+    std::vector<std::unique_ptr<FeatureServer>> servers;
+    std::vector<TrainStream> streams;
+    long nFrames = 0;
+    for (size_t i = 0; i < streamNames.size(); i++) {
+      const std::string &in = streamNames[i];
+      std::vector<std::string> files;
+      if (in.size() > 4 && in.compare(in.size() - 4, 4, ".lst") == 0)
+        files = XList(in).allElements();
+      else
+        files.push_back(in);
+      servers.emplace_back(new FeatureServer(c, files));
+      SegCluster segs = selectedSegments(c, *servers.back(), label);
+      if (segs.empty()) LIA_THROW("TrainWorld error: no frame selected with label " + label + " in stream " + in);
+      nFrames += totalFrame(segs);
+      streams.push_back(TrainStream{servers.back().get(), segs, weights[i]});
+    }
+    const int vectSize = servers[0]->getVectSize();
     std::vector<double> gMean, gCov;
     if (c.getBool("use01", false)) {
-      gMean.assign(fs.getVectSize(), 0.0);
-      gCov.assign(fs.getVectSize(), 1.0);
+      gMean.assign(vectSize, 0.0);
+      gCov.assign(vectSize, 1.0);
     } else {
-      computeMeanCov(fs, segs, gMean, gCov);
+      computeMeanCov(streams, gMean, gCov);
     }
     MixtureGD world;
     if (c.existsParam("inputWorldFilename")) {
       world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
     } else {
-      world.resize((int)c.getLong("mixtureDistribCount"), fs.getVectSize());
-      mixtureInit(fs, segs, gCov, c, world);  // (deterministic: every rank builds the same initial model)
+      world.resize((int)c.getLong("mixtureDistribCount"), vectSize);
+      mixtureInit(streams, gCov, c, world);  // (deterministic: every rank builds the same initial model)
       if (c.getBool("saveInitModel", true) && Shard::get().rank == 0) world.saveFromConfig(out + "init", c);
     }
-    if (verbose) std::cout << "Train world model: " << world.C << " components, " << totalFrame(segs) << " frames" << std::endl;
-    trainModel(c, fs, segs, gCov, world, cfg);
+    if (verbose)
+      std::cout << "Train world model: " << world.C << " components, " << streams.size() << " stream(s), " << nFrames
+                << " frames" << std::endl;
+    trainModel(c, streams, gCov, world, cfg);
     if (Shard::get().rank == 0) world.saveFromConfig(out, c);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;

@@ -75,47 +75,72 @@ double accumulateStatEM(const FeatureServer &fs, const Gmm &g, const SegCluster 
   return llk;
 }
 
-void computeMeanCov(const FeatureServer &fs, const SegCluster &segs, std::vector<double> &mean,
-                    std::vector<double> &cov) {
-  // FrameAccGD over the selected frames: gather them (labels may skip frames), then one device pass
-  const int D = fs.getVectSize();
+void computeMeanCov(const std::vector<TrainStream> &streams, std::vector<double> &mean, std::vector<double> &cov) {
+  // one FrameAccGD over the selected frames of every stream (TrainTools.cpp:593-602): gather them
+  // (labels may skip frames), then one device pass
+  if (streams.empty()) LIA_THROW("computeMeanCov: no input stream");
+  const int D = streams[0].fs->getVectSize();
   std::vector<float> sel;
-  for (auto &s : segs) {
-    const float *p = fs.data() + (fs.getFirstFeatureIndexOfASource(s.source) + s.begin) * fs.ld();
-    sel.insert(sel.end(), p, p + (size_t)s.length * D);
-  }
+  for (const TrainStream &st : streams)
+    for (auto &s : st.segs) {
+      const float *p = st.fs->data() + (st.fs->getFirstFeatureIndexOfASource(s.source) + s.begin) * st.fs->ld();
+      if ((int)st.fs->ld() == D) {
+        sel.insert(sel.end(), p, p + (size_t)s.length * D);
+      } else {
+        for (long t = 0; t < s.length; t++) sel.insert(sel.end(), p + (size_t)t * st.fs->ld(), p + (size_t)t * st.fs->ld() + D);
+      }
+    }
   if (sel.empty()) LIA_THROW("computeMeanCov: no selected frame");
   mean.assign(D, 0.0);
   cov.assign(D, 0.0);
   LIA_CHECK(lr_frames_mean_cov(sel.data(), sel.size() / D, D, D, mean.data(), cov.data()));
 }
 
-void mixtureInit(const FeatureServer &fs, const SegCluster &segs, const std::vector<double> &globalCov,
+void computeMeanCov(const FeatureServer &fs, const SegCluster &segs, std::vector<double> &mean,
+                    std::vector<double> &cov) {
+  computeMeanCov(std::vector<TrainStream>{TrainStream{&fs, segs, 1.0}}, mean, cov);
+}
+
+void mixtureInit(const std::vector<TrainStream> &streams, const std::vector<double> &globalCov,
                  const Config &c, MixtureGD &world) {
   // mean of randomly picked 3..7-frame chunks per component, cov = global cov, equal weights
+  // (TrainTools.cpp:674-766; every stream contributes nbFrameToSelect x weight frames per component)
   const long minLen = c.getLong("baggedMinimalLength", 3), maxLen = c.getLong("baggedMaximalLength", 7);
   const double nbFrameToSelect = (double)c.getLong("nbFrameToSelect", 50);
   const int C = world.C, D = world.D;
-  const long total = totalFrame(segs);
-  double proba = nbFrameToSelect / (double)std::max(1L, total);
   std::vector<double> sum((size_t)C * D, 0.0), cnt(C, 0.0);
-  srand(100 + 1);  // ((stream+1)*100)+(baggedIt+1) for stream 0, iteration 0 (TrainTools.cpp:737)
-  // one pass over the segments, each chunk assigned to a random component when selected
-  for (const Seg &seg : segs) {
-    long begin = seg.begin, left = seg.length;
-    const size_t first = fs.getFirstFeatureIndexOfASource(seg.source);
-    while (left > 0) {
-      long length = std::min(std::min(std::max(left, minLen), maxLen), left);
-      for (int k = 0; k < C; k++) {
-        if (!baggedFrame(proba)) continue;
-        for (long t = 0; t < length; t++) {
-          const float *x = fs.data() + (first + begin + t) * fs.ld();
-          for (int i = 0; i < D; i++) sum[(size_t)k * D + i] += x[i];
+  for (size_t stream = 0; stream < streams.size(); stream++) {
+    const FeatureServer &fs = *streams[stream].fs;
+    const SegCluster &segs = streams[stream].segs;
+    const long total = totalFrame(segs);
+    double proba = nbFrameToSelect * streams[stream].weight / (double)std::max(1L, total);
+    // a probability above 1 becomes several passes (the reference's loop at :707-711 does not terminate
+    // in that case; this is trainModelStream's rule, :1062-1066)
+    long baggedIt = 1;
+    if (proba > 1) {
+      baggedIt = (long)proba + 1;
+      proba /= (double)baggedIt;
+    }
+    for (long it = 0; it < baggedIt; it++) {
+      srand((unsigned)(((stream + 1) * 100) + (it + 1)));  // :737
+      // one pass over the segments, each chunk assigned to a random component when selected
+      for (const Seg &seg : segs) {
+        long begin = seg.begin, left = seg.length;
+        const size_t first = fs.getFirstFeatureIndexOfASource(seg.source);
+        while (left > 0) {
+          long length = std::min(std::min(std::max(left, minLen), maxLen), left);
+          for (int k = 0; k < C; k++) {
+            if (!baggedFrame(proba)) continue;
+            for (long t = 0; t < length; t++) {
+              const float *x = fs.data() + (first + begin + t) * fs.ld();
+              for (int i = 0; i < D; i++) sum[(size_t)k * D + i] += x[i];
+            }
+            cnt[k] += (double)length;
+          }
+          left -= length;
+          begin += length;
         }
-        cnt[k] += (double)length;
       }
-      left -= length;
-      begin += length;
     }
   }
   for (int k = 0; k < C; k++) {
@@ -128,32 +153,56 @@ void mixtureInit(const FeatureServer &fs, const SegCluster &segs, const std::vec
   world.computeAll();
 }
 
-void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs,
-                const std::vector<double> &globalCov, MixtureGD &world, const TrainCfg &cfg) {
-  // trainModelStream (TrainTools.cpp:1030-1110), single stream
+void mixtureInit(const FeatureServer &fs, const SegCluster &segs, const std::vector<double> &globalCov,
+                 const Config &c, MixtureGD &world) {
+  mixtureInit(std::vector<TrainStream>{TrainStream{&fs, segs, 1.0}}, globalCov, c, world);
+}
+
+void trainModel(const Config &c, const std::vector<TrainStream> &streams, const std::vector<double> &globalCov,
+                MixtureGD &world, const TrainCfg &cfg) {
+  // trainModelStream (TrainTools.cpp:1030-1110): every iteration draws, per stream, bagged 3..7-frame
+  // chunks with probability nbFrameToSelect x weight / totalFrame(stream) -- several passes when that
+  // exceeds 1 -- and accumulates them all into ONE EM accumulator
   const long minLen = c.getLong("baggedMinimalLength", 3), maxLen = c.getLong("baggedMaximalLength", 7);
   const long initRand = c.getLong("initRand", 0);
   const bool verbose = c.getBool("verbose", false);
   Gmm g(world);
   EmAcc acc;
-  double llkPrev = 0;
+  const Shard &sh = Shard::get();
   for (long it = 0; it < cfg.nbTrainIt; it++) {
     const double flooring = setItParameter(cfg.initVarianceFlooring, cfg.finalVarianceFlooring, (int)cfg.nbTrainIt, (int)it);
     const double ceiling = setItParameter(cfg.initVarianceCeiling, cfg.finalVarianceCeiling, (int)cfg.nbTrainIt, (int)it);
+    unsigned long nbTotalFrame = 0;  // :1054 (truncated per stream like the reference)
+    for (const TrainStream &st : streams) nbTotalFrame += (unsigned long)((double)totalFrame(st.segs) * st.weight);
+    const double nbFrameToSelect = cfg.baggedFrameProbability * (double)nbTotalFrame;
     acc.reset(world.C, world.D);  // emAcc.resetEM()
-    srand((unsigned)(((it + 1 + initRand) * 200) + 20 + 1));  // :1070 (stream 0, baggedIt 0)
-    SegCluster bagged = cfg.baggedFrameProbability >= 1.0 ? segs
-                                                          : baggedSegments(segs, cfg.baggedFrameProbability, minLen, maxLen);
-    // several ranks: each accumulates a contiguous range of the (identically bagged) segments balanced by
-    // frames, then ONE all-reduce of {occ, m1, m2, llk, n} -- emAcc.addAccEM (AccumulateStat.cpp:286-292)
-    const Shard &sh = Shard::get();
-    double llk;
+    double llk = 0.0;
+    for (size_t stream = 0; stream < streams.size(); stream++) {
+      const TrainStream &st = streams[stream];
+      long nbBaggedIt = 1;
+      double baggedProba = nbFrameToSelect * st.weight / (double)std::max(1L, totalFrame(st.segs));
+      if (baggedProba > 1) {
+        nbBaggedIt = (long)baggedProba + 1;
+        baggedProba /= (double)nbBaggedIt;
+      }
+      for (long baggedIt = 0; baggedIt < nbBaggedIt; baggedIt++) {
+        srand((unsigned)(((it + 1 + initRand) * 200) + (((stream + 1) * 20) + (baggedIt + 1))));  // :1070
+        SegCluster bagged = baggedProba >= 1.0 ? st.segs : baggedSegments(st.segs, baggedProba, minLen, maxLen);
+        // several ranks: each accumulates a contiguous range of the (identically bagged) segments balanced
+        // by frames; ONE all-reduce of {occ, m1, m2, llk, n} per iteration follows (emAcc.addAccEM,
+        // AccumulateStat.cpp:286-292)
+        if (sh.world > 1) {
+          std::vector<double> wgt(bagged.size());
+          for (size_t i = 0; i < bagged.size(); i++) wgt[i] = (double)bagged[i].length;
+          auto r = sh.rangeByWeight(wgt);
+          SegCluster mine(bagged.begin() + r.first, bagged.begin() + r.second);
+          if (!mine.empty()) llk += accumulateStatEM(*st.fs, g, mine, acc);
+        } else if (!bagged.empty()) {
+          llk += accumulateStatEM(*st.fs, g, bagged, acc);
+        }
+      }
+    }
     if (sh.world > 1) {
-      std::vector<double> wgt(bagged.size());
-      for (size_t i = 0; i < bagged.size(); i++) wgt[i] = (double)bagged[i].length;
-      auto r = sh.rangeByWeight(wgt);
-      SegCluster mine(bagged.begin() + r.first, bagged.begin() + r.second);
-      llk = mine.empty() ? 0.0 : accumulateStatEM(fs, g, mine, acc);
       const size_t cC = world.C, cd = (size_t)world.C * world.D;
       std::vector<double> pack(cC + 2 * cd + 2);
       std::copy(acc.occ.begin(), acc.occ.end(), pack.begin());
@@ -167,8 +216,6 @@ void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs
       std::copy(pack.begin() + cC + cd, pack.begin() + cC + 2 * cd, acc.m2.begin());
       llk = pack[cC + 2 * cd];
       acc.n = pack[cC + 2 * cd + 1];
-    } else {
-      llk = accumulateStatEM(fs, g, bagged, acc);
     }
     // *world = emAcc.getEM(); varianceControl(world, flooring, ceiling, globalCov)  (:1076-1077)
     LIA_CHECK(lr_gmm_em_update(g.h(), acc.occ.data(), acc.m1.data(), acc.m2.data(), flooring, ceiling,
@@ -176,10 +223,13 @@ void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs
     if (verbose)
       std::cout << "ML (partial) estimate it[" << it << "] (take care, it corresponds to the previous it,0 means init likelihood) = "
                 << (acc.n > 0 ? llk / acc.n : 0.0) << std::endl;
-    llkPrev = llk;
   }
-  (void)llkPrev;
   g.get(world);
+}
+
+void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs,
+                const std::vector<double> &globalCov, MixtureGD &world, const TrainCfg &cfg) {
+  trainModel(c, std::vector<TrainStream>{TrainStream{&fs, segs, 1.0}}, globalCov, world, cfg);
 }
 
 // ------------------------------------------------------------------ MAP

@@ -188,11 +188,13 @@ __device__ __forceinline__ double i32_to_f64(uint32_t bits) {
   return __hiloint2double(0x43300000, (int)(bits ^ 0x80000000u)) - 4503601774854144.0;
 }
 
+template <int S>  // digit planes per operand (compile time: the issue loop is fully unrolled)
 __global__ void __launch_bounds__(kThreads, 1)
-k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsigned char *__restrict__ Bp,
+k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char *__restrict__ Bp,
           const double *__restrict__ scaleA, const double *__restrict__ scaleB, double *__restrict__ Cout,
           size_t ldc, long M, long N, double alpha, double beta) {
   extern __shared__ unsigned char smem_raw[];
+  constexpr int s = S;
   Bars sm;
   sm.s = s;
   sm.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -238,6 +240,7 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
         if (leader) {
           const unsigned char *src = Bp + ((size_t)nt * sched.nchunk + kc) * s * kBBytes;
           mbar_expect_tx(sm.b_full(bst), (uint32_t)(s * kBBytes));
+#pragma unroll
           for (int j = 0; j < s; j++)
             bulk_g2s(sm.b_stage(bst) + j * kBBytes, src + (size_t)j * kBBytes, kBBytes, sm.b_full(bst));
         }
@@ -262,40 +265,47 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
       }
     }
   } else if (warp == 1) {
-    // ---- UMMA issuer
+    // ---- UMMA issuer.  Everything that can be is a compile-time constant: the single issuing thread
+    // must feed one UMMA per 48 clk (SS M128 N64 K32 is bound by the 128 B/clk operand read), and it
+    // did not when it rebuilt descriptors per instruction (80 clk measured).  Descriptors = constant high
+    // word + low word (start address >> 4, LBO) advanced by immediates.
     const bool leader = elect_one();
     long aseq = 0, bseq = 0, tile_seq = 0;
+    constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((sm.a_stage(0) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t b_lo0 = ((sm.b_stage(0) >> 4) & 0x3FFFu) | (1u << 16);
     for (int it = first_item; it < sched.n_items; it += item_step, tile_seq++) {
       int mt, nt, c0, c1;
       bool live;
       sched.get(it, crank, mt, nt, c0, c1, live);
       if (tile_seq > 0) mbar_wait(sm.acc_empty(), (uint32_t)((tile_seq - 1) & 1));
       tc_fence_after();
-      uint32_t touched = 0;  // classes that already hold a product of this item
       for (int kc = c0; kc < c1; kc++, bseq++) {
         const int bst = (int)(bseq % kBStages);
         mbar_wait(sm.b_full(bst), (uint32_t)((bseq / kBStages) & 1));
+        const uint32_t b_lo = b_lo0 + (uint32_t)bst * (uint32_t)((s * kBBytes) >> 4);
+        const uint32_t later = kc > c0 ? 1u : 0u;  // plane 0 comes first and opens every class of the item
+#pragma unroll
         for (int ii = 0; ii < s; ii++, aseq++) {
           const int i = plane_order(ii, s);
           const int ast = (int)(aseq % kAStages);
           mbar_wait(sm.a_full(ast), (uint32_t)((aseq / kAStages) & 1));
           tc_fence_after();
           if (leader) {
-            const uint64_t adesc = make_desc(sm.a_stage(ast), 16, 1024);
-            for (int j = 0; j < s - i; j++) {
-              const uint64_t bdesc = make_desc(sm.b_stage(bst) + j * kBBytes, 16, 1024);
-              const int d = i + j;
-              const uint32_t dcol = tmem_base + d * kI8TileN;
-              const uint32_t first = (touched >> d) & 1u;
+            const uint32_t a_lo = a_lo0 + (uint32_t)ast * (uint32_t)(kABytes >> 4);
 #pragma unroll
-              for (int kk = 0; kk < 4; kk++)
-                umma_ss_i8(dcol, desc_add(adesc, kk * 32), desc_add(bdesc, kk * 32), idesc, kk ? 1u : first);
+            for (int j = 0; j < s - i; j++) {
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++) {
+                const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + kk * 2);
+                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + j * (kBBytes >> 4) + kk * 2);
+                umma_ss_i8(tmem_base + (i + j) * kI8TileN, adesc, bdesc, idesc, (i == 0 && kk == 0) ? later : 1u);
+              }
             }
             if (csz > 1) umma_commit_mc(sm.a_empty(ast), cmask);
             else umma_commit(sm.a_empty(ast));
           }
           __syncwarp();
-          touched |= ((1u << (s - i)) - 1u) << i;
         }
         if (leader) umma_commit(sm.b_empty(bst));
         __syncwarp();
@@ -318,6 +328,7 @@ k_gemm_i8(Sched sched, int s, const unsigned char *__restrict__ Ap, const unsign
       double v[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] = 0.0;
+#pragma unroll
       for (int d = s - 1; d >= 0; d--) {  // Horner over the classes: v = v 2^-7 + acc_d
         uint32_t r32[32];
         tmem_ld32(tmem_base + lane_addr + d * kI8TileN + h * 32, r32);
@@ -424,10 +435,15 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
   if (M <= 0 || N <= 0) return LR_OK;
   LR_REQUIRE(s >= 1 && s <= kI8MaxSlices, "gemm_i8: %d digit planes outside [1, %d]", s, kI8MaxSlices);
   LR_REQUIRE(K >= 1, "gemm_i8: K = %ld", K);
+  using KernelT = void (*)(Sched, const unsigned char *, const unsigned char *, const double *, const double *,
+                           double *, size_t, long, long, double, double);
+  static const KernelT kernels[kI8MaxSlices + 1] = {nullptr,      k_gemm_i8<1>, k_gemm_i8<2>, k_gemm_i8<3>, k_gemm_i8<4>,
+                                                    k_gemm_i8<5>, k_gemm_i8<6>, k_gemm_i8<7>, k_gemm_i8<8>};
+  const KernelT kern = kernels[s];
   bool &done = e.attr_set[Engine::kAttrGemmI8];
   if (!done) {
-    LR_CUDA(cudaFuncSetAttribute(k_gemm_i8, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem_bytes(kI8MaxSlices)));
+    for (int i = 1; i <= kI8MaxSlices; i++)
+      LR_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(i)));
     done = true;
   }
   Sched sc;
@@ -442,7 +458,6 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
   sc.ksplit = std::max(1, std::min(ksplit, sc.nchunk));
   // clusters of csz CTAs take csz adjacent column tiles and share every A plane by multicast
   int csz = e.i8_cluster;
-  if (const char *env = getenv("LR_I8_CLUSTER")) csz = atoi(env);  // A/B switch (temporary)
   if (csz != 1 && csz != 2 && csz != 4) csz = 1;
   if (sc.nt_count < 2) csz = 1;
   sc.csz = csz;
@@ -472,7 +487,7 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
       cfg.gridDim = dim3((unsigned)(csz * 64));
       cfg.dynamicSmemBytes = smem_bytes(kI8MaxSlices);
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, k_gemm_i8, &cfg) == cudaSuccess && n > 0) cached = n;
+      if (cudaOccupancyMaxActiveClusters(&n, kernels[kI8MaxSlices], &cfg) == cudaSuccess && n > 0) cached = n;
       else {
         cudaGetLastError();
         cached = max_clusters;
@@ -482,7 +497,7 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
     max_clusters = std::min(max_clusters, cached);
   }
   cfg.gridDim = dim3((unsigned)(csz * std::min(max_clusters, sc.n_items)));
-  LR_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_i8, sc, s, dAp, dBp, dAscale, dBscale, dC, ldc, M, N, alpha, beta));
+  LR_CUDA(cudaLaunchKernelEx(&cfg, kern, sc, dAp, dBp, dAscale, dBscale, dC, ldc, M, N, alpha, beta));
   count_launch();
   return LR_OK;
 }

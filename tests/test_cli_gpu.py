@@ -122,6 +122,48 @@ def test_train_world_cli(world, oracle):
     assert np.abs(cov - g.cov).max() < 2e-3 * np.abs(g.cov).max()
 
 
+def test_train_world_multi_stream_cli(world, oracle):
+    """inputStreamList / weightStreamList (TrainWorld.cpp:120-141, trainModelStream TrainTools.cpp:1030-1110).
+    Weights (1, 0) make the bagging deterministic: stream A is taken whole (probability exactly 1), stream B
+    never -- while the global covariance of the variance control still covers both streams."""
+    d = world["dir"]
+    start = synth.perturb_ubm(world["w"], world["mean"], world["cov"], seed=82, frac=1.0, scale=0.4)
+    lf.write_raw_gmm(d / "start2.gmm", *start)
+    lf.write_lines(d / "stream_a.lst", [[f"utt{i}"] for i in range(3)])
+    lf.write_lines(d / "stream_b.lst", [[f"utt{i}"] for i in range(3, 6)])
+    lf.write_lines(d / "streams.lst", [[str(d / "stream_a.lst")], [str(d / "stream_b.lst")]])
+    lf.write_lines(d / "weights.lst", [["1.0"], ["0.0"]])
+    lf.write_cfg(d / "tw2.cfg", **world["common"], inputStreamList=str(d / "streams.lst"),
+                 weightStreamList=str(d / "weights.lst"), inputWorldFilename="start2", outputWorldFilename="trained2",
+                 nbTrainIt=2, baggedFrameProbability=1.0, initVarianceFlooring=0.4, finalVarianceFlooring=0.2,
+                 initVarianceCeiling=8.0, finalVarianceCeiling=6.0)
+    _run("TrainWorld", d / "tw2.cfg")
+    w, mean, cov = lf.read_raw_gmm(d / "trained2.gmm")
+    sel = lambda i: world["utts"][f"utt{i}"][_selected(f"utt{i}", world["utts"][f"utt{i}"])]
+    Xa = np.ascontiguousarray(np.concatenate([sel(i) for i in range(3)]))
+    Xall = np.ascontiguousarray(np.concatenate([sel(i) for i in range(6)]))
+    _, gcov = oracle.mean_cov(Xall)
+    g = oracle.gmm(*start)
+    for it in range(2):
+        fl = oracle.set_it_parameter(0.4, 0.2, 2, it)
+        ce = oracle.set_it_parameter(8.0, 6.0, 2, it)
+        _, _, occ, m1, m2 = oracle.em_accumulate(g, Xa)
+        wn, mn, cn = oracle.em_get(g, occ, m1, m2)
+        cn, _, _ = oracle.variance_control(cn, fl, ce, gcov)
+        g = oracle.gmm(wn, mn, cn)
+    assert np.allclose(w, g.w, rtol=1e-3, atol=1e-6)
+    assert np.abs(mean - g.mean).max() < 1e-3 * np.abs(g.mean).max()
+    assert np.abs(cov - g.cov).max() < 2e-3 * np.abs(g.cov).max()
+    # equal weights (the default): both streams are bagged at random -- the run completes and moves the model
+    lf.write_cfg(d / "tw3.cfg", **world["common"], inputStreamList=str(d / "streams.lst"),
+                 inputWorldFilename="start2", outputWorldFilename="trained3", nbTrainIt=2,
+                 baggedFrameProbability=0.8, initVarianceFlooring=0.4, finalVarianceFlooring=0.2,
+                 initVarianceCeiling=8.0, finalVarianceCeiling=6.0)
+    _run("TrainWorld", d / "tw3.cfg")
+    w3, mean3, _ = lf.read_raw_gmm(d / "trained3.gmm")
+    assert abs(w3.sum() - 1.0) < 1e-9 and np.abs(mean3 - start[1]).max() > 1e-3
+
+
 def test_ivector_and_tv_cli(world, oracle):
     d, C, D, R = world["dir"], world["C"], world["D"], 5
     invvar = (1.0 / world["cov"]).reshape(-1)
