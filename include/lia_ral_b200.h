@@ -85,6 +85,10 @@ typedef struct lr_feats lr_feats;
 lr_feats *lr_feats_upload(const float *X, size_t T, size_t ldx, int D);
 lr_feats *lr_feats_wrap_device(const float *dX, size_t T, size_t ldx, int D);
 void lr_feats_destroy(lr_feats *f);
+/* A handle keeps, between lr_gmm_em_accumulate_dev calls over the same frame range, the frames' tensor-core
+ * operand (512 B per frame; dropped above LR_CONV_CACHE_GB, default 24): EM iterations re-read unchanged
+ * frames.  Frames of a WRAPPED buffer must therefore not change while the handle lives -- or call this. */
+lr_status lr_feats_invalidate(lr_feats *f);
 
 /* A run of selected frames and the statistics row it feeds: the reference's Seg
  * (sourceName/begin/length after fs.getFirstFeatureIndexOfASource) + the NDX line from
@@ -272,7 +276,7 @@ lr_status lr_tv_dims(const lr_tv *tv, int *C, int *D, int *R);
 lr_status lr_gemm_digits(size_t M, size_t N, size_t K, const double *A, const double *B, double *C,
                          double alpha, double beta, int planes);
 /* Contraction kernel of the TV rows: which = 0 the INT8 digit GEMM (default), 1 cuBLAS fp64 (the
- * cross-check of the parity tests); planes = digit planes per operand (3..8, 0 = keep).  Takes effect
+ * cross-check of the parity tests); planes = digit planes per operand (3..7, 0 = keep).  Takes effect
  * at the next lr_tv_estimate_tett. */
 lr_status lr_set_tv_gemm(int which, int planes);
 

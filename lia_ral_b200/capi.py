@@ -149,7 +149,7 @@ def get_gmm_kernel():
 
 def set_tv_gemm(which=0, planes=0):
     """Contraction kernel of the TV rows: 0 = INT8 digit GEMM (default), 1 = cuBLAS fp64 cross-check;
-    planes = digit planes per operand (3..8, 0 = keep).  Effective at the next estimate_tett()."""
+    planes = digit planes per operand (3..7, 0 = keep).  Effective at the next estimate_tett()."""
     _check(lib().lr_set_tv_gemm(int(which), int(planes)))
 
 
@@ -181,6 +181,10 @@ class Feats:
             self.h = _handle(L.lr_feats_wrap_device(ct.c_void_p(int(device_ptr)),
                                                     ct.c_size_t(self.T), ct.c_size_t(self.ldx),
                                                     self.D))
+
+    def invalidate(self):
+        """The wrapped frames changed: drop the cached tensor-core operand."""
+        _check(lib().lr_feats_invalidate(self.h))
 
     def close(self):
         if self.h:

@@ -24,12 +24,11 @@ struct Engine {
   cublasHandle_t blas = nullptr;
   void *solver = nullptr;          // cusolverDnHandle_t, created on first use (plda.cu / ivbackend.cu)
   uint64_t launches = 0;
+  unsigned long long norm_seq = 0;  // normalisation identifiers of the tensor-core path (gmm_tc.cu)
   int gmm_kernel = 0;  // 0 auto, 1 simt, 2 tcgen05 (one-pass statistics), 3 tcgen05 two-pass
   int tc_debug = 0;    // profiling experiments only (LR_TC_DEBUG builds): results are WRONG when set
   int tv_gemm = 0;     // TV contractions: 0 = INT8 digit GEMM (gemm_i8.cu), 1 = cuBLAS fp64 (cross-check)
   int tv_planes = 6;   // digit planes per operand of the INT8 digit GEMM
-  int i8_cluster = 1;  // CTAs per cluster of the digit GEMM (A planes multicast): 1, 2 or 4 (measured: no gain)
-  int i8_max_clusters[5] = {};  // co-resident clusters per cluster size (queried once)
   // per-device "cudaFuncSetAttribute done" flags (reset by lr_shutdown: the attribute is per context)
   enum { kAttrTc = 0, kAttrSimtLse, kAttrSimtAcc, kAttrTopk, kAttrTvDiag, kAttrTvGemm, kAttrPlda, kAttrGemmI8, kAttrCount };
   bool attr_set[kAttrCount] = {};

@@ -39,13 +39,13 @@ namespace lr {
 namespace {
 using namespace tcptx;
 
-constexpr int kThreads = 384;  // warp 0 producer, 1 UMMA issuer, 2 TMEM allocator, 4-11 epilogue
-constexpr int kAStages = 5, kBStages = 2;
+constexpr int kThreads = 512;  // warp 0 producer, 1 UMMA issuer, 2 TMEM allocator, 4-7 movers, 8-15 epilogue
+constexpr int kAStages = 4;    // shared-memory slots of A planes (the TMEM slots behind them add up to 4 more)
 constexpr int kABytes = kI8TileM * 128;  // one digit plane of the A tile, one K chunk
 constexpr int kBBytes = kI8TileN * 128;
 constexpr int kChunkK = 128;
 
-static size_t smem_bytes(int s) { return 1024 + (size_t)kAStages * kABytes + (size_t)kBStages * s * kBBytes + 256; }
+static size_t smem_bytes(int s) { return 1024 + (size_t)kAStages * kABytes + (size_t)(s <= 6 ? 3 : 2) * s * kBBytes + 256; }
 
 // ------------------------------------------------------------------ operand preparation
 // max |x| per row, as the bit pattern of the (non-negative) double
@@ -130,64 +130,94 @@ k_i8_planes(const double *__restrict__ X, size_t stride_row, size_t stride_k, lo
 }
 
 // ------------------------------------------------------------------ the GEMM kernel
-__device__ __forceinline__ void umma_ss_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// D[tmem] (+)= A[tmem] B[smem], int8 x int8 -> int32
+__device__ __forceinline__ void umma_ts_i8(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
                                            uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // instruction descriptor: s8 x s8 -> s32, M x N, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// non-blocking look at an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// TMEM: class accumulators in columns [0, 64 s), A planes in slots of 32 columns (128 int8 per lane) above
+__host__ __device__ constexpr int tmem_slots(int s) { return (512 - 64 * s) / 32 < 4 ? (512 - 64 * s) / 32 : 4; }
+__host__ __device__ constexpr int b_stages(int s) { return s <= 6 ? 3 : 2; }
 
 struct Bars {
   uint32_t base, bar;
   int s;
   __device__ __forceinline__ uint32_t a_stage(int i) const { return base + i * kABytes; }
   __device__ __forceinline__ uint32_t b_stage(int i) const { return base + kAStages * kABytes + i * s * kBBytes; }
-  __device__ __forceinline__ uint32_t a_full(int i) const { return bar + 8 * i; }
-  __device__ __forceinline__ uint32_t a_empty(int i) const { return bar + 40 + 8 * i; }
-  __device__ __forceinline__ uint32_t b_full(int i) const { return bar + 80 + 8 * i; }
-  __device__ __forceinline__ uint32_t b_empty(int i) const { return bar + 96 + 8 * i; }
-  __device__ __forceinline__ uint32_t acc_full() const { return bar + 112; }
-  __device__ __forceinline__ uint32_t acc_empty() const { return bar + 120; }
-  __device__ __forceinline__ uint32_t tmem_slot() const { return bar + 128; }
+  __device__ __forceinline__ uint32_t a_full(int i) const { return bar + 8 * i; }        // kAStages <= 4
+  __device__ __forceinline__ uint32_t a_empty(int i) const { return bar + 32 + 8 * i; }
+  __device__ __forceinline__ uint32_t b_full(int i) const { return bar + 64 + 8 * i; }   // <= 3
+  __device__ __forceinline__ uint32_t b_empty(int i) const { return bar + 88 + 8 * i; }
+  __device__ __forceinline__ uint32_t at_full(int i) const { return bar + 112 + 8 * i; }  // <= 4
+  __device__ __forceinline__ uint32_t at_empty(int i) const { return bar + 144 + 8 * i; }
+  __device__ __forceinline__ uint32_t acc_full() const { return bar + 176; }
+  __device__ __forceinline__ uint32_t acc_empty() const { return bar + 184; }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return bar + 192; }
 };
 
 // work item -> (row tile, column tile, K chunk range); row tiles fastest so that the CTAs running at
 // one moment share a few B panels and all of A through L2
 struct Sched {
   int mt_count, nt_count, ksplit, nchunk, n_items;
-  int csz;  // CTAs per cluster: one item = csz adjacent column tiles (same A planes, multicast)
-  // `nt` is clamped to the last column tile (a surplus CTA of the cluster recomputes it); live = false
-  // tells its epilogue not to store
-  __host__ __device__ void get(int it, int crank, int &mt, int &nt, int &c0, int &c1, bool &live) const {
+  __host__ __device__ void get(int it, int &mt, int &nt, int &c0, int &c1) const {
     mt = it % mt_count;
     const int rest = it / mt_count;
     const int ks = rest % ksplit;
-    nt = (rest / ksplit) * csz + crank;
-    live = nt < nt_count;
-    if (!live) nt = nt_count - 1;
+    nt = rest / ksplit;
     c0 = (int)((long)nchunk * ks / ksplit);
     c1 = (int)((long)nchunk * (ks + 1) / ksplit);
   }
 };
 
 // order in which the A planes of a chunk are consumed: 0, s-1, 1, s-2, ... (s - i products each:
-// heavy and light planes alternate, so the A ring drains at an even rate)
-__device__ __forceinline__ int plane_order(int ii, int s) { return (ii & 1) ? s - 1 - (ii >> 1) : (ii >> 1); }
+// heavy and light planes alternate, so the rings drain at an even rate)
+__host__ __device__ constexpr int plane_order(int ii, int s) { return (ii & 1) ? s - 1 - (ii >> 1) : (ii >> 1); }
 
 __device__ __forceinline__ double i32_to_f64(uint32_t bits) {
   // exact: 2^52 + 2^31 + x as a double whose low word is x + 2^31, minus the constant
   return __hiloint2double(0x43300000, (int)(bits ^ 0x80000000u)) - 4503601774854144.0;
 }
 
+// Warp roles (512 threads): 0 bulk-copy producer, 1 UMMA issuer, 2 TMEM allocator, 4-7 movers (one per
+// TMEM lane quarter: A plane shared memory -> registers -> TMEM), 8-15 epilogue (lane quarter x column half).
+// The A operand of every UMMA comes from TMEM (TS mode): the SS form of M128 N64 K32 is bound by the
+// 128 B/clk shared-memory operand read (48 clk per UMMA measured, scripts/umma_i8_probe.cu), the TS form
+// runs at the tensor pipe's 32 clk.
 template <int S>  // digit planes per operand (compile time: the issue loop is fully unrolled)
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char *__restrict__ Bp,
@@ -195,23 +225,25 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
           size_t ldc, long M, long N, double alpha, double beta) {
   extern __shared__ unsigned char smem_raw[];
   constexpr int s = S;
+  constexpr int kBSt = b_stages(S), kTSlots = tmem_slots(S);
+  constexpr uint32_t kAcol = 64 * S;  // first TMEM column of the A plane slots
   Bars sm;
   sm.s = s;
   sm.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  sm.bar = sm.base + kAStages * kABytes + kBStages * s * kBBytes;
+  sm.bar = sm.base + kAStages * kABytes + kBSt * s * kBBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int csz = sched.csz;
-  const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
-  const int first_item = blockIdx.x / csz, item_step = gridDim.x / csz;
-  const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kAStages; i++) {
       mbar_init(sm.a_full(i), 1);
-      mbar_init(sm.a_empty(i), csz);  // every CTA of the cluster has consumed the multicast plane
+      mbar_init(sm.a_empty(i), 4);  // the four mover warps have read the plane
     }
-    for (int i = 0; i < kBStages; i++) {
+    for (int i = 0; i < kBSt; i++) {
       mbar_init(sm.b_full(i), 1);
       mbar_init(sm.b_empty(i), 1);
+    }
+    for (int i = 0; i < kTSlots; i++) {
+      mbar_init(sm.at_full(i), 4);   // the four mover warps have written their lane quarter
+      mbar_init(sm.at_empty(i), 1);  // the UMMAs reading the slot have completed
     }
     mbar_init(sm.acc_full(), 1);
     mbar_init(sm.acc_empty(), 8);
@@ -220,23 +252,21 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
   if (warp == 2) tmem_alloc(sm.tmem_slot(), 512);
   tc_fence_before();
   __syncthreads();
-  if (csz > 1) cluster_sync_all();  // the peers' barriers exist before anything is multicast at them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot()));
   constexpr uint32_t idesc = make_idesc_i8(kI8TileM, kI8TileN);
 
   if (warp == 0) {
-    // ---- producer
+    // ---- producer: per chunk the s B planes (one stage), then the A planes in consumption order
     const bool leader = elect_one();
     long aseq = 0, bseq = 0;
-    for (int it = first_item; it < sched.n_items; it += item_step) {
+    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x) {
       int mt, nt, c0, c1;
-      bool live;
-      sched.get(it, crank, mt, nt, c0, c1, live);
+      sched.get(it, mt, nt, c0, c1);
       for (int kc = c0; kc < c1; kc++) {
-        const int bst = (int)(bseq % kBStages);
-        mbar_wait(sm.b_empty(bst), (uint32_t)(((bseq / kBStages) & 1) ^ 1));
+        const int bst = (int)(bseq % kBSt);
+        mbar_wait(sm.b_empty(bst), (uint32_t)(((bseq / kBSt) & 1) ^ 1));
         if (leader) {
           const unsigned char *src = Bp + ((size_t)nt * sched.nchunk + kc) * s * kBBytes;
           mbar_expect_tx(sm.b_full(bst), (uint32_t)(s * kBBytes));
@@ -246,64 +276,61 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
         }
         __syncwarp();
         bseq++;
+#pragma unroll
         for (int ii = 0; ii < s; ii++, aseq++) {
           const int i = plane_order(ii, s);
           const int ast = (int)(aseq % kAStages);
           mbar_wait(sm.a_empty(ast), (uint32_t)(((aseq / kAStages) & 1) ^ 1));
           if (leader) {
             const unsigned char *src = Ap + (((size_t)mt * sched.nchunk + kc) * s + i) * kABytes;
-            mbar_expect_tx(sm.a_full(ast), kABytes);  // the whole plane: 1 / csz of it from every CTA
-            if (csz > 1) {
-              const uint32_t part = kABytes / csz;
-              bulk_g2s_mc(sm.a_stage(ast) + crank * part, src + (size_t)crank * part, part, sm.a_full(ast), cmask);
-            } else {
-              bulk_g2s(sm.a_stage(ast), src, kABytes, sm.a_full(ast));
-            }
+            mbar_expect_tx(sm.a_full(ast), kABytes);
+            bulk_g2s(sm.a_stage(ast), src, kABytes, sm.a_full(ast));
           }
           __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ---- UMMA issuer.  Everything that can be is a compile-time constant: the single issuing thread
-    // must feed one UMMA per 48 clk (SS M128 N64 K32 is bound by the 128 B/clk operand read), and it
-    // did not when it rebuilt descriptors per instruction (80 clk measured).  Descriptors = constant high
-    // word + low word (start address >> 4, LBO) advanced by immediates.
+    // ---- UMMA issuer.  Everything that can be is a compile-time constant, and the barrier of the NEXT
+    // plane is looked at (non-blocking) before the current plane's UMMAs are issued: the single issuing
+    // thread has 32 clk per UMMA, a blocking wait between two planes idles the pipe.
     const bool leader = elect_one();
     long aseq = 0, bseq = 0, tile_seq = 0;
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t a_lo0 = ((sm.a_stage(0) >> 4) & 0x3FFFu) | (1u << 16);
     const uint32_t b_lo0 = ((sm.b_stage(0) >> 4) & 0x3FFFu) | (1u << 16);
-    for (int it = first_item; it < sched.n_items; it += item_step, tile_seq++) {
+    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x, tile_seq++) {
       int mt, nt, c0, c1;
-      bool live;
-      sched.get(it, crank, mt, nt, c0, c1, live);
+      sched.get(it, mt, nt, c0, c1);
       if (tile_seq > 0) mbar_wait(sm.acc_empty(), (uint32_t)((tile_seq - 1) & 1));
       tc_fence_after();
+      bool have = false;  // the barrier of plane `aseq` has already been seen complete
       for (int kc = c0; kc < c1; kc++, bseq++) {
-        const int bst = (int)(bseq % kBStages);
-        mbar_wait(sm.b_full(bst), (uint32_t)((bseq / kBStages) & 1));
+        const int bst = (int)(bseq % kBSt);
+        mbar_wait(sm.b_full(bst), (uint32_t)((bseq / kBSt) & 1));
         const uint32_t b_lo = b_lo0 + (uint32_t)bst * (uint32_t)((s * kBBytes) >> 4);
         const uint32_t later = kc > c0 ? 1u : 0u;  // plane 0 comes first and opens every class of the item
 #pragma unroll
         for (int ii = 0; ii < s; ii++, aseq++) {
           const int i = plane_order(ii, s);
-          const int ast = (int)(aseq % kAStages);
-          mbar_wait(sm.a_full(ast), (uint32_t)((aseq / kAStages) & 1));
+          const int ts = (int)(aseq % kTSlots);
+          if (!have) mbar_wait(sm.at_full(ts), (uint32_t)((aseq / kTSlots) & 1));
           tc_fence_after();
+          // look ahead (the next plane of this item, if any)
+          const bool more = (ii + 1 < s) || (kc + 1 < c1);
+          have = more && __all_sync(0xffffffffu, mbar_test(sm.at_full((int)((aseq + 1) % kTSlots)),
+                                                           (uint32_t)(((aseq + 1) / kTSlots) & 1)));
           if (leader) {
-            const uint32_t a_lo = a_lo0 + (uint32_t)ast * (uint32_t)(kABytes >> 4);
+            const uint32_t a_t = tmem_base + kAcol + (uint32_t)ts * 32u;
 #pragma unroll
             for (int j = 0; j < s - i; j++) {
 #pragma unroll
               for (int kk = 0; kk < 4; kk++) {
-                const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + kk * 2);
                 const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + j * (kBBytes >> 4) + kk * 2);
-                umma_ss_i8(tmem_base + (i + j) * kI8TileN, adesc, bdesc, idesc, (i == 0 && kk == 0) ? later : 1u);
+                umma_ts_i8(tmem_base + (i + j) * kI8TileN, a_t + kk * 8, bdesc, idesc,
+                           (i == 0 && kk == 0) ? later : 1u);
               }
             }
-            if (csz > 1) umma_commit_mc(sm.a_empty(ast), cmask);
-            else umma_commit(sm.a_empty(ast));
+            umma_commit(sm.at_empty(ts));
           }
           __syncwarp();
         }
@@ -313,67 +340,113 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
       if (leader) umma_commit(sm.acc_full());
       __syncwarp();
     }
-  } else if (warp >= 4) {
-    // ---- epilogue: TMEM lane quarter q (rows), column half h of the 64-wide tile
-    const int q = warp & 3, h = (warp - 4) >> 2;
+  } else if (warp >= 4 && warp < 8) {
+    // ---- movers: lane quarter q of every A plane, shared memory -> registers -> TMEM slot
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row of the tile = TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    long aseq = 0;
+    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x) {
+      int mt, nt, c0, c1;
+      sched.get(it, mt, nt, c0, c1);
+      for (long n = (long)(c1 - c0) * s; n > 0; n--, aseq++) {
+        const int ast = (int)(aseq % kAStages), ts = (int)(aseq % kTSlots);
+        mbar_wait(sm.a_full(ast), (uint32_t)((aseq / kAStages) & 1));
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const uint32_t a = sm.a_stage(ast) + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3])
+                       : "r"(a));
+        }
+        // (the loads above have returned: they feed the stores below) -- the shared-memory slot is free
+        mbar_wait(sm.at_empty(ts), (uint32_t)(((aseq / kTSlots) & 1) ^ 1));
+        tc_fence_after();
+        {
+          uint32_t lo16[16], hi16[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            lo16[j] = v[j];
+            hi16[j] = v[16 + j];
+          }
+          tmem_st16(tmem_base + lane_addr + kAcol + (uint32_t)ts * 32u, lo16);
+          tmem_st16(tmem_base + lane_addr + kAcol + (uint32_t)ts * 32u + 16u, hi16);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(sm.a_empty(ast));
+          mbar_arrive(sm.at_full(ts));
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ---- epilogue: TMEM lane quarter q (rows), column half h of the 64-wide tile, 16 columns at a time
+    const int q = warp & 3, h = (warp - 8) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     long tile_seq = 0;
     const bool split = sched.ksplit > 1;
-    for (int it = first_item; it < sched.n_items; it += item_step, tile_seq++) {
+    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x, tile_seq++) {
       int mt, nt, c0, c1;
-      bool live;
-      sched.get(it, crank, mt, nt, c0, c1, live);
+      sched.get(it, mt, nt, c0, c1);
+      const long m = (long)mt * kI8TileM + q * 32 + lane;
+      const double sa = m < M ? scaleA[m] * alpha * (1.0 / 4096.0) : 0.0;  // digit weights 2^-6 x 2^-6
       mbar_wait(sm.acc_full(), (uint32_t)(tile_seq & 1));
       tc_fence_after();
-      double v[32];
+      double v[2][16];
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] = 0.0;
+      for (int g = 0; g < 2; g++) {
 #pragma unroll
-      for (int d = s - 1; d >= 0; d--) {  // Horner over the classes: v = v 2^-7 + acc_d
-        uint32_t r32[32];
-        tmem_ld32(tmem_base + lane_addr + d * kI8TileN + h * 32, r32);
-        tmem_wait_ld();
+        for (int j = 0; j < 16; j++) v[g][j] = 0.0;
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = fma(v[j], 0.0078125, i32_to_f64(r32[j]));
+        for (int d = s - 1; d >= 0; d--) {  // Horner over the classes: v = v 2^-7 + acc_d
+          uint32_t r16[16];
+          tmem_ld16(tmem_base + lane_addr + d * kI8TileN + h * 32 + g * 16, r16);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[g][j] = fma(v[g][j], 0.0078125, i32_to_f64(r16[j]));
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.acc_empty());
-      const long m = (long)mt * kI8TileM + q * 32 + lane;
-      const long n_base = (long)nt * kI8TileN + h * 32;
-      if (live && m < M && n_base < N) {
-        const double sa = scaleA[m] * alpha * (1.0 / 4096.0);  // digit weights 2^-6 x 2^-6
-        double *dst = Cout + (size_t)m * ldc + n_base;
-        const bool full = n_base + 32 <= N;
-        const bool vec_ok = full && ((ldc * sizeof(double)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] *= sa * __ldg(scaleB + n_base + j);  // scaleB is padded to the tile
-        if (split) {
+      for (int g = 0; g < 2; g++) {
+        const long n_base = (long)nt * kI8TileN + h * 32 + g * 16;
+        if (m < M && n_base < N) {
+          double *dst = Cout + (size_t)m * ldc + n_base;
+          const bool full = n_base + 16 <= N;
+          const bool vec_ok = full && ((ldc * sizeof(double)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (full || n_base + j < N) atomicAdd(dst + j, v[j]);
-        } else if (vec_ok) {
-          if (beta != 0.0) {
+          for (int j = 0; j < 16; j++) v[g][j] *= sa * __ldg(scaleB + n_base + j);  // scaleB is padded to the tile
+          if (split) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const double2 c = *reinterpret_cast<const double2 *>(dst + j);
-              v[j] = fma(beta, c.x, v[j]);
-              v[j + 1] = fma(beta, c.y, v[j + 1]);
+            for (int j = 0; j < 16; j++)
+              if (full || n_base + j < N) atomicAdd(dst + j, v[g][j]);
+          } else if (vec_ok) {
+            if (beta != 0.0) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const double2 c = *reinterpret_cast<const double2 *>(dst + j);
+                v[g][j] = fma(beta, c.x, v[g][j]);
+                v[g][j + 1] = fma(beta, c.y, v[g][j + 1]);
+              }
             }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2 *>(dst + j) = make_double2(v[g][j], v[g][j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if (n_base + j < N) dst[j] = (beta != 0.0 ? beta * dst[j] : 0.0) + v[g][j];
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2 *>(dst + j) = make_double2(v[j], v[j + 1]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (n_base + j < N) dst[j] = (beta != 0.0 ? beta * dst[j] : 0.0) + v[j];
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (csz > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast at it
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -437,8 +510,8 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
   LR_REQUIRE(K >= 1, "gemm_i8: K = %ld", K);
   using KernelT = void (*)(Sched, const unsigned char *, const unsigned char *, const double *, const double *,
                            double *, size_t, long, long, double, double);
-  static const KernelT kernels[kI8MaxSlices + 1] = {nullptr,      k_gemm_i8<1>, k_gemm_i8<2>, k_gemm_i8<3>, k_gemm_i8<4>,
-                                                    k_gemm_i8<5>, k_gemm_i8<6>, k_gemm_i8<7>, k_gemm_i8<8>};
+  static const KernelT kernels[kI8MaxSlices + 1] = {nullptr,      k_gemm_i8<1>, k_gemm_i8<2>, k_gemm_i8<3>,
+                                                    k_gemm_i8<4>, k_gemm_i8<5>, k_gemm_i8<6>, k_gemm_i8<7>};
   const KernelT kern = kernels[s];
   bool &done = e.attr_set[Engine::kAttrGemmI8];
   if (!done) {
@@ -456,12 +529,7 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
   int ksplit = ceil_div(sc.nchunk, 256);
   if (tiles < 2L * e.sm_count) ksplit = std::max<int>(ksplit, std::min<long>(sc.nchunk / 4, ceil_div(2L * e.sm_count, tiles)));
   sc.ksplit = std::max(1, std::min(ksplit, sc.nchunk));
-  // clusters of csz CTAs take csz adjacent column tiles and share every A plane by multicast
-  int csz = e.i8_cluster;
-  if (csz != 1 && csz != 2 && csz != 4) csz = 1;
-  if (sc.nt_count < 2) csz = 1;
-  sc.csz = csz;
-  sc.n_items = sc.mt_count * ceil_div(sc.nt_count, csz) * sc.ksplit;
+  sc.n_items = (int)(tiles * sc.ksplit);
   if (sc.ksplit > 1) {
     LR_REQUIRE(beta == 0.0 || beta == 1.0, "gemm_i8: beta must be 0 or 1 when the K range is split");
     if (beta == 0.0) {
@@ -469,35 +537,9 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
       LR_CHECK_LAUNCH();
     }
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes(s);
-  cfg.stream = e.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)csz;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int max_clusters = e.sm_count / csz;
-  if (csz > 1) {  // whole clusters that fit the GPCs (one CTA per SM)
-    int &cached = e.i8_max_clusters[csz];
-    if (cached == 0) {
-      cfg.gridDim = dim3((unsigned)(csz * 64));
-      cfg.dynamicSmemBytes = smem_bytes(kI8MaxSlices);
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kernels[kI8MaxSlices], &cfg) == cudaSuccess && n > 0) cached = n;
-      else {
-        cudaGetLastError();
-        cached = max_clusters;
-      }
-      cfg.dynamicSmemBytes = smem_bytes(s);
-    }
-    max_clusters = std::min(max_clusters, cached);
-  }
-  cfg.gridDim = dim3((unsigned)(csz * std::min(max_clusters, sc.n_items)));
-  LR_CUDA(cudaLaunchKernelEx(&cfg, kern, sc, dAp, dBp, dAscale, dBscale, dC, ldc, M, N, alpha, beta));
+  const int grid = std::min(e.sm_count, sc.n_items);
+  kern<<<grid, kThreads, smem_bytes(s), e.stream>>>(sc, dAp, dBp, dAscale, dBscale, dC, ldc, M, N, alpha, beta);
+  LR_CUDA(cudaGetLastError());
   count_launch();
   return LR_OK;
 }

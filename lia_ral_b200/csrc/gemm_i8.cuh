@@ -7,7 +7,7 @@
 
 namespace lr {
 
-constexpr int kI8MaxSlices = 8;
+constexpr int kI8MaxSlices = 7;  // 64 s accumulator columns + A plane slots <= 512 TMEM columns
 constexpr int kI8TileM = 128, kI8TileN = 64;
 
 // bytes of the digit panels of a [rows x K] operand cut in tiles of tile_rows (128: A side, 64: B side)

@@ -365,7 +365,14 @@ lr_feats *lr_feats_wrap_device(const float *dX, size_t T, size_t ldx, int D) {
 void lr_feats_destroy(lr_feats *f) {
   if (!f) return;
   if (f->owned) cudaFree((void *)f->d_x);
+  cudaFree(f->d_conv);
   delete f;
+}
+
+lr_status lr_feats_invalidate(lr_feats *f) {
+  LR_REQUIRE(f, "lr_feats_invalidate: null handle");
+  f->conv_norm = 0;  // the frames changed under the handle: the next EM pass converts them again
+  return LR_OK;
 }
 
 }  // extern "C"

@@ -37,6 +37,14 @@ struct lr_feats {
   size_t T = 0, ldx = 0;
   int D = 0;
   bool owned = false;
+  // tensor-core frame operand of the range [conv_t0, conv_t0 + conv_T) (k_tc_convert output, 512 B per
+  // frame), kept between EM iterations over resident frames: it depends on the frames and on the
+  // normalisation (conv_norm) only, and tc_derive keeps the normalisation while the mixture's global
+  // mean / deviation stay close to it.  mutable: filled behind the const handle of the _dev entry points.
+  mutable unsigned char *d_conv = nullptr;
+  mutable size_t conv_cap = 0;
+  mutable size_t conv_t0 = 0, conv_T = 0;
+  mutable unsigned long long conv_norm = 0;  // 0 = nothing cached
 };
 
 namespace lr {
@@ -72,9 +80,14 @@ bool tc_supported(const lr_gmm *g);
 lr_status tc_derive(lr_gmm *g);
 lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_llk_sum);
 // likelihood + statistics over a tile-padded frame list (chunks tile aligned, host copy)
+// conv != nullptr: the converted operand of this frame list lives there (n_tiles x 64 KB); it is
+// (re)written unless conv_valid
 lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk> &chunks,
                        double fw, double *out_N, double *out_F, double *out_S2,
-                       double *d_llk_sum);
+                       double *d_llk_sum, unsigned char *conv = nullptr, bool conv_valid = false);
+// identifier of the normalisation the model's tensor-core operands are expressed in (0: none)
+unsigned long long tc_norm_id(const lr_gmm *g);
+constexpr size_t kTcTileBytesPub = 65536;  // converted operand per 128 frames
 void tc_free(lr_gmm *g);
 // true when the tensor-core path serves this model under the current lr_set_gmm_kernel choice;
 // sets *err when the choice is "tcgen05" but the model cannot be served

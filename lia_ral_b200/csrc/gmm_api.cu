@@ -3,6 +3,7 @@
 // computeAndAccumulateTVStat, the ComputeTest frame loop), staging host frames through two
 // device buffers so the PCIe copy of block k+1 overlaps the kernels of block k.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gmm_topk.cuh"
 
@@ -103,7 +104,8 @@ lr_status check_segs(const lr_seg *segs, size_t n_segs, size_t T, size_t U, bool
 
 // Upload the plan and run pass 1 (+ pass 2 when any output is requested) over it.
 lr_status run_plan(lr_gmm *g, const float *dX, size_t ldx, const Plan &plan, bool tc, double fw,
-                   double *dN, double *dF, double *dS2, double *d_llk_sum) {
+                   double *dN, double *dF, double *dS2, double *d_llk_sum, unsigned char *conv = nullptr,
+                   bool conv_valid = false) {
   if (plan.P == 0) return LR_OK;
   Engine &e = engine();
   unsigned *d_index = nullptr;
@@ -118,7 +120,7 @@ lr_status run_plan(lr_gmm *g, const float *dX, size_t ldx, const Plan &plan, boo
     LR_CHECK_LAUNCH();
   }
   FrameList fl{dX, ldx, d_index, plan.P};
-  if (tc) return tc_run_stats(g, fl, plan.chunks, fw, dN, dF, dS2, d_llk_sum);
+  if (tc) return tc_run_stats(g, fl, plan.chunks, fw, dN, dF, dS2, d_llk_sum, conv, conv_valid);
   float *d_lse = (float *)scratch_get(kSlotLse, (plan.P + 128) * sizeof(float));
   if (!d_lse) return LR_ERR_CUDA;
   lr_status st = gmm_pass_lse(g, fl, d_lse, nullptr, d_llk_sum);
@@ -250,12 +252,47 @@ lr_status lr_gmm_em_accumulate_dev(lr_gmm *g, const lr_feats *f, size_t t0, size
   const bool tc = tc_selected(g, &sel);
   if (sel != LR_OK) return sel;
   const long step = dev_block_step((long)t0, (long)(t0 + T));
+  // The converted frame operand (512 B per frame) is kept with the handle between calls over the same
+  // range: EM iterations re-read the same frames, and tc_derive keeps the normalised space stable.
+  // Budget: LR_CONV_CACHE_GB (default 24) -- beyond it, or if the allocation fails, every call converts.
+  bool cache = false, cache_valid = false;
+  if (tc && engine().gmm_kernel != 3) {
+    size_t tiles = 0;
+    for (long b0 = (long)t0; b0 < (long)(t0 + T); b0 += step)
+      tiles += (size_t)((std::min<long>((long)(t0 + T), b0 + step) - b0 + 127) / 128);
+    const size_t need = tiles * kTcTileBytesPub;
+    static const double budget_gb = getenv("LR_CONV_CACHE_GB") ? atof(getenv("LR_CONV_CACHE_GB")) : 24.0;
+    if ((double)need <= budget_gb * 1e9) {
+      if (f->conv_cap < need) {
+        cudaFree(f->d_conv);
+        f->d_conv = nullptr;
+        f->conv_cap = 0;
+        f->conv_norm = 0;
+        if (cudaMalloc(&f->d_conv, need) == cudaSuccess) f->conv_cap = need;
+        else cudaGetLastError();
+      }
+      cache = f->d_conv != nullptr;
+      const unsigned long long norm = tc_norm_id(g);
+      cache_valid = cache && norm != 0 && f->conv_norm == norm && f->conv_t0 == t0 && f->conv_T == T;
+      if (cache && !cache_valid) {
+        f->conv_norm = norm;
+        f->conv_t0 = t0;
+        f->conv_T = T;
+      }
+    }
+  }
+  size_t tile_off = 0;
   for (long b0 = (long)t0; b0 < (long)(t0 + T); b0 += step) {
     long b1 = std::min<long>((long)(t0 + T), b0 + step);
     build_plan(nullptr, 0, b0, b1, b0, false, tc, plan);
     lr_status st = run_plan(g, f->d_x + (size_t)b0 * f->ldx, f->ldx, plan, tc, frame_weight, d_stats,
-                            d_stats + C, d_stats + C + cd, d_stats + C + 2 * cd);
-    if (st != LR_OK) return st;
+                            d_stats + C, d_stats + C + cd, d_stats + C + 2 * cd,
+                            cache ? f->d_conv + tile_off * kTcTileBytesPub : nullptr, cache_valid);
+    if (st != LR_OK) {
+      f->conv_norm = 0;
+      return st;
+    }
+    tile_off += (size_t)((b1 - b0 + 127) / 128);
   }
   // n_frames accumulates on the device too (no host sync in this variant)
   k_add_scalar<<<1, 1, 0, engine().stream>>>(d_stats + C + 2 * cd + 1, frame_weight * (double)T);

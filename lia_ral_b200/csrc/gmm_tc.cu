@@ -67,8 +67,7 @@ __device__ __forceinline__ void split2(float v, __half &hi, __half &lo) {
 // g, s per dimension: mixture mean / standard deviation (fp64)
 __global__ void k_tc_norm(int C, int D, const double *__restrict__ w,
                           const double *__restrict__ mean, const double *__restrict__ cov,
-                          double *__restrict__ g, double *__restrict__ s, float *__restrict__ gf,
-                          float *__restrict__ rsf) {
+                          double *__restrict__ g, double *__restrict__ s) {
   int i = blockIdx.x;
   if (i >= D) return;
   __shared__ double sh[3][256];
@@ -93,12 +92,8 @@ __global__ void k_tc_norm(int C, int D, const double *__restrict__ w,
     double gi = sh[0][0] / wsum;
     double var = sh[1][0] / wsum - gi * gi;
     double si = var > 1e-300 ? sqrt(var) : 1.0;
-    // the converter normalises with the fp32 values; the weights and the flush use exactly those
-    float gfl = (float)gi, rsfl = (float)(1.0 / si);
-    gf[i] = gfl;
-    rsf[i] = rsfl;
-    g[i] = (double)gfl;
-    s[i] = 1.0 / (double)rsfl;
+    g[i] = gi;  // candidates: k_tc_norm_adopt decides
+    s[i] = si;
   }
 }
 
@@ -1461,9 +1456,42 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
 // ------------------------------------------------------------------ host side
 struct TcState {
   unsigned char *d_W = nullptr;  // [slices][64 KB]
-  int *d_flag = nullptr;
+  int *d_flag = nullptr;         // [0] weights out of the fp16 range, [1] normalisation re-derived
+  double *d_cand = nullptr;      // candidate normalisation: g[64] | s[64]
   bool ok = false;
+  unsigned long long norm_id = 0;
 };
+
+unsigned long long tc_norm_id(const lr_gmm *g) {
+  const TcState *st = g ? (const TcState *)g->d_tc_w : nullptr;
+  return st ? st->norm_id : 0;
+}
+
+// The normalised space is a free choice (any shift / scale gives the same mathematics; it only
+// conditions the fp16 split), so the current one is KEPT while the mixture's global mean stays within a
+// quarter deviation and its deviation within 25 % of it: EM preserves the first two moments of the data,
+// so after the first iteration the frames' converted operand can be reused (lr_feats cache).
+__global__ void k_tc_norm_adopt(int D, int have, const double *__restrict__ cand, double *__restrict__ g,
+                                double *__restrict__ s, float *__restrict__ gf, float *__restrict__ rsf,
+                                int *__restrict__ flag) {
+  __shared__ int change;
+  if (threadIdx.x == 0) change = have ? 0 : 1;
+  __syncthreads();
+  const int i = threadIdx.x;
+  if (i < D && have) {
+    const double dg = fabs(cand[i] - g[i]), ratio = cand[64 + i] / s[i];
+    if (!(dg <= 0.25 * s[i]) || !(ratio >= 0.8 && ratio <= 1.25)) change = 1;
+  }
+  __syncthreads();
+  if (change && i < D) {
+    const float gfl = (float)cand[i], rsfl = (float)(1.0 / cand[64 + i]);
+    gf[i] = gfl;
+    rsf[i] = rsfl;
+    g[i] = (double)gfl;  // the converter normalises with the fp32 values; weights and flush use exactly those
+    s[i] = 1.0 / (double)rsfl;
+  }
+  if (i == 0) flag[1] = change;
+}
 
 bool tc_supported(const lr_gmm *g) {
   if (!g || g->D > kOneCol) return false;
@@ -1499,24 +1527,28 @@ lr_status tc_derive(lr_gmm *g) {
     g->d_tc_w = st;
     size_t wbytes = (size_t)(g->Cp / kSlice) * 4 * kPanelBytes;
     LR_CUDA(cudaMalloc(&st->d_W, wbytes));
-    LR_CUDA(cudaMalloc(&st->d_flag, sizeof(int)));
+    LR_CUDA(cudaMalloc(&st->d_flag, 2 * sizeof(int)));
+    LR_CUDA(cudaMalloc(&st->d_cand, 128 * sizeof(double)));
     LR_CUDA(cudaMalloc(&g->d_g, g->D * sizeof(double)));
     LR_CUDA(cudaMalloc(&g->d_s, g->D * sizeof(double)));
     LR_CUDA(cudaMalloc(&g->d_gf, 64 * sizeof(float)));
     LR_CUDA(cudaMalloc(&g->d_rsf, 64 * sizeof(float)));
   }
-  LR_CUDA(cudaMemsetAsync(st->d_flag, 0, sizeof(int), e.stream));
-  k_tc_norm<<<g->D, 256, 0, e.stream>>>(g->C, g->D, g->d_w, g->d_mean, g->d_cov, g->d_g, g->d_s,
-                                        g->d_gf, g->d_rsf);
+  LR_CUDA(cudaMemsetAsync(st->d_flag, 0, 2 * sizeof(int), e.stream));
+  k_tc_norm<<<g->D, 256, 0, e.stream>>>(g->C, g->D, g->d_w, g->d_mean, g->d_cov, st->d_cand, st->d_cand + 64);
+  LR_CHECK_LAUNCH();
+  k_tc_norm_adopt<<<1, 64, 0, e.stream>>>(g->D, st->norm_id != 0 ? 1 : 0, st->d_cand, g->d_g, g->d_s, g->d_gf,
+                                         g->d_rsf, st->d_flag);
   LR_CHECK_LAUNCH();
   k_tc_weights<<<ceil_div(g->Cp, 128), 128, 0, e.stream>>>(g->C, g->D, g->Cp, g->d_w, g->d_mean,
                                                            g->d_covinv, g->d_cst, g->d_g, g->d_s,
                                                            st->d_W, st->d_flag);
   LR_CHECK_LAUNCH();
-  int flag = 0;
-  LR_CUDA(cudaMemcpyAsync(&flag, st->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+  int flag[2] = {0, 0};
+  LR_CUDA(cudaMemcpyAsync(flag, st->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
   LR_CUDA(cudaStreamSynchronize(e.stream));
-  st->ok = flag == 0;  // weights outside the fp16 range -> this model stays on the SIMT path
+  st->ok = flag[0] == 0;  // weights outside the fp16 range -> this model stays on the SIMT path
+  if (flag[1]) st->norm_id = ++e.norm_seq;  // a new normalised space: cached frame operands are stale
   return LR_OK;
 }
 
@@ -1525,6 +1557,7 @@ void tc_free(lr_gmm *g) {
   if (!st) return;
   cudaFree(st->d_W);
   cudaFree(st->d_flag);
+  cudaFree(st->d_cand);
   delete st;
   g->d_tc_w = nullptr;
 }
@@ -1668,7 +1701,7 @@ lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_l
 // (build_plan(..., pad = true)): chunk.pos % 128 == 0, padding entries carry kPadIndex.
 lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk> &chunks,
                        double fw, double *out_N, double *out_F, double *out_S2,
-                       double *d_llk_sum) {
+                       double *d_llk_sum, unsigned char *conv, bool conv_valid) {
   Engine &e = engine();
   TcState *st = (TcState *)g->d_tc_w;
   lr_status rc = tc_set_attrs();
@@ -1722,7 +1755,7 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
   const bool want_stats = out_N || out_F || out_S2;
   if (want_stats && e.gmm_kernel != 3 && n_slices <= e.sm_count) {
     // ---- one pass: likelihood GEMM, log-sum-exp exchange and statistics GEMM in one kernel
-    unsigned char *Xh1 = (unsigned char *)scratch_get(kSlotTmpA, (size_t)n_tiles * kTileBytes);
+    unsigned char *Xh1 = conv ? conv : (unsigned char *)scratch_get(kSlotTmpA, (size_t)n_tiles * kTileBytes);
     int *d_cuts1 = (int *)scratch_get(kSlotRest, (groups + 1) * sizeof(int));
     TileInfo *d_tinfo1 = (TileInfo *)scratch_get(kSlotChunks, (size_t)n_tiles * sizeof(TileInfo));
     // exchange ring: kXRing half tiles x n_slices x 64 frames of (max, sum) words per group.  A CTA
@@ -1736,9 +1769,11 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
     LR_CUDA(cudaMemcpyAsync(d_tinfo1, tinfo.data(), (size_t)n_tiles * sizeof(TileInfo),
                             cudaMemcpyHostToDevice, e.stream));
     LR_CUDA(cudaMemsetAsync(d_xch, 0, xbytes, e.stream));  // lap tags start at 1
-    k_tc_convert<<<(unsigned)((P_pad * 8 + 255) / 256), 256, 0, e.stream>>>(
-        g->D, fl.dX, fl.ldx, fl.d_index, fl.P, P_pad, g->d_gf, g->d_rsf, Xh1);
-    LR_CHECK_LAUNCH();
+    if (!(conv && conv_valid)) {
+      k_tc_convert<<<(unsigned)((P_pad * 8 + 255) / 256), 256, 0, e.stream>>>(
+          g->D, fl.dX, fl.ldx, fl.d_index, fl.P, P_pad, g->d_gf, g->d_rsf, Xh1);
+      LR_CHECK_LAUNCH();
+    }
 #ifdef LR_DEBUG_BUILD  // phase profiler / experiment switches: `make DEBUG=1` builds only
     static const bool kProf = getenv("LR_TC_PROF") != nullptr;
     static const int kEnvDbg = getenv("LR_TC_DEBUG") ? atoi(getenv("LR_TC_DEBUG")) : 0;

@@ -279,12 +279,14 @@ k_chol_solve(int n, const double *__restrict__ Lall, size_t stride, double *__re
 // The diagonal-block inverses are kept: the explicit inverse of the E-step reuses them.
 constexpr int kNB = 64;
 constexpr int kDiagThreads = 4 * kNB;  // four lanes per row / column (adjacent lanes of one warp)
+// Shared memory: ONE [64][65] array.  The factor occupies the lower triangle (columns <= row); the
+// inverse X = L^-1 (lower triangular too) is stored transposed-and-shifted in the strict upper part,
+// X[i][j] at Ls[j][i + 1] (i >= j: columns j+1 .. 64, the padding column included) -- 33 KB per CTA,
+// six CTAs per SM, which is what this latency-bound kernel needs.
 __global__ void __launch_bounds__(kDiagThreads)
 k_diag_chol_inv(int n, double *__restrict__ Lall, size_t stride, double *__restrict__ invD,
                 int nblk, int blk, int *__restrict__ bad) {
-  extern __shared__ double dsm[];
-  double (*Ls)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm);
-  double (*Xs)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm + kNB * (kNB + 1));
+  __shared__ double Ls[kNB][kNB + 1];
   __shared__ int fail_flag;
   const int mat = blockIdx.x;
   const int k0 = blk * kNB, nb = min(kNB, n - k0);
@@ -292,7 +294,7 @@ k_diag_chol_inv(int n, double *__restrict__ Lall, size_t stride, double *__restr
   const int j = threadIdx.x >> 2, q = threadIdx.x & 3;
   if (threadIdx.x == 0) fail_flag = 0;
   for (int c = q; c < nb; c += 4)
-    if (j < nb) Ls[j][c] = (j >= c) ? L[(size_t)(k0 + c) * n + k0 + j] : 0.0;  // Ls[row][col]
+    if (j < nb && j >= c) Ls[j][c] = L[(size_t)(k0 + c) * n + k0 + j];  // Ls[row][col], lower triangle
   __syncthreads();
   // right-looking Cholesky of the block: the four lanes of row j share its trailing update
   for (int c = 0; c < nb; c++) {
@@ -301,35 +303,180 @@ k_diag_chol_inv(int n, double *__restrict__ Lall, size_t stride, double *__restr
       if (threadIdx.x == 0) fail_flag = 1;
       d = 1.0;
     }
-    const double s = sqrt(d);
-    const double ljc = (j > c && j < nb) ? Ls[j][c] / s : 0.0;
+    const double sq = sqrt(d);
+    const double ljc = (j > c && j < nb) ? Ls[j][c] / sq : 0.0;
     __syncthreads();  // everyone has read column c as it was
     if (q == 0) {
-      if (j == c) Ls[c][c] = s;
+      if (j == c) Ls[c][c] = sq;
       else if (j > c && j < nb) Ls[j][c] = ljc;
     }
     __syncthreads();
-    if (j > c && j < nb)
-      for (int k = c + 1 + q; k <= j; k += 4) Ls[j][k] -= ljc * Ls[k][c];
+    if (j > c && j < nb) {
+#pragma unroll 4
+      for (int k = c + 1 + q; k <= j; k += 4) Ls[j][k] = fma(-ljc, Ls[k][c], Ls[j][k]);
+    }
+    // (the next column's reads of Ls[.][c + 1] are ordered by the barrier at the top of the loop body)
     __syncthreads();
   }
   if (threadIdx.x == 0 && fail_flag) atomicExch(bad, mat + 1);
   for (int c = q; c < nb; c += 4)
     if (j < nb && j >= c) L[(size_t)(k0 + c) * n + k0 + j] = Ls[j][c];
   // inverse of the block factor: the four lanes of column j split the dot product of the forward
-  // substitution (they sit in one warp: shuffles + __syncwarp, no block barrier)
+  // substitution (they sit in one warp: shuffles + __syncwarp, no block barrier).  Column j of X lives
+  // in row j of Ls (strict upper part), which only this quad touches.
+  __shared__ double rdiag[kNB];
+  if (q == 0 && j < nb) rdiag[j] = 1.0 / Ls[j][j];
+  __syncthreads();
   for (int i = 0; i < nb; i++) {
     double v = 0.0;
-    if (j < nb && i > j)
-      for (int k = j + q; k < i; k += 4) v -= Ls[i][k] * Xs[k][j];
+    if (j < nb && i > j) {
+#pragma unroll 4
+      for (int k = j + q; k < i; k += 4) v = fma(-Ls[i][k], Ls[j][k + 1], v);
+    }
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (q == 0 && j < nb) Xs[i][j] = i < j ? 0.0 : ((i == j ? 1.0 : 0.0) + v) / Ls[i][i];
+    if (q == 0 && j < nb && i >= j) Ls[j][i + 1] = (i == j) ? rdiag[j] : v * rdiag[i];
     __syncwarp();
   }
   __syncthreads();
-  double *out = invD + ((size_t)mat * nblk + blk) * kNB * kNB;  // column-major, ld = kNB
-  for (int c = q; c < kNB; c += 4) out[(size_t)c * kNB + j] = (j < nb && c < nb) ? Xs[j][c] : 0.0;
+  double *out = invD + ((size_t)mat * nblk + blk) * kNB * kNB;  // column-major, ld = kNB: out[c * 64 + r] = X[r][c]
+  for (int c = q; c < kNB; c += 4) out[(size_t)c * kNB + j] = (j < nb && c < nb && j >= c) ? Ls[c][j + 1] : 0.0;
+}
+
+// Batched fp64 GEMM on the DMMA pipe for the panel work of the blocked Cholesky:
+//     C[b] = alpha A[b] B[b]^T + beta C[b]        (all column-major: A m x K, B n x K, C m x n)
+// One CTA per 64 x 64 tile of one matrix of the batch; 8 warps, each a 16 x 32 warp tile of eight
+// mma.m8n8k4 accumulators; K in slabs of 16 through shared memory (k-major slabs, leading dimension
+// 72 doubles: the four k rows a fragment load touches fall on two disjoint bank halves).  The tile is
+// held in registers until the end, so C may alias A when a CTA's rows of A are read by nobody else
+// (the panel solve X = P invD^T overwrites P).
+constexpr int kBgTile = 64, kBgSlab = 16, kBgLd = 72;
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256)
+k_bgemm_nt(int M, int N, int K, double alpha, const double *A, int lda, size_t strideA,
+           const double *B, int ldb, size_t strideB, double beta, double *C, int ldc,
+           size_t strideC) {
+  __shared__ double As[kBgSlab][kBgLd], Bs[kBgSlab][kBgLd];
+  const int m0 = blockIdx.x * kBgTile, n0 = blockIdx.y * kBgTile;
+  A += (size_t)blockIdx.z * strideA;
+  B += (size_t)blockIdx.z * strideB;
+  C += (size_t)blockIdx.z * strideC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;  // warp tile origin inside the CTA tile
+  const int fr = lane >> 2, fk = lane & 3;                // fragment row (m or n) and k
+  const int lk = threadIdx.x >> 4, l4 = (threadIdx.x & 15) * 4;  // slab loader: k row, first of 4 m / n
+  double acc[2][4][2] = {};
+  double ra[4], rb[4];  // next slab, fetched while the current one is multiplied
+  auto fetch = [&](int k0) {
+    const int k = k0 + lk;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int m = m0 + l4 + e, n = n0 + l4 + e;
+      ra[e] = (k < K && m < M) ? A[(size_t)k * lda + m] : 0.0;
+      rb[e] = (k < K && n < N) ? B[(size_t)k * ldb + n] : 0.0;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kBgSlab) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      As[lk][l4 + e] = ra[e];
+      Bs[lk][l4 + e] = rb[e];
+    }
+    __syncthreads();
+    if (k0 + kBgSlab < K) fetch(k0 + kBgSlab);
+#pragma unroll
+    for (int kk = 0; kk < kBgSlab; kk += 4) {
+      double a[2], b[4];
+#pragma unroll
+      for (int x = 0; x < 2; x++) a[x] = As[kk + fk][wm + 8 * x + fr];
+#pragma unroll
+      for (int y = 0; y < 4; y++) b[y] = Bs[kk + fk][wn + 8 * y + fr];
+#pragma unroll
+      for (int x = 0; x < 2; x++)
+#pragma unroll
+        for (int y = 0; y < 4; y++) dmma_8x8x4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < 2; x++) {
+    const int m = m0 + wm + 8 * x + fr;
+    if (m >= M) continue;
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+#pragma unroll
+      for (int z = 0; z < 2; z++) {
+        const int n = n0 + wn + 8 * y + 2 * fk + z;
+        if (n >= N) continue;
+        double *dst = C + (size_t)n * ldc + m;
+        *dst = alpha * acc[x][y][z] + (beta != 0.0 ? beta * *dst : 0.0);
+      }
+  }
+}
+inline lr_status bgemm_nt(int M, int N, int K, double alpha, const double *A, int lda, size_t sA, const double *B,
+                          int ldb, size_t sB, double beta, double *C, int ldc, size_t sC, int batch) {
+  if (M <= 0 || N <= 0 || batch <= 0) return LR_OK;
+  dim3 grid((unsigned)ceil_div(M, kBgTile), (unsigned)ceil_div(N, kBgTile), (unsigned)batch);
+  k_bgemm_nt<<<grid, 256, 0, engine().stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+// Solve L L^T x = b for ONE right-hand side per matrix with the factor of chol_batched AND its
+// diagonal-block inverses: block forward / backward substitution, x_i = invD_ii (b_i - sum_j L_ij x_j),
+// two barriers per 64-wide block instead of two per column (k_chol_solve: 2 n barriers, each behind a
+// dependent global load).  One CTA per matrix, four lanes per row.
+__global__ void __launch_bounds__(256)
+k_chol_solve_blocked(int n, const double *__restrict__ Lall, size_t stride, const double *__restrict__ invD,
+                     int nblk, double *__restrict__ rhs) {
+  extern __shared__ double xs[];  // [nblk * 64] solution in progress, then ys[64]
+  double *ys = xs + (size_t)nblk * kNB;
+  const double *L = Lall + (size_t)blockIdx.x * stride;
+  const double *iD = invD + (size_t)blockIdx.x * nblk * kNB * kNB;
+  double *b = rhs + (size_t)blockIdx.x * n;
+  const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+  for (int i = threadIdx.x; i < nblk * kNB; i += blockDim.x) xs[i] = i < n ? b[i] : 0.0;
+  __syncthreads();
+  for (int bi = 0; bi < nblk; bi++) {  // L y = b
+    const int i0 = bi * kNB;
+    const bool in = i0 + r < n;
+    double acc = 0.0;
+    if (in)
+      for (int c = q; c < i0; c += 4) acc = fma(L[(size_t)c * n + i0 + r], xs[c], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0) ys[r] = in ? xs[i0 + r] - acc : 0.0;
+    __syncthreads();
+    double t = 0.0;
+    for (int c = q; c <= r; c += 4) t = fma(iD[(size_t)bi * kNB * kNB + (size_t)c * kNB + r], ys[c], t);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    if (q == 0) xs[i0 + r] = t;
+    __syncthreads();
+  }
+  for (int bi = nblk - 1; bi >= 0; bi--) {  // L^T x = y; here r indexes the COLUMN i0 + r of L
+    const int i0 = bi * kNB, i1 = min(n, i0 + kNB);
+    const bool in = i0 + r < n;
+    double acc = 0.0;
+    if (in)
+      for (int k = i1 + q; k < n; k += 4) acc = fma(L[(size_t)(i0 + r) * n + k], xs[k], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0) ys[r] = in ? xs[i0 + r] - acc : 0.0;
+    __syncthreads();
+    double t = 0.0;  // x[r] = sum_{c >= r} invD[c][r] y[c]
+    for (int c = r + q; c < kNB; c += 4) t = fma(iD[(size_t)bi * kNB * kNB + (size_t)r * kNB + c], ys[c], t);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    if (q == 0) xs[i0 + r] = t;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] = xs[i];
 }
 
 // dst[mat][0:rows, 0:cols] = src[mat][0:rows, 0:cols]  (column-major, own ld / stride each)
@@ -515,36 +662,21 @@ lr_status chol_batched(lr_tv *tv, double *Lb, int n, int nb, double *invD, doubl
   const size_t rr = (size_t)n * n;
   const int nblk = (n + kNB - 1) / kNB;
   const long long sD = (long long)nblk * kNB * kNB;
-  const double one = 1.0, zero = 0.0, mone = -1.0;
-  bool &diag_attr = engine().attr_set[Engine::kAttrTvDiag];
-  const size_t diag_smem = 2 * kNB * (kNB + 1) * sizeof(double);
-  if (!diag_attr) {
-    LR_CUDA(cudaFuncSetAttribute(k_diag_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)diag_smem));
-    diag_attr = true;
-  }
   int *bad = tv->d_info;
   LR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), e.stream));
   for (int k = 0; k < nblk; k++) {
     const int k0 = k * kNB, nbk = std::min(kNB, n - k0), m = n - k0, m2 = m - nbk;
-    if (k0 > 0) {
-      LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, m, nbk, k0, &mone,
-                                          Lb + k0, n, (long long)rr, Lb + k0, n, (long long)rr, &one,
-                                          Lb + (size_t)k0 * n + k0, n, (long long)rr, nb));
-      count_launch();
+    lr_status st;
+    if (k0 > 0) {  // A[k0:, k] -= L[k0:, 0:k0] L[k, 0:k0]^T
+      st = bgemm_nt(m, nbk, k0, -1.0, Lb + k0, n, rr, Lb + k0, n, rr, 1.0, Lb + (size_t)k0 * n + k0, n, rr, nb);
+      if (st != LR_OK) return st;
     }
-    k_diag_chol_inv<<<nb, kDiagThreads, diag_smem, e.stream>>>(n, Lb, rr, invD, nblk, k, bad);
+    k_diag_chol_inv<<<nb, kDiagThreads, 0, e.stream>>>(n, Lb, rr, invD, nblk, k, bad);
     LR_CHECK_LAUNCH();
-    if (m2 > 0) {
-      const long long sP = (long long)n * kNB;
-      LR_CUBLAS(cublasDgemmStridedBatched(e.blas, CUBLAS_OP_N, CUBLAS_OP_T, m2, nbk, nbk, &one,
-                                          Lb + (size_t)k0 * n + k0 + nbk, n, (long long)rr,
-                                          invD + (size_t)k * kNB * kNB, kNB, sD, &zero, panel, m2, sP,
-                                          nb));
-      count_launch();
-      k_copy_rect<<<dim3(ceil_div((long)m2 * nbk, 256), nb), 256, 0, e.stream>>>(
-          m2, nbk, panel, m2, (size_t)sP, Lb + (size_t)k0 * n + k0 + nbk, n, rr);
-      LR_CHECK_LAUNCH();
+    if (m2 > 0) {  // L[k1:, k] = A[k1:, k] invD_kk^T, in place (a CTA's rows are read by that CTA only)
+      double *P = Lb + (size_t)k0 * n + k0 + nbk;
+      st = bgemm_nt(m2, nbk, nbk, 1.0, P, n, rr, invD + (size_t)k * kNB * kNB, kNB, (size_t)sD, 0.0, P, n, rr, nb);
+      if (st != LR_OK) return st;
     }
   }
   int h = 0;
@@ -606,8 +738,9 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
   if (st != LR_OK) return st;
   if (!want_inverse) {
     // w = L^-1 aux: one CTA per utterance, aux sits in W and is overwritten by the i-vector
-    k_chol_solve<<<nb, kSolveThreads, R * sizeof(double), e.stream>>>(R, tv->d_Lb, rr,
-                                                                      tv->d_W + u0 * R);
+    const int nblk_s = (R + kNB - 1) / kNB;
+    k_chol_solve_blocked<<<nb, 256, (size_t)(nblk_s + 1) * kNB * sizeof(double), e.stream>>>(
+        R, tv->d_Lb, rr, tv->d_invD, nblk_s, tv->d_W + u0 * R);
     LR_CHECK_LAUNCH();
     return LR_OK;
   }

@@ -404,6 +404,58 @@ def test_block_boundaries(capi):
     assert np.allclose(s[256:256 + 256 * 20], m1.ravel(), rtol=2e-5, atol=2e-5 * np.abs(m1).max())
 
 
+def test_resident_em_operand_cache(capi, oracle):
+    """EM iterations over resident frames reuse the frames' converted tensor-core operand (kept with the
+    lr_feats handle; the normalised space is frozen while the mixture's global moments stay close).
+    Three chained device iterations against the oracle; a second handle without history must give the
+    same statistics; a changed buffer needs invalidate()."""
+    import torch
+    C, D, T = 256, 20, 40000
+    w, mean, cov = synth.make_ubm(C, D, seed=23)
+    X = synth.make_frames(w, mean, cov * 1.5, T, seed=24)
+    start = synth.perturb_ubm(w, mean, cov, seed=25, frac=1.0, scale=0.3)
+    xd = torch.tensor(X, device="cuda")
+    feats = capi.Feats(device_ptr=xd.data_ptr(), T=T, ldx=D, D=D)
+    g = capi.GMM(*start)
+    go = oracle.gmm(*start)
+    n = g.em_stats_len()
+    stats = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for it in range(3):
+        stats.zero_()
+        torch.cuda.synchronize()
+        g.em_accumulate_dev(feats, 0, T, 1.0, stats.data_ptr())
+        capi.synchronize()
+        s = stats.cpu().numpy()
+        llk_r, n_r, occ_r, m1_r, m2_r = oracle.em_accumulate(go, X)
+        assert abs(s[-2] - llk_r) < 1e-5 * abs(llk_r)
+        assert np.abs(s[:C] - occ_r).max() < 1e-4 * occ_r.max()
+        assert np.abs(s[C:C + C * D] - m1_r.ravel()).max() < 1e-4 * np.abs(m1_r).max()
+        # a handle without history (converts afresh with the model's current normalisation)
+        fresh = capi.Feats(device_ptr=xd.data_ptr(), T=T, ldx=D, D=D)
+        stats2 = torch.zeros(n, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        g.em_accumulate_dev(fresh, 0, T, 1.0, stats2.data_ptr())
+        capi.synchronize()
+        # (fp64 RED adds land in a different order from run to run: equal to rounding, not bit for bit)
+        assert torch.allclose(stats, stats2, rtol=1e-10, atol=1e-9)
+        fresh.close()
+        g.em_update_dev(stats.data_ptr())
+        capi.synchronize()
+        wn, mn, cn = oracle.em_get(go, occ_r, m1_r, m2_r)
+        go = oracle.gmm(wn, mn, cn)
+    # the buffer changes under the handle: stale until invalidate()
+    xd.mul_(1.05)
+    torch.cuda.synchronize()
+    feats.invalidate()
+    stats.zero_()
+    torch.cuda.synchronize()
+    g.em_accumulate_dev(feats, 0, T, 1.0, stats.data_ptr())
+    capi.synchronize()
+    llk_r, _, occ_r, _, _ = oracle.em_accumulate(go, np.ascontiguousarray(xd.cpu().numpy()))
+    s = stats.cpu().numpy()
+    assert abs(s[-2] - llk_r) < 1e-5 * abs(llk_r) and np.abs(s[:C] - occ_r).max() < 1e-4 * occ_r.max()
+
+
 def test_traintarget_validate_gmm_on_gpu(capi, golden_dir):
     """The reference's TrainTarget fixture (indicative pin, see tests/test_oracle_golden.py) through the CUDA
     EM-statistics path: occupancies -> MAPOccDep means vs the reference's adapted model."""
