@@ -193,6 +193,8 @@ def ivector_rate(torch, capi, dev, U=1024, R=400, reps=3):
     flop = U * (C * R * (R + 1) + 2 * C * D * R + R ** 3 / 3 + 2 * R * R)   # SURVEY.md §8d per utterance
     return {"value": U / dt, "unit": "i-vectors/s", "utterances": U, "rank": R, "ms": dt * 1e3,
             "tett_ms_once_per_T": t_tett * 1e3, "algorithmic_fp64_tflops": flop / dt / 1e12,
+            "contraction": "INT8 digit GEMM (k_gemm_i8, 6 planes of 7 bits, exact int32 UMMA classes in TMEM) + own "
+                           "fused batched Cholesky (DMMA)",
             "workload": "estimateW on resident BW statistics, 2048c/60d, R=400 (configs[2] per-GPU slice)"}
 
 
@@ -656,6 +658,9 @@ def main():
             "config": {"workload": "TrainWorld EM iteration, 2048c/60d diagonal UBM, 10M frames/GPU (configs[1])",
                        "frames_per_gpu": T, "components": C, "dim": D,
                        "l2": "inputs (2.4 GB/GPU) exceed L2, no flush needed",
+                       "operand_cache": "the frames' fp16 hi/lo tensor-core operand (512 B/frame) is converted by the "
+                                        "first warm-up step and reused by every later EM iteration over the same "
+                                        "resident frames (lr_feats handle), as a 5-iteration TrainWorld run would",
                        "kernel": {0: "auto", 1: "simt-fp32", 2: "tcgen05", 3: "tcgen05-two-pass"}[args.kernel],
                        "arithmetic": "fp16 hi/lo split operands (22 significand bits, 3 UMMA products), fp32 TMEM "
                                      "accumulation, fp64 statistics" if args.kernel != 1 else "fp32 FMA, fp64 statistics",

@@ -332,6 +332,7 @@ void writeIvTestScores(const Config &c, const Matrix &scores, const std::vector<
 int TrainWorld(Config &c);        // LIA_SpkDet/TrainWorld/src/TrainWorld.cpp:101
 int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:90
 int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:70 (mode classic)
+int ComputeJFAStats(Config &c);  // ComputeJFAStats.cpp:71-87 (per-session + per-speaker BW statistics)
 int IvExtractorUbmWeigth(Config &c);          // IvExtractor.cpp:151 (mode ubmWeight; the reference's spelling)
 int IvExtractorEigenDecomposition(Config &c); // IvExtractor.cpp:254 (mode eigenDecomposition)
 int TotalVariability(Config &c);  // LIA_SpkDet/TotalVariability/src/TotalVariability.cpp:71

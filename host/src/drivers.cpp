@@ -1,6 +1,8 @@
 // drivers.cpp -- int Foo(Config&) entry points with the reference programs' parameter names and
 // output formats.  Errors follow the reference: catch, print e.toString(), return 0.
+#include <map>
 #include <memory>
+#include <set>
 #include <algorithm>
 #include <fstream>
 #include <iostream>
@@ -218,6 +220,64 @@ int IvExtractor(Config &c) {
     tv.estimateTETt();
     tv.estimateW();
     tv.saveWbyFile(c);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ ComputeJFAStats
+// JFAAcc("Accumulate") + computeAndAccumulateJFAStat + saveAccs (ComputeJFAStats.cpp:71-87,
+// AccumulateJFAStat.cpp:520-576, 4779-4800).  Every element of an NDX line is a session file of that
+// line's speaker (JFATranslate, AccumulateJFAStat.h:99-111): speaker = line, session = running count; a
+// file listed twice keeps the indices of its first occurrence (_idxOfID).
+int ComputeJFAStats(Config &c) {
+  try {
+    XList ndx(c.getParam("ndxFilename"));
+    std::vector<std::string> files;
+    std::vector<int32_t> spkOfSession;
+    std::map<std::string, int> sessionOfFile;
+    int loc = 0;
+    for (auto &l : ndx.lines()) {
+      for (auto &f : l) {
+        if (!sessionOfFile.count(f)) sessionOfFile[f] = (int)spkOfSession.size();
+        files.push_back(f);
+        spkOfSession.push_back(loc);
+      }
+      loc++;
+    }
+    const size_t nSessions = spkOfSession.size(), nSpeakers = (size_t)loc;
+    if (nSessions == 0) LIA_THROW("ComputeJFAStats: empty ndx");
+    std::vector<std::string> unique;
+    {
+      std::set<std::string> seen;
+      for (auto &f : files)
+        if (seen.insert(f).second) unique.push_back(f);
+    }
+    MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+    FeatureServer fs(c, unique);
+    SegCluster sel = selectedSegments(c, fs, c.getParam("labelSelectedFrames"));
+    std::vector<lr_seg> segs;
+    for (const Seg &s : sel) {
+      lr_seg e;
+      e.begin = (int64_t)(fs.getFirstFeatureIndexOfASource(s.source) + s.begin);
+      e.length = s.length;
+      e.row = (int32_t)sessionOfFile[s.source];
+      e.pad_ = 0;
+      segs.push_back(e);
+    }
+    const size_t C = world.C, sv = (size_t)world.C * world.D;
+    Matrix Nh(nSessions, C), Fh(nSessions, sv), N(nSpeakers, C), F(nSpeakers, sv);
+    Gmm g(world, true);
+    LIA_CHECK(lr_jfa_bwstats(g.h(), fs.data(), fs.getFeatureCount(), fs.ld(), segs.data(), segs.size(), nSessions,
+                             spkOfSession.data(), nSpeakers, Nh.data.data(), Fh.data.data(), N.data.data(),
+                             F.data.data()));
+    const std::string path = c.getString("matrixFilesPath", ""), ext = c.getString("saveMatrixFilesExtension", "");
+    const std::string fmt = c.getString("saveMatrixFormat", "DB");
+    F.save(path + c.getString("firstOrderStatSpeaker", "F_X") + ext, fmt);
+    Fh.save(path + c.getString("firstOrderStatSession", "F_X_h") + ext, fmt);
+    Nh.save(path + c.getString("nullOrderStatSession", "N_h") + ext, fmt);
+    N.save(path + c.getString("nullOrderStatSpeaker", "N") + ext, fmt);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }

@@ -139,6 +139,13 @@ lr_status lr_gmm_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const 
 /* device-resident variant: d_N / d_F device doubles, d_segs host array (small) */
 lr_status lr_gmm_bwstats_dev(lr_gmm *g, const lr_feats *f, const lr_seg *segs, size_t n_segs,
                              size_t U, double *d_N, double *d_F);
+/* JFAAcc::computeAndAccumulateJFAStat (AccumulateJFAStat.cpp:520-576; threaded :600-700): the same
+ * posteriors accumulate per SESSION (N_h[n_sessions x C], F_h[n_sessions x C*D]) and per SPEAKER
+ * (N[n_speakers x C], F[n_speakers x C*D]); segs[].row = session (JFATranslate::sessionNb),
+ * speaker_of_session[session] = NDX line (locNb).  += like the reference's loop. */
+lr_status lr_jfa_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const lr_seg *segs, size_t n_segs,
+                         size_t n_sessions, const int32_t *speaker_of_session, size_t n_speakers, double *N_h,
+                         double *F_h, double *N, double *F);
 
 /* ---- a7: MixtureGDStat::computeAndAccumulateLLK (call sites ComputeTest.cpp:162-167,
  * TopGauss.cpp:166-192, AccumulateStat.cpp:77).

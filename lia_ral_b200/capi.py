@@ -276,6 +276,19 @@ class GMM:
                                     ct.c_size_t(U), _d(N), _d(F)))
         return N, F
 
+    def jfa_bwstats(self, X, segs, speaker_of_session, n_speakers):
+        """(N_h, F_h, N, F): per-session and per-speaker Baum-Welch statistics of JFAAcc; segs rows = sessions."""
+        X = _f32(X)
+        spk = np.ascontiguousarray(speaker_of_session, dtype=np.int32)
+        nh = len(spk)
+        N_h, F_h = np.zeros((nh, self.C)), np.zeros((nh, self.C * self.D))
+        N, F = np.zeros((n_speakers, self.C)), np.zeros((n_speakers, self.C * self.D))
+        sa, ns = _segs(segs)
+        _check(lib().lr_jfa_bwstats(self.h, X.ctypes.data_as(c_fp), ct.c_size_t(X.shape[0]),
+                                    ct.c_size_t(X.strides[0] // 4), sa, ct.c_size_t(ns), ct.c_size_t(nh),
+                                    spk.ctypes.data_as(c_ip), ct.c_size_t(n_speakers), _d(N_h), _d(F_h), _d(N), _d(F)))
+        return N_h, F_h, N, F
+
     def bwstats_dev(self, feats, segs, U, d_N_ptr, d_F_ptr):
         sa, ns = _segs(segs)
         _check(lib().lr_gmm_bwstats_dev(self.h, feats.h, sa, ct.c_size_t(ns), ct.c_size_t(U),

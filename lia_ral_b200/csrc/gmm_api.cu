@@ -191,6 +191,18 @@ lr_status for_each_host_block(const float *X, size_t ldx, long lo, long hi, Fn f
 
 __global__ void k_add_scalar(double *dst, double v) { *dst += v; }
 
+// session rows -> += session accumulator, += speaker accumulator (several sessions per speaker: RED adds)
+__global__ void k_jfa_fold(size_t n_sessions, size_t width, const int *__restrict__ spk,
+                           const double *__restrict__ t, double *__restrict__ acc_h, double *__restrict__ acc) {
+  const size_t total = n_sessions * width;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t h = i / width, k = i - h * width;
+    const double v = t[i];
+    acc_h[i] += v;
+    if (v != 0.0) atomicAdd(acc + (size_t)spk[h] * width + k, v);
+  }
+}
+
 }  // namespace
 }  // namespace lr
 
@@ -355,6 +367,65 @@ lr_status lr_gmm_bwstats_dev(lr_gmm *g, const lr_feats *f, const lr_seg *segs, s
     lr_status st = run_plan(g, f->d_x, f->ldx, plan, tc, 1.0, d_N, d_F, nullptr, nullptr);
     if (st != LR_OK) return st;
   }
+  return LR_OK;
+}
+
+// JFAAcc::computeAndAccumulateJFAStat (AccumulateJFAStat.cpp:520-576): the same posteriors feed a
+// per-SESSION accumulator (N_h, F_X_h) and a per-SPEAKER one (N, F_X).  The frames x components kernel
+// runs once with one statistics row per session; the speaker rows are folded from the session rows.
+lr_status lr_jfa_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const lr_seg *segs, size_t n_segs,
+                         size_t n_sessions, const int32_t *speaker_of_session, size_t n_speakers, double *N_h,
+                         double *F_h, double *N, double *F) {
+  LR_READY();
+  LR_REQUIRE(g && X && segs && speaker_of_session && N_h && F_h && N && F && n_sessions > 0 && n_speakers > 0,
+             "lr_jfa_bwstats: null argument");
+  LR_REQUIRE(ldx >= (size_t)g->D && T < (1ull << 32), "lr_jfa_bwstats: bad T / ldx");
+  for (size_t i = 0; i < n_sessions; i++)
+    LR_REQUIRE(speaker_of_session[i] >= 0 && (size_t)speaker_of_session[i] < n_speakers,
+               "lr_jfa_bwstats: session %zu belongs to speaker %d outside [0, %zu)", i, speaker_of_session[i],
+               n_speakers);
+  lr_status st = check_segs(segs, n_segs, T, n_sessions, true);
+  if (st != LR_OK) return st;
+  Engine &e = engine();
+  const size_t C = g->C, sv = C * g->D;
+  DevBuf<double> tN, tF, dNh, dFh, dN, dF;
+  DevBuf<int> dSpk;
+  LR_CUDA(tN.alloc(n_sessions * C));
+  LR_CUDA(tF.alloc(n_sessions * sv));
+  LR_CUDA(dNh.alloc(n_sessions * C));
+  LR_CUDA(dFh.alloc(n_sessions * sv));
+  LR_CUDA(dN.alloc(n_speakers * C));
+  LR_CUDA(dF.alloc(n_speakers * sv));
+  LR_CUDA(dSpk.alloc(n_sessions));
+  LR_CUDA(cudaMemsetAsync(tN.p, 0, n_sessions * C * sizeof(double), e.stream));
+  LR_CUDA(cudaMemsetAsync(tF.p, 0, n_sessions * sv * sizeof(double), e.stream));
+  LR_CUDA(cudaMemcpyAsync(dNh.p, N_h, n_sessions * C * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  LR_CUDA(cudaMemcpyAsync(dFh.p, F_h, n_sessions * sv * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  LR_CUDA(cudaMemcpyAsync(dN.p, N, n_speakers * C * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  LR_CUDA(cudaMemcpyAsync(dF.p, F, n_speakers * sv * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  LR_CUDA(cudaMemcpyAsync(dSpk.p, speaker_of_session, n_sessions * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  long lo, hi;
+  seg_range(segs, n_segs, T, lo, hi);
+  Plan plan;
+  lr_status sel = LR_OK;
+  const bool tc = tc_selected(g, &sel);
+  if (sel != LR_OK) return sel;
+  st = for_each_host_block(X, ldx, lo, hi, [&](const float *dX, long b0, long b1) {
+    build_plan(segs, n_segs, b0, b1, b0, true, tc, plan);
+    return run_plan(g, dX, ldx, plan, tc, 1.0, tN.p, tF.p, nullptr, nullptr);
+  });
+  if (st != LR_OK) return st;
+  k_jfa_fold<<<(unsigned)std::min<size_t>(4096, (n_sessions * C + 255) / 256), 256, 0, e.stream>>>(
+      n_sessions, C, dSpk.p, tN.p, dNh.p, dN.p);
+  LR_CHECK_LAUNCH();
+  k_jfa_fold<<<(unsigned)std::min<size_t>(65535, (n_sessions * sv + 255) / 256), 256, 0, e.stream>>>(
+      n_sessions, sv, dSpk.p, tF.p, dFh.p, dF.p);
+  LR_CHECK_LAUNCH();
+  LR_CUDA(cudaMemcpyAsync(N_h, dNh.p, n_sessions * C * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaMemcpyAsync(F_h, dFh.p, n_sessions * sv * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaMemcpyAsync(N, dN.p, n_speakers * C * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaMemcpyAsync(F, dF.p, n_speakers * sv * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
   return LR_OK;
 }
 

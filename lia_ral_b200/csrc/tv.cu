@@ -270,83 +270,16 @@ k_chol_solve(int n, const double *__restrict__ Lall, size_t stride, double *__re
   for (int i = tid; i < n; i += kSolveThreads) b[i] = xs[i];
 }
 
-// Blocked batched Cholesky (cusolverDnDpotrfBatched runs at ~1.4 TFLOP/s for R = 400..600:
-// measured 52 us per 600 x 600 matrix, profiles/r01_tv_breakdown.md).  Left-looking over 64-wide
-// block columns; everything heavy is a strided-batched DGEMM:
-//   A[k0:, k] -= L[k0:, 0:k0] L[k, 0:k0]^T          (DGEMM)
-//   L_kk = chol(A_kk), invD_kk = L_kk^-1             (k_diag_chol_inv, one CTA per matrix)
-//   L[k1:, k] = A[k1:, k] invD_kk^T                  (DGEMM, through a panel buffer)
-// The diagonal-block inverses are kept: the explicit inverse of the E-step reuses them.
+// Blocked batched Cholesky (cusolverDnDpotrfBatched runs at ~1.4 TFLOP/s for R = 400..600: measured
+// 52 us per 600 x 600 matrix, profiles/r01_tv_breakdown.md): left-looking over 64-wide block columns,
+// one CTA per matrix for the whole factorization (k_chol_fused below).  The inverses of the diagonal
+// blocks are kept: the blocked solve, the E-step's explicit inverse and the M-step reuse them.
 constexpr int kNB = 64;
-constexpr int kDiagThreads = 4 * kNB;  // four lanes per row / column (adjacent lanes of one warp)
-// Shared memory: ONE [64][65] array.  The factor occupies the lower triangle (columns <= row); the
-// inverse X = L^-1 (lower triangular too) is stored transposed-and-shifted in the strict upper part,
-// X[i][j] at Ls[j][i + 1] (i >= j: columns j+1 .. 64, the padding column included) -- 33 KB per CTA,
-// six CTAs per SM, which is what this latency-bound kernel needs.
-__global__ void __launch_bounds__(kDiagThreads)
-k_diag_chol_inv(int n, double *__restrict__ Lall, size_t stride, double *__restrict__ invD,
-                int nblk, int blk, int *__restrict__ bad) {
-  __shared__ double Ls[kNB][kNB + 1];
-  __shared__ int fail_flag;
-  const int mat = blockIdx.x;
-  const int k0 = blk * kNB, nb = min(kNB, n - k0);
-  double *L = Lall + (size_t)mat * stride;
-  const int j = threadIdx.x >> 2, q = threadIdx.x & 3;
-  if (threadIdx.x == 0) fail_flag = 0;
-  for (int c = q; c < nb; c += 4)
-    if (j < nb && j >= c) Ls[j][c] = L[(size_t)(k0 + c) * n + k0 + j];  // Ls[row][col], lower triangle
-  __syncthreads();
-  // right-looking Cholesky of the block: the four lanes of row j share its trailing update
-  for (int c = 0; c < nb; c++) {
-    double d = Ls[c][c];
-    if (!(d > 0.0)) {
-      if (threadIdx.x == 0) fail_flag = 1;
-      d = 1.0;
-    }
-    const double sq = sqrt(d);
-    const double ljc = (j > c && j < nb) ? Ls[j][c] / sq : 0.0;
-    __syncthreads();  // everyone has read column c as it was
-    if (q == 0) {
-      if (j == c) Ls[c][c] = sq;
-      else if (j > c && j < nb) Ls[j][c] = ljc;
-    }
-    __syncthreads();
-    if (j > c && j < nb) {
-#pragma unroll 4
-      for (int k = c + 1 + q; k <= j; k += 4) Ls[j][k] = fma(-ljc, Ls[k][c], Ls[j][k]);
-    }
-    // (the next column's reads of Ls[.][c + 1] are ordered by the barrier at the top of the loop body)
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && fail_flag) atomicExch(bad, mat + 1);
-  for (int c = q; c < nb; c += 4)
-    if (j < nb && j >= c) L[(size_t)(k0 + c) * n + k0 + j] = Ls[j][c];
-  // inverse of the block factor: the four lanes of column j split the dot product of the forward
-  // substitution (they sit in one warp: shuffles + __syncwarp, no block barrier).  Column j of X lives
-  // in row j of Ls (strict upper part), which only this quad touches.
-  __shared__ double rdiag[kNB];
-  if (q == 0 && j < nb) rdiag[j] = 1.0 / Ls[j][j];
-  __syncthreads();
-  for (int i = 0; i < nb; i++) {
-    double v = 0.0;
-    if (j < nb && i > j) {
-#pragma unroll 4
-      for (int k = j + q; k < i; k += 4) v = fma(-Ls[i][k], Ls[j][k + 1], v);
-    }
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (q == 0 && j < nb && i >= j) Ls[j][i + 1] = (i == j) ? rdiag[j] : v * rdiag[i];
-    __syncwarp();
-  }
-  __syncthreads();
-  double *out = invD + ((size_t)mat * nblk + blk) * kNB * kNB;  // column-major, ld = kNB: out[c * 64 + r] = X[r][c]
-  for (int c = q; c < kNB; c += 4) out[(size_t)c * kNB + j] = (j < nb && c < nb && j >= c) ? Ls[c][j + 1] : 0.0;
-}
-
-// Batched fp64 GEMM on the DMMA pipe for the panel work of the blocked Cholesky:
+// Batched fp64 GEMM on the DMMA pipe (the M-step's block substitutions; the tile loop of k_chol_fused):
 //     C[b] = alpha A[b] B[b]^T + beta C[b]        (all column-major: A m x K, B n x K, C m x n)
 // One CTA per 64 x 64 tile of one matrix of the batch; 8 warps, each a 16 x 32 warp tile of eight
-// mma.m8n8k4 accumulators; K in slabs of 16 through shared memory (k-major slabs, leading dimension
+// mma.m8n8k4 accumulators; K in slabs of 16 through shared memory, the next slab fetched into registers
+// while the current one is multiplied (k-major slabs, leading dimension
 // 72 doubles: the four k rows a fragment load touches fall on two disjoint bank halves).  The tile is
 // held in registers until the end, so C may alias A when a CTA's rows of A are read by nobody else
 // (the panel solve X = P invD^T overwrites P).
@@ -356,10 +289,12 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+// AT / BT: the operand is given TRANSPOSED in memory (k contiguous instead of m / n):
+//   !AT: A(m, k) at A[k lda + m]      AT: A(m, k) at A[m lda + k]      (same for B with n)
+template <bool AT, bool BT>
 __global__ void __launch_bounds__(256)
-k_bgemm_nt(int M, int N, int K, double alpha, const double *A, int lda, size_t strideA,
-           const double *B, int ldb, size_t strideB, double beta, double *C, int ldc,
-           size_t strideC) {
+k_bgemm(int M, int N, int K, double alpha, const double *A, int lda, size_t strideA, const double *B, int ldb,
+        size_t strideB, double beta, double *C, int ldc, size_t strideC) {
   __shared__ double As[kBgSlab][kBgLd], Bs[kBgSlab][kBgLd];
   const int m0 = blockIdx.x * kBgTile, n0 = blockIdx.y * kBgTile;
   A += (size_t)blockIdx.z * strideA;
@@ -368,24 +303,38 @@ k_bgemm_nt(int M, int N, int K, double alpha, const double *A, int lda, size_t s
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;  // warp tile origin inside the CTA tile
   const int fr = lane >> 2, fk = lane & 3;                // fragment row (m or n) and k
-  const int lk = threadIdx.x >> 4, l4 = (threadIdx.x & 15) * 4;  // slab loader: k row, first of 4 m / n
+  // slab loaders: 4 consecutive elements along the contiguous index per thread
+  const int lk = threadIdx.x >> 4, l4 = (threadIdx.x & 15) * 4;  // plain: k row, first of 4 m / n
+  const int tr = threadIdx.x >> 2, tk = (threadIdx.x & 3) * 4;   // transposed: m / n row, first of 4 k
   double acc[2][4][2] = {};
   double ra[4], rb[4];  // next slab, fetched while the current one is multiplied
   auto fetch = [&](int k0) {
-    const int k = k0 + lk;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const int m = m0 + l4 + e, n = n0 + l4 + e;
-      ra[e] = (k < K && m < M) ? A[(size_t)k * lda + m] : 0.0;
-      rb[e] = (k < K && n < N) ? B[(size_t)k * ldb + n] : 0.0;
+      if (AT) {
+        const int m = m0 + tr, k = k0 + tk + e;
+        ra[e] = (k < K && m < M) ? A[(size_t)m * lda + k] : 0.0;
+      } else {
+        const int m = m0 + l4 + e, k = k0 + lk;
+        ra[e] = (k < K && m < M) ? A[(size_t)k * lda + m] : 0.0;
+      }
+      if (BT) {
+        const int n = n0 + tr, k = k0 + tk + e;
+        rb[e] = (k < K && n < N) ? B[(size_t)n * ldb + k] : 0.0;
+      } else {
+        const int n = n0 + l4 + e, k = k0 + lk;
+        rb[e] = (k < K && n < N) ? B[(size_t)k * ldb + n] : 0.0;
+      }
     }
   };
   fetch(0);
   for (int k0 = 0; k0 < K; k0 += kBgSlab) {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      As[lk][l4 + e] = ra[e];
-      Bs[lk][l4 + e] = rb[e];
+      if (AT) As[tk + e][tr] = ra[e];
+      else As[lk][l4 + e] = ra[e];
+      if (BT) Bs[tk + e][tr] = rb[e];
+      else Bs[lk][l4 + e] = rb[e];
     }
     __syncthreads();
     if (k0 + kBgSlab < K) fetch(k0 + kBgSlab);
@@ -418,13 +367,281 @@ k_bgemm_nt(int M, int N, int K, double alpha, const double *A, int lda, size_t s
       }
   }
 }
-inline lr_status bgemm_nt(int M, int N, int K, double alpha, const double *A, int lda, size_t sA, const double *B,
-                          int ldb, size_t sB, double beta, double *C, int ldc, size_t sC, int batch) {
+// C = alpha op(A) op(B)^T + beta C over a batch; ta / tb: operand stored with k contiguous
+inline lr_status bgemm(bool ta, bool tb, int M, int N, int K, double alpha, const double *A, int lda, size_t sA,
+                       const double *B, int ldb, size_t sB, double beta, double *C, int ldc, size_t sC, int batch) {
   if (M <= 0 || N <= 0 || batch <= 0) return LR_OK;
   dim3 grid((unsigned)ceil_div(M, kBgTile), (unsigned)ceil_div(N, kBgTile), (unsigned)batch);
-  k_bgemm_nt<<<grid, 256, 0, engine().stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC);
+  cudaStream_t st = engine().stream;
+  if (!ta && !tb) k_bgemm<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC);
+  else if (!ta && tb) k_bgemm<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC);
+  else if (ta && !tb) k_bgemm<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC);
+  else k_bgemm<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC);
   LR_CHECK_LAUNCH();
   return LR_OK;
+}
+inline lr_status bgemm_nt(int M, int N, int K, double alpha, const double *A, int lda, size_t sA, const double *B,
+                          int ldb, size_t sB, double beta, double *C, int ldc, size_t sC, int batch) {
+  return bgemm(false, false, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+}
+
+// ---- fused batched Cholesky: ONE launch factors every matrix of the batch -------------------------
+// A CTA owns one matrix and runs the whole left-looking factorization on it (the launches-per-block-step
+// version above it spent more time in launch gaps and half-empty waves than in arithmetic, and its
+// latency-bound 64 x 64 diagonal factorizations ran alone on the machine; here they overlap with the DMMA
+// work of the other CTA on the SM).  Per block column k and 64-row tile t of it:
+//   acc = L[tile rows, 0:k0] L[k rows, 0:k0]^T          (DMMA, slabs through shared memory)
+//   P   = A[tile, k] - acc                                (fragments)
+//   t = 0: L_kk = chol(P), X = L_kk^-1 (shared memory, 16-wide sub-blocks) -> global + invD
+//   t > 0: L[tile, k] = P X^T                             (DMMA: P through shared memory, X from Ls)
+// The factor is read back by the same CTA only: __syncthreads orders its global writes and reads.
+// (the panel tile Ps aliases the K slabs As / Bs: they are never live together)
+constexpr size_t kCholFusedSmem = (kNB * kBgLd + kNB * (kNB + 1) + kNB) * sizeof(double);
+
+// acc += A_tile B_tile^T over K (A(m, k) at A[k lda + m], B(n, k) at B[k ldb + n]; rows >= mv / nv are zero)
+__device__ __forceinline__ void chol_tile_mma(double (&acc)[2][4][2], const double *A, int lda, int mv,
+                                              const double *B, int ldb, int nv, int K, double (*As)[kBgLd],
+                                              double (*Bs)[kBgLd]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int lk = threadIdx.x >> 4, l4 = (threadIdx.x & 15) * 4;
+  double ra[4], rb[4];
+  auto fetch = [&](int k0) {
+    const int k = k0 + lk;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      ra[e] = (k < K && l4 + e < mv) ? A[(size_t)k * lda + l4 + e] : 0.0;
+      rb[e] = (k < K && l4 + e < nv) ? B[(size_t)k * ldb + l4 + e] : 0.0;
+    }
+  };
+  if (K > 0) fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kBgSlab) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      As[lk][l4 + e] = ra[e];
+      Bs[lk][l4 + e] = rb[e];
+    }
+    __syncthreads();
+    if (k0 + kBgSlab < K) fetch(k0 + kBgSlab);
+#pragma unroll
+    for (int kk = 0; kk < kBgSlab; kk += 4) {
+      double a[2], b[4];
+#pragma unroll
+      for (int x = 0; x < 2; x++) a[x] = As[kk + fk][wm + 8 * x + fr];
+#pragma unroll
+      for (int y = 0; y < 4; y++) b[y] = Bs[kk + fk][wn + 8 * y + fr];
+#pragma unroll
+      for (int x = 0; x < 2; x++)
+#pragma unroll
+        for (int y = 0; y < 4; y++) dmma_8x8x4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+    }
+    __syncthreads();
+  }
+}
+
+// packed != nullptr: the input matrices are PACKED lower triangles (column j holds rows j..n-1) with
+// diag_add on the diagonal -- the output of the L = N TETt digit GEMM, or the M-step's A accumulators;
+// the factor is still written to the full column-major Lall.
+__global__ void __launch_bounds__(256, 3)
+k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ packed, double diag_add,
+             double *__restrict__ invD, int nblk, int *__restrict__ bad) {
+  extern __shared__ double csm[];
+  double (*As)[kBgLd] = reinterpret_cast<double (*)[kBgLd]>(csm);
+  double (*Bs)[kBgLd] = reinterpret_cast<double (*)[kBgLd]>(csm + kBgSlab * kBgLd);
+  double (*Ps)[kBgLd] = reinterpret_cast<double (*)[kBgLd]>(csm);
+  double (*Ls)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(csm + kNB * kBgLd);
+  double *rdiag = csm + kNB * kBgLd + kNB * (kNB + 1);
+  __shared__ int fail_flag;
+  const int mat = blockIdx.x;
+  double *L = Lall + (size_t)mat * stride;
+  const size_t rp = (size_t)n * (n + 1) / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int j = threadIdx.x >> 2, q = threadIdx.x & 3;  // diagonal-block roles: row / column j, lane q of its quad
+  if (threadIdx.x == 0) fail_flag = 0;
+  for (int k = 0; k < nblk; k++) {
+    const int k0 = k * kNB, nb = min(kNB, n - k0);
+    for (int m0 = k0; m0 < n; m0 += kNB) {
+      const int mv = min(kNB, n - m0);
+      double acc[2][4][2] = {};
+      chol_tile_mma(acc, L + m0, n, mv, L + k0, n, nb, k0, As, Bs);
+      // P = A[tile, k] - acc, in fragment layout: (row, col) = (wm + 8x + fr, wn + 8y + 2fk + z)
+#pragma unroll
+      for (int x = 0; x < 2; x++)
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+          for (int z = 0; z < 2; z++) {
+            const int r = wm + 8 * x + fr, c = wn + 8 * y + 2 * fk + z;
+            double a = 0.0;
+            if (r < mv && c < nb) {
+              const int row = m0 + r, col = k0 + c;
+              if (!packed) a = L[(size_t)col * n + row];
+              else if (row >= col)
+                a = packed[(size_t)mat * rp + packed_off(n, col) + (row - col)] + (row == col ? diag_add : 0.0);
+            }
+            acc[x][y][z] = a - acc[x][y][z];
+          }
+      if (m0 == k0) {
+        // ---- diagonal block: factor + inverse in shared memory
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+          for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int z = 0; z < 2; z++) Ls[wm + 8 * x + fr][wn + 8 * y + 2 * fk + z] = acc[x][y][z];
+        __syncthreads();
+        // rows / columns past the matrix edge: identity, so the arithmetic below needs no masks
+        if (threadIdx.x >= nb && threadIdx.x < kNB) {
+          for (int c = 0; c < (int)threadIdx.x; c++) Ls[threadIdx.x][c] = 0.0;
+          Ls[threadIdx.x][threadIdx.x] = 1.0;
+        }
+        __syncthreads();
+        // Blocked in 16-wide sub-blocks so that the latency-bound column recurrence is 16 columns of ONE
+        // warp (barriers = __syncwarp) instead of 64 columns of the whole CTA; everything else is
+        // element-parallel over the 256 threads.  X[i][j] (i >= j) lives at Ls[j][i + 1].
+        constexpr int kSB = 16;
+        for (int s0 = 0; s0 < kNB; s0 += kSB) {
+          if (warp == 0) {
+            const int rr = lane >> 1, qq = lane & 1, r = s0 + rr;
+            // (a) factor the 16 x 16 diagonal sub-block
+            for (int cc = 0; cc < kSB; cc++) {
+              const int c = s0 + cc;
+              double d = Ls[c][c];
+              if (!(d > 0.0)) {
+                fail_flag = 1;
+                d = 1.0;
+              }
+              const double rs = rsqrt(d);
+              const double ljc = rr > cc ? Ls[r][c] * rs : 0.0;
+              __syncwarp();
+              if (qq == 0) {
+                if (rr == cc) Ls[c][c] = d * rs;
+                else if (rr > cc) Ls[r][c] = ljc;
+              }
+              __syncwarp();
+              if (rr > cc)
+                for (int kk = cc + 1 + qq; kk <= rr; kk += 2) Ls[r][s0 + kk] = fma(-ljc, Ls[s0 + kk][c], Ls[r][s0 + kk]);
+              __syncwarp();
+            }
+            // ... and its inverse: column rr by the lane pair (rr, qq)
+            if (qq == 0) rdiag[r] = 1.0 / Ls[r][r];
+            __syncwarp();
+            for (int ii = 0; ii < kSB; ii++) {
+              double v = 0.0;
+              if (ii > rr)
+                for (int kk = rr + qq; kk < ii; kk += 2) v = fma(-Ls[s0 + ii][s0 + kk], Ls[r][s0 + kk + 1], v);
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              if (qq == 0 && ii >= rr) Ls[r][s0 + ii + 1] = (ii == rr) ? rdiag[r] : v * rdiag[s0 + ii];
+              __syncwarp();
+            }
+          }
+          __syncthreads();
+          const int nr = kNB - s0 - kSB;  // rows below the sub-block
+          if (nr > 0) {
+            // (b) panel below it: L[r, s0 + cc] = sum_{k <= cc} P[r, s0 + k] X[s0 + cc][s0 + k]
+            double pv[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              const int e = threadIdx.x + 256 * u;
+              pv[u] = 0.0;
+              if (e < nr * kSB) {
+                const int r = s0 + kSB + e / kSB, cc = e % kSB;
+                double v = 0.0;
+                for (int kk = 0; kk <= cc; kk++) v = fma(Ls[r][s0 + kk], Ls[s0 + kk][s0 + cc + 1], v);
+                pv[u] = v;
+              }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              const int e = threadIdx.x + 256 * u;
+              if (e < nr * kSB) Ls[s0 + kSB + e / kSB][s0 + e % kSB] = pv[u];
+            }
+            __syncthreads();
+            // (c) trailing update of the lower triangle: A[r][c] -= sum_cc L[r, s0 + cc] L[c, s0 + cc]
+            for (int e = threadIdx.x; e < nr * nr; e += 256) {
+              const int r = s0 + kSB + e / nr, c = s0 + kSB + e % nr;
+              if (c > r) continue;
+              double v = Ls[r][c];
+#pragma unroll
+              for (int cc = 0; cc < kSB; cc++) v = fma(-Ls[r][s0 + cc], Ls[c][s0 + cc], v);
+              Ls[r][c] = v;
+            }
+            __syncthreads();
+          }
+        }
+        for (int c = q; c < nb; c += 4)
+          if (j < nb && j >= c) L[(size_t)(k0 + c) * n + k0 + j] = Ls[j][c];
+        // off-diagonal 16 x 16 blocks of X = L^-1, one block diagonal at a time:
+        //   X_ij = -X_ii (sum_{kb = j .. i-1} L_i,kb X_kb,j);   T goes through Ps (free during this tile)
+        double *Tm = &Ps[0][0];
+        for (int dlev = 1; dlev < kNB / kSB; dlev++) {
+          const int nblkd = kNB / kSB - dlev;
+          const int ea = threadIdx.x >> 4, eb = threadIdx.x & 15;
+          for (int u = 0; u < nblkd; u++) {
+            const int bi = dlev + u, bj = u;  // block row / column
+            double v = 0.0;
+            const int row = kSB * bi + ea, col = kSB * bj + eb;
+            for (int m = col; m < kSB * bi; m++) v = fma(Ls[row][m], Ls[col][m + 1], v);  // X[m][col], m >= col
+            Tm[u * 256 + threadIdx.x] = v;
+          }
+          __syncthreads();
+          for (int u = 0; u < nblkd; u++) {
+            const int bi = dlev + u, bj = u;
+            const int row = kSB * bi + ea, col = kSB * bj + eb;
+            double v = 0.0;
+            for (int m = 0; m <= ea; m++) v = fma(Ls[kSB * bi + m][row + 1], Tm[u * 256 + m * 16 + eb], v);  // X[row][16 bi + m]
+            Ls[col][row + 1] = -v;
+          }
+          __syncthreads();
+        }
+        double *out = invD + ((size_t)mat * nblk + k) * kNB * kNB;  // column-major, ld 64: out[c 64 + r] = X[r][c]
+        for (int c = q; c < kNB; c += 4) out[(size_t)c * kNB + j] = (j < nb && c < nb && j >= c) ? Ls[c][j + 1] : 0.0;
+      } else {
+        // ---- panel tile: L[tile, k] = P X^T.  P goes through shared memory as the k-major A operand
+        // (Ps[c'][r]); B(n = c, k = c') = X[c][c'] = Ls[c'][c + 1] for c' <= c, zero above the diagonal
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+          for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int z = 0; z < 2; z++) Ps[wn + 8 * y + 2 * fk + z][wm + 8 * x + fr] = acc[x][y][z];
+        __syncthreads();
+        double out[2][4][2] = {};
+#pragma unroll 4
+        for (int kk = 0; kk < kNB; kk += 4) {
+          const int kc = kk + fk;
+          double a[2], b[4];
+#pragma unroll
+          for (int x = 0; x < 2; x++) a[x] = Ps[kc][wm + 8 * x + fr];
+#pragma unroll
+          for (int y = 0; y < 4; y++) {
+            const int c = wn + 8 * y + fr;
+            b[y] = (kc <= c && c < nb) ? Ls[kc][c + 1] : 0.0;
+          }
+#pragma unroll
+          for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) dmma_8x8x4(out[x][y][0], out[x][y][1], a[x], b[y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+          for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int z = 0; z < 2; z++) {
+              const int r = wm + 8 * x + fr, c = wn + 8 * y + 2 * fk + z;
+              if (r < mv && c < nb) L[(size_t)(k0 + c) * n + m0 + r] = out[x][y][z];
+            }
+        __syncthreads();  // Ps is reused by the next tile
+      }
+    }
+    __syncthreads();  // block column k is in global memory for the updates of k + 1
+  }
+  if (threadIdx.x == 0 && fail_flag) atomicExch(bad, mat + 1);
 }
 
 // Solve L L^T x = b for ONE right-hand side per matrix with the factor of chol_batched AND its
@@ -656,7 +873,7 @@ lr_status check_factor(lr_tv *tv, int n, const char *what) {
 // In-place blocked Cholesky of `nb` column-major n x n matrices (lower triangle; the strict upper
 // triangle is left with garbage).  invD receives the inverses of the diagonal-block factors;
 // panel: [nb x n x kNB] scratch.
-lr_status chol_batched(lr_tv *tv, double *Lb, int n, int nb, double *invD, double *panel,
+lr_status chol_batched(lr_tv *tv, double *Lb, int n, int nb, double *invD, const double *packed, double diag_add,
                        const char *what) {
   Engine &e = engine();
   const size_t rr = (size_t)n * n;
@@ -664,21 +881,13 @@ lr_status chol_batched(lr_tv *tv, double *Lb, int n, int nb, double *invD, doubl
   const long long sD = (long long)nblk * kNB * kNB;
   int *bad = tv->d_info;
   LR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), e.stream));
-  for (int k = 0; k < nblk; k++) {
-    const int k0 = k * kNB, nbk = std::min(kNB, n - k0), m = n - k0, m2 = m - nbk;
-    lr_status st;
-    if (k0 > 0) {  // A[k0:, k] -= L[k0:, 0:k0] L[k, 0:k0]^T
-      st = bgemm_nt(m, nbk, k0, -1.0, Lb + k0, n, rr, Lb + k0, n, rr, 1.0, Lb + (size_t)k0 * n + k0, n, rr, nb);
-      if (st != LR_OK) return st;
-    }
-    k_diag_chol_inv<<<nb, kDiagThreads, 0, e.stream>>>(n, Lb, rr, invD, nblk, k, bad);
-    LR_CHECK_LAUNCH();
-    if (m2 > 0) {  // L[k1:, k] = A[k1:, k] invD_kk^T, in place (a CTA's rows are read by that CTA only)
-      double *P = Lb + (size_t)k0 * n + k0 + nbk;
-      st = bgemm_nt(m2, nbk, nbk, 1.0, P, n, rr, invD + (size_t)k * kNB * kNB, kNB, (size_t)sD, 0.0, P, n, rr, nb);
-      if (st != LR_OK) return st;
-    }
+  bool &attr = e.attr_set[Engine::kAttrTvDiag];
+  if (!attr) {
+    LR_CUDA(cudaFuncSetAttribute(k_chol_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholFusedSmem));
+    attr = true;
   }
+  k_chol_fused<<<nb, 256, kCholFusedSmem, e.stream>>>(n, Lb, rr, packed, diag_add, invD, nblk, bad);
+  LR_CHECK_LAUNCH();
   int h = 0;
   LR_CUDA(cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
   LR_CUDA(cudaStreamSynchronize(e.stream));
@@ -714,9 +923,6 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
                           tv->d_N + u0 * C, C, &zero, tv->d_Eb, rp));
     count_launch();
   }
-  k_unpack_lower<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>((size_t)nb, R, tv->d_Eb, tv->d_Lb,
-                                                                   1.0, 0);
-  LR_CHECK_LAUNCH();
   // aux[nb x R] = Fc_b[nb x sv] * Ts^T  -> written straight into W
   if (s > 0) {
     DevBuf<unsigned char> pF;
@@ -733,7 +939,8 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
                           (int)tv->sv, tv->d_F + u0 * tv->sv, (int)tv->sv, &zero, tv->d_W + u0 * R, R));
     count_launch();
   }
-  lr_status st = chol_batched(tv, tv->d_Lb, R, nb, tv->d_invD, tv->d_Eb,
+  // the Cholesky reads L = I + (packed product in Eb) directly and writes its factor to Lb
+  lr_status st = chol_batched(tv, tv->d_Lb, R, nb, tv->d_invD, tv->d_Eb, 1.0,
                               "i-vector posterior precision L");
   if (st != LR_OK) return st;
   if (!want_inverse) {
@@ -752,6 +959,9 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
   const double mone = -1.0;
   LR_CUDA(cudaMemsetAsync(tv->d_Yb, 0, (size_t)nb * rr * sizeof(double), e.stream));
   const long long sD = (long long)nblk * kNB * kNB;
+  // (cuBLAS fp64 for these three product families: the repo's DMMA kernel k_bgemm, which runs the Cholesky
+  // panels and the M-step, reaches 16 TFLOP/s on them against cuBLAS's 36 -- measured, r2c20 -- so the
+  // library keeps them until that kernel is tiled wider)
   for (int i = 0; i < nblk; i++) {
     const int r0 = i * kNB, nbi = std::min(kNB, R - r0);
     if (i > 0) {
@@ -1161,27 +1371,46 @@ lr_status lr_tv_update_t_range(lr_tv *tv, int c0, int c1) {
   const int R = tv->R, D = tv->D, nc = c1 - c0;
   const size_t rr = (size_t)R * R;
   const double one = 1.0;
-  // factor a copy of A in the TETt buffer (TETt is re-estimated from the new T anyway)
-  k_unpack_lower<<<grid_for((size_t)nc * rr), 256, 0, e.stream>>>((size_t)nc, R, tv->A() + (size_t)c0 * tv->Rp(),
-                                                                 tv->d_tett + (size_t)c0 * rr, 0.0, 0);
-  LR_CHECK_LAUNCH();
-  LR_CUSOLVER(cusolverDnDpotrfBatched(tv->solver, CUBLAS_FILL_MODE_LOWER, R, tv->d_ptr_A + c0, R,
-                                      tv->d_info, nc));
-  count_launch();
-  lr_status st = check_factor(tv, nc, "M-step accumulator A_c");
-  if (st != LR_OK) return st;
-  // T_c = A_c^-1 Cmx_c: column-major we hold T_c^T (D x R, ld sv): X^T L L^T = Cmx_c^T
+  // the factors of the (packed) A_c go to the TETt buffer (TETt is re-estimated from the new T anyway)
+  // T_c = A_c^-1 Cmx_c.  Held as T_c^T: the D x R column-major view (ld sv) of the row-major slice
+  // T[:, cD:(c+1)D]; with A_c = L L^T the system is Z L L^T = B (B = Cmx_c^T, copied in first), solved block
+  // column by block column with the factor's diagonal-block inverses -- the same two panel products as the
+  // Cholesky itself (own DMMA kernel; the reference inverts A_c, :985-990):
+  //   forward   Y_j = (B_j - sum_{k<j} Y_k L_jk^T) invD_jj^T
+  //   backward  Z_j = (Y_j - sum_{k>j} Z_k L_kj)   invD_jj
   LR_CUDA(cudaMemcpy2DAsync(tv->d_T + (size_t)c0 * D, tv->sv * sizeof(double), tv->Cmx() + (size_t)c0 * D,
                             tv->sv * sizeof(double), (size_t)nc * D * sizeof(double), R,
                             cudaMemcpyDeviceToDevice, e.stream));
-  LR_CUBLAS(cublasDtrsmBatched(e.blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T,
-                               CUBLAS_DIAG_NON_UNIT, D, R, &one, tv->d_ptr_A + c0, R, tv->d_ptr_Tc + c0,
-                               (int)tv->sv, nc));
-  count_launch();
-  LR_CUBLAS(cublasDtrsmBatched(e.blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N,
-                               CUBLAS_DIAG_NON_UNIT, D, R, &one, tv->d_ptr_A + c0, R, tv->d_ptr_Tc + c0,
-                               (int)tv->sv, nc));
-  count_launch();
+  const int nblk = (R + kNB - 1) / kNB, ldt = (int)tv->sv;
+  const size_t sD = (size_t)nblk * kNB * kNB;
+  for (int b0 = 0; b0 < nc; b0 += tv->batch) {
+    const int nbm = std::min(tv->batch, nc - b0);
+    double *Ab = tv->d_tett + (size_t)(c0 + b0) * rr;
+    double *Tc = tv->d_T + (size_t)(c0 + b0) * D;
+    lr_status st = chol_batched(tv, Ab, R, nbm, tv->d_invD, tv->A() + (size_t)(c0 + b0) * tv->Rp(), 0.0,
+                                "M-step accumulator A_c");
+    if (st != LR_OK) return st;
+    for (int j = 0; j < nblk; j++) {
+      const int j0 = j * kNB, nbj = std::min(kNB, R - j0);
+      double *P = Tc + (size_t)j0 * ldt;
+      if (j0 > 0 && (st = bgemm(false, false, D, nbj, j0, -1.0, Tc, ldt, (size_t)D, Ab + j0, R, rr, 1.0, P, ldt,
+                                (size_t)D, nbm)) != LR_OK)
+        return st;
+      if ((st = bgemm(false, false, D, nbj, nbj, 1.0, P, ldt, (size_t)D, tv->d_invD + (size_t)j * kNB * kNB, kNB, sD,
+                      0.0, P, ldt, (size_t)D, nbm)) != LR_OK)
+        return st;
+    }
+    for (int j = nblk - 1; j >= 0; j--) {
+      const int j0 = j * kNB, nbj = std::min(kNB, R - j0), j1 = j0 + nbj;
+      double *P = Tc + (size_t)j0 * ldt;
+      if (j1 < R && (st = bgemm(false, true, D, nbj, R - j1, -1.0, Tc + (size_t)j1 * ldt, ldt, (size_t)D,
+                                Ab + (size_t)j0 * R + j1, R, rr, 1.0, P, ldt, (size_t)D, nbm)) != LR_OK)
+        return st;
+      if ((st = bgemm(false, true, D, nbj, nbj, 1.0, P, ldt, (size_t)D, tv->d_invD + (size_t)j * kNB * kNB, kNB, sD,
+                      0.0, P, ldt, (size_t)D, nbm)) != LR_OK)
+        return st;
+    }
+  }
   LR_CUDA(cudaStreamSynchronize(e.stream));
   return LR_OK;
 }

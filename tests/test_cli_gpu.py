@@ -164,6 +164,35 @@ def test_train_world_multi_stream_cli(world, oracle):
     assert abs(w3.sum() - 1.0) < 1e-9 and np.abs(mean3 - start[1]).max() > 1e-3
 
 
+def test_compute_jfa_stats_cli(world, oracle):
+    """ComputeJFAStats (ComputeJFAStats.cpp:71-87): N, F_X per speaker (NDX line) and N_h, F_X_h per session
+    (every element of a line is a session file, JFATranslate)."""
+    d, C, D = world["dir"], world["C"], world["D"]
+    ndx = [["utt0", "utt1"], ["utt2"], ["utt3", "utt4", "utt5"]]
+    lf.write_lines(d / "jfa.ndx", ndx)
+    lf.write_cfg(d / "jfa.cfg", **world["common"], ndxFilename=str(d / "jfa.ndx"), inputWorldFilename="wld",
+                 nullOrderStatSpeaker="N_jfa", firstOrderStatSpeaker="FX_jfa", nullOrderStatSession="Nh_jfa",
+                 firstOrderStatSession="FXh_jfa")
+    _run("ComputeJFAStats", d / "jfa.cfg")
+    N, F = lf.read_db(d / "N_jfa.mat"), lf.read_db(d / "FX_jfa.mat")
+    Nh, Fh = lf.read_db(d / "Nh_jfa.mat"), lf.read_db(d / "FXh_jfa.mat")
+    assert N.shape == (3, C) and F.shape == (3, C * D) and Nh.shape == (6, C) and Fh.shape == (6, C * D)
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    session = 0
+    for spk_i, line in enumerate(ndx):
+        n_spk, f_spk = np.zeros(C), np.zeros(C * D)
+        for u in line:
+            X = np.ascontiguousarray(world["utts"][u][_selected(u, world["utts"][u])])
+            n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+            assert np.abs(Nh[session] - n1[0]).max() < 1e-4 * np.abs(n1).max()
+            assert np.abs(Fh[session] - f1[0]).max() < 1e-4 * np.abs(f1).max()
+            n_spk += n1[0]
+            f_spk += f1[0]
+            session += 1
+        assert np.abs(N[spk_i] - n_spk).max() < 1e-4 * np.abs(n_spk).max()
+        assert np.abs(F[spk_i] - f_spk).max() < 1e-4 * np.abs(f_spk).max()
+
+
 def test_ivector_and_tv_cli(world, oracle):
     d, C, D, R = world["dir"], world["C"], world["D"], 5
     invvar = (1.0 / world["cov"]).reshape(-1)

@@ -456,6 +456,38 @@ def test_resident_em_operand_cache(capi, oracle):
     assert abs(s[-2] - llk_r) < 1e-5 * abs(llk_r) and np.abs(s[:C] - occ_r).max() < 1e-4 * occ_r.max()
 
 
+@pytest.mark.parametrize("kern", [1, 0], ids=["simt", "auto"])
+def test_jfa_bwstats(capi, oracle, kern):
+    """JFAAcc::computeAndAccumulateJFAStat (AccumulateJFAStat.cpp:520-576): per-session and per-speaker
+    accumulators from one pass; several sessions per speaker, a session in two segments, += semantics."""
+    C, D, T = 256, 20, 6000
+    w, mean, cov = synth.make_ubm(C, D, seed=71)
+    X = synth.make_frames(w, mean, cov * 2.0, T, seed=72)
+    capi.set_gmm_kernel(kern)
+    try:
+        g, o = capi.GMM(w, mean, cov), oracle.gmm(w, mean, cov)
+        # 5 sessions, 3 speakers; session 1 is made of two segments; frames 5500.. are in no segment
+        segs = [(0, 1000, 0), (1000, 700, 1), (3000, 400, 1), (1700, 1300, 2), (3400, 1100, 3), (4500, 1000, 4)]
+        spk = [0, 0, 1, 2, 2]
+        N_h, F_h, N, F = g.jfa_bwstats(X, segs, spk, 3)
+        f2r = np.full(T, -1, dtype=np.int32)
+        for b, n, r in segs:
+            f2r[b:b + n] = r
+        sel = f2r >= 0
+        Nh_r, Fh_r = oracle.bwstats(o, np.ascontiguousarray(X[sel]), f2r[sel], 5)
+        tol = 1e-4 if kern == 0 else 1e-5
+        assert np.abs(N_h - Nh_r).max() <= tol * np.abs(Nh_r).max()
+        assert np.abs(F_h - Fh_r).max() <= tol * np.abs(Fh_r).max()
+        for s_ in range(3):
+            rows = [h for h in range(5) if spk[h] == s_]
+            assert np.allclose(N[s_], N_h[rows].sum(0), rtol=1e-12, atol=1e-12)
+            assert np.allclose(F[s_], F_h[rows].sum(0), rtol=1e-12, atol=1e-9)
+        # (posteriors of the tensor-core path are fp16 x power of two: the total occupancy is exact to ~4e-6)
+        assert abs(N.sum() - sel.sum()) < 2e-5 * sel.sum()
+    finally:
+        capi.set_gmm_kernel(0)
+
+
 def test_traintarget_validate_gmm_on_gpu(capi, golden_dir):
     """The reference's TrainTarget fixture (indicative pin, see tests/test_oracle_golden.py) through the CUDA
     EM-statistics path: occupancies -> MAPOccDep means vs the reference's adapted model."""
