@@ -398,14 +398,17 @@ inline lr_status bgemm_nt(int M, int N, int K, double alpha, const double *A, in
 // (the panel tile Ps aliases the K slabs As / Bs: they are never live together)
 constexpr size_t kCholFusedSmem = (kNB * kBgLd + kNB * (kNB + 1) + kNB) * sizeof(double);
 
-// acc += A_tile B_tile^T over K (A(m, k) at A[k lda + m], B(n, k) at B[k ldb + n]; rows >= mv / nv are zero)
+// acc += A_tile B_tile^T over K (A(m, k) at A[k lda + m], B(n, k) at B[k ldb + n]; rows >= mv / nv are zero).
+// Two shared-memory slab buffers (buf: [2][A | B][16][72] doubles) and ONE barrier per 16-deep slab: the next
+// slab is fetched into registers before the current one is multiplied and stored into the other buffer after.
 __device__ __forceinline__ void chol_tile_mma(double (&acc)[2][4][2], const double *A, int lda, int mv,
-                                              const double *B, int ldb, int nv, int K, double (*As)[kBgLd],
-                                              double (*Bs)[kBgLd]) {
+                                              const double *B, int ldb, int nv, int K, double *buf) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
   const int fr = lane >> 2, fk = lane & 3;
   const int lk = threadIdx.x >> 4, l4 = (threadIdx.x & 15) * 4;
+  constexpr int kHalf = kBgSlab * kBgLd;  // doubles per operand slab
+  if (K <= 0) return;
   double ra[4], rb[4];
   auto fetch = [&](int k0) {
     const int k = k0 + lk;
@@ -415,27 +418,35 @@ __device__ __forceinline__ void chol_tile_mma(double (&acc)[2][4][2], const doub
       rb[e] = (k < K && l4 + e < nv) ? B[(size_t)k * ldb + l4 + e] : 0.0;
     }
   };
-  if (K > 0) fetch(0);
-  for (int k0 = 0; k0 < K; k0 += kBgSlab) {
+  auto store = [&](int which) {
+    double *As = buf + which * 2 * kHalf, *Bs = As + kHalf;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      As[lk][l4 + e] = ra[e];
-      Bs[lk][l4 + e] = rb[e];
+      As[lk * kBgLd + l4 + e] = ra[e];
+      Bs[lk * kBgLd + l4 + e] = rb[e];
     }
-    __syncthreads();
-    if (k0 + kBgSlab < K) fetch(k0 + kBgSlab);
+  };
+  fetch(0);
+  store(0);
+  __syncthreads();
+  int which = 0;
+  for (int k0 = 0; k0 < K; k0 += kBgSlab, which ^= 1) {
+    const bool more = k0 + kBgSlab < K;
+    if (more) fetch(k0 + kBgSlab);
+    const double *As = buf + which * 2 * kHalf, *Bs = As + kHalf;
 #pragma unroll
     for (int kk = 0; kk < kBgSlab; kk += 4) {
       double a[2], b[4];
 #pragma unroll
-      for (int x = 0; x < 2; x++) a[x] = As[kk + fk][wm + 8 * x + fr];
+      for (int x = 0; x < 2; x++) a[x] = As[(kk + fk) * kBgLd + wm + 8 * x + fr];
 #pragma unroll
-      for (int y = 0; y < 4; y++) b[y] = Bs[kk + fk][wn + 8 * y + fr];
+      for (int y = 0; y < 4; y++) b[y] = Bs[(kk + fk) * kBgLd + wn + 8 * y + fr];
 #pragma unroll
       for (int x = 0; x < 2; x++)
 #pragma unroll
         for (int y = 0; y < 4; y++) dmma_8x8x4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
     }
+    if (more) store(which ^ 1);
     __syncthreads();
   }
 }
@@ -447,8 +458,7 @@ __global__ void __launch_bounds__(256, 3)
 k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ packed, double diag_add,
              double *__restrict__ invD, int nblk, int *__restrict__ bad) {
   extern __shared__ double csm[];
-  double (*As)[kBgLd] = reinterpret_cast<double (*)[kBgLd]>(csm);
-  double (*Bs)[kBgLd] = reinterpret_cast<double (*)[kBgLd]>(csm + kBgSlab * kBgLd);
+  double *slabs = csm;  // [2 buffers][A | B][16][72]: exactly the 64 x 72 doubles of Ps
   double (*Ps)[kBgLd] = reinterpret_cast<double (*)[kBgLd]>(csm);
   double (*Ls)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(csm + kNB * kBgLd);
   double *rdiag = csm + kNB * kBgLd + kNB * (kNB + 1);
@@ -466,7 +476,7 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
     for (int m0 = k0; m0 < n; m0 += kNB) {
       const int mv = min(kNB, n - m0);
       double acc[2][4][2] = {};
-      chol_tile_mma(acc, L + m0, n, mv, L + k0, n, nb, k0, As, Bs);
+      chol_tile_mma(acc, L + m0, n, mv, L + k0, n, nb, k0, slabs);
       // P = A[tile, k] - acc, in fragment layout: (row, col) = (wm + 8x + fr, wn + 8y + 2fk + z)
 #pragma unroll
       for (int x = 0; x < 2; x++)
