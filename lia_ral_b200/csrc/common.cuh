@@ -29,7 +29,6 @@ struct Engine {
   int tc_debug = 0;    // profiling experiments only (LR_TC_DEBUG builds): results are WRONG when set
   int tv_gemm = 0;     // TV contractions: 0 = INT8 digit GEMM (gemm_i8.cu), 1 = cuBLAS fp64 (cross-check)
   int tv_planes = 6;   // digit planes per operand of the INT8 digit GEMM
-  int i8_max_clusters = 0;  // co-resident 2-CTA clusters of the digit GEMM (queried once per device)
   // per-device "cudaFuncSetAttribute done" flags (reset by lr_shutdown: the attribute is per context)
   enum { kAttrTc = 0, kAttrSimtLse, kAttrSimtAcc, kAttrTopk, kAttrTvDiag, kAttrTvGemm, kAttrPlda, kAttrGemmI8, kAttrCount };
   bool attr_set[kAttrCount] = {};

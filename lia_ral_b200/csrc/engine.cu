@@ -203,7 +203,6 @@ lr_status lr_shutdown(void) {
   profile_clear();
   e.profile = false;
   for (bool &b : e.attr_set) b = false;
-  e.i8_max_clusters = 0;
   pool_release_all();
   for (int i = 0; i < Engine::kScratchSlots; i++) {
     if (e.scratch[i]) cudaFree(e.scratch[i]);

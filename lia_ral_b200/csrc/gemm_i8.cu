@@ -194,32 +194,15 @@ struct Bars {
 // one moment share a few B panels and all of A through L2
 struct Sched {
   int mt_count, nt_count, ksplit, nchunk, n_items;
-  int csz;  // CTAs per cluster (1 or 2): an item = csz adjacent column tiles sharing every A plane by multicast
-  // nt is clamped to the last column tile (the surplus CTA of a cluster recomputes it); live = false tells
-  // its epilogue not to store
-  __host__ __device__ void get(int it, int crank, int &mt, int &nt, int &c0, int &c1, bool &live) const {
+  __host__ __device__ void get(int it, int &mt, int &nt, int &c0, int &c1) const {
     mt = it % mt_count;
     const int rest = it / mt_count;
     const int ks = rest % ksplit;
-    nt = (rest / ksplit) * csz + crank;
-    live = nt < nt_count;
-    if (!live) nt = nt_count - 1;
+    nt = rest / ksplit;
     c0 = (int)((long)nchunk * ks / ksplit);
     c1 = (int)((long)nchunk * (ks + 1) / ksplit);
   }
 };
-
-// arrive on the mbarrier at the same shared-memory offset of CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(bar),
-      "r"(rank)
-      : "memory");
-}
 
 // order in which the A planes of a chunk are consumed: 0, s-1, 1, s-2, ... (s - i products each:
 // heavy and light planes alternate, so the rings drain at an even rate)
@@ -249,13 +232,10 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
   sm.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   sm.bar = sm.base + kAStages * kABytes + kBSt * s * kBBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int csz = sched.csz;
-  const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
-  const int first_item = blockIdx.x / csz, item_step = gridDim.x / csz;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kAStages; i++) {
       mbar_init(sm.a_full(i), 1);
-      mbar_init(sm.a_empty(i), 4 * csz);  // the mover warps of EVERY CTA of the cluster have read the plane
+      mbar_init(sm.a_empty(i), 4);  // the four mover warps have read the plane
     }
     for (int i = 0; i < kBSt; i++) {
       mbar_init(sm.b_full(i), 1);
@@ -272,23 +252,18 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
   if (warp == 2) tmem_alloc(sm.tmem_slot(), 512);
   tc_fence_before();
   __syncthreads();
-  if (csz > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast / arrived at them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_slot()));
   constexpr uint32_t idesc = make_idesc_i8(kI8TileM, kI8TileN);
 
   if (warp == 0) {
-    // ---- producer: per chunk the s B planes (one stage), then the A planes in consumption order.  In a
-    // cluster every CTA fetches 1 / csz of each A plane and multicasts it to all (the CTAs of a cluster work
-    // on adjacent column tiles of the same row tile): the L2 -> SM operand stream, which bounds the kernel,
-    // shrinks by a third.
+    // ---- producer: per chunk the s B planes (one stage), then the A planes in consumption order
     const bool leader = elect_one();
     long aseq = 0, bseq = 0;
-    for (int it = first_item; it < sched.n_items; it += item_step) {
+    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x) {
       int mt, nt, c0, c1;
-      bool live;
-      sched.get(it, crank, mt, nt, c0, c1, live);
+      sched.get(it, mt, nt, c0, c1);
       for (int kc = c0; kc < c1; kc++) {
         const int bst = (int)(bseq % kBSt);
         mbar_wait(sm.b_empty(bst), (uint32_t)(((bseq / kBSt) & 1) ^ 1));
@@ -308,14 +283,8 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
           mbar_wait(sm.a_empty(ast), (uint32_t)(((aseq / kAStages) & 1) ^ 1));
           if (leader) {
             const unsigned char *src = Ap + (((size_t)mt * sched.nchunk + kc) * s + i) * kABytes;
-            mbar_expect_tx(sm.a_full(ast), kABytes);  // the whole plane, whoever fetches which part
-            if (csz > 1) {
-              const uint32_t part = kABytes / csz;
-              bulk_g2s_mc(sm.a_stage(ast) + crank * part, src + (size_t)crank * part, part, sm.a_full(ast),
-                          (uint16_t)((1u << csz) - 1u));
-            } else {
-              bulk_g2s(sm.a_stage(ast), src, kABytes, sm.a_full(ast));
-            }
+            mbar_expect_tx(sm.a_full(ast), kABytes);
+            bulk_g2s(sm.a_stage(ast), src, kABytes, sm.a_full(ast));
           }
           __syncwarp();
         }
@@ -329,10 +298,9 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
     long aseq = 0, bseq = 0, tile_seq = 0;
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t b_lo0 = ((sm.b_stage(0) >> 4) & 0x3FFFu) | (1u << 16);
-    for (int it = first_item; it < sched.n_items; it += item_step, tile_seq++) {
+    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x, tile_seq++) {
       int mt, nt, c0, c1;
-      bool live;
-      sched.get(it, crank, mt, nt, c0, c1, live);
+      sched.get(it, mt, nt, c0, c1);
       if (tile_seq > 0) mbar_wait(sm.acc_empty(), (uint32_t)((tile_seq - 1) & 1));
       tc_fence_after();
       bool have = false;  // the barrier of plane `aseq` has already been seen complete
@@ -378,10 +346,9 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
     const int r = q * 32 + lane;  // row of the tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     long aseq = 0;
-    for (int it = first_item; it < sched.n_items; it += item_step) {
+    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x) {
       int mt, nt, c0, c1;
-      bool live;
-      sched.get(it, crank, mt, nt, c0, c1, live);
+      sched.get(it, mt, nt, c0, c1);
       for (long n = (long)(c1 - c0) * s; n > 0; n--, aseq++) {
         const int ast = (int)(aseq % kAStages), ts = (int)(aseq % kTSlots);
         mbar_wait(sm.a_full(ast), (uint32_t)((aseq / kAStages) & 1));
@@ -410,11 +377,7 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (csz > 1) {
-            for (int rk = 0; rk < csz; rk++) mbar_arrive_remote(sm.a_empty(ast), (uint32_t)rk);
-          } else {
-            mbar_arrive(sm.a_empty(ast));
-          }
+          mbar_arrive(sm.a_empty(ast));
           mbar_arrive(sm.at_full(ts));
         }
       }
@@ -425,10 +388,9 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     long tile_seq = 0;
     const bool split = sched.ksplit > 1;
-    for (int it = first_item; it < sched.n_items; it += item_step, tile_seq++) {
+    for (int it = blockIdx.x; it < sched.n_items; it += gridDim.x, tile_seq++) {
       int mt, nt, c0, c1;
-      bool live;
-      sched.get(it, crank, mt, nt, c0, c1, live);
+      sched.get(it, mt, nt, c0, c1);
       const long m = (long)mt * kI8TileM + q * 32 + lane;
       const double sa = m < M ? scaleA[m] * alpha * (1.0 / 4096.0) : 0.0;  // digit weights 2^-6 x 2^-6
       mbar_wait(sm.acc_full(), (uint32_t)(tile_seq & 1));
@@ -453,7 +415,7 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
 #pragma unroll
       for (int g = 0; g < 2; g++) {
         const long n_base = (long)nt * kI8TileN + h * 32 + g * 16;
-        if (live && m < M && n_base < N) {
+        if (m < M && n_base < N) {
           double *dst = Cout + (size_t)m * ldc + n_base;
           const bool full = n_base + 16 <= N;
           const bool vec_ok = full && ((ldc * sizeof(double)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
@@ -485,7 +447,6 @@ k_gemm_i8(Sched sched, const unsigned char *__restrict__ Ap, const unsigned char
   }
   tc_fence_before();
   __syncthreads();
-  if (csz > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast / arrive at it
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -568,11 +529,7 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
   int ksplit = ceil_div(sc.nchunk, 256);
   if (tiles < 2L * e.sm_count) ksplit = std::max<int>(ksplit, std::min<long>(sc.nchunk / 4, ceil_div(2L * e.sm_count, tiles)));
   sc.ksplit = std::max(1, std::min(ksplit, sc.nchunk));
-  int csz = 2;
-  if (const char *env = getenv("LR_I8_CLUSTER")) csz = atoi(env);  // A/B switch (temporary)
-  if (csz != 2 || sc.nt_count < 2 || e.sm_count % 2) csz = 1;
-  sc.csz = csz;
-  sc.n_items = sc.mt_count * ceil_div(sc.nt_count, csz) * sc.ksplit;
+  sc.n_items = (int)(tiles * sc.ksplit);
   if (sc.ksplit > 1) {
     LR_REQUIRE(beta == 0.0 || beta == 1.0, "gemm_i8: beta must be 0 or 1 when the K range is split");
     if (beta == 0.0) {
@@ -580,32 +537,9 @@ lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, c
       LR_CHECK_LAUNCH();
     }
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes(s);
-  cfg.stream = e.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)csz;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int max_clusters = e.sm_count / csz;
-  if (csz > 1) {  // whole clusters that are co-resident (one CTA per SM)
-    if (e.i8_max_clusters == 0) {
-      cfg.gridDim = dim3((unsigned)(csz * 64));
-      int nmax = 0;
-      if (cudaOccupancyMaxActiveClusters(&nmax, kern, &cfg) == cudaSuccess && nmax > 0) e.i8_max_clusters = nmax;
-      else {
-        cudaGetLastError();
-        e.i8_max_clusters = max_clusters;
-      }
-    }
-    max_clusters = std::min(max_clusters, e.i8_max_clusters);
-  }
-  cfg.gridDim = dim3((unsigned)(csz * std::min(max_clusters, sc.n_items)));
-  LR_CUDA(cudaLaunchKernelEx(&cfg, kern, sc, dAp, dBp, dAscale, dBscale, dC, ldc, M, N, alpha, beta));
+  const int grid = std::min(e.sm_count, sc.n_items);
+  kern<<<grid, kThreads, smem_bytes(s), e.stream>>>(sc, dAp, dBp, dAscale, dBscale, dC, ldc, M, N, alpha, beta);
+  LR_CUDA(cudaGetLastError());
   count_launch();
   return LR_OK;
 }
