@@ -286,6 +286,7 @@ class PldaDev {
   void computeWccnChol(Matrix &WCCN);                            // :1113-1175
   void computeMahalanobis(Matrix &M);                            // :1366-1378
   void computeLDA(Matrix &ldaMat, long ldaRank, const Config &c);  // :1381-1415 (ldaMode covariance)
+  void computeScatterMat(Matrix &SB, Matrix &SW);  // computeScatterMatUnThreaded :1607-1640, as written
   void sphericalNuisanceNormalization(const Config &c);          // :1822-1929 (estimates, saves, applies)
   void applySphericalNuisanceNormalization(const Config &c);     // :1931-1975
 

@@ -91,11 +91,44 @@ void PldaDev::computeMahalanobis(Matrix &M) {
   LIA_CHECK(lr_iv_mahalanobis_matrix((int)data_.rows, data_.cols, data_.data.data(), class_.data(), nSpk_,
                                      M.data.data()));
 }
+// computeScatterMatUnThreaded (PldaTools.cpp:1607-1640), restated AS WRITTEN: SB sums the unnormalised outer
+// products of the centred speaker means; SW is ASSIGNED (not accumulated) per speaker, and its inner loop runs over
+// the sessions 0 .. n_c - 1 of the WHOLE set for every speaker c -- so what reaches the eigenproblem is the scatter
+// of the first n_last sessions around their own speakers' means, divided by n_last (n_last = session count of the
+// last speaker).  Kept so that `ldaMode scatterMatrices` gives the reference's matrices; d x d host arithmetic on
+// means the engine computed (lr_iv_cov_mat).
+void PldaDev::computeScatterMat(Matrix &SB, Matrix &SW) {
+  const size_t d = data_.rows, n = data_.cols;
+  std::vector<double> mean(d), spk(d * nSpk_);
+  LIA_CHECK(lr_iv_cov_mat((int)d, n, data_.data.data(), class_.data(), nSpk_, mean.data(), spk.data(), nullptr, nullptr,
+                          nullptr));
+  SB = Matrix(d, d);
+  SW = Matrix(d, d);
+  std::vector<double> cm(d);
+  for (size_t cs = 0; cs < nSpk_; cs++) {
+    for (size_t i = 0; i < d; i++) cm[i] = spk[i * nSpk_ + cs] - mean[i];
+    for (size_t i = 0; i < d; i++)
+      for (size_t j = 0; j < d; j++) SB(i, j) += cm[i] * cm[j];
+  }
+  size_t nLast = 0;
+  for (size_t s2 = 0; s2 < n; s2++)
+    if ((size_t)class_[s2] == nSpk_ - 1) nLast++;
+  if (nLast == 0) LIA_THROW("computeScatterMat: the last speaker has no session");
+  std::vector<double> xc(d);
+  for (size_t s2 = 0; s2 < std::min(nLast, n); s2++) {
+    for (size_t i = 0; i < d; i++) xc[i] = data_(i, s2) - spk[i * nSpk_ + (size_t)class_[s2]];
+    for (size_t i = 0; i < d; i++)
+      for (size_t j = 0; j < d; j++) SW(i, j) += xc[i] * xc[j];
+  }
+  for (double &v : SW.data) v /= (double)nLast;
+}
+
 void PldaDev::computeLDA(Matrix &ldaMat, long ldaRank, const Config &c) {
-  if (c.getString("ldaMode", "covariance") == "scatterMatrices")
-    LIA_THROW("computeLDA: ldaMode scatterMatrices is not implemented by this engine");
   Matrix Sigma, W, B;
-  computeCovMat(Sigma, W, B);
+  if (c.getString("ldaMode", "covariance") == "scatterMatrices")
+    computeScatterMat(B, W);
+  else
+    computeCovMat(Sigma, W, B);
   ldaMat = Matrix((size_t)ldaRank, data_.rows);
   LIA_CHECK(lr_iv_lda((int)data_.rows, W.data.data(), B.data.data(), (int)ldaRank, ldaMat.data.data()));
 }

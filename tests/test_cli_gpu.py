@@ -336,6 +336,52 @@ def test_ivtest_plda_cli(world, oracle):
         assert abs(float(l[4]) - ref[m, s]) < 1e-5 * max(1.0, abs(ref[m, s]))
 
 
+def test_ivtest_lda_scatter_matrices_cli(world, oracle):
+    """ldaMode scatterMatrices (PldaTools.cpp:1389, computeScatterMatUnThreaded :1607-1640), restated AS WRITTEN:
+    SB = unnormalised scatter of the speaker means; SW = scatter of the FIRST n_last sessions around their own
+    speakers' means / n_last (n_last = sessions of the last speaker) -- the loop assigns SW per speaker and always
+    walks the sessions from 0.  Only usable when n_last >= vectSize; the test set is built that way."""
+    d = world["dir"]
+    dim, n_spk, per = 4, 6, 6
+    rng = np.random.default_rng(131)
+    os.makedirs(d / "svec", exist_ok=True)
+    spk_c = rng.standard_normal((dim, n_spk)) * 1.5
+    lines, cols = [], []
+    for c in range(n_spk):
+        names = []
+        for j in range(per):
+            v = spk_c[:, c] + rng.standard_normal(dim)
+            names.append(f"sd{c}_{j}")
+            cols.append((v, c))
+            lf.write_db(d / "svec" / f"{names[-1]}.y", v[None])
+        lines.append(names)
+    lf.write_lines(d / "sdev.ndx", lines)
+    data = np.stack([c[0] for c in cols], axis=1)
+    cls = np.array([c[1] for c in cols], dtype=np.int32)
+    models, segments = rng.standard_normal((dim, 3)), rng.standard_normal((dim, 3))
+    for j in range(3):
+        lf.write_db(d / "svec" / f"sm{j}.y", models[:, j][None])
+        lf.write_db(d / "svec" / f"st{j}.y", segments[:, j][None])
+    lf.write_lines(d / "strials.ndx", [[f"st{j}", "sm0", "sm1", "sm2"] for j in range(3)])
+    gmean, spk_means, _, _, _ = oracle.iv_cov_mat(data, cls, n_spk)
+    cm = spk_means - gmean[:, None]
+    SB = cm @ cm.T
+    xc = data[:, :per] - spk_means[:, cls[:per]]
+    SW = xc @ xc.T / per
+    lda = oracle.iv_lda(SW, SB, 2)
+    ref = oracle.iv_cosine(oracle.iv_rotate_left(lda, models), oracle.iv_rotate_left(lda, segments))
+    lf.write_cfg(d / "sc.cfg", **world["common"], ndxFilename=str(d / "strials.ndx"), testVectorFilesPath=str(d / "svec"),
+                 loadVectorFilesPath=str(d / "svec"), loadVectorFilesExtension=".y", backgroundNdxFilename=str(d / "sdev.ndx"),
+                 ivNorm="false", LDA="true", ldaRank=2, ldaMode="scatterMatrices", ldaMatrix="ldaScatter", gender="M",
+                 wccn="false", scoring="cosine", outputFilename=str(d / "sc.res"))
+    _run("IvTest", d / "sc.cfg")
+    out = [l.split() for l in open(d / "sc.res")]
+    assert len(out) == 9
+    for l in out:
+        m, sg = int(l[1][2:]), int(l[3][2:])
+        assert abs(float(l[4]) - ref[m, sg]) < 1e-6, l
+
+
 def test_ivtest_backend_and_ivnorm_cli(world, oracle):
     """IvTest scoring = cosine (+ WCCN) / mahalanobis / 2cov with EFR + LDA normalisation estimated on
     a development list (IvTest.cpp:112-391), and the IvNorm program (IvNorm.cpp:72-128), against the
