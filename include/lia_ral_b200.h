@@ -119,8 +119,9 @@ size_t lr_gmm_em_stats_len(const lr_gmm *g); /* C + 2*C*D + 2 */
 /* MixtureGDStat::getEM + varianceControl (TrainTools.cpp:567-587,1076-1077) on the device:
  * w = occ/sum occ, mean = m1/occ, cov = m2/occ - mean^2, then clamp cov to
  * [flooring*cov_signal, ceiling*cov_signal] (floor first), then computeAll.  d_cov_signal may
- * be NULL (no variance control).  g is updated in place on the device; the call ends with ONE 4-byte
- * readback (the fp16 range guard of the tensor-core operands), i.e. it waits for the M-step kernels.
+ * be NULL (no variance control).  g is updated in place on the device; the call ends with ONE 8-byte
+ * readback (the fp16 range guard of the tensor-core operands and the "normalised space re-derived" flag
+ * that invalidates cached frame operands), i.e. it waits for the M-step kernels.
  * Weights are left unchanged when the total occupation is not positive. */
 lr_status lr_gmm_em_update_dev(lr_gmm *g, const double *d_stats, double flooring, double ceiling,
                                const double *d_cov_signal);

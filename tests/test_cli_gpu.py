@@ -372,7 +372,8 @@ def test_ivtest_lda_scatter_matrices_cli(world, oracle):
     ref = oracle.iv_cosine(oracle.iv_rotate_left(lda, models), oracle.iv_rotate_left(lda, segments))
     lf.write_cfg(d / "sc.cfg", **world["common"], ndxFilename=str(d / "strials.ndx"), testVectorFilesPath=str(d / "svec"),
                  loadVectorFilesPath=str(d / "svec"), loadVectorFilesExtension=".y", backgroundNdxFilename=str(d / "sdev.ndx"),
-                 ivNorm="false", LDA="true", ldaRank=2, ldaMode="scatterMatrices", ldaMatrix="ldaScatter", gender="M",
+                 ivNorm="true", ivNormLoadParam="false", ivNormIterationNb=0, LDA="true", ldaRank=2,   # LDA only, no EFR
+                 ldaMode="scatterMatrices", ldaMatrix="ldaScatter", gender="M",
                  wccn="false", scoring="cosine", outputFilename=str(d / "sc.res"))
     _run("IvTest", d / "sc.cfg")
     out = [l.split() for l in open(d / "sc.res")]
