@@ -470,7 +470,8 @@ size_t gemm_i8_scale_count(long rows, int tile_rows) {
 }
 
 lr_status gemm_i8_prepare(const double *dX, size_t stride_row, size_t stride_k, long rows, long K, int s,
-                          int tile_rows, unsigned char *d_panels, double *d_scale) {
+                          int tile_rows, unsigned char *d_panels, double *d_scale,
+                          const unsigned long long *d_rowmax) {
   Engine &e = engine();
   LR_REQUIRE(s >= 1 && s <= kI8MaxSlices, "gemm_i8: %d digit planes outside [1, %d]", s, kI8MaxSlices);
   LR_REQUIRE(tile_rows == kI8TileM || tile_rows == kI8TileN, "gemm_i8: tile_rows %d", tile_rows);
@@ -478,25 +479,29 @@ lr_status gemm_i8_prepare(const double *dX, size_t stride_row, size_t stride_k, 
   LR_REQUIRE(rows >= 1 && K >= 1, "gemm_i8: empty operand");
   const long rows_pad = (long)gemm_i8_scale_count(rows, tile_rows);
   const int nchunk = (int)((K + kChunkK - 1) / kChunkK);
-  DevBuf<unsigned long long> maxbits;
-  LR_CUDA(maxbits.alloc((size_t)rows));
+  DevBuf<unsigned long long> maxbuf;
   const bool k_contig = stride_k == 1;
-  if (k_contig) {
-    k_i8_rowmax<true><<<(unsigned)ceil_div(rows, 8), 256, 0, e.stream>>>(dX, stride_row, stride_k, rows, K, maxbits.p);
-  } else {
-    LR_CUDA(cudaMemsetAsync(maxbits.p, 0, (size_t)rows * sizeof(unsigned long long), e.stream));
-    dim3 grid((unsigned)ceil_div(rows, 256), (unsigned)ceil_div(K, 64));
-    k_i8_rowmax<false><<<grid, 256, 0, e.stream>>>(dX, stride_row, stride_k, rows, K, maxbits.p);
+  const unsigned long long *maxp = d_rowmax;  // the caller may already know the row maxima
+  if (!maxp) {
+    LR_CUDA(maxbuf.alloc((size_t)rows));
+    if (k_contig) {
+      k_i8_rowmax<true><<<(unsigned)ceil_div(rows, 8), 256, 0, e.stream>>>(dX, stride_row, stride_k, rows, K, maxbuf.p);
+    } else {
+      LR_CUDA(cudaMemsetAsync(maxbuf.p, 0, (size_t)rows * sizeof(unsigned long long), e.stream));
+      dim3 grid((unsigned)ceil_div(rows, 256), (unsigned)ceil_div(K, 64));
+      k_i8_rowmax<false><<<grid, 256, 0, e.stream>>>(dX, stride_row, stride_k, rows, K, maxbuf.p);
+    }
+    LR_CHECK_LAUNCH();
+    maxp = maxbuf.p;
   }
-  LR_CHECK_LAUNCH();
   const long threads = rows_pad * nchunk * 8;
   const unsigned blocks = (unsigned)((threads + 255) / 256);
   if (k_contig)
     k_i8_planes<true><<<blocks, 256, 0, e.stream>>>(dX, stride_row, stride_k, rows, K, rows_pad, nchunk, s,
-                                                     tile_rows, maxbits.p, d_scale, d_panels);
+                                                     tile_rows, maxp, d_scale, d_panels);
   else
     k_i8_planes<false><<<blocks, 256, 0, e.stream>>>(dX, stride_row, stride_k, rows, K, rows_pad, nchunk, s,
-                                                      tile_rows, maxbits.p, d_scale, d_panels);
+                                                      tile_rows, maxp, d_scale, d_panels);
   LR_CHECK_LAUNCH();
   return LR_OK;
 }

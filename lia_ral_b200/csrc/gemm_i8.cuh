@@ -16,8 +16,10 @@ size_t gemm_i8_panel_bytes(long rows, long K, int s, int tile_rows);
 size_t gemm_i8_scale_count(long rows, int tile_rows);
 // dX: element (r, k) at dX[r * stride_row + k * stride_k], one of the strides == 1.
 // d_panels: gemm_i8_panel_bytes; d_scale: gemm_i8_scale_count doubles (power-of-two row scales)
+// d_rowmax (optional): max |x| of every row as the bit pattern of the double, when the caller has it
 lr_status gemm_i8_prepare(const double *dX, size_t stride_row, size_t stride_k, long rows, long K, int s,
-                          int tile_rows, unsigned char *d_panels, double *d_scale);
+                          int tile_rows, unsigned char *d_panels, double *d_scale,
+                          const unsigned long long *d_rowmax = nullptr);
 // C (device, row-major, leading dimension ldc); beta must be 0 or 1 when the K range is split
 lr_status gemm_i8_run(const unsigned char *dAp, const double *dAscale, long M, const unsigned char *dBp,
                       const double *dBscale, long N, long K, int s, double alpha, double beta, double *dC,

@@ -47,6 +47,10 @@ struct lr_tv {
   unsigned char *d_tett_planes = nullptr, *d_ts_planes = nullptr;
   double *d_tett_scale = nullptr, *d_ts_scale = nullptr;
   int planes = 0;  // digit planes the two were cut into (0: not prepared, cuBLAS path)
+  // max |F[s, :]| per utterance (bit pattern of the double), a by-product of substractM: the digit GEMM's
+  // row scale of the aux operand.  Valid until F is written again (set_stats, dev_F hand-out, normStatistics).
+  unsigned long long *d_fmax = nullptr;
+  bool fmax_valid = false;
   size_t Rp() const { return (size_t)R * (R + 1) / 2; }
   double *A() const { return d_acc; }  // packed: A_c at d_acc + c * Rp
   double *Cmx() const { return d_acc + (size_t)C * Rp(); }
@@ -59,15 +63,24 @@ struct lr_tv {
 namespace lr {
 namespace {
 
-// substractM (AccumulateTVStat.cpp:1088-1105): F[s, c, :] -= mean[c, :] * N[s, c]
-__global__ void k_subtract_m(size_t U, int C, int D, const double *__restrict__ N,
-                             const double *__restrict__ mean, double *__restrict__ F) {
-  size_t sv = (size_t)C * D;
-  size_t total = U * sv;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    size_t s = i / sv, k = i - s * sv;
-    F[i] -= mean[k] * N[s * C + k / D];
+// substractM (AccumulateTVStat.cpp:1088-1105): F[s, c, :] -= mean[c, :] * N[s, c]; one block per
+// (utterance, 8192-element segment), which also leaves max |F[s, :]| behind (rowmax, bit pattern of the double)
+constexpr int kSubSeg = 8192;
+__global__ void __launch_bounds__(256)
+k_subtract_m(size_t U, int C, int D, const double *__restrict__ N, const double *__restrict__ mean,
+             double *__restrict__ F, unsigned long long *__restrict__ rowmax) {
+  const size_t sv = (size_t)C * D;
+  const size_t k0 = (size_t)blockIdx.x * kSubSeg, k1 = min(sv, k0 + kSubSeg);
+  for (size_t s = blockIdx.y; s < U; s += gridDim.y) {
+    double m = 0.0;
+    for (size_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+      const double v = F[s * sv + k] - mean[k] * N[s * C + k / D];
+      F[s * sv + k] = v;
+      m = fmax(m, fabs(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(rowmax + s, (unsigned long long)__double_as_longlong(m));
   }
 }
 
@@ -169,13 +182,20 @@ k_tett_packed(int R, int D, size_t sv, const double *__restrict__ Ts, const doub
   }
 }
 
-// E[b] += w_b w_b^T  (Linv += y y^T, AccumulateTVStat.cpp:1766-1768)
-__global__ void k_rank1(int nb, int R, const double *__restrict__ W, double *__restrict__ E) {
-  size_t total = (size_t)nb * R * R;
+// packed[b] = lower triangle of (E[b] + w_b w_b^T), E[b] column-major R x R with a valid lower triangle
+// (Linv += y y^T, AccumulateTVStat.cpp:1766-1768, fused with the packing)
+__global__ void k_pack_lower_rank1(size_t n, int R, const double *__restrict__ full, const double *__restrict__ W,
+                                   double *__restrict__ packed) {
+  const size_t rp = (size_t)R * (R + 1) / 2, rr = (size_t)R * R, total = n * rp;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
-    size_t b = i / ((size_t)R * R), e = i - b * (size_t)R * R;
-    E[i] += W[b * R + e / R] * W[b * R + e % R];
+    const size_t m = i / rp, e = i - m * rp;
+    // column of the packed index e: largest col with col R - col (col - 1) / 2 <= e
+    int col = (int)(((2.0 * R + 1.0) - sqrt((2.0 * R + 1.0) * (2.0 * R + 1.0) - 8.0 * (double)e)) * 0.5);
+    while (col > 0 && packed_off(R, col) > e) col--;
+    while (col + 1 < R && packed_off(R, col + 1) <= e) col++;
+    const int row = col + (int)(e - packed_off(R, col));
+    packed[i] = full[m * rr + (size_t)col * R + row] + W[m * R + row] * W[m * R + col];
   }
 }
 
@@ -852,6 +872,7 @@ void tv_free(lr_tv *tv) {
   cudaFree(tv->d_ptr_A);
   cudaFree(tv->d_ptr_Tc);
   cudaFree(tv->d_info);
+  cudaFree(tv->d_fmax);
   cudaFree(tv->d_tett_planes);
   cudaFree(tv->d_ts_planes);
   cudaFree(tv->d_tett_scale);
@@ -939,7 +960,8 @@ lr_status posterior_batch(lr_tv *tv, size_t u0, int nb, bool want_inverse) {
     DevBuf<double> sF;
     LR_CUDA(pF.alloc(gemm_i8_panel_bytes(nb, (long)tv->sv, s, kI8TileM)));
     LR_CUDA(sF.alloc(gemm_i8_scale_count(nb, kI8TileM)));
-    lr_status st = gemm_i8_prepare(tv->d_F + u0 * tv->sv, tv->sv, 1, nb, (long)tv->sv, s, kI8TileM, pF.p, sF.p);
+    lr_status st = gemm_i8_prepare(tv->d_F + u0 * tv->sv, tv->sv, 1, nb, (long)tv->sv, s, kI8TileM, pF.p, sF.p,
+                                   tv->fmax_valid ? tv->d_fmax + u0 : nullptr);
     if (st != LR_OK) return st;
     st = gemm_i8_run(pF.p, sF.p, nb, tv->d_ts_planes, tv->d_ts_scale, R, (long)tv->sv, s, 1.0, 0.0,
                      tv->d_W + u0 * R, (size_t)R);
@@ -1130,6 +1152,7 @@ void lr_tv_destroy(lr_tv *tv) { tv_free(tv); }
 lr_status lr_tv_set_stats(lr_tv *tv, const double *N, const double *F) {
   LR_READY();
   LR_REQUIRE(tv && N && F, "lr_tv_set_stats: null argument");
+  tv->fmax_valid = false;
   TV_COPY(tv->d_N, N, tv->U * tv->C, cudaMemcpyHostToDevice);
   TV_COPY(tv->d_F, F, tv->U * tv->sv, cudaMemcpyHostToDevice);
   LR_CUDA(cudaStreamSynchronize(engine().stream));
@@ -1146,7 +1169,10 @@ lr_status lr_tv_get_stats(lr_tv *tv, double *N, double *F) {
 }
 
 double *lr_tv_dev_N(lr_tv *tv) { return tv ? tv->d_N : nullptr; }
-double *lr_tv_dev_F(lr_tv *tv) { return tv ? tv->d_F : nullptr; }
+double *lr_tv_dev_F(lr_tv *tv) {
+  if (tv) tv->fmax_valid = false;  // the caller may write F: its row maxima are recomputed by the next substractM
+  return tv ? tv->d_F : nullptr;
+}
 
 lr_status lr_tv_set_T(lr_tv *tv, const double *T) {
   LR_READY();
@@ -1219,9 +1245,12 @@ lr_status lr_tv_reset_tmp_acc(lr_tv *tv) {
 lr_status lr_tv_subtract_m(lr_tv *tv) {
   LR_READY();
   LR_REQUIRE(tv, "lr_tv_subtract_m: null handle");
-  k_subtract_m<<<grid_for(tv->U * tv->sv), 256, 0, engine().stream>>>(tv->U, tv->C, tv->D, tv->d_N,
-                                                                      tv->d_mean, tv->d_F);
+  if (!tv->d_fmax) LR_CUDA(cudaMalloc(&tv->d_fmax, tv->U * sizeof(unsigned long long)));
+  LR_CUDA(cudaMemsetAsync(tv->d_fmax, 0, tv->U * sizeof(unsigned long long), engine().stream));
+  dim3 grid((unsigned)ceil_div((long)tv->sv, kSubSeg), (unsigned)std::min<size_t>(tv->U, 65535));
+  k_subtract_m<<<grid, 256, 0, engine().stream>>>(tv->U, tv->C, tv->D, tv->d_N, tv->d_mean, tv->d_F, tv->d_fmax);
   LR_CHECK_LAUNCH();
+  tv->fmax_valid = true;
   return LR_OK;
 }
 
@@ -1301,6 +1330,9 @@ lr_status lr_tv_estimate_a_and_c(lr_tv *tv) {
   const int rp = (int)tv->Rp();
   LR_CUDA(cudaMemsetAsync(tv->A(), 0, (size_t)C * rp * sizeof(double), e.stream));
   LR_CUDA(cudaMemsetAsync(tv->Rm(), 0, (rr + 2 * (size_t)R) * sizeof(double), e.stream));
+  DevBuf<double> Rmp;  // packed sum of the E_b
+  LR_CUDA(Rmp.alloc((size_t)rp));
+  LR_CUDA(cudaMemsetAsync(Rmp.p, 0, (size_t)rp * sizeof(double), e.stream));
   for (size_t u0 = 0; u0 < tv->U; u0 += tv->batch) {
     int nb = (int)std::min<size_t>(tv->batch, tv->U - u0);
     lr_status st = posterior_batch(tv, u0, nb, true);
@@ -1309,17 +1341,14 @@ lr_status lr_tv_estimate_a_and_c(lr_tv *tv) {
     // r += sum_b w_b ; sumW likewise (:1762, :1772)
     LR_CUBLAS(cublasDgemv(e.blas, CUBLAS_OP_N, R, nb, &one, Wb, R, tv->d_ones, 1, &one, tv->r(), 1));
     count_launch();
-    // E_b = Linv_b + w_b w_b^T
-    k_rank1<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>(nb, R, Wb, tv->d_Eb);
+    // E_b = Linv_b + w_b w_b^T (:1766-1768), formed straight into PACKED lower triangles (E_b is symmetric;
+    // the reference's loops run over the full R x R)
+    k_pack_lower_rank1<<<grid_for((size_t)nb * rp), 256, 0, e.stream>>>((size_t)nb, R, tv->d_Eb, Wb, tv->d_Lb);
     LR_CHECK_LAUNCH();
-    // Rm += sum_b E_b (:1770)
-    LR_CUBLAS(cublasDgemv(e.blas, CUBLAS_OP_N, (int)rr, nb, &one, tv->d_Eb, (int)rr, tv->d_ones, 1,
-                          &one, tv->Rm(), 1));
+    // Rm += sum_b E_b (:1770), on the packed form (unpacked + mirrored once at the end)
+    LR_CUBLAS(cublasDgemv(e.blas, CUBLAS_OP_N, rp, nb, &one, tv->d_Lb, rp, tv->d_ones, 1, &one, Rmp.p, 1));
     count_launch();
-    // A[C x Rp] += N_b^T pack(E_b) (:1775-1782; E_b is symmetric, only its lower triangle is
-    // accumulated -- the reference's loop runs over the full R x R)
-    k_pack_lower<<<grid_for((size_t)nb * rr), 256, 0, e.stream>>>((size_t)nb, R, tv->d_Eb, tv->d_Lb);
-    LR_CHECK_LAUNCH();
+    // A[C x Rp] += N_b^T pack(E_b) (:1775-1782)
     if (tv->planes > 0) {
       const int s = tv->planes;
       {  // rows = components, K = the batch's utterances
@@ -1354,8 +1383,8 @@ lr_status lr_tv_estimate_a_and_c(lr_tv *tv) {
       count_launch();
     }
   }
-  // only the lower triangles of the E_b were formed: mirror the sum
-  k_mirror_lower<<<ceil_div((long)rr, 256), 256, 0, e.stream>>>(R, tv->Rm());
+  // Rm = the symmetric matrix of the packed sum
+  k_unpack_lower<<<grid_for(rr), 256, 0, e.stream>>>((size_t)1, R, Rmp.p, tv->Rm(), 0.0, 1);
   LR_CHECK_LAUNCH();
   LR_CUDA(cudaMemcpyAsync(tv->sumW(), tv->r(), R * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
   return lr_tv_finish_estep(tv, (double)tv->U);
@@ -1545,6 +1574,7 @@ lr_status lr_tv_norm_t(lr_tv *tv) {
 lr_status lr_tv_norm_statistics(lr_tv *tv) {
   LR_READY();
   LR_REQUIRE(tv, "lr_tv_norm_statistics: null handle");
+  tv->fmax_valid = false;
   k_norm_stats<<<grid_for(tv->U * tv->sv), 256, 0, engine().stream>>>(tv->U, tv->C, tv->D, tv->d_N,
                                                                       tv->d_mean, tv->d_invvar, tv->d_F);
   LR_CHECK_LAUNCH();
