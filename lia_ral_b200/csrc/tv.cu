@@ -98,16 +98,6 @@ __global__ void k_scale_cols(int R, size_t sv, const double *__restrict__ T,
 __device__ __forceinline__ size_t packed_off(int R, int col) {
   return (size_t)col * R - (size_t)col * (col - 1) / 2;
 }
-__global__ void k_pack_lower(size_t n, int R, const double *__restrict__ full,
-                             double *__restrict__ packed) {
-  const size_t rr = (size_t)R * R, rp = (size_t)R * (R + 1) / 2, total = n * rr;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    size_t m = i / rr, e = i - m * rr;
-    int col = (int)(e / R), row = (int)(e - (size_t)col * R);
-    if (row >= col) packed[m * rp + packed_off(R, col) + (row - col)] = full[i];
-  }
-}
 // full[m] (column-major, ld R): lower triangle from the packed form (+ diag_add on the diagonal);
 // the strict upper triangle is zeroed (sym == 0) or mirrored (sym != 0).
 __global__ void k_unpack_lower(size_t n, int R, const double *__restrict__ packed,
@@ -199,15 +189,6 @@ __global__ void k_pack_lower_rank1(size_t n, int R, const double *__restrict__ f
   }
 }
 
-// column-major R x R: upper triangle <- lower triangle
-__global__ void k_mirror_lower(int R, double *__restrict__ M) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < R * R) {
-    int col = e / R, row = e - col * R;
-    if (row < col) M[e] = M[(size_t)row * R + col];
-  }
-}
-
 __global__ void k_check_info(int n, const int *__restrict__ info, int *__restrict__ bad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && info[i] != 0) atomicExch(bad, i + 1);
@@ -253,43 +234,6 @@ __global__ void k_scale_row(size_t n, const double *__restrict__ nrm, double *__
 // cusolverDnDpotrsBatched and cublasDtrsmBatched run at < 1 TFLOP/s for R = 400..600 (measured,
 // profiles/r01_extra.md); the two routines below replace them.
 //
-// Solve L L^T x = b for ONE right-hand side per matrix (column-major lower factor, ld = n).
-// One CTA per matrix; x lives in shared memory.  Forward substitution is column oriented
-// (axpy over the contiguous column j), the backward pass is a dot product with column j.
-constexpr int kSolveThreads = 256;
-__global__ void __launch_bounds__(kSolveThreads)
-k_chol_solve(int n, const double *__restrict__ Lall, size_t stride, double *__restrict__ rhs) {
-  extern __shared__ double xs[];
-  __shared__ double red[kSolveThreads / 32];
-  const double *L = Lall + (size_t)blockIdx.x * stride;
-  double *b = rhs + (size_t)blockIdx.x * n;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < n; i += kSolveThreads) xs[i] = b[i];
-  __syncthreads();
-  for (int j = 0; j < n; j++) {  // L y = b
-    const double xj = xs[j] / L[(size_t)j * n + j];
-    __syncthreads();
-    if (tid == 0) xs[j] = xj;
-    for (int i = j + 1 + tid; i < n; i += kSolveThreads) xs[i] -= L[(size_t)j * n + i] * xj;
-    __syncthreads();
-  }
-  for (int j = n - 1; j >= 0; j--) {  // L^T x = y :  x_j = (y_j - sum_{i>j} L_ij x_i) / L_jj
-    double part = 0.0;
-    for (int i = j + 1 + tid; i < n; i += kSolveThreads) part += L[(size_t)j * n + i] * xs[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((tid & 31) == 0) red[tid >> 5] = part;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < kSolveThreads / 32; w++) t += red[w];
-      xs[j] = (xs[j] - t) / L[(size_t)j * n + j];
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < n; i += kSolveThreads) b[i] = xs[i];
-}
-
 // Blocked batched Cholesky (cusolverDnDpotrfBatched runs at ~1.4 TFLOP/s for R = 400..600: measured
 // 52 us per 600 x 600 matrix, profiles/r01_tv_breakdown.md): left-looking over 64-wide block columns,
 // one CTA per matrix for the whole factorization (k_chol_fused below).  The inverses of the diagonal
@@ -676,8 +620,8 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
 
 // Solve L L^T x = b for ONE right-hand side per matrix with the factor of chol_batched AND its
 // diagonal-block inverses: block forward / backward substitution, x_i = invD_ii (b_i - sum_j L_ij x_j),
-// two barriers per 64-wide block instead of two per column (k_chol_solve: 2 n barriers, each behind a
-// dependent global load).  One CTA per matrix, four lanes per row.
+// two barriers per 64-wide block instead of two per column (the column-by-column kernel it replaced
+// spent 2 n barriers, each behind a dependent global load).  One CTA per matrix, four lanes per row.
 __global__ void __launch_bounds__(256)
 k_chol_solve_blocked(int n, const double *__restrict__ Lall, size_t stride, const double *__restrict__ invD,
                      int nblk, double *__restrict__ rhs) {
