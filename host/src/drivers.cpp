@@ -231,53 +231,113 @@ int IvExtractor(Config &c) {
 // AccumulateJFAStat.cpp:520-576, 4779-4800).  Every element of an NDX line is a session file of that
 // line's speaker (JFATranslate, AccumulateJFAStat.h:99-111): speaker = line, session = running count; a
 // file listed twice keeps the indices of its first occurrence (_idxOfID).
+namespace {
+// one pass over the files of a JFA NDX: per-session and per-speaker statistics, saved under the reference's
+// names (saveAccs :4779-4800)
+void jfaStatsToDisk(const Config &c) {
+  XList ndx(c.getParam("ndxFilename"));
+  std::vector<std::string> files;
+  std::vector<int32_t> spkOfSession;
+  std::map<std::string, int> sessionOfFile;
+  int loc = 0;
+  for (auto &l : ndx.lines()) {
+    for (auto &f : l) {
+      if (!sessionOfFile.count(f)) sessionOfFile[f] = (int)spkOfSession.size();
+      files.push_back(f);
+      spkOfSession.push_back(loc);
+    }
+    loc++;
+  }
+  const size_t nSessions = spkOfSession.size(), nSpeakers = (size_t)loc;
+  if (nSessions == 0) LIA_THROW("JFA statistics: empty ndx");
+  std::vector<std::string> unique;
+  {
+    std::set<std::string> seen;
+    for (auto &f : files)
+      if (seen.insert(f).second) unique.push_back(f);
+  }
+  MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+  FeatureServer fs(c, unique);
+  SegCluster sel = selectedSegments(c, fs, c.getParam("labelSelectedFrames"));
+  std::vector<lr_seg> segs;
+  for (const Seg &s : sel) {
+    lr_seg e;
+    e.begin = (int64_t)(fs.getFirstFeatureIndexOfASource(s.source) + s.begin);
+    e.length = s.length;
+    e.row = (int32_t)sessionOfFile[s.source];
+    e.pad_ = 0;
+    segs.push_back(e);
+  }
+  const size_t C = world.C, sv = (size_t)world.C * world.D;
+  Matrix Nh(nSessions, C), Fh(nSessions, sv), N(nSpeakers, C), F(nSpeakers, sv);
+  Gmm g(world, true);
+  LIA_CHECK(lr_jfa_bwstats(g.h(), fs.data(), fs.getFeatureCount(), fs.ld(), segs.data(), segs.size(), nSessions,
+                           spkOfSession.data(), nSpeakers, Nh.data.data(), Fh.data.data(), N.data.data(),
+                           F.data.data()));
+  const std::string path = c.getString("matrixFilesPath", ""), ext = c.getString("saveMatrixFilesExtension", "");
+  const std::string fmt = c.getString("saveMatrixFormat", "DB");
+  F.save(path + c.getString("firstOrderStatSpeaker", "F_X") + ext, fmt);
+  Fh.save(path + c.getString("firstOrderStatSession", "F_X_h") + ext, fmt);
+  Nh.save(path + c.getString("nullOrderStatSession", "N_h") + ext, fmt);
+  N.save(path + c.getString("nullOrderStatSpeaker", "N") + ext, fmt);
+}
+}  // namespace
+
 int ComputeJFAStats(Config &c) {
   try {
-    XList ndx(c.getParam("ndxFilename"));
-    std::vector<std::string> files;
-    std::vector<int32_t> spkOfSession;
-    std::map<std::string, int> sessionOfFile;
-    int loc = 0;
-    for (auto &l : ndx.lines()) {
-      for (auto &f : l) {
-        if (!sessionOfFile.count(f)) sessionOfFile[f] = (int)spkOfSession.size();
-        files.push_back(f);
-        spkOfSession.push_back(loc);
+    jfaStatsToDisk(c);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ EigenVoice
+// EigenVoice.cpp:71-165.  With D, Z, U, X at their initial zeros the JFAAcc steps of this program are the
+// TVAcc steps under other names -- estimateVEVT = estimateTETt (:1266-1293 vs AccumulateTVStat.cpp:777-805),
+// estimateAndInverseL_EV + estimateYandV = estimateAandC (:2467-2515 vs :1702-1795), substractMplusDZ =
+// substractM (Z = 0), substractUX = nothing (U = 0), updateVestimate = updateTestimate (:3597-3618),
+// orthonormalizeV = orthonormalizeT, storeAccs / restoreAccs = the reload of N / F_X -- on the per-SPEAKER
+// statistics, so the eigenvoice matrix V is trained by the same device path as T.
+int EigenVoice(Config &c) {
+  try {
+    Config c2 = c;
+    c2.setParam("totalVariabilityNumber", c.getParam("eigenVoiceNumber"));
+    if (!c2.existsParam("nullOrderStatSpeaker")) c2.setParam("nullOrderStatSpeaker", "N");
+    if (!c2.existsParam("firstOrderStatSpeaker")) c2.setParam("firstOrderStatSpeaker", "F_X");
+    TVAcc tv(c2.getParam("ndxFilename"), c2);
+    if (!c.getBool("loadAccs", false)) {
+      if (Shard::get().world == 1) {
+        jfaStatsToDisk(c2);  // N, F_X, N_h, F_X_h (computeAndAccumulateJFAStat + saveAccs)
+        tv.loadN(c2);
+        tv.loadF_X(c2);
+      } else {
+        tv.computeAndAccumulateTVStat(c2);  // the speaker-level pair, sharded by NDX line
+        tv.saveAccs(c2);
       }
-      loc++;
+    } else {
+      tv.loadN(c2);
+      tv.loadF_X(c2);
     }
-    const size_t nSessions = spkOfSession.size(), nSpeakers = (size_t)loc;
-    if (nSessions == 0) LIA_THROW("ComputeJFAStats: empty ndx");
-    std::vector<std::string> unique;
-    {
-      std::set<std::string> seen;
-      for (auto &f : files)
-        if (seen.insert(f).second) unique.push_back(f);
+    if (c.getBool("loadInitEigenVoiceMatrix", false))
+      tv.loadT(c.getParam("initEigenVoiceMatrix"), c2);
+    else
+      tv.initT(c2);
+    const bool root = Shard::get().rank == 0;
+    if (c.getBool("saveInitEigenVoiceMatrix", false) && root) tv.saveT(c.getParam("eigenVoiceMatrix") + "_init", c2);
+    const long nbIt = c.getLong("nbIt");
+    for (long it = 0; it < nbIt; it++) {
+      std::cout << "\t(EigenVoices) --------- start iteration " << it << " --------" << std::endl;
+      tv.estimateTETt();   // estimateVEVT
+      tv.substractM();     // substractMplusDZ with Z = 0 (the order against estimateVEVT does not matter)
+      tv.estimateAandC();  // estimateAndInverseL_EV + estimateYandV
+      tv.updateTestimate();
+      if (c.getBool("orthonormalizeV", false)) tv.orthonormalizeT();
+      tv.resetTmpAcc();
+      tv.reloadStats();  // restoreAccs
+      if (c.getBool("saveAllEVMatrices", false) && root) tv.saveT(c.getParam("eigenVoiceMatrix") + std::to_string(it), c2);
     }
-    MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
-    FeatureServer fs(c, unique);
-    SegCluster sel = selectedSegments(c, fs, c.getParam("labelSelectedFrames"));
-    std::vector<lr_seg> segs;
-    for (const Seg &s : sel) {
-      lr_seg e;
-      e.begin = (int64_t)(fs.getFirstFeatureIndexOfASource(s.source) + s.begin);
-      e.length = s.length;
-      e.row = (int32_t)sessionOfFile[s.source];
-      e.pad_ = 0;
-      segs.push_back(e);
-    }
-    const size_t C = world.C, sv = (size_t)world.C * world.D;
-    Matrix Nh(nSessions, C), Fh(nSessions, sv), N(nSpeakers, C), F(nSpeakers, sv);
-    Gmm g(world, true);
-    LIA_CHECK(lr_jfa_bwstats(g.h(), fs.data(), fs.getFeatureCount(), fs.ld(), segs.data(), segs.size(), nSessions,
-                             spkOfSession.data(), nSpeakers, Nh.data.data(), Fh.data.data(), N.data.data(),
-                             F.data.data()));
-    const std::string path = c.getString("matrixFilesPath", ""), ext = c.getString("saveMatrixFilesExtension", "");
-    const std::string fmt = c.getString("saveMatrixFormat", "DB");
-    F.save(path + c.getString("firstOrderStatSpeaker", "F_X") + ext, fmt);
-    Fh.save(path + c.getString("firstOrderStatSession", "F_X_h") + ext, fmt);
-    Nh.save(path + c.getString("nullOrderStatSession", "N_h") + ext, fmt);
-    N.save(path + c.getString("nullOrderStatSpeaker", "N") + ext, fmt);
+    if (root) tv.saveT(c.getParam("eigenVoiceMatrix"), c2);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }

@@ -241,6 +241,41 @@ def test_ivector_and_tv_cli(world, oracle):
     assert np.abs(lf.read_db(d / "meanEst.mat")[0] - mean).max() < 1e-4 * np.abs(mean).max()
 
 
+def test_eigenvoice_cli(world, oracle):
+    """EigenVoice (EigenVoice.cpp:71-165): with D = Z = U = X = 0 the JFAAcc iteration IS the TVAcc iteration on the
+    per-speaker statistics (estimateVEVT / estimateAndInverseL_EV / estimateYandV / updateVestimate), so V after two
+    iterations is the oracle's T-matrix EM without minDivergence; the program also leaves the four JFA statistics."""
+    d, C, D, R = world["dir"], world["C"], world["D"], 5
+    invvar = (1.0 / world["cov"]).reshape(-1)
+    V0 = synth.make_T(R, C, D, invvar, seed=291, scale=0.05)
+    lf.write_db(d / "V0.mat", V0)
+    ndx = [["utt0", "utt1"], ["utt2"], ["utt3", "utt4"], ["utt5"]]
+    lf.write_lines(d / "ev.ndx", ndx)
+    lf.write_cfg(d / "ev.cfg", **world["common"], ndxFilename=str(d / "ev.ndx"), inputWorldFilename="wld",
+                 eigenVoiceNumber=R, eigenVoiceMatrix="V_out", loadInitEigenVoiceMatrix="true", initEigenVoiceMatrix="V0",
+                 nullOrderStatSpeaker="N_ev", firstOrderStatSpeaker="FX_ev", nullOrderStatSession="Nh_ev",
+                 firstOrderStatSession="FXh_ev", nbIt=2)
+    _run("EigenVoice", d / "ev.cfg")
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    N, F = np.zeros((len(ndx), C)), np.zeros((len(ndx), C * D))
+    for row, line in enumerate(ndx):
+        for u in line:
+            X = np.ascontiguousarray(world["utts"][u][_selected(u, world["utts"][u])])
+            n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+            N[row] += n1[0]
+            F[row] += f1[0]
+    assert lf.read_db(d / "Nh_ev.mat").shape == (6, C) and lf.read_db(d / "FXh_ev.mat").shape == (6, C * D)
+    assert np.abs(lf.read_db(d / "N_ev.mat") - N).max() < 1e-4 * np.abs(N).max()
+    Vr, mean = V0.copy(), world["mean"].reshape(-1)
+    for it in range(2):
+        Fc = oracle.tv_subtract_m(N, F, mean)
+        tett = oracle.tv_tett(Vr, invvar, C, D)
+        _, A, Cmx, _, _, _ = oracle.tv_estep(N, Fc, Vr, invvar, tett)
+        Vr = oracle.tv_mstep(A, Cmx, C, D)
+    got = lf.read_db(d / "V_out.mat")
+    assert np.abs(got - Vr).max() < 1e-3 * np.abs(Vr).max()
+
+
 def test_ivextractor_approximate_modes_cli(world, oracle):
     """IvExtractor --mode ubmWeight / eigenDecomposition (IvExtractor.cpp:151-363), both computing the
     approximation parameters on the fly and loading the ones TotalVariability wrote with
