@@ -78,7 +78,8 @@ lr_status gmm_pass_acc(lr_gmm *g, const FrameList &fl, const float *d_lse2,
 // tcgen05 implementations of the same two passes (gmm_tc.cu)
 bool tc_supported(const lr_gmm *g);
 lr_status tc_derive(lr_gmm *g);
-lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_llk_sum);
+// d_S (optional): [P x Cp] fp32 log2 joint likelihoods, the scores the top-K path nominates on
+lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_llk_sum, float *d_S = nullptr);
 // likelihood + statistics over a tile-padded frame list (chunks tile aligned, host copy)
 // conv != nullptr: the converted operand of this frame list lives there (n_tiles x 64 KB); it is
 // (re)written unless conv_valid

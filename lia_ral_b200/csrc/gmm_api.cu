@@ -483,8 +483,13 @@ static lr_status topk_block(lr_gmm *world, const float *dX, size_t ldx, long P, 
   *d_rest = rest;
   *d_restw = rest + P;
   FrameList fl{dX, ldx, nullptr, P};
-  // the top-K path always uses the fp32 SIMT scores (it needs the full S matrix)
-  lr_status st = gmm_pass_lse(world, fl, d_lse, d_S, nullptr);
+  // candidate nomination needs the full S matrix: from the tcgen05 likelihood pass when the world model is
+  // served by it (a 2048-component world: the same contraction as a1), else from the fp32 SIMT pass.  Either
+  // way the candidates are re-evaluated in fp64 in the reference's operation order (gmm_topk.cu).
+  lr_status sel = LR_OK;
+  const bool tc = tc_selected(world, &sel);
+  if (sel != LR_OK) return sel;
+  lr_status st = tc ? tc_pass_lse(world, fl, d_lse, nullptr, d_S) : gmm_pass_lse(world, fl, d_lse, d_S, nullptr);
   if (st != LR_OK) return st;
   return gmm_topk(world, fl, d_S, K, complete, min_llk, max_llk, *d_llk, *d_idx, *d_top, *d_rest,
                   *d_restw);

@@ -316,7 +316,8 @@ __device__ __forceinline__ void issue_g1_ts(uint32_t d_tmem, uint32_t w_tmem, ui
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_tc_lse(int n_slices, int csize, const unsigned char *__restrict__ Wp,
          const unsigned char *__restrict__ Xh, const int *__restrict__ group_tiles /*[groups + 1]*/,
-         long P_pad, float2 *__restrict__ part /*[slices][P_pad]*/, int dbg) {
+         long P_pad, float2 *__restrict__ part /*[slices][P_pad]*/, int dbg,
+         float *__restrict__ S_out /*[P][Cp] log2 joint likelihoods, or null*/, long P, int Cp) {
   extern __shared__ unsigned char smem_raw[];
   const Smem sm = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -410,6 +411,14 @@ k_tc_lse(int n_slices, int csize, const unsigned char *__restrict__ Wp,
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + ch * 32, r);
         tmem_wait_ld();
+        if (S_out) {  // the top-K path nominates its candidates on these scores (gmm_topk.cu)
+          const long pf = (long)(t_begin + i) * kTile + q * 32 + lane;
+          if (pf < P) {
+            uint4 *dst = reinterpret_cast<uint4 *>(S_out + (size_t)pf * Cp + (size_t)slice * kSlice + ch * 32);
+#pragma unroll
+            for (int e = 0; e < 8; e++) dst[e] = make_uint4(r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
+          }
+        }
         float c8[8];
 #pragma unroll
         for (int e = 0; e < 8; e++)
@@ -1662,7 +1671,7 @@ static lr_status tc_launch_coop(void (*kern)(Args...), int grid, Args... args) {
 
 // The tensor-core path works on a PADDED frame list (P_pad = multiple of 128; padding entries
 // carry index 0xFFFFFFFF): see tc_pad_plan in gmm_api.cu.  fl.P is the padded length here.
-lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_llk_sum) {
+lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_llk_sum, float *d_S) {
   Engine &e = engine();
   TcState *st = (TcState *)g->d_tc_w;
   lr_status rc = tc_set_attrs();
@@ -1688,7 +1697,7 @@ lr_status tc_pass_lse(lr_gmm *g, const FrameList &fl, float *d_lse2, double *d_l
     ProfileScope prof(0);
     rc = tc_launch(k_tc_lse, n_slices * groups, csize, n_slices, csize,
                    (const unsigned char *)st->d_W, (const unsigned char *)Xh, (const int *)d_cuts,
-                   P_pad, part, e.tc_debug);
+                   P_pad, part, e.tc_debug, d_S, P, g->Cp);
     if (rc != LR_OK) return rc;
   }
   k_tc_combine<<<(unsigned)((P_pad + 255) / 256), 256, 0, e.stream>>>(n_slices, P, P_pad, fl.d_index,
