@@ -344,6 +344,114 @@ int EigenVoice(Config &c) {
   return 0;
 }
 
+// ------------------------------------------------------------------ EigenChannel (JFA mode)
+// EigenChannelJFA (EigenChannel.cpp:71-160).  Speaker factors first (estimateVEVT, estimateAndInverseL_EV,
+// substractMplusDZ, estimateY = the i-vector solve on the speaker statistics with V), then the channel subspace
+// is trained on the SESSION statistics after removing every speaker's own supervector,
+//   F_X_h[h] -= N_h[h] o (M + V y_spk(h))                    (substractMplusVYplusDZ :4400-4428, Z = 0)
+// and from there estimateUEUT / estimateAndInverseL_EC / estimateXandU / updateUestimate (:3040-3088, :3620-3640)
+// are the TVAcc steps on (N_h, F_X_h) with a zero mean -- the same device path as T and V.
+int EigenChannel(Config &c) {
+  try {
+    if (Shard::get().world != 1) LIA_THROW("EigenChannel: one process only (the session statistics are not sharded)");
+    const std::string path = c.getString("matrixFilesPath", ""), lext = c.getString("loadMatrixFilesExtension", "");
+    const std::string sext = c.getString("saveMatrixFilesExtension", ""), lfmt = c.getString("loadMatrixFormat", "DB");
+    const std::string sfmt = c.getString("saveMatrixFormat", "DB");
+    Config cs = c;  // the four statistics under explicit names
+    if (!cs.existsParam("nullOrderStatSpeaker")) cs.setParam("nullOrderStatSpeaker", "N");
+    if (!cs.existsParam("firstOrderStatSpeaker")) cs.setParam("firstOrderStatSpeaker", "F_X");
+    if (!cs.existsParam("nullOrderStatSession")) cs.setParam("nullOrderStatSession", "N_h");
+    if (!cs.existsParam("firstOrderStatSession")) cs.setParam("firstOrderStatSession", "F_X_h");
+    if (!c.getBool("loadAccs", false)) jfaStatsToDisk(cs);
+    // speaker / session structure of the NDX (JFATranslate)
+    XList ndx(c.getParam("ndxFilename"));
+    std::vector<int> spkOfSession;
+    std::vector<std::vector<std::string>> sessionLines;
+    int loc = 0;
+    for (auto &l : ndx.lines()) {
+      for (auto &f : l) {
+        spkOfSession.push_back(loc);
+        sessionLines.push_back({f});
+      }
+      loc++;
+    }
+    const size_t nSessions = spkOfSession.size(), nSpk = (size_t)loc;
+    MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+    const size_t C = world.C, sv = (size_t)world.C * world.D;
+    // ---- speaker factors y with the eigenvoice matrix (V = 0 when none is given: y = 0)
+    Matrix off(nSpk, sv);  // V y per speaker
+    if (c.existsParam("eigenVoiceMatrix")) {
+      Config cv = cs;
+      cv.setParam("totalVariabilityNumber", c.getParam("eigenVoiceNumber"));
+      TVAcc tvV(c.getParam("ndxFilename"), cv);
+      tvV.loadN(cv);
+      tvV.loadF_X(cv);
+      tvV.loadT(c.getParam("eigenVoiceMatrix"), cv);
+      tvV.substractM();
+      tvV.estimateTETt();
+      tvV.estimateW();
+      Matrix Y = tvV.getW();  // [nSpk x Rv]
+      Matrix V;
+      V.load(path + c.getParam("eigenVoiceMatrix") + lext, lfmt);
+      if (V.cols < V.rows) {  // stored transposed (loadEV, like loadT :636-639)
+        Matrix t(V.cols, V.rows);
+        for (size_t i = 0; i < V.rows; i++)
+          for (size_t j = 0; j < V.cols; j++) t(j, i) = V(i, j);
+        V = t;
+      }
+      Matrix Vt(sv, V.rows);
+      for (size_t i = 0; i < V.rows; i++)
+        for (size_t j = 0; j < sv; j++) Vt(j, i) = V(i, j);
+      LIA_CHECK(lr_gemm_digits(nSpk, sv, V.rows, Y.data.data(), Vt.data.data(), off.data.data(), 1.0, 0.0, 0));
+    }
+    // ---- session statistics minus the speaker supervectors
+    Matrix Nh, Fh;
+    Nh.load(path + cs.getParam("nullOrderStatSession") + lext, lfmt);
+    Fh.load(path + cs.getParam("firstOrderStatSession") + lext, lfmt);
+    if (Nh.rows != nSessions || Nh.cols != C || Fh.rows != nSessions || Fh.cols != sv)
+      LIA_THROW("Incorrect dimension of the session statistics");
+    for (size_t h = 0; h < nSessions; h++) {
+      const size_t sp = (size_t)spkOfSession[h];
+      for (size_t k = 0; k < C; k++) {
+        const double n = Nh(h, k);
+        for (int i = 0; i < world.D; i++) {
+          const size_t j = k * world.D + i;
+          Fh(h, j) -= n * (world.mean[j] + off(sp, j));
+        }
+      }
+    }
+    Fh.save(path + "F_X_h_centered" + sext, sfmt);
+    Config cu = cs;
+    cu.setParam("totalVariabilityNumber", c.getParam("eigenChannelNumber"));
+    cu.setParam("nullOrderStatSpeaker", cs.getParam("nullOrderStatSession"));
+    cu.setParam("firstOrderStatSpeaker", "F_X_h_centered");
+    TVAcc tvU(sessionLines, cu);
+    tvU.loadN(cu);
+    tvU.loadF_X(cu);
+    tvU.loadMeanEstimate(std::vector<double>(sv, 0.0));  // everything was subtracted above
+    if (c.getBool("loadInitChannelMatrix", false))
+      tvU.loadT(c.getParam("initEigenChannelMatrix"), cu);
+    else
+      tvU.initT(cu);
+    if (c.getBool("saveInitChannelMatrix", false)) tvU.saveT(c.getParam("initEigenChannelMatrix"), cu);
+    const long nbIt = c.getLong("nbIt");
+    for (long it = 0; it < nbIt; it++) {
+      std::cout << "\t(EigenChannel) --------- start iteration " << it << " --------" << std::endl;
+      tvU.estimateTETt();   // estimateUEUT
+      tvU.substractM();     // zero mean: keeps the row maxima of F for the digit GEMM up to date
+      tvU.estimateAandC();  // estimateAndInverseL_EC + estimateXandU
+      tvU.updateTestimate();
+      tvU.resetTmpAcc();
+      tvU.reloadStats();
+      if (c.getBool("saveAllECMatrices", false)) tvU.saveT(c.getParam("eigenChannelMatrix") + std::to_string(it), cu);
+    }
+    tvU.saveT(c.getParam("eigenChannelMatrix"), cu);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ IvExtractor (approximate modes)
 namespace {
 // shared head / tail of IvExtractorUbmWeigth and IvExtractorEigenDecomposition

@@ -1,0 +1,25 @@
+// EigenChannelMain.cpp -- command-line entry point: "--config <file>" plus "--name value" overrides,
+// like LIA_SpkDet/EigenChannel/src/EigenChannelMain.cpp (channelCompensation JFA).
+#include <iostream>
+
+#include "lia_host.h"
+
+int main(int argc, char **argv) {
+  try {
+    lia::Config config;
+    config.parseCmdLine(argc, argv);
+    if (config.existsParam("help")) {
+      std::cout << "EigenChannel (lia_ral_b200 engine, JFA mode): --config <file> [--param value ...]" << std::endl;
+      return 0;
+    }
+    if (config.existsParam("channelCompensation") && config.getParam("channelCompensation") != "JFA") {
+      std::cout << "EigenChannel: only channelCompensation JFA is implemented by this engine" << std::endl;
+      return 0;
+    }
+    lia::initEngine(config);
+    return lia::EigenChannel(config);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}

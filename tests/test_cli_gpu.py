@@ -276,6 +276,49 @@ def test_eigenvoice_cli(world, oracle):
     assert np.abs(got - Vr).max() < 1e-3 * np.abs(Vr).max()
 
 
+def test_eigenchannel_cli(world, oracle):
+    """EigenChannel, JFA mode (EigenChannel.cpp:71-160): speaker factors with V, session statistics minus
+    N_h o (M + V y_spk), then the channel matrix U by the TVAcc iteration on the session statistics."""
+    d, C, D, Rv, Ru = world["dir"], world["C"], world["D"], 4, 3
+    invvar = (1.0 / world["cov"]).reshape(-1)
+    V0 = synth.make_T(Rv, C, D, invvar, seed=391, scale=0.05)
+    U0 = synth.make_T(Ru, C, D, invvar, seed=392, scale=0.05)
+    lf.write_db(d / "ecV.mat", V0)
+    lf.write_db(d / "ecU0.mat", U0)
+    ndx = [["utt0", "utt1"], ["utt2", "utt3"], ["utt4", "utt5"]]
+    lf.write_lines(d / "ec.ndx", ndx)
+    lf.write_cfg(d / "ec.cfg", **world["common"], ndxFilename=str(d / "ec.ndx"), inputWorldFilename="wld",
+                 channelCompensation="JFA", eigenVoiceNumber=Rv, eigenVoiceMatrix="ecV", eigenChannelNumber=Ru,
+                 eigenChannelMatrix="ecU_out", loadInitChannelMatrix="true", initEigenChannelMatrix="ecU0",
+                 nullOrderStatSpeaker="N_ec", firstOrderStatSpeaker="FX_ec", nullOrderStatSession="Nh_ec",
+                 firstOrderStatSession="FXh_ec", nbIt=2)
+    _run("EigenChannel", d / "ec.cfg")
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    mean = world["mean"].reshape(-1)
+    n_sess = sum(len(l) for l in ndx)
+    N, F = np.zeros((len(ndx), C)), np.zeros((len(ndx), C * D))
+    Nh, Fh, spk_of = np.zeros((n_sess, C)), np.zeros((n_sess, C * D)), []
+    h = 0
+    for row, line in enumerate(ndx):
+        for u in line:
+            X = np.ascontiguousarray(world["utts"][u][_selected(u, world["utts"][u])])
+            n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+            Nh[h], Fh[h] = n1[0], f1[0]
+            N[row] += n1[0]
+            F[row] += f1[0]
+            spk_of.append(row)
+            h += 1
+    Y = oracle.tv_ivectors(N, oracle.tv_subtract_m(N, F, mean), V0, invvar, oracle.tv_tett(V0, invvar, C, D))
+    sup = mean[None, :] + Y @ V0                                   # M + V y per speaker
+    Fc = Fh - np.repeat(Nh, D, axis=1) * sup[np.array(spk_of)]
+    Ur = U0.copy()
+    for it in range(2):
+        _, A, Cmx, _, _, _ = oracle.tv_estep(Nh, Fc, Ur, invvar, oracle.tv_tett(Ur, invvar, C, D))
+        Ur = oracle.tv_mstep(A, Cmx, C, D)
+    got = lf.read_db(d / "ecU_out.mat")
+    assert np.abs(got - Ur).max() < 1e-3 * np.abs(Ur).max()
+
+
 def test_ivextractor_approximate_modes_cli(world, oracle):
     """IvExtractor --mode ubmWeight / eigenDecomposition (IvExtractor.cpp:151-363), both computing the
     approximation parameters on the fly and loading the ones TotalVariability wrote with
