@@ -336,6 +336,7 @@ int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:
 int ComputeJFAStats(Config &c);  // ComputeJFAStats.cpp:71-87 (per-session + per-speaker BW statistics)
 int EigenVoice(Config &c);       // EigenVoice.cpp:71-165 (V trained by the TVAcc device path on speaker statistics)
 int EigenChannel(Config &c);     // EigenChannel.cpp:71-160, JFA mode (U trained on the session statistics)
+int EstimateDMatrix(Config &c);  // EstimateDMatrix.cpp:99-210 (y, x on the device path, diagonal D update)
 int IvExtractorUbmWeigth(Config &c);          // IvExtractor.cpp:151 (mode ubmWeight; the reference's spelling)
 int IvExtractorEigenDecomposition(Config &c); // IvExtractor.cpp:254 (mode eigenDecomposition)
 int TotalVariability(Config &c);  // LIA_SpkDet/TotalVariability/src/TotalVariability.cpp:71

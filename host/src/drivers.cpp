@@ -1,5 +1,6 @@
 // drivers.cpp -- int Foo(Config&) entry points with the reference programs' parameter names and
 // output formats.  Errors follow the reference: catch, print e.toString(), return 0.
+#include <cmath>
 #include <map>
 #include <memory>
 #include <set>
@@ -351,101 +352,223 @@ int EigenVoice(Config &c) {
 //   F_X_h[h] -= N_h[h] o (M + V y_spk(h))                    (substractMplusVYplusDZ :4400-4428, Z = 0)
 // and from there estimateUEUT / estimateAndInverseL_EC / estimateXandU / updateUestimate (:3040-3088, :3620-3640)
 // are the TVAcc steps on (N_h, F_X_h) with a zero mean -- the same device path as T and V.
+namespace {
+// What EigenChannelJFA and EstimateDMatrix share: the four statistics, the NDX structure, the speaker factors y
+// (estimateVEVT, estimateAndInverseL_EV, substractMplusDZ with Z = 0, estimateY) and the speaker supervectors V y.
+struct JfaState {
+  Config cs;  // the configuration with the four statistics under explicit names
+  std::string path, lext, sext, lfmt, sfmt;
+  std::vector<int> spkOfSession;
+  std::vector<std::vector<std::string>> sessionLines;
+  size_t nSessions = 0, nSpk = 0, C = 0, sv = 0;
+  MixtureGD world;
+  Matrix N, F, Nh, Fh;  // speaker / session statistics
+  Matrix VY;            // [nSpk x sv] V y (zero without an eigenvoice matrix)
+};
+Matrix loadSubspace(const JfaState &j, const std::string &name) {
+  Matrix V;
+  V.load(j.path + name + j.lext, j.lfmt);
+  if (V.cols < V.rows) {  // stored transposed (loadEV / loadEC, like loadT :636-639)
+    Matrix t(V.cols, V.rows);
+    for (size_t i = 0; i < V.rows; i++)
+      for (size_t k = 0; k < V.cols; k++) t(k, i) = V(i, k);
+    V = t;
+  }
+  if (V.cols != j.sv) LIA_THROW("Incorrect dimension of the subspace matrix " + name);
+  return V;
+}
+// rows[n x R] * M[R x sv] through the digit GEMM (the supervectors V y / U x)
+Matrix supervectors(const Matrix &rows, const Matrix &M) {
+  Matrix Mt(M.cols, M.rows);
+  for (size_t i = 0; i < M.rows; i++)
+    for (size_t k = 0; k < M.cols; k++) Mt(k, i) = M(i, k);
+  Matrix out(rows.rows, M.cols);
+  LIA_CHECK(lr_gemm_digits(rows.rows, M.cols, M.rows, rows.data.data(), Mt.data.data(), out.data.data(), 1.0, 0.0, 0));
+  return out;
+}
+void jfaPrepare(Config &c, JfaState &j) {
+  if (Shard::get().world != 1) LIA_THROW("JFA training programs: one process only (the session statistics are not sharded)");
+  j.path = c.getString("matrixFilesPath", "");
+  j.lext = c.getString("loadMatrixFilesExtension", "");
+  j.sext = c.getString("saveMatrixFilesExtension", "");
+  j.lfmt = c.getString("loadMatrixFormat", "DB");
+  j.sfmt = c.getString("saveMatrixFormat", "DB");
+  j.cs = c;
+  if (!j.cs.existsParam("nullOrderStatSpeaker")) j.cs.setParam("nullOrderStatSpeaker", "N");
+  if (!j.cs.existsParam("firstOrderStatSpeaker")) j.cs.setParam("firstOrderStatSpeaker", "F_X");
+  if (!j.cs.existsParam("nullOrderStatSession")) j.cs.setParam("nullOrderStatSession", "N_h");
+  if (!j.cs.existsParam("firstOrderStatSession")) j.cs.setParam("firstOrderStatSession", "F_X_h");
+  if (!c.getBool("loadAccs", false)) jfaStatsToDisk(j.cs);
+  XList ndx(c.getParam("ndxFilename"));
+  int loc = 0;
+  for (auto &l : ndx.lines()) {
+    for (auto &f : l) {
+      j.spkOfSession.push_back(loc);
+      j.sessionLines.push_back({f});
+    }
+    loc++;
+  }
+  j.nSessions = j.spkOfSession.size();
+  j.nSpk = (size_t)loc;
+  j.world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+  j.C = j.world.C;
+  j.sv = (size_t)j.world.C * j.world.D;
+  j.N.load(j.path + j.cs.getParam("nullOrderStatSpeaker") + j.lext, j.lfmt);
+  j.F.load(j.path + j.cs.getParam("firstOrderStatSpeaker") + j.lext, j.lfmt);
+  j.Nh.load(j.path + j.cs.getParam("nullOrderStatSession") + j.lext, j.lfmt);
+  j.Fh.load(j.path + j.cs.getParam("firstOrderStatSession") + j.lext, j.lfmt);
+  if (j.N.rows != j.nSpk || j.N.cols != j.C || j.F.rows != j.nSpk || j.F.cols != j.sv || j.Nh.rows != j.nSessions ||
+      j.Nh.cols != j.C || j.Fh.rows != j.nSessions || j.Fh.cols != j.sv)
+    LIA_THROW("Incorrect dimension of the JFA statistics");
+  j.VY = Matrix(j.nSpk, j.sv);
+  if (c.existsParam("eigenVoiceMatrix")) {
+    Config cv = j.cs;
+    cv.setParam("totalVariabilityNumber", c.getParam("eigenVoiceNumber"));
+    TVAcc tvV(c.getParam("ndxFilename"), cv);
+    tvV.loadN(cv);
+    tvV.loadF_X(cv);
+    tvV.loadT(c.getParam("eigenVoiceMatrix"), cv);
+    tvV.substractM();
+    tvV.estimateTETt();
+    tvV.estimateW();
+    j.VY = supervectors(tvV.getW(), loadSubspace(j, c.getParam("eigenVoiceMatrix")));
+  }
+}
+// F_X_h[h] -= N_h[h] o (M + V y_spk(h))   (substractMplusVYplusDZ :4400-4428 with Z = 0)
+Matrix centredSessionStats(const JfaState &j) {
+  Matrix Fc = j.Fh;
+  const int D = j.world.D;
+  for (size_t h = 0; h < j.nSessions; h++) {
+    const size_t sp = (size_t)j.spkOfSession[h];
+    for (size_t k = 0; k < j.C; k++) {
+      const double n = j.Nh(h, k);
+      for (int i = 0; i < D; i++) {
+        const size_t e = k * D + i;
+        Fc(h, e) -= n * (j.world.mean[e] + j.VY(sp, e));
+      }
+    }
+  }
+  return Fc;
+}
+// a TVAcc over the sessions (one NDX line per session) holding (N_h, centred F_X_h) with a zero mean
+std::unique_ptr<TVAcc> sessionAcc(const JfaState &j, const Matrix &Fc, const std::string &rankKeyValue, Config &cu) {
+  Fc.save(j.path + "F_X_h_centered" + j.sext, j.sfmt);
+  cu = j.cs;
+  cu.setParam("totalVariabilityNumber", rankKeyValue);
+  cu.setParam("nullOrderStatSpeaker", j.cs.getParam("nullOrderStatSession"));
+  cu.setParam("firstOrderStatSpeaker", "F_X_h_centered");
+  std::unique_ptr<TVAcc> tv(new TVAcc(j.sessionLines, cu));
+  tv->loadN(cu);
+  tv->loadF_X(cu);
+  tv->loadMeanEstimate(std::vector<double>(j.sv, 0.0));  // everything was subtracted already
+  return tv;
+}
+}  // namespace
+
 int EigenChannel(Config &c) {
   try {
-    if (Shard::get().world != 1) LIA_THROW("EigenChannel: one process only (the session statistics are not sharded)");
-    const std::string path = c.getString("matrixFilesPath", ""), lext = c.getString("loadMatrixFilesExtension", "");
-    const std::string sext = c.getString("saveMatrixFilesExtension", ""), lfmt = c.getString("loadMatrixFormat", "DB");
-    const std::string sfmt = c.getString("saveMatrixFormat", "DB");
-    Config cs = c;  // the four statistics under explicit names
-    if (!cs.existsParam("nullOrderStatSpeaker")) cs.setParam("nullOrderStatSpeaker", "N");
-    if (!cs.existsParam("firstOrderStatSpeaker")) cs.setParam("firstOrderStatSpeaker", "F_X");
-    if (!cs.existsParam("nullOrderStatSession")) cs.setParam("nullOrderStatSession", "N_h");
-    if (!cs.existsParam("firstOrderStatSession")) cs.setParam("firstOrderStatSession", "F_X_h");
-    if (!c.getBool("loadAccs", false)) jfaStatsToDisk(cs);
-    // speaker / session structure of the NDX (JFATranslate)
-    XList ndx(c.getParam("ndxFilename"));
-    std::vector<int> spkOfSession;
-    std::vector<std::vector<std::string>> sessionLines;
-    int loc = 0;
-    for (auto &l : ndx.lines()) {
-      for (auto &f : l) {
-        spkOfSession.push_back(loc);
-        sessionLines.push_back({f});
-      }
-      loc++;
-    }
-    const size_t nSessions = spkOfSession.size(), nSpk = (size_t)loc;
-    MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
-    const size_t C = world.C, sv = (size_t)world.C * world.D;
-    // ---- speaker factors y with the eigenvoice matrix (V = 0 when none is given: y = 0)
-    Matrix off(nSpk, sv);  // V y per speaker
-    if (c.existsParam("eigenVoiceMatrix")) {
-      Config cv = cs;
-      cv.setParam("totalVariabilityNumber", c.getParam("eigenVoiceNumber"));
-      TVAcc tvV(c.getParam("ndxFilename"), cv);
-      tvV.loadN(cv);
-      tvV.loadF_X(cv);
-      tvV.loadT(c.getParam("eigenVoiceMatrix"), cv);
-      tvV.substractM();
-      tvV.estimateTETt();
-      tvV.estimateW();
-      Matrix Y = tvV.getW();  // [nSpk x Rv]
-      Matrix V;
-      V.load(path + c.getParam("eigenVoiceMatrix") + lext, lfmt);
-      if (V.cols < V.rows) {  // stored transposed (loadEV, like loadT :636-639)
-        Matrix t(V.cols, V.rows);
-        for (size_t i = 0; i < V.rows; i++)
-          for (size_t j = 0; j < V.cols; j++) t(j, i) = V(i, j);
-        V = t;
-      }
-      Matrix Vt(sv, V.rows);
-      for (size_t i = 0; i < V.rows; i++)
-        for (size_t j = 0; j < sv; j++) Vt(j, i) = V(i, j);
-      LIA_CHECK(lr_gemm_digits(nSpk, sv, V.rows, Y.data.data(), Vt.data.data(), off.data.data(), 1.0, 0.0, 0));
-    }
-    // ---- session statistics minus the speaker supervectors
-    Matrix Nh, Fh;
-    Nh.load(path + cs.getParam("nullOrderStatSession") + lext, lfmt);
-    Fh.load(path + cs.getParam("firstOrderStatSession") + lext, lfmt);
-    if (Nh.rows != nSessions || Nh.cols != C || Fh.rows != nSessions || Fh.cols != sv)
-      LIA_THROW("Incorrect dimension of the session statistics");
-    for (size_t h = 0; h < nSessions; h++) {
-      const size_t sp = (size_t)spkOfSession[h];
-      for (size_t k = 0; k < C; k++) {
-        const double n = Nh(h, k);
-        for (int i = 0; i < world.D; i++) {
-          const size_t j = k * world.D + i;
-          Fh(h, j) -= n * (world.mean[j] + off(sp, j));
-        }
-      }
-    }
-    Fh.save(path + "F_X_h_centered" + sext, sfmt);
-    Config cu = cs;
-    cu.setParam("totalVariabilityNumber", c.getParam("eigenChannelNumber"));
-    cu.setParam("nullOrderStatSpeaker", cs.getParam("nullOrderStatSession"));
-    cu.setParam("firstOrderStatSpeaker", "F_X_h_centered");
-    TVAcc tvU(sessionLines, cu);
-    tvU.loadN(cu);
-    tvU.loadF_X(cu);
-    tvU.loadMeanEstimate(std::vector<double>(sv, 0.0));  // everything was subtracted above
+    JfaState j;
+    jfaPrepare(c, j);
+    Config cu;
+    std::unique_ptr<TVAcc> tvU = sessionAcc(j, centredSessionStats(j), c.getParam("eigenChannelNumber"), cu);
     if (c.getBool("loadInitChannelMatrix", false))
-      tvU.loadT(c.getParam("initEigenChannelMatrix"), cu);
+      tvU->loadT(c.getParam("initEigenChannelMatrix"), cu);
     else
-      tvU.initT(cu);
-    if (c.getBool("saveInitChannelMatrix", false)) tvU.saveT(c.getParam("initEigenChannelMatrix"), cu);
+      tvU->initT(cu);
+    if (c.getBool("saveInitChannelMatrix", false)) tvU->saveT(c.getParam("initEigenChannelMatrix"), cu);
     const long nbIt = c.getLong("nbIt");
     for (long it = 0; it < nbIt; it++) {
       std::cout << "\t(EigenChannel) --------- start iteration " << it << " --------" << std::endl;
-      tvU.estimateTETt();   // estimateUEUT
-      tvU.substractM();     // zero mean: keeps the row maxima of F for the digit GEMM up to date
-      tvU.estimateAandC();  // estimateAndInverseL_EC + estimateXandU
-      tvU.updateTestimate();
-      tvU.resetTmpAcc();
-      tvU.reloadStats();
-      if (c.getBool("saveAllECMatrices", false)) tvU.saveT(c.getParam("eigenChannelMatrix") + std::to_string(it), cu);
+      tvU->estimateTETt();   // estimateUEUT
+      tvU->substractM();     // zero mean: keeps the row maxima of F for the digit GEMM up to date
+      tvU->estimateAandC();  // estimateAndInverseL_EC + estimateXandU
+      tvU->updateTestimate();
+      tvU->resetTmpAcc();
+      tvU->reloadStats();
+      if (c.getBool("saveAllECMatrices", false)) tvU->saveT(c.getParam("eigenChannelMatrix") + std::to_string(it), cu);
     }
-    tvU.saveT(c.getParam("eigenChannelMatrix"), cu);
+    tvU->saveT(c.getParam("eigenChannelMatrix"), cu);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ EstimateDMatrix
+// EstimateDMatrix.cpp:99-210.  y with V on the speaker statistics, x with U on the session statistics (both the
+// i-vector solve of the device path), then per iteration on F' = F_X - N o (M + V y) - sum_{h of spk} N_h o (U x_h)
+// (substractMplusVY :3988-4007, substractUX :4152-4178) the diagonal update estimateZandD (:3480-3515):
+//   L = 1 + N Sigma^-1 D^2,  z = F' Sigma^-1 D / L,  D <- sum_spk z F' / sum_spk (1 / L + z^2) N.
+int EstimateDMatrix(Config &c) {
+  try {
+    JfaState j;
+    jfaPrepare(c, j);
+    const int D = j.world.D;
+    // x per session with the eigenchannel matrix (U = 0 when none is given: x = 0)
+    Matrix UX(j.nSessions, j.sv);
+    if (c.existsParam("eigenChannelMatrix")) {
+      Config cu;
+      std::unique_ptr<TVAcc> tvU = sessionAcc(j, centredSessionStats(j), c.getParam("eigenChannelNumber"), cu);
+      tvU->loadT(c.getParam("eigenChannelMatrix"), cu);
+      tvU->substractM();
+      tvU->estimateTETt();
+      tvU->estimateW();
+      UX = supervectors(tvU->getW(), loadSubspace(j, c.getParam("eigenChannelMatrix")));
+    }
+    // F' (the same at every iteration: restoreAccs, then the same two subtractions)
+    Matrix Fp = j.F;
+    for (size_t sp = 0; sp < j.nSpk; sp++)
+      for (size_t k = 0; k < j.C; k++)
+        for (int i = 0; i < D; i++) {
+          const size_t e = k * D + i;
+          Fp(sp, e) -= j.N(sp, k) * (j.world.mean[e] + j.VY(sp, e));
+        }
+    for (size_t h = 0; h < j.nSessions; h++) {
+      const size_t sp = (size_t)j.spkOfSession[h];
+      for (size_t k = 0; k < j.C; k++)
+        for (int i = 0; i < D; i++) {
+          const size_t e = k * D + i;
+          Fp(sp, e) -= j.Nh(h, k) * UX(h, e);
+        }
+    }
+    std::vector<double> Dm(j.sv);
+    if (c.getBool("loadInitDMatrix", false)) {
+      Matrix d0;
+      d0.load(j.path + c.getParam("initDMatrix") + j.sext, j.lfmt);  // (loadD reads with the SAVE extension, :998)
+      if (d0.rows != 1 || d0.cols != j.sv) LIA_THROW("Incorrect dimension of D Matrix");
+      Dm = d0.data;
+    } else {
+      const std::string type = c.getString("initDType", "MAP");
+      if (type != "MAP") LIA_THROW("initDType " + type + " is not implemented by this engine (MAP | loadInitDMatrix)");
+      const double reg = c.getDouble("regulationFactor");
+      for (size_t e = 0; e < j.sv; e++) Dm[e] = std::sqrt(1.0 / (j.world.covinv[e] * reg));  // initD :1212-1216
+    }
+    auto saveD = [&](const std::string &name) {
+      Matrix d(1, j.sv);
+      d.data = Dm;
+      d.save(j.path + name + j.sext, j.sfmt);
+    };
+    if (c.getBool("saveInitD", false)) saveD(c.getParam("DMatrix") + "_init");
+    const long nbIt = c.getLong("nbIt");
+    std::vector<double> aux1(j.sv), aux2(j.sv);
+    for (long it = 0; it < nbIt; it++) {
+      std::cout << "\t(EstimateDMatrix) --------- start iteration " << it << " --------" << std::endl;
+      std::fill(aux1.begin(), aux1.end(), 0.0);
+      std::fill(aux2.begin(), aux2.end(), 0.0);
+      for (size_t sp = 0; sp < j.nSpk; sp++)
+        for (size_t k = 0; k < j.C; k++)
+          for (int i = 0; i < D; i++) {
+            const size_t e = k * D + i;
+            const double n = j.N(sp, k), iv = j.world.covinv[e];
+            const double L = 1.0 + n * iv * Dm[e] * Dm[e];
+            const double z = Fp(sp, e) * iv * Dm[e] / L;
+            aux1[e] += (1.0 / L + z * z) * n;
+            aux2[e] += z * Fp(sp, e);
+          }
+      for (size_t e = 0; e < j.sv; e++) Dm[e] = aux2[e] / aux1[e];
+      if (c.getBool("saveAllDMatrices", false)) saveD(c.getParam("DMatrix") + std::to_string(it));
+    }
+    saveD(c.getParam("DMatrix"));
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }

@@ -319,6 +319,57 @@ def test_eigenchannel_cli(world, oracle):
     assert np.abs(got - Ur).max() < 1e-3 * np.abs(Ur).max()
 
 
+def test_estimate_d_matrix_cli(world, oracle):
+    """EstimateDMatrix (EstimateDMatrix.cpp:99-210): y with V, x with U, then the diagonal update estimateZandD
+    (AccumulateJFAStat.cpp:3480-3515) on F' = F_X - N o (M + V y) - sum_h N_h o (U x_h); MAP initialisation."""
+    d, C, D, Rv, Ru = world["dir"], world["C"], world["D"], 4, 3
+    invvar = (1.0 / world["cov"]).reshape(-1)
+    V0 = synth.make_T(Rv, C, D, invvar, seed=491, scale=0.05)
+    U0 = synth.make_T(Ru, C, D, invvar, seed=492, scale=0.05)
+    lf.write_db(d / "edV.mat", V0)
+    lf.write_db(d / "edU.mat", U0)
+    ndx = [["utt0", "utt1"], ["utt2", "utt3"], ["utt4", "utt5"]]
+    lf.write_lines(d / "ed.ndx", ndx)
+    reg = 14.0
+    lf.write_cfg(d / "ed.cfg", **world["common"], ndxFilename=str(d / "ed.ndx"), inputWorldFilename="wld",
+                 eigenVoiceNumber=Rv, eigenVoiceMatrix="edV", eigenChannelNumber=Ru, eigenChannelMatrix="edU",
+                 DMatrix="edD", regulationFactor=reg, saveAllDMatrices="false", nullOrderStatSpeaker="N_ed",
+                 firstOrderStatSpeaker="FX_ed", nullOrderStatSession="Nh_ed", firstOrderStatSession="FXh_ed", nbIt=3)
+    _run("EstimateDMatrix", d / "ed.cfg")
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    mean = world["mean"].reshape(-1)
+    n_sess = sum(len(l) for l in ndx)
+    N, F = np.zeros((len(ndx), C)), np.zeros((len(ndx), C * D))
+    Nh, Fh, spk_of = np.zeros((n_sess, C)), np.zeros((n_sess, C * D)), []
+    h = 0
+    for row, line in enumerate(ndx):
+        for u in line:
+            X = np.ascontiguousarray(world["utts"][u][_selected(u, world["utts"][u])])
+            n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+            Nh[h], Fh[h] = n1[0], f1[0]
+            N[row] += n1[0]
+            F[row] += f1[0]
+            spk_of.append(row)
+            h += 1
+    spk_of = np.array(spk_of)
+    Y = oracle.tv_ivectors(N, oracle.tv_subtract_m(N, F, mean), V0, invvar, oracle.tv_tett(V0, invvar, C, D))
+    sup = mean[None, :] + Y @ V0
+    Fhc = Fh - np.repeat(Nh, D, axis=1) * sup[spk_of]
+    Xs = oracle.tv_ivectors(Nh, Fhc, U0, invvar, oracle.tv_tett(U0, invvar, C, D))
+    Fp = F - np.repeat(N, D, axis=1) * sup
+    UX = np.repeat(Nh, D, axis=1) * (Xs @ U0)
+    for hh in range(n_sess):
+        Fp[spk_of[hh]] -= UX[hh]
+    Dm = np.sqrt(1.0 / (invvar * reg))
+    Nr = np.repeat(N, D, axis=1)
+    for it in range(3):
+        L = 1.0 + Nr * invvar * Dm ** 2
+        Z = Fp * invvar * Dm / L
+        Dm = (Z * Fp).sum(0) / ((1.0 / L + Z * Z) * Nr).sum(0)
+    got = lf.read_db(d / "edD.mat")
+    assert got.shape == (1, C * D) and np.abs(got[0] - Dm).max() < 1e-3 * np.abs(Dm).max()
+
+
 def test_ivextractor_approximate_modes_cli(world, oracle):
     """IvExtractor --mode ubmWeight / eigenDecomposition (IvExtractor.cpp:151-363), both computing the
     approximation parameters on the fly and loading the ones TotalVariability wrote with
