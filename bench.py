@@ -156,9 +156,10 @@ def bind_to_gpu_numa(index):
     return info
 
 
-def ivector_rate(torch, capi, dev, U=1024, R=400, reps=3):
+def ivector_rate(torch, capi, dev, U=1250, R=400, reps=3):
     """The metric's second half: i-vectors/s of the classic extraction (estimateW: L = I + N TETt,
-    Cholesky, solve) at 2048c/60d, rank 400, on statistics resident in HBM.  Synthetic statistics:
+    Cholesky, solve) at 2048c/60d, rank 400, on statistics resident in HBM; U = configs[2]'s per-GPU share
+    (10 k utterances / 8).  Synthetic statistics:
     64 active components per utterance, 3000 frames, F = N mu + noise."""
     from lia_ral_b200 import synth
     w, mean, cov = synth.make_ubm(C, D, seed=1)

@@ -1030,12 +1030,19 @@ lr_tv *lr_tv_create(int C, int D, int R, size_t U, const double *ubm_mean,
   tv->U = U;
   tv->sv = (size_t)C * D;
   size_t rr = (size_t)R * R;
-  // utterances per posterior batch: 2 GB for the largest of the per-utterance buffers (L / E / Y
-  // hold R x R doubles, invD ceil(R / 64) 64 x 64 blocks -- the larger one at small R), capped at
-  // 4096 so that small ranks with many utterances do not over-allocate
+  // utterances per posterior batch: at most 2.6 GB for the largest of the per-utterance buffers (L / E / Y
+  // hold R x R doubles, invD ceil(R / 64) 64 x 64 blocks -- the larger one at small R), capped at 4096 so that
+  // small ranks with many utterances do not over-allocate.  A batch is a whole number of Cholesky waves when
+  // one fits (k_chol_fused: one CTA per matrix, 3 per SM), else whole 128-row tiles / K chunks of the digit
+  // GEMM: the Cholesky is the largest single share of the i-vector solve and a 1.4-wave batch leaves a
+  // quarter of it idle.
   const size_t per_utt = std::max(rr, (size_t)((R + kNB - 1) / kNB) * kNB * kNB) * sizeof(double);
-  tv->batch = (int)std::min<size_t>(std::min<size_t>(U, 4096), std::max<size_t>(32, ((size_t)1 << 31) / per_utt));
-  if (tv->batch > 128) tv->batch -= tv->batch % 128;  // whole 128-row tiles / K chunks of the digit GEMM
+  size_t fit = std::min<size_t>(4096, std::max<size_t>(32, (size_t)2600000000ull / per_utt));
+  const size_t wave = 3 * (size_t)std::max(1, engine().sm_count);
+  if (U <= fit) fit = U;  // everything in one batch
+  else if (fit >= wave) fit -= fit % wave;
+  else if (fit > 128) fit -= fit % 128;
+  tv->batch = (int)fit;
   const int nbmax = tv->batch;
   auto A = [&](double **p, size_t n) { return cudaMalloc(p, n * sizeof(double)) == cudaSuccess; };
   bool ok = A(&tv->d_N, U * C) && A(&tv->d_F, U * tv->sv) && A(&tv->d_T, R * tv->sv) &&
