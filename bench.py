@@ -462,6 +462,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=0,
                     help="0 auto, 1 fp32 SIMT, 2 tcgen05 (one-pass statistics), 3 tcgen05 two-pass")
+    ap.add_argument("--products", type=int, default=-1,
+                    help="fp16 products of the one-pass kernel: -1 = library default (0), 0 = five, 1 = four, "
+                         "2 = three; 1 and 2 are opt-in, outside the parity bounds of tests/ (lr_set_gmm_products)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-ivectors", action="store_true", help="skip the i-vectors/s side measurement")
@@ -493,6 +496,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     capi.init(local)
     capi.set_gmm_kernel(args.kernel)
+    if args.products >= 0:
+        capi.set_gmm_products(args.products)
+    products = capi.get_gmm_products()
     lr_stream = torch.cuda.ExternalStream(capi.stream_handle(), device=dev)
 
     (w, mean, cov), start = synth_model()
@@ -607,10 +613,36 @@ def main():
         strong = {"value": Ts * world / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms, "frames_total": Ts * world,
                   "n_gpus": world, "scaling": "strong",
                   "workload": "the same EM iteration with configs[1]'s 10 M frames in total, frames / N per GPU"}
+    # ---- the opt-in product levels of the one-pass kernel (lr_set_gmm_products), same step, rank 0's clock
+    levels = None
+    if not args.no_extra and feats is not None and args.kernel != 1 and products == 0:
+        levels = {"note": "opt-in, NOT the headline: level 1 (statistics GEMM on the hi frame panels only) fails the "
+                          "small-occupation parity tests, level 2 (likelihood GEMM without W_hi X_lo too) the 1e-4 "
+                          "i-vector contract (tests/test_gmm_gpu.py::test_full_size_oracle_parity, DESIGN 4.6)"}
+        for lv in (1, 2):
+            capi.set_gmm_products(lv)
+            for _ in range(3):
+                step()
+            sync_all()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(lr_stream):
+                p0.record()
+            for _ in range(5):
+                step()
+            with torch.cuda.stream(lr_stream):
+                p1.record()
+            sync_all()
+            pms = _max_over_ranks(torch, dist, world, dev, p0.elapsed_time(p1) / 5.0)
+            levels[str(lv)] = {"value": world * T / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms,
+                               "path_frac": FLOP_PER_FRAME_EM * T / (pms * 1e-3) / 1e12 / peaks()["bf16"],
+                               "ceiling": {1: 0.46875, 2: 0.625}[lv]}
+        capi.set_gmm_products(0)
     # ---- side measurements (each rank on its own shard): i-vectors/s, the sharded IvExtractor pipeline,
     # TotalVariability EM
     iv = None
     extra = {}
+    if levels is not None:
+        extra["product_levels"] = levels
     del X, feats
     torch.cuda.empty_cache()
     if not args.no_ivectors:
@@ -647,7 +679,11 @@ def main():
         # what the tensor pipe executes per frame: fp16 hi/lo split = 3 products of the K = 128 likelihood
         # contraction (once in the one-pass kernel, twice in the two-pass design) + the statistics GEMM over
         # the hi and the lo frame panels (2 x 128 columns)
-        issued = 2 * C * ((768 if two_pass else 384) + 256)
+        # one-pass kernel: likelihood 3 products (2 at product level 2) x K = 128, statistics 2 (1 at level >= 1) x 128 columns
+        g1_k = 768 if two_pass else (256 if products >= 2 else 384)
+        g2_k = 256 if (two_pass or products == 0) else 128
+        issued = 2 * C * (g1_k + g2_k)
+        ceiling = FLOP_PER_FRAME_EM / issued
         kname = {1: "fp32 SIMT accumulate pass"}.get(
             args.kernel, "k_tc_acc (two-pass statistics kernel: likelihood recompute + g x / g x^2 accumulation)"
             if two_pass else "k_tc_one<EM> (one-pass: likelihood GEMM + log-sum-exp exchange + statistics GEMM)")
@@ -663,8 +699,10 @@ def main():
                                         "first warm-up step and reused by every later EM iteration over the same "
                                         "resident frames (lr_feats handle), as a 5-iteration TrainWorld run would",
                        "kernel": {0: "auto", 1: "simt-fp32", 2: "tcgen05", 3: "tcgen05-two-pass"}[args.kernel],
-                       "arithmetic": "fp16 hi/lo split operands (22 significand bits, 3 UMMA products), fp32 TMEM "
-                                     "accumulation, fp64 statistics" if args.kernel != 1 else "fp32 FMA, fp64 statistics",
+                       "arithmetic": ("fp16 hi/lo split operands (22 significand bits) in the likelihood GEMM, "
+                                      f"{g1_k // 128 + g2_k // 128} fp16 UMMA products per tile (lr_set_gmm_products "
+                                      f"level {products}), fp32 TMEM accumulation, fp64 statistics")
+                                     if args.kernel != 1 else "fp32 FMA, fp64 statistics",
                        "mean_llk_per_frame": llk_per_frame},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -690,12 +728,19 @@ def main():
                          # the contract's precision (1e-4 on statistics / i-vectors) needs 3 fp16 products per
                          # likelihood term, so the tensor pipe issues >= 2 C (384 + 256) flop per frame for the
                          # 8 C D algorithmic ones: frac cannot exceed 0.375 in one pass (0.234 in two)
-                         "ceiling": 0.375 if not two_pass else 0.234,
-                         "ceiling_reason": "fp16 hi/lo split: 3 UMMA products of the K=128 likelihood contraction + "
-                                           "the statistics GEMM over hi and lo frame panels = 2 C (384 + 256) issued "
-                                           "flop/frame for 8 C D algorithmic; BASELINE's 0.70 target is above this "
-                                           "ceiling for any tensor-core formulation at the contract's precision",
-                         "frac_of_ceiling": path_tf / pk["bf16"] / (0.375 if not two_pass else 0.234),
+                         "ceiling": ceiling,
+                         "ceiling_reason": "fp16 hi/lo split: the K=128 likelihood contraction is issued as "
+                                           f"{g1_k // 128} fp16 UMMA products (W_hi X_hi, W_lo X_hi"
+                                           + (", W_hi X_lo" if g1_k >= 384 else "") + ") and the statistics GEMM over "
+                                           + ("the hi and lo frame panels" if g2_k == 256 else "the hi frame panels (one fp16 "
+                                              "posterior x one fp16 frame value)")
+                                           + f" = 2 C ({g1_k} + {g2_k}) issued flop/frame for 8 C D algorithmic; "
+                                           "BASELINE's 0.70 target is above this ceiling for any tensor-core "
+                                           "formulation inside the parity bounds (opt-in levels measured in "
+                                           "`product_levels`: four products fail the small-occupation tests, three "
+                                           "the 1e-4 i-vector contract: DESIGN 4.6)",
+                         "frac_of_ceiling": path_tf / pk["bf16"] / ceiling,
+                         "products_level": products,
                          "issued_flop_per_frame": issued,
                          "issued_tflops": issued * T * args.steps / max((lse_ms + acc_ms) * 1e-3, 1e-9) / 1e12,
                          "gmm_kernels_ms_per_step": gmm_ms},

@@ -63,6 +63,18 @@ lr_status lr_profile_read(int kind, double *total_ms, uint64_t *n_launches);
  * statistics kernels of round 1 (kept as the cross-check of the one-pass kernel). */
 lr_status lr_set_gmm_kernel(int which);
 int lr_get_gmm_kernel(void);
+/* fp16 products the one-pass tcgen05 kernel issues per frame tile.  The frame operand is carried as
+ * hi + lo fp16 panels, the model operand as hi + lo, the posteriors as ONE fp16 value:
+ *   0: (default) likelihood  W_hi X_hi + W_hi X_lo + W_lo X_hi, statistics  P X_hi + P X_lo   (5 products)
+ *   1: statistics on X_hi only (4 products): a zero-mean 2^-12 relative rounding per frame term.  Inside
+ *      the contract wherever a component sees >= 100 frames; a component fed by a handful of frames with
+ *      one-hot posteriors shows it directly (first-order statistics to 1e-4, variances to 2e-3)
+ *   2: likelihood without W_hi X_lo as well (3 products): per-frame log-likelihoods to ~3e-5 relative,
+ *      i-vectors of 20 000-frame utterances to 1.1e-4 -- outside the 1e-4 contract
+ * Levels 1 and 2 are opt-in (+8 % / +19 % frames/s at 2048c/60d).
+ * Measured errors and speeds per level: DESIGN.md 4.6 (scripts/products_probe.py). */
+lr_status lr_set_gmm_products(int level);
+int lr_get_gmm_products(void);
 
 /* ------------------------------------------------------------------ GMM (MixtureGD) ------
  * Replaces MixtureGD + DistribGD::computeAll (alize-core; constants probed on

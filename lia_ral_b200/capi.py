@@ -147,6 +147,15 @@ def get_gmm_kernel():
     return int(lib().lr_get_gmm_kernel())
 
 
+def set_gmm_products(level):
+    """0 = five fp16 products per tile (default), 1 = four, 2 = three (see include/lia_ral_b200.h)."""
+    _check(lib().lr_set_gmm_products(int(level)))
+
+
+def get_gmm_products():
+    return int(lib().lr_get_gmm_products())
+
+
 def set_tv_gemm(which=0, planes=0):
     """Contraction kernel of the TV rows: 0 = INT8 digit GEMM (default), 1 = cuBLAS fp64 cross-check;
     planes = digit planes per operand (3..7, 0 = keep).  Effective at the next estimate_tett()."""

@@ -28,6 +28,8 @@ struct Engine {
   int gmm_kernel = 0;  // 0 auto, 1 simt, 2 tcgen05 (one-pass statistics), 3 tcgen05 two-pass
   int tc_debug = 0;    // profiling experiments only (LR_TC_DEBUG builds): results are WRONG when set
   int tv_gemm = 0;     // TV contractions: 0 = INT8 digit GEMM (gemm_i8.cu), 1 = cuBLAS fp64 (cross-check)
+  int gmm_products = 0;  // one-pass kernel: 0 = all five fp16 products (default), 1 = statistics GEMM on the hi frame panels only,
+                         // 2 = likelihood GEMM too (lr_set_gmm_products)
   int tv_planes = 6;   // digit planes per operand of the INT8 digit GEMM
   // per-device "cudaFuncSetAttribute done" flags (reset by lr_shutdown: the attribute is per context)
   enum { kAttrTc = 0, kAttrSimtLse, kAttrSimtAcc, kAttrTopk, kAttrTvDiag, kAttrTvGemm, kAttrPlda, kAttrGemmI8, kAttrCount };

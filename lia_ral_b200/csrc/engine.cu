@@ -271,6 +271,12 @@ lr_status lr_set_gmm_kernel(int which) {
   return LR_OK;
 }
 int lr_get_gmm_kernel(void) { return engine().gmm_kernel; }
+lr_status lr_set_gmm_products(int level) {
+  LR_REQUIRE(level >= 0 && level <= 2, "product level must be 0 (five fp16 products), 1 (four) or 2 (three)");
+  engine().gmm_products = level;
+  return LR_OK;
+}
+int lr_get_gmm_products(void) { return engine().gmm_products; }
 #ifdef LR_DEBUG_BUILD
 // profiling experiments (results are WRONG while set): only in `make DEBUG=1` builds, not part of the product ABI
 void lr_debug_flags(int flags) { engine().tc_debug = flags; }

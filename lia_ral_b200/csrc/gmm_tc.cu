@@ -1038,10 +1038,11 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
         if (h == 4) mbar_wait(sm.w_tmem(), 0);  // stages 4, 5 held the weights until they were in TMEM
         mbar_wait(sm.empty(st), ((h / kOStages) & 1) ^ 1);
         if (leader) {
-          mbar_expect_tx(sm.full(st), kHalfBytes);
+          const int np = (dbg & 512) ? 2 : 4;  // product level 2 never reads the lo panels
+          mbar_expect_tx(sm.full(st), np * kHalfPanel);
           const unsigned char *src =
               Xh + (size_t)(t_begin + (h >> 1)) * kTileBytes + (size_t)(h & 1) * kHalfPanel;
-          for (int p = 0; p < 4; p++)
+          for (int p = 0; p < np; p++)
             bulk_g2s(sm.stage0 + st * kHalfBytes + p * kHalfPanel, src + (size_t)p * kPanelBytes,
                      kHalfPanel, sm.full(st));
         }
@@ -1068,6 +1069,7 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
           uint32_t acc = 0;
 #pragma unroll
           for (int q = 0; q < 6; q++) {
+            if ((q == 2 || q == 3) && (dbg & 512)) continue;  // product level 2: no W_hi X_lo
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
               umma_ts(d_tmem, tmem_base + kOColW + wp[q] * 32 + kk * 8,
@@ -1133,6 +1135,7 @@ k_tc_one(int C, int D, int n_slices, const unsigned char *__restrict__ Wp,
           const uint64_t bd0 = desc_add(b_desc0, st * kHalfBytes);
 #pragma unroll
           for (int part = 0; part < 2; part++) {
+            if (part == 1 && (dbg & 256)) break;  // product level >= 1: hi frame panels only
 #pragma unroll
             for (int kk = 0; kk < kHF / 16; kk++) {
               umma_ts(tmem_f, tmem_base + kOColP + ps * 32 + kk * 8,
@@ -1803,7 +1806,8 @@ lr_status tc_run_stats(lr_gmm *g, const FrameList &fl, const std::vector<LrChunk
       rc = tc_launch_coop(kern, n_slices * groups, g->C, g->D, n_slices, (const unsigned char *)st->d_W,
                           (const unsigned char *)Xh1, (const int *)d_cuts1, (const TileInfo *)d_tinfo1,
                           d_xch, (float *)nullptr, fl.d_index, fl.P, d_llk_sum, (const double *)g->d_g,
-                          (const double *)g->d_s, fw, out_N, out_F, out_S2, e.tc_debug | kEnvDbg, d_prof);
+                          (const double *)g->d_s, fw, out_N, out_F, out_S2,
+                          e.tc_debug | kEnvDbg | (e.gmm_products >= 1 ? 256 : 0) | (e.gmm_products >= 2 ? 512 : 0), d_prof);
     }
     if (rc == LR_OK && kProf) {
       long long hp[96];

@@ -508,7 +508,7 @@ def test_traintarget_validate_gmm_on_gpu(capi, golden_dir):
 _FULL_REF = {}
 
 
-@pytest.mark.parametrize("kname", ["tc", "tc2p"])
+@pytest.mark.parametrize("kname", ["tc", "tc2p", "tc_p1", "tc_p2"])
 def test_full_size_oracle_parity(capi, oracle, kname):
     """BASELINE's own shape (2048c / 60d) against the fp64 oracle on 200 k frames in 10 utterances of 20 000
     frames (the oracle runs threaded: seconds).  The model is deliberately BLURRED (means shrunk towards the
@@ -518,8 +518,17 @@ def test_full_size_oracle_parity(capi, oracle, kname):
       * per (utterance, component) RELATIVE checks wherever the occupation is >= 1: 1e-4 for occ >= 100 and
         the 3-sigma bound of the fp16 posterior rounding, 1.2e-3 / sqrt(occ), below that;
       * the contract itself: i-vectors (rank 40) computed from the GPU statistics vs from the oracle's agree
-        to 1e-4 of the largest coefficient."""
-    capi.set_gmm_kernel(KERNELS[kname])
+        to 1e-4 of the largest coefficient.
+    "tc" runs the library default (lr_set_gmm_products level 0: five fp16 products per tile); the opt-in
+    "tc_p1" (four products) meets the SAME bounds at these occupations -- the small cases of this file, where a
+    component sees a handful of frames, are where it fails, which is why it is not the default; "tc_p2" (three
+    products) is held to 3x the bounds: it sits at 1.1e-4 on the i-vectors, outside the contract
+    (measured: scripts/products_probe.py)."""
+    level = {"tc_p1": 1, "tc_p2": 2}.get(kname)
+    slack = 3.0 if level == 2 else 1.0
+    capi.set_gmm_kernel(KERNELS[kname.split("_")[0]])
+    if level is not None:
+        capi.set_gmm_products(level)
     try:
         C, D, U, per = 2048, 60, 10, 20000
         w, mean, cov = synth.make_ubm(C, D, seed=1)
@@ -533,17 +542,18 @@ def test_full_size_oracle_parity(capi, oracle, kname):
         N, F = g.bwstats(X, [(u * per, per, u) for u in range(U)], U)
     finally:
         capi.set_gmm_kernel(0)
+        capi.set_gmm_products(0)
     assert np.abs(N.sum(1) - per).max() < 1e-4 * per
     rel = np.abs(N - N_ref) / np.maximum(N_ref, 1e-300)
     big = N_ref >= 100.0
     mid = (N_ref >= 1.0) & ~big
     assert big.sum() > 50 and mid.sum() > 10000
-    assert rel[big].max() < 1e-4, rel[big].max()
-    assert (rel[mid] * np.sqrt(N_ref[mid])).max() < 1.2e-3, (rel[mid] * np.sqrt(N_ref[mid])).max()
+    assert rel[big].max() < 1e-4 * slack, rel[big].max()
+    assert (rel[mid] * np.sqrt(N_ref[mid])).max() < 1.2e-3 * slack, (rel[mid] * np.sqrt(N_ref[mid])).max()
     F3, F3r = F.reshape(U, C, D), F_ref.reshape(U, C, D)
     relF = np.linalg.norm(F3 - F3r, axis=2) / np.maximum(np.linalg.norm(F3r, axis=2), 1e-300)
-    assert relF[big].max() < 1e-4, relF[big].max()
-    assert (relF[mid] * np.sqrt(N_ref[mid])).max() < 1.2e-3
+    assert relF[big].max() < 1e-4 * slack, relF[big].max()
+    assert (relF[mid] * np.sqrt(N_ref[mid])).max() < 1.2e-3 * slack
     # i-vectors from both sets of statistics
     R = 40
     invvar = (1.0 / c2).reshape(-1)
@@ -551,4 +561,4 @@ def test_full_size_oracle_parity(capi, oracle, kname):
     tett = oracle.tv_tett(Tm, invvar, C, D, threads=os.cpu_count() or 1)
     W_ref = oracle.tv_ivectors(N_ref, oracle.tv_subtract_m(N_ref, F_ref, m2.reshape(-1)), Tm, invvar, tett)
     W_gpu = oracle.tv_ivectors(N, oracle.tv_subtract_m(N, F, m2.reshape(-1)), Tm, invvar, tett)
-    assert np.abs(W_gpu - W_ref).max() < 1e-4 * np.abs(W_ref).max(), np.abs(W_gpu - W_ref).max() / np.abs(W_ref).max()
+    assert np.abs(W_gpu - W_ref).max() < 1e-4 * slack * np.abs(W_ref).max(), np.abs(W_gpu - W_ref).max() / np.abs(W_ref).max()
