@@ -116,6 +116,7 @@ class FeatureServer {
   size_t getFirstFeatureIndexOfASource(const std::string &name) const;
   size_t getFeatureCountOfASource(const std::string &name) const;
   const float *data() const { return X_.data(); }
+  float *mutableData() { return X_.data(); }  // writeFeature: JFA feature compensation works in place
   size_t ld() const { return (size_t)D_; }
 
  private:
@@ -251,6 +252,8 @@ class TVAcc {
   void reloadStats();      // resend the host copy of N / F_X (TotalVariability.cpp:149-153)
   Matrix getUbmMeans();
   Matrix getW();
+  const Matrix &getN() const { return N_; }    // host copies of the raw statistics
+  const Matrix &getF_X() const { return F_; }
   size_t nSpeakers() const { return lines_.size(); }
   int rank() const { return R_; }
 
@@ -332,6 +335,9 @@ void writeIvTestScores(const Config &c, const Matrix &scores, const std::vector<
 // ---- drivers: int Foo(Config&) like the reference programs
 int TrainWorld(Config &c);        // LIA_SpkDet/TrainWorld/src/TrainWorld.cpp:101
 int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:90
+int ComputeTestDotProduct(Config &c);  // :228-370 (JFA: channel-compensated statistics . client supervector)
+int ComputeTestJFA(Config &c);         // :376-572 (JFA: U x removed from the frames, then the top-K LLR)
+int ComputeTestDispatch(Config &c);    // ComputeTestMain.cpp:137-165 (channelCompensation / scoring)
 int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:70 (mode classic)
 int ComputeJFAStats(Config &c);  // ComputeJFAStats.cpp:71-87 (per-session + per-speaker BW statistics)
 int EigenVoice(Config &c);       // EigenVoice.cpp:71-165 (V trained by the TVAcc device path on speaker statistics)

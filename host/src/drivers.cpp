@@ -575,6 +575,174 @@ int EstimateDMatrix(Config &c) {
   return 0;
 }
 
+// ------------------------------------------------------------------ ComputeTest, JFA channel compensation
+namespace {
+// What ComputeTestDotProduct (:228-370) and ComputeTestJFA (:376-572) do per NDX line before scoring, batched over
+// the lines: Baum-Welch statistics of the test segment under the world model (computeAndAccumulateJFAStat),
+// x = L^-1 U' Sigma^-1 (F - N o M) with L = I + sum_k N_k U_k' Sigma_k^-1 U_k (estimateUEUT, estimateAndInverseL_EC,
+// substractMplusVYplusDZ with y = z = 0 for a test segment, estimateX :3264-3295) -- the i-vector solve with U in
+// the place of T, one batched device pass for every test segment -- and the supervector offsets U x.
+struct JfaTestSide {
+  std::vector<std::vector<std::string>> lines;  // NDX lines: test segment + client ids
+  MixtureGD world;
+  Matrix N, F;  // raw statistics per line
+  Matrix UX;    // [lines x sv] (zero without an eigenchannel matrix: x = 0)
+};
+void jfaTestSide(Config &c, JfaTestSide &j) {
+  if (Shard::get().world != 1) LIA_THROW("ComputeTest with channelCompensation JFA: one process only");
+  XList ndx(c.getParam("ndxFilename"));
+  j.lines = ndx.lines();
+  if (j.lines.empty()) LIA_THROW("ComputeTest: empty NDX list");
+  j.world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+  const size_t sv = (size_t)j.world.C * j.world.D;
+  std::vector<std::vector<std::string>> tests;
+  for (auto &l : j.lines) tests.push_back({l[0]});
+  Config ct = c;
+  long rank = 1;
+  Matrix U;
+  const bool haveU = c.existsParam("eigenChannelMatrix");
+  if (haveU) {
+    U.load(c.getString("matrixFilesPath", "") + c.getParam("eigenChannelMatrix") + c.getString("loadMatrixFilesExtension", ""),
+           c.getString("loadMatrixFormat", "DB"));
+    if (U.cols < U.rows) {  // loadEC transposes a matrix stored the other way round
+      Matrix t(U.cols, U.rows);
+      for (size_t i = 0; i < U.rows; i++)
+        for (size_t k = 0; k < U.cols; k++) t(k, i) = U(i, k);
+      U = t;
+    }
+    if (U.cols != sv) LIA_THROW("Incorrect dimension of the eigenchannel matrix");
+    rank = (long)U.rows;
+  }
+  ct.setParam("totalVariabilityNumber", std::to_string(rank));
+  TVAcc tv(tests, ct);
+  tv.computeAndAccumulateTVStat(ct);
+  j.N = tv.getN();
+  j.F = tv.getF_X();
+  j.UX = Matrix(j.lines.size(), sv);
+  if (haveU) {
+    tv.loadT(c.getParam("eigenChannelMatrix"), ct);
+    tv.substractM();
+    tv.estimateTETt();
+    tv.estimateW();
+    Matrix Ut(U.cols, U.rows);
+    for (size_t i = 0; i < U.rows; i++)
+      for (size_t k = 0; k < U.cols; k++) Ut(k, i) = U(i, k);
+    Matrix X = tv.getW();
+    LIA_CHECK(lr_gemm_digits(X.rows, sv, U.rows, X.data.data(), Ut.data.data(), j.UX.data.data(), 1.0, 0.0, 0));
+  }
+}
+}  // namespace
+
+int ComputeTestDotProduct(Config &c) {
+  try {
+    const std::string gender = c.getParam("gender");
+    const double threshold = c.getDouble("decisionThreshold", 0.0);
+    JfaTestSide j;
+    jfaTestSide(c, j);
+    const int D = j.world.D;
+    const size_t C = (size_t)j.world.C, sv = C * D;
+    std::ofstream outNist(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
+    std::vector<double> fx(sv);
+    for (size_t li = 0; li < j.lines.size(); li++) {
+      // substractMplusUX (:4336-4362) on the raw statistics, then / sum N (:323-331)
+      double sumN = 0.0;
+      for (size_t k = 0; k < C; k++) sumN += j.N(li, k);
+      for (size_t k = 0; k < C; k++)
+        for (int i = 0; i < D; i++) {
+          const size_t e = k * D + i;
+          fx[e] = (j.F(li, e) - j.N(li, k) * (j.world.mean[e] + j.UX(li, e))) / sumN;
+        }
+      for (size_t i = 1; i < j.lines[li].size(); i++) {
+        Matrix sup;
+        sup.load(c.getParam("loadVectorFilesPath") + "/" + j.lines[li][i] + c.getParam("vectorFilesExtension"),
+                 c.getString("loadMatrixFormat", "DB"));
+        if (sup.data.size() < sv) LIA_THROW("client supervector " + j.lines[li][i] + " is shorter than the model");
+        double score = 0.0;
+        for (size_t e = 0; e < sv; e++) score += sup.data[e] * fx[e];
+        outputResultLine(score, j.lines[li][i], j.lines[li][0], gender, setDecision(score, threshold), outNist);
+      }
+    }
+    outNist.close();
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+int ComputeTestJFA(Config &c) {
+  try {
+    const std::string gender = c.getParam("gender");
+    const std::string label = c.getParam("labelSelectedFrames");
+    const double threshold = c.getDouble("decisionThreshold", 0.0);
+    const int K = (int)c.getLong("topDistribsCount", 10);
+    const bool complete = c.getString("computeLLKWithTopDistribs", "COMPLETE") == "COMPLETE";
+    const double minLLK = c.getDouble("minLLK", -200.0), maxLLK = c.getDouble("maxLLK", 200.0);
+    const long worldDecime = c.getLong("worldDecime", 1);
+    if (worldDecime < 1) LIA_THROW("worldDecime must be >= 1");
+    JfaTestSide j;
+    jfaTestSide(c, j);
+    const size_t sv = (size_t)j.world.C * j.world.D;
+    Gmm world(j.world, true);
+    std::map<std::string, std::unique_ptr<Gmm>> cache;
+    std::ofstream outNist(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
+    for (size_t li = 0; li < j.lines.size(); li++) {
+      const auto &line = j.lines[li];
+      FeatureServer fs(c, {line[0]});
+      SegCluster segs = selectedSegments(c, fs, label);
+      if (segs.empty()) {
+        std::cout << "ATTENTION, TEST FILE [" << line[0] << "] is empty" << std::endl;
+        continue;
+      }
+      std::vector<lr_seg> es = toEngineSegs(fs, segs);
+      // substractUXfromFeatures (:4689-4698): posteriors under M + U x (getSpeakerModel :4605-4620 with y = z = 0)
+      MixtureGD session = j.world;
+      for (size_t e = 0; e < sv; e++) session.mean[e] += j.UX(li, e);
+      {
+        Gmm sessionModel(session, true);
+        LIA_CHECK(lr_jfa_normalize_features(sessionModel.h(), &j.UX.data[li * sv], fs.mutableData(), fs.getFeatureCount(),
+                                            fs.ld(), es.data(), es.size()));
+      }
+      std::vector<lr_gmm *> clients;
+      for (size_t i = 1; i < line.size(); i++) {
+        auto it = cache.find(line[i]);
+        if (it == cache.end())
+          it = cache.emplace(line[i], std::unique_ptr<Gmm>(new Gmm(MixtureGD::loadFromConfig(line[i], c), true))).first;
+        clients.push_back(it->second->h());
+      }
+      std::vector<double> mw(1), mc(clients.size());
+      LIA_CHECK(lr_compute_test_decime(world.h(), clients.data(), (int)clients.size(), fs.data(), fs.getFeatureCount(),
+                                       fs.ld(), es.data(), es.size(), K, complete ? 1 : 0, minLLK, maxLLK, 0,
+                                       (int)worldDecime, mw.data(), mc.data()));
+      for (size_t i = 0; i < clients.size(); i++) {
+        const double llr = mc[i] - mw[0];
+        outputResultLine(llr, line[i + 1], line[0], gender, setDecision(llr, threshold), outNist);
+      }
+    }
+    outNist.close();
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// ComputeTestMain.cpp:137-165
+int ComputeTestDispatch(Config &c) {
+  if (c.existsParam("byLabelModel") || c.existsParam("histoMode")) {
+    std::cout << "(ComputeTest) byLabelModel / histoMode are not implemented by this engine" << std::endl;
+    return 1;
+  }
+  if (c.existsParam("channelCompensation")) {
+    const std::string cc = c.getParam("channelCompensation");
+    if (cc == "JFA") return c.getString("scoring", "DotProduct") == "FrameByFrame" ? ComputeTestJFA(c) : ComputeTestDotProduct(c);
+    if (cc == "LFA" || cc == "NAP") {
+      std::cout << "(ComputeTest) channelCompensation " << cc << " is not implemented by this engine" << std::endl;
+      return 1;
+    }
+    std::cout << "(ComputeTest) No Channel Compensation" << std::endl;
+  }
+  return ComputeTest(c);
+}
+
 // ------------------------------------------------------------------ IvExtractor (approximate modes)
 namespace {
 // shared head / tail of IvExtractorUbmWeigth and IvExtractorEigenDecomposition

@@ -159,6 +159,14 @@ lr_status lr_gmm_bwstats_dev(lr_gmm *g, const lr_feats *f, const lr_seg *segs, s
 lr_status lr_jfa_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const lr_seg *segs, size_t n_segs,
                          size_t n_sessions, const int32_t *speaker_of_session, size_t n_speakers, double *N_h,
                          double *F_h, double *N, double *F);
+/* JFAAcc::normalizeFeatures (AccumulateJFAStat.cpp:4623-4680; called by substractUXfromFeatures :4689-4698 from
+ * ComputeTestJFA, ComputeTest.cpp:455): every frame of the segments, IN PLACE in the host buffer X,
+ *   x_t -= sum_k P(k | x_t) ux[k*D + i],   P under session_model (means M + U x, the world's weights / variances).
+ * ux[C*D] = U x of the session.  Segments are visited in order; a frame covered by several segments is
+ * compensated once per occurrence from its current value, like the reference's read-modify-write loop.
+ * The reference's topGauss branch throws ("no topgauss yet"), so there is none here. */
+lr_status lr_jfa_normalize_features(lr_gmm *session_model, const double *ux, float *X, size_t T, size_t ldx,
+                                    const lr_seg *segs, size_t n_segs);
 
 /* ---- a7: MixtureGDStat::computeAndAccumulateLLK (call sites ComputeTest.cpp:162-167,
  * TopGauss.cpp:166-192, AccumulateStat.cpp:77).

@@ -298,6 +298,16 @@ class GMM:
                                     spk.ctypes.data_as(c_ip), ct.c_size_t(n_speakers), _d(N_h), _d(F_h), _d(N), _d(F)))
         return N_h, F_h, N, F
 
+    def jfa_normalize_features(self, ux, X, segs):
+        """JFAAcc::normalizeFeatures with self as the session model: returns the compensated copy of X."""
+        X = np.array(_f32(X), copy=True, order="C")
+        ux = np.ascontiguousarray(ux, dtype=np.float64).reshape(-1)
+        assert ux.size == self.C * self.D
+        sa, ns = _segs(segs)
+        _check(lib().lr_jfa_normalize_features(self.h, _d(ux), X.ctypes.data_as(c_fp), ct.c_size_t(X.shape[0]),
+                                               ct.c_size_t(X.strides[0] // 4), sa, ct.c_size_t(ns)))
+        return X
+
     def bwstats_dev(self, feats, segs, U, d_N_ptr, d_F_ptr):
         sa, ns = _segs(segs)
         _check(lib().lr_gmm_bwstats_dev(self.h, feats.h, sa, ct.c_size_t(ns), ct.c_size_t(U),

@@ -429,6 +429,126 @@ lr_status lr_jfa_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const 
   return LR_OK;
 }
 
+// -------------------------------------------------------------------------- JFA feature compensation
+// JFAAcc::normalizeFeatures (AccumulateJFAStat.cpp:4623-4680): every selected frame loses the posterior-
+// weighted channel offset,  x_t -= sum_k P(k | x_t) (U x)_k,  the posteriors taken under the session model
+// (means M + U x, the world's weights and variances).  The frames x components scores come from the same
+// likelihood pass that feeds the top-K path (tcgen05 for a tensor-core-served model); this kernel is the
+// contraction of the [P x C] posteriors with the [C x D] offset: one warp per frame, the lanes over the
+// components (so each exp2 is evaluated once), 64 fp32 accumulators per lane, the offset streamed through
+// shared memory in chunks of 128 components.
+constexpr int kJfaChunk = 128, kJfaStride = 65, kJfaWarps = 8;
+constexpr long kJfaBlock = 1L << 15;  // frames per likelihood pass (S is P x Cp floats)
+
+__global__ void __launch_bounds__(kJfaWarps * 32)
+k_jfa_compensate(int C, int Cp, int D, const float *__restrict__ S, const float *__restrict__ lse2,
+                 const float *__restrict__ ux /*[Cp][64], zero padded*/, const unsigned *__restrict__ index,
+                 long P, float *__restrict__ X, size_t ldx) {
+  __shared__ float su[kJfaChunk * kJfaStride];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long p = (long)blockIdx.x * kJfaWarps + warp;
+  const bool live = p < P;
+  const float l2 = live ? lse2[p] : 0.f;
+  const float *Sp = S + (size_t)(live ? p : 0) * Cp;
+  float acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; d++) acc[d] = 0.f;
+  for (int c0 = 0; c0 < C; c0 += kJfaChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kJfaChunk * 64; i += kJfaWarps * 32) {
+      const int c = i >> 6, d = i & 63;
+      su[c * kJfaStride + d] = (c0 + c < C) ? ux[(size_t)(c0 + c) * 64 + d] : 0.f;
+    }
+    __syncthreads();
+    if (!live) continue;
+#pragma unroll
+    for (int j = 0; j < kJfaChunk / 32; j++) {
+      const int c = c0 + 32 * j + lane;
+      const float g = c < C ? exp2f(Sp[c] - l2) : 0.f;
+      const float *u = su + (32 * j + lane) * kJfaStride;
+#pragma unroll
+      for (int d = 0; d < 64; d++) acc[d] = fmaf(g, u[d], acc[d]);
+    }
+  }
+  if (!live) return;
+#pragma unroll
+  for (int d = 0; d < 64; d++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(0xFFFFFFFFu, acc[d], o);
+  }
+  const size_t fr = index ? index[p] : (size_t)p;
+  float *x = X + fr * ldx;
+#pragma unroll
+  for (int d = 0; d < 64; d++)
+    if ((d & 31) == lane && d < D) x[d] -= acc[d];
+}
+
+lr_status lr_jfa_normalize_features(lr_gmm *session_model, const double *ux, float *X, size_t T, size_t ldx,
+                                    const lr_seg *segs, size_t n_segs) {
+  LR_READY();
+  LR_REQUIRE(session_model && ux && X && segs, "lr_jfa_normalize_features: null argument");
+  lr_gmm *g = session_model;
+  LR_REQUIRE(ldx >= (size_t)g->D && T < (1ull << 32) && g->D <= 64, "lr_jfa_normalize_features: bad T / ldx / D");
+  lr_status st = check_segs(segs, n_segs, T, 1, false);
+  if (st != LR_OK) return st;
+  long lo, hi;
+  seg_range(segs, n_segs, T, lo, hi);
+  if (hi <= lo) return LR_OK;
+  Engine &e = engine();
+  // the frames are visited segment by segment like the reference's loop: a frame covered by several
+  // segments is compensated once per occurrence, each time from its CURRENT value.  Layer r holds the
+  // r-th occurrence of every frame; within a layer the frames are distinct (in-place update, no race)
+  std::vector<std::vector<unsigned>> layers;
+  {
+    std::vector<unsigned char> seen((size_t)(hi - lo), 0);
+    for (size_t s = 0; s < n_segs; s++)
+      for (long t = segs[s].begin; t < segs[s].begin + segs[s].length; t++) {
+        const unsigned r = seen[(size_t)(t - lo)]++;
+        LR_REQUIRE(r < 255, "lr_jfa_normalize_features: frame %ld is covered by more than 255 segments", t);
+        if (layers.size() <= r) layers.emplace_back();
+        layers[r].push_back((unsigned)(t - lo));
+      }
+  }
+  const int C = g->C, Cp = g->Cp, D = g->D;
+  DevBuf<float> dX, dU;
+  DevBuf<unsigned> dIdx;
+  LR_CUDA(dX.alloc((size_t)(hi - lo) * ldx));
+  LR_CUDA(dU.alloc((size_t)Cp * 64));
+  {
+    std::vector<float> uf((size_t)Cp * 64, 0.f);
+    for (int c = 0; c < C; c++)
+      for (int d = 0; d < D; d++) uf[(size_t)c * 64 + d] = (float)ux[(size_t)c * D + d];
+    LR_CUDA(cudaMemcpyAsync(dU.p, uf.data(), uf.size() * sizeof(float), cudaMemcpyHostToDevice, e.stream));
+    LR_CUDA(cudaMemcpyAsync(dX.p, X + (size_t)lo * ldx, (size_t)(hi - lo) * ldx * sizeof(float),
+                            cudaMemcpyHostToDevice, e.stream));
+    LR_CUDA(cudaStreamSynchronize(e.stream));  // uf leaves scope
+  }
+  lr_status sel = LR_OK;
+  const bool tc = tc_selected(g, &sel);
+  if (sel != LR_OK) return sel;
+  for (const auto &layer : layers) {
+    LR_CUDA(dIdx.alloc(layer.size()));
+    LR_CUDA(cudaMemcpyAsync(dIdx.p, layer.data(), layer.size() * sizeof(unsigned), cudaMemcpyHostToDevice, e.stream));
+    for (long b0 = 0; b0 < (long)layer.size(); b0 += kJfaBlock) {
+      const long P = std::min<long>(kJfaBlock, (long)layer.size() - b0);
+      float *d_lse = (float *)scratch_get(kSlotLse, (P + 128) * sizeof(float));
+      float *d_S = (float *)scratch_get(kSlotS, (size_t)P * Cp * sizeof(float));
+      if (!d_lse || !d_S) return LR_ERR_CUDA;
+      FrameList fl{dX.p, ldx, dIdx.p + b0, P};
+      st = tc ? tc_pass_lse(g, fl, d_lse, nullptr, d_S) : gmm_pass_lse(g, fl, d_lse, d_S, nullptr);
+      if (st != LR_OK) return st;
+      k_jfa_compensate<<<(unsigned)((P + kJfaWarps - 1) / kJfaWarps), kJfaWarps * 32, 0, e.stream>>>(
+          C, Cp, D, d_S, d_lse, dU.p, dIdx.p + b0, P, dX.p, ldx);
+      LR_CHECK_LAUNCH();
+    }
+    LR_CUDA(cudaStreamSynchronize(e.stream));  // layer.data() / dIdx are reused
+  }
+  LR_CUDA(cudaMemcpyAsync(X + (size_t)lo * ldx, dX.p, (size_t)(hi - lo) * ldx * sizeof(float),
+                          cudaMemcpyDeviceToHost, e.stream));
+  LR_CUDA(cudaStreamSynchronize(e.stream));
+  return LR_OK;
+}
+
 // -------------------------------------------------------------------------- LLK / top-K
 lr_status lr_gmm_llk(lr_gmm *g, const float *X, size_t T, size_t ldx, double min_llk,
                      double max_llk, double *llk) {

@@ -100,6 +100,17 @@ class Oracle:
                              ct.c_size_t(U), _d(N), _d(F), threads)
         return N, F
 
+    def jfa_normalize_features(self, g, ux, X, segs):
+        """JFAAcc::normalizeFeatures under the session model g; segs = [(begin, length), ...]; returns a copy."""
+        X = np.array(_f32(X), copy=True, order="C")
+        ux = np.ascontiguousarray(ux, dtype=np.float64).reshape(-1)
+        b = np.ascontiguousarray([s[0] for s in segs], dtype=np.int64)
+        n = np.ascontiguousarray([s[1] for s in segs], dtype=np.int64)
+        self.lib.orc_jfa_normalize_features(*g.args(), _d(ux), X.ctypes.data_as(c_fp), ct.c_size_t(X.strides[0] // 4),
+                                            b.ctypes.data_as(ct.POINTER(ct.c_int64)),
+                                            n.ctypes.data_as(ct.POINTER(ct.c_int64)), ct.c_size_t(len(segs)))
+        return X
+
     def em_accumulate(self, g, X, weight=1.0, occ=None, m1=None, m2=None, threads=1):
         X = _f32(X)
         T = X.shape[0]

@@ -149,6 +149,28 @@ void orc_bwstats(int C, int D, const double *w, const double *mean, const double
   parallel_ranges(U, threads, bw_range, &a);
 }
 
+/* JFAAcc::normalizeFeatures (AccumulateJFAStat.cpp:4623-4680): for every frame of every selected segment, in
+ * order, Prob[k] = w_k lk_k(f) / sum under the session model, then ff[i] -= Prob[k] ux[k*D + i] (k outer, i inner)
+ * and the frame is written back -- here into the float32 buffer the engine's FeatureServer keeps. */
+void orc_jfa_normalize_features(int C, int D, const double *w, const double *mean, const double *covinv,
+                                const double *cst, const double *ux, float *X, size_t ldx,
+                                const int64_t *seg_begin, const int64_t *seg_len, size_t n_segs) {
+  double *p = (double *)malloc(sizeof(double) * C);
+  double xd[1024];
+  for (size_t s = 0; s < n_segs; s++)
+    for (int64_t t = seg_begin[s]; t < seg_begin[s] + seg_len[s]; t++) {
+      float *x = X + (size_t)t * ldx;
+      for (int i = 0; i < D; i++) xd[i] = (double)x[i];
+      double sum = frame_lk_d(C, D, w, mean, covinv, cst, xd, p);
+      for (int k = 0; k < C; k++) {
+        double g = p[k] / sum;
+        for (int i = 0; i < D; i++) xd[i] -= g * ux[(size_t)k * D + i];
+      }
+      for (int i = 0; i < D; i++) x[i] = (float)xd[i];
+    }
+  free(p);
+}
+
 /* ------------------------------------------------------------------ A.5 */
 typedef struct {
   int C, D;

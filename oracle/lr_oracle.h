@@ -60,6 +60,12 @@ void orc_bwstats(int C, int D, const double *w, const double *mean, const double
                  const double *cst, const float *X, size_t T, size_t ldx,
                  const int32_t *frame2row, size_t U, double *N, double *F, int threads);
 
+/* JFAAcc::normalizeFeatures (AccumulateJFAStat.cpp:4623-4680): x_t -= sum_k P(k | x_t) ux[k*D + i] for the
+ * frames of the segments, in order, in place, posteriors under the session model (w, mean, covinv, cst). */
+void orc_jfa_normalize_features(int C, int D, const double *w, const double *mean, const double *covinv,
+                                const double *cst, const double *ux, float *X, size_t ldx,
+                                const int64_t *seg_begin, const int64_t *seg_len, size_t n_segs);
+
 /* ---- A.5 EM accumulate (MixtureGDStat::computeAndAccumulateEM [ALIZE], driver
  * AccumulateStat.cpp:103-128, threaded :170-299).  Accumulates into occ[C],
  * m1[C*D], m2[C*D]; returns sum_t log(sum_c p_c) and adds T*weight to *nframes. */

@@ -370,6 +370,74 @@ def test_estimate_d_matrix_cli(world, oracle):
     assert got.shape == (1, C * D) and np.abs(got[0] - Dm).max() < 1e-3 * np.abs(Dm).max()
 
 
+def test_compute_test_jfa_cli(world, oracle):
+    """ComputeTest --channelCompensation JFA (ComputeTest.cpp:228-370 DotProduct, :376-572 FrameByFrame): channel
+    factor x of every test segment with U (y = z = 0), then either the compensated, occupation-normalised first-order
+    statistics against the client supervector, or U x removed from the frames (posteriors under M + U x) followed by
+    the ordinary top-K LLR against the world."""
+    d, C, D, Ru = world["dir"], world["C"], world["D"], 3
+    invvar = (1.0 / world["cov"]).reshape(-1)
+    mean = world["mean"].reshape(-1)
+    U = synth.make_T(Ru, C, D, invvar, seed=491, scale=1.0) * np.sqrt(world["cov"]).reshape(-1) * 0.4
+    lf.write_db(d / "jtU.mat", U)
+    rng = np.random.default_rng(492)
+    # test segments WITH a channel offset: frames drawn around M + U x_true (no label file: every frame selected)
+    utts = {}
+    for i in range(3):
+        x_true = rng.standard_normal(Ru)
+        utts[f"jfa{i}"] = synth.make_frames(world["w"], world["mean"] + (x_true @ U).reshape(C, D), world["cov"] * 1.5,
+                                            400 + 50 * i, seed=480 + i)
+        lf.write_spro4(d / f"jfa{i}.prm", utts[f"jfa{i}"])
+    clients, sups = {}, {}
+    for k in range(2):
+        p_ = synth.perturb_ubm(world["w"], world["mean"], world["cov"], seed=493 + k, frac=0.4, scale=0.5)
+        clients[f"jspk{k}"] = p_
+        lf.write_raw_gmm(d / f"jspk{k}.gmm", *p_)
+        sups[f"jspk{k}"] = rng.standard_normal(C * D)
+        lf.write_db(d / f"jspk{k}.sv", sups[f"jspk{k}"][None, :])
+    ndx = [["jfa0", "jspk0", "jspk1"], ["jfa1", "jspk1"], ["jfa2", "jspk0"]]
+    lf.write_lines(d / "jt.ndx", ndx)
+    lf.write_cfg(d / "jt.cfg", **world["common"], ndxFilename=str(d / "jt.ndx"), inputWorldFilename="wld",
+                 outputFilename=str(d / "jt_dot.res"), gender="M", topDistribsCount=5, computeLLKWithTopDistribs="COMPLETE",
+                 channelCompensation="JFA", eigenChannelMatrix="jtU", eigenChannelNumber=Ru,
+                 loadVectorFilesPath=str(d), vectorFilesExtension=".sv")
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    tett = oracle.tv_tett(U, invvar, C, D)
+    ref_dot, ref_llr = [], []
+    for line in ndx:
+        X = np.ascontiguousarray(utts[line[0]], dtype=np.float32)
+        n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+        x = oracle.tv_ivectors(n1, oracle.tv_subtract_m(n1, f1, mean), U, invvar, tett)
+        ux = (x @ U)[0]
+        fx = (f1[0] - np.repeat(n1[0], D) * (mean + ux)) / n1[0].sum()
+        Xc = oracle.jfa_normalize_features(oracle.gmm(world["w"], world["mean"] + ux.reshape(C, D), world["cov"]), ux, X,
+                                           [(0, len(X))])
+        assert np.abs(Xc - X).max() > 0.1 * np.sqrt(world["cov"]).mean()    # the compensation moves the frames
+        llk_w, idx, _, rest, _ = oracle.llk_determine_top(ow, Xc, 5, True)
+        for cl in line[1:]:
+            ref_dot.append((cl, line[0], float(sups[cl] @ fx)))
+            llk_c = oracle.llk_use_top(oracle.gmm(*clients[cl]), Xc, idx, rest, True)
+            ref_llr.append((cl, line[0], float(llk_c.mean() - llk_w.mean())))
+    _run("ComputeTest", d / "jt.cfg")                       # scoring defaults to DotProduct
+    got = [l.split() for l in open(d / "jt_dot.res")]
+    assert [(l[1], l[3]) for l in got] == [(r[0], r[1]) for r in ref_dot]
+    scale = max(abs(r[2]) for r in ref_dot)
+    for l, r in zip(got, ref_dot):
+        assert l[0] == "M" and abs(float(l[4]) - r[2]) < 1e-4 * scale, (l, r)
+    _run("ComputeTest", d / "jt.cfg", scoring="FrameByFrame", outputFilename=str(d / "jt_fbf.res"))
+    got = [l.split() for l in open(d / "jt_fbf.res")]
+    assert [(l[1], l[3]) for l in got] == [(r[0], r[1]) for r in ref_llr]
+    for l, r in zip(got, ref_llr):
+        assert abs(float(l[4]) - r[2]) < 2e-4 and int(l[2]) == int(r[2] > 0), (l, r)
+    # without an eigenchannel matrix x = 0: FrameByFrame is the plain ComputeTest
+    lf.write_cfg(d / "jt0.cfg", **world["common"], ndxFilename=str(d / "jt.ndx"), inputWorldFilename="wld",
+                 outputFilename=str(d / "jt0.res"), gender="M", topDistribsCount=5, computeLLKWithTopDistribs="COMPLETE",
+                 channelCompensation="JFA", scoring="FrameByFrame")
+    _run("ComputeTest", d / "jt0.cfg")
+    _run("ComputeTest", d / "jt0.cfg", channelCompensation="none", outputFilename=str(d / "jt0_plain.res"))
+    assert open(d / "jt0.res").read() == open(d / "jt0_plain.res").read()
+
+
 def test_ivextractor_approximate_modes_cli(world, oracle):
     """IvExtractor --mode ubmWeight / eigenDecomposition (IvExtractor.cpp:151-363), both computing the
     approximation parameters on the fly and loading the ones TotalVariability wrote with

@@ -488,6 +488,36 @@ def test_jfa_bwstats(capi, oracle, kern):
         capi.set_gmm_kernel(0)
 
 
+@pytest.mark.parametrize("shape,kern", [((256, 20, 5000), 1), ((256, 20, 5000), 0), ((2048, 60, 3000), 0)],
+                         ids=["256c-simt", "256c-auto", "2048c-auto"])
+def test_jfa_normalize_features(capi, oracle, shape, kern):
+    """JFAAcc::normalizeFeatures (AccumulateJFAStat.cpp:4623-4680): x_t -= sum_k P(k | x_t) (U x)_k under the session
+    model M + U x, for the selected frames only, in segment order.  One frame range is covered by two segments
+    (compensated twice, the second time from the already compensated value), one segment is empty, and the frames
+    outside every segment must come back bit-identical."""
+    C, D, T = shape
+    w, mean, cov = synth.make_ubm(C, D, seed=81)
+    cov = cov * 3.0                      # soft posteriors: the offset is a real mixture over components
+    X = synth.make_frames(w, mean, cov, T, seed=82)
+    rng = np.random.default_rng(83)
+    ux = 0.3 * np.sqrt(cov) * rng.standard_normal((C, D))
+    capi.set_gmm_kernel(kern)
+    try:
+        g, o = capi.GMM(w, mean + ux, cov), oracle.gmm(w, mean + ux, cov)
+        segs = [(100, 900), (1500, 0), (800, 600), (2000, T - 2300)]      # [800, 1000) twice
+        Y = g.jfa_normalize_features(ux, X, [(b, n, 0) for b, n in segs])
+        Y_ref = oracle.jfa_normalize_features(o, ux, X, segs)
+    finally:
+        capi.set_gmm_kernel(0)
+    touched = np.zeros(T, bool)
+    for b, n in segs:
+        touched[b:b + n] = True
+    assert np.array_equal(Y[~touched], X[~touched])
+    moved = np.abs(Y_ref - X)[touched].max()
+    assert moved > 0.05 * np.sqrt(cov).mean()                   # the compensation is not a no-op
+    assert np.abs(Y - Y_ref).max() <= 1e-4 * moved + 4e-7 * np.abs(X).max(), np.abs(Y - Y_ref).max() / moved
+
+
 def test_traintarget_validate_gmm_on_gpu(capi, golden_dir):
     """The reference's TrainTarget fixture (indicative pin, see tests/test_oracle_golden.py) through the CUDA
     EM-statistics path: occupancies -> MAPOccDep means vs the reference's adapted model."""

@@ -30,6 +30,26 @@ def test_bwstats_matches_numpy(oracle, small):
     assert np.array_equal(N, N3) and np.array_equal(F, F3)
 
 
+def test_jfa_normalize_features_matches_numpy(oracle, small):
+    """orc_jfa_normalize_features vs a log-domain numpy restatement of JFAAcc::normalizeFeatures
+    (AccumulateJFAStat.cpp:4623-4680), with a frame range covered twice."""
+    w, mean, cov, X = small
+    cov = cov * 3.0
+    ux = 0.3 * np.sqrt(cov) * np.random.default_rng(5).standard_normal(mean.shape)
+    segs = [(10, 300), (250, 100), (600, 0)]
+    Y = oracle.jfa_normalize_features(oracle.gmm(w, mean + ux, cov), ux, X, segs)
+    Z = np.array(X, dtype=np.float32)
+    for b, n in segs:
+        for t in range(b, b + n):
+            x = Z[t].astype(np.float64)
+            ll = np.log(w) - 0.5 * np.log(2 * np.pi * cov).sum(1) - 0.5 * ((x - mean - ux) ** 2 / cov).sum(1)
+            p = np.exp(ll - ll.max())
+            Z[t] = (x - (p / p.sum()) @ ux).astype(np.float32)
+    assert np.abs(Y - Z).max() <= 2e-7 * np.abs(X).max()
+    assert np.array_equal(Y[350:], np.asarray(X, dtype=np.float32)[350:])
+    assert np.abs(Y - X)[10:350].max() > 0.1
+
+
 def test_em_matches_numpy_and_is_monotone(oracle, small):
     w, mean, cov, X = small
     w0, m0, c0 = synth.perturb_ubm(w, mean, cov, seed=13, frac=1.0, scale=0.5)
