@@ -226,6 +226,7 @@ class TVAcc {
   void computeAndAccumulateTVStat(const Config &c);  // :268
   void loadT(const std::string &name, const Config &c);  // :632 (transposes when rows > cols)
   void initT(const Config &c);                            // :701 (Box-Muller on libc rand())
+  void setT(const Matrix &T);                             // [rank x C*D] held by the caller (JFA: V, U or [V; U])
   void saveT(const std::string &name, const Config &c);
   void loadN(const Config &c);
   void loadF_X(const Config &c);
@@ -335,6 +336,8 @@ void writeIvTestScores(const Config &c, const Matrix &scores, const std::vector<
 // ---- drivers: int Foo(Config&) like the reference programs
 int TrainWorld(Config &c);        // LIA_SpkDet/TrainWorld/src/TrainWorld.cpp:101
 int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:90
+int TrainTargetJFA(Config &c);       // TrainTarget.cpp:393-617 (joint [y; x] with [V; U], z with D, supervector + model)
+int TrainTargetDispatch(Config &c);  // TrainTargetMain.cpp:160-171 (channelCompensation)
 int ComputeTestDotProduct(Config &c);  // :228-370 (JFA: channel-compensated statistics . client supervector)
 int ComputeTestJFA(Config &c);         // :376-572 (JFA: U x removed from the frames, then the top-K LLR)
 int ComputeTestDispatch(Config &c);    // ComputeTestMain.cpp:137-165 (channelCompensation / scoring)

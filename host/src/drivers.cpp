@@ -575,6 +575,136 @@ int EstimateDMatrix(Config &c) {
   return 0;
 }
 
+// ------------------------------------------------------------------ TrainTarget, JFA
+namespace {
+// eigenvoice / eigenchannel matrix of the JFA programs: rank x sv, a single zero row when the key is absent
+// (TrainTarget.cpp:437-462, ComputeTest.cpp:259-282)
+Matrix jfaSubspace(const Config &c, const char *key, size_t sv) {
+  Matrix M(1, sv);
+  if (!c.existsParam(key)) return M;
+  M.load(c.getString("matrixFilesPath", "") + c.getParam(key) + c.getString("loadMatrixFilesExtension", ""),
+         c.getString("loadMatrixFormat", "DB"));
+  if (M.cols < M.rows) {
+    Matrix t(M.cols, M.rows);
+    for (size_t i = 0; i < M.rows; i++)
+      for (size_t k = 0; k < M.cols; k++) t(k, i) = M(i, k);
+    M = t;
+  }
+  if (M.cols != sv) LIA_THROW(std::string("Incorrect dimension of the matrix given by ") + key);
+  return M;
+}
+}  // namespace
+
+// TrainTarget.cpp:393-617.  Per client (id + files, all files pooled into ONE set of speaker statistics): the joint
+// factors [y; x] with the stacked matrix [V; U] (initVU :1227, estimateVUEVUT :1584-1608, estimateAndInverseL_VU
+// :2300-2330, substractMplusDZ with z = 0, estimateYX :3518-3547) -- the i-vector solve with [V; U] in the place of T,
+// batched over ALL clients of the list in one device pass -- then on the raw statistics minus N o (M + [V; U]'[y; x])
+// (substractMplusVUYX :4364-4386) the diagonal factor z = F' Sigma^-1 D / (1 + N Sigma^-1 D^2) (estimateZ :3550-3572).
+// Outputs: the client model M + V y + D z (saveMixture), the supervector Sigma^-1 (V y + D z) (saveSuperVector),
+// optionally x / y / z.
+int TrainTargetJFA(Config &c) {
+  try {
+    if (Shard::get().world != 1) LIA_THROW("TrainTarget with channelCompensation JFA: one process only");
+    if (c.getBool("useIdForSelectedFrame", false)) LIA_THROW("useIdForSelectedFrame is not implemented by this engine");
+    XList ids(c.getParam("targetIdList"));
+    const auto lines = ids.lines();
+    if (lines.empty()) LIA_THROW("TrainTarget: empty targetIdList");
+    MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
+    const int D = world.D;
+    const size_t C = (size_t)world.C, sv = C * D;
+    const Matrix V = jfaSubspace(c, "eigenVoiceMatrix", sv), U = jfaSubspace(c, "eigenChannelMatrix", sv);
+    std::vector<double> Dm(sv, 0.0);
+    if (c.existsParam("DMatrix")) {
+      Matrix d;
+      d.load(c.getString("matrixFilesPath", "") + c.getParam("DMatrix") + c.getString("loadMatrixFilesExtension", ""),
+             c.getString("loadMatrixFormat", "DB"));
+      if (d.rows != 1 || d.cols != sv) LIA_THROW("Incorrect dimension of D Matrix");
+      Dm = d.data;
+    }
+    const size_t Rv = V.rows, Ru = U.rows, R = Rv + Ru;
+    Matrix VU(R, sv);
+    std::copy(V.data.begin(), V.data.end(), VU.data.begin());
+    std::copy(U.data.begin(), U.data.end(), VU.data.begin() + Rv * sv);
+    std::vector<std::vector<std::string>> files;
+    for (auto &l : lines) {
+      if (l.size() < 2) LIA_THROW("TrainTarget: client [" + l[0] + "] has no feature file");
+      files.emplace_back(l.begin() + 1, l.end());
+    }
+    Config ct = c;
+    ct.setParam("totalVariabilityNumber", std::to_string(R));
+    TVAcc tv(files, ct);
+    tv.computeAndAccumulateTVStat(ct);
+    const Matrix N = tv.getN(), F = tv.getF_X();
+    tv.setT(VU);
+    tv.substractM();
+    tv.estimateTETt();
+    tv.estimateW();
+    const Matrix YX = tv.getW();  // [clients x (Rv + Ru)]
+    Matrix Y(lines.size(), Rv), X(lines.size(), Ru);
+    for (size_t s = 0; s < lines.size(); s++) {
+      for (size_t i = 0; i < Rv; i++) Y(s, i) = YX(s, i);
+      for (size_t i = 0; i < Ru; i++) X(s, i) = YX(s, Rv + i);
+    }
+    const Matrix VUYX = supervectors(YX, VU), VY = supervectors(Y, V);
+    const bool saveMixture = c.getBool("saveMixture", true), saveSuperVector = c.getBool("saveSuperVector", true);
+    const bool saveEmpty = c.getBool("saveEmptyModel", false);
+    const std::string sfmt = c.getString("saveMatrixFormat", "DB");
+    auto saveRow = [&](const std::string &file, const double *v, size_t n) {
+      Matrix m(1, n);
+      std::copy(v, v + n, m.data.begin());
+      m.save(file, sfmt);
+    };
+    std::vector<double> z(sv), sup(sv);
+    for (size_t s = 0; s < lines.size(); s++) {
+      const std::string &id = lines[s][0];
+      double occ = 0.0;
+      for (size_t k = 0; k < C; k++) occ += N(s, k);
+      if (occ <= 0.0) {
+        std::cout << " WARNING - NO DATA FOR TRAINING [" << id << "]";
+        if (saveEmpty) {
+          std::cout << " World model is returned" << std::endl;
+          world.saveFromConfig(id, c);
+        }
+        continue;
+      }
+      MixtureGD client = world;
+      client.id = id;
+      for (size_t k = 0; k < C; k++)
+        for (int i = 0; i < D; i++) {
+          const size_t e = k * D + i;
+          const double n = N(s, k), iv = world.covinv[e];
+          const double fp = F(s, e) - n * (world.mean[e] + VUYX(s, e));
+          z[e] = fp * iv * Dm[e] / (1.0 + n * iv * Dm[e] * Dm[e]);
+          const double off = VY(s, e) + Dm[e] * z[e];  // getVYplusDZ :1817-1831
+          sup[e] = off * iv;
+          client.mean[e] = world.mean[e] + off;
+        }
+      if (saveMixture) client.saveFromConfig(id, c);
+      if (saveSuperVector) saveRow(c.getParam("saveVectorFilesPath") + id + c.getParam("vectorFilesExtension"), sup.data(), sv);
+      // (the reference builds these three names from a shadowed, empty path variable, :590-603: relative to the cwd)
+      if (c.getBool("saveX", false)) saveRow(id + c.getString("xExtension", ".x"), &X.data[s * Ru], Ru);
+      if (c.getBool("saveY", false)) saveRow(id + c.getString("yExtension", ".y"), &Y.data[s * Rv], Rv);
+      if (c.getBool("saveZ", false)) saveRow(id + c.getString("zExtension", ".z"), z.data(), sv);
+    }
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// TrainTargetMain.cpp:160-171
+int TrainTargetDispatch(Config &c) {
+  if (c.existsParam("channelCompensation")) {
+    const std::string cc = c.getParam("channelCompensation");
+    if (cc == "JFA") return TrainTargetJFA(c);
+    if (cc == "LFA") {
+      std::cout << "(TrainTarget) channelCompensation LFA is not implemented by this engine" << std::endl;
+      return 1;
+    }
+  }
+  return TrainTarget(c);
+}
+
 // ------------------------------------------------------------------ ComputeTest, JFA channel compensation
 namespace {
 // What ComputeTestDotProduct (:228-370) and ComputeTestJFA (:376-572) do per NDX line before scoring, batched over

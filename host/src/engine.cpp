@@ -427,6 +427,11 @@ void TVAcc::loadT(const std::string &name, const Config &c) {
   LIA_CHECK(lr_tv_set_T(tv_, T.data.data()));
 }
 
+void TVAcc::setT(const Matrix &T) {
+  if ((long)T.rows != R_ || T.cols != (size_t)world_.C * world_.D) LIA_THROW("TVAcc::setT: incorrect dimension");
+  LIA_CHECK(lr_tv_set_T(tv_, T.data.data()));
+}
+
 void TVAcc::initT(const Config &c) {
   const size_t sv = (size_t)world_.C * world_.D;
   Matrix T(R_, sv);

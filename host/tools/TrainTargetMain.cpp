@@ -13,7 +13,7 @@ int main(int argc, char **argv) {
       return 0;
     }
     lia::initEngine(config);  // device + (several ranks) the NCCL communicator
-    return lia::TrainTarget(config);
+    return lia::TrainTargetDispatch(config);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }

@@ -760,3 +760,52 @@ def test_train_target_cli(world, oracle):
         assert np.allclose(gw, w, rtol=1e-3, atol=1e-7)
         assert np.abs(gm - m).max() < 1e-4 * np.abs(m).max()
         assert np.allclose(gc, c, rtol=1e-9)
+
+
+def test_train_target_jfa_cli(world, oracle):
+    """TrainTarget --channelCompensation JFA (TrainTarget.cpp:393-617): joint [y; x] with the stacked [V; U] on the
+    pooled statistics of a client's files, z with D on the statistics minus N o (M + V y + U x); outputs the client
+    model M + V y + D z, the supervector Sigma^-1 (V y + D z) and, on request, x / y / z."""
+    d, C, D, Rv, Ru = world["dir"], world["C"], world["D"], 4, 2
+    invvar = (1.0 / world["cov"]).reshape(-1)
+    mean = world["mean"].reshape(-1)
+    sd = np.sqrt(world["cov"]).reshape(-1)
+    V = synth.make_T(Rv, C, D, invvar, seed=591, scale=1.0) * sd * 0.3
+    U = synth.make_T(Ru, C, D, invvar, seed=592, scale=1.0) * sd * 0.3
+    Dm = 0.2 * sd * (1.0 + 0.5 * np.random.default_rng(593).random(C * D))
+    lf.write_db(d / "ttV.mat", V)
+    lf.write_db(d / "ttU.mat", U)
+    lf.write_db(d / "ttD.mat", Dm[None, :])
+    ids = [["jclA", "utt0", "utt2"], ["jclB", "utt3"]]
+    lf.write_lines(d / "ttj.ndx", ids)
+    os.makedirs(d / "jsv", exist_ok=True)
+    lf.write_cfg(d / "ttj.cfg", **world["common"], targetIdList=str(d / "ttj.ndx"), inputWorldFilename="wld",
+                 channelCompensation="JFA", eigenVoiceMatrix="ttV", eigenChannelMatrix="ttU", DMatrix="ttD",
+                 saveVectorFilesPath=str(d / "jsv") + "/", vectorFilesExtension=".sv", saveY="true",
+                 yExtension=".yfac")
+    cwd = os.getcwd()
+    os.chdir(d)                         # x / y / z land relative to the working directory, like the reference's
+    try:
+        _run("TrainTarget", d / "ttj.cfg")
+    finally:
+        os.chdir(cwd)
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    VU = np.concatenate([V, U])
+    tett = oracle.tv_tett(VU, invvar, C, D)
+    for line in ids:
+        X = np.ascontiguousarray(np.concatenate([world["utts"][u][_selected(u, world["utts"][u])] for u in line[1:]]))
+        n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+        yx = oracle.tv_ivectors(n1, oracle.tv_subtract_m(n1, f1, mean), VU, invvar, tett)[0]
+        y = yx[:Rv]
+        nrep = np.repeat(n1[0], D)
+        fp = f1[0] - nrep * (mean + yx @ VU)
+        z = fp * invvar * Dm / (1.0 + nrep * invvar * Dm * Dm)
+        off = y @ V + Dm * z
+        gw, gm, gc = lf.read_raw_gmm(d / f"{line[0]}.gmm")
+        assert np.allclose(gw, world["w"], rtol=1e-12) and np.allclose(gc, world["cov"], rtol=1e-12)
+        assert np.abs(off).max() > 0.02 * sd.mean()
+        assert np.abs(gm.reshape(-1) - (mean + off)).max() < 1e-4 * np.abs(off).max()
+        sv = lf.read_db(d / "jsv" / f"{line[0]}.sv").reshape(-1)
+        assert np.abs(sv - off * invvar).max() < 1e-4 * np.abs(off * invvar).max()
+        got_y = lf.read_db(d / f"{line[0]}.yfac").reshape(-1)
+        assert np.abs(got_y - y).max() < 1e-4 * np.abs(yx).max()
