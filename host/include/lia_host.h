@@ -226,6 +226,8 @@ class TVAcc {
   void computeAndAccumulateTVStat(const Config &c);  // :268
   void loadT(const std::string &name, const Config &c);  // :632 (transposes when rows > cols)
   void initT(const Config &c);                            // :701 (Box-Muller on libc rand())
+  Matrix getT();
+  void setStats(const Matrix &N, const Matrix &F);        // statistics held by the caller (JFA: re-centred per iteration)
   void setT(const Matrix &T);                             // [rank x C*D] held by the caller (JFA: V, U or [V; U])
   void saveT(const std::string &name, const Config &c);
   void loadN(const Config &c);
@@ -345,6 +347,8 @@ int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:
 int ComputeJFAStats(Config &c);  // ComputeJFAStats.cpp:71-87 (per-session + per-speaker BW statistics)
 int EigenVoice(Config &c);       // EigenVoice.cpp:71-165 (V trained by the TVAcc device path on speaker statistics)
 int EigenChannel(Config &c);     // EigenChannel.cpp:71-160, JFA mode (U trained on the session statistics)
+int EigenChannelLFA(Config &c);  // EigenChannel.cpp:178-290 (MAP D, z re-estimated every iteration)
+int EigenChannelDispatch(Config &c);  // EigenChannelMain.cpp:139-143 (eigenChannelMode)
 int EstimateDMatrix(Config &c);  // EstimateDMatrix.cpp:99-210 (y, x on the device path, diagonal D update)
 int IvExtractorUbmWeigth(Config &c);          // IvExtractor.cpp:151 (mode ubmWeight; the reference's spelling)
 int IvExtractorEigenDecomposition(Config &c); // IvExtractor.cpp:254 (mode eigenDecomposition)

@@ -494,6 +494,87 @@ int EigenChannel(Config &c) {
   return 0;
 }
 
+// EigenChannel.cpp:178-290.  The LFA variant keeps a MAP-style diagonal term next to U: D = sqrt(Sigma / tau) (initD
+// :1176-1222) and a speaker offset D z re-estimated at every iteration.  Per iteration, on the restored statistics:
+//   F_X_h -= N_h o (M + V y + D z)            substractMplusVYplusDZ (:4400-4428), z from the previous iteration
+//   x = L^-1 U' Sigma^-1 F_X_h                estimateUEUT, estimateAndInverseL_EC, estimateX (:3264-3295)
+//   F_X  -= sum_{h of spk} N_h o (M + U x_h)  substractMplusUX (:4336-4362), on the SPEAKER statistics
+//   z = tau / (tau + N) D Sigma^-1 F_X        estimateZMAP (:3576-3594), tau = regulationFactor read as an integer
+//   A_k += (L^-1 + x x') N_hk, C += x F_X_h'  estimateU (:3424-3476), then updateUestimate
+// x, A and C are one device E-step (estimateAandC computes the same x internally), the rest is element-wise.
+int EigenChannelLFA(Config &c) {
+  try {
+    JfaState j;
+    jfaPrepare(c, j);
+    const int D = j.world.D;
+    const std::string type = c.getString("initDType", "MAP");
+    if (type != "MAP") LIA_THROW("initDType " + type + " is not implemented by this engine (MAP)");
+    const double reg = c.getDouble("regulationFactor");
+    const double tau = (double)c.getLong("regulationFactor");  // estimateZMAP takes regulationFactor.toLong()
+    std::vector<double> Dm(j.sv);
+    for (size_t e = 0; e < j.sv; e++) Dm[e] = std::sqrt(1.0 / (j.world.covinv[e] * reg));
+    Matrix Z(j.nSpk, j.sv);
+    Config cu = j.cs;
+    cu.setParam("totalVariabilityNumber", c.getParam("eigenChannelNumber"));
+    TVAcc tvU(j.sessionLines, cu);
+    tvU.loadMeanEstimate(std::vector<double>(j.sv, 0.0));  // the statistics arrive centred
+    if (c.getBool("loadInitChannelMatrix", false))
+      tvU.loadT(c.getParam("initEigenChannelMatrix"), cu);
+    else
+      tvU.initT(cu);
+    if (c.getBool("saveInitChannelMatrix", false)) tvU.saveT(c.getParam("initEigenChannelMatrix"), cu);
+    const long nbIt = c.getLong("nbIt");
+    Matrix Fc(j.nSessions, j.sv), Fs(j.nSpk, j.sv);
+    for (long it = 0; it < nbIt; it++) {
+      std::cout << "\t(EigenChannel) --------- start iteration " << it << " --------" << std::endl;
+      for (size_t h = 0; h < j.nSessions; h++) {
+        const size_t sp = (size_t)j.spkOfSession[h];
+        for (size_t k = 0; k < j.C; k++)
+          for (int i = 0; i < D; i++) {
+            const size_t e = k * D + i;
+            Fc(h, e) = j.Fh(h, e) - j.Nh(h, k) * (j.world.mean[e] + j.VY(sp, e) + Dm[e] * Z(sp, e));
+          }
+      }
+      tvU.setStats(j.Nh, Fc);
+      tvU.estimateTETt();
+      tvU.substractM();
+      tvU.estimateAandC();
+      const Matrix UX = supervectors(tvU.getW(), tvU.getT());
+      Fs = j.F;
+      for (size_t h = 0; h < j.nSessions; h++) {
+        const size_t sp = (size_t)j.spkOfSession[h];
+        for (size_t k = 0; k < j.C; k++)
+          for (int i = 0; i < D; i++) {
+            const size_t e = k * D + i;
+            Fs(sp, e) -= j.Nh(h, k) * (j.world.mean[e] + UX(h, e));
+          }
+      }
+      for (size_t sp = 0; sp < j.nSpk; sp++)
+        for (size_t k = 0; k < j.C; k++)
+          for (int i = 0; i < D; i++) {
+            const size_t e = k * D + i;
+            Z(sp, e) = tau / (tau + j.N(sp, k)) * Dm[e] * j.world.covinv[e] * Fs(sp, e);
+          }
+      tvU.updateTestimate();
+      tvU.resetTmpAcc();
+      if (c.getBool("saveAllECMatrices", false)) tvU.saveT(c.getParam("eigenChannelMatrix") + std::to_string(it), cu);
+    }
+    tvU.saveT(c.getParam("eigenChannelMatrix"), cu);
+  } catch (std::exception &e) {
+    std::cout << e.what() << std::endl;
+  }
+  return 0;
+}
+
+// EigenChannelMain.cpp:139-143
+int EigenChannelDispatch(Config &c) {
+  const std::string mode = c.getString("eigenChannelMode", "JFA");
+  if (mode == "JFA") return EigenChannel(c);
+  if (mode == "LFA") return EigenChannelLFA(c);
+  std::cout << "Error : wrong eigenChannelMode parameter, please chose JFA or LFA" << std::endl;
+  return 1;
+}
+
 // ------------------------------------------------------------------ EstimateDMatrix
 // EstimateDMatrix.cpp:99-210.  y with V on the speaker statistics, x with U on the session statistics (both the
 // i-vector solve of the device path), then per iteration on F' = F_X - N o (M + V y) - sum_{h of spk} N_h o (U x_h)

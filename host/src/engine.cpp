@@ -427,6 +427,18 @@ void TVAcc::loadT(const std::string &name, const Config &c) {
   LIA_CHECK(lr_tv_set_T(tv_, T.data.data()));
 }
 
+Matrix TVAcc::getT() {
+  Matrix T(R_, (size_t)world_.C * world_.D);
+  LIA_CHECK(lr_tv_get_T(tv_, T.data.data()));
+  return T;
+}
+void TVAcc::setStats(const Matrix &N, const Matrix &F) {
+  if (N.rows != N_.rows || N.cols != N_.cols || F.rows != F_.rows || F.cols != F_.cols)
+    LIA_THROW("TVAcc::setStats: incorrect dimension");
+  N_ = N;
+  F_ = F;
+  reloadStats();
+}
 void TVAcc::setT(const Matrix &T) {
   if ((long)T.rows != R_ || T.cols != (size_t)world_.C * world_.D) LIA_THROW("TVAcc::setT: incorrect dimension");
   LIA_CHECK(lr_tv_set_T(tv_, T.data.data()));

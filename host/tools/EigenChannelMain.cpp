@@ -9,15 +9,11 @@ int main(int argc, char **argv) {
     lia::Config config;
     config.parseCmdLine(argc, argv);
     if (config.existsParam("help")) {
-      std::cout << "EigenChannel (lia_ral_b200 engine, JFA mode): --config <file> [--param value ...]" << std::endl;
-      return 0;
-    }
-    if (config.existsParam("channelCompensation") && config.getParam("channelCompensation") != "JFA") {
-      std::cout << "EigenChannel: only channelCompensation JFA is implemented by this engine" << std::endl;
+      std::cout << "EigenChannel (lia_ral_b200 engine, eigenChannelMode JFA | LFA): --config <file> [--param value ...]" << std::endl;
       return 0;
     }
     lia::initEngine(config);
-    return lia::EigenChannel(config);
+    return lia::EigenChannelDispatch(config);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
   }

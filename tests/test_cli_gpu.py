@@ -319,6 +319,66 @@ def test_eigenchannel_cli(world, oracle):
     assert np.abs(got - Ur).max() < 1e-3 * np.abs(Ur).max()
 
 
+def test_eigenchannel_lfa_cli(world, oracle):
+    """EigenChannel --eigenChannelMode LFA (EigenChannel.cpp:178-290): D = sqrt(Sigma / tau), and per iteration the
+    session statistics are centred by M + V y + D z (z from the previous iteration), x and the U accumulators come
+    from them, z = tau / (tau + N) D Sigma^-1 (F_X - sum_h N_h o (M + U x_h)) on the speaker statistics."""
+    d, C, D, Rv, Ru, tau = world["dir"], world["C"], world["D"], 4, 3, 14
+    invvar = (1.0 / world["cov"]).reshape(-1)
+    V0 = synth.make_T(Rv, C, D, invvar, seed=391, scale=0.05)
+    U0 = synth.make_T(Ru, C, D, invvar, seed=392, scale=0.05)
+    lf.write_db(d / "lfV.mat", V0)
+    lf.write_db(d / "lfU0.mat", U0)
+    ndx = [["utt0", "utt1"], ["utt2", "utt3"], ["utt4", "utt5"]]
+    lf.write_lines(d / "lf.ndx", ndx)
+    lf.write_cfg(d / "lf.cfg", **world["common"], ndxFilename=str(d / "lf.ndx"), inputWorldFilename="wld",
+                 eigenChannelMode="LFA", eigenVoiceNumber=Rv, eigenVoiceMatrix="lfV", eigenChannelNumber=Ru,
+                 eigenChannelMatrix="lfU_out", loadInitChannelMatrix="true", initEigenChannelMatrix="lfU0",
+                 nullOrderStatSpeaker="N_lf", firstOrderStatSpeaker="FX_lf", nullOrderStatSession="Nh_lf",
+                 firstOrderStatSession="FXh_lf", nbIt=3, regulationFactor=tau)
+    _run("EigenChannel", d / "lf.cfg")
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    mean = world["mean"].reshape(-1)
+    n_sess = sum(len(l) for l in ndx)
+    N, F = np.zeros((len(ndx), C)), np.zeros((len(ndx), C * D))
+    Nh, Fh, spk_of = np.zeros((n_sess, C)), np.zeros((n_sess, C * D)), []
+    h = 0
+    for row, line in enumerate(ndx):
+        for u in line:
+            X = np.ascontiguousarray(world["utts"][u][_selected(u, world["utts"][u])])
+            n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+            Nh[h], Fh[h] = n1[0], f1[0]
+            N[row] += n1[0]
+            F[row] += f1[0]
+            spk_of.append(row)
+            h += 1
+    spk_of = np.array(spk_of)
+    Y = oracle.tv_ivectors(N, oracle.tv_subtract_m(N, F, mean), V0, invvar, oracle.tv_tett(V0, invvar, C, D))
+    VY = Y @ V0
+    Dm = np.sqrt(1.0 / (invvar * tau))
+    Z = np.zeros((len(ndx), C * D))
+    Ur = U0.copy()
+    NhR, NR = np.repeat(Nh, D, axis=1), np.repeat(N, D, axis=1)
+    for it in range(3):
+        Fc = Fh - NhR * (mean[None, :] + VY[spk_of] + Dm[None, :] * Z[spk_of])
+        Xf, A, Cmx, _, _, _ = oracle.tv_estep(Nh, Fc, Ur, invvar, oracle.tv_tett(Ur, invvar, C, D))
+        Fs = F.copy()
+        np.subtract.at(Fs, spk_of, NhR * (mean[None, :] + Xf @ Ur))
+        Z = tau / (tau + NR) * Dm[None, :] * invvar[None, :] * Fs
+        Ur = oracle.tv_mstep(A, Cmx, C, D)
+    assert np.abs(Z).max() > 0                                    # the z feedback is exercised from iteration 1 on
+    got = lf.read_db(d / "lfU_out.mat")
+    assert np.abs(got - Ur).max() < 1e-3 * np.abs(Ur).max()
+    # ... and it matters: the JFA-mode result on the same data is a different matrix
+    lf.write_cfg(d / "lfj.cfg", **world["common"], ndxFilename=str(d / "lf.ndx"), inputWorldFilename="wld",
+                 eigenChannelMode="JFA", eigenVoiceNumber=Rv, eigenVoiceMatrix="lfV", eigenChannelNumber=Ru,
+                 eigenChannelMatrix="lfU_jfa", loadInitChannelMatrix="true", initEigenChannelMatrix="lfU0",
+                 nullOrderStatSpeaker="N_lf", firstOrderStatSpeaker="FX_lf", nullOrderStatSession="Nh_lf",
+                 firstOrderStatSession="FXh_lf", nbIt=3, loadAccs="true")
+    _run("EigenChannel", d / "lfj.cfg")
+    assert np.abs(lf.read_db(d / "lfU_jfa.mat") - Ur).max() > 1e-2 * np.abs(Ur).max()
+
+
 def test_estimate_d_matrix_cli(world, oracle):
     """EstimateDMatrix (EstimateDMatrix.cpp:99-210): y with V, x with U, then the diagonal update estimateZandD
     (AccumulateJFAStat.cpp:3480-3515) on F' = F_X - N o (M + V y) - sum_h N_h o (U x_h); MAP initialisation."""
