@@ -339,9 +339,11 @@ void writeIvTestScores(const Config &c, const Matrix &scores, const std::vector<
 int TrainWorld(Config &c);        // LIA_SpkDet/TrainWorld/src/TrainWorld.cpp:101
 int ComputeTest(Config &c);       // LIA_SpkDet/ComputeTest/src/ComputeTest.cpp:90
 int TrainTargetJFA(Config &c);       // TrainTarget.cpp:393-617 (joint [y; x] with [V; U], z with D, supervector + model)
+int TrainTargetLFA(Config &c);       // TrainTarget.cpp:620-760 (the same with D = sqrt(Sigma / tau) and the MAP z)
 int TrainTargetDispatch(Config &c);  // TrainTargetMain.cpp:160-171 (channelCompensation)
 int ComputeTestDotProduct(Config &c);  // :228-370 (JFA: channel-compensated statistics . client supervector)
 int ComputeTestJFA(Config &c);         // :376-572 (JFA: U x removed from the frames, then the top-K LLR)
+int ComputeTestLFA(Config &c);         // :574-762 (LFA: the same with the MAP offset D z in the session model, optional cms)
 int ComputeTestDispatch(Config &c);    // ComputeTestMain.cpp:137-165 (channelCompensation / scoring)
 int IvExtractor(Config &c);       // LIA_SpkDet/IvExtractor/src/IvExtractor.cpp:70 (mode classic)
 int ComputeJFAStats(Config &c);  // ComputeJFAStats.cpp:71-87 (per-session + per-speaker BW statistics)

@@ -683,9 +683,10 @@ Matrix jfaSubspace(const Config &c, const char *key, size_t sv) {
 // (substractMplusVUYX :4364-4386) the diagonal factor z = F' Sigma^-1 D / (1 + N Sigma^-1 D^2) (estimateZ :3550-3572).
 // Outputs: the client model M + V y + D z (saveMixture), the supervector Sigma^-1 (V y + D z) (saveSuperVector),
 // optionally x / y / z.
-int TrainTargetJFA(Config &c) {
+namespace {
+int trainTargetFactorAnalysis(Config &c, bool lfa) {
   try {
-    if (Shard::get().world != 1) LIA_THROW("TrainTarget with channelCompensation JFA: one process only");
+    if (Shard::get().world != 1) LIA_THROW("TrainTarget with channelCompensation JFA / LFA: one process only");
     if (c.getBool("useIdForSelectedFrame", false)) LIA_THROW("useIdForSelectedFrame is not implemented by this engine");
     XList ids(c.getParam("targetIdList"));
     const auto lines = ids.lines();
@@ -695,7 +696,12 @@ int TrainTargetJFA(Config &c) {
     const size_t C = (size_t)world.C, sv = C * D;
     const Matrix V = jfaSubspace(c, "eigenVoiceMatrix", sv), U = jfaSubspace(c, "eigenChannelMatrix", sv);
     std::vector<double> Dm(sv, 0.0);
-    if (c.existsParam("DMatrix")) {
+    // LFA (TrainTarget.cpp:664-668, 738-739): D = sqrt(Sigma / tau), z by estimateZMAP with tau read as an integer
+    const double tau = lfa ? (double)c.getLong("regulationFactor") : 0.0;
+    if (lfa) {
+      const double reg = c.getDouble("regulationFactor");
+      for (size_t e = 0; e < sv; e++) Dm[e] = std::sqrt(1.0 / (world.covinv[e] * reg));
+    } else if (c.existsParam("DMatrix")) {
       Matrix d;
       d.load(c.getString("matrixFilesPath", "") + c.getParam("DMatrix") + c.getString("loadMatrixFilesExtension", ""),
              c.getString("loadMatrixFormat", "DB"));
@@ -727,7 +733,8 @@ int TrainTargetJFA(Config &c) {
       for (size_t i = 0; i < Ru; i++) X(s, i) = YX(s, Rv + i);
     }
     const Matrix VUYX = supervectors(YX, VU), VY = supervectors(Y, V);
-    const bool saveMixture = c.getBool("saveMixture", true), saveSuperVector = c.getBool("saveSuperVector", true);
+    // (TrainTargetLFA saves the mixture only, :745-748)
+    const bool saveMixture = lfa || c.getBool("saveMixture", true), saveSuperVector = !lfa && c.getBool("saveSuperVector", true);
     const bool saveEmpty = c.getBool("saveEmptyModel", false);
     const std::string sfmt = c.getString("saveMatrixFormat", "DB");
     auto saveRow = [&](const std::string &file, const double *v, size_t n) {
@@ -755,7 +762,8 @@ int TrainTargetJFA(Config &c) {
           const size_t e = k * D + i;
           const double n = N(s, k), iv = world.covinv[e];
           const double fp = F(s, e) - n * (world.mean[e] + VUYX(s, e));
-          z[e] = fp * iv * Dm[e] / (1.0 + n * iv * Dm[e] * Dm[e]);
+          z[e] = lfa ? tau / (tau + n) * Dm[e] * iv * fp                       // estimateZMAP :3576-3594
+                     : fp * iv * Dm[e] / (1.0 + n * iv * Dm[e] * Dm[e]);  // estimateZ :3550-3572
           const double off = VY(s, e) + Dm[e] * z[e];  // getVYplusDZ :1817-1831
           sup[e] = off * iv;
           client.mean[e] = world.mean[e] + off;
@@ -763,9 +771,9 @@ int TrainTargetJFA(Config &c) {
       if (saveMixture) client.saveFromConfig(id, c);
       if (saveSuperVector) saveRow(c.getParam("saveVectorFilesPath") + id + c.getParam("vectorFilesExtension"), sup.data(), sv);
       // (the reference builds these three names from a shadowed, empty path variable, :590-603: relative to the cwd)
-      if (c.getBool("saveX", false)) saveRow(id + c.getString("xExtension", ".x"), &X.data[s * Ru], Ru);
-      if (c.getBool("saveY", false)) saveRow(id + c.getString("yExtension", ".y"), &Y.data[s * Rv], Rv);
-      if (c.getBool("saveZ", false)) saveRow(id + c.getString("zExtension", ".z"), z.data(), sv);
+      if (!lfa && c.getBool("saveX", false)) saveRow(id + c.getString("xExtension", ".x"), &X.data[s * Ru], Ru);
+      if (!lfa && c.getBool("saveY", false)) saveRow(id + c.getString("yExtension", ".y"), &Y.data[s * Rv], Rv);
+      if (!lfa && c.getBool("saveZ", false)) saveRow(id + c.getString("zExtension", ".z"), z.data(), sv);
     }
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;
@@ -773,15 +781,16 @@ int TrainTargetJFA(Config &c) {
   return 0;
 }
 
+}  // namespace
+int TrainTargetJFA(Config &c) { return trainTargetFactorAnalysis(c, false); }
+int TrainTargetLFA(Config &c) { return trainTargetFactorAnalysis(c, true); }
+
 // TrainTargetMain.cpp:160-171
 int TrainTargetDispatch(Config &c) {
   if (c.existsParam("channelCompensation")) {
     const std::string cc = c.getParam("channelCompensation");
     if (cc == "JFA") return TrainTargetJFA(c);
-    if (cc == "LFA") {
-      std::cout << "(TrainTarget) channelCompensation LFA is not implemented by this engine" << std::endl;
-      return 1;
-    }
+    if (cc == "LFA") return TrainTargetLFA(c);
   }
   return TrainTarget(c);
 }
@@ -880,7 +889,8 @@ int ComputeTestDotProduct(Config &c) {
   return 0;
 }
 
-int ComputeTestJFA(Config &c) {
+namespace {
+int computeTestFrameByFrame(Config &c, bool lfa) {
   try {
     const std::string gender = c.getParam("gender");
     const std::string label = c.getParam("labelSelectedFrames");
@@ -892,7 +902,13 @@ int ComputeTestJFA(Config &c) {
     if (worldDecime < 1) LIA_THROW("worldDecime must be >= 1");
     JfaTestSide j;
     jfaTestSide(c, j);
-    const size_t sv = (size_t)j.world.C * j.world.D;
+    const int D = j.world.D;
+    const size_t C = (size_t)j.world.C, sv = C * D;
+    // LFA (ComputeTest.cpp:640-644, 660-667): D = sqrt(Sigma / tau); with x = z = 0 when they are formed, the channel
+    // factor is the same x and z = tau / (tau + N) D Sigma^-1 (F - N o M) (estimateZMAP) joins the session model
+    const double tau = lfa ? (double)c.getLong("regulationFactor") : 0.0;
+    const double reg = lfa ? c.getDouble("regulationFactor") : 1.0;
+    const bool doCms = lfa && c.getBool("cms", false);
     Gmm world(j.world, true);
     std::map<std::string, std::unique_ptr<Gmm>> cache;
     std::ofstream outNist(c.getParam("outputFilename").c_str(), std::ios::out | std::ios::trunc);
@@ -908,10 +924,38 @@ int ComputeTestJFA(Config &c) {
       // substractUXfromFeatures (:4689-4698): posteriors under M + U x (getSpeakerModel :4605-4620 with y = z = 0)
       MixtureGD session = j.world;
       for (size_t e = 0; e < sv; e++) session.mean[e] += j.UX(li, e);
+      if (lfa)
+        for (size_t k = 0; k < C; k++)
+          for (int i = 0; i < D; i++) {
+            const size_t e = k * D + i;
+            const double iv = j.world.covinv[e], dm = std::sqrt(1.0 / (iv * reg));
+            const double z = tau / (tau + j.N(li, k)) * dm * iv * (j.F(li, e) - j.N(li, k) * j.world.mean[e]);
+            session.mean[e] += dm * z;
+          }
       {
         Gmm sessionModel(session, true);
         LIA_CHECK(lr_jfa_normalize_features(sessionModel.h(), &j.UX.data[li * sv], fs.mutableData(), fs.getFeatureCount(),
                                             fs.ld(), es.data(), es.size()));
+      }
+      if (doCms) {  // cms() (GeneralTools.cpp:713-730): zero mean, unit deviation over the selected frames
+        float *Xf = fs.mutableData();
+        const size_t ld = fs.ld();
+        std::vector<double> m(D, 0.0), m2(D, 0.0);
+        double n = 0.0;
+        for (const lr_seg &sg : es)
+          for (int64_t t = sg.begin; t < sg.begin + sg.length; t++, n += 1.0)
+            for (int i = 0; i < D; i++) {
+              const double v = Xf[(size_t)t * ld + i];
+              m[i] += v;
+              m2[i] += v * v;
+            }
+        for (int i = 0; i < D; i++) {
+          m[i] /= n;
+          m2[i] = std::sqrt(m2[i] / n - m[i] * m[i]);
+        }
+        for (const lr_seg &sg : es)
+          for (int64_t t = sg.begin; t < sg.begin + sg.length; t++)
+            for (int i = 0; i < D; i++) Xf[(size_t)t * ld + i] = (float)(((double)Xf[(size_t)t * ld + i] - m[i]) / m2[i]);
       }
       std::vector<lr_gmm *> clients;
       for (size_t i = 1; i < line.size(); i++) {
@@ -936,6 +980,10 @@ int ComputeTestJFA(Config &c) {
   return 0;
 }
 
+}  // namespace
+int ComputeTestJFA(Config &c) { return computeTestFrameByFrame(c, false); }
+int ComputeTestLFA(Config &c) { return computeTestFrameByFrame(c, true); }
+
 // ComputeTestMain.cpp:137-165
 int ComputeTestDispatch(Config &c) {
   if (c.existsParam("byLabelModel") || c.existsParam("histoMode")) {
@@ -945,8 +993,9 @@ int ComputeTestDispatch(Config &c) {
   if (c.existsParam("channelCompensation")) {
     const std::string cc = c.getParam("channelCompensation");
     if (cc == "JFA") return c.getString("scoring", "DotProduct") == "FrameByFrame" ? ComputeTestJFA(c) : ComputeTestDotProduct(c);
-    if (cc == "LFA" || cc == "NAP") {
-      std::cout << "(ComputeTest) channelCompensation " << cc << " is not implemented by this engine" << std::endl;
+    if (cc == "LFA") return ComputeTestLFA(c);
+    if (cc == "NAP") {
+      std::cout << "(ComputeTest) channelCompensation NAP is not implemented by this engine" << std::endl;
       return 1;
     }
     std::cout << "(ComputeTest) No Channel Compensation" << std::endl;

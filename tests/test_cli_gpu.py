@@ -463,7 +463,9 @@ def test_compute_test_jfa_cli(world, oracle):
                  loadVectorFilesPath=str(d), vectorFilesExtension=".sv")
     ow = oracle.gmm(world["w"], world["mean"], world["cov"])
     tett = oracle.tv_tett(U, invvar, C, D)
-    ref_dot, ref_llr = [], []
+    ref_dot, ref_llr, ref_lfa, ref_lfa_cms = [], [], [], []
+    tau = 14
+    Dm = np.sqrt(1.0 / (invvar * tau))
     for line in ndx:
         X = np.ascontiguousarray(utts[line[0]], dtype=np.float32)
         n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
@@ -478,6 +480,19 @@ def test_compute_test_jfa_cli(world, oracle):
             ref_dot.append((cl, line[0], float(sups[cl] @ fx)))
             llk_c = oracle.llk_use_top(oracle.gmm(*clients[cl]), Xc, idx, rest, True)
             ref_llr.append((cl, line[0], float(llk_c.mean() - llk_w.mean())))
+        # LFA (ComputeTest.cpp:574-762): the session model also carries D z, z = tau / (tau + N) D Sigma^-1 (F - N o M)
+        nrep = np.repeat(n1[0], D)
+        z = tau / (tau + nrep) * Dm * invvar * (f1[0] - nrep * mean)
+        Xl = oracle.jfa_normalize_features(
+            oracle.gmm(world["w"], world["mean"] + (ux + Dm * z).reshape(C, D), world["cov"]), ux, X, [(0, len(X))])
+        assert np.abs(Xl - Xc).max() > 1e-3
+        Xs = Xl.astype(np.float64)
+        Xs = ((Xs - Xs.mean(0)) / Xs.std(0)).astype(np.float32)          # cms(): zero mean, unit deviation
+        for Xv, out in ((Xl, ref_lfa), (Xs, ref_lfa_cms)):
+            llk_w, idx, _, rest, _ = oracle.llk_determine_top(ow, Xv, 5, True)
+            for cl in line[1:]:
+                llk_c = oracle.llk_use_top(oracle.gmm(*clients[cl]), Xv, idx, rest, True)
+                out.append((cl, line[0], float(llk_c.mean() - llk_w.mean())))
     _run("ComputeTest", d / "jt.cfg")                       # scoring defaults to DotProduct
     got = [l.split() for l in open(d / "jt_dot.res")]
     assert [(l[1], l[3]) for l in got] == [(r[0], r[1]) for r in ref_dot]
@@ -489,6 +504,13 @@ def test_compute_test_jfa_cli(world, oracle):
     assert [(l[1], l[3]) for l in got] == [(r[0], r[1]) for r in ref_llr]
     for l, r in zip(got, ref_llr):
         assert abs(float(l[4]) - r[2]) < 2e-4 and int(l[2]) == int(r[2] > 0), (l, r)
+    for ref, over in ((ref_lfa, {}), (ref_lfa_cms, dict(cms="true"))):
+        _run("ComputeTest", d / "jt.cfg", channelCompensation="LFA", regulationFactor=tau,
+             outputFilename=str(d / "jt_lfa.res"), **over)
+        got = [l.split() for l in open(d / "jt_lfa.res")]
+        assert [(l[1], l[3]) for l in got] == [(r[0], r[1]) for r in ref]
+        for l, r in zip(got, ref):
+            assert abs(float(l[4]) - r[2]) < 2e-4 * max(1.0, abs(r[2])), (l, r)
     # without an eigenchannel matrix x = 0: FrameByFrame is the plain ComputeTest
     lf.write_cfg(d / "jt0.cfg", **world["common"], ndxFilename=str(d / "jt.ndx"), inputWorldFilename="wld",
                  outputFilename=str(d / "jt0.res"), gender="M", topDistribsCount=5, computeLLKWithTopDistribs="COMPLETE",
@@ -869,3 +891,17 @@ def test_train_target_jfa_cli(world, oracle):
         assert np.abs(sv - off * invvar).max() < 1e-4 * np.abs(off * invvar).max()
         got_y = lf.read_db(d / f"{line[0]}.yfac").reshape(-1)
         assert np.abs(got_y - y).max() < 1e-4 * np.abs(yx).max()
+    # LFA (TrainTarget.cpp:620-760): D = sqrt(Sigma / tau), z = tau / (tau + N) D Sigma^-1 F', the model only
+    tau = 12
+    _run("TrainTarget", d / "ttj.cfg", channelCompensation="LFA", regulationFactor=tau,
+         mixtureFilesPath=str(d) + "/", saveMixtureFileExtension=".lfa.gmm")
+    Dl = np.sqrt(1.0 / (invvar * tau))
+    for line in ids:
+        X = np.ascontiguousarray(np.concatenate([world["utts"][u][_selected(u, world["utts"][u])] for u in line[1:]]))
+        n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+        yx = oracle.tv_ivectors(n1, oracle.tv_subtract_m(n1, f1, mean), VU, invvar, tett)[0]
+        nrep = np.repeat(n1[0], D)
+        z = tau / (tau + nrep) * Dl * invvar * (f1[0] - nrep * (mean + yx @ VU))
+        off = yx[:Rv] @ V + Dl * z
+        _, gm, _ = lf.read_raw_gmm(d / f"{line[0]}.lfa.gmm")
+        assert np.abs(gm.reshape(-1) - (mean + off)).max() < 1e-4 * np.abs(off).max()
