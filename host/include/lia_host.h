@@ -153,8 +153,17 @@ struct TrainCfg {  // TrainTools.cpp:67-93
   double initVarianceFlooring, initVarianceCeiling, finalVarianceFlooring, finalVarianceCeiling;
   long nbTrainIt;
   double baggedFrameProbability;
+  bool normalizeModel = false, normalizeModelMeanOnly = false;  // :76-86
+  long normalizeModelNbIt = 1;
+  bool componentReduction = false;                                // :87-92
+  long targetDistribCount = 0;
   explicit TrainCfg(const Config &c);
 };
+// normalizeMixture (TrainTools.cpp:287-315) towards N(0, 1): every component is expressed relative to the
+// moment-matched single Gaussian of the mixture (mixtureFusion :273-283); meanOnly repeats nbIt times
+void normalizeMixture(MixtureGD &m, long nbIt, bool meanOnly);
+// selectComponent(nbTop) + reduceModel + normalizeWeights (:197-229): the nbTop heaviest components, in index order
+void reduceToTopWeights(MixtureGD &m, size_t nbTop);
 double setItParameter(double begin, double end, int nbIt, int it);  // TrainTools.cpp:560-564
 // bagging of 3..7-frame chunks with libc rand() exactly like GeneralTools.cpp:309-313, 455-500
 SegCluster baggedSegments(const SegCluster &in, double p, long minLen, long maxLen);
@@ -210,6 +219,8 @@ struct MAPCfg {
   double r[3] = {0, 0, 0};
   long nbTrainIt = 1;
   double baggedFrameProbability = 1.0;
+  bool normalizeModel = false, normalizeModelMeanOnly = false;  // TrainTools.cpp:129-139
+  long normalizeModelNbIt = 1;
   explicit MAPCfg(const Config &c);
 };
 // client holds the ML (EM) estimate on entry, the MAP estimate on return (computeMAPOccDep)

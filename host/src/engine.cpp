@@ -32,6 +32,69 @@ TrainCfg::TrainCfg(const Config &c) {
   finalVarianceCeiling = c.getDouble("finalVarianceCeiling");
   nbTrainIt = c.getLong("nbTrainIt");
   baggedFrameProbability = c.getDouble("baggedFrameProbability");
+  normalizeModel = c.getBool("normalizeModel", false);
+  if (normalizeModel) {
+    normalizeModelMeanOnly = c.getBool("normalizeModelMeanOnly", false);
+    if (normalizeModelMeanOnly) normalizeModelNbIt = c.getLong("normalizeModelNbIt");
+  }
+  componentReduction = c.getBool("componentReduction", false);
+  if (componentReduction) targetDistribCount = c.getLong("targetMixtureDistribCount");
+}
+
+void normalizeMixture(MixtureGD &m, long nbIt, bool meanOnly) {
+  const int C = m.C, D = m.D;
+  std::vector<double> gm(D), gc(D);
+  for (long it = 0; it < nbIt; it++) {
+    // mixtureFusion: sequential gaussianFusion (:258-283) -- exact moment matching, accumulated in the same order
+    for (int i = 0; i < D; i++) {
+      gm[i] = m.mean[i];
+      gc[i] = m.cov[i];
+    }
+    double wacc = m.w[0];
+    for (int k = 1; k < C; k++) {
+      const double a1 = m.w[k] / (m.w[k] + wacc), a2 = 1.0 - a1;
+      for (int i = 0; i < D; i++) {
+        const double d = m.mean[(size_t)k * D + i] - gm[i];
+        gc[i] = a1 * m.cov[(size_t)k * D + i] + a2 * gc[i] + a1 * a2 * d * d;
+        gm[i] = a1 * m.mean[(size_t)k * D + i] + a2 * gm[i];
+      }
+      wacc += m.w[k];
+    }
+    for (int k = 0; k < C; k++)
+      for (int i = 0; i < D; i++) {
+        const size_t e = (size_t)k * D + i;
+        m.mean[e] = (m.mean[e] - gm[i]) / std::sqrt(gc[i]);
+        if (!meanOnly) m.cov[e] /= gc[i];
+      }
+  }
+  m.computeAll();
+}
+
+void reduceToTopWeights(MixtureGD &m, size_t nbTop) {
+  const size_t C = (size_t)m.C, D = (size_t)m.D;
+  if (nbTop >= C) return;
+  std::vector<size_t> order(C);
+  for (size_t k = 0; k < C; k++) order[k] = k;
+  // TabWeight sorts by decreasing weight with qsort (GeneralTools.cpp:277-280; ties are unordered there, by index here)
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return m.w[a] > m.w[b]; });
+  std::vector<char> keep(C, 0);
+  for (size_t i = 0; i < nbTop; i++) keep[order[i]] = 1;
+  MixtureGD out;
+  out.id = m.id;
+  out.resize((int)nbTop, m.D);
+  size_t o = 0;
+  double tot = 0.0;
+  for (size_t k = 0; k < C; k++)
+    if (keep[k]) {
+      out.w[o] = m.w[k];
+      tot += m.w[k];
+      std::copy(m.mean.begin() + k * D, m.mean.begin() + (k + 1) * D, out.mean.begin() + o * D);
+      std::copy(m.cov.begin() + k * D, m.cov.begin() + (k + 1) * D, out.cov.begin() + o * D);
+      o++;
+    }
+  for (size_t k = 0; k < nbTop; k++) out.w[k] /= tot;
+  out.computeAll();
+  m = out;
 }
 
 double setItParameter(double begin, double end, int nbIt, int it) {
@@ -166,10 +229,12 @@ void trainModel(const Config &c, const std::vector<TrainStream> &streams, const 
   const long minLen = c.getLong("baggedMinimalLength", 3), maxLen = c.getLong("baggedMaximalLength", 7);
   const long initRand = c.getLong("initRand", 0);
   const bool verbose = c.getBool("verbose", false);
-  Gmm g(world);
+  std::unique_ptr<Gmm> gp(new Gmm(world));
   EmAcc acc;
   const Shard &sh = Shard::get();
+  const long initialDistribCount = world.C;
   for (long it = 0; it < cfg.nbTrainIt; it++) {
+    Gmm &g = *gp;
     const double flooring = setItParameter(cfg.initVarianceFlooring, cfg.finalVarianceFlooring, (int)cfg.nbTrainIt, (int)it);
     const double ceiling = setItParameter(cfg.initVarianceCeiling, cfg.finalVarianceCeiling, (int)cfg.nbTrainIt, (int)it);
     unsigned long nbTotalFrame = 0;  // :1054 (truncated per stream like the reference)
@@ -220,11 +285,30 @@ void trainModel(const Config &c, const std::vector<TrainStream> &streams, const 
     // *world = emAcc.getEM(); varianceControl(world, flooring, ceiling, globalCov)  (:1076-1077)
     LIA_CHECK(lr_gmm_em_update(g.h(), acc.occ.data(), acc.m1.data(), acc.m2.data(), flooring, ceiling,
                                globalCov.data()));
+    if (cfg.componentReduction || cfg.normalizeModel) {  // :1078-1098, on the host: O(C D) between two EM passes
+      g.get(world);
+      bool rebuilt = false;
+      if (cfg.componentReduction) {
+        const double diff = (double)(initialDistribCount - cfg.targetDistribCount) / (double)cfg.nbTrainIt;
+        long nbTop = initialDistribCount - (long)((double)(it + 1) * diff);
+        if (it == cfg.nbTrainIt - 1) nbTop = cfg.targetDistribCount;
+        if (nbTop < 1) LIA_THROW("componentReduction: targetMixtureDistribCount must be >= 1");
+        if (nbTop < world.C) {
+          reduceToTopWeights(world, (size_t)nbTop);
+          rebuilt = true;
+        }
+      }
+      if (cfg.normalizeModel) normalizeMixture(world, cfg.normalizeModelNbIt, cfg.normalizeModelMeanOnly);
+      if (rebuilt)
+        gp.reset(new Gmm(world));  // the device model has a fixed number of components
+      else
+        g.set(world);
+    }
     if (verbose)
       std::cout << "ML (partial) estimate it[" << it << "] (take care, it corresponds to the previous it,0 means init likelihood) = "
                 << (acc.n > 0 ? llk / acc.n : 0.0) << std::endl;
   }
-  g.get(world);
+  gp->get(world);
 }
 
 void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs,
@@ -244,6 +328,11 @@ MAPCfg::MAPCfg(const Config &c) {
   if (weight) r[2] = c.getDouble("MAPRegFactorWeight");
   nbTrainIt = c.getLong("nbTrainIt", 1);
   baggedFrameProbability = c.getDouble("baggedFrameProbability", 1.0);
+  normalizeModel = c.getBool("normalizeModel", false);
+  if (normalizeModel) {
+    normalizeModelMeanOnly = c.getBool("normalizeModelMeanOnly", false);
+    if (normalizeModelMeanOnly) normalizeModelNbIt = c.getLong("normalizeModelNbIt");
+  }
 }
 
 void computeMAPOccDep(const MixtureGD &w, MixtureGD &client, const MAPCfg &cfg, double frameCount) {
@@ -293,6 +382,7 @@ void adaptModel(const Config &c, const FeatureServer &fs, const SegCluster &segs
     LIA_CHECK(lr_gmm_em_update(g.h(), acc.occ.data(), acc.m1.data(), acc.m2.data(), 0.0, 0.0, nullptr));
     g.get(client);
     computeMAPOccDep(apriori, client, cfg, acc.n);
+    if (cfg.normalizeModel) normalizeMixture(client, cfg.normalizeModelNbIt, cfg.normalizeModelMeanOnly);  // :898
     g.set(client);
   }
 }

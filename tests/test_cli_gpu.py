@@ -122,6 +122,68 @@ def test_train_world_cli(world, oracle):
     assert np.abs(cov - g.cov).max() < 2e-3 * np.abs(g.cov).max()
 
 
+def test_train_world_reduction_and_normalize_cli(world, oracle):
+    """componentReduction / targetMixtureDistribCount and normalizeModel of trainModelStream (TrainTools.cpp:1078-1098):
+    after getEM + varianceControl the heaviest nbTop components survive (nbTop shrinks linearly to the target, weights
+    renormalised), then the mixture is re-expressed relative to its moment-matched single Gaussian
+    (normalizeMixture :287-315 with the N(0, 1) target)."""
+    d = world["dir"]
+    start = synth.perturb_ubm(world["w"], world["mean"], world["cov"], seed=81, frac=1.0, scale=0.4)
+    lf.write_raw_gmm(d / "start_r.gmm", *start)
+    lf.write_lines(d / "train_r.lst", [[f"utt{i}"] for i in range(6)])
+    X = np.ascontiguousarray(np.concatenate(
+        [world["utts"][f"utt{i}"][_selected(f"utt{i}", world["utts"][f"utt{i}"])] for i in range(6)]))
+    _, gcov = oracle.mean_cov(X)
+    C0, target, nb_it = world["C"], 20, 3
+
+    def reference(reduce, normalize, mean_only=False, norm_it=1):
+        g = oracle.gmm(*start)
+        for it in range(nb_it):
+            fl = oracle.set_it_parameter(0.4, 0.2, nb_it, it)
+            ce = oracle.set_it_parameter(8.0, 6.0, nb_it, it)
+            _, _, occ, m1, m2 = oracle.em_accumulate(g, X)
+            wn, mn, cn = oracle.em_get(g, occ, m1, m2)
+            cn, _, _ = oracle.variance_control(cn, fl, ce, gcov)
+            if reduce:
+                nb_top = C0 - int((it + 1) * ((C0 - target) / nb_it))
+                if it == nb_it - 1:
+                    nb_top = target
+                if nb_top < len(wn):
+                    keep = np.sort(np.argsort(-wn, kind="stable")[:nb_top])
+                    wn, mn, cn = wn[keep] / wn[keep].sum(), mn[keep], cn[keep]
+            if normalize:
+                for _ in range(norm_it):
+                    gm = (wn[:, None] * mn).sum(0) / wn.sum()
+                    gc = (wn[:, None] * (cn + mn ** 2)).sum(0) / wn.sum() - gm ** 2
+                    mn = (mn - gm) / np.sqrt(gc)
+                    if not mean_only:
+                        cn = cn / gc
+            g = oracle.gmm(wn, mn, cn)
+        return g
+
+    base = dict(**world["common"], inputFeatureFilename=str(d / "train_r.lst"), inputWorldFilename="start_r",
+                nbTrainIt=nb_it, baggedFrameProbability=1.0, initVarianceFlooring=0.4, finalVarianceFlooring=0.2,
+                initVarianceCeiling=8.0, finalVarianceCeiling=6.0)
+    cases = [("red", dict(componentReduction="true", targetMixtureDistribCount=target), (True, False)),
+             ("norm", dict(normalizeModel="true"), (False, True)),
+             ("both", dict(componentReduction="true", targetMixtureDistribCount=target, normalizeModel="true",
+                           normalizeModelMeanOnly="true", normalizeModelNbIt=2), (True, True, True, 2))]
+    for name, extra, ref_args in cases:
+        lf.write_cfg(d / f"tw_{name}.cfg", **base, outputWorldFilename=f"trained_{name}", **extra)
+        _run("TrainWorld", d / f"tw_{name}.cfg")
+        w, mean, cov = lf.read_raw_gmm(d / f"trained_{name}.gmm")
+        g = reference(*ref_args)
+        assert len(w) == len(g.w) == (target if ref_args[0] else C0)
+        assert abs(w.sum() - 1.0) < 1e-9
+        assert np.allclose(w, g.w, rtol=1e-3, atol=1e-6)
+        assert np.abs(mean - g.mean).max() < 1e-3 * np.abs(g.mean).max()
+        assert np.abs(cov - g.cov).max() < 2e-3 * np.abs(g.cov).max()
+        if ref_args[1] and not (len(ref_args) > 2 and ref_args[2]):
+            # the normalised mixture has zero mean and unit variance as a whole
+            assert np.abs((w[:, None] * mean).sum(0)).max() < 1e-9
+            assert np.abs((w[:, None] * (cov + mean ** 2)).sum(0) - 1.0).max() < 1e-9
+
+
 def test_train_world_multi_stream_cli(world, oracle):
     """inputStreamList / weightStreamList (TrainWorld.cpp:120-141, trainModelStream TrainTools.cpp:1030-1110).
     Weights (1, 0) make the bagging deterministic: stream A is taken whole (probability exactly 1), stream B
