@@ -365,8 +365,22 @@ constexpr size_t kCholFusedSmem = (kNB * kBgLd + kNB * (kNB + 1) + kNB) * sizeof
 // acc += A_tile B_tile^T over K (A(m, k) at A[k lda + m], B(n, k) at B[k ldb + n]; rows >= mv / nv are zero).
 // Two shared-memory slab buffers (buf: [2][A | B][16][72] doubles) and ONE barrier per 16-deep slab: the next
 // slab is fetched into registers before the current one is multiplied and stored into the other buffer after.
+// `live` (bit 4 x + y): the 8 x 8 sub-tiles of this warp that are needed at all -- rows below mv, columns below nv
+// and, on a diagonal tile, not strictly above the diagonal; the others are skipped (a 400-row matrix ends in a
+// 16-row block whose tiles would otherwise cost as much as full ones)
+__device__ __forceinline__ unsigned chol_live_mask(int wm, int wn, int mv, int nv, bool diag) {
+  unsigned live = 0;
+#pragma unroll
+  for (int x = 0; x < 2; x++)
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+      if (wm + 8 * x < mv && wn + 8 * y < nv && !(diag && wn + 8 * y >= wm + 8 * x + 8)) live |= 1u << (4 * x + y);
+  return live;
+}
+
 __device__ __forceinline__ void chol_tile_mma(double (&acc)[2][4][2], const double *A, int lda, int mv,
-                                              const double *B, int ldb, int nv, int K, double *buf) {
+                                              const double *B, int ldb, int nv, int K, double *buf,
+                                              unsigned live = 0xFFu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
   const int fr = lane >> 2, fk = lane & 3;
@@ -398,17 +412,33 @@ __device__ __forceinline__ void chol_tile_mma(double (&acc)[2][4][2], const doub
     const bool more = k0 + kBgSlab < K;
     if (more) fetch(k0 + kBgSlab);
     const double *As = buf + which * 2 * kHalf, *Bs = As + kHalf;
+    if (live == 0xFFu) {
 #pragma unroll
-    for (int kk = 0; kk < kBgSlab; kk += 4) {
-      double a[2], b[4];
+      for (int kk = 0; kk < kBgSlab; kk += 4) {
+        double a[2], b[4];
 #pragma unroll
-      for (int x = 0; x < 2; x++) a[x] = As[(kk + fk) * kBgLd + wm + 8 * x + fr];
+        for (int x = 0; x < 2; x++) a[x] = As[(kk + fk) * kBgLd + wm + 8 * x + fr];
 #pragma unroll
-      for (int y = 0; y < 4; y++) b[y] = Bs[(kk + fk) * kBgLd + wn + 8 * y + fr];
+        for (int y = 0; y < 4; y++) b[y] = Bs[(kk + fk) * kBgLd + wn + 8 * y + fr];
 #pragma unroll
-      for (int x = 0; x < 2; x++)
+        for (int x = 0; x < 2; x++)
 #pragma unroll
-        for (int y = 0; y < 4; y++) dmma_8x8x4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+          for (int y = 0; y < 4; y++) dmma_8x8x4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+      }
+    } else if (live) {
+#pragma unroll
+      for (int kk = 0; kk < kBgSlab; kk += 4) {
+        double a[2], b[4];
+#pragma unroll
+        for (int x = 0; x < 2; x++) a[x] = As[(kk + fk) * kBgLd + wm + 8 * x + fr];
+#pragma unroll
+        for (int y = 0; y < 4; y++) b[y] = Bs[(kk + fk) * kBgLd + wn + 8 * y + fr];
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+          for (int y = 0; y < 4; y++)
+            if (live >> (4 * x + y) & 1) dmma_8x8x4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+      }
     }
     if (more) store(which ^ 1);
     __syncthreads();
@@ -440,7 +470,8 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
     for (int m0 = k0; m0 < n; m0 += kNB) {
       const int mv = min(kNB, n - m0);
       double acc[2][4][2] = {};
-      chol_tile_mma(acc, L + m0, n, mv, L + k0, n, nb, k0, slabs);
+      const unsigned live = chol_live_mask(wm, wn, mv, nb, m0 == k0);
+      chol_tile_mma(acc, L + m0, n, mv, L + k0, n, nb, k0, slabs, live);
       // P = A[tile, k] - acc, in fragment layout: (row, col) = (wm + 8x + fr, wn + 8y + 2fk + z)
 #pragma unroll
       for (int x = 0; x < 2; x++)
@@ -599,7 +630,8 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
 #pragma unroll
           for (int x = 0; x < 2; x++)
 #pragma unroll
-            for (int y = 0; y < 4; y++) dmma_8x8x4(out[x][y][0], out[x][y][1], a[x], b[y]);
+            for (int y = 0; y < 4; y++)  // X is lower triangular: k blocks past the column block contribute zeros
+              if ((live >> (4 * x + y) & 1) && kk < wn + 8 * y + 8) dmma_8x8x4(out[x][y][0], out[x][y][1], a[x], b[y]);
         }
 #pragma unroll
         for (int x = 0; x < 2; x++)
