@@ -378,56 +378,57 @@ __device__ __forceinline__ unsigned chol_live_mask(int wm, int wn, int mv, int n
   return live;
 }
 
+// 8-byte asynchronous copy global -> shared; !valid copies nothing and zero-fills (src-size 0)
+__device__ __forceinline__ void cp_async_f64(double *dst_smem, const double *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// acc += A^T B over K rows: A[k][0 .. mv), B[k][0 .. nv) (leading dimensions lda / ldb), the K range streamed through
+// a ring of kCsStages shared-memory slabs of kCsSlab rows filled by cp.async (no register staging): the copies of
+// three slabs are in flight while one is multiplied, one barrier per slab.  The ring occupies exactly the
+// 64 x 72 doubles of Ps.  Ends with a barrier: the caller may reuse the memory.
+constexpr int kCsSlab = 8, kCsStages = 4;
+static_assert(kCsStages * 2 * kCsSlab * kBgLd == kNB * kBgLd, "slab ring == Ps");
 __device__ __forceinline__ void chol_tile_mma(double (&acc)[2][4][2], const double *A, int lda, int mv,
                                               const double *B, int ldb, int nv, int K, double *buf,
                                               unsigned live = 0xFFu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
   const int fr = lane >> 2, fk = lane & 3;
-  const int lk = threadIdx.x >> 4, l4 = (threadIdx.x & 15) * 4;
-  constexpr int kHalf = kBgSlab * kBgLd;  // doubles per operand slab
+  constexpr int kHalf = kCsSlab * kBgLd;  // doubles per operand slab
   if (K <= 0) return;
-  double ra[4], rb[4];
-  auto fetch = [&](int k0) {
-    const int k = k0 + lk;
+  const int nslab = (K + kCsSlab - 1) / kCsSlab;
+  // slab s -> stage s % kCsStages; 2 operands x kCsSlab rows x 64 columns = 4 elements per thread
+  auto issue = [&](int s) {
+    if (s < nslab) {
+      double *As = buf + (s % kCsStages) * 2 * kHalf;
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      ra[e] = (k < K && l4 + e < mv) ? A[(size_t)k * lda + l4 + e] : 0.0;
-      rb[e] = (k < K && l4 + e < nv) ? B[(size_t)k * ldb + l4 + e] : 0.0;
-    }
-  };
-  auto store = [&](int which) {
-    double *As = buf + which * 2 * kHalf, *Bs = As + kHalf;
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      As[lk * kBgLd + l4 + e] = ra[e];
-      Bs[lk * kBgLd + l4 + e] = rb[e];
-    }
-  };
-  fetch(0);
-  store(0);
-  __syncthreads();
-  int which = 0;
-  for (int k0 = 0; k0 < K; k0 += kBgSlab, which ^= 1) {
-    const bool more = k0 + kBgSlab < K;
-    if (more) fetch(k0 + kBgSlab);
-    const double *As = buf + which * 2 * kHalf, *Bs = As + kHalf;
-    if (live == 0xFFu) {
-#pragma unroll
-      for (int kk = 0; kk < kBgSlab; kk += 4) {
-        double a[2], b[4];
-#pragma unroll
-        for (int x = 0; x < 2; x++) a[x] = As[(kk + fk) * kBgLd + wm + 8 * x + fr];
-#pragma unroll
-        for (int y = 0; y < 4; y++) b[y] = Bs[(kk + fk) * kBgLd + wn + 8 * y + fr];
-#pragma unroll
-        for (int x = 0; x < 2; x++)
-#pragma unroll
-          for (int y = 0; y < 4; y++) dmma_8x8x4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+      for (int j = 0; j < 2 * kCsSlab * 64 / 256; j++) {
+        const int idx = threadIdx.x + 256 * j;
+        const int op = idx / (kCsSlab * 64), rem = idx % (kCsSlab * 64);
+        const int kr = rem >> 6, c = rem & 63, k = s * kCsSlab + kr;
+        const bool ok = k < K && c < (op ? nv : mv);
+        const double *src = op ? B + (size_t)k * ldb + c : A + (size_t)k * lda + c;
+        cp_async_f64(As + op * kHalf + kr * kBgLd + c, ok ? src : A, ok);
       }
-    } else if (live) {
+    }
+    cp_async_commit();  // (empty groups keep the wait count uniform)
+  };
 #pragma unroll
-      for (int kk = 0; kk < kBgSlab; kk += 4) {
+  for (int s = 0; s < kCsStages - 1; s++) issue(s);
+  for (int s = 0; s < nslab; s++) {
+    cp_async_wait<kCsStages - 2>();  // slab s has landed (this thread's copies)
+    __syncthreads();                 // ... everyone's, and stage (s - 1) % kCsStages is free
+    issue(s + kCsStages - 1);
+    const double *As = buf + (s % kCsStages) * 2 * kHalf, *Bs = As + kHalf;
+    if (live) {
+#pragma unroll
+      for (int kk = 0; kk < kCsSlab; kk += 4) {
         double a[2], b[4];
 #pragma unroll
         for (int x = 0; x < 2; x++) a[x] = As[(kk + fk) * kBgLd + wm + 8 * x + fr];
@@ -440,9 +441,9 @@ __device__ __forceinline__ void chol_tile_mma(double (&acc)[2][4][2], const doub
             if (live >> (4 * x + y) & 1) dmma_8x8x4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
       }
     }
-    if (more) store(which ^ 1);
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();
 }
 
 // packed != nullptr: the input matrices are PACKED lower triangles (column j holds rows j..n-1) with
@@ -450,9 +451,19 @@ __device__ __forceinline__ void chol_tile_mma(double (&acc)[2][4][2], const doub
 // the factor is still written to the full column-major Lall.
 __global__ void __launch_bounds__(256, 3)
 k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ packed, double diag_add,
-             double *__restrict__ invD, int nblk, int *__restrict__ bad) {
+             double *__restrict__ invD, int nblk, int *__restrict__ bad, unsigned long long *prof) {
   extern __shared__ double csm[];
-  double *slabs = csm;  // [2 buffers][A | B][16][72]: exactly the 64 x 72 doubles of Ps
+  // phase clocks of thread 0, summed over the grid (LR_CHOL_PROF=1; prof == nullptr otherwise)
+  long long tlast = prof ? clock64() : 0;
+#define CH_T(i)                                                    \
+  do {                                                             \
+    if (prof && threadIdx.x == 0) {                                \
+      const long long t_ = clock64();                              \
+      atomicAdd(prof + (i), (unsigned long long)(t_ - tlast));     \
+      tlast = t_;                                                  \
+    }                                                              \
+  } while (0)
+  double *slabs = csm;  // cp.async ring of chol_tile_mma: exactly the 64 x 72 doubles of Ps
   double (*Ps)[kBgLd] = reinterpret_cast<double (*)[kBgLd]>(csm);
   double (*Ls)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(csm + kNB * kBgLd);
   double *rdiag = csm + kNB * kBgLd + kNB * (kNB + 1);
@@ -471,7 +482,30 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
       const int mv = min(kNB, n - m0);
       double acc[2][4][2] = {};
       const unsigned live = chol_live_mask(wm, wn, mv, nb, m0 == k0);
+      // the tile of the INPUT matrix this update is subtracted from: element (x, y, z) of the fragment layout.
+      // Its 16 addresses are prefetched into L2 before the update loop and loaded as one batch after it
+      // (a clamped, always-valid address + a select, no branch between the loads: one memory latency, not 16).
+      const double *in_base = packed ? packed + (size_t)mat * rp : L;
+      auto in_off = [&](int x, int y, int z) -> long long {  // < 0: outside the tile / above the diagonal
+        const int r = wm + 8 * x + fr, c = wn + 8 * y + 2 * fk + z;
+        const int row = m0 + r, col = k0 + c;
+        if (r >= mv || c >= nb || (packed && row < col)) return -1;
+        return packed ? (long long)(packed_off(n, col) + (size_t)(row - col)) : (long long)col * n + row;
+      };
+      if (k0 > 0) {
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+          for (int y = 0; y < 4; y++) {
+#pragma unroll
+            for (int z = 0; z < 2; z++) {  // z = 1 is the next column: another 32-byte sector
+              const long long o = in_off(x, y, z);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(in_base + (o < 0 ? 0 : o)));
+            }
+          }
+      }
       chol_tile_mma(acc, L + m0, n, mv, L + k0, n, nb, k0, slabs, live);
+      CH_T(0);
       // P = A[tile, k] - acc, in fragment layout: (row, col) = (wm + 8x + fr, wn + 8y + 2fk + z)
 #pragma unroll
       for (int x = 0; x < 2; x++)
@@ -479,16 +513,12 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
         for (int y = 0; y < 4; y++)
 #pragma unroll
           for (int z = 0; z < 2; z++) {
-            const int r = wm + 8 * x + fr, c = wn + 8 * y + 2 * fk + z;
-            double a = 0.0;
-            if (r < mv && c < nb) {
-              const int row = m0 + r, col = k0 + c;
-              if (!packed) a = L[(size_t)col * n + row];
-              else if (row >= col)
-                a = packed[(size_t)mat * rp + packed_off(n, col) + (row - col)] + (row == col ? diag_add : 0.0);
-            }
-            acc[x][y][z] = a - acc[x][y][z];
+            const long long o = in_off(x, y, z);
+            const double a = in_base[o < 0 ? 0 : o];
+            const bool dg = packed && m0 + wm + 8 * x + fr == k0 + wn + 8 * y + 2 * fk + z;
+            acc[x][y][z] = (o < 0 ? 0.0 : a + (dg ? diag_add : 0.0)) - acc[x][y][z];
           }
+      CH_T(1);
       if (m0 == k0) {
         // ---- diagonal block: factor + inverse in shared memory
 #pragma unroll
@@ -508,42 +538,60 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
         // warp (barriers = __syncwarp) instead of 64 columns of the whole CTA; everything else is
         // element-parallel over the 256 threads.  X[i][j] (i >= j) lives at Ls[j][i + 1].
         constexpr int kSB = 16;
+        CH_T(2);
         for (int s0 = 0; s0 < kNB; s0 += kSB) {
           if (warp == 0) {
             const int rr = lane >> 1, qq = lane & 1, r = s0 + rr;
             // (a) factor the 16 x 16 diagonal sub-block
+            // left-looking: column cc of row r is A[r][c] - sum_{kk < cc} L[r][kk] L[c][kk] -- independent
+            // shared-memory loads feeding one FMA chain per lane (the right-looking form it replaces was a
+            // read-modify-write of shared memory per term), the two lanes of a row split the sum
             for (int cc = 0; cc < kSB; cc++) {
               const int c = s0 + cc;
-              double d = Ls[c][c];
+              // fixed trip count + predication: the 16 loads issue back to back, then two FMA chains of four
+              double v = 0.0, v2 = 0.0;
+#pragma unroll
+              for (int i = 0; i < kSB / 2; i += 2) {
+                const int ka = qq + 2 * i, kb = ka + 2;
+                const bool oa = rr >= cc && ka < cc, ob = rr >= cc && kb < cc;
+                const double la = Ls[r][s0 + (oa ? ka : 0)], pa = Ls[c][s0 + (oa ? ka : 0)];
+                const double lb = Ls[r][s0 + (ob ? kb : 0)], pb = Ls[c][s0 + (ob ? kb : 0)];
+                v = fma(oa ? -la : 0.0, pa, v);
+                v2 = fma(ob ? -lb : 0.0, pb, v2);
+              }
+              v += v2;
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              if (rr >= cc) v += Ls[r][c];
+              double d = __shfl_sync(0xffffffffu, v, 2 * cc);  // the pivot: row cc
               if (!(d > 0.0)) {
                 fail_flag = 1;
                 d = 1.0;
               }
               const double rs = rsqrt(d);
-              const double ljc = rr > cc ? Ls[r][c] * rs : 0.0;
-              __syncwarp();
-              if (qq == 0) {
-                if (rr == cc) Ls[c][c] = d * rs;
-                else if (rr > cc) Ls[r][c] = ljc;
-              }
-              __syncwarp();
-              if (rr > cc)
-                for (int kk = cc + 1 + qq; kk <= rr; kk += 2) Ls[r][s0 + kk] = fma(-ljc, Ls[s0 + kk][c], Ls[r][s0 + kk]);
+              if (qq == 0 && rr >= cc) Ls[r][c] = rr == cc ? d * rs : v * rs;
+              if (lane == 2 * cc) rdiag[c] = rs;  // 1 / L[c][c]
               __syncwarp();
             }
             // ... and its inverse: column rr by the lane pair (rr, qq)
-            if (qq == 0) rdiag[r] = 1.0 / Ls[r][r];
-            __syncwarp();
             for (int ii = 0; ii < kSB; ii++) {
-              double v = 0.0;
-              if (ii > rr)
-                for (int kk = rr + qq; kk < ii; kk += 2) v = fma(-Ls[s0 + ii][s0 + kk], Ls[r][s0 + kk + 1], v);
+              double v = 0.0, v2 = 0.0;
+#pragma unroll
+              for (int i = 0; i < kSB / 2; i += 2) {
+                const int ka = rr + qq + 2 * i, kb = ka + 2;
+                const bool oa = ka < ii, ob = kb < ii;
+                const double la = Ls[s0 + ii][s0 + (oa ? ka : 0)], xa = Ls[r][s0 + (oa ? ka : 0) + 1];
+                const double lb = Ls[s0 + ii][s0 + (ob ? kb : 0)], xb = Ls[r][s0 + (ob ? kb : 0) + 1];
+                v = fma(oa ? -la : 0.0, xa, v);
+                v2 = fma(ob ? -lb : 0.0, xb, v2);
+              }
+              v += v2;
               v += __shfl_xor_sync(0xffffffffu, v, 1);
               if (qq == 0 && ii >= rr) Ls[r][s0 + ii + 1] = (ii == rr) ? rdiag[r] : v * rdiag[s0 + ii];
               __syncwarp();
             }
           }
           __syncthreads();
+          CH_T(3);
           const int nr = kNB - s0 - kSB;  // rows below the sub-block
           if (nr > 0) {
             // (b) panel below it: L[r, s0 + cc] = sum_{k <= cc} P[r, s0 + k] X[s0 + cc][s0 + k]
@@ -577,6 +625,7 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
             }
             __syncthreads();
           }
+          CH_T(4);
         }
         for (int c = q; c < nb; c += 4)
           if (j < nb && j >= c) L[(size_t)(k0 + c) * n + k0 + j] = Ls[j][c];
@@ -605,6 +654,7 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
         }
         double *out = invD + ((size_t)mat * nblk + k) * kNB * kNB;  // column-major, ld 64: out[c 64 + r] = X[r][c]
         for (int c = q; c < kNB; c += 4) out[(size_t)c * kNB + j] = (j < nb && c < nb && j >= c) ? Ls[c][j + 1] : 0.0;
+        CH_T(5);
       } else {
         // ---- panel tile: L[tile, k] = P X^T.  P goes through shared memory as the k-major A operand
         // (Ps[c'][r]); B(n = c, k = c') = X[c][c'] = Ls[c'][c + 1] for c' <= c, zero above the diagonal
@@ -643,10 +693,13 @@ k_chol_fused(int n, double *Lall, size_t stride, const double *__restrict__ pack
               if (r < mv && c < nb) L[(size_t)(k0 + c) * n + m0 + r] = out[x][y][z];
             }
         __syncthreads();  // Ps is reused by the next tile
+        CH_T(6);
       }
     }
     __syncthreads();  // block column k is in global memory for the updates of k + 1
+    CH_T(7);
   }
+#undef CH_T
   if (threadIdx.x == 0 && fail_flag) atomicExch(bad, mat + 1);
 }
 
@@ -893,8 +946,24 @@ lr_status chol_batched(lr_tv *tv, double *Lb, int n, int nb, double *invD, const
     LR_CUDA(cudaFuncSetAttribute(k_chol_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholFusedSmem));
     attr = true;
   }
-  k_chol_fused<<<nb, 256, kCholFusedSmem, e.stream>>>(n, Lb, rr, packed, diag_add, invD, nblk, bad);
+  static const bool kProf = getenv("LR_CHOL_PROF") != nullptr;  // phase clocks of the kernel, printed per launch
+  DevBuf<unsigned long long> prof;
+  if (kProf) {
+    LR_CUDA(prof.alloc(8));
+    LR_CUDA(cudaMemsetAsync(prof.p, 0, 8 * sizeof(unsigned long long), e.stream));
+  }
+  k_chol_fused<<<nb, 256, kCholFusedSmem, e.stream>>>(n, Lb, rr, packed, diag_add, invD, nblk, bad, prof.p);
   LR_CHECK_LAUNCH();
+  if (kProf) {
+    unsigned long long hp[8];
+    LR_CUDA(cudaMemcpyAsync(hp, prof.p, sizeof(hp), cudaMemcpyDeviceToHost, e.stream));
+    LR_CUDA(cudaStreamSynchronize(e.stream));
+    static const char *name[8] = {"update MMA", "P assembly", "diag store", "diag 16-col factor+inverse (warp 0)",
+                                  "diag panel+trailing", "diag X blocks + write", "panel solve", "column sync"};
+    fprintf(stderr, "[chol_prof] n=%d matrices=%d, clk per matrix:", n, nb);
+    for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%.0f", name[i], (double)hp[i] / nb);
+    fprintf(stderr, "\n");
+  }
   int h = 0;
   LR_CUDA(cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
   LR_CUDA(cudaStreamSynchronize(e.stream));

@@ -1,6 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-O=gpurun_out/r2c35
+O=gpurun_out/r2c40
 timeout -k 10 600 python -m pytest tests/test_tv_plda_gpu.py tests/test_gemm_digits_gpu.py -x -q -m gpu 2>&1 | tail -2
 timeout -k 10 600 python scripts/tv_gemm_perf.py > $O.perf.log 2>&1; echo "perf rc=$?"
 grep -E '^(digits6)' $O.perf.log | cut -c1-330
+LR_CHOL_PROF=1 timeout -k 10 600 python scripts/tv_gemm_perf.py > /dev/null 2> $O.prof.err
+grep "n=400" $O.prof.err | tail -1 | cut -c1-400
+grep "n=600 matrices=888" $O.prof.err | tail -1 | cut -c1-400
