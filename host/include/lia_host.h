@@ -215,7 +215,7 @@ void initEngine(const Config &c);
 // ---- MAP adaptation (TrainTools.cpp:110-147, 445-489, 871-904): the "next" row TrainTarget
 struct MAPCfg {
   bool mean = false, var = false, weight = false;
-  std::string method;  // MAPOccDep
+  std::string method;  // MAPOccDep | MAPModelBased (regulation factors), MAPConst | MAPConst2 (a priori weights)
   double r[3] = {0, 0, 0};
   long nbTrainIt = 1;
   double baggedFrameProbability = 1.0;
@@ -225,6 +225,10 @@ struct MAPCfg {
 };
 // client holds the ML (EM) estimate on entry, the MAP estimate on return (computeMAPOccDep)
 void computeMAPOccDep(const MixtureGD &initModel, MixtureGD &client, const MAPCfg &cfg, double frameCount);
+void computeMAPConst(const MixtureGD &initModel, MixtureGD &client, const MAPCfg &cfg);   // TrainTools.cpp:355-382
+void computeMAPConst2(const MixtureGD &initModel, MixtureGD &client, const MAPCfg &cfg);  // :388-419
+// computeMAP (:547-559): dispatch on MAPAlgo
+void computeMAP(const MixtureGD &initModel, MixtureGD &client, const MAPCfg &cfg, double frameCount);
 void adaptModel(const Config &c, const FeatureServer &fs, const SegCluster &segs, const MixtureGD &apriori,
                 MixtureGD &client, const MAPCfg &cfg);
 

@@ -322,10 +322,17 @@ MAPCfg::MAPCfg(const Config &c) {
   var = c.getBool("varAdapt", false);
   weight = c.getBool("weightAdapt", false);
   method = c.getParam("MAPAlgo");
-  if (method != "MAPOccDep") LIA_THROW("mapAlgo[" + method + "] is not implemented by this engine (MAPOccDep only)");
-  if (mean) r[0] = c.getDouble("MAPRegFactorMean");
-  if (var) r[1] = c.getDouble("MAPRegFactorVar");
-  if (weight) r[2] = c.getDouble("MAPRegFactorWeight");
+  if (method == "MAPConst" || method == "MAPConst2") {  // a priori probability of the initial model (:113-117)
+    if (mean) r[0] = c.getDouble("MAPAlphaMean");
+    if (var) r[1] = c.getDouble("MAPAlphaVar");
+    if (weight) r[2] = c.getDouble("MAPAlphaWeight");
+  } else if (method == "MAPOccDep" || method == "MAPModelBased") {
+    if (mean) r[0] = c.getDouble("MAPRegFactorMean");
+    if (var) r[1] = c.getDouble("MAPRegFactorVar");
+    if (weight) r[2] = c.getDouble("MAPRegFactorWeight");
+  } else {
+    LIA_THROW("mapAlgo[" + method + "] is not implemented by this engine (MAPOccDep | MAPModelBased | MAPConst | MAPConst2)");
+  }
   nbTrainIt = c.getLong("nbTrainIt", 1);
   baggedFrameProbability = c.getDouble("baggedFrameProbability", 1.0);
   normalizeModel = c.getBool("normalizeModel", false);
@@ -368,6 +375,38 @@ void computeMAPOccDep(const MixtureGD &w, MixtureGD &client, const MAPCfg &cfg, 
   client = t;
 }
 
+// Direct mean-only interpolation with a constant a priori weight; the variance / weight branches are TODOs in the
+// reference (:372-379), so the result keeps the initial model's weights and variances
+void computeMAPConst(const MixtureGD &w, MixtureGD &client, const MAPCfg &cfg) {
+  MixtureGD t = w;
+  if (cfg.mean) {
+    const double alpha = cfg.r[0];
+    for (size_t e = 0; e < t.mean.size(); e++) t.mean[e] = alpha * w.mean[e] + (1 - alpha) * client.mean[e];
+  }
+  t.id = client.id;
+  client = t;
+}
+// ... the same with the component weights in the interpolation (:388-419)
+void computeMAPConst2(const MixtureGD &w, MixtureGD &client, const MAPCfg &cfg) {
+  MixtureGD t = w;
+  if (cfg.mean) {
+    const double alpha = cfg.r[0];
+    for (int k = 0; k < w.C; k++)
+      for (int i = 0; i < w.D; i++) {
+        const size_t e = (size_t)k * w.D + i;
+        t.mean[e] = (alpha * w.w[k] * w.mean[e] + (1 - alpha) * client.w[k] * client.mean[e]) /
+                    (w.w[k] * alpha + client.w[k] * (1 - alpha));
+      }
+  }
+  t.id = client.id;
+  client = t;
+}
+void computeMAP(const MixtureGD &w, MixtureGD &client, const MAPCfg &cfg, double frameCount) {
+  if (cfg.method == "MAPConst") computeMAPConst(w, client, cfg);
+  else if (cfg.method == "MAPConst2") computeMAPConst2(w, client, cfg);
+  else computeMAPOccDep(w, client, cfg, frameCount);  // MAPOccDep and MAPModelBased share the formulas (:445-489, :491-545)
+}
+
 void adaptModel(const Config &c, const FeatureServer &fs, const SegCluster &segs, const MixtureGD &apriori,
                 MixtureGD &client, const MAPCfg &cfg) {
   const long minLen = c.getLong("baggedMinimalLength", 3), maxLen = c.getLong("baggedMaximalLength", 7);
@@ -381,7 +420,7 @@ void adaptModel(const Config &c, const FeatureServer &fs, const SegCluster &segs
     // clientMixture = emAcc.getEM() on the device (no variance control), then MAP on the host (O(C D))
     LIA_CHECK(lr_gmm_em_update(g.h(), acc.occ.data(), acc.m1.data(), acc.m2.data(), 0.0, 0.0, nullptr));
     g.get(client);
-    computeMAPOccDep(apriori, client, cfg, acc.n);
+    computeMAP(apriori, client, cfg, acc.n);
     if (cfg.normalizeModel) normalizeMixture(client, cfg.normalizeModelNbIt, cfg.normalizeModelMeanOnly);  // :898
     g.set(client);
   }

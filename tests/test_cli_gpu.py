@@ -904,6 +904,29 @@ def test_train_target_cli(world, oracle):
         assert np.allclose(gw, w, rtol=1e-3, atol=1e-7)
         assert np.abs(gm - m).max() < 1e-4 * np.abs(m).max()
         assert np.allclose(gc, c, rtol=1e-9)
+    # MAPConst / MAPConst2 (TrainTools.cpp:355-419): mean-only interpolation with a constant a priori weight (with and
+    # without the component weights); weights and variances stay the world's
+    for algo in ("MAPConst", "MAPConst2"):
+        lf.write_cfg(d / f"tt_{algo}.cfg", **world["common"], targetIdList=str(d / "target.ndx"),
+                     inputWorldFilename="wld", MAPAlgo=algo, meanAdapt="true", MAPAlphaMean=0.75, nbTrainIt=2,
+                     baggedFrameProbability=1.0)
+        _run("TrainTarget", d / f"tt_{algo}.cfg", saveMixtureFileExtension=f".{algo}.gmm")
+        for cid, files in (("clientA", ["utt1", "utt2"]), ("clientB", ["utt4"])):
+            X = np.ascontiguousarray(np.concatenate([world["utts"][u][_selected(u, world["utts"][u])] for u in files]))
+            w0, m0, c0 = world["w"], world["mean"], world["cov"]
+            m = m0
+            for it in range(2):
+                g = oracle.gmm(w0, m, c0)
+                _, n, occ, m1, m2 = oracle.em_accumulate(g, X)
+                w_ml, m_ml, _ = oracle.em_get(g, occ, m1, m2)
+                if algo == "MAPConst":
+                    m = 0.75 * m0 + 0.25 * m_ml
+                else:
+                    m = (0.75 * w0[:, None] * m0 + 0.25 * w_ml[:, None] * m_ml) / (0.75 * w0 + 0.25 * w_ml)[:, None]
+            gw, gm, gc = lf.read_raw_gmm(d / f"{cid}.{algo}.gmm")
+            assert np.allclose(gw, w0, rtol=1e-12) and np.allclose(gc, c0, rtol=1e-12)
+            assert np.abs(gm - m).max() < 1e-4 * np.abs(m).max()
+            assert np.abs(gm - m0).max() > 1e-3 * np.abs(m0).max()
 
 
 def test_train_target_jfa_cli(world, oracle):
