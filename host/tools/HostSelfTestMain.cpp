@@ -26,6 +26,45 @@ int main(int argc, char **argv) {
     double dmax = 0;
     for (size_t i = 0; i < m.mean.size(); i++) dmax = std::max(dmax, std::abs(m.mean[i] - x.mean[i]) + std::abs(m.covinv[i] - x.covinv[i]));
     std::cout << "xml_roundtrip " << dmax << "\n";
+    {
+      // model surgery of the training loops (no engine call): normalizeMixture, reduceToTopWeights, the MAP variants
+      lia::MixtureGD nm = m;
+      lia::normalizeMixture(nm, 1, false);
+      double gm = 0, gv = 0;  // worst deviation of the normalised mixture's global mean / variance from N(0, 1)
+      for (int i = 0; i < nm.D; i++) {
+        double a = 0, b = 0;
+        for (int k = 0; k < nm.C; k++) {
+          a += nm.w[k] * nm.mean[(size_t)k * nm.D + i];
+          b += nm.w[k] * (nm.cov[(size_t)k * nm.D + i] + nm.mean[(size_t)k * nm.D + i] * nm.mean[(size_t)k * nm.D + i]);
+        }
+        gm = std::max(gm, std::abs(a));
+        gv = std::max(gv, std::abs(b - a * a - 1.0));
+      }
+      lia::MixtureGD mo = m;
+      lia::normalizeMixture(mo, 2, true);
+      double covSame = 0, mo0 = 0;
+      for (size_t e = 0; e < m.cov.size(); e++) covSame = std::max(covSame, std::abs(mo.cov[e] - m.cov[e]));
+      for (int k = 0; k < mo.C; k++) mo0 += mo.w[k] * mo.mean[(size_t)k * mo.D];
+      std::cout << "normalize " << gm << " " << gv << " " << covSame << " " << mo0 << "\n";
+      lia::MixtureGD rm = m;
+      lia::reduceToTopWeights(rm, 3);
+      double sw3 = 0;
+      for (double v : rm.w) sw3 += v;
+      std::cout << "reduce " << rm.C << " " << sw3 << " " << rm.w[0] << " " << rm.w[1] << " " << rm.w[2] << " " << rm.mean[0] << " "
+                << rm.cst[0] << "\n";
+      lia::Config mc = c;
+      mc.setParam("MAPAlgo", "MAPConst2");
+      mc.setParam("meanAdapt", "true");
+      mc.setParam("MAPAlphaMean", "0.75");
+      lia::MAPCfg cfg(mc);
+      lia::MixtureGD cl = m;
+      for (double &v : cl.mean) v += 1.0;
+      for (int k = 0; k < cl.C; k++) cl.w[k] = 1.0 / cl.C;
+      lia::computeMAP(m, cl, cfg, 100.0);
+      const double wk = m.w[1], ck = 1.0 / m.C;
+      const double expect = (0.75 * wk * m.mean[m.D] + 0.25 * ck * (m.mean[m.D] + 1.0)) / (0.75 * wk + 0.25 * ck);
+      std::cout << "map_const2 " << std::abs(cl.mean[m.D] - expect) << " " << std::abs(cl.w[1] - m.w[1]) << "\n";
+    }
     lia::XList ndx(c.getParam("ndxFilename"));
     std::cout << "ndx " << ndx.lines().size() << " " << ndx.allElements().size() << " " << ndx.allUniqueElements().size() << "\n";
     std::vector<std::string> files;

@@ -55,6 +55,16 @@ def test_file_formats_and_selection(built, tmp_path):
     assert math.isclose(float(g[2]), w.sum(), rel_tol=1e-12) and math.isclose(float(g[3]), mean.sum(), rel_tol=1e-12)
     assert math.isclose(float(g[4]), cov.sum(), rel_tol=1e-12) and math.isclose(float(g[5]), 1.0, rel_tol=1e-12)
     assert float(r["xml_roundtrip"][0]) < 1e-14
+    # normalizeMixture (N(0, 1) as a whole; meanOnly keeps the variances), reduceToTopWeights, computeMAPConst2
+    nz = [float(v) for v in r["normalize"]]
+    assert nz[0] < 1e-12 and nz[1] < 1e-12 and nz[2] == 0.0 and abs(nz[3]) < 1e-12
+    keep = np.sort(np.argsort(-w, kind="stable")[:3])
+    rd = r["reduce"]
+    assert int(rd[0]) == 3 and math.isclose(float(rd[1]), 1.0, rel_tol=1e-12)
+    assert np.allclose([float(v) for v in rd[2:5]], w[keep] / w[keep].sum(), rtol=1e-12)
+    assert math.isclose(float(rd[5]), mean[keep[0], 0], rel_tol=1e-12)
+    assert math.isclose(float(rd[6]), 1.0 / np.sqrt((2 * np.pi) ** 9 * np.prod(cov[keep[0]])), rel_tol=1e-10)
+    assert float(r["map_const2"][0]) < 1e-12 and float(r["map_const2"][1]) == 0.0
     assert [int(v) for v in r["ndx"]] == [2, 5, 4]
     mask = [0, 1, 2, 3, 5, 6, 7, 8, 9]
     allx = np.concatenate([feats["f0"][:, mask], feats["f1"][:, mask]])
