@@ -148,6 +148,20 @@ class Gmm {
   lr_gmm *h_ = nullptr;
 };
 
+// ---- TopGauss (TopGauss.cpp:68-200): for every selected frame of a file, the indices of the retained top components
+// (topGauss >= 1: that many; < 1: as many as it takes to exceed that share of the frame likelihood) and the weight /
+// likelihood mass outside them.  File (nbGaussianFilesDir + name, native unsigned long = u64):
+//   nt, nbgcnt, nbg[nt], idx[nbgcnt], snsw[nt], snsl[nt]
+class TopGauss {
+ public:
+  double compute(const MixtureGD &ubm, const FeatureServer &fs, const std::string &file, const Config &c);  // mean LLK
+  void write(const std::string &file, const Config &c) const;
+  void read(const std::string &file, const Config &c);
+  uint64_t nt = 0, nbgcnt = 0;
+  std::vector<uint64_t> nbg, idx;
+  std::vector<double> snsw, snsl;
+};
+
 // ---- TrainTools
 struct TrainCfg {  // TrainTools.cpp:67-93
   double initVarianceFlooring, initVarianceCeiling, finalVarianceFlooring, finalVarianceCeiling;

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <fstream>
 #include <iostream>
 #include <set>
 
@@ -314,6 +315,92 @@ void trainModel(const Config &c, const std::vector<TrainStream> &streams, const 
 void trainModel(const Config &c, const FeatureServer &fs, const SegCluster &segs,
                 const std::vector<double> &globalCov, MixtureGD &world, const TrainCfg &cfg) {
   trainModel(c, std::vector<TrainStream>{TrainStream{&fs, segs, 1.0}}, globalCov, world, cfg);
+}
+
+// ------------------------------------------------------------------ TopGauss
+double TopGauss::compute(const MixtureGD &ubm, const FeatureServer &fs, const std::string &file, const Config &c) {
+  const double topD = c.getDouble("topGauss");
+  const int K = (int)c.getLong("topDistribsCount", 10);
+  if (topD >= 1.0 && (long)topD > K) LIA_THROW("topGauss exceeds topDistribsCount");
+  const bool complete = c.getString("computeLLKWithTopDistribs", "COMPLETE") == "COMPLETE";
+  const double minLLK = c.getDouble("minLLK", -200.0), maxLLK = c.getDouble("maxLLK", 200.0);
+  SegCluster all = selectedSegments(c, fs, c.getParam("labelSelectedFrames")), sel;
+  for (const Seg &s : all)
+    if (s.source == file) sel.push_back(s);
+  nt = (uint64_t)totalFrame(sel);
+  nbg.assign(nt, 0);
+  idx.clear();
+  snsw.clear();
+  snsl.clear();
+  nbgcnt = 0;
+  if (nt == 0) return 0.0;
+  const size_t D = fs.ld();
+  std::vector<float> X((size_t)nt * D);
+  size_t t = 0;
+  for (const Seg &s : sel) {
+    const float *p = fs.data() + (fs.getFirstFeatureIndexOfASource(s.source) + (size_t)s.begin) * D;
+    std::copy(p, p + (size_t)s.length * D, X.begin() + t * D);
+    t += (size_t)s.length;
+  }
+  Gmm g(ubm, true);
+  std::vector<double> llk(nt), top((size_t)nt * K), rest(nt), restw(nt);
+  std::vector<uint32_t> ix((size_t)nt * K);
+  LIA_CHECK(lr_gmm_llk_topk(g.h(), X.data(), nt, D, K, complete ? 1 : 0, minLLK, maxLLK, llk.data(), ix.data(), top.data(),
+                            rest.data(), restw.data()));
+  double sum = 0.0;
+  for (uint64_t f = 0; f < nt; f++) {
+    sum += llk[f];
+    const double lkTot = std::exp(llk[f]);
+    uint64_t n = 0;
+    if (topD < 1.0) {
+      double val = 0.0;
+      for (int j = 0; j < K; j++) {  // :173-179
+        if (val > topD * lkTot) break;
+        val += top[f * K + j];
+        n++;
+      }
+    } else {
+      n = (uint64_t)topD;
+    }
+    nbg[f] = n;
+    nbgcnt += n;
+    double w = 1.0, l = lkTot;  // :183-193
+    for (uint64_t j = 0; j < n; j++) {
+      idx.push_back(ix[f * K + j]);
+      w -= ubm.w[ix[f * K + j]];
+      l -= top[f * K + j];
+    }
+    snsw.push_back(w);
+    snsl.push_back(l < 1e-200 ? 1e-200 : l);
+  }
+  return sum / (double)nt;
+}
+void TopGauss::write(const std::string &file, const Config &c) const {
+  const std::string name = c.getParam("nbGaussianFilesDir") + file;
+  std::ofstream f(name.c_str(), std::ios::out | std::ios::binary);
+  if (!f) LIA_THROW("Cannot find nbGaussian file " + name);
+  f.write((const char *)&nt, 8);
+  f.write((const char *)&nbgcnt, 8);
+  f.write((const char *)nbg.data(), 8 * nbg.size());
+  f.write((const char *)idx.data(), 8 * idx.size());
+  f.write((const char *)snsw.data(), 8 * snsw.size());
+  f.write((const char *)snsl.data(), 8 * snsl.size());
+}
+void TopGauss::read(const std::string &file, const Config &c) {
+  const std::string name = c.getParam("nbGaussianFilesDir") + file;
+  std::ifstream f(name.c_str(), std::ios::in | std::ios::binary);
+  if (!f) LIA_THROW("Cannot find nbGaussian file " + name);
+  f.read((char *)&nt, 8);
+  f.read((char *)&nbgcnt, 8);
+  nbg.assign(nt, 0);
+  idx.assign(nbgcnt, 0);
+  snsw.assign(nt, 0.0);
+  snsl.assign(nt, 0.0);
+  f.read((char *)nbg.data(), 8 * nt);
+  f.read((char *)idx.data(), 8 * nbgcnt);
+  f.read((char *)snsw.data(), 8 * nt);
+  f.read((char *)snsl.data(), 8 * nt);
+  if (!f) LIA_THROW("nbGaussian file " + name + " is truncated");
 }
 
 // ------------------------------------------------------------------ MAP

@@ -66,6 +66,18 @@ int main(int argc, char **argv) {
       std::cout << "map_const2 " << std::abs(cl.mean[m.D] - expect) << " " << std::abs(cl.w[1] - m.w[1]) << "\n";
     }
     lia::XList ndx(c.getParam("ndxFilename"));
+    if (c.existsParam("topGauss")) {  // needs the engine: TopGauss::compute -> write -> read for the first test file
+      lia::initEngine(c);
+      lia::FeatureServer tfs(c, {ndx.lines()[0][0]});
+      lia::TopGauss tg, back;
+      const double llk = tg.compute(m, tfs, ndx.lines()[0][0], c);
+      tg.write(ndx.lines()[0][0] + ".tg", c);
+      back.read(ndx.lines()[0][0] + ".tg", c);
+      const bool same = back.nt == tg.nt && back.nbgcnt == tg.nbgcnt && back.nbg == tg.nbg && back.idx == tg.idx &&
+                        back.snsw == tg.snsw && back.snsl == tg.snsl;
+      std::cout << "topgauss " << tg.nt << " " << tg.nbgcnt << " " << llk << " " << same << "\n";
+      return 0;
+    }
     std::cout << "ndx " << ndx.lines().size() << " " << ndx.allElements().size() << " " << ndx.allUniqueElements().size() << "\n";
     std::vector<std::string> files;
     for (auto &l : ndx.lines()) files.push_back(l[0]);

@@ -990,3 +990,42 @@ def test_train_target_jfa_cli(world, oracle):
         off = yx[:Rv] @ V + Dl * z
         _, gm, _ = lf.read_raw_gmm(d / f"{line[0]}.lfa.gmm")
         assert np.abs(gm.reshape(-1) - (mean + off)).max() < 1e-4 * np.abs(off).max()
+
+
+def test_topgauss_index_file(world, oracle):
+    """TopGauss::compute / write / read (TopGauss.cpp:68-200) through the host class (driven by HostSelfTest): per
+    selected frame the retained top components (a fixed count, or as many as exceed a share of the frame likelihood),
+    1 - sum of their weights, the likelihood outside them; the binary layout nt, nbgcnt, nbg[], idx[], snsw[], snsl[]."""
+    d, K = world["dir"], 5
+    lf.write_lines(d / "tg.ndx", [["utt2", "x"], ["utt3", "y"]])
+    lf.write_cfg(d / "tg.cfg", **world["common"], ndxFilename=str(d / "tg.ndx"), inputWorldFilename="wld",
+                 tmpPrefix=str(d / "tg_tmp"), topDistribsCount=K, computeLLKWithTopDistribs="COMPLETE",
+                 nbGaussianFilesDir=str(d) + "/")
+    X = np.ascontiguousarray(world["utts"]["utt2"][_selected("utt2", world["utts"]["utt2"])])
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    llk, idx, top_lk, _, _ = oracle.llk_determine_top(ow, X, K, True)
+    for top_d in (3, 0.9):
+        out = _run("HostSelfTest", d / "tg.cfg", topGauss=top_d)
+        r = {l.split()[0]: l.split()[1:] for l in out.strip().splitlines()}
+        nt, cnt, mean_llk, same = int(r["topgauss"][0]), int(r["topgauss"][1]), float(r["topgauss"][2]), r["topgauss"][3]
+        raw = open(d / "utt2.tg", "rb").read()
+        assert same == "1" and nt == len(X) and tuple(np.frombuffer(raw, "<u8", 2)) == (nt, cnt)
+        nbg = np.frombuffer(raw, "<u8", nt, 16)
+        fidx = np.frombuffer(raw, "<u8", cnt, 16 + 8 * nt)
+        snsw = np.frombuffer(raw, "<f8", nt, 16 + 8 * nt + 8 * cnt)
+        snsl = np.frombuffer(raw, "<f8", nt, 16 + 16 * nt + 8 * cnt)
+        assert len(raw) == 16 + 24 * nt + 8 * cnt
+        lk_tot = np.exp(llk)
+        if top_d >= 1:
+            ref_n = np.full(nt, int(top_d))
+        else:  # the count that first pushes the running sum over the share (checked before each addition, :173-179)
+            cum = np.concatenate([np.zeros((nt, 1)), np.cumsum(top_lk, axis=1)], axis=1)[:, :K]
+            ref_n = (cum <= top_d * lk_tot[:, None]).sum(1)
+        assert np.array_equal(nbg, ref_n) and cnt == ref_n.sum()
+        ref_idx = np.concatenate([idx[t, :ref_n[t]] for t in range(nt)])
+        assert np.array_equal(fidx, ref_idx)
+        ref_w = np.array([1.0 - world["w"][idx[t, :ref_n[t]]].sum() for t in range(nt)])
+        ref_l = np.maximum(np.array([lk_tot[t] - top_lk[t, :ref_n[t]].sum() for t in range(nt)]), 1e-200)
+        assert np.allclose(snsw, ref_w, rtol=1e-9, atol=1e-12)
+        assert np.allclose(snsl, ref_l, rtol=1e-6, atol=1e-9 * lk_tot.max())
+        assert abs(mean_llk - llk.mean()) < 2e-4
