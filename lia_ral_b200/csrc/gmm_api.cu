@@ -434,53 +434,67 @@ lr_status lr_jfa_bwstats(lr_gmm *g, const float *X, size_t T, size_t ldx, const 
 // weighted channel offset,  x_t -= sum_k P(k | x_t) (U x)_k,  the posteriors taken under the session model
 // (means M + U x, the world's weights and variances).  The frames x components scores come from the same
 // likelihood pass that feeds the top-K path (tcgen05 for a tensor-core-served model); this kernel is the
-// contraction of the [P x C] posteriors with the [C x D] offset: one warp per frame, the lanes over the
-// components (so each exp2 is evaluated once), 64 fp32 accumulators per lane, the offset streamed through
-// shared memory in chunks of 128 components.
-constexpr int kJfaChunk = 128, kJfaStride = 65, kJfaWarps = 8;
+// contraction of the [P x C] posteriors with the [C x D] offset (k_jfa_compensate below).
+constexpr int kJfaChunk = 64, kJfaWarps = 8, kJfaFr = 4;  // components per chunk, warps per block, frames per warp
 constexpr long kJfaBlock = 1L << 15;  // frames per likelihood pass (S is P x Cp floats)
 
+// One warp per FOUR frames, the lanes over the dimensions (d = lane, lane + 32): per chunk of 64 components the
+// block stages the offset rows, every warp turns its frames' scores into posteriors once (two exp2 per lane and
+// frame, stored [c][frame] so one 16-byte broadcast load fetches the four), then each component costs three
+// shared-memory loads for eight FMAs and nothing has to be reduced across lanes at the end.
 __global__ void __launch_bounds__(kJfaWarps * 32)
 k_jfa_compensate(int C, int Cp, int D, const float *__restrict__ S, const float *__restrict__ lse2,
                  const float *__restrict__ ux /*[Cp][64], zero padded*/, const unsigned *__restrict__ index,
                  long P, float *__restrict__ X, size_t ldx) {
-  __shared__ float su[kJfaChunk * kJfaStride];
+  __shared__ __align__(16) float su[kJfaChunk][64];
+  __shared__ __align__(16) float gs[kJfaWarps][kJfaChunk][kJfaFr];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long p = (long)blockIdx.x * kJfaWarps + warp;
-  const bool live = p < P;
-  const float l2 = live ? lse2[p] : 0.f;
-  const float *Sp = S + (size_t)(live ? p : 0) * Cp;
-  float acc[64];
+  const long p0 = ((long)blockIdx.x * kJfaWarps + warp) * kJfaFr;
+  float l2[kJfaFr];
 #pragma unroll
-  for (int d = 0; d < 64; d++) acc[d] = 0.f;
+  for (int f = 0; f < kJfaFr; f++) l2[f] = p0 + f < P ? lse2[p0 + f] : 0.f;
+  float acc[kJfaFr][2];
+#pragma unroll
+  for (int f = 0; f < kJfaFr; f++) acc[f][0] = acc[f][1] = 0.f;
   for (int c0 = 0; c0 < C; c0 += kJfaChunk) {
-    __syncthreads();
+    __syncthreads();  // the previous chunk has been consumed
     for (int i = threadIdx.x; i < kJfaChunk * 64; i += kJfaWarps * 32) {
       const int c = i >> 6, d = i & 63;
-      su[c * kJfaStride + d] = (c0 + c < C) ? ux[(size_t)(c0 + c) * 64 + d] : 0.f;
+      su[c][d] = (c0 + c < C) ? ux[(size_t)(c0 + c) * 64 + d] : 0.f;
+    }
+#pragma unroll
+    for (int f = 0; f < kJfaFr; f++) {
+      const bool live = p0 + f < P;
+      const float *Sp = S + (size_t)(live ? p0 + f : 0) * Cp + c0;
+#pragma unroll
+      for (int h = 0; h < kJfaChunk / 32; h++) {
+        const int c = 32 * h + lane;
+        gs[warp][c][f] = (live && c0 + c < C) ? exp2f(Sp[c] - l2[f]) : 0.f;
+      }
     }
     __syncthreads();
-    if (!live) continue;
-#pragma unroll
-    for (int j = 0; j < kJfaChunk / 32; j++) {
-      const int c = c0 + 32 * j + lane;
-      const float g = c < C ? exp2f(Sp[c] - l2) : 0.f;
-      const float *u = su + (32 * j + lane) * kJfaStride;
-#pragma unroll
-      for (int d = 0; d < 64; d++) acc[d] = fmaf(g, u[d], acc[d]);
+#pragma unroll 8
+    for (int c = 0; c < kJfaChunk; c++) {
+      const float4 g4 = *reinterpret_cast<const float4 *>(&gs[warp][c][0]);
+      const float u0 = su[c][lane], u1 = su[c][lane + 32];
+      acc[0][0] = fmaf(g4.x, u0, acc[0][0]);
+      acc[0][1] = fmaf(g4.x, u1, acc[0][1]);
+      acc[1][0] = fmaf(g4.y, u0, acc[1][0]);
+      acc[1][1] = fmaf(g4.y, u1, acc[1][1]);
+      acc[2][0] = fmaf(g4.z, u0, acc[2][0]);
+      acc[2][1] = fmaf(g4.z, u1, acc[2][1]);
+      acc[3][0] = fmaf(g4.w, u0, acc[3][0]);
+      acc[3][1] = fmaf(g4.w, u1, acc[3][1]);
     }
   }
-  if (!live) return;
 #pragma unroll
-  for (int d = 0; d < 64; d++) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(0xFFFFFFFFu, acc[d], o);
+  for (int f = 0; f < kJfaFr; f++) {
+    if (p0 + f >= P) continue;
+    const size_t fr = index ? index[p0 + f] : (size_t)(p0 + f);
+    float *x = X + fr * ldx;
+    if (lane < D) x[lane] -= acc[f][0];
+    if (lane + 32 < D) x[lane + 32] -= acc[f][1];
   }
-  const size_t fr = index ? index[p] : (size_t)p;
-  float *x = X + fr * ldx;
-#pragma unroll
-  for (int d = 0; d < 64; d++)
-    if ((d & 31) == lane && d < D) x[d] -= acc[d];
 }
 
 lr_status lr_jfa_normalize_features(lr_gmm *session_model, const double *ux, float *X, size_t T, size_t ldx,
@@ -537,7 +551,7 @@ lr_status lr_jfa_normalize_features(lr_gmm *session_model, const double *ux, flo
       FrameList fl{dX.p, ldx, dIdx.p + b0, P};
       st = tc ? tc_pass_lse(g, fl, d_lse, nullptr, d_S) : gmm_pass_lse(g, fl, d_lse, d_S, nullptr);
       if (st != LR_OK) return st;
-      k_jfa_compensate<<<(unsigned)((P + kJfaWarps - 1) / kJfaWarps), kJfaWarps * 32, 0, e.stream>>>(
+      k_jfa_compensate<<<(unsigned)((P + kJfaWarps * kJfaFr - 1) / (kJfaWarps * kJfaFr)), kJfaWarps * 32, 0, e.stream>>>(
           C, Cp, D, d_S, d_lse, dU.p, dIdx.p + b0, P, dX.p, ldx);
       LR_CHECK_LAUNCH();
     }
