@@ -132,6 +132,13 @@ int ComputeTest(Config &c) {
     const double minLLK = c.getDouble("minLLK", -200.0), maxLLK = c.getDouble("maxLLK", 200.0);
     const long worldDecime = c.getLong("worldDecime", 1);  // ComputeTest.cpp:111-113
     if (worldDecime < 1) LIA_THROW("worldDecime must be >= 1");
+    // windowLLR (WindowLLR, UnsupervisedTools.cpp:92-150; ComputeTest.cpp:100, 143, 165-178): a score per client for
+    // every window of windowLLRSize selected frames, shifted by windowLLRDec, next to the file / segment scores
+    const bool windowSet = c.getBool("windowLLR", false);
+    const long windowSize = windowSet ? c.getLong("windowLLRSize", 30) : 0;
+    const long windowDec = windowSet ? c.getLong("windowLLRDec", windowSize) : 0;
+    if (windowSet && (windowSize < 1 || windowDec < 1 || windowDec > windowSize)) LIA_THROW("windowLLRSize / windowLLRDec out of range");
+    if (windowSet && worldDecime != 1) LIA_THROW("windowLLR with worldDecime > 1 is not implemented by this engine");
     XList ndx(c.getParam("ndxFilename"));
     MixtureGD worldM = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
     Gmm world(worldM, true);
@@ -163,6 +170,83 @@ int ComputeTest(Config &c) {
       std::vector<lr_seg> es = toEngineSegs(fs, segs);
       const size_t nOut = segmental ? es.size() : 1;
       std::vector<double> mw(nOut), mc(clients.size() * nOut);
+      if (windowSet) {
+        // per-frame world / client log-likelihoods of the selected frames (the same DETERMINE_TOP / USE_TOP entry
+        // points), then the reference's loop replayed on them: window lines in frame order, the segment / file lines
+        // where the reference writes them
+        const size_t D = fs.ld(), nC = clients.size();
+        size_t nSel = 0;
+        for (const lr_seg &sg : es) nSel += (size_t)sg.length;
+        std::vector<float> Xs(nSel * D);
+        {
+          size_t t = 0;
+          for (const lr_seg &sg : es) {
+            std::copy(fs.data() + (size_t)sg.begin * D, fs.data() + (size_t)(sg.begin + sg.length) * D, Xs.begin() + t * D);
+            t += (size_t)sg.length;
+          }
+        }
+        std::vector<double> llkw(nSel), rest(nSel), llkc(nC * nSel);
+        std::vector<uint32_t> idx(nSel * (size_t)K);
+        LIA_CHECK(lr_gmm_llk_topk(world.h(), Xs.data(), nSel, D, K, complete ? 1 : 0, minLLK, maxLLK, llkw.data(), idx.data(),
+                                  nullptr, rest.data(), nullptr));
+        for (size_t i = 0; i < nC; i++)
+          LIA_CHECK(lr_gmm_llk_use_topk(clients[i], Xs.data(), nSel, D, K, idx.data(), rest.data(), complete ? 1 : 0, minLLK,
+                                        maxLLK, &llkc[i * nSel]));
+        // WindowLLR state (setNbClient resets it per NDX line)
+        std::vector<unsigned long> idxA((size_t)windowSize, 0);
+        std::vector<double> accLlr(nC, 0.0), llrM((size_t)windowSize * nC, 0.0);
+        long bIdx = 0, count = 0;
+        double sumW = 0.0, nAcc = 0.0;
+        std::vector<double> sumC(nC, 0.0);
+        size_t t = 0;
+        for (size_t o = 0; o < es.size(); o++) {
+          for (long f = 0; f < es[o].length; f++, t++) {
+            const unsigned long frame = (unsigned long)(es[o].begin + f);
+            sumW += llkw[t];
+            nAcc += 1.0;
+            if (count < windowSize) {  // dec(): the window is not full yet
+              count++;
+              idxA[(size_t)((bIdx + count - 1) % windowSize)] = frame;
+            } else {  // full: drop windowDec frames from its head
+              for (long w = 0; w < windowDec; w++) {
+                for (size_t i = 0; i < nC; i++) accLlr[i] -= llrM[(size_t)bIdx * nC + i];
+                bIdx = (bIdx + 1) % windowSize;
+              }
+              count -= windowDec - 1;
+              idxA[(size_t)((bIdx + count - 1) % windowSize)] = frame;
+            }
+            for (size_t i = 0; i < nC; i++) {
+              sumC[i] += llkc[i * nSel + t];
+              const double llr = llkc[i * nSel + t] - llkw[t];
+              llrM[(size_t)((bIdx + count - 1) % windowSize) * nC + i] = llr;  // accLLR()
+              accLlr[i] += llr;
+            }
+            if (count == windowSize)
+              for (size_t i = 0; i < nC; i++) {
+                const double llr = accLlr[i] / (double)windowSize;
+                outputResultLine(llr, line[i + 1], test, idxA[(size_t)bIdx] * frameLength,
+                                 idxA[(size_t)((bIdx + count - 1) % windowSize)] * frameLength, gender,
+                                 setDecision(llr, threshold), outNist);
+              }
+          }
+          if (segmental) {
+            for (size_t i = 0; i < nC; i++) {
+              const double llr = sumC[i] / nAcc - sumW / nAcc;
+              outputResultLine(llr, line[i + 1], test, es[o].begin * frameLength, (es[o].begin + es[o].length) * frameLength,
+                               gender, setDecision(llr, threshold), outNist);
+              sumC[i] = 0.0;
+            }
+            sumW = 0.0;
+            nAcc = 0.0;
+          }
+        }
+        if (!segmental)
+          for (size_t i = 0; i < nC; i++) {
+            const double llr = sumC[i] / nAcc - sumW / nAcc;
+            outputResultLine(llr, line[i + 1], test, gender, setDecision(llr, threshold), outNist);
+          }
+        continue;
+      }
       LIA_CHECK(lr_compute_test_decime(world.h(), clients.data(), (int)clients.size(), fs.data(),
                                        fs.getFeatureCount(), fs.ld(), es.data(), es.size(), K, complete ? 1 : 0,
                                        minLLK, maxLLK, segmental ? 1 : 0, (int)worldDecime, mw.data(), mc.data()));
@@ -286,6 +370,15 @@ void jfaStatsToDisk(const Config &c) {
 
 int ComputeJFAStats(Config &c) {
   try {
+    // ComputeJFAStatsMain.cpp:108-117: computeStatMode JFA (default) | ivector (ComputeTVStats :89-103)
+    const std::string mode = c.getString("computeStatMode", "JFA");
+    if (mode == "ivector") {
+      TVAcc tv(c.getParam("ndxFilename"), c);
+      tv.computeAndAccumulateTVStat(c);
+      tv.saveAccs(c);
+      return 0;
+    }
+    if (mode != "JFA") LIA_THROW("computeStatMode must be JFA or ivector");
     jfaStatsToDisk(c);
   } catch (std::exception &e) {
     std::cout << e.what() << std::endl;

@@ -1029,3 +1029,77 @@ def test_topgauss_index_file(world, oracle):
         assert np.allclose(snsw, ref_w, rtol=1e-9, atol=1e-12)
         assert np.allclose(snsl, ref_l, rtol=1e-6, atol=1e-9 * lk_tot.max())
         assert abs(mean_llk - llk.mean()) < 2e-4
+
+
+def test_compute_test_window_llr_cli(world, oracle):
+    """ComputeTest --windowLLR (WindowLLR, UnsupervisedTools.cpp:92-150; ComputeTest.cpp:100, 143, 165-178): a result
+    line per client for every window of windowLLRSize selected frames (shift windowLLRDec; the window runs across
+    the selected segments), written in frame order before the file-level lines."""
+    d, K, size, dec = world["dir"], 5, 40, 15
+    clients = {}
+    for k in range(2):
+        p = synth.perturb_ubm(world["w"], world["mean"], world["cov"], seed=170 + k, frac=0.4, scale=0.5)
+        clients[f"wspk{k}"] = p
+        lf.write_raw_gmm(d / f"wspk{k}.gmm", *p)
+    lf.write_lines(d / "win.ndx", [["utt1", "wspk0", "wspk1"], ["utt5", "wspk1"]])
+    lf.write_cfg(d / "win.cfg", **world["common"], ndxFilename=str(d / "win.ndx"), inputWorldFilename="wld",
+                 outputFilename=str(d / "win.res"), gender="F", topDistribsCount=K, computeLLKWithTopDistribs="COMPLETE",
+                 windowLLR="true", windowLLRSize=size)
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+
+    def reference(dec_):
+        ref = []
+        for line in [["utt1", "wspk0", "wspk1"], ["utt5", "wspk1"]]:
+            sel = _selected(line[0], world["utts"][line[0]])
+            X = np.ascontiguousarray(world["utts"][line[0]][sel])
+            llkw, idx, _, rest, _ = oracle.llk_determine_top(ow, X, K, True)
+            llr = np.stack([oracle.llk_use_top(oracle.gmm(*clients[c]), X, idx, rest, True) - llkw for c in line[1:]], 1)
+            # the reference's ring buffer, restated on the frame list: positions [lo, hi] of the current window
+            lo, cnt = 0, 0
+            for t in range(len(X)):
+                if cnt < size:
+                    cnt += 1
+                else:
+                    lo += dec_
+                    cnt -= dec_ - 1
+                if cnt == size:
+                    hi = lo + cnt - 1
+                    assert hi == t
+                    for i, c in enumerate(line[1:]):
+                        ref.append((c, line[0], sel[lo] * 0.01, sel[hi] * 0.01, llr[lo:hi + 1, i].sum() / size))
+            for i, c in enumerate(line[1:]):
+                ref.append((c, line[0], None, None, llr[:, i].mean()))
+        return ref
+
+    for dec_, over in ((size, {}), (dec, dict(windowLLRDec=dec))):
+        _run("ComputeTest", d / "win.cfg", **over)
+        got = [l.split() for l in open(d / "win.res")]
+        ref = reference(dec_)
+        assert len(got) == len(ref) and sum(r[2] is not None for r in ref) > 10
+        for l, r in zip(got, ref):
+            assert (l[1], l[3]) == (r[0], r[1]), (l, r)
+            if r[2] is None:
+                assert len(l) == 5 and abs(float(l[4]) - r[4]) < 2e-4
+            else:
+                assert len(l) == 7 and abs(float(l[4]) - r[2]) < 1e-6 and abs(float(l[5]) - r[3]) < 1e-6
+                assert abs(float(l[6]) - r[4]) < 2e-4, (l, r)
+
+
+def test_compute_stats_ivector_mode_cli(world, oracle):
+    """ComputeJFAStats --computeStatMode ivector (ComputeJFAStatsMain.cpp:108-117, ComputeTVStats :89-103): the TVAcc
+    statistics of every NDX line, saved under nullOrderStatSpeaker / firstOrderStatSpeaker."""
+    d, C, D = world["dir"], world["C"], world["D"]
+    ndx = [["utt0", "utt1"], ["utt3"]]
+    lf.write_lines(d / "cs.ndx", ndx)
+    lf.write_cfg(d / "cs.cfg", **world["common"], ndxFilename=str(d / "cs.ndx"), inputWorldFilename="wld",
+                 computeStatMode="ivector", nullOrderStatSpeaker="N_cs", firstOrderStatSpeaker="FX_cs",
+                 totalVariabilityNumber=4)
+    _run("ComputeJFAStats", d / "cs.cfg")
+    ow = oracle.gmm(world["w"], world["mean"], world["cov"])
+    N, F = lf.read_db(d / "N_cs.mat"), lf.read_db(d / "FX_cs.mat")
+    assert N.shape == (2, C) and F.shape == (2, C * D)
+    for row, line in enumerate(ndx):
+        X = np.ascontiguousarray(np.concatenate([world["utts"][u][_selected(u, world["utts"][u])] for u in line]))
+        n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
+        assert np.abs(N[row] - n1[0]).max() < 1e-4 * n1[0].max()
+        assert np.abs(F[row] - f1[0]).max() < 1e-4 * np.abs(f1[0]).max()
