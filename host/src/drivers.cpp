@@ -100,17 +100,37 @@ int TrainTarget(Config &c) {
     MAPCfg mapCfg(c);
     MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
     XList ids(c.getParam("targetIdList"));  // "id file1 file2 ..." per line (TrainTarget.cpp:100-130)
+    const bool initByClient = c.getBool("initByClient", false);    // EM starts from the client's existing model (:136-139)
+    const bool saveEmptyModel = c.getBool("saveEmptyModel", false);
+    Matrix channel;  // NAP: the client supervector loses its projection on the channel subspace (:96-102, 154-157)
+    const bool nap = c.existsParam("NAP");
+    if (nap) {
+      channel.load(c.getParam("NAP"), c.getString("loadMatrixFormat", "DB"));
+      if (channel.cols != (size_t)world.C * world.D) LIA_THROW("Incorrect dimension of the NAP channel matrix");
+    }
     for (auto &line : ids.lines()) {
       std::vector<std::string> files(line.begin() + 1, line.end());
       FeatureServer fs(c, files);
       SegCluster segs = selectedSegments(c, fs, label);
+      MixtureGD client = world;  // the client starts from the world model
+      if (initByClient) client = MixtureGD::loadFromConfig(line[0], c);
+      client.id = line[0];
       if (segs.empty()) {
-        std::cout << "TrainTarget: no selected frame for [" << line[0] << "]" << std::endl;
+        std::cout << " WARNING - NO DATA FOR TRAINING [" << line[0] << "]";
+        if (saveEmptyModel) {
+          std::cout << " World model is returned" << std::endl;
+          client.saveFromConfig(line[0], c);
+        }
         continue;
       }
-      MixtureGD client = world;  // the client starts from the world model
-      client.id = line[0];
       adaptModel(c, fs, segs, world, client, mapCfg);
+      if (nap) {  // computeNap (SuperVectors.cpp:128-138): v -= U'(U v) on the mean supervector
+        std::vector<double> t(channel.rows, 0.0);
+        for (size_t i = 0; i < channel.rows; i++)
+          for (size_t k = 0; k < channel.cols; k++) t[i] += channel(i, k) * client.mean[k];
+        for (size_t i = 0; i < channel.rows; i++)
+          for (size_t k = 0; k < channel.cols; k++) client.mean[k] -= channel(i, k) * t[i];
+      }
       client.saveFromConfig(line[0], c);
     }
   } catch (std::exception &e) {

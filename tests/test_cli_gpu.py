@@ -1103,3 +1103,33 @@ def test_compute_stats_ivector_mode_cli(world, oracle):
         n1, f1 = oracle.bwstats(ow, X, np.zeros(len(X), dtype=np.int32), 1)
         assert np.abs(N[row] - n1[0]).max() < 1e-4 * n1[0].max()
         assert np.abs(F[row] - f1[0]).max() < 1e-4 * np.abs(f1[0]).max()
+
+
+def test_train_target_init_by_client_and_nap_cli(world, oracle):
+    """TrainTarget options around the MAP loop (TrainTarget.cpp:96-102, 136-157): initByClient (EM starts from the
+    client's existing model, the world stays the a priori), NAP (the adapted mean supervector loses its projection on
+    the channel subspace, computeNap SuperVectors.cpp:128-138), saveEmptyModel."""
+    from oracle import np_oracle
+    d, C, D = world["dir"], world["C"], world["D"]
+    w0, m0, c0 = world["w"], world["mean"], world["cov"]
+    start = synth.perturb_ubm(w0, m0, c0, seed=601, frac=1.0, scale=0.3)
+    lf.write_raw_gmm(d / "nclA.gmm", *start)
+    Q, _ = np.linalg.qr(np.random.default_rng(602).standard_normal((C * D, 3)))
+    U = np.ascontiguousarray(Q.T)                                  # orthonormal rows [3 x C*D]
+    lf.write_db(d / "nap.mat", U)
+    lf.write_lines(d / "nt.ndx", [["nclA", "utt1", "utt2"]])
+    lf.write_cfg(d / "nt.cfg", **world["common"], targetIdList=str(d / "nt.ndx"), inputWorldFilename="wld",
+                 MAPAlgo="MAPOccDep", meanAdapt="true", MAPRegFactorMean=14.0, nbTrainIt=1, baggedFrameProbability=1.0,
+                 initByClient="true", NAP=str(d / "nap.mat"))
+    _run("TrainTarget", d / "nt.cfg", saveMixtureFileExtension=".nap.gmm")
+    X = np.ascontiguousarray(np.concatenate([world["utts"][u][_selected(u, world["utts"][u])] for u in ("utt1", "utt2")]))
+    g = oracle.gmm(*start)                                         # EM statistics under the client's own model
+    _, n, occ, m1, m2 = oracle.em_accumulate(g, X)
+    w_ml, m_ml, c_ml = oracle.em_get(g, occ, m1, m2)
+    _, m, _ = np_oracle.map_occ_dep(w0, m0, c0, w_ml, m_ml, c_ml, n, r_mean=14.0, r_weight=None)
+    v = m.reshape(-1)
+    v = v - U.T @ (U @ v)
+    gw, gm, gc = lf.read_raw_gmm(d / "nclA.nap.gmm")
+    assert np.abs(gm.reshape(-1) - v).max() < 1e-4 * np.abs(v).max()
+    assert np.abs(U @ gm.reshape(-1)).max() < 1e-9 * np.abs(v).max()      # nothing left in the channel subspace
+    assert np.allclose(gw, w0, rtol=1e-12) and np.allclose(gc, c0, rtol=1e-12)
