@@ -100,6 +100,11 @@ int TrainTarget(Config &c) {
     MAPCfg mapCfg(c);
     MixtureGD world = MixtureGD::loadFromConfig(c.getParam("inputWorldFilename"), c);
     XList ids(c.getParam("targetIdList"));  // "id file1 file2 ..." per line (TrainTarget.cpp:100-130)
+    // options of the reference this engine does not implement are refused, not ignored
+    if (c.getBool("useModelData", false)) LIA_THROW("useModelData (modelBasedadaptModel) is not implemented by this engine");
+    if (c.existsParam("mixtureServer")) LIA_THROW("mixtureServer output is not implemented by this engine");
+    if (c.getBool("outputAdaptParam", false) || c.existsParam("superVectors"))
+      LIA_THROW("outputAdaptParam / superVectors is not implemented by this engine (TrainTarget --channelCompensation JFA writes supervectors)");
     const bool initByClient = c.getBool("initByClient", false);    // EM starts from the client's existing model (:136-139)
     const bool saveEmptyModel = c.getBool("saveEmptyModel", false);
     Matrix channel;  // NAP: the client supervector loses its projection on the channel subspace (:96-102, 154-157)
