@@ -22,7 +22,8 @@ def built():
 
 
 def test_programs_exist_and_print_help(built):
-    for p in ("TrainWorld", "TrainTarget", "ComputeTest", "IvExtractor", "TotalVariability", "IvTest", "IvNorm", "PLDA"):
+    for p in ("TrainWorld", "TrainTarget", "ComputeTest", "IvExtractor", "TotalVariability", "IvTest", "IvNorm", "PLDA",
+              "ComputeJFAStats", "EigenVoice", "EigenChannel", "EstimateDMatrix"):
         out = subprocess.run([os.path.join(built, p), "--help"], capture_output=True, text=True, timeout=60)
         assert out.returncode == 0 and p in out.stdout
 
