@@ -108,3 +108,29 @@ def test_file_formats_and_selection(built, tmp_path):
                               capture_output=True, text=True, timeout=60)
         r2 = {l.split()[0]: l.split()[1:] for l in out2.stdout.strip().splitlines()}
         assert r2["features"] == r["features"] and r2["selected"] == r["selected"], (fmt, ext, out2.stdout)
+
+
+def test_unimplemented_modes_are_refused_loudly(built, tmp_path):
+    """Options of the reference this engine does not implement must be refused with a message, never silently ignored
+    (both refusals happen before any engine call, so this runs without a GPU)."""
+    w, mean, cov = synth.make_ubm(4, 5, seed=7)
+    lf.write_raw_gmm(tmp_path / "wld.gmm", w, mean, cov)
+    lf.write_lines(tmp_path / "ids", [["spk", "f0"]])
+    lf.write_lines(tmp_path / "ndx", [["f0", "spk"]])
+    common = dict(mixtureFilesPath=str(tmp_path) + "/", loadMixtureFileExtension=".gmm", loadMixtureFileFormat="RAW",
+                  inputWorldFilename="wld", labelSelectedFrames="speech", targetIdList=str(tmp_path / "ids"),
+                  ndxFilename=str(tmp_path / "ndx"), outputFilename=str(tmp_path / "out.res"), gender="F",
+                  MAPAlgo="MAPOccDep", meanAdapt="true", MAPRegFactorMean=14.0)
+    lf.write_cfg(tmp_path / "r.cfg", **common)
+    out = subprocess.run([os.path.join(built, "TrainTarget"), "--config", str(tmp_path / "r.cfg"), "--useModelData", "true"],
+                         capture_output=True, text=True, timeout=60)
+    assert "not implemented" in out.stdout and not os.path.exists(tmp_path / "spk.gmm")
+    out = subprocess.run([os.path.join(built, "TrainTarget"), "--config", str(tmp_path / "r.cfg"), "--MAPAlgo", "MLLR"],
+                         capture_output=True, text=True, timeout=60)
+    assert "not implemented" in out.stdout
+    out = subprocess.run([os.path.join(built, "ComputeTest"), "--config", str(tmp_path / "r.cfg"),
+                          "--channelCompensation", "NAP"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "not implemented" in out.stdout
+    out = subprocess.run([os.path.join(built, "EigenChannel"), "--config", str(tmp_path / "r.cfg"),
+                          "--eigenChannelMode", "XFA"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "wrong eigenChannelMode" in out.stdout
